@@ -1,0 +1,177 @@
+/*
+ * tzk.h — C-ABI of the B200-native sparse-embedding + feature-interaction engine.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one operator that the
+ * reference reaches through third-party wheels (torchrec 1.7.0 / fbgemm-gpu 1.7.0, pinned in
+ * /root/reference/requirements/runtime.txt:5,25) or plain ATen; the call site inside the reference is
+ * cited on each declaration (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.  All pointers are DEVICE pointers unless the
+ *    parameter name ends in `_host`.
+ *  - The library never allocates or frees device memory: callers pass outputs and a workspace
+ *    (`tzk_*_workspace_bytes` tells how big).
+ *  - Every call only enqueues work on `stream` (a cudaStream_t passed as void*) and returns; no host sync,
+ *    so every call is CUDA-graph capturable.
+ *  - Return 0 on success, non-zero on failure; `tzk_last_error()` returns a thread-local message.
+ *  - fp32 tables / fp32 accumulate; ids int64; lengths int32; offsets int64 (KJT layout of
+ *    tzrec/datasets/utils.py:299-342: values key-major, lengths[f*B + b]).
+ *
+ * "Feature descriptor" arrays (one entry per KJT key f, device memory, built once at module init):
+ *    feat_w_off[f]   int64  element offset of the feature's table inside the shard arena `weights`
+ *    feat_rows[f]    int64  number of rows of that (local shard of the) table
+ *    feat_dim[f]     int32  embedding dim D_f (multiple of 4 is the fast path; any D >= 1 works)
+ *    feat_col[f]     int32  first output column of the feature in the pooled row
+ *    feat_pool[f]    int32  0 = SUM, 1 = MEAN
+ *    feat_key_base[f] int64 first sort key of the feature's table (row r of the table has key base + r);
+ *                           tables sharing a physical table share the base.
+ */
+#ifndef TZK_H_
+#define TZK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TZK_ABI_VERSION 1
+
+#define TZK_POOL_SUM 0
+#define TZK_POOL_MEAN 1
+
+#define TZK_OPT_SGD 0             /* w -= lr*g                                   (App. A.10) */
+#define TZK_OPT_ADAGRAD 1         /* s += g*g ; w -= lr*g/(sqrt(s)+eps)          (EXACT_ADAGRAD) */
+#define TZK_OPT_ROWWISE_ADAGRAD 2 /* s_row += mean_d(g*g) ; w -= lr*g/(sqrt(s_row)+eps) */
+
+typedef void* tzk_stream_t; /* cudaStream_t */
+
+/* ---- misc --------------------------------------------------------------------------------------- */
+int tzk_abi_version(void);
+const char* tzk_last_error(void);
+/* number of SMs of the current device (used by callers to size persistent grids); <0 on error */
+int tzk_sm_count(void);
+
+/* ---- K3: lengths -> offsets  ([EXT] fbgemm::asynchronous_complete_cumsum, implicit in every
+ * KeyedJaggedTensor.offsets(); reached from tzrec/modules/embedding.py:930) -------------------------
+ * offsets[0] = 0, offsets[i+1] = sum(lengths[0..i]).  n may be 0. */
+size_t tzk_lengths_to_offsets_workspace_bytes(int64_t n);
+int tzk_lengths_to_offsets(const int32_t* lengths, int64_t n, int64_t* offsets, void* workspace,
+                           size_t workspace_bytes, tzk_stream_t stream);
+
+/* ---- K4: pooled gather forward  ([EXT] fbgemm TBE split_embedding_codegen_forward_unweighted; the
+ * reference call is `self.ebc(sparse_feature)` tzrec/modules/embedding.py:930) ------------------------
+ * out[b, feat_col[f] : +D_f] = pool_{l in bag(f,b)} weights[feat_w_off[f] + ids[l]*D_f : +D_f]
+ * bag(f,b) = [offsets[f*B+b], offsets[f*B+b+1]).  MEAN of an empty bag is 0.  Sequential fp32 add in
+ * list order.  Ids outside [0, feat_rows[f]) read row 0 (fbgemm bounds_check WARNING mode, App. A.9).
+ * Launch hints (host scalars, known at module init): max_dim = max_f D_f; vec_ok != 0 promises that every
+ * D_f, feat_col[f] and feat_w_off[f] is a multiple of 4 (16-B vector path). */
+int tzk_pooled_gather_fwd(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                          const int32_t* feat_dim, const int32_t* feat_col, const int32_t* feat_pool,
+                          const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B,
+                          int32_t max_dim, int32_t vec_ok, float* out, int64_t ld_out,
+                          tzk_stream_t stream);
+
+/* ---- K4-nobag: un-pooled (sequence) gather  ([EXT] TBE ..._nobag; `ec(kjt)` embedding.py:1301) ------
+ * out[l, 0:D] = weights[feat_w_off[f(l)] + ids[l]*D : +D]  for l in [0, nnz); every feature must have
+ * the same dim D (the reference builds one EmbeddingCollection per dim, embedding.py:1193-1197).
+ * f(l) is found from `offsets` (key boundaries offsets[f*B]). */
+int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                       const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t D,
+                       int64_t nnz, float* out, tzk_stream_t stream);
+
+/* ---- K5: fused backward + sparse optimizer  ([EXT] TBE split_embedding_backward_codegen_*_exact,
+ * installed by apply_optimizer_in_backward at tzrec/main.py:774-781; optimizer choice
+ * tzrec/optim/optimizer_builder.py:30-97) -------------------------------------------------------------
+ * For every table row touched by the batch: g = sum over all (bag, slot) hitting the row of
+ * grad_scale * grad_out[b, feat_col[f] : +D] (MEAN bags contribute /L), then ONE optimizer update in
+ * place.  Deterministic: contributions are ordered by a stable sort on (table,row).
+ * `state`: ADAGRAD -> same layout as `weights`; ROWWISE_ADAGRAD -> one float per key (state[key]);
+ * SGD -> ignored (may be NULL).
+ * pooled == 0 selects the un-pooled (sequence) layout: grad_out is [nnz, D] indexed by id position.
+ * total_keys = one past the largest sort key (sum of physical rows).  Requires nnz < 2^31. */
+size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys);
+int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                  const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                  const int32_t* feat_col, const int32_t* feat_pool, const int64_t* feat_key_base,
+                  const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int64_t nnz,
+                  int64_t total_keys, int32_t max_dim, int32_t vec_ok, float* weights, float* state,
+                  float lr, float eps, float grad_scale, void* workspace, size_t workspace_bytes,
+                  tzk_stream_t stream);
+
+/* ---- K1: row-wise block bucketize  ([EXT] fbgemm::block_bucketize_sparse_features, reached through
+ * DistributedModelParallel at tzrec/main.py:799; geometry App. A.7) -----------------------------------
+ * dest r = id / block[f], local id = id - r*block[f].  Outputs, laid out [W][F][B] (dest-major):
+ *   out_lengths[(r*F+f)*B + b]   number of ids of bag (f,b) that go to rank r
+ *   out_ids                       bucketed local ids, same order as out_lengths, original relative
+ *                                 order kept inside a bag (bucketize_pos = false)
+ *   out_pos (nullable)            for each output slot, the input position it came from
+ *                                 (the "unbucketize permute" for sequence features)
+ * out_offsets [W*F*B+1] is produced as a by-product (scan of out_lengths). */
+size_t tzk_bucketize_rw_workspace_bytes(int32_t F, int32_t B, int32_t W, int64_t nnz);
+int tzk_bucketize_rw(const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t W,
+                     const int64_t* feat_block, int64_t nnz, int32_t* out_lengths, int64_t* out_offsets,
+                     int64_t* out_ids, int32_t* out_pos, void* workspace, size_t workspace_bytes,
+                     tzk_stream_t stream);
+
+/* ---- K2: KJT segment permute  ([EXT] fbgemm::permute_2D_sparse_data, KeyedJaggedTensor.permute;
+ * used by the TW input-dist, App. A.5) ----------------------------------------------------------------
+ * Segment s (= key, or (rank,key)) of the output is segment perm[s] of the input; each segment has B
+ * bags.  out_offsets [S_out*B+1] must already hold the scan of the permuted lengths (use
+ * tzk_permute_lengths + tzk_lengths_to_offsets). */
+int tzk_permute_lengths(const int32_t* lengths, const int32_t* perm, int32_t S_out, int32_t B,
+                        int32_t* out_lengths, tzk_stream_t stream);
+int tzk_permute_ids(const int64_t* ids, const int64_t* in_offsets, const int64_t* out_offsets,
+                    const int32_t* perm, int32_t S_out, int32_t B, int64_t* out_ids,
+                    tzk_stream_t stream);
+
+/* ---- K6: regroup  ([EXT] fbgemm::permute_pooled_embs / KeyedTensor.regroup_as_dict, called at
+ * tzrec/modules/embedding.py:972-976; App. A.13) ------------------------------------------------------
+ * Column gather-sum into ONE destination [rows, C]:
+ *   out[row, c] = sum_{k in [col_start[c], col_start[c+1])} srcs[col_src[k]][row*src_ld[col_src[k]] + col_srccol[k]]
+ * Forward regroup: one call per feature group, every output column has exactly one contributor.
+ * Backward: destination = grad of a source KeyedTensor, contributors = the grads of every group that
+ * copied the column (a feature may sit in several groups, e.g. DeepFM `fm` and `deep`); columns nobody
+ * read get 0.  srcs / src_ld are device arrays of device pointers / leading dims. */
+int tzk_col_gather_sum(const float* const* srcs, const int64_t* src_ld, const int32_t* col_start,
+                       const int32_t* col_src, const int32_t* col_srccol, int32_t C, int64_t rows,
+                       float* out, int64_t ld_out, tzk_stream_t stream);
+
+/* ---- K7: jagged -> padded dense and back  ([EXT] fbgemm::jagged_to_padded_dense via
+ * JaggedTensor.to_padded_dense, tzrec/modules/embedding.py:1429,1480; App. A.14) ----------------------
+ * out[b, t, 0:D] = values[offsets[b]+t] for t < min(len_b, T) else 0. */
+int tzk_jagged_to_padded(const float* values, const int64_t* offsets, int32_t B, int32_t T, int32_t D,
+                         float* out, tzk_stream_t stream);
+/* backward: grad_values[offsets[b]+t] = grad_out[b,t] for t < min(len_b,T); rows beyond T get 0 */
+int tzk_padded_to_jagged(const float* grad_out, const int64_t* offsets, int32_t B, int32_t T, int32_t D,
+                         int64_t nnz, float* grad_values, tzk_stream_t stream);
+
+/* ---- A7: factorization machine  (tzrec/modules/fm.py:28-42) ------------------------------------------
+ * y[b,d] = 0.5 * ((sum_n x[b,n,d])^2 - sum_n x[b,n,d]^2);  x row b starts at x + b*ld_x, [N,D] dense. */
+int tzk_fm_fwd(const float* x, int64_t ld_x, int64_t B, int32_t N, int32_t D, float* y, int64_t ld_y,
+               tzk_stream_t stream);
+/* dx[b,n,d] = dy[b,d] * (sum_n x[b,n,d] - x[b,n,d]) */
+int tzk_fm_bwd(const float* x, int64_t ld_x, const float* dy, int64_t ld_dy, int64_t B, int32_t N,
+               int32_t D, float* dx, int64_t ld_dx, tzk_stream_t stream);
+
+/* ---- A9/A10: DLRM dot interaction  (tzrec/modules/interaction.py:80-91, concat glue
+ * tzrec/models/dlrm.py:113-131) -----------------------------------------------------------------------
+ * X_b = [dense[b] (optional, one row of D) ; sparse[b] (Ns rows of D)]  -> N = Ns + (dense != NULL)
+ * out[b, 0:P]          = strict upper triangle of X_b X_b^T, row-major (triu_indices(N,N,1)), P=N(N-1)/2
+ * out[b, P:P+D]        = dense[b]          (only if copy_dense  != 0)
+ * out[b, .. : +Ns*D]   = sparse[b]         (only if copy_sparse != 0)
+ * i.e. with both flags it emits the whole `final_mlp` input of DLRM in one pass. N <= 64, D <= 128. */
+int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const float* sparse, int64_t ld_sparse,
+                         int64_t B, int32_t Ns, int32_t D, int32_t copy_dense, int32_t copy_sparse,
+                         float* out, int64_t ld_out, tzk_stream_t stream);
+/* d_dense (nullable iff dense == NULL), d_sparse from d_out (same layout as `out`). */
+int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const float* sparse, int64_t ld_sparse,
+                         const float* d_out, int64_t ld_dout, int64_t B, int32_t Ns, int32_t D,
+                         int32_t copy_dense, int32_t copy_sparse, float* d_dense, int64_t ld_ddense,
+                         float* d_sparse, int64_t ld_dsparse, tzk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TZK_H_ */

@@ -1,0 +1,52 @@
+"""C-ABI surface: the library loads, and include/tzk.h <-> exported symbols <-> ctypes table agree."""
+import os
+import re
+import subprocess
+
+from torcheasyrec_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "tzk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(tzk_[a-z0-9_]+)\s*\(", src))
+
+
+def test_library_loads_and_reports_version():
+    handle = _lib.lib()
+    assert handle.tzk_abi_version() == 1
+    assert handle.tzk_last_error() is not None
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = _declared()
+    assert len(declared) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (tzk_[a-z0-9_]+)", out))
+    assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
+    assert exported <= declared, f"exported but not declared in tzk.h: {sorted(exported - declared)}"
+    assert declared == set(_lib.SIGNATURES), sorted(declared ^ set(_lib.SIGNATURES))
+
+
+def test_workspace_queries_need_no_gpu():
+    handle = _lib.lib()
+    assert handle.tzk_lengths_to_offsets_workspace_bytes(0) >= 8
+    assert handle.tzk_lengths_to_offsets_workspace_bytes(1 << 20) >= (1 << 20) // 4096 * 8
+    assert handle.tzk_fused_bwd_workspace_bytes(1000, 1 << 20) > 1000 * 16
+    assert handle.tzk_bucketize_rw_workspace_bytes(26, 512, 8, 26 * 512) > 0
+
+
+def test_product_has_no_cpu_fallback():
+    import pytest
+    import torch
+
+    from torcheasyrec_b200.kernels import CudaKernels, TzkError
+
+    k = CudaKernels()
+    with pytest.raises(TzkError):
+        k.lengths_to_offsets(torch.ones(4, dtype=torch.int32))
+    # and the package never imports the oracle
+    import sys
+    assert not any(m == "oracle" or m.startswith("oracle.") for m in sys.modules if "torcheasyrec" in m)

@@ -1,0 +1,290 @@
+"""GPU parity: every tzk kernel (through the C-ABI) against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact for integer / index work; <= 1e-5 relative for pooled
+embeddings, interactions and updated weights.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tzk_oracle as O
+from torcheasyrec_b200.kernels import ColPlan, build_layout
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_dense_modules.npz"))
+DEV = "cuda"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def random_kjt(rng, F, B, rows, max_len, empty_frac=0.2, fixed_len=None):
+    if fixed_len is not None:
+        lengths = np.full(F * B, fixed_len, dtype=np.int32)
+    else:
+        lengths = rng.integers(0, max_len + 1, size=F * B).astype(np.int32)
+        lengths[rng.random(F * B) < empty_frac] = 0
+    offsets = O.lengths_to_offsets(lengths)
+    parts = [rng.integers(0, rows[f], size=int(lengths[f * B:(f + 1) * B].sum())) for f in range(F)]
+    ids = np.concatenate(parts).astype(np.int64) if offsets[-1] else np.zeros(0, np.int64)
+    return ids, lengths, offsets
+
+
+def make_arena(lay, tables, feat_table):
+    arena = np.zeros(lay.arena_elems, dtype=np.float32)
+    seen = set()
+    for f, t in enumerate(feat_table):
+        if t in seen:
+            continue
+        seen.add(t)
+        arena[lay.w_off[f]:lay.w_off[f] + tables[t].size] = tables[t].ravel()
+    return arena
+
+
+def split_arena(arena, lay, tables, feat_table):
+    out = {}
+    for f, t in enumerate(feat_table):
+        out[t] = arena[lay.w_off[f]:lay.w_off[f] + tables[t].size].reshape(tables[t].shape)
+    return [out[t] for t in range(len(tables))]
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4096, 4097, 100003, 26 * 65536])
+def test_lengths_to_offsets_bit_exact(kernels, n):
+    rng = np.random.default_rng(n)
+    lengths = rng.integers(0, 9, size=n).astype(np.int32)
+    got = kernels.lengths_to_offsets(cu(lengths)).cpu().numpy()
+    np.testing.assert_array_equal(got, O.lengths_to_offsets(lengths))
+
+
+CASES = {
+    # name: (rows, dims, feat_table, B, max_len)
+    "criteo_like_L1": ([1000] * 6, [16] * 6, list(range(6)), 300, None),
+    "deepfm_mixed_dims": ([50, 50, 700, 700], [4, 4, 16, 16], [0, 1, 2, 3], 257, 5),
+    "shared_table": ([40, 900], [16, 8], [0, 1, 0, 1], 129, 4),
+    "wide_rows": ([300, 20], [128, 64], [0, 1], 65, 3),
+    "very_wide_rows": ([64], [256], [0], 33, 3),
+    "unaligned_dims": ([30, 70], [13, 6], [0, 1], 77, 4),
+    "tiny_tables_long_runs": ([3, 4, 10], [16, 16, 16], [0, 1, 2], 2000, 2),
+    "multi_hot_33": ([5000], [16], [0], 50, 33),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("pool", [O.POOL_SUM, O.POOL_MEAN])
+def test_pooled_gather_fwd(kernels, case, pool):
+    rows, dims, feat_table, B, max_len = CASES[case]
+    rng = np.random.default_rng(zlib.crc32(case.encode()) % 1000)
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    F = len(feat_table)
+    frows = [rows[t] for t in feat_table]
+    ids, lengths, offsets = random_kjt(rng, F, B, frows, max_len or 1, fixed_len=1 if max_len is None else None)
+    if len(ids) > 4:  # out-of-range ids read row 0 (A.9)
+        ids[1] = frows[0] + 5 if lengths[:B].sum() > 1 else ids[1]
+    lay = build_layout(rows, dims, feat_table, [pool] * F).to(DEV)
+    arena = cu(make_arena(lay, tables, feat_table))
+    got = kernels.pooled_gather_fwd(arena, lay, cu(ids), cu(offsets), B).cpu().numpy()
+    want = O.pooled_lookup(tables, feat_table, [pool] * F, ids, offsets, B)
+    if pool == O.POOL_SUM and (max_len is None):
+        np.testing.assert_array_equal(got, want)  # L=1: pure copy, bit exact
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-7)
+
+
+def test_pooled_gather_empty_batch_and_all_empty_bags(kernels):
+    lay = build_layout([10], [16], [0], [0]).to(DEV)
+    arena = torch.randn(lay.arena_elems, device=DEV)
+    B = 8
+    offsets = torch.zeros(B + 1, dtype=torch.int64, device=DEV)
+    out = kernels.pooled_gather_fwd(arena, lay, torch.zeros(0, dtype=torch.int64, device=DEV), offsets, B)
+    assert out.shape == (B, 16) and float(out.abs().sum()) == 0.0
+
+
+def test_seq_gather_fwd(kernels):
+    rng = np.random.default_rng(2)
+    rows, dims, feat_table, B = [500, 60, 500], [16, 16, 16], [0, 1, 2], 40
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    ids, lengths, offsets = random_kjt(rng, 3, B, rows, 20)
+    lay = build_layout(rows, dims, feat_table, [0] * 3).to(DEV)
+    arena = cu(make_arena(lay, tables, feat_table))
+    got = kernels.seq_gather_fwd(arena, lay, cu(ids), cu(offsets), B).cpu().numpy()
+    np.testing.assert_array_equal(got, O.seq_lookup(tables, feat_table, ids, offsets, B))
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("opt", [O.OPT_SGD, O.OPT_ADAGRAD, O.OPT_ROWWISE_ADAGRAD])
+@pytest.mark.parametrize("pool", [O.POOL_SUM, O.POOL_MEAN])
+def test_fused_bwd(kernels, case, opt, pool):
+    rows, dims, feat_table, B, max_len = CASES[case]
+    rng = np.random.default_rng(zlib.crc32(case.encode()) % 1000 + 17)
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    F = len(feat_table)
+    frows = [rows[t] for t in feat_table]
+    ids, lengths, offsets = random_kjt(rng, F, B, frows, max_len or 1, fixed_len=1 if max_len is None else None)
+    lay = build_layout(rows, dims, feat_table, [pool] * F).to(DEV)
+    arena = cu(make_arena(lay, tables, feat_table))
+    grad = rng.standard_normal((B, lay.total_dim)).astype(np.float32)
+    lr, eps, gs = 0.05, 1e-8, 0.5
+    if opt == O.OPT_ADAGRAD:
+        st_np = [np.abs(rng.standard_normal(t.shape)).astype(np.float32) * 0.01 for t in tables]
+        state = cu(make_arena(lay, st_np, feat_table))
+    elif opt == O.OPT_ROWWISE_ADAGRAD:
+        st_np = [np.abs(rng.standard_normal(t.shape[0])).astype(np.float32) * 0.01 for t in tables]
+        state = cu(np.concatenate(st_np))
+    else:
+        st_np, state = [None] * len(tables), None
+    two_steps = 2
+    want = [t.copy() for t in tables]
+    for _ in range(two_steps):  # second step exercises the updated state
+        kernels.fused_bwd(opt, True, cu(grad), arena, state, lay, cu(ids), cu(offsets), B, lr, eps, gs)
+        O.fused_update(opt, want, st_np, feat_table, [pool] * F, ids, offsets, B, grad, lr, eps, gs)
+    got = split_arena(arena.cpu().numpy(), lay, tables, feat_table)
+    for t in range(len(tables)):
+        np.testing.assert_allclose(got[t], want[t], rtol=1e-5, atol=1e-6, err_msg=f"table {t}")
+    if opt == O.OPT_ADAGRAD:
+        gs_ = split_arena(state.cpu().numpy(), lay, tables, feat_table)
+        for t in range(len(tables)):
+            np.testing.assert_allclose(gs_[t], st_np[t], rtol=2e-5, atol=1e-7)
+    if opt == O.OPT_ROWWISE_ADAGRAD:
+        np.testing.assert_allclose(state.cpu().numpy(), np.concatenate(st_np), rtol=2e-5, atol=1e-7)
+
+
+def test_fused_bwd_is_run_to_run_deterministic(kernels):
+    rng = np.random.default_rng(9)
+    rows, dims, feat_table, B = [3, 7, 5000], [16, 16, 16], [0, 1, 2], 4096
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    ids, lengths, offsets = random_kjt(rng, 3, B, rows, 3)
+    lay = build_layout(rows, dims, feat_table, [0] * 3).to(DEV)
+    grad = cu(rng.standard_normal((B, lay.total_dim)).astype(np.float32))
+    res = []
+    for _ in range(3):
+        arena = cu(make_arena(lay, tables, feat_table))
+        state = torch.zeros_like(arena)
+        kernels.fused_bwd(O.OPT_ADAGRAD, True, grad, arena, state, lay, cu(ids), cu(offsets), B, 0.01, 1e-8, 1.0)
+        res.append(arena.cpu().numpy())
+    np.testing.assert_array_equal(res[0], res[1])
+    np.testing.assert_array_equal(res[0], res[2])
+
+
+def test_fused_bwd_sequence_layout(kernels):
+    rng = np.random.default_rng(21)
+    rows, dims, feat_table, B = [400, 30, 400], [16, 16, 16], [0, 1, 2], 64
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    ids, lengths, offsets = random_kjt(rng, 3, B, rows, 12)
+    lay = build_layout(rows, dims, feat_table, [0] * 3).to(DEV)
+    arena = cu(make_arena(lay, tables, feat_table))
+    state = torch.zeros_like(arena)
+    grad = rng.standard_normal((len(ids), 16)).astype(np.float32)
+    kernels.fused_bwd(O.OPT_ADAGRAD, False, cu(grad), arena, state, lay, cu(ids), cu(offsets), B, 0.02, 1e-8, 1.0)
+    want = [t.copy() for t in tables]
+    st = [np.zeros_like(t) for t in tables]
+    O.fused_update(O.OPT_ADAGRAD, want, st, feat_table, [0] * 3, ids, offsets, B, grad, 0.02, 1e-8, 1.0, pooled=False)
+    got = split_arena(arena.cpu().numpy(), lay, tables, feat_table)
+    for t in range(3):
+        np.testing.assert_allclose(got[t], want[t], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("W", [1, 2, 8])
+@pytest.mark.parametrize("max_len", [None, 6])
+def test_bucketize_rw_bit_exact(kernels, W, max_len):
+    rng = np.random.default_rng(W * 10 + (max_len or 0))
+    F, B = 5, 333
+    rows = [39060, 3, 4, 100000, 17]  # hash_size % W != 0 and tables smaller than W (SURVEY §8c golden (5))
+    ids, lengths, offsets = random_kjt(rng, F, B, rows, max_len or 1, fixed_len=1 if max_len is None else None)
+    blocks = [O.rw_block_size(r, W) for r in rows]
+    ol, oo, oi, op = kernels.bucketize_rw(cu(ids), cu(offsets), F, B, W, cu(np.asarray(blocks, np.int64)), want_pos=True)
+    wl, wo, wi, wp = O.bucketize_rw(ids, offsets, F, B, W, blocks)
+    np.testing.assert_array_equal(ol.cpu().numpy(), wl)
+    np.testing.assert_array_equal(oo.cpu().numpy(), wo)
+    np.testing.assert_array_equal(oi.cpu().numpy(), wi)
+    np.testing.assert_array_equal(op.cpu().numpy(), wp)
+
+
+def test_kjt_permute_bit_exact(kernels):
+    rng = np.random.default_rng(4)
+    F, B = 7, 100
+    ids, lengths, offsets = random_kjt(rng, F, B, [1000] * F, 5)
+    perm = [3, 0, 6, 6, 1]
+    wi, wl = O.kjt_permute(ids, lengths, perm, B)
+    pl = kernels.permute_lengths(cu(lengths), cu(np.asarray(perm, np.int32)), B)
+    np.testing.assert_array_equal(pl.cpu().numpy(), wl)
+    po = kernels.lengths_to_offsets(pl)
+    pi = kernels.permute_ids(cu(ids), cu(offsets), po, cu(np.asarray(perm, np.int32)), B, len(wi))
+    np.testing.assert_array_equal(pi.cpu().numpy(), wi)
+
+
+def test_col_gather_sum_regroup_fwd_and_bwd(kernels):
+    rng = np.random.default_rng(6)
+    B = 77
+    kt = rng.standard_normal((B, 104 + 416)).astype(np.float32)   # DeepFM: 26 wide(4) + 26 deep(16)
+    dense = rng.standard_normal((B, 13)).astype(np.float32)
+    # group "deep" = 13 dense cols then the 416 emb cols ; group "fm" = the 416 emb cols
+    plan_deep = ColPlan(list(range(13 + 416 + 1)), [1] * 13 + [0] * 416, list(range(13)) + list(range(104, 520))).to(DEV)
+    got = kernels.col_gather_sum([cu(kt), cu(dense)], plan_deep, B).cpu().numpy()
+    np.testing.assert_array_equal(got, np.concatenate([dense, kt[:, 104:]], axis=1))
+    # backward into kt: wide cols <- g_wide ; emb cols <- g_fm + g_deep[:, 13:]
+    g_wide = rng.standard_normal((B, 104)).astype(np.float32)
+    g_fm = rng.standard_normal((B, 416)).astype(np.float32)
+    g_deep = rng.standard_normal((B, 429)).astype(np.float32)
+    start, src, scol = [0], [], []
+    for c in range(520):
+        if c < 104:
+            src += [0]; scol += [c]
+        else:
+            src += [1, 2]; scol += [c - 104, 13 + c - 104]
+        start.append(len(src))
+    plan_bwd = ColPlan(start, src, scol).to(DEV)
+    gk = kernels.col_gather_sum([cu(g_wide), cu(g_fm), cu(g_deep)], plan_bwd, B).cpu().numpy()
+    want = np.concatenate([g_wide, g_fm + g_deep[:, 13:]], axis=1)
+    np.testing.assert_array_equal(gk, want)
+
+
+def test_jagged_padded_round_trip(kernels):
+    rng = np.random.default_rng(8)
+    B, D = 50, 16
+    lengths = rng.integers(0, 101, size=B).astype(np.int32)
+    lengths[:3] = [0, 100, 1]
+    offsets = O.lengths_to_offsets(lengths)
+    vals = rng.standard_normal((int(offsets[-1]), D)).astype(np.float32)
+    for T in [int(lengths.max()), 10, 1]:
+        got = kernels.jagged_to_padded(cu(vals), cu(offsets), T).cpu().numpy()
+        np.testing.assert_array_equal(got, O.to_padded_dense(vals, offsets, T))
+        g = rng.standard_normal((B, T, D)).astype(np.float32)
+        back = kernels.padded_to_jagged(cu(g), cu(offsets), len(vals)).cpu().numpy()
+        np.testing.assert_array_equal(back, O.padded_to_jagged(g, offsets, len(vals)))
+
+
+@pytest.mark.parametrize("tag", ["fm_criteo", "fm_small", "fm_wide"])
+def test_fm_matches_reference_golden(kernels, tag):
+    x, y, dy, dx = (GOLD[f"{tag}_{k}"] for k in ("x", "y", "dy", "dx"))
+    B, N, D = x.shape
+    got = kernels.fm_fwd(cu(x.reshape(B, N * D)), N, D).cpu().numpy()
+    np.testing.assert_allclose(got, y, rtol=1e-5, atol=1e-5)
+    gdx = kernels.fm_bwd(cu(x.reshape(B, N * D)), cu(dy), N, D).cpu().numpy()
+    np.testing.assert_allclose(gdx.reshape(B, N, D), dx, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["ia_criteo", "ia_min", "ia_odd", "ia_wide"])
+def test_dot_interaction_matches_reference_golden(kernels, tag):
+    x, z, dz, dx = (GOLD[f"{tag}_{k}"] for k in ("x", "z", "dz", "dx"))
+    B, N, D = x.shape
+    xs = cu(x.reshape(B, N * D))
+    got = kernels.dot_interact_fwd(None, xs, N, D, False, False).cpu().numpy()
+    np.testing.assert_allclose(got, z, rtol=1e-5, atol=1e-5)
+    _, ds = kernels.dot_interact_bwd(None, xs, cu(dz), N, D, False, False)
+    np.testing.assert_allclose(ds.cpu().numpy().reshape(B, N, D), dx, rtol=1e-5, atol=2e-5)
+
+
+def test_dlrm_fused_interaction_vs_reference_golden_and_oracle(kernels):
+    sparse, all_feat = GOLD["dlrm_sparse"], GOLD["dlrm_all_feat"]
+    dense_feat = all_feat[:, 351:367]
+    got = kernels.dot_interact_fwd(cu(dense_feat), cu(sparse), 26, 16, True, True).cpu().numpy()
+    np.testing.assert_allclose(got, all_feat, rtol=1e-5, atol=1e-5)
+    rng = np.random.default_rng(1)
+    d_out = rng.standard_normal(all_feat.shape).astype(np.float32)
+    dd, ds = kernels.dot_interact_bwd(cu(dense_feat), cu(sparse), cu(d_out), 26, 16, True, True)
+    wd, ws = O.dlrm_interact_bwd(dense_feat, sparse, d_out, 26, 16)
+    np.testing.assert_allclose(dd.cpu().numpy(), wd, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(ds.cpu().numpy(), ws, rtol=1e-5, atol=2e-5)

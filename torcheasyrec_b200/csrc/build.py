@@ -1,0 +1,59 @@
+"""Builds libtzk.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+No torch dependency: plain `nvcc -shared`.  Objects are rebuilt only when a source is newer.
+"""
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["tzk_core.cu", "tzk_gather.cu", "tzk_bwd.cu", "tzk_dist.cu", "tzk_dense.cu"]
+HEADERS = ["tzk_common.cuh", os.path.join("..", "..", "include", "tzk.h")]
+LIB = os.path.join(HERE, "libtzk.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _mtime(p):
+    return os.path.getmtime(p) if os.path.exists(p) else 0.0
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    hdr_time = max(_mtime(os.path.join(HERE, h)) for h in HEADERS)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        s = os.path.join(HERE, src)
+        o = os.path.join(HERE, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _mtime(o) < max(_mtime(s), hdr_time):
+            cmd = [NVCC, *FLAGS, "-c", s, "-o", o]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+                print(" ".join(cmd), flush=True)
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"nvcc failed for {src}:\n{out}\n")
+        elif verbose and out:
+            print(out)
+    if failed:
+        raise RuntimeError("libtzk build failed")
+    if force or procs or _mtime(LIB) < max(_mtime(o) for o in objs):
+        cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs]
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

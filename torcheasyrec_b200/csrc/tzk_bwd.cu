@@ -1,0 +1,514 @@
+// tzk_bwd.cu — K5 fused segmented backward + sparse optimizer (sm_100a).
+//
+// Pipeline (all on the caller's stream, no host sync):
+//   1. linearize : key[l] = feat_key_base[f] + id[l], val[l] = bag (pooled) or l (sequence)
+//   2. stable LSD radix sort of (key,val) over ceil(log2(total_keys)) bits (CUB DeviceRadixSort — the one
+//      library primitive on this path; everything else is hand-written)
+//   3. fused run kernel: one lane group per sorted position; the group that sits on the head of a run of
+//      equal keys sums the run's gradient rows in sorted (= stable, ascending bag) order and applies ONE
+//      optimizer update to the table row in place — no dense gradient, no atomics, run-to-run
+//      deterministic.  Runs longer than kShortRun are deferred to
+//   4. long-run kernel: one CTA per long run (tiny tables / hot ids), strided partial sums per lane group
+//      + fixed-order tree in shared memory, then the update.
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "tzk_common.cuh"
+
+using namespace tzk;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kShortRun = 32;
+
+struct BwdFeat {
+  int64_t w_off;
+  int64_t rows;
+  int64_t key_base;
+  int32_t dim;
+  int32_t col;
+  int32_t pool;
+  int32_t pad;
+};
+
+struct BwdArgs {
+  const float* grad_out;
+  int64_t ld_grad;
+  const int64_t* offsets;
+  float* weights;
+  float* state;
+  float lr, eps, grad_scale;
+  int32_t F, B;
+  int32_t optimizer;
+  int32_t pooled;
+  int64_t n;
+};
+
+__device__ __forceinline__ void stage_feats(BwdFeat* fd, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                            const int64_t* feat_key_base, const int32_t* feat_dim,
+                                            const int32_t* feat_col, const int32_t* feat_pool, int F) {
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    fd[f].w_off = feat_w_off[f];
+    fd[f].rows = feat_rows[f];
+    fd[f].key_base = feat_key_base[f];
+    fd[f].dim = feat_dim[f];
+    fd[f].col = feat_col ? feat_col[f] : 0;
+    fd[f].pool = feat_pool ? feat_pool[f] : 0;
+  }
+  __syncthreads();
+}
+
+// ---- 1. linearize ------------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads)
+linearize_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
+                 const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_key_base, int F,
+                 int B, int pooled, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int64_t n_bags = (int64_t)F * B;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t bag = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bag < n_bags; bag += stride) {
+    const int f = (int)(bag / B);
+    const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
+    const int64_t base = __ldg(feat_key_base + f), rows = __ldg(feat_rows + f);
+    for (int64_t l = s; l < e; ++l) {
+      int64_t id = __ldg(ids + l);
+      if ((uint64_t)id >= (uint64_t)rows) id = 0;
+      keys[l] = (KeyT)(base + id);
+      vals[l] = pooled ? (int32_t)bag : (int32_t)l;
+    }
+  }
+}
+
+// gradient-row address + scale of one sorted entry
+struct Entry {
+  const float* g;
+  float scale;
+  int f;
+};
+
+__device__ __forceinline__ Entry entry_of(const BwdArgs& a, const BwdFeat* fd, int32_t v, int f_hint) {
+  Entry en;
+  if (a.pooled) {
+    const int f = v / a.B;
+    const int b = v - f * a.B;
+    en.f = f;
+    en.g = a.grad_out + (int64_t)b * a.ld_grad + fd[f].col;
+    en.scale = a.grad_scale;
+    if (fd[f].pool == TZK_POOL_MEAN) {
+      const int64_t L = __ldg(a.offsets + v + 1) - __ldg(a.offsets + v);
+      en.scale = a.grad_scale / (float)L;  // L >= 1 because the entry exists
+    }
+  } else {
+    en.f = f_hint;
+    en.g = a.grad_out + (int64_t)v * a.ld_grad;
+    en.scale = a.grad_scale;
+  }
+  return en;
+}
+
+template <typename KeyT>
+__device__ __forceinline__ int feat_of_key(const BwdFeat* fd, int F, KeyT key) {
+  // features sharing a table share key_base; any of them gives the right table geometry
+  int best = 0;
+  int64_t best_base = -1;
+  for (int f = 0; f < F; ++f) {
+    const int64_t kb = fd[f].key_base;
+    if (kb <= (int64_t)key && kb > best_base) { best = f; best_base = kb; }
+  }
+  return best;
+}
+
+// apply the optimizer to one float4 chunk; for row-wise Adagrad `rw_state` is the already updated row sum
+template <int VEC>
+__device__ __forceinline__ void apply_update(const BwdArgs& a, float* w, float* s, const float* g,
+                                             float rw_denom) {
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float gk = g[k];
+    if (a.optimizer == TZK_OPT_SGD) {
+      w[k] = w[k] - a.lr * gk;
+    } else if (a.optimizer == TZK_OPT_ADAGRAD) {
+      const float sk = s[k] + gk * gk;
+      s[k] = sk;
+      w[k] = w[k] - a.lr * gk / (sqrtf(sk) + a.eps);
+    } else {
+      w[k] = w[k] - a.lr * gk / rw_denom;
+    }
+  }
+}
+
+// mask of the G lanes of this thread's lane group inside its warp (groups diverge independently)
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  if (G >= 32) return 0xffffffffu;
+  const unsigned lane_in_warp = threadIdx.x & 31u;
+  return ((1u << G) - 1u) << (lane_in_warp / G * G);
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+  const unsigned m = group_mask<G>();
+#pragma unroll
+  for (int d = G / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(m, v, d, G);
+  return v;
+}
+
+// finish a run: `acc` holds this lane's chunk(s) of the summed gradient.  Only called with all G lanes
+// of the group active (needed for the row-wise shuffle).
+template <int G, int VEC, int CH>
+__device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, int64_t row, int64_t key,
+                                           float (&acc)[CH][VEC], int lane) {
+  float rw_denom = 1.f;
+  if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {
+    float ss = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = (ch * G + lane) * VEC;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (c + k < d.dim) ss += acc[ch][k] * acc[ch][k];
+    }
+    ss = group_sum<G>(ss);
+    float sr = 0.f;
+    if (lane == 0) {
+      sr = a.state[key] + ss / (float)d.dim;
+      a.state[key] = sr;
+    }
+    sr = __shfl_sync(group_mask<G>(), sr, 0, G);
+    rw_denom = sqrtf(sr) + a.eps;
+  }
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    const int c = (ch * G + lane) * VEC;
+    if (c >= d.dim) continue;
+    float* wp = a.weights + d.w_off + row * d.dim + c;
+    float* sp = (a.optimizer == TZK_OPT_ADAGRAD) ? a.state + d.w_off + row * d.dim + c : nullptr;
+    if (VEC == 4) {
+      float4 w4 = *reinterpret_cast<float4*>(wp);
+      float w[4] = {w4.x, w4.y, w4.z, w4.w};
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      if (sp) {
+        float4 s4 = *reinterpret_cast<float4*>(sp);
+        s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
+      }
+      apply_update<4>(a, w, s, acc[ch], rw_denom);
+      *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
+      if (sp) *reinterpret_cast<float4*>(sp) = make_float4(s[0], s[1], s[2], s[3]);
+    } else {
+      float w[1] = {wp[0]};
+      float s[1] = {sp ? sp[0] : 0.f};
+      apply_update<1>(a, w, s, acc[ch], rw_denom);
+      wp[0] = w[0];
+      if (sp) sp[0] = s[0];
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_grad(const float* p, float (&g)[VEC]) {
+  if (VEC == 4) {
+    float4 v = ld_row_f4(p);
+    g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+  } else {
+    g[0] = __ldg(p);
+  }
+}
+
+// ---- 3. short runs ---------------------------------------------------------------------------------
+// CH = float4 (or scalar) chunks per lane: dims up to G*VEC*CH are supported.
+template <typename KeyT, int G, int VEC, int CH>
+__global__ void __launch_bounds__(kThreads)
+run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
+                  const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
+                  const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                  const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
+                  int32_t* __restrict__ long_list, int32_t* __restrict__ long_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
+  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+
+  constexpr int NG = kThreads / G;
+  const int lane = threadIdx.x % G;
+  const int64_t stride = (int64_t)gridDim.x * NG;
+  // all G lanes of a group follow the same control flow (p, key, len are group-uniform)
+  for (int64_t p = (int64_t)blockIdx.x * NG + threadIdx.x / G; p < a.n; p += stride) {
+    const KeyT key = keys[p];
+    if (p > 0 && keys[p - 1] == key) continue;  // not a run head
+    int len = 1;
+    while (len <= kShortRun && p + len < a.n && keys[p + len] == key) ++len;
+    if (len > kShortRun) {
+      if (lane == 0) long_list[atomicAdd(long_count, 1)] = (int32_t)p;
+      continue;
+    }
+    const int32_t v0 = vals[p];
+    int f0;
+    if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
+    const BwdFeat d = fd[f0];
+    const int64_t row = (int64_t)key - d.key_base;
+
+    float acc[CH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+    for (int j = 0; j < len; ++j) {
+      const Entry en = entry_of(a, fd, j == 0 ? v0 : vals[p + j], f0);
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * G + lane) * VEC;
+        if (c < d.dim) {
+          float g[VEC];
+          load_grad<VEC>(en.g + c, g);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[ch][k] += g[k] * en.scale;
+        }
+      }
+    }
+    finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
+  }
+}
+
+// ---- 4. long runs ----------------------------------------------------------------------------------
+template <typename KeyT, int G, int VEC, int CH>
+__global__ void __launch_bounds__(kThreads)
+long_run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off,
+                       const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_key_base,
+                       const int32_t* __restrict__ feat_dim, const int32_t* __restrict__ feat_col,
+                       const int32_t* __restrict__ feat_pool, const KeyT* __restrict__ keys,
+                       const int32_t* __restrict__ vals, const int32_t* __restrict__ long_list,
+                       const int32_t* __restrict__ long_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NG = kThreads / G;
+  BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
+  // partial sums: [NG][CH*G*VEC] floats, after the descriptors (16-B aligned: BwdFeat is 48 B)
+  float* part = reinterpret_cast<float*>(smem_raw + align16((size_t)a.F * sizeof(BwdFeat)));
+  __shared__ int64_t run_end_s;
+  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+
+  const int lane = threadIdx.x % G;
+  const int g = threadIdx.x / G;
+  const int n_long = *long_count;
+  constexpr int ROWF = CH * G * VEC;  // floats per partial row
+
+  for (int r = blockIdx.x; r < n_long; r += gridDim.x) {
+    const int64_t p = long_list[r];
+    const KeyT key = keys[p];
+    if (threadIdx.x == 0) {
+      // gallop + binary search for the end of the run
+      int64_t lo = p, step = kShortRun;  // keys[lo] == key
+      int64_t hi = p + step;
+      while (hi < a.n && keys[hi] == key) { lo = hi; step <<= 1; hi = lo + step; }
+      if (hi > a.n) hi = a.n;  // keys[hi] != key or hi == n
+      while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] == key) lo = mid; else hi = mid;
+      }
+      run_end_s = hi;
+    }
+    __syncthreads();
+    const int64_t end = run_end_s;
+    const int32_t v0 = vals[p];
+    int f0;
+    if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
+    const BwdFeat d = fd[f0];
+    const int64_t row = (int64_t)key - d.key_base;
+
+    float acc[CH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+    for (int64_t q = p + g; q < end; q += NG) {
+      const Entry en = entry_of(a, fd, vals[q], f0);
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * G + lane) * VEC;
+        if (c < d.dim) {
+          float gr[VEC];
+          load_grad<VEC>(en.g + c, gr);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[ch][k] += gr[k] * en.scale;
+        }
+      }
+    }
+    // fixed-order tree over the NG lane groups
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) part[g * ROWF + (ch * G + lane) * VEC + k] = acc[ch][k];
+    __syncthreads();
+    for (int half = NG / 2; half >= 1; half >>= 1) {
+      if (g < half) {
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const int o = (ch * G + lane) * VEC + k;
+            part[g * ROWF + o] += part[(g + half) * ROWF + o];
+          }
+      }
+      __syncthreads();
+    }
+    if (g == 0) {
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[ch][k] = part[(ch * G + lane) * VEC + k];
+      finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void zero_counter(int32_t* c) { *c = 0; }
+
+inline int bits_for(int64_t total_keys) {
+  int b = 1;
+  while (b < 63 && ((int64_t)1 << b) < total_keys) ++b;
+  return b;
+}
+
+struct WsLayout {
+  size_t keys_in, keys_out, vals_in, vals_out, long_list, long_count, cub_tmp, total;
+  size_t cub_bytes;
+};
+
+template <typename KeyT>
+cudaError_t cub_sort(void* tmp, size_t& tmp_bytes, const KeyT* kin, KeyT* kout, const int32_t* vin,
+                     int32_t* vout, int64_t n, int bits, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, (int)n, 0, bits, st);
+}
+
+WsLayout ws_layout(int64_t nnz, int64_t total_keys) {
+  WsLayout L;
+  const bool k64 = total_keys > ((int64_t)1 << 32);
+  const size_t ksz = k64 ? 8 : 4;
+  const int64_t n = nnz < 1 ? 1 : nnz;
+  size_t o = 0;
+  L.keys_in = o; o = align_up(o + n * ksz, 256);
+  L.keys_out = o; o = align_up(o + n * ksz, 256);
+  L.vals_in = o; o = align_up(o + n * 4, 256);
+  L.vals_out = o; o = align_up(o + n * 4, 256);
+  L.long_list = o; o = align_up(o + n * 4, 256);
+  L.long_count = o; o = align_up(o + 256, 256);
+  size_t tb = 0;
+  const int bits = bits_for(total_keys);
+  if (k64) cub_sort<uint64_t>(nullptr, tb, nullptr, nullptr, nullptr, nullptr, n, bits, 0);
+  else cub_sort<uint32_t>(nullptr, tb, nullptr, nullptr, nullptr, nullptr, n, bits, 0);
+  L.cub_bytes = tb;
+  L.cub_tmp = o; o = align_up(o + tb, 256);
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+#define TZK_BWD_LAUNCH(KeyT, G_, VEC_, CH_)                                                          \
+  do {                                                                                                \
+    size_t smem_s = (size_t)F * sizeof(BwdFeat);                                                      \
+    run_update_kernel<KeyT, G_, VEC_, CH_><<<grid_s, kThreads, smem_s, st>>>(                         \
+        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
+        vals_out, long_list, long_count);                                                             \
+    TZK_CHECK_LAUNCH("run_update_kernel");                                                            \
+    size_t smem_l = tzk::align16((size_t)F * sizeof(BwdFeat)) +                                  \
+                    (size_t)(kThreads / G_) * (CH_ * G_ * VEC_) * sizeof(float);                      \
+    long_run_update_kernel<KeyT, G_, VEC_, CH_><<<kSmCountB200 * 4, kThreads, smem_l, st>>>(          \
+        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
+        vals_out, long_list, long_count);                                                             \
+    TZK_CHECK_LAUNCH("long_run_update_kernel");                                                       \
+  } while (0)
+
+#define TZK_BWD_DISPATCH_G(KeyT, VEC_, CH_)                 \
+  switch (G) {                                              \
+    case 1: TZK_BWD_LAUNCH(KeyT, 1, VEC_, CH_); break;      \
+    case 2: TZK_BWD_LAUNCH(KeyT, 2, VEC_, CH_); break;      \
+    case 4: TZK_BWD_LAUNCH(KeyT, 4, VEC_, CH_); break;      \
+    case 8: TZK_BWD_LAUNCH(KeyT, 8, VEC_, CH_); break;      \
+    case 16: TZK_BWD_LAUNCH(KeyT, 16, VEC_, CH_); break;    \
+    default: TZK_BWD_LAUNCH(KeyT, 32, VEC_, CH_); break;    \
+  }
+
+extern "C" size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys) {
+  return ws_layout(nnz, total_keys).total;
+}
+
+extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                             const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                             const int32_t* feat_col, const int32_t* feat_pool,
+                             const int64_t* feat_key_base, const int64_t* ids, const int64_t* offsets,
+                             int32_t F, int32_t B, int64_t nnz, int64_t total_keys, int32_t max_dim,
+                             int32_t vec_ok, float* weights, float* state, float lr, float eps,
+                             float grad_scale, void* workspace, size_t workspace_bytes,
+                             tzk_stream_t stream) {
+  TZK_REQUIRE(optimizer >= 0 && optimizer <= 2, "fused_bwd: unknown optimizer %d", optimizer);
+  TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0, "fused_bwd: negative size");
+  if (F == 0 || B == 0 || nnz == 0) return 0;
+  TZK_REQUIRE(nnz < ((int64_t)1 << 31) && (int64_t)F * B < ((int64_t)1 << 31),
+              "fused_bwd: nnz or F*B >= 2^31 not supported");
+  TZK_REQUIRE(grad_out && feat_w_off && feat_rows && feat_dim && feat_key_base && ids && offsets && weights,
+              "fused_bwd: NULL argument");
+  TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
+  TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
+  TZK_REQUIRE(F <= 256, "fused_bwd: F=%d > 256 keys per collection", F);
+  TZK_REQUIRE(max_dim >= 1 && max_dim <= 1024, "fused_bwd: max_dim=%d out of range [1,1024]", max_dim);
+  WsLayout L = ws_layout(nnz, total_keys);
+  TZK_REQUIRE(workspace && workspace_bytes >= L.total, "fused_bwd: workspace too small (%zu < %zu)",
+              workspace_bytes, L.total);
+  cudaStream_t st = as_stream(stream);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  void* keys_in = ws + L.keys_in;
+  void* keys_out = ws + L.keys_out;
+  int32_t* vals_in = reinterpret_cast<int32_t*>(ws + L.vals_in);
+  int32_t* vals_out = reinterpret_cast<int32_t*>(ws + L.vals_out);
+  int32_t* long_list = reinterpret_cast<int32_t*>(ws + L.long_list);
+  int32_t* long_count = reinterpret_cast<int32_t*>(ws + L.long_count);
+  const bool k64 = total_keys > ((int64_t)1 << 32);
+  const int bits = bits_for(total_keys);
+
+  zero_counter<<<1, 1, 0, st>>>(long_count);
+  const int64_t n_bags = (int64_t)F * B;
+  int grid_lin = (int)std::min<int64_t>(ceil_div64(n_bags, kThreads), kSmCountB200 * 16);
+  size_t cub_bytes = L.cub_bytes;
+  cudaError_t ce;
+  if (k64) {
+    linearize_kernel<uint64_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
+                                                              pooled, (uint64_t*)keys_in, vals_in);
+    TZK_CHECK_LAUNCH("linearize_kernel");
+    ce = cub_sort<uint64_t>(ws + L.cub_tmp, cub_bytes, (const uint64_t*)keys_in, (uint64_t*)keys_out, vals_in,
+                            vals_out, nnz, bits, st);
+  } else {
+    linearize_kernel<uint32_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
+                                                              pooled, (uint32_t*)keys_in, vals_in);
+    TZK_CHECK_LAUNCH("linearize_kernel");
+    ce = cub_sort<uint32_t>(ws + L.cub_tmp, cub_bytes, (const uint32_t*)keys_in, (uint32_t*)keys_out, vals_in,
+                            vals_out, nnz, bits, st);
+  }
+  TZK_REQUIRE(ce == cudaSuccess, "fused_bwd: radix sort failed: %s", cudaGetErrorString(ce));
+
+  BwdArgs a;
+  a.grad_out = grad_out; a.ld_grad = ld_grad; a.offsets = offsets; a.weights = weights; a.state = state;
+  a.lr = lr; a.eps = eps; a.grad_scale = grad_scale; a.F = F; a.B = B; a.optimizer = optimizer;
+  a.pooled = pooled; a.n = nnz;
+
+  const int vec = (vec_ok && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)grad_out % 16 == 0) &&
+                   (ld_grad % 4 == 0) && (optimizer != TZK_OPT_ADAGRAD || (uintptr_t)state % 16 == 0))
+                      ? 4 : 1;
+  int need = (max_dim + vec - 1) / vec;  // chunks per row
+  int G = 1;
+  while (G < need && G < 32) G <<= 1;
+  const int ch = (need + G - 1) / G;
+  TZK_REQUIRE(ch <= 8, "fused_bwd: max_dim=%d needs %d chunks per lane (> 8); unaligned wide rows are not supported",
+              max_dim, ch);
+  const int NG = kThreads / G;
+  int grid_s = (int)std::min<int64_t>(ceil_div64(nnz, NG), kSmCountB200 * 16);
+
+  // CH is compiled for 1 (D <= 128 aligned), 2 and 8
+  if (k64) {
+    if (vec == 4) { if (ch == 1) { TZK_BWD_DISPATCH_G(uint64_t, 4, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint64_t, 32, 4, 2); } else { TZK_BWD_LAUNCH(uint64_t, 32, 4, 8); } }
+    else { if (ch == 1) { TZK_BWD_DISPATCH_G(uint64_t, 1, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint64_t, 32, 1, 2); } else { TZK_BWD_LAUNCH(uint64_t, 32, 1, 8); } }
+  } else {
+    if (vec == 4) { if (ch == 1) { TZK_BWD_DISPATCH_G(uint32_t, 4, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint32_t, 32, 4, 2); } else { TZK_BWD_LAUNCH(uint32_t, 32, 4, 8); } }
+    else { if (ch == 1) { TZK_BWD_DISPATCH_G(uint32_t, 1, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint32_t, 32, 1, 2); } else { TZK_BWD_LAUNCH(uint32_t, 32, 1, 8); } }
+  }
+  return 0;
+}

@@ -1,0 +1,59 @@
+// Shared helpers for the tzk kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tzk.h"
+
+namespace tzk {
+
+void set_error(const char* fmt, ...);
+
+inline cudaStream_t as_stream(tzk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define TZK_CHECK_LAUNCH(name)                                                      \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      ::tzk::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));     \
+      return 2;                                                                     \
+    }                                                                               \
+  } while (0)
+
+#define TZK_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::tzk::set_error(__VA_ARGS__);  \
+      return 1;                       \
+    }                                 \
+  } while (0)
+
+constexpr int kSmCountB200 = 148;
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
+
+// 128-bit streaming loads/stores.  Table rows are random-access and re-used only through L2, so they
+// bypass L1 allocation; index lists / outputs are touched once.
+__device__ __forceinline__ float4 ld_row_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_scale(const float4& a, float s) {
+  return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+
+}  // namespace tzk

@@ -1,0 +1,428 @@
+// tzk_dense.cu — K6 regroup (column gather-sum), K7 jagged<->padded, A7 FM, A9/A10 DLRM dot interaction.
+// All HBM-bound fp32 movers; the interaction is 7.4 FLOP/B so it is written as a
+// register-tiled FFMA kernel that reads each pooled row once and emits the whole final-MLP input.
+#include "tzk_common.cuh"
+
+using namespace tzk;
+
+namespace {
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------
+// K6: out[row, c] = sum_{k in [col_start[c], col_start[c+1])} srcs[col_src[k]][row*ld + col_srccol[k]]
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+col_gather_sum_kernel(const float* const* __restrict__ srcs, const int64_t* __restrict__ src_ld,
+                      const int32_t* __restrict__ col_start, const int32_t* __restrict__ col_src,
+                      const int32_t* __restrict__ col_srccol, int C, int64_t rows, float* __restrict__ out,
+                      int64_t ld_out) {
+  const int64_t n = rows * C;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t row = i / C;
+    const int c = (int)(i - row * C);
+    const int k0 = __ldg(col_start + c), k1 = __ldg(col_start + c + 1);
+    float acc = 0.f;
+    for (int k = k0; k < k1; ++k) {
+      const int s = __ldg(col_src + k);
+      acc += __ldg(srcs[s] + row * __ldg(src_ld + s) + __ldg(col_srccol + k));
+    }
+    out[row * ld_out + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K7
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+jagged_to_padded_kernel(const float* __restrict__ values, const int64_t* __restrict__ offsets, int B, int T,
+                        int D, float* __restrict__ out) {
+  const int64_t n = (int64_t)B * T * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int d = (int)(i % D);
+    const int64_t bt = i / D;
+    const int t = (int)(bt % T);
+    const int b = (int)(bt / T);
+    const int64_t s = __ldg(offsets + b), e = __ldg(offsets + b + 1);
+    out[i] = (s + t < e) ? __ldg(values + (s + t) * D + d) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+padded_to_jagged_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ offsets, int B, int T,
+                        int D, int64_t nnz, float* __restrict__ grad_values) {
+  // one thread per (jagged row, d): find b by binary search over offsets
+  const int64_t n = nnz * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t l = i / D;
+    const int d = (int)(i - l * D);
+    int lo = 0, hi = B;  // largest b with offsets[b] <= l
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(offsets + mid) <= l) lo = mid; else hi = mid;
+    }
+    const int64_t t = l - __ldg(offsets + lo);
+    grad_values[i] = (t < T) ? __ldg(grad_out + ((int64_t)lo * T + t) * D + d) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A7: FM.  one thread per (b, d): two running sums over n.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+fm_fwd_kernel(const float* __restrict__ x, int64_t ld_x, int64_t B, int N, int D, float* __restrict__ y,
+              int64_t ld_y) {
+  const int64_t n = B * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t b = i / D;
+    const int d = (int)(i - b * D);
+    const float* xb = x + b * ld_x + d;
+    float s = 0.f, q = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < N; ++k) {
+      const float v = __ldg(xb + (int64_t)k * D);
+      s += v;
+      q += v * v;
+    }
+    y[b * ld_y + d] = 0.5f * (s * s - q);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fm_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ dy, int64_t ld_dy,
+              int64_t B, int N, int D, float* __restrict__ dx, int64_t ld_dx) {
+  const int64_t n = B * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t b = i / D;
+    const int d = (int)(i - b * D);
+    const float* xb = x + b * ld_x + d;
+    float s = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < N; ++k) s += __ldg(xb + (int64_t)k * D);
+    const float g = __ldg(dy + b * ld_dy + d);
+    float* dxb = dx + b * ld_dx + d;
+#pragma unroll 4
+    for (int k = 0; k < N; ++k) dxb[(int64_t)k * D] = g * (s - __ldg(xb + (int64_t)k * D));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A9/A10: dot interaction.  One warp per sample.  X_b (N x D) is staged in shared memory with a row
+// stride of D+4 floats (keeps 16-B alignment, spreads rows over banks); each lane owns 4x4 blocks of the
+// Gram matrix (only blocks touching the strict upper triangle), so every k step costs 2 LDS.128 for
+// 16 FMAs.  Results are staged in shared memory and the whole output row [P | D | Ns*D] is written
+// with coalesced stores.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kIWarps = 8;  // warps (= samples in flight) per CTA
+
+__device__ __forceinline__ int tri_index(int i, int j, int N) {  // i < j
+  return i * N - (i * (i + 1)) / 2 + (j - i - 1);
+}
+
+__global__ void __launch_bounds__(kIWarps * 32)
+dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
+                        int64_t ld_sparse, int64_t B, int Ns, int D, int copy_dense, int copy_sparse,
+                        float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = Ns + (dense != nullptr);
+  const int Np = (N + 3) & ~3;        // rows padded to a multiple of 4 (pad rows are zero)
+  const int DS = D + 4;               // row stride
+  const int P = N * (N - 1) / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Pp = (P + 3) & ~3;        // keeps every warp's slab 16-B aligned
+  float* X = smem + (size_t)warp * (Np * DS + Pp);
+  float* O = X + Np * DS;
+  const int nb = Np / 4;
+  const int n_blocks = nb * (nb + 1) / 2;
+  const int D4 = D / 4;  // D % 4 == 0 enforced by the host wrapper
+
+  for (int64_t b = (int64_t)blockIdx.x * kIWarps + warp; b < B; b += (int64_t)gridDim.x * kIWarps) {
+    // ---- stage X_b ------------------------------------------------------------------------------
+    const float* sp = sparse + b * ld_sparse;
+    const int doff = dense ? 1 : 0;
+    for (int i = lane; i < Ns * D4; i += 32) {
+      const int r = i / D4, c4 = i - r * D4;
+      float4 v = ld_row_f4(sp + (int64_t)r * D + c4 * 4);
+      *reinterpret_cast<float4*>(X + (r + doff) * DS + c4 * 4) = v;
+    }
+    if (dense) {
+      for (int c4 = lane; c4 < D4; c4 += 32)
+        *reinterpret_cast<float4*>(X + c4 * 4) = ld_row_f4(dense + b * ld_dense + c4 * 4);
+    }
+    for (int i = lane; i < (Np - N) * D4; i += 32) {
+      const int r = N + i / D4, c4 = i % D4;
+      *reinterpret_cast<float4*>(X + r * DS + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    // ---- Gram blocks ------------------------------------------------------------------------------
+    for (int blk = lane; blk < n_blocks; blk += 32) {
+      // decode (bi <= bj) from the linear upper-triangular block index
+      int bi = 0, rem = blk;
+      while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+      const int bj = bi + rem;
+      const float* xi = X + (bi * 4) * DS;
+      const float* xj = X + (bj * 4) * DS;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      for (int k = 0; k < D; k += 4) {
+        float4 a[4], bb[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          a[r] = *reinterpret_cast<const float4*>(xi + r * DS + k);
+          bb[r] = *reinterpret_cast<const float4*>(xj + r * DS + k);
+        }
+        // accumulate in k order (k, k+1, k+2, k+3) so the sum order matches a sequential dot product
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[r][c] = fmaf(a[r].x, bb[c].x, acc[r][c]);
+            acc[r][c] = fmaf(a[r].y, bb[c].y, acc[r][c]);
+            acc[r][c] = fmaf(a[r].z, bb[c].z, acc[r][c]);
+            acc[r][c] = fmaf(a[r].w, bb[c].w, acc[r][c]);
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = bi * 4 + r, j = bj * 4 + c;
+          if (i < j && j < N) O[tri_index(i, j, N)] = acc[r][c];
+        }
+    }
+    __syncwarp();
+    // ---- coalesced output row ---------------------------------------------------------------------
+    float* orow = out + b * ld_out;
+    for (int i = lane; i < P; i += 32) orow[i] = O[i];
+    int o = P;
+    if (copy_dense && dense) {
+      for (int c = lane; c < D; c += 32) orow[o + c] = X[c];
+      o += D;
+    }
+    if (copy_sparse) {
+      for (int i = lane; i < Ns * D; i += 32) {
+        const int r = i / D, c = i - r * D;
+        orow[o + i] = X[(r + doff) * DS + c];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// backward: dX = (G + G^T) X (+ pass-through grads); lane owns 4 rows x 4 cols blocks of dX.
+__global__ void __launch_bounds__(kIWarps * 32)
+dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
+                        int64_t ld_sparse, const float* __restrict__ d_out, int64_t ld_dout, int64_t B,
+                        int Ns, int D, int copy_dense, int copy_sparse, float* __restrict__ d_dense,
+                        int64_t ld_ddense, float* __restrict__ d_sparse, int64_t ld_dsparse) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = Ns + (dense != nullptr);
+  const int Np = (N + 3) & ~3;
+  const int DS = D + 4;
+  const int SS = Np + 4;  // stride of the symmetric grad matrix
+  const int P = N * (N - 1) / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* X = smem + (size_t)warp * (Np * DS + Np * SS);
+  float* S = X + Np * DS;
+  const int D4 = D / 4;
+  const int nb = Np / 4;
+  const int doff = dense ? 1 : 0;
+
+  for (int64_t b = (int64_t)blockIdx.x * kIWarps + warp; b < B; b += (int64_t)gridDim.x * kIWarps) {
+    const float* sp = sparse + b * ld_sparse;
+    for (int i = lane; i < Ns * D4; i += 32) {
+      const int r = i / D4, c4 = i - r * D4;
+      *reinterpret_cast<float4*>(X + (r + doff) * DS + c4 * 4) = ld_row_f4(sp + (int64_t)r * D + c4 * 4);
+    }
+    if (dense)
+      for (int c4 = lane; c4 < D4; c4 += 32)
+        *reinterpret_cast<float4*>(X + c4 * 4) = ld_row_f4(dense + b * ld_dense + c4 * 4);
+    for (int i = lane; i < (Np - N) * D4; i += 32) {
+      const int r = N + i / D4, c4 = i % D4;
+      *reinterpret_cast<float4*>(X + r * DS + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = lane; i < Np * SS; i += 32) S[i] = 0.f;
+    __syncwarp();
+    const float* go = d_out + b * ld_dout;
+    // scatter the P upper-triangular grads into the symmetric matrix (coalesced read of d_out)
+    {
+      // walk (i,j) incrementally: lane handles indices lane, lane+32, ...
+      for (int idx = lane; idx < P; idx += 32) {
+        // invert tri_index: find i with row_start(i) <= idx < row_start(i+1)
+        int i = 0, rs = 0;
+        while (idx >= rs + (N - 1 - i)) { rs += N - 1 - i; ++i; }
+        const int j = i + 1 + (idx - rs);
+        const float g = __ldg(go + idx);
+        S[i * SS + j] = g;
+        S[j * SS + i] = g;
+      }
+    }
+    __syncwarp();
+    // dX[i0..i0+3][k..k+3] = sum_j S[j][i0..i0+3] * X[j][k..k+3]
+    const int n_blocks = nb * D4;
+    for (int blk = lane; blk < n_blocks; blk += 32) {
+      const int bi = blk / D4, c4 = blk - bi * D4;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      for (int j = 0; j < N; ++j) {
+        const float4 s4 = *reinterpret_cast<const float4*>(S + j * SS + bi * 4);
+        const float4 x4 = *reinterpret_cast<const float4*>(X + j * DS + c4 * 4);
+        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(sv[r], xv[c], acc[r][c]);
+      }
+      // pass-through grads and store
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = bi * 4 + r;
+        if (i >= N) continue;
+        float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        if (dense && i == 0) {
+          if (copy_dense) {
+            const float* gp = go + P + c4 * 4;
+            v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
+          }
+          float* dp = d_dense + b * ld_ddense + c4 * 4;
+          dp[0] = v.x; dp[1] = v.y; dp[2] = v.z; dp[3] = v.w;
+        } else {
+          const int r_s = i - doff;
+          if (copy_sparse) {
+            const float* gp = go + P + ((copy_dense && dense) ? D : 0) + r_s * D + c4 * 4;
+            v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
+          }
+          float* dp = d_sparse + b * ld_dsparse + (int64_t)r_s * D + c4 * 4;
+          dp[0] = v.x; dp[1] = v.y; dp[2] = v.z; dp[3] = v.w;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+inline int grid_for(int64_t n, int per_block, int max_blocks) {
+  int64_t g = ceil_div64(n, per_block);
+  if (g < 1) g = 1;
+  return (int)(g < max_blocks ? g : max_blocks);
+}
+}  // namespace
+
+extern "C" int tzk_col_gather_sum(const float* const* srcs, const int64_t* src_ld, const int32_t* col_start,
+                                  const int32_t* col_src, const int32_t* col_srccol, int32_t C, int64_t rows,
+                                  float* out, int64_t ld_out, tzk_stream_t stream) {
+  TZK_REQUIRE(C >= 0 && rows >= 0, "col_gather_sum: negative size");
+  if (C == 0 || rows == 0) return 0;
+  TZK_REQUIRE(srcs && src_ld && col_start && col_src && col_srccol && out, "col_gather_sum: NULL argument");
+  col_gather_sum_kernel<<<grid_for(rows * C, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(
+      srcs, src_ld, col_start, col_src, col_srccol, C, rows, out, ld_out);
+  TZK_CHECK_LAUNCH("col_gather_sum_kernel");
+  return 0;
+}
+
+extern "C" int tzk_jagged_to_padded(const float* values, const int64_t* offsets, int32_t B, int32_t T,
+                                    int32_t D, float* out, tzk_stream_t stream) {
+  TZK_REQUIRE(B >= 0 && T >= 0 && D >= 1, "jagged_to_padded: bad sizes");
+  if (B == 0 || T == 0) return 0;
+  TZK_REQUIRE(offsets && out, "jagged_to_padded: NULL argument");
+  jagged_to_padded_kernel<<<grid_for((int64_t)B * T * D, kThreads, kSmCountB200 * 16), kThreads, 0,
+                            as_stream(stream)>>>(values, offsets, B, T, D, out);
+  TZK_CHECK_LAUNCH("jagged_to_padded_kernel");
+  return 0;
+}
+
+extern "C" int tzk_padded_to_jagged(const float* grad_out, const int64_t* offsets, int32_t B, int32_t T,
+                                    int32_t D, int64_t nnz, float* grad_values, tzk_stream_t stream) {
+  TZK_REQUIRE(B >= 0 && T >= 0 && D >= 1 && nnz >= 0, "padded_to_jagged: bad sizes");
+  if (nnz == 0) return 0;
+  TZK_REQUIRE(B > 0 && offsets && grad_values && (T == 0 || grad_out), "padded_to_jagged: NULL argument");
+  padded_to_jagged_kernel<<<grid_for(nnz * D, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(
+      grad_out, offsets, B, T, D, nnz, grad_values);
+  TZK_CHECK_LAUNCH("padded_to_jagged_kernel");
+  return 0;
+}
+
+extern "C" int tzk_fm_fwd(const float* x, int64_t ld_x, int64_t B, int32_t N, int32_t D, float* y,
+                          int64_t ld_y, tzk_stream_t stream) {
+  TZK_REQUIRE(B >= 0 && N >= 0 && D >= 1, "fm_fwd: bad sizes");
+  if (B == 0) return 0;
+  TZK_REQUIRE(x && y, "fm_fwd: NULL argument");
+  fm_fwd_kernel<<<grid_for(B * D, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(
+      x, ld_x, B, N, D, y, ld_y);
+  TZK_CHECK_LAUNCH("fm_fwd_kernel");
+  return 0;
+}
+
+extern "C" int tzk_fm_bwd(const float* x, int64_t ld_x, const float* dy, int64_t ld_dy, int64_t B, int32_t N,
+                          int32_t D, float* dx, int64_t ld_dx, tzk_stream_t stream) {
+  TZK_REQUIRE(B >= 0 && N >= 0 && D >= 1, "fm_bwd: bad sizes");
+  if (B == 0) return 0;
+  TZK_REQUIRE(x && dy && dx, "fm_bwd: NULL argument");
+  fm_bwd_kernel<<<grid_for(B * D, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(
+      x, ld_x, dy, ld_dy, B, N, D, dx, ld_dx);
+  TZK_CHECK_LAUNCH("fm_bwd_kernel");
+  return 0;
+}
+
+static int interact_check(const char* who, const float* dense, int64_t ld_dense, const float* sparse,
+                          int64_t ld_sparse, int64_t B, int32_t Ns, int32_t D) {
+  TZK_REQUIRE(B >= 0 && Ns >= 1 && D >= 4, "%s: bad sizes", who);
+  TZK_REQUIRE(D % 4 == 0 && D <= 128, "%s: D=%d must be a multiple of 4 and <= 128", who, D);
+  TZK_REQUIRE(Ns + (dense != nullptr) <= 64, "%s: more than 64 interacting features", who);
+  TZK_REQUIRE(sparse != nullptr, "%s: sparse is NULL", who);
+  TZK_REQUIRE(((uintptr_t)sparse % 16 == 0) && (ld_sparse % 4 == 0), "%s: sparse must be 16-B aligned", who);
+  TZK_REQUIRE(!dense || (((uintptr_t)dense % 16 == 0) && (ld_dense % 4 == 0)), "%s: dense must be 16-B aligned",
+              who);
+  return 0;
+}
+
+extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const float* sparse,
+                                    int64_t ld_sparse, int64_t B, int32_t Ns, int32_t D, int32_t copy_dense,
+                                    int32_t copy_sparse, float* out, int64_t ld_out, tzk_stream_t stream) {
+  int rc = interact_check("dot_interact_fwd", dense, ld_dense, sparse, ld_sparse, B, Ns, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  TZK_REQUIRE(out, "dot_interact_fwd: out is NULL");
+  const int N = Ns + (dense != nullptr);
+  const int Np = (N + 3) & ~3;
+  const int P = N * (N - 1) / 2;
+  size_t smem = (size_t)kIWarps * (Np * (D + 4) + ((P + 3) & ~3)) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(dot_interact_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dot_interact_fwd_kernel<<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>(
+      dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, out, ld_out);
+  TZK_CHECK_LAUNCH("dot_interact_fwd_kernel");
+  return 0;
+}
+
+extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const float* sparse,
+                                    int64_t ld_sparse, const float* d_out, int64_t ld_dout, int64_t B,
+                                    int32_t Ns, int32_t D, int32_t copy_dense, int32_t copy_sparse,
+                                    float* d_dense, int64_t ld_ddense, float* d_sparse, int64_t ld_dsparse,
+                                    tzk_stream_t stream) {
+  int rc = interact_check("dot_interact_bwd", dense, ld_dense, sparse, ld_sparse, B, Ns, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  TZK_REQUIRE(d_out && d_sparse && (!dense || d_dense), "dot_interact_bwd: NULL argument");
+  const int N = Ns + (dense != nullptr);
+  const int Np = (N + 3) & ~3;
+  size_t smem = (size_t)kIWarps * (Np * (D + 4) + Np * (Np + 4)) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(dot_interact_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dot_interact_bwd_kernel<<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>(
+      dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, Ns, D, copy_dense, copy_sparse, d_dense, ld_ddense,
+      d_sparse, ld_dsparse);
+  TZK_CHECK_LAUNCH("dot_interact_bwd_kernel");
+  return 0;
+}

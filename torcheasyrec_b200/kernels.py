@@ -1,0 +1,361 @@
+"""Tensor-level wrappers over the tzk C-ABI (include/tzk.h).
+
+`CudaKernels` is the only compute backend the package ships.  It validates device / dtype / contiguity,
+allocates outputs and workspaces through torch's caching allocator, passes raw pointers + the current
+CUDA stream across the ABI, and raises `TzkError` on any failure.  There is deliberately no CPU
+implementation here: host-logic tests inject their own checker backend (tests/oracle_backend.py).
+"""
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import TzkError, check, lib
+
+POOL_SUM, POOL_MEAN = 0, 1
+OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD = 0, 1, 2
+
+
+@dataclass
+class FeatureLayout:
+    """Host-side description of the keys served by one shard arena (one entry per KJT key).
+
+    Mirrors the "feature descriptor" arrays of include/tzk.h.  `key_base` linearises (table,row) for the
+    backward sort; features that share a physical table share w_off / key_base.
+    """
+
+    w_off: List[int]
+    rows: List[int]
+    dim: List[int]
+    col: List[int]
+    pool: List[int]
+    key_base: List[int]
+    total_keys: int
+    total_dim: int
+    arena_elems: int
+    # device copies (filled by .to())
+    d_w_off: Optional[torch.Tensor] = None
+    d_rows: Optional[torch.Tensor] = None
+    d_dim: Optional[torch.Tensor] = None
+    d_col: Optional[torch.Tensor] = None
+    d_pool: Optional[torch.Tensor] = None
+    d_key_base: Optional[torch.Tensor] = None
+
+    @property
+    def num_features(self) -> int:
+        return len(self.dim)
+
+    @property
+    def max_dim(self) -> int:
+        return max(self.dim) if self.dim else 1
+
+    @property
+    def vec_ok(self) -> int:
+        return int(all(d % 4 == 0 for d in self.dim) and all(c % 4 == 0 for c in self.col)
+                   and all(o % 4 == 0 for o in self.w_off))
+
+    def to(self, device) -> "FeatureLayout":
+        self.d_w_off = torch.tensor(self.w_off, dtype=torch.int64, device=device)
+        self.d_rows = torch.tensor(self.rows, dtype=torch.int64, device=device)
+        self.d_dim = torch.tensor(self.dim, dtype=torch.int32, device=device)
+        self.d_col = torch.tensor(self.col, dtype=torch.int32, device=device)
+        self.d_pool = torch.tensor(self.pool, dtype=torch.int32, device=device)
+        self.d_key_base = torch.tensor(self.key_base, dtype=torch.int64, device=device)
+        return self
+
+
+def build_layout(table_rows: Sequence[int], table_dim: Sequence[int], feat_table: Sequence[int],
+                 feat_pool: Sequence[int], align: int = 4) -> FeatureLayout:
+    """Packs tables back to back into one arena (row starts 16-B aligned) and lays features out in order."""
+    t_off, t_key = [], []
+    o = k = 0
+    for r, d in zip(table_rows, table_dim):
+        o = (o + align - 1) // align * align
+        t_off.append(o)
+        t_key.append(k)
+        o += r * d
+        k += r
+    col, c = [], 0
+    for t in feat_table:
+        col.append(c)
+        c += table_dim[t]
+    return FeatureLayout(
+        w_off=[t_off[t] for t in feat_table], rows=[table_rows[t] for t in feat_table],
+        dim=[table_dim[t] for t in feat_table], col=col, pool=list(feat_pool),
+        key_base=[t_key[t] for t in feat_table], total_keys=max(k, 1), total_dim=c, arena_elems=max(o, 1))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise TzkError(f"{name}: expected a CUDA tensor, got {t.device} (no CPU fallback in torcheasyrec_b200)")
+    if t.dtype != dtype:
+        raise TzkError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise TzkError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _rows2d(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """Accepts a 2-D fp32 CUDA tensor whose rows are contiguous (column slices of a wider buffer are fine)."""
+    if not t.is_cuda:
+        raise TzkError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise TzkError(f"{name}: expected a 2-D float32 tensor")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise TzkError(f"{name}: rows must be contiguous")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    return t, ld
+
+
+class CudaKernels:
+    """sm_100a implementation of the hot path.  Stateless apart from cached workspaces."""
+
+    name = "cuda"
+
+    def __init__(self) -> None:
+        self._lib = lib()
+        self._ws = {}
+
+    # ------------------------------------------------------------------ workspace cache
+    def _workspace(self, key, nbytes: int, device) -> torch.Tensor:
+        ws = self._ws.get((key, device))
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self._ws[(key, device)] = ws
+        return ws
+
+    # ------------------------------------------------------------------ K3
+    def lengths_to_offsets(self, lengths: torch.Tensor) -> torch.Tensor:
+        _need(lengths, torch.int32, "lengths")
+        n = lengths.numel()
+        out = torch.empty(n + 1, dtype=torch.int64, device=lengths.device)
+        nb = self._lib.tzk_lengths_to_offsets_workspace_bytes(n)
+        ws = self._workspace("scan", nb, lengths.device)
+        check(self._lib.tzk_lengths_to_offsets(_ptr(lengths), n, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+              "tzk_lengths_to_offsets")
+        return out
+
+    # ------------------------------------------------------------------ K4
+    def pooled_gather_fwd(self, weights: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor,
+                          offsets: torch.Tensor, B: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _need(weights, torch.float32, "weights")
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        F = lay.num_features
+        if offsets.numel() != F * B + 1:
+            raise TzkError(f"offsets has {offsets.numel()} entries, expected F*B+1 = {F * B + 1}")
+        if out is None:
+            out = torch.empty((B, lay.total_dim), dtype=torch.float32, device=weights.device)
+        out, ld = _rows2d(out, "out")
+        check(self._lib.tzk_pooled_gather_fwd(
+            _ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim), _ptr(lay.d_col),
+            _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, lay.max_dim, lay.vec_ok, _ptr(out), ld,
+            _stream()), "tzk_pooled_gather_fwd")
+        return out
+
+    def seq_gather_fwd(self, weights: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor,
+                       offsets: torch.Tensor, B: int) -> torch.Tensor:
+        _need(weights, torch.float32, "weights")
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        F = lay.num_features
+        D = lay.dim[0] if F else 1
+        if any(d != D for d in lay.dim):
+            raise TzkError("seq_gather_fwd: all features of an un-pooled collection must share one dim")
+        nnz = ids.numel()
+        out = torch.empty((nnz, D), dtype=torch.float32, device=weights.device)
+        check(self._lib.tzk_seq_gather_fwd(_ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(ids),
+                                           _ptr(offsets), F, B, D, nnz, _ptr(out), _stream()),
+              "tzk_seq_gather_fwd")
+        return out
+
+    # ------------------------------------------------------------------ K5
+    def fused_bwd(self, optimizer: int, pooled: bool, grad_out: torch.Tensor, weights: torch.Tensor,
+                  state: Optional[torch.Tensor], lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
+                  B: int, lr: float, eps: float, grad_scale: float = 1.0) -> None:
+        _need(weights, torch.float32, "weights")
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        grad_out, ld = _rows2d(grad_out, "grad_out")
+        if state is not None:
+            _need(state, torch.float32, "state")
+        F = lay.num_features
+        nnz = ids.numel()
+        nb = self._lib.tzk_fused_bwd_workspace_bytes(nnz, lay.total_keys)
+        ws = self._workspace("bwd", nb, weights.device)
+        check(self._lib.tzk_fused_bwd(
+            optimizer, int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
+            _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets), F, B, nnz,
+            lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
+            _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
+
+    # ------------------------------------------------------------------ K1 / K2
+    def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
+                     feat_block: torch.Tensor, want_pos: bool = False):
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        _need(feat_block, torch.int64, "feat_block")
+        dev = offsets.device
+        nnz = ids.numel()
+        out_lengths = torch.empty(W * F * B, dtype=torch.int32, device=dev)
+        out_offsets = torch.empty(W * F * B + 1, dtype=torch.int64, device=dev)
+        out_ids = torch.empty(nnz, dtype=torch.int64, device=dev)
+        out_pos = torch.empty(nnz, dtype=torch.int32, device=dev) if want_pos else None
+        nb = self._lib.tzk_bucketize_rw_workspace_bytes(F, B, W, nnz)
+        ws = self._workspace("bucketize", nb, dev)
+        check(self._lib.tzk_bucketize_rw(_ptr(ids), _ptr(offsets), F, B, W, _ptr(feat_block), nnz,
+                                         _ptr(out_lengths), _ptr(out_offsets), _ptr(out_ids), _ptr(out_pos),
+                                         _ptr(ws), ws.numel(), _stream()), "tzk_bucketize_rw")
+        return out_lengths, out_offsets, out_ids, out_pos
+
+    def permute_lengths(self, lengths: torch.Tensor, perm: torch.Tensor, B: int) -> torch.Tensor:
+        _need(lengths, torch.int32, "lengths")
+        _need(perm, torch.int32, "perm")
+        S = perm.numel()
+        out = torch.empty(S * B, dtype=torch.int32, device=lengths.device)
+        check(self._lib.tzk_permute_lengths(_ptr(lengths), _ptr(perm), S, B, _ptr(out), _stream()),
+              "tzk_permute_lengths")
+        return out
+
+    def permute_ids(self, ids: torch.Tensor, in_offsets: torch.Tensor, out_offsets: torch.Tensor,
+                    perm: torch.Tensor, B: int, out_nnz: int) -> torch.Tensor:
+        _need(ids, torch.int64, "ids")
+        _need(in_offsets, torch.int64, "in_offsets")
+        _need(out_offsets, torch.int64, "out_offsets")
+        _need(perm, torch.int32, "perm")
+        out = torch.empty(out_nnz, dtype=torch.int64, device=ids.device)
+        check(self._lib.tzk_permute_ids(_ptr(ids), _ptr(in_offsets), _ptr(out_offsets), _ptr(perm),
+                                        perm.numel(), B, _ptr(out), _stream()), "tzk_permute_ids")
+        return out
+
+    # ------------------------------------------------------------------ K6
+    def col_gather_sum(self, srcs: Sequence[torch.Tensor], plan: "ColPlan", rows: int,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lds = []
+        for i, s in enumerate(srcs):
+            s, ld = _rows2d(s, f"srcs[{i}]")
+            lds.append(ld)
+        dev = srcs[0].device
+        if out is None:
+            out = torch.empty((rows, plan.C), dtype=torch.float32, device=dev)
+        out, ld_out = _rows2d(out, "out")
+        # pointer table: tiny H2D copy from pinned-free python ints; one per call (graph-safe callers pre-bind)
+        ptrs = torch.tensor([s.data_ptr() for s in srcs], dtype=torch.int64, device=dev)
+        ldt = torch.tensor(lds, dtype=torch.int64, device=dev)
+        check(self._lib.tzk_col_gather_sum(_ptr(ptrs), _ptr(ldt), _ptr(plan.d_col_start), _ptr(plan.d_col_src),
+                                           _ptr(plan.d_col_srccol), plan.C, rows, _ptr(out), ld_out, _stream()),
+              "tzk_col_gather_sum")
+        return out
+
+    # ------------------------------------------------------------------ K7
+    def jagged_to_padded(self, values: torch.Tensor, offsets: torch.Tensor, T: int) -> torch.Tensor:
+        _need(values, torch.float32, "values")
+        _need(offsets, torch.int64, "offsets")
+        B = offsets.numel() - 1
+        D = values.shape[1]
+        out = torch.empty((B, T, D), dtype=torch.float32, device=values.device)
+        check(self._lib.tzk_jagged_to_padded(_ptr(values), _ptr(offsets), B, T, D, _ptr(out), _stream()),
+              "tzk_jagged_to_padded")
+        return out
+
+    def padded_to_jagged(self, grad_out: torch.Tensor, offsets: torch.Tensor, nnz: int) -> torch.Tensor:
+        _need(grad_out, torch.float32, "grad_out")
+        _need(offsets, torch.int64, "offsets")
+        B, T, D = grad_out.shape
+        out = torch.empty((nnz, D), dtype=torch.float32, device=grad_out.device)
+        check(self._lib.tzk_padded_to_jagged(_ptr(grad_out), _ptr(offsets), B, T, D, nnz, _ptr(out), _stream()),
+              "tzk_padded_to_jagged")
+        return out
+
+    # ------------------------------------------------------------------ A7
+    def fm_fwd(self, x: torch.Tensor, N: int, D: int) -> torch.Tensor:
+        x, ld = _rows2d(x, "x")
+        B = x.shape[0]
+        y = torch.empty((B, D), dtype=torch.float32, device=x.device)
+        check(self._lib.tzk_fm_fwd(_ptr(x), ld, B, N, D, _ptr(y), D, _stream()), "tzk_fm_fwd")
+        return y
+
+    def fm_bwd(self, x: torch.Tensor, dy: torch.Tensor, N: int, D: int) -> torch.Tensor:
+        x, ld = _rows2d(x, "x")
+        dy, ld_dy = _rows2d(dy, "dy")
+        B = x.shape[0]
+        dx = torch.empty((B, N * D), dtype=torch.float32, device=x.device)
+        check(self._lib.tzk_fm_bwd(_ptr(x), ld, _ptr(dy), ld_dy, B, N, D, _ptr(dx), N * D, _stream()),
+              "tzk_fm_bwd")
+        return dx
+
+    # ------------------------------------------------------------------ A9 / A10
+    def dot_interact_fwd(self, dense: Optional[torch.Tensor], sparse: torch.Tensor, Ns: int, D: int,
+                         copy_dense: bool, copy_sparse: bool) -> torch.Tensor:
+        sparse, ld_s = _rows2d(sparse, "sparse")
+        B = sparse.shape[0]
+        ld_d = 0
+        if dense is not None:
+            dense, ld_d = _rows2d(dense, "dense")
+        N = Ns + (dense is not None)
+        width = N * (N - 1) // 2 + (D if (copy_dense and dense is not None) else 0) + (Ns * D if copy_sparse else 0)
+        out = torch.empty((B, width), dtype=torch.float32, device=sparse.device)
+        check(self._lib.tzk_dot_interact_fwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, B, Ns, D, int(copy_dense),
+                                             int(copy_sparse), _ptr(out), width, _stream()),
+              "tzk_dot_interact_fwd")
+        return out
+
+    def dot_interact_bwd(self, dense: Optional[torch.Tensor], sparse: torch.Tensor, d_out: torch.Tensor,
+                         Ns: int, D: int, copy_dense: bool, copy_sparse: bool):
+        sparse, ld_s = _rows2d(sparse, "sparse")
+        d_out, ld_o = _rows2d(d_out, "d_out")
+        B = sparse.shape[0]
+        ld_d = 0
+        d_dense = None
+        if dense is not None:
+            dense, ld_d = _rows2d(dense, "dense")
+            d_dense = torch.empty((B, D), dtype=torch.float32, device=sparse.device)
+        d_sparse = torch.empty((B, Ns * D), dtype=torch.float32, device=sparse.device)
+        check(self._lib.tzk_dot_interact_bwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, _ptr(d_out), ld_o, B, Ns, D,
+                                             int(copy_dense), int(copy_sparse), _ptr(d_dense), D,
+                                             _ptr(d_sparse), Ns * D, _stream()), "tzk_dot_interact_bwd")
+        return d_dense, d_sparse
+
+
+@dataclass
+class ColPlan:
+    """CSR description of a column gather-sum (K6): column c of the destination sums
+    srcs[col_src[k]][:, col_srccol[k]] for k in [col_start[c], col_start[c+1])."""
+
+    col_start: List[int]
+    col_src: List[int]
+    col_srccol: List[int]
+    d_col_start: Optional[torch.Tensor] = None
+    d_col_src: Optional[torch.Tensor] = None
+    d_col_srccol: Optional[torch.Tensor] = None
+
+    @property
+    def C(self) -> int:
+        return len(self.col_start) - 1
+
+    def to(self, device) -> "ColPlan":
+        self.d_col_start = torch.tensor(self.col_start, dtype=torch.int32, device=device)
+        self.d_col_src = torch.tensor(self.col_src or [0], dtype=torch.int32, device=device)
+        self.d_col_srccol = torch.tensor(self.col_srccol or [0], dtype=torch.int32, device=device)
+        return self
+
+
+_default: Optional[CudaKernels] = None
+
+
+def default_kernels() -> CudaKernels:
+    global _default
+    if _default is None:
+        _default = CudaKernels()
+    return _default
