@@ -1,0 +1,327 @@
+"""bench.py — samples/sec of the DLRM-Criteo train step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one synthetic Criteo batch: KJT scan -> (bucketize + all-to-all at
+N>1) -> pooled gather -> DLRM dot interaction + dense towers -> BCE loss -> backward with the fused sparse
+Adagrad update -> dense Adam step.  fp32 everywhere (TF32 off, as the reference's default train.proto:14).
+Workload at N=1: BASELINE.json configs[1] (examples/dlrm_criteo.config, full hash sizes, row-wise, B=65536
+per rank) — it fits one GPU (12.2 GiB tables + 12.2 GiB Adagrad state).
+
+Prints ONE JSON line (see DESIGN.md §7 for every field).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "samples/sec (DLRM-Criteo synth, train step fwd+bwd+optimizer)"
+UNIT = "samples/s"
+ROW_BYTES_PER_SAMPLE = 26 * 16 * 4                       # 1664 B: SURVEY.md §8d "gather HBM GB/s" numerator
+GATHER_BYTES_PER_SAMPLE = 1664 + 1664 + 26 * 8 + 26 * 4   # rows + pooled write + ids + lengths = 3640 B
+BWD_BYTES_PER_SAMPLE = 1664 + 26 * 4 * 64 + 26 * 8        # grad read + w/state RMW (U=26) + ids = 8528 B
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-size", type=int, default=65536, help="per-rank batch (data_config.batch_size)")
+    ap.add_argument("--model", default="dlrm_criteo")
+    ap.add_argument("--id-dist", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--max-rows", type=int, default=0, help="cap every table (0 = full hash sizes)")
+    ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through the steps")
+    ap.add_argument("--cpu-batch", type=int, default=8192, help="samples per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0) -> None:
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 8 and r[4 + j] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the same step on host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_step_rate(model: str, batch: int, steps: int, warmup: int, max_rows: int, id_dist: str):
+    """Times the CPU restatement of the step (torch-CPU dense towers + oracle sparse path)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_backend import OracleKernels
+
+    from torcheasyrec_b200 import functional as Fn
+    from torcheasyrec_b200.engine import Pipeline
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pipe = Pipeline(model, device="cpu", max_rows=max_rows or None)
+    batches = [pipe.synthetic_batch(batch, seed=100 + i, id_dist=id_dist) for i in range(2)]
+    with Fn.use_backend(OracleKernels()):
+        for i in range(warmup):
+            pipe.eager_step(batches[i % 2])
+        t0 = time.perf_counter()
+        for i in range(steps):
+            pipe.eager_step(batches[i % 2])
+        dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores, OracleKernels.name
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import psutil
+
+    # full hash sizes need 2 x 12.2 GiB of host RAM (tables + Adagrad state); cap them if the box is small
+    max_rows = args.max_rows
+    note = "full hash sizes"
+    if not max_rows and psutil.virtual_memory().available < 40 * 2 ** 30:
+        max_rows, note = 4_000_000, "tables capped at 4M rows (host RAM < 40 GiB)"
+    steps = max(1, min(args.steps, 3))
+    rate, ms, cores, kind = cpu_step_rate(args.model, args.cpu_batch, steps, 1, max_rows, args.id_dist)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} (examples/{args.model}.config), {note}, Adagrad lr=1e-3 + Adam, "
+                               f"id_dist={args.id_dist}", "per_step_samples": args.cpu_batch},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of {args.cpu_batch} samples; oracle restatement "
+                                   "(torch-CPU dense towers + oracle/ sparse path); the reference's own path "
+                                   "needs torchrec/fbgemm wheels that are not installable offline"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def time_kernel(fn, iters: int):
+    """Average duration (ms) of `fn` launches, CUDA events on the launching (current) stream."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    torch.cuda.synchronize()
+    for i in range(iters):
+        ev[i][0].record()
+        fn(i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev) / iters
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from torcheasyrec_b200.engine import GraphedTrainStep, Pipeline
+    from torcheasyrec_b200.kernels import default_kernels
+
+    B, K, W = args.batch_size, args.steps, max(args.warmup, 3)
+    pipe = Pipeline(args.model, device=dev, max_rows=args.max_rows or None)
+    if world > 1:
+        from torcheasyrec_b200.distributed import shard_pipeline
+
+        shard_pipeline(pipe, "row_wise")
+    host = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + i, id_dist=args.id_dist).pin_memory()
+            for i in range(args.ring)]
+    ring = [hb.to(dev) for hb in host]
+    kern = default_kernels()
+    step = GraphedTrainStep(pipe, host[0], warmup=3)
+    launches_before = kern.launches
+    # count this step's own kernels once (eager replica of the captured step on the static inputs)
+    step._fresh_kjt_caches()
+    pipe.eager_step(step.static)
+    launches_per_step = kern.launches - launches_before
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM (device ring, D2D into the graph's static buffers) -----------------
+    for i in range(W):
+        step.load(ring[i % len(ring)])
+        step.replay()
+    barrier()
+    clocks = ClockSampler(local_rank).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step.load(ring[i % len(ring)])
+        step.replay()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    # ---- e2e: pinned host batch -> H2D -> step -> loss back on the host, every step --------------------------
+    for i in range(2):
+        step.load(host[i % len(host)])
+        step.replay()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    last = 0.0
+    for i in range(K):
+        step.load(host[i % len(host)], non_blocking=True)
+        loss = step.replay()
+        last = float(loss.item())          # device -> host read of the step's result
+    g1.record()
+    barrier()
+    ms_e2e = g0.elapsed_time(g1)
+    clk = clocks.stop() if clocks else None
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernels (rank 0, standalone launches on the same inputs) -----------------
+    ebc = pipe.model.sparse_collections()[0]
+    lay = ebc.layout
+    offs = [kern.lengths_to_offsets(b.sparse_features["__BASE__"].lengths()) for b in ring]
+    ids = [b.sparse_features["__BASE__"].values() for b in ring]
+    out = torch.empty((B, lay.total_dim), device=dev)
+    grad = torch.randn((B, lay.total_dim), device=dev) * 1e-3
+    R = len(ring)
+    it = max(K, 10)
+    fwd_ms = time_kernel(lambda i: kern.pooled_gather_fwd(ebc.weights.data, lay, ids[i % R], offs[i % R], B, out), it)
+    spec = ebc.optimizer
+    bwd_ms = time_kernel(lambda i: kern.fused_bwd(spec.kind, True, grad, ebc.weights.data, ebc.opt_state, lay,
+                                                  ids[i % R], offs[i % R], B, spec.lr, spec.eps, 1.0), it)
+    peak, peak_src = measured_peak_gbs()
+    fwd_gbs = GATHER_BYTES_PER_SAMPLE * B / (fwd_ms * 1e-3) / 1e9
+    bwd_gbs = BWD_BYTES_PER_SAMPLE * B / (bwd_ms * 1e-3) / 1e9
+    dominant = "tzk_fused_bwd (linearize + radix sort + run_update)" if bwd_ms > fwd_ms else "pooled_gather_fwd_kernel"
+    ach = bwd_gbs if bwd_ms > fwd_ms else fwd_gbs
+    roofline = {
+        "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "traffic": None, "peak_source": peak_src,
+        "kernels": {
+            "pooled_gather_fwd": {"ms": fwd_ms, "algorithmic_GBps": fwd_gbs, "frac": fwd_gbs / peak,
+                                  "row_read_GBps": ROW_BYTES_PER_SAMPLE * B / (fwd_ms * 1e-3) / 1e9,
+                                  "bytes_per_sample": GATHER_BYTES_PER_SAMPLE},
+            "fused_bwd_adagrad": {"ms": bwd_ms, "algorithmic_GBps": bwd_gbs, "frac": bwd_gbs / peak,
+                                  "bytes_per_sample": BWD_BYTES_PER_SAMPLE},
+        },
+        "share_of_step": {"pooled_gather_fwd": fwd_ms / (ms_total / K), "fused_bwd_adagrad": bwd_ms / (ms_total / K)},
+    }
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            steps_cpu = 2
+            cpu_rows = args.max_rows or (4_000_000 if _small_host() else 0)
+            rate, ms_cpu, cores, _ = cpu_step_rate(args.model, args.cpu_batch, steps_cpu, 1, cpu_rows, args.id_dist)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{steps_cpu} steps of {args.cpu_batch} samples of the same workload through the oracle "
+                             f"restatement ({ms_cpu:.0f} ms/step)"}
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    global_batch = B * world
+    h2d = host[0].nbytes()
+    line = {
+        "metric": METRIC, "value": global_batch * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model}: examples/{args.model}.config, "
+                               f"{'full hash sizes' if not args.max_rows else f'tables capped at {args.max_rows} rows'}, "
+                               f"row-wise over {world} rank(s), per-rank batch {B}, sparse Adagrad lr=1e-3 fused in "
+                               f"backward + dense Adam, ids {args.id_dist}",
+                   "global_batch": global_batch, "parallelism": f"rw{world}+dp{world}",
+                   "l2": f"inputs rotate over {len(ring)} distinct batches; tables 12.2 GiB + state 12.2 GiB >> 126 MB L2",
+                   "cuda_graph": True},
+        "e2e": {"value": global_batch * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last},
+        "gpu_launches": launches_per_step * K,
+        "gpu_launches_per_step": launches_per_step,
+        "clocks": clk,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _small_host() -> bool:
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available < 40 * 2 ** 30
+    except Exception:
+        return True
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1 and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

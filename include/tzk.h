@@ -133,10 +133,11 @@ int tzk_permute_ids(const int64_t* ids, const int64_t* in_offsets, const int64_t
  * Forward regroup: one call per feature group, every output column has exactly one contributor.
  * Backward: destination = grad of a source KeyedTensor, contributors = the grads of every group that
  * copied the column (a feature may sit in several groups, e.g. DeepFM `fm` and `deep`); columns nobody
- * read get 0.  srcs / src_ld are device arrays of device pointers / leading dims. */
-int tzk_col_gather_sum(const float* const* srcs, const int64_t* src_ld, const int32_t* col_start,
-                       const int32_t* col_src, const int32_t* col_srccol, int32_t C, int64_t rows,
-                       float* out, int64_t ld_out, tzk_stream_t stream);
+ * read get 0.  srcs_host / src_ld_host are HOST arrays (n_src <= 16) of device pointers / leading dims:
+ * they travel as kernel parameters, so the call stays CUDA-graph capturable. */
+int tzk_col_gather_sum(const float* const* srcs_host, const int64_t* src_ld_host, int32_t n_src,
+                       const int32_t* col_start, const int32_t* col_src, const int32_t* col_srccol,
+                       int32_t C, int64_t rows, float* out, int64_t ld_out, tzk_stream_t stream);
 
 /* ---- K7: jagged -> padded dense and back  ([EXT] fbgemm::jagged_to_padded_dense via
  * JaggedTensor.to_padded_dense, tzrec/modules/embedding.py:1429,1480; App. A.14) ----------------------

@@ -1,0 +1,109 @@
+"""Checker backend: the CudaKernels method set implemented with the CPU oracle (numpy).
+
+TEST INFRASTRUCTURE.  Lets tests drive the package's HOST logic (EmbeddingGroup, regroup plans, sharding /
+all-to-all plumbing under gloo) on a box without a GPU, and gives -m gpu tests an independent model-level
+reference.  Never imported by torcheasyrec_b200 itself.
+"""
+import numpy as np
+import torch
+
+from oracle import tzk_oracle as O
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def _tables(weights, lay):
+    """Views of the arena (shared memory with the torch tensor) as per-table arrays, one per feature slot."""
+    arr = weights.detach().numpy() if not weights.is_cuda else None
+    assert arr is not None, "oracle backend works on CPU tensors"
+    tabs, feat_table, seen = [], [], {}
+    for f in range(lay.num_features):
+        key = lay.w_off[f]
+        if key not in seen:
+            seen[key] = len(tabs)
+            tabs.append(arr[key:key + lay.rows[f] * lay.dim[f]].reshape(lay.rows[f], lay.dim[f]))
+        feat_table.append(seen[key])
+    return tabs, feat_table
+
+
+class OracleKernels:
+    name = "oracle"
+
+    def lengths_to_offsets(self, lengths):
+        return torch.from_numpy(O.lengths_to_offsets(_np(lengths)))
+
+    def pooled_gather_fwd(self, weights, lay, ids, offsets, B, out=None):
+        tabs, ft = _tables(weights, lay)
+        res = torch.from_numpy(O.pooled_lookup(tabs, ft, lay.pool, _np(ids), _np(offsets), B))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def seq_gather_fwd(self, weights, lay, ids, offsets, B):
+        tabs, ft = _tables(weights, lay)
+        return torch.from_numpy(O.seq_lookup(tabs, ft, _np(ids), _np(offsets), B))
+
+    def fused_bwd(self, optimizer, pooled, grad_out, weights, state, lay, ids, offsets, B, lr, eps, grad_scale=1.0):
+        tabs, ft = _tables(weights, lay)
+        states = [None] * len(tabs)
+        if state is not None:
+            sarr = state.numpy()
+            for f in range(lay.num_features):
+                t = ft[f]
+                if states[t] is None:
+                    if optimizer == O.OPT_ADAGRAD:
+                        states[t] = sarr[lay.w_off[f]:lay.w_off[f] + lay.rows[f] * lay.dim[f]].reshape(lay.rows[f], lay.dim[f])
+                    else:
+                        states[t] = sarr[lay.key_base[f]:lay.key_base[f] + lay.rows[f]]
+        O.fused_update(optimizer, tabs, states, ft, lay.pool, _np(ids), _np(offsets), B, _np(grad_out), lr, eps,
+                       grad_scale, pooled=bool(pooled))
+
+    def bucketize_rw(self, ids, offsets, F, B, W, feat_block, want_pos=False):
+        ol, oo, oi, op = O.bucketize_rw(_np(ids), _np(offsets), F, B, W, _np(feat_block).tolist())
+        return (torch.from_numpy(ol), torch.from_numpy(oo), torch.from_numpy(oi),
+                torch.from_numpy(op) if want_pos else None)
+
+    def permute_lengths(self, lengths, perm, B):
+        l = _np(lengths)
+        p = _np(perm)
+        return torch.from_numpy(np.concatenate([l[i * B:(i + 1) * B] for i in p]).astype(np.int32)
+                                if len(p) else l[:0])
+
+    def permute_ids(self, ids, in_offsets, out_offsets, perm, B, out_nnz):
+        i, off, p = _np(ids), _np(in_offsets), _np(perm)
+        parts = [i[off[k * B]:off[(k + 1) * B]] for k in p]
+        return torch.from_numpy(np.concatenate(parts).astype(np.int64) if parts else i[:0])
+
+    def col_gather_sum(self, srcs, plan, rows, out=None):
+        res = np.zeros((rows, plan.C), dtype=np.float32)
+        arrs = [_np(s) for s in srcs]
+        for c in range(plan.C):
+            for k in range(plan.col_start[c], plan.col_start[c + 1]):
+                res[:, c] += arrs[plan.col_src[k]][:, plan.col_srccol[k]]
+        res = torch.from_numpy(res)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def jagged_to_padded(self, values, offsets, T):
+        return torch.from_numpy(O.to_padded_dense(_np(values), _np(offsets), T))
+
+    def padded_to_jagged(self, grad_out, offsets, nnz):
+        return torch.from_numpy(O.padded_to_jagged(_np(grad_out), _np(offsets), nnz))
+
+    def fm_fwd(self, x, N, D):
+        return torch.from_numpy(O.fm(_np(x).reshape(-1, N, D)))
+
+    def fm_bwd(self, x, dy, N, D):
+        return torch.from_numpy(O.fm_bwd(_np(x).reshape(-1, N, D), _np(dy)).reshape(-1, N * D))
+
+    def dot_interact_fwd(self, dense, sparse, Ns, D, copy_dense, copy_sparse):
+        return torch.from_numpy(O.dlrm_interact(_np(dense), _np(sparse), Ns, D, copy_dense, copy_sparse))
+
+    def dot_interact_bwd(self, dense, sparse, d_out, Ns, D, copy_dense, copy_sparse):
+        dd, ds = O.dlrm_interact_bwd(_np(dense), _np(sparse), _np(d_out), Ns, D, copy_dense, copy_sparse)
+        return (None if dd is None else torch.from_numpy(dd)), torch.from_numpy(ds)

@@ -136,6 +136,10 @@ def test_fused_bwd(kernels, case, opt, pool):
     else:
         st_np, state = [None] * len(tables), None
     two_steps = 2
+    # Runs longer than 32 contributions are summed as 64 strided partials + a fixed tree (fbgemm's long-row
+    # path is a tree too), the oracle adds sequentially: with ~700 cancelling terms per row both are ~1e-5
+    # from the exact sum, and the accumulator s += g*g doubles the relative gap.  Weights stay within 1e-5.
+    state_rtol = 3e-4 if case == "tiny_tables_long_runs" else 2e-5
     want = [t.copy() for t in tables]
     for _ in range(two_steps):  # second step exercises the updated state
         kernels.fused_bwd(opt, True, cu(grad), arena, state, lay, cu(ids), cu(offsets), B, lr, eps, gs)
@@ -146,9 +150,9 @@ def test_fused_bwd(kernels, case, opt, pool):
     if opt == O.OPT_ADAGRAD:
         gs_ = split_arena(state.cpu().numpy(), lay, tables, feat_table)
         for t in range(len(tables)):
-            np.testing.assert_allclose(gs_[t], st_np[t], rtol=2e-5, atol=1e-7)
+            np.testing.assert_allclose(gs_[t], st_np[t], rtol=state_rtol, atol=1e-7)
     if opt == O.OPT_ROWWISE_ADAGRAD:
-        np.testing.assert_allclose(state.cpu().numpy(), np.concatenate(st_np), rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(state.cpu().numpy(), np.concatenate(st_np), rtol=state_rtol, atol=1e-7)
 
 
 def test_fused_bwd_is_run_to_run_deterministic(kernels):

@@ -38,7 +38,7 @@ SIGNATURES = {
     ),
     "tzk_permute_lengths": (c_int32, [P, P, c_int32, c_int32, P, P]),
     "tzk_permute_ids": (c_int32, [P, P, P, P, c_int32, c_int32, P, P]),
-    "tzk_col_gather_sum": (c_int32, [P, P, P, P, P, c_int32, c_int64, P, c_int64, P]),
+    "tzk_col_gather_sum": (c_int32, [P, P, c_int32, P, P, P, c_int32, c_int64, P, c_int64, P]),
     "tzk_jagged_to_padded": (c_int32, [P, P, c_int32, c_int32, c_int32, P, P]),
     "tzk_padded_to_jagged": (c_int32, [P, P, c_int32, c_int32, c_int32, c_int64, P, P]),
     "tzk_fm_fwd": (c_int32, [P, c_int64, c_int64, c_int32, c_int32, P, c_int64, P]),

@@ -11,9 +11,14 @@ constexpr int kThreads = 256;
 // ---------------------------------------------------------------------------------------------------
 // K6: out[row, c] = sum_{k in [col_start[c], col_start[c+1])} srcs[col_src[k]][row*ld + col_srccol[k]]
 // ---------------------------------------------------------------------------------------------------
+constexpr int kMaxSrc = 16;
+struct SrcTable {  // passed by value: no device-side pointer table, so the call is CUDA-graph safe
+  const float* p[kMaxSrc];
+  int64_t ld[kMaxSrc];
+};
+
 __global__ void __launch_bounds__(kThreads)
-col_gather_sum_kernel(const float* const* __restrict__ srcs, const int64_t* __restrict__ src_ld,
-                      const int32_t* __restrict__ col_start, const int32_t* __restrict__ col_src,
+col_gather_sum_kernel(const SrcTable srcs, const int32_t* __restrict__ col_start, const int32_t* __restrict__ col_src,
                       const int32_t* __restrict__ col_srccol, int C, int64_t rows, float* __restrict__ out,
                       int64_t ld_out) {
   const int64_t n = rows * C;
@@ -25,7 +30,7 @@ col_gather_sum_kernel(const float* const* __restrict__ srcs, const int64_t* __re
     float acc = 0.f;
     for (int k = k0; k < k1; ++k) {
       const int s = __ldg(col_src + k);
-      acc += __ldg(srcs[s] + row * __ldg(src_ld + s) + __ldg(col_srccol + k));
+      acc += __ldg(srcs.p[s] + row * srcs.ld[s] + __ldg(col_srccol + k));
     }
     out[row * ld_out + c] = acc;
   }
@@ -319,14 +324,21 @@ inline int grid_for(int64_t n, int per_block, int max_blocks) {
 }
 }  // namespace
 
-extern "C" int tzk_col_gather_sum(const float* const* srcs, const int64_t* src_ld, const int32_t* col_start,
-                                  const int32_t* col_src, const int32_t* col_srccol, int32_t C, int64_t rows,
-                                  float* out, int64_t ld_out, tzk_stream_t stream) {
+extern "C" int tzk_col_gather_sum(const float* const* srcs_host, const int64_t* src_ld_host, int32_t n_src,
+                                  const int32_t* col_start, const int32_t* col_src, const int32_t* col_srccol,
+                                  int32_t C, int64_t rows, float* out, int64_t ld_out, tzk_stream_t stream) {
   TZK_REQUIRE(C >= 0 && rows >= 0, "col_gather_sum: negative size");
   if (C == 0 || rows == 0) return 0;
-  TZK_REQUIRE(srcs && src_ld && col_start && col_src && col_srccol && out, "col_gather_sum: NULL argument");
+  TZK_REQUIRE(srcs_host && src_ld_host && col_start && col_src && col_srccol && out,
+              "col_gather_sum: NULL argument");
+  TZK_REQUIRE(n_src >= 1 && n_src <= kMaxSrc, "col_gather_sum: n_src=%d out of range [1,%d]", n_src, kMaxSrc);
+  SrcTable srcs;
+  for (int i = 0; i < kMaxSrc; ++i) {
+    srcs.p[i] = i < n_src ? srcs_host[i] : nullptr;
+    srcs.ld[i] = i < n_src ? src_ld_host[i] : 0;
+  }
   col_gather_sum_kernel<<<grid_for(rows * C, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(
-      srcs, src_ld, col_start, col_src, col_srccol, C, rows, out, ld_out);
+      srcs, col_start, col_src, col_srccol, C, rows, out, ld_out);
   TZK_CHECK_LAUNCH("col_gather_sum_kernel");
   return 0;
 }

@@ -1,0 +1,304 @@
+"""EmbeddingBagCollection / EmbeddingCollection with HBM-resident shard arenas and a fused backward.
+
+This is the module object the reference builds at tzrec/modules/embedding.py:855 (EBC) and :1195 (EC) and
+calls with one KeyedJaggedTensor at :930 / :1301.  In the reference these classes come from torchrec
+([EXT] torchrec.modules.embedding_modules / embedding_configs) and the arithmetic from fbgemm TBE; here the
+tables of a collection live back to back in ONE fp32 arena per rank, the forward is the tzk pooled / sequence
+gather, and the backward applies the sparse optimizer in place (the reference installs the same behaviour
+with apply_optimizer_in_backward, tzrec/main.py:774-781) — no dense gradient is ever materialised.
+"""
+
+import math
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from .kernels import OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_SGD, POOL_MEAN, POOL_SUM, FeatureLayout, build_layout
+from .sparse import JaggedTensor, KeyedJaggedTensor, KeyedTensor
+
+
+class PoolingType(Enum):
+    SUM = "SUM"
+    MEAN = "MEAN"
+    NONE = "NONE"
+
+
+class DataType(Enum):
+    FP32 = "FP32"
+    FP16 = "FP16"
+
+
+@dataclass
+class BaseEmbeddingConfig:
+    num_embeddings: int
+    embedding_dim: int
+    name: str = ""
+    data_type: DataType = DataType.FP32
+    feature_names: List[str] = field(default_factory=list)
+    init_fn: Optional[Callable[[torch.Tensor], Optional[torch.Tensor]]] = None
+
+    def get_weight_init_max(self) -> float:
+        return math.sqrt(1.0 / self.num_embeddings)
+
+
+@dataclass
+class EmbeddingBagConfig(BaseEmbeddingConfig):
+    pooling: PoolingType = PoolingType.SUM
+
+
+@dataclass
+class EmbeddingConfig(BaseEmbeddingConfig):
+    pass
+
+
+@dataclass
+class SparseOptimizerSpec:
+    """What tzrec/optim/optimizer_builder.py:30-97 hands to apply_optimizer_in_backward."""
+
+    kind: int = OPT_ADAGRAD
+    lr: float = 0.001
+    eps: float = 1e-8                      # fbgemm TBE default (App. A.10)
+    initial_accumulator_value: float = 0.0  # optimizer_builder.py:57-61
+
+    @staticmethod
+    def from_name(name: str, **kw) -> "SparseOptimizerSpec":
+        kinds = {"sgd": OPT_SGD, "adagrad": OPT_ADAGRAD, "rowwise_adagrad": OPT_ROWWISE_ADAGRAD,
+                 "row_wise_adagrad": OPT_ROWWISE_ADAGRAD}
+        return SparseOptimizerSpec(kind=kinds[name.lower()], **kw)
+
+
+def _default_init(cfg: BaseEmbeddingConfig, w: torch.Tensor) -> None:
+    # [EXT] torchrec default init_fn: uniform(-1/sqrt(N), +1/sqrt(N))  (App. A.4)
+    bound = cfg.get_weight_init_max()
+    w.uniform_(-bound, bound)
+
+
+class _TableView(nn.Module):
+    """`embedding_bags.<table>.weight` / `embeddings.<table>.weight` handle (a view into the arena)."""
+
+    def __init__(self, owner: "_ArenaCollection", t: int) -> None:
+        super().__init__()
+        self._owner = [owner]
+        self._t = t
+
+    @property
+    def weight(self) -> torch.Tensor:
+        return self._owner[0].table_weight(self._t)
+
+
+class _ArenaCollection(nn.Module):
+    """Shared machinery: arena, layout, optimizer state, key mapping."""
+
+    _pooled = True
+
+    def __init__(self, tables: Sequence[BaseEmbeddingConfig], device=None, local_rows: Optional[Sequence[int]] = None):
+        super().__init__()
+        self._configs = list(tables)
+        names = [c.name for c in self._configs]
+        assert len(set(names)) == len(names), f"duplicate table names {names}"
+        self._device = torch.device(device) if device is not None else torch.device("cpu")
+        # output keys: a feature served by >1 table of this collection is emitted as feat@table (App. A.2)
+        count: Dict[str, int] = {}
+        for c in self._configs:
+            for f in c.feature_names:
+                count[f] = count.get(f, 0) + 1
+        self._feature_names: List[str] = []     # KJT key consumed by each slot
+        self._embedding_names: List[str] = []   # output key of each slot
+        self._names_by_table: List[List[str]] = []
+        feat_table, feat_pool = [], []
+        for t, c in enumerate(self._configs):
+            per = []
+            for f in c.feature_names:
+                self._feature_names.append(f)
+                per.append(f + "@" + c.name if count[f] > 1 else f)
+                feat_table.append(t)
+                pool = getattr(c, "pooling", PoolingType.SUM)
+                feat_pool.append(POOL_MEAN if pool == PoolingType.MEAN else POOL_SUM)
+            self._embedding_names.extend(per)
+            self._names_by_table.append(per)
+        self._feat_table = feat_table
+        rows = list(local_rows) if local_rows is not None else [c.num_embeddings for c in self._configs]
+        self._table_rows = rows
+        self._table_dim = [c.embedding_dim for c in self._configs]
+        self.layout: FeatureLayout = build_layout(rows, self._table_dim, feat_table, feat_pool)
+        self._table_off, self._table_key = {}, {}
+        for f, t in enumerate(feat_table):
+            self._table_off[t] = self.layout.w_off[f]
+            self._table_key[t] = self.layout.key_base[f]
+        self.weights = nn.Parameter(torch.empty(self.layout.arena_elems, dtype=torch.float32, device=self._device),
+                                    requires_grad=False)
+        self._opt: Optional[SparseOptimizerSpec] = None
+        self.register_buffer("opt_state", None, persistent=False)
+        self._hook = None
+        self.grad_scale = 1.0  # sharded wrappers set 1/W here (App. A.6)
+        if self._device.type != "meta":
+            self.reset_parameters()
+            self.layout.to(self._device)
+
+    # ---- parameters -----------------------------------------------------------------------------------
+    def reset_parameters(self) -> None:
+        with torch.no_grad():
+            for t, c in enumerate(self._configs):
+                if t not in self._table_off:
+                    continue
+                w = self.table_weight(t)
+                if w.numel() == 0:
+                    continue
+                (c.init_fn or (lambda x, c=c: _default_init(c, x)))(w)
+
+    def table_weight(self, t: int) -> torch.Tensor:
+        o = self._table_off[t]
+        return self.weights.data[o:o + self._table_rows[t] * self._table_dim[t]].view(self._table_rows[t],
+                                                                                       self._table_dim[t])
+
+    def table_state(self, t: int) -> Optional[torch.Tensor]:
+        if self.opt_state is None:
+            return None
+        if self._opt.kind == OPT_ADAGRAD:
+            o = self._table_off[t]
+            return self.opt_state[o:o + self._table_rows[t] * self._table_dim[t]].view(self._table_rows[t], -1)
+        k = self._table_key[t]
+        return self.opt_state[k:k + self._table_rows[t]]
+
+    def set_table_weight(self, t: int, w: torch.Tensor) -> None:
+        with torch.no_grad():
+            self.table_weight(t).copy_(w)
+
+    # ---- fused optimizer ------------------------------------------------------------------------------
+    def set_optimizer(self, spec: SparseOptimizerSpec) -> None:
+        """apply_optimizer_in_backward equivalent (tzrec/main.py:774-781)."""
+        self._opt = spec
+        dev = self.weights.device
+        if spec.kind == OPT_ADAGRAD:
+            self.opt_state = torch.full((self.layout.arena_elems,), spec.initial_accumulator_value,
+                                        dtype=torch.float32, device=dev)
+        elif spec.kind == OPT_ROWWISE_ADAGRAD:
+            self.opt_state = torch.full((self.layout.total_keys,), spec.initial_accumulator_value,
+                                        dtype=torch.float32, device=dev)
+        else:
+            self.opt_state = None
+
+    @property
+    def optimizer(self) -> Optional[SparseOptimizerSpec]:
+        return self._opt
+
+    # ---- introspection used by tzrec (models/model.py:162-201, embedding.py:670-671) --------------------
+    def embedding_names_by_table(self) -> List[List[str]]:
+        return self._names_by_table
+
+    def feature_names(self) -> List[str]:
+        return self._feature_names
+
+    def _hook_tensor(self) -> torch.Tensor:
+        # autograd needs one differentiable input to schedule the fused backward
+        if self._hook is None or self._hook.device != self.weights.device:
+            self._hook = torch.zeros(1, device=self.weights.device, requires_grad=True)
+        return self._hook
+
+    def _select(self, kjt: KeyedJaggedTensor) -> KeyedJaggedTensor:
+        """Bring the KJT into this collection's slot order (identity when it already is)."""
+        keys = kjt.keys()
+        if keys == self._feature_names:
+            return kjt
+        pos = {k: i for i, k in enumerate(keys)}
+        return kjt.permute([pos[f] for f in self._feature_names])
+
+
+class _PooledLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hook, mod, ids, offsets, B):
+        out = Fn.backend().pooled_gather_fwd(mod.weights.data, mod.layout, ids, offsets, B)
+        ctx.mod, ctx.B = mod, B
+        ctx.save_for_backward(ids, offsets)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mod = ctx.mod
+        ids, offsets = ctx.saved_tensors
+        spec = mod.optimizer
+        if spec is None:
+            raise RuntimeError("EmbeddingBagCollection.backward: no sparse optimizer set (call set_optimizer); "
+                               "tables are updated inside the backward kernel like the reference's fused TBE")
+        if ids.numel():
+            Fn.backend().fused_bwd(spec.kind, True, Fn._rows_contig(grad_out), mod.weights.data, mod.opt_state,
+                                   mod.layout, ids, offsets, ctx.B, spec.lr, spec.eps, mod.grad_scale)
+        return None, None, None, None, None
+
+
+class _SeqLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hook, mod, ids, offsets, B):
+        out = Fn.backend().seq_gather_fwd(mod.weights.data, mod.layout, ids, offsets, B)
+        ctx.mod, ctx.B = mod, B
+        ctx.save_for_backward(ids, offsets)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mod = ctx.mod
+        ids, offsets = ctx.saved_tensors
+        spec = mod.optimizer
+        if spec is None:
+            raise RuntimeError("EmbeddingCollection.backward: no sparse optimizer set (call set_optimizer)")
+        if ids.numel():
+            Fn.backend().fused_bwd(spec.kind, False, grad_out.contiguous(), mod.weights.data, mod.opt_state,
+                                   mod.layout, ids, offsets, ctx.B, spec.lr, spec.eps, mod.grad_scale)
+        return None, None, None, None, None
+
+
+class EmbeddingBagCollection(_ArenaCollection):
+    """Pooled lookup: forward(KJT) -> KeyedTensor [B, sum_t sum_f D_t]  (embedding.py:855,930; App. A.2/A.3)."""
+
+    def __init__(self, tables: Sequence[EmbeddingBagConfig], device=None, local_rows=None) -> None:
+        super().__init__(tables, device, local_rows)
+        self.embedding_bags = nn.ModuleDict({c.name: _TableView(self, t) for t, c in enumerate(self._configs)})
+        self._lengths_per_key = [self._table_dim[t] for t in self._feat_table]
+
+    def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
+        return self._configs
+
+    def pooled_values(self, kjt: KeyedJaggedTensor) -> torch.Tensor:
+        kjt = self._select(kjt)
+        B = kjt.stride()
+        hook = self._hook_tensor() if torch.is_grad_enabled() else None
+        return _PooledLookup.apply(hook, self, kjt.values(), kjt.offsets(), B)
+
+    def forward(self, features: KeyedJaggedTensor) -> KeyedTensor:
+        return KeyedTensor(self._embedding_names, self._lengths_per_key, self.pooled_values(features))
+
+
+class EmbeddingCollection(_ArenaCollection):
+    """Un-pooled lookup: forward(KJT) -> {key: JaggedTensor([sum len, D], lengths[B])} (embedding.py:1195,1301)."""
+
+    _pooled = False
+
+    def __init__(self, tables: Sequence[EmbeddingConfig], device=None, local_rows=None) -> None:
+        super().__init__(tables, device, local_rows)
+        dims = set(self._table_dim)
+        assert len(dims) <= 1, f"EmbeddingCollection tables must share one embedding_dim, got {dims}"
+        self._dim = self._table_dim[0] if self._table_dim else 0
+        self.embeddings = nn.ModuleDict({c.name: _TableView(self, t) for t, c in enumerate(self._configs)})
+
+    def embedding_configs(self) -> List[EmbeddingConfig]:
+        return self._configs
+
+    def embedding_dim(self) -> int:
+        return self._dim
+
+    def forward(self, features: KeyedJaggedTensor) -> Dict[str, JaggedTensor]:
+        kjt = self._select(features)
+        B = kjt.stride()
+        hook = self._hook_tensor() if torch.is_grad_enabled() else None
+        rows = _SeqLookup.apply(hook, self, kjt.values(), kjt.offsets(), B)
+        lpk = kjt.length_per_key()
+        lengths = kjt.lengths()
+        out, s = {}, 0
+        for f, key in enumerate(self._embedding_names):
+            out[key] = JaggedTensor(rows[s:s + lpk[f]], lengths=lengths[f * B:(f + 1) * B])
+            s += lpk[f]
+        return out

@@ -1,0 +1,139 @@
+"""Step driver: builds a model from a tzrec pipeline config and runs train steps on one B200.
+
+Replaces the part of tzrec/main.py that surrounds the hot path (model construction :763-781, optimizers
+:814-876, the step loop :519-547) and torchrec's TrainPipelineSparseDist (tzrec/utils/dist_util.py:221-303)
+with a B200-first design: the whole step (KJT scan, gather, interaction, dense towers, loss, backward incl.
+the fused sparse update, dense optimizer) is captured ONCE in a CUDA graph over static device buffers and
+replayed; a side stream stages the next host batch (pinned H2D) while the current graph runs.
+Variable-shape workloads (sequence features) run the same code eagerly.
+"""
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from .batch import Batch, synthetic_batch
+from .config import Message, edit_config, load_pipeline_config
+from .features import BaseFeature, create_features
+from .rank_models import (RankModel, TrainWrapper, create_model, dense_optimizer_from_config,
+                          sparse_optimizer_from_config)
+from .sparse import KeyedJaggedTensor, KeyedTensor
+
+
+def override_num_buckets(cfg: Message, cap: int) -> None:
+    """`num_buckets -> cap` for every id feature (BASELINE.json configs[0]: "1k-row tables")."""
+    def fix(sub):
+        for fld in ("num_buckets", "hash_bucket_size"):
+            if sub._spec(fld) is not None and sub.HasField(fld):
+                setattr(sub, fld, min(getattr(sub, fld), cap))
+    for fc in cfg.feature_configs:
+        kind = fc.WhichOneof("feature")
+        sub = getattr(fc, kind)
+        if sub._type == "SequenceFeature":
+            for s in sub.features:
+                fix(getattr(s, s.WhichOneof("feature")))
+        else:
+            fix(sub)
+
+
+class Pipeline:
+    """Everything needed to step one model: config, features, model, optimizers."""
+
+    def __init__(self, config: str, device="cuda", max_rows: Optional[int] = None,
+                 edits: Optional[Dict[str, Any]] = None, seed: int = 1234, capturable: bool = True) -> None:
+        """`config`: path of a pipeline .config/.json, or the name of a built-in example
+        (example_configs.GENERATORS: dlrm_criteo, deepfm_criteo, mmoe_taobao, multi_tower_din_taobao)."""
+        from . import example_configs
+        from .config import parse_text
+
+        if config in example_configs.GENERATORS:
+            self.cfg = parse_text(example_configs.GENERATORS[config]())
+        else:
+            self.cfg = load_pipeline_config(config)
+        if edits:
+            edit_config(self.cfg, edits)
+        if max_rows:
+            override_num_buckets(self.cfg, max_rows)
+        self.device = torch.device(device)
+        self.features: List[BaseFeature] = create_features(list(self.cfg.feature_configs),
+                                                           fg_mode=self.cfg.data_config.fg_mode)
+        self.labels = list(self.cfg.data_config.label_fields)
+        torch.manual_seed(seed)
+        self.model: RankModel = create_model(self.cfg.model_config, self.features, self.labels, device=self.device)
+        self.model.to(self.device)
+        self.model.set_sparse_optimizer(sparse_optimizer_from_config(self.cfg.train_config))
+        kw = {}
+        if self.device.type == "cuda" and capturable:
+            kw = dict(capturable=True, fused=True)
+        self.dense_optimizer = dense_optimizer_from_config(self.cfg.train_config, self.model.dense_parameters(), **kw)
+        self.train_wrapper = TrainWrapper(self.model)
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.train_config.cuda_matmul_allow_tf32)
+
+    def synthetic_batch(self, batch_size: int, seed: int = 0, id_dist: str = "uniform") -> Batch:
+        b = synthetic_batch(self.features, batch_size, self.labels, seed=seed, id_dist=id_dist)
+        for kjt in b.sparse_features.values():
+            kjt.length_per_key()  # host-side, before the copy: keeps the device path free of syncs
+        return b
+
+    def eager_step(self, batch: Batch) -> torch.Tensor:
+        self.dense_optimizer.zero_grad(set_to_none=True)
+        loss, _ = self.train_wrapper(batch)
+        loss.backward()
+        self.dense_optimizer.step()
+        return loss.detach()
+
+
+def _tensors_of(batch: Batch) -> List[torch.Tensor]:
+    out = []
+    for k in sorted(batch.sparse_features):
+        kjt = batch.sparse_features[k]
+        out += [kjt.values(), kjt.lengths()]
+    for k in sorted(batch.dense_features):
+        out.append(batch.dense_features[k].values())
+    for k in sorted(batch.labels):
+        out.append(batch.labels[k])
+    return out
+
+
+class GraphedTrainStep:
+    """One CUDA graph per (model, batch shape).  `load()` refreshes the static inputs, `replay()` runs a step."""
+
+    def __init__(self, pipe: Pipeline, example: Batch, warmup: int = 3) -> None:
+        assert pipe.device.type == "cuda"
+        self.pipe = pipe
+        self.static = example.to(pipe.device)
+        for k, kjt in example.sparse_features.items():
+            self.static.sparse_features[k]._length_per_key = kjt._length_per_key
+        self._static_tensors = _tensors_of(self.static)
+        self.copy_stream = torch.cuda.Stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._fresh_kjt_caches()
+                pipe.eager_step(self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        pipe.dense_optimizer.zero_grad(set_to_none=True)
+        self._fresh_kjt_caches()
+        with torch.cuda.graph(self.graph):
+            loss, _ = pipe.train_wrapper(self.static)
+            loss.backward()
+            pipe.dense_optimizer.step()
+            self.loss = loss.detach()
+        torch.cuda.synchronize()
+
+    def _fresh_kjt_caches(self) -> None:
+        # offsets are derived data: recompute them from the (possibly refreshed) lengths inside every step
+        for kjt in self.static.sparse_features.values():
+            kjt._offsets = None
+
+    def load(self, batch: Batch, non_blocking: bool = True) -> None:
+        """Copies a batch (host pinned or device) into the static buffers on the current stream."""
+        for dst, src in zip(self._static_tensors, _tensors_of(batch)):
+            dst.copy_(src, non_blocking=non_blocking)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss

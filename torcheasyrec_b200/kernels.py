@@ -6,7 +6,8 @@ CUDA stream across the ABI, and raises `TzkError` on any failure.  There is deli
 implementation here: host-logic tests inject their own checker backend (tests/oracle_backend.py).
 """
 
-from dataclasses import dataclass, field
+import ctypes
+from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -126,6 +127,7 @@ class CudaKernels:
     def __init__(self) -> None:
         self._lib = lib()
         self._ws = {}
+        self.launches = 0  # hand-written tzk kernels enqueued so far (CUB's sort kernels are not counted)
 
     # ------------------------------------------------------------------ workspace cache
     def _workspace(self, key, nbytes: int, device) -> torch.Tensor:
@@ -144,6 +146,7 @@ class CudaKernels:
         ws = self._workspace("scan", nb, lengths.device)
         check(self._lib.tzk_lengths_to_offsets(_ptr(lengths), n, _ptr(out), _ptr(ws), ws.numel(), _stream()),
               "tzk_lengths_to_offsets")
+        self.launches += 3 if n else 1
         return out
 
     # ------------------------------------------------------------------ K4
@@ -162,6 +165,7 @@ class CudaKernels:
             _ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim), _ptr(lay.d_col),
             _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, lay.max_dim, lay.vec_ok, _ptr(out), ld,
             _stream()), "tzk_pooled_gather_fwd")
+        self.launches += 1
         return out
 
     def seq_gather_fwd(self, weights: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor,
@@ -178,6 +182,7 @@ class CudaKernels:
         check(self._lib.tzk_seq_gather_fwd(_ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(ids),
                                            _ptr(offsets), F, B, D, nnz, _ptr(out), _stream()),
               "tzk_seq_gather_fwd")
+        self.launches += 1
         return out
 
     # ------------------------------------------------------------------ K5
@@ -199,6 +204,7 @@ class CudaKernels:
             _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets), F, B, nnz,
             lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
             _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
+        self.launches += 4  # zero_counter, linearize, run_update, long_run_update (+ CUB radix sort)
 
     # ------------------------------------------------------------------ K1 / K2
     def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
@@ -217,6 +223,7 @@ class CudaKernels:
         check(self._lib.tzk_bucketize_rw(_ptr(ids), _ptr(offsets), F, B, W, _ptr(feat_block), nnz,
                                          _ptr(out_lengths), _ptr(out_offsets), _ptr(out_ids), _ptr(out_pos),
                                          _ptr(ws), ws.numel(), _stream()), "tzk_bucketize_rw")
+        self.launches += 5
         return out_lengths, out_offsets, out_ids, out_pos
 
     def permute_lengths(self, lengths: torch.Tensor, perm: torch.Tensor, B: int) -> torch.Tensor:
@@ -226,6 +233,7 @@ class CudaKernels:
         out = torch.empty(S * B, dtype=torch.int32, device=lengths.device)
         check(self._lib.tzk_permute_lengths(_ptr(lengths), _ptr(perm), S, B, _ptr(out), _stream()),
               "tzk_permute_lengths")
+        self.launches += 1
         return out
 
     def permute_ids(self, ids: torch.Tensor, in_offsets: torch.Tensor, out_offsets: torch.Tensor,
@@ -237,6 +245,7 @@ class CudaKernels:
         out = torch.empty(out_nnz, dtype=torch.int64, device=ids.device)
         check(self._lib.tzk_permute_ids(_ptr(ids), _ptr(in_offsets), _ptr(out_offsets), _ptr(perm),
                                         perm.numel(), B, _ptr(out), _stream()), "tzk_permute_ids")
+        self.launches += 1
         return out
 
     # ------------------------------------------------------------------ K6
@@ -250,12 +259,13 @@ class CudaKernels:
         if out is None:
             out = torch.empty((rows, plan.C), dtype=torch.float32, device=dev)
         out, ld_out = _rows2d(out, "out")
-        # pointer table: tiny H2D copy from pinned-free python ints; one per call (graph-safe callers pre-bind)
-        ptrs = torch.tensor([s.data_ptr() for s in srcs], dtype=torch.int64, device=dev)
-        ldt = torch.tensor(lds, dtype=torch.int64, device=dev)
-        check(self._lib.tzk_col_gather_sum(_ptr(ptrs), _ptr(ldt), _ptr(plan.d_col_start), _ptr(plan.d_col_src),
+        n = len(srcs)
+        ptrs = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])  # host arrays -> kernel parameters
+        ldt = (ctypes.c_int64 * n)(*lds)
+        check(self._lib.tzk_col_gather_sum(ptrs, ldt, n, _ptr(plan.d_col_start), _ptr(plan.d_col_src),
                                            _ptr(plan.d_col_srccol), plan.C, rows, _ptr(out), ld_out, _stream()),
               "tzk_col_gather_sum")
+        self.launches += 1
         return out
 
     # ------------------------------------------------------------------ K7
@@ -267,6 +277,7 @@ class CudaKernels:
         out = torch.empty((B, T, D), dtype=torch.float32, device=values.device)
         check(self._lib.tzk_jagged_to_padded(_ptr(values), _ptr(offsets), B, T, D, _ptr(out), _stream()),
               "tzk_jagged_to_padded")
+        self.launches += 1
         return out
 
     def padded_to_jagged(self, grad_out: torch.Tensor, offsets: torch.Tensor, nnz: int) -> torch.Tensor:
@@ -276,6 +287,7 @@ class CudaKernels:
         out = torch.empty((nnz, D), dtype=torch.float32, device=grad_out.device)
         check(self._lib.tzk_padded_to_jagged(_ptr(grad_out), _ptr(offsets), B, T, D, nnz, _ptr(out), _stream()),
               "tzk_padded_to_jagged")
+        self.launches += 1
         return out
 
     # ------------------------------------------------------------------ A7
@@ -284,6 +296,7 @@ class CudaKernels:
         B = x.shape[0]
         y = torch.empty((B, D), dtype=torch.float32, device=x.device)
         check(self._lib.tzk_fm_fwd(_ptr(x), ld, B, N, D, _ptr(y), D, _stream()), "tzk_fm_fwd")
+        self.launches += 1
         return y
 
     def fm_bwd(self, x: torch.Tensor, dy: torch.Tensor, N: int, D: int) -> torch.Tensor:
@@ -293,6 +306,7 @@ class CudaKernels:
         dx = torch.empty((B, N * D), dtype=torch.float32, device=x.device)
         check(self._lib.tzk_fm_bwd(_ptr(x), ld, _ptr(dy), ld_dy, B, N, D, _ptr(dx), N * D, _stream()),
               "tzk_fm_bwd")
+        self.launches += 1
         return dx
 
     # ------------------------------------------------------------------ A9 / A10
@@ -309,6 +323,7 @@ class CudaKernels:
         check(self._lib.tzk_dot_interact_fwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, B, Ns, D, int(copy_dense),
                                              int(copy_sparse), _ptr(out), width, _stream()),
               "tzk_dot_interact_fwd")
+        self.launches += 1
         return out
 
     def dot_interact_bwd(self, dense: Optional[torch.Tensor], sparse: torch.Tensor, d_out: torch.Tensor,
@@ -325,6 +340,7 @@ class CudaKernels:
         check(self._lib.tzk_dot_interact_bwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, _ptr(d_out), ld_o, B, Ns, D,
                                              int(copy_dense), int(copy_sparse), _ptr(d_dense), D,
                                              _ptr(d_sparse), Ns * D, _stream()), "tzk_dot_interact_bwd")
+        self.launches += 1
         return d_dense, d_sparse
 
 
