@@ -91,7 +91,7 @@ int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_off, const in
  * SGD -> ignored (may be NULL).
  * pooled == 0 selects the un-pooled (sequence) layout: grad_out is [nnz, D] indexed by id position.
  * total_keys = one past the largest sort key (sum of physical rows).  Requires nnz < 2^31. */
-size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys);
+size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys, int32_t max_dim);
 int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
                   const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
                   const int32_t* feat_col, const int32_t* feat_pool, const int64_t* feat_key_base,
@@ -100,20 +100,32 @@ int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int6
                   float lr, float eps, float grad_scale, void* workspace, size_t workspace_bytes,
                   tzk_stream_t stream);
 
-/* ---- K1: row-wise block bucketize  ([EXT] fbgemm::block_bucketize_sparse_features, reached through
- * DistributedModelParallel at tzrec/main.py:799; geometry App. A.7) -----------------------------------
- * dest r = id / block[f], local id = id - r*block[f].  Outputs, laid out [W][F][B] (dest-major):
+/* ---- pooled-lookup backward w.r.t. a row buffer in which every row is referenced exactly once (the
+ * sample owner's half of the sharded backward; our replacement of [EXT] PooledEmbeddingsAllToAll /
+ * PooledEmbeddingsReduceScatter backward, App. A.6 / A.8):
+ *   g_rows[slot[l], 0:D] = grad_out[b, feat_col[f] : +D] * (MEAN ? 1/L(f,b) : 1)   for every id position l
+ * of bag (f,b).  All features share one dim D. */
+int tzk_bag_grad_expand(const float* grad_out, int64_t ld_grad, const int32_t* feat_col,
+                        const int32_t* feat_pool, const int64_t* offsets, const int32_t* slot, int32_t F,
+                        int32_t B, int32_t D, float* g_rows, tzk_stream_t stream);
+
+/* ---- K1: block bucketize  ([EXT] fbgemm::block_bucketize_sparse_features, reached through
+ * DistributedModelParallel at tzrec/main.py:799; geometry App. A.5 / A.7) ----------------------------
+ * dest r = feat_owner[f] + id / feat_block[f], local id = id - (id / feat_block[f]) * feat_block[f].
+ *   row-wise   : owner 0, block = ceil(rows / W)
+ *   table-wise : owner = rank holding the table, block >= rows (quotient 0, id unchanged)
+ * feat_owner may be NULL (all 0).  Outputs, laid out [W][F][B] (dest-major):
  *   out_lengths[(r*F+f)*B + b]   number of ids of bag (f,b) that go to rank r
- *   out_ids                       bucketed local ids, same order as out_lengths, original relative
- *                                 order kept inside a bag (bucketize_pos = false)
- *   out_pos (nullable)            for each output slot, the input position it came from
- *                                 (the "unbucketize permute" for sequence features)
- * out_offsets [W*F*B+1] is produced as a by-product (scan of out_lengths). */
+ *   out_offsets [W*F*B+1]         scan of out_lengths (by-product)
+ *   out_ids                       local ids in that order; relative order inside a bag is kept
+ *                                 (bucketize_pos = false)
+ *   out_pos (nullable)            out_pos[o] = input position of output slot o ("unbucketize permute")
+ *   out_inv (nullable)            out_inv[l] = output slot of input position l (its inverse) */
 size_t tzk_bucketize_rw_workspace_bytes(int32_t F, int32_t B, int32_t W, int64_t nnz);
 int tzk_bucketize_rw(const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t W,
-                     const int64_t* feat_block, int64_t nnz, int32_t* out_lengths, int64_t* out_offsets,
-                     int64_t* out_ids, int32_t* out_pos, void* workspace, size_t workspace_bytes,
-                     tzk_stream_t stream);
+                     const int64_t* feat_block, const int32_t* feat_owner, int64_t nnz,
+                     int32_t* out_lengths, int64_t* out_offsets, int64_t* out_ids, int32_t* out_pos,
+                     int32_t* out_inv, void* workspace, size_t workspace_bytes, tzk_stream_t stream);
 
 /* ---- K2: KJT segment permute  ([EXT] fbgemm::permute_2D_sparse_data, KeyedJaggedTensor.permute;
  * used by the TW input-dist, App. A.5) ----------------------------------------------------------------

@@ -167,20 +167,45 @@ def rw_block_size(rows: int, W: int) -> int:
     return max((rows + W - 1) // W, 1)
 
 
-def bucketize_rw(ids: np.ndarray, offsets: np.ndarray, F: int, B: int, W: int, feat_block: Sequence[int]):
-    """Returns (out_lengths [W*F*B] int32, out_offsets [W*F*B+1], out_ids [nnz], out_pos [nnz] int32)."""
+def bucketize_rw(ids: np.ndarray, offsets: np.ndarray, F: int, B: int, W: int, feat_block: Sequence[int],
+                 feat_owner: Optional[Sequence[int]] = None):
+    """dest = owner + id // block, local = id - (id // block) * block (row-wise: owner 0; table-wise: block >= rows).
+
+    Returns (out_lengths [W*F*B] int32, out_offsets [W*F*B+1], out_ids [nnz], out_pos [nnz] int32) with the
+    [W][F][B] layout; ids of a bag keep their relative order (bucketize_pos=False)."""
     nnz = len(ids)
     bag = _bag_of_position(offsets)
     f_of = bag // B
     blk = np.asarray(feat_block, dtype=np.int64)[f_of] if nnz else np.zeros(0, np.int64)
-    dest = np.where(ids < 0, 0, np.minimum(ids // np.maximum(blk, 1), W - 1)).astype(np.int64) if nnz else bag
+    own = (np.asarray(feat_owner, dtype=np.int64)[f_of] if feat_owner is not None else np.zeros(nnz, np.int64)) \
+        if nnz else np.zeros(0, np.int64)
+    q = np.where(ids < 0, 0, ids // np.maximum(blk, 1)) if nnz else bag
+    dest = own + q
+    over = np.maximum(dest - (W - 1), 0)
+    q, dest = q - over, dest - over
     out_bag = dest * (F * B) + bag  # [W][F][B] layout
     out_lengths = np.bincount(out_bag, minlength=W * F * B).astype(np.int32)
     out_offsets = lengths_to_offsets(out_lengths)
     order = np.argsort(out_bag, kind="stable")  # keeps original relative order inside a bag
-    out_ids = (ids - dest * blk)[order].astype(np.int64)
+    out_ids = (ids - q * blk)[order].astype(np.int64)
     out_pos = order.astype(np.int32)
     return out_lengths, out_offsets, out_ids, out_pos
+
+
+def bag_grad_expand(grad_out: np.ndarray, feat_col: Sequence[int], feat_pool: Sequence[int], offsets: np.ndarray,
+                    slot: np.ndarray, F: int, B: int, D: int, n_rows: int) -> np.ndarray:
+    """One gradient row per id position, placed at its wire slot (sample-owner half of the sharded backward)."""
+    out = np.zeros((n_rows, D), dtype=f32)
+    bag = _bag_of_position(offsets)
+    f_of, b_of = bag // B, bag % B
+    L = np.diff(offsets).astype(f32)
+    for f in range(F):
+        m = f_of == f
+        g = grad_out[b_of[m], feat_col[f]:feat_col[f] + D].astype(f32)
+        if feat_pool[f] == POOL_MEAN:
+            g = g * (f32(1.0) / L[bag[m]])[:, None]
+        out[slot[m]] = g
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------

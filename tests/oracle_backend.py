@@ -20,10 +20,10 @@ def _tables(weights, lay):
     assert arr is not None, "oracle backend works on CPU tensors"
     tabs, feat_table, seen = [], [], {}
     for f in range(lay.num_features):
-        key = lay.w_off[f]
+        key = (lay.w_off[f], lay.rows[f], lay.dim[f])   # zero-row shards share an offset with their neighbour
         if key not in seen:
             seen[key] = len(tabs)
-            tabs.append(arr[key:key + lay.rows[f] * lay.dim[f]].reshape(lay.rows[f], lay.dim[f]))
+            tabs.append(arr[key[0]:key[0] + lay.rows[f] * lay.dim[f]].reshape(lay.rows[f], lay.dim[f]))
         feat_table.append(seen[key])
     return tabs, feat_table
 
@@ -61,10 +61,20 @@ class OracleKernels:
         O.fused_update(optimizer, tabs, states, ft, lay.pool, _np(ids), _np(offsets), B, _np(grad_out), lr, eps,
                        grad_scale, pooled=bool(pooled))
 
-    def bucketize_rw(self, ids, offsets, F, B, W, feat_block, want_pos=False):
-        ol, oo, oi, op = O.bucketize_rw(_np(ids), _np(offsets), F, B, W, _np(feat_block).tolist())
+    def bucketize_rw(self, ids, offsets, F, B, W, feat_block, want_pos=False, feat_owner=None, want_inv=False):
+        ol, oo, oi, op = O.bucketize_rw(_np(ids), _np(offsets), F, B, W, _np(feat_block).tolist(),
+                                        None if feat_owner is None else _np(feat_owner).tolist())
+        inv = None
+        if want_inv:
+            inv = np.empty(len(op), dtype=np.int32)
+            inv[op] = np.arange(len(op), dtype=np.int32)
+            inv = torch.from_numpy(inv)
         return (torch.from_numpy(ol), torch.from_numpy(oo), torch.from_numpy(oi),
-                torch.from_numpy(op) if want_pos else None)
+                torch.from_numpy(op) if want_pos else None, inv)
+
+    def bag_grad_expand(self, grad_out, lay, offsets, slot, B, n_rows):
+        return torch.from_numpy(O.bag_grad_expand(_np(grad_out), lay.col, lay.pool, _np(offsets), _np(slot),
+                                                  lay.num_features, B, lay.dim[0], n_rows))
 
     def permute_lengths(self, lengths, perm, B):
         l = _np(lengths)

@@ -34,7 +34,7 @@ def test_workspace_queries_need_no_gpu():
     handle = _lib.lib()
     assert handle.tzk_lengths_to_offsets_workspace_bytes(0) >= 8
     assert handle.tzk_lengths_to_offsets_workspace_bytes(1 << 20) >= (1 << 20) // 4096 * 8
-    assert handle.tzk_fused_bwd_workspace_bytes(1000, 1 << 20) > 1000 * 16
+    assert handle.tzk_fused_bwd_workspace_bytes(1000, 1 << 20, 16) > 1000 * 16
     assert handle.tzk_bucketize_rw_workspace_bytes(26, 512, 8, 26 * 512) > 0
 
 

@@ -39,33 +39,35 @@ def test_train_steps_match_oracle(name):
             loss_c, (_, preds_c, _) = cpu.train_wrapper(batch)
             loss_c.backward()
             cpu.dense_optimizer.step()
-        np.testing.assert_allclose(float(loss_g), float(loss_c), rtol=1e-5)
+        np.testing.assert_allclose(float(loss_g.detach()), float(loss_c.detach()), rtol=1e-5)
         for k in preds_c:
             if k.startswith("logits"):
-                np.testing.assert_allclose(preds_g[k].cpu().numpy(), preds_c[k].numpy(), rtol=1e-4, atol=2e-6)
+                # 1e-5 relative to the logit scale: cuBLAS vs MKL fp32 GEMMs of the dense towers differ in
+                # summation order, which is an absolute (not relative) error on logits that cross zero
+                ref = preds_c[k].numpy()
+                np.testing.assert_allclose(preds_g[k].cpu().numpy(), ref, rtol=1e-5,
+                                           atol=1e-5 * max(1.0, float(np.abs(ref).max())))
         for cg, cc in zip(gpu.model.sparse_collections(), cpu.model.sparse_collections()):
             np.testing.assert_allclose(cg.weights.detach().cpu().numpy(), cc.weights.detach().numpy(), rtol=1e-5,
                                        atol=1e-7)
-            np.testing.assert_allclose(cg.opt_state.cpu().numpy(), cc.opt_state.numpy(), rtol=1e-4, atol=1e-12)
+            np.testing.assert_allclose(cg.opt_state.cpu().numpy(), cc.opt_state.numpy(), rtol=1e-4, atol=1e-10)
 
 
 def test_cuda_graph_step_equals_eager_step():
     a = Pipeline("dlrm_criteo", device="cuda:0", max_rows=5000, seed=3)
-    b = Pipeline("dlrm_criteo", device="cuda:0", max_rows=5000, seed=3)
+    batches = [a.synthetic_batch(1024, seed=40 + i) for i in range(4)]
+    step = GraphedTrainStep(a, batches[0], warmup=3)      # warm-up steps already trained `a` a little
+    b = Pipeline("dlrm_criteo", device="cuda:0", max_rows=5000, seed=3)   # eager twin, cloned AFTER the capture
     b.model.load_state_dict(a.model.state_dict())
-    batches = [a.synthetic_batch(1024, seed=40 + i) for i in range(3)]
-    snap = {k: v.clone() for k, v in a.model.state_dict().items()}
-    step = GraphedTrainStep(a, batches[0], warmup=3)      # warm-up steps mutate the model: restore it
-    a.model.load_state_dict(snap)
-    for c in a.model.sparse_collections():
-        c.opt_state.zero_()
-    a.dense_optimizer.load_state_dict(b.dense_optimizer.state_dict())
+    for ca, cb in zip(a.model.sparse_collections(), b.model.sparse_collections()):
+        cb.opt_state.copy_(ca.opt_state)
+    b.dense_optimizer.load_state_dict(a.dense_optimizer.state_dict())
     losses_a, losses_b = [], []
-    for bt in batches:
+    for bt in batches[1:]:
         step.load(bt.pin_memory())
         losses_a.append(float(step.replay()))
         losses_b.append(float(b.eager_step(bt.to("cuda:0"))))
-    np.testing.assert_allclose(losses_a, losses_b, rtol=1e-5)
+    np.testing.assert_allclose(losses_a, losses_b, rtol=1e-6)
     wa = a.model.sparse_collections()[0].weights.detach().cpu().numpy()
     wb = b.model.sparse_collections()[0].weights.detach().cpu().numpy()
-    np.testing.assert_allclose(wa, wb, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(wa, wb, rtol=1e-6, atol=1e-8)

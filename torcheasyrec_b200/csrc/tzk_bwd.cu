@@ -80,6 +80,78 @@ linearize_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ of
   }
 }
 
+// sequence layout (pooled == 0): bags may be arbitrarily long (a whole (src,feature) segment when B == 1), so
+// the work item is the id position and the feature comes from a binary search over the key boundaries.
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads)
+linearize_seq_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
+                     const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_key_base, int F,
+                     int B, int64_t n, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int64_t* key_start = reinterpret_cast<int64_t*>(smem_raw);  // [F+1]
+  int64_t* base = key_start + (F + 1);
+  int64_t* rows = base + F;
+  for (int f = threadIdx.x; f <= F; f += blockDim.x) key_start[f] = offsets[(int64_t)f * B];
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    base[f] = feat_key_base[f];
+    rows[f] = feat_rows[f];
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += stride) {
+    int lo = 0, hi = F;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (key_start[mid] <= l) lo = mid; else hi = mid;
+    }
+    int64_t id = __ldg(ids + l);
+    if ((uint64_t)id >= (uint64_t)rows[lo]) id = 0;
+    keys[l] = (KeyT)(base[lo] + id);
+    vals[l] = (int32_t)l;
+  }
+}
+
+// sample-owner half of the sharded backward: one gradient row per id position, written to its wire slot
+__global__ void __launch_bounds__(kThreads)
+bag_grad_expand_kernel(const float* __restrict__ grad_out, int64_t ld_grad, const int32_t* __restrict__ feat_col,
+                       const int32_t* __restrict__ feat_pool, const int64_t* __restrict__ offsets,
+                       const int32_t* __restrict__ slot, int F, int B, int D, float* __restrict__ g_rows) {
+  const int D4 = D >> 2;  // D % 4 == 0 on this path (checked by the host wrapper), else scalar kernel below
+  const int64_t n_items = (int64_t)F * B * D4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
+    const int64_t bag = i / D4;
+    const int c = (int)(i - bag * D4) * 4;
+    const int f = (int)(bag / B);
+    const int b = (int)(bag - (int64_t)f * B);
+    const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
+    if (e == s) continue;
+    float4 g = ld_row_f4(grad_out + (int64_t)b * ld_grad + __ldg(feat_col + f) + c);
+    if (__ldg(feat_pool + f) == TZK_POOL_MEAN) g = f4_scale(g, 1.0f / (float)(e - s));
+    for (int64_t l = s; l < e; ++l) st_stream_f4(g_rows + (int64_t)__ldg(slot + l) * D + c, g);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+bag_grad_expand_scalar_kernel(const float* __restrict__ grad_out, int64_t ld_grad,
+                              const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                              const int64_t* __restrict__ offsets, const int32_t* __restrict__ slot, int F, int B,
+                              int D, float* __restrict__ g_rows) {
+  const int64_t n_items = (int64_t)F * B * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
+    const int64_t bag = i / D;
+    const int c = (int)(i - bag * D);
+    const int f = (int)(bag / B);
+    const int b = (int)(bag - (int64_t)f * B);
+    const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
+    if (e == s) continue;
+    float g = __ldg(grad_out + (int64_t)b * ld_grad + __ldg(feat_col + f) + c);
+    if (__ldg(feat_pool + f) == TZK_POOL_MEAN) g *= 1.0f / (float)(e - s);
+    for (int64_t l = s; l < e; ++l) g_rows[(int64_t)__ldg(slot + l) * D + c] = g;
+  }
+}
+
 // gradient-row address + scale of one sorted entry
 struct Entry {
   const float* g;
@@ -215,14 +287,33 @@ __device__ __forceinline__ void load_grad(const float* p, float (&g)[VEC]) {
 }
 
 // ---- 3. short runs ---------------------------------------------------------------------------------
+// Work lists for runs longer than kShortRun (tiny tables, hot ids).  A long run is cut into chunks of kChunk
+// sorted positions; one CTA reduces one chunk (4a).  Single-chunk runs are finished by that CTA; multi-chunk
+// runs park per-chunk partial sums that 4b adds up in chunk order — so the result does not depend on which
+// CTA ran what.
+constexpr int kChunk = 1024;
+struct ChunkItem {
+  int32_t start, end;   // sorted positions [start, end)
+  int32_t n_chunks;     // chunks of the run
+  int32_t pslot;        // multi-chunk runs: slot of this chunk's partial sum (run base + chunk index)
+};
+struct LongRun {
+  int32_t head, pslot, n_chunks, pad;
+};
+struct WorkLists {
+  ChunkItem* items;
+  LongRun* runs;
+  int32_t* counters;  // [0] items, [1] multi-chunk runs, [2] partial slots
+  float* partials;    // [slots][ROWF]
+};
+
 // CH = float4 (or scalar) chunks per lane: dims up to G*VEC*CH are supported.
 template <typename KeyT, int G, int VEC, int CH>
 __global__ void __launch_bounds__(kThreads)
 run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
                   const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
                   const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
-                  const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
-                  int32_t* __restrict__ long_list, int32_t* __restrict__ long_count) {
+                  const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
@@ -232,15 +323,48 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   const int64_t stride = (int64_t)gridDim.x * NG;
   // all G lanes of a group follow the same control flow (p, key, len are group-uniform)
   for (int64_t p = (int64_t)blockIdx.x * NG + threadIdx.x / G; p < a.n; p += stride) {
+    // independent loads first: neighbours decide head / run length 1, v0 addresses the gradient row
     const KeyT key = keys[p];
-    if (p > 0 && keys[p - 1] == key) continue;  // not a run head
+    const KeyT kprev = p > 0 ? keys[p - 1] : (KeyT)~key;
+    const KeyT knext = p + 1 < a.n ? keys[p + 1] : (KeyT)~key;
+    const int32_t v0 = vals[p];
+    if (kprev == key) continue;  // not a run head
     int len = 1;
-    while (len <= kShortRun && p + len < a.n && keys[p + len] == key) ++len;
+    if (knext == key) {
+      len = 2;
+      while (len <= kShortRun && p + len < a.n && keys[p + len] == key) ++len;
+    }
     if (len > kShortRun) {
-      if (lane == 0) long_list[atomicAdd(long_count, 1)] = (int32_t)p;
+      if (lane == 0) {
+        // gallop + binary search for the end of the run, then enqueue its chunks
+        int64_t lo = p + kShortRun, step = kShortRun;  // keys[lo] == key
+        int64_t hi = lo + step;
+        while (hi < a.n && keys[hi] == key) { lo = hi; step <<= 1; hi = lo + step; }
+        if (hi > a.n) hi = a.n;
+        while (hi - lo > 1) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (keys[mid] == key) lo = mid; else hi = mid;
+        }
+        const int64_t end = hi;
+        const int n_chunks = (int)((end - p + kChunk - 1) / kChunk);
+        const int base = atomicAdd(wl.counters + 0, n_chunks);
+        int pslot = -1;
+        if (n_chunks > 1) {
+          pslot = atomicAdd(wl.counters + 2, n_chunks);
+          LongRun lr; lr.head = (int32_t)p; lr.pslot = pslot; lr.n_chunks = n_chunks; lr.pad = 0;
+          wl.runs[atomicAdd(wl.counters + 1, 1)] = lr;
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+          ChunkItem it;
+          it.start = (int32_t)(p + (int64_t)c * kChunk);
+          it.end = (int32_t)((p + (int64_t)(c + 1) * kChunk) < end ? (p + (int64_t)(c + 1) * kChunk) : end);
+          it.n_chunks = n_chunks;
+          it.pslot = n_chunks > 1 ? pslot + c : -1;
+          wl.items[base + c] = it;
+        }
+      }
       continue;
     }
-    const int32_t v0 = vals[p];
     int f0;
     if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
     const BwdFeat d = fd[f0];
@@ -268,46 +392,29 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   }
 }
 
-// ---- 4. long runs ----------------------------------------------------------------------------------
+// ---- 4a. one CTA per chunk of a long run -----------------------------------------------------------------
 template <typename KeyT, int G, int VEC, int CH>
 __global__ void __launch_bounds__(kThreads)
-long_run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off,
-                       const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_key_base,
-                       const int32_t* __restrict__ feat_dim, const int32_t* __restrict__ feat_col,
-                       const int32_t* __restrict__ feat_pool, const KeyT* __restrict__ keys,
-                       const int32_t* __restrict__ vals, const int32_t* __restrict__ long_list,
-                       const int32_t* __restrict__ long_count) {
+long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
+                  const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
+                  const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                  const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NG = kThreads / G;
+  constexpr int ROWF = CH * G * VEC;  // floats per partial row
+  constexpr int U = 4;                // independent gradient rows in flight per lane group
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
-  // partial sums: [NG][CH*G*VEC] floats, after the descriptors (16-B aligned: BwdFeat is 48 B)
   float* part = reinterpret_cast<float*>(smem_raw + align16((size_t)a.F * sizeof(BwdFeat)));
-  __shared__ int64_t run_end_s;
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
 
   const int lane = threadIdx.x % G;
   const int g = threadIdx.x / G;
-  const int n_long = *long_count;
-  constexpr int ROWF = CH * G * VEC;  // floats per partial row
+  const int n_items = wl.counters[0];
 
-  for (int r = blockIdx.x; r < n_long; r += gridDim.x) {
-    const int64_t p = long_list[r];
-    const KeyT key = keys[p];
-    if (threadIdx.x == 0) {
-      // gallop + binary search for the end of the run
-      int64_t lo = p, step = kShortRun;  // keys[lo] == key
-      int64_t hi = p + step;
-      while (hi < a.n && keys[hi] == key) { lo = hi; step <<= 1; hi = lo + step; }
-      if (hi > a.n) hi = a.n;  // keys[hi] != key or hi == n
-      while (hi - lo > 1) {
-        int64_t mid = (lo + hi) >> 1;
-        if (keys[mid] == key) lo = mid; else hi = mid;
-      }
-      run_end_s = hi;
-    }
-    __syncthreads();
-    const int64_t end = run_end_s;
-    const int32_t v0 = vals[p];
+  for (int r = blockIdx.x; r < n_items; r += gridDim.x) {
+    const ChunkItem it = wl.items[r];
+    const KeyT key = keys[it.start];
+    const int32_t v0 = vals[it.start];
     int f0;
     if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
     const BwdFeat d = fd[f0];
@@ -318,16 +425,28 @@ long_run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off,
     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-    for (int64_t q = p + g; q < end; q += NG) {
-      const Entry en = entry_of(a, fd, vals[q], f0);
+    for (int q0 = it.start + g; q0 < it.end; q0 += NG * U) {
+      Entry en[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = q0 + u * NG;
+        ok[u] = q < it.end;
+        en[u] = entry_of(a, fd, ok[u] ? vals[q] : v0, f0);
+      }
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
         const int c = (ch * G + lane) * VEC;
         if (c < d.dim) {
-          float gr[VEC];
-          load_grad<VEC>(en.g + c, gr);
+          float gr[U][VEC];
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) acc[ch][k] += gr[k] * en.scale;
+          for (int u = 0; u < U; ++u) load_grad<VEC>(en[u].g + c, gr[u]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (ok[u]) {
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) acc[ch][k] += gr[u][k] * en[u].scale;
+            }
         }
       }
     }
@@ -350,17 +469,62 @@ long_run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off,
       __syncthreads();
     }
     if (g == 0) {
+      if (it.n_chunks == 1) {
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
+        for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[ch][k] = part[(ch * G + lane) * VEC + k];
-      finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
+          for (int k = 0; k < VEC; ++k) acc[ch][k] = part[(ch * G + lane) * VEC + k];
+        finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
+      } else {
+        float* dst = wl.partials + (int64_t)it.pslot * ROWF;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) dst[(ch * G + lane) * VEC + k] = part[(ch * G + lane) * VEC + k];
+      }
     }
     __syncthreads();
   }
 }
 
-__global__ void zero_counter(int32_t* c) { *c = 0; }
+// ---- 4b. multi-chunk runs: add the chunk partials in chunk order, then update ------------------------------
+template <typename KeyT, int G, int VEC, int CH>
+__global__ void __launch_bounds__(kThreads)
+long_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
+                    const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
+                    const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                    const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NG = kThreads / G;
+  constexpr int ROWF = CH * G * VEC;
+  BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
+  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  const int lane = threadIdx.x % G;
+  const int n_runs = wl.counters[1];
+  for (int r = blockIdx.x * NG + threadIdx.x / G; r < n_runs; r += gridDim.x * NG) {
+    const LongRun lr = wl.runs[r];
+    const KeyT key = keys[lr.head];
+    const int32_t v0 = vals[lr.head];
+    int f0;
+    if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
+    const BwdFeat d = fd[f0];
+    float acc[CH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+    for (int c = 0; c < lr.n_chunks; ++c) {
+      const float* src = wl.partials + (int64_t)(lr.pslot + c) * ROWF;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[ch][k] += src[(ch * G + lane) * VEC + k];
+    }
+    finish_run<G, VEC, CH>(a, d, (int64_t)key - d.key_base, (int64_t)key, acc, lane);
+  }
+}
+
+__global__ void zero_counters(int32_t* c) { c[0] = 0; c[1] = 0; c[2] = 0; }
 
 inline int bits_for(int64_t total_keys) {
   int b = 1;
@@ -369,7 +533,7 @@ inline int bits_for(int64_t total_keys) {
 }
 
 struct WsLayout {
-  size_t keys_in, keys_out, vals_in, vals_out, long_list, long_count, cub_tmp, total;
+  size_t keys_in, keys_out, vals_in, vals_out, items, runs, counters, partials, cub_tmp, total;
   size_t cub_bytes;
 };
 
@@ -379,7 +543,10 @@ cudaError_t cub_sort(void* tmp, size_t& tmp_bytes, const KeyT* kin, KeyT* kout, 
   return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, (int)n, 0, bits, st);
 }
 
-WsLayout ws_layout(int64_t nnz, int64_t total_keys) {
+inline int64_t max_items(int64_t n) { return n / kShortRun + n / kChunk + 2; }   // every long run has > 32 ids
+inline int64_t max_pslots(int64_t n) { return 2 * (n / kChunk) + 2; }            // multi-chunk runs have > 1024
+
+WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
   WsLayout L;
   const bool k64 = total_keys > ((int64_t)1 << 32);
   const size_t ksz = k64 ? 8 : 4;
@@ -389,8 +556,11 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys) {
   L.keys_out = o; o = align_up(o + n * ksz, 256);
   L.vals_in = o; o = align_up(o + n * 4, 256);
   L.vals_out = o; o = align_up(o + n * 4, 256);
-  L.long_list = o; o = align_up(o + n * 4, 256);
-  L.long_count = o; o = align_up(o + 256, 256);
+  L.items = o; o = align_up(o + max_items(n) * sizeof(ChunkItem), 256);
+  L.runs = o; o = align_up(o + (n / kChunk + 2) * sizeof(LongRun), 256);
+  L.counters = o; o = align_up(o + 256, 256);
+  const size_t rowf = (size_t)((max_dim + 127) / 128 * 128 < 128 ? 128 : (max_dim + 127) / 128 * 128) * 4;
+  L.partials = o; o = align_up(o + max_pslots(n) * rowf * sizeof(float), 256);
   size_t tb = 0;
   const int bits = bits_for(total_keys);
   if (k64) cub_sort<uint64_t>(nullptr, tb, nullptr, nullptr, nullptr, nullptr, n, bits, 0);
@@ -406,16 +576,29 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys) {
 #define TZK_BWD_LAUNCH(KeyT, G_, VEC_, CH_)                                                          \
   do {                                                                                                \
     size_t smem_s = (size_t)F * sizeof(BwdFeat);                                                      \
+    if (smem_s > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(run_update_kernel<KeyT, G_, VEC_, CH_>,                                    \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
     run_update_kernel<KeyT, G_, VEC_, CH_><<<grid_s, kThreads, smem_s, st>>>(                         \
         a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
-        vals_out, long_list, long_count);                                                             \
+        vals_out, wl);                                                                                \
     TZK_CHECK_LAUNCH("run_update_kernel");                                                            \
-    size_t smem_l = tzk::align16((size_t)F * sizeof(BwdFeat)) +                                  \
+    size_t smem_l = tzk::align16((size_t)F * sizeof(BwdFeat)) +                                       \
                     (size_t)(kThreads / G_) * (CH_ * G_ * VEC_) * sizeof(float);                      \
-    long_run_update_kernel<KeyT, G_, VEC_, CH_><<<kSmCountB200 * 4, kThreads, smem_l, st>>>(          \
+    if (smem_l > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(long_chunk_kernel<KeyT, G_, VEC_, CH_>,                                    \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);                 \
+    long_chunk_kernel<KeyT, G_, VEC_, CH_><<<kSmCountB200 * 8, kThreads, smem_l, st>>>(               \
         a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
-        vals_out, long_list, long_count);                                                             \
-    TZK_CHECK_LAUNCH("long_run_update_kernel");                                                       \
+        vals_out, wl);                                                                                \
+    TZK_CHECK_LAUNCH("long_chunk_kernel");                                                            \
+    if (smem_s > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(long_combine_kernel<KeyT, G_, VEC_, CH_>,                                  \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
+    long_combine_kernel<KeyT, G_, VEC_, CH_><<<kSmCountB200, kThreads, smem_s, st>>>(                 \
+        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
+        vals_out, wl);                                                                                \
+    TZK_CHECK_LAUNCH("long_combine_kernel");                                                          \
   } while (0)
 
 #define TZK_BWD_DISPATCH_G(KeyT, VEC_, CH_)                 \
@@ -428,8 +611,8 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys) {
     default: TZK_BWD_LAUNCH(KeyT, 32, VEC_, CH_); break;    \
   }
 
-extern "C" size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys) {
-  return ws_layout(nnz, total_keys).total;
+extern "C" size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys, int32_t max_dim) {
+  return ws_layout(nnz, total_keys, max_dim < 1 ? 1 : max_dim).total;
 }
 
 extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
@@ -443,15 +626,15 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
   TZK_REQUIRE(optimizer >= 0 && optimizer <= 2, "fused_bwd: unknown optimizer %d", optimizer);
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0, "fused_bwd: negative size");
   if (F == 0 || B == 0 || nnz == 0) return 0;
-  TZK_REQUIRE(nnz < ((int64_t)1 << 31) && (int64_t)F * B < ((int64_t)1 << 31),
+  TZK_REQUIRE(nnz < ((int64_t)1 << 31) && (int64_t)F * std::max(B, 1) < ((int64_t)1 << 31),
               "fused_bwd: nnz or F*B >= 2^31 not supported");
   TZK_REQUIRE(grad_out && feat_w_off && feat_rows && feat_dim && feat_key_base && ids && offsets && weights,
               "fused_bwd: NULL argument");
   TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
   TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
-  TZK_REQUIRE(F <= 256, "fused_bwd: F=%d > 256 keys per collection", F);
+  TZK_REQUIRE(F <= 2048, "fused_bwd: F=%d > 2048 keys per collection", F);
   TZK_REQUIRE(max_dim >= 1 && max_dim <= 1024, "fused_bwd: max_dim=%d out of range [1,1024]", max_dim);
-  WsLayout L = ws_layout(nnz, total_keys);
+  WsLayout L = ws_layout(nnz, total_keys, max_dim);
   TZK_REQUIRE(workspace && workspace_bytes >= L.total, "fused_bwd: workspace too small (%zu < %zu)",
               workspace_bytes, L.total);
   cudaStream_t st = as_stream(stream);
@@ -460,25 +643,38 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
   void* keys_out = ws + L.keys_out;
   int32_t* vals_in = reinterpret_cast<int32_t*>(ws + L.vals_in);
   int32_t* vals_out = reinterpret_cast<int32_t*>(ws + L.vals_out);
-  int32_t* long_list = reinterpret_cast<int32_t*>(ws + L.long_list);
-  int32_t* long_count = reinterpret_cast<int32_t*>(ws + L.long_count);
+  WorkLists wl;
+  wl.items = reinterpret_cast<ChunkItem*>(ws + L.items);
+  wl.runs = reinterpret_cast<LongRun*>(ws + L.runs);
+  wl.counters = reinterpret_cast<int32_t*>(ws + L.counters);
+  wl.partials = reinterpret_cast<float*>(ws + L.partials);
   const bool k64 = total_keys > ((int64_t)1 << 32);
   const int bits = bits_for(total_keys);
 
-  zero_counter<<<1, 1, 0, st>>>(long_count);
+  zero_counters<<<1, 1, 0, st>>>(wl.counters);
   const int64_t n_bags = (int64_t)F * B;
   int grid_lin = (int)std::min<int64_t>(ceil_div64(n_bags, kThreads), kSmCountB200 * 16);
   size_t cub_bytes = L.cub_bytes;
   cudaError_t ce;
+  const size_t smem_lin = (size_t)(3 * F + 1) * sizeof(int64_t);
+  const int grid_seq = (int)std::min<int64_t>(ceil_div64(nnz, kThreads), kSmCountB200 * 16);
   if (k64) {
-    linearize_kernel<uint64_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
-                                                              pooled, (uint64_t*)keys_in, vals_in);
+    if (pooled)
+      linearize_kernel<uint64_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
+                                                                pooled, (uint64_t*)keys_in, vals_in);
+    else
+      linearize_seq_kernel<uint64_t><<<grid_seq, kThreads, smem_lin, st>>>(ids, offsets, feat_rows, feat_key_base,
+                                                                           F, B, nnz, (uint64_t*)keys_in, vals_in);
     TZK_CHECK_LAUNCH("linearize_kernel");
     ce = cub_sort<uint64_t>(ws + L.cub_tmp, cub_bytes, (const uint64_t*)keys_in, (uint64_t*)keys_out, vals_in,
                             vals_out, nnz, bits, st);
   } else {
-    linearize_kernel<uint32_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
-                                                              pooled, (uint32_t*)keys_in, vals_in);
+    if (pooled)
+      linearize_kernel<uint32_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
+                                                                pooled, (uint32_t*)keys_in, vals_in);
+    else
+      linearize_seq_kernel<uint32_t><<<grid_seq, kThreads, smem_lin, st>>>(ids, offsets, feat_rows, feat_key_base,
+                                                                           F, B, nnz, (uint32_t*)keys_in, vals_in);
     TZK_CHECK_LAUNCH("linearize_kernel");
     ce = cub_sort<uint32_t>(ws + L.cub_tmp, cub_bytes, (const uint32_t*)keys_in, (uint32_t*)keys_out, vals_in,
                             vals_out, nnz, bits, st);
@@ -510,5 +706,25 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
     if (vec == 4) { if (ch == 1) { TZK_BWD_DISPATCH_G(uint32_t, 4, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint32_t, 32, 4, 2); } else { TZK_BWD_LAUNCH(uint32_t, 32, 4, 8); } }
     else { if (ch == 1) { TZK_BWD_DISPATCH_G(uint32_t, 1, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint32_t, 32, 1, 2); } else { TZK_BWD_LAUNCH(uint32_t, 32, 1, 8); } }
   }
+  return 0;
+}
+
+extern "C" int tzk_bag_grad_expand(const float* grad_out, int64_t ld_grad, const int32_t* feat_col,
+                                   const int32_t* feat_pool, const int64_t* offsets, const int32_t* slot,
+                                   int32_t F, int32_t B, int32_t D, float* g_rows, tzk_stream_t stream) {
+  TZK_REQUIRE(F >= 0 && B >= 0 && D >= 1, "bag_grad_expand: bad sizes");
+  if (F == 0 || B == 0) return 0;
+  TZK_REQUIRE(grad_out && feat_col && feat_pool && offsets && slot && g_rows, "bag_grad_expand: NULL argument");
+  cudaStream_t st = as_stream(stream);
+  const bool vec = (D % 4 == 0) && ((uintptr_t)grad_out % 16 == 0) && ((uintptr_t)g_rows % 16 == 0) && (ld_grad % 4 == 0);
+  const int64_t items = (int64_t)F * B * (vec ? D / 4 : D);
+  const int grid = (int)std::min<int64_t>(ceil_div64(items, kThreads), kSmCountB200 * 16);
+  if (vec)
+    bag_grad_expand_kernel<<<grid, kThreads, 0, st>>>(grad_out, ld_grad, feat_col, feat_pool, offsets, slot, F, B, D,
+                                                       g_rows);
+  else
+    bag_grad_expand_scalar_kernel<<<grid, kThreads, 0, st>>>(grad_out, ld_grad, feat_col, feat_pool, offsets, slot,
+                                                              F, B, D, g_rows);
+  TZK_CHECK_LAUNCH("bag_grad_expand_kernel");
   return 0;
 }

@@ -7,18 +7,21 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kMaxW = 64;
 
-__device__ __forceinline__ int dest_of(int64_t id, int64_t block, int W) {
-  // ids are expected in [0, rows); anything else is clamped into a valid rank (fbgemm bounds WARNING mode
-  // would have remapped it to row 0 later anyway).
-  if (id < 0) return 0;
-  int64_t r = id / block;
-  return r >= W ? W - 1 : (int)r;
+// dest = owner + id / block (row-wise: owner 0, block = ceil(rows/W); table-wise: block >= rows so the
+// quotient is 0 and dest = owner; table-row-wise: both).  ids are expected in [0, rows); anything else is
+// clamped into a valid rank (fbgemm bounds WARNING mode would have remapped it to row 0 later anyway).
+__device__ __forceinline__ int dest_of(int64_t id, int64_t block, int owner, int W, int64_t* local) {
+  int64_t q = id < 0 ? 0 : id / block;
+  int64_t r = owner + q;
+  if (r >= W) { q -= r - (W - 1); r = W - 1; }
+  *local = id - q * block;
+  return (int)r;
 }
 
 __global__ void __launch_bounds__(kThreads)
 bucketize_count_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
-                       const int64_t* __restrict__ feat_block, int F, int B, int W,
-                       int32_t* __restrict__ out_lengths) {
+                       const int64_t* __restrict__ feat_block, const int32_t* __restrict__ feat_owner, int F,
+                       int B, int W, int32_t* __restrict__ out_lengths) {
   const int64_t n_bags = (int64_t)F * B;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t bag = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bag < n_bags; bag += stride) {
@@ -26,13 +29,15 @@ bucketize_count_kernel(const int64_t* __restrict__ ids, const int64_t* __restric
     const int b = (int)(bag - (int64_t)f * B);
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     const int64_t blk = __ldg(feat_block + f);
+    const int own = feat_owner ? __ldg(feat_owner + f) : 0;
+    int64_t loc;
     if (e - s == 1) {
-      const int r = dest_of(__ldg(ids + s), blk, W);
+      const int r = dest_of(__ldg(ids + s), blk, own, W, &loc);
       for (int w = 0; w < W; ++w) out_lengths[((int64_t)w * F + f) * B + b] = (w == r);
     } else {
       for (int w = 0; w < W; ++w) {
         int32_t c = 0;
-        for (int64_t l = s; l < e; ++l) c += (dest_of(__ldg(ids + l), blk, W) == w);
+        for (int64_t l = s; l < e; ++l) c += (dest_of(__ldg(ids + l), blk, own, W, &loc) == w);
         out_lengths[((int64_t)w * F + f) * B + b] = c;
       }
     }
@@ -41,9 +46,9 @@ bucketize_count_kernel(const int64_t* __restrict__ ids, const int64_t* __restric
 
 __global__ void __launch_bounds__(kThreads)
 bucketize_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
-                         const int64_t* __restrict__ feat_block, int F, int B, int W,
-                         const int64_t* __restrict__ out_offsets, int64_t* __restrict__ out_ids,
-                         int32_t* __restrict__ out_pos) {
+                         const int64_t* __restrict__ feat_block, const int32_t* __restrict__ feat_owner, int F,
+                         int B, int W, const int64_t* __restrict__ out_offsets, int64_t* __restrict__ out_ids,
+                         int32_t* __restrict__ out_pos, int32_t* __restrict__ out_inv) {
   const int64_t n_bags = (int64_t)F * B;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t bag = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bag < n_bags; bag += stride) {
@@ -51,21 +56,23 @@ bucketize_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restr
     const int b = (int)(bag - (int64_t)f * B);
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     const int64_t blk = __ldg(feat_block + f);
+    const int own = feat_owner ? __ldg(feat_owner + f) : 0;
+    int64_t loc;
     if (e - s == 1) {
-      const int64_t id = __ldg(ids + s);
-      const int r = dest_of(id, blk, W);
+      const int r = dest_of(__ldg(ids + s), blk, own, W, &loc);
       const int64_t o = __ldg(out_offsets + ((int64_t)r * F + f) * B + b);
-      out_ids[o] = id - (int64_t)r * blk;
+      out_ids[o] = loc;
       if (out_pos) out_pos[o] = (int32_t)s;
+      if (out_inv) out_inv[s] = (int32_t)o;
     } else if (e > s) {
       int32_t cnt[kMaxW];
       for (int w = 0; w < W; ++w) cnt[w] = 0;
       for (int64_t l = s; l < e; ++l) {
-        const int64_t id = __ldg(ids + l);
-        const int r = dest_of(id, blk, W);
+        const int r = dest_of(__ldg(ids + l), blk, own, W, &loc);
         const int64_t o = __ldg(out_offsets + ((int64_t)r * F + f) * B + b) + cnt[r]++;
-        out_ids[o] = id - (int64_t)r * blk;
+        out_ids[o] = loc;
         if (out_pos) out_pos[o] = (int32_t)l;
+        if (out_inv) out_inv[l] = (int32_t)o;
       }
     }
   }
@@ -104,9 +111,10 @@ extern "C" size_t tzk_bucketize_rw_workspace_bytes(int32_t F, int32_t B, int32_t
 }
 
 extern "C" int tzk_bucketize_rw(const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t W,
-                                const int64_t* feat_block, int64_t nnz, int32_t* out_lengths,
-                                int64_t* out_offsets, int64_t* out_ids, int32_t* out_pos, void* workspace,
-                                size_t workspace_bytes, tzk_stream_t stream) {
+                                const int64_t* feat_block, const int32_t* feat_owner, int64_t nnz,
+                                int32_t* out_lengths, int64_t* out_offsets, int64_t* out_ids, int32_t* out_pos,
+                                int32_t* out_inv, void* workspace, size_t workspace_bytes,
+                                tzk_stream_t stream) {
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0, "bucketize_rw: negative size");
   TZK_REQUIRE(W >= 1 && W <= kMaxW, "bucketize_rw: W=%d out of range [1,%d]", W, kMaxW);
   TZK_REQUIRE(nnz < ((int64_t)1 << 31), "bucketize_rw: nnz >= 2^31");
@@ -118,13 +126,13 @@ extern "C" int tzk_bucketize_rw(const int64_t* ids, const int64_t* offsets, int3
               "bucketize_rw: NULL argument");
   int grid = (int)(ceil_div64(n_bags, kThreads) < kSmCountB200 * 16 ? ceil_div64(n_bags, kThreads)
                                                                    : kSmCountB200 * 16);
-  bucketize_count_kernel<<<grid, kThreads, 0, st>>>(ids, offsets, feat_block, F, B, W, out_lengths);
+  bucketize_count_kernel<<<grid, kThreads, 0, st>>>(ids, offsets, feat_block, feat_owner, F, B, W, out_lengths);
   TZK_CHECK_LAUNCH("bucketize_count_kernel");
   int rc = tzk_lengths_to_offsets(out_lengths, n_bags * W, out_offsets, workspace, workspace_bytes, stream);
   if (rc) return rc;
   if (nnz > 0) {
-    bucketize_scatter_kernel<<<grid, kThreads, 0, st>>>(ids, offsets, feat_block, F, B, W, out_offsets,
-                                                        out_ids, out_pos);
+    bucketize_scatter_kernel<<<grid, kThreads, 0, st>>>(ids, offsets, feat_block, feat_owner, F, B, W,
+                                                        out_offsets, out_ids, out_pos, out_inv);
     TZK_CHECK_LAUNCH("bucketize_scatter_kernel");
   }
   return 0;

@@ -77,6 +77,16 @@ def _default_init(cfg: BaseEmbeddingConfig, w: torch.Tensor) -> None:
     w.uniform_(-bound, bound)
 
 
+def output_names_by_table(configs: Sequence[BaseEmbeddingConfig]) -> List[List[str]]:
+    """Output key of every (table, feature) slot: `feature`, or `feature@table` when the feature is served by
+    more than one table of the collection (App. A.2; tzrec/modules/embedding.py:826-827 relies on it)."""
+    count: Dict[str, int] = {}
+    for c in configs:
+        for f in c.feature_names:
+            count[f] = count.get(f, 0) + 1
+    return [[f + "@" + c.name if count[f] > 1 else f for f in c.feature_names] for c in configs]
+
+
 class _TableView(nn.Module):
     """`embedding_bags.<table>.weight` / `embeddings.<table>.weight` handle (a view into the arena)."""
 
@@ -95,26 +105,24 @@ class _ArenaCollection(nn.Module):
 
     _pooled = True
 
-    def __init__(self, tables: Sequence[BaseEmbeddingConfig], device=None, local_rows: Optional[Sequence[int]] = None):
+    def __init__(self, tables: Sequence[BaseEmbeddingConfig], device=None, local_rows: Optional[Sequence[int]] = None,
+                 names_by_table: Optional[List[List[str]]] = None):
         super().__init__()
         self._configs = list(tables)
         names = [c.name for c in self._configs]
         assert len(set(names)) == len(names), f"duplicate table names {names}"
         self._device = torch.device(device) if device is not None else torch.device("cpu")
-        # output keys: a feature served by >1 table of this collection is emitted as feat@table (App. A.2)
-        count: Dict[str, int] = {}
-        for c in self._configs:
-            for f in c.feature_names:
-                count[f] = count.get(f, 0) + 1
+        # output keys: a feature served by >1 table of the (whole, unsharded) collection is feat@table (App. A.2)
+        if names_by_table is None:
+            names_by_table = output_names_by_table(self._configs)
         self._feature_names: List[str] = []     # KJT key consumed by each slot
         self._embedding_names: List[str] = []   # output key of each slot
         self._names_by_table: List[List[str]] = []
         feat_table, feat_pool = [], []
         for t, c in enumerate(self._configs):
-            per = []
+            per = list(names_by_table[t])
             for f in c.feature_names:
                 self._feature_names.append(f)
-                per.append(f + "@" + c.name if count[f] > 1 else f)
                 feat_table.append(t)
                 pool = getattr(c, "pooling", PoolingType.SUM)
                 feat_pool.append(POOL_MEAN if pool == PoolingType.MEAN else POOL_SUM)
@@ -254,8 +262,8 @@ class _SeqLookup(torch.autograd.Function):
 class EmbeddingBagCollection(_ArenaCollection):
     """Pooled lookup: forward(KJT) -> KeyedTensor [B, sum_t sum_f D_t]  (embedding.py:855,930; App. A.2/A.3)."""
 
-    def __init__(self, tables: Sequence[EmbeddingBagConfig], device=None, local_rows=None) -> None:
-        super().__init__(tables, device, local_rows)
+    def __init__(self, tables: Sequence[EmbeddingBagConfig], device=None, local_rows=None, names_by_table=None) -> None:
+        super().__init__(tables, device, local_rows, names_by_table)
         self.embedding_bags = nn.ModuleDict({c.name: _TableView(self, t) for t, c in enumerate(self._configs)})
         self._lengths_per_key = [self._table_dim[t] for t in self._feat_table]
 
@@ -277,8 +285,8 @@ class EmbeddingCollection(_ArenaCollection):
 
     _pooled = False
 
-    def __init__(self, tables: Sequence[EmbeddingConfig], device=None, local_rows=None) -> None:
-        super().__init__(tables, device, local_rows)
+    def __init__(self, tables: Sequence[EmbeddingConfig], device=None, local_rows=None, names_by_table=None) -> None:
+        super().__init__(tables, device, local_rows, names_by_table)
         dims = set(self._table_dim)
         assert len(dims) <= 1, f"EmbeddingCollection tables must share one embedding_dim, got {dims}"
         self._dim = self._table_dim[0] if self._table_dim else 0

@@ -40,7 +40,8 @@ class Pipeline:
     """Everything needed to step one model: config, features, model, optimizers."""
 
     def __init__(self, config: str, device="cuda", max_rows: Optional[int] = None,
-                 edits: Optional[Dict[str, Any]] = None, seed: int = 1234, capturable: bool = True) -> None:
+                 edits: Optional[Dict[str, Any]] = None, seed: int = 1234, capturable: bool = True,
+                 sharding: Optional[str] = None, group=None, rw_min_rows: int = 0) -> None:
         """`config`: path of a pipeline .config/.json, or the name of a built-in example
         (example_configs.GENERATORS: dlrm_criteo, deepfm_criteo, mmoe_taobao, multi_tower_din_taobao)."""
         from . import example_configs
@@ -59,8 +60,20 @@ class Pipeline:
                                                            fg_mode=self.cfg.data_config.fg_mode)
         self.labels = list(self.cfg.data_config.label_fields)
         torch.manual_seed(seed)
-        self.model: RankModel = create_model(self.cfg.model_config, self.features, self.labels, device=self.device)
+        self.sharded, self.grad_sync = [], None
+        if sharding is None:
+            self.model: RankModel = create_model(self.cfg.model_config, self.features, self.labels,
+                                                 device=self.device)
+        else:
+            # tables are built on the meta device and materialised per shard (embedding.py:187-188, main.py:799)
+            from .distributed import DenseGradSync, shard_model
+
+            self.model = create_model(self.cfg.model_config, self.features, self.labels, device=torch.device("meta"))
+            self.sharded = shard_model(self.model, self.device, default=sharding, group=group,
+                                       rw_min_rows=rw_min_rows, constraints=self._table_constraints())
         self.model.to(self.device)
+        if sharding is not None:
+            self.grad_sync = DenseGradSync(self.model.dense_parameters(), group)
         self.model.set_sparse_optimizer(sparse_optimizer_from_config(self.cfg.train_config))
         kw = {}
         if self.device.type == "cuda" and capturable:
@@ -69,6 +82,28 @@ class Pipeline:
         self.train_wrapper = TrainWrapper(self.model)
         torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.train_config.cuda_matmul_allow_tf32)
 
+    def _table_constraints(self) -> Dict[str, List[str]]:
+        """{table: allowed sharding types} from per-feature `embedding_constraints` (features/feature.py:832-845)
+        with train_config.global_embedding_constraints as the fallback (tzrec/main.py:788-790)."""
+        eg = self.model.embedding_group
+        out: Dict[str, List[str]] = {}
+        gc = self.cfg.train_config.global_embedding_constraints
+        default = list(gc.sharding_types) if self.cfg.train_config.HasField("global_embedding_constraints") else []
+        for impl in eg.emb_impls.values():
+            if impl.has_sparse:
+                for c in impl.ebc.embedding_bag_configs():
+                    out[c.name] = default
+            for name, pc in impl._emb_bag_constraints.items():
+                out[name] = pc.sharding_types or default
+        for impl in eg.seq_emb_impls.values():
+            for ec in impl.ec_dict.values():
+                for c in ec.embedding_configs():
+                    out[c.name] = default
+            for consts in impl._dim_to_emb_constraints.values():
+                for name, pc in consts.items():
+                    out[name] = pc.sharding_types or default
+        return out
+
     def synthetic_batch(self, batch_size: int, seed: int = 0, id_dist: str = "uniform") -> Batch:
         b = synthetic_batch(self.features, batch_size, self.labels, seed=seed, id_dist=id_dist)
         for kjt in b.sparse_features.values():
@@ -76,9 +111,14 @@ class Pipeline:
         return b
 
     def eager_step(self, batch: Batch) -> torch.Tensor:
-        self.dense_optimizer.zero_grad(set_to_none=True)
+        if self.grad_sync is not None:
+            self.grad_sync.zero()
+        else:
+            self.dense_optimizer.zero_grad(set_to_none=True)
         loss, _ = self.train_wrapper(batch)
         loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync.sync()
         self.dense_optimizer.step()
         return loss.detach()
 

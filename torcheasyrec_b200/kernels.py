@@ -197,34 +197,55 @@ class CudaKernels:
             _need(state, torch.float32, "state")
         F = lay.num_features
         nnz = ids.numel()
-        nb = self._lib.tzk_fused_bwd_workspace_bytes(nnz, lay.total_keys)
+        nb = self._lib.tzk_fused_bwd_workspace_bytes(nnz, lay.total_keys, lay.max_dim)
         ws = self._workspace("bwd", nb, weights.device)
         check(self._lib.tzk_fused_bwd(
             optimizer, int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
             _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets), F, B, nnz,
             lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
             _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
-        self.launches += 4  # zero_counter, linearize, run_update, long_run_update (+ CUB radix sort)
+        self.launches += 5  # zero_counters, linearize, run_update, long_chunk, long_combine (+ CUB radix sort)
 
     # ------------------------------------------------------------------ K1 / K2
     def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
-                     feat_block: torch.Tensor, want_pos: bool = False):
+                     feat_block: torch.Tensor, want_pos: bool = False, feat_owner: Optional[torch.Tensor] = None,
+                     want_inv: bool = False):
+        """-> (out_lengths [W*F*B], out_offsets [W*F*B+1], out_ids [nnz], out_pos|None, out_inv|None)."""
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         _need(feat_block, torch.int64, "feat_block")
+        if feat_owner is not None:
+            _need(feat_owner, torch.int32, "feat_owner")
         dev = offsets.device
         nnz = ids.numel()
         out_lengths = torch.empty(W * F * B, dtype=torch.int32, device=dev)
         out_offsets = torch.empty(W * F * B + 1, dtype=torch.int64, device=dev)
         out_ids = torch.empty(nnz, dtype=torch.int64, device=dev)
         out_pos = torch.empty(nnz, dtype=torch.int32, device=dev) if want_pos else None
+        out_inv = torch.empty(nnz, dtype=torch.int32, device=dev) if want_inv else None
         nb = self._lib.tzk_bucketize_rw_workspace_bytes(F, B, W, nnz)
         ws = self._workspace("bucketize", nb, dev)
-        check(self._lib.tzk_bucketize_rw(_ptr(ids), _ptr(offsets), F, B, W, _ptr(feat_block), nnz,
+        check(self._lib.tzk_bucketize_rw(_ptr(ids), _ptr(offsets), F, B, W, _ptr(feat_block), _ptr(feat_owner), nnz,
                                          _ptr(out_lengths), _ptr(out_offsets), _ptr(out_ids), _ptr(out_pos),
-                                         _ptr(ws), ws.numel(), _stream()), "tzk_bucketize_rw")
+                                         _ptr(out_inv), _ptr(ws), ws.numel(), _stream()), "tzk_bucketize_rw")
         self.launches += 5
-        return out_lengths, out_offsets, out_ids, out_pos
+        return out_lengths, out_offsets, out_ids, out_pos, out_inv
+
+    def bag_grad_expand(self, grad_out: torch.Tensor, lay: FeatureLayout, offsets: torch.Tensor, slot: torch.Tensor,
+                        B: int, n_rows: int) -> torch.Tensor:
+        """g_rows[slot[l]] = grad_out[b, col_f:+D] (/L for MEAN) for every id position l of bag (f,b)."""
+        grad_out, ld = _rows2d(grad_out, "grad_out")
+        _need(offsets, torch.int64, "offsets")
+        _need(slot, torch.int32, "slot")
+        D = lay.dim[0]
+        if any(d != D for d in lay.dim):
+            raise TzkError("bag_grad_expand: all features must share one dim")
+        out = torch.empty((n_rows, D), dtype=torch.float32, device=grad_out.device)
+        check(self._lib.tzk_bag_grad_expand(_ptr(grad_out), ld, _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(offsets),
+                                            _ptr(slot), lay.num_features, B, D, _ptr(out), _stream()),
+              "tzk_bag_grad_expand")
+        self.launches += 1
+        return out
 
     def permute_lengths(self, lengths: torch.Tensor, perm: torch.Tensor, B: int) -> torch.Tensor:
         _need(lengths, torch.int32, "lengths")
