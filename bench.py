@@ -109,14 +109,15 @@ def cpu_step_rate(model: str, batch: int, steps: int, warmup: int, max_rows: int
     torch.set_num_threads(cores)
     pipe = Pipeline(model, device="cpu", max_rows=max_rows or None)
     batches = [pipe.synthetic_batch(batch, seed=100 + i, id_dist=id_dist) for i in range(2)]
-    with Fn.use_backend(OracleKernels()):
+    backend = OracleKernels(use_c=True)   # C/OpenMP restatement when oracle/libtzk_oracle.so is built
+    with Fn.use_backend(backend):
         for i in range(warmup):
             pipe.eager_step(batches[i % 2])
         t0 = time.perf_counter()
         for i in range(steps):
             pipe.eager_step(batches[i % 2])
         dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3, cores, OracleKernels.name
+    return batch * steps / dt, dt / steps * 1e3, cores, backend.name
 
 
 def run_reference(args):
@@ -175,21 +176,39 @@ def run_ours(args):
     from torcheasyrec_b200.kernels import default_kernels
 
     B, K, W = args.batch_size, args.steps, max(args.warmup, 3)
-    pipe = Pipeline(args.model, device=dev, max_rows=args.max_rows or None)
-    if world > 1:
-        from torcheasyrec_b200.distributed import shard_pipeline
-
-        shard_pipeline(pipe, "row_wise")
+    pipe = Pipeline(args.model, device=dev, max_rows=args.max_rows or None,
+                    sharding="row_wise" if world > 1 else None)
     host = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + i, id_dist=args.id_dist).pin_memory()
             for i in range(args.ring)]
     ring = [hb.to(dev) for hb in host]
     kern = default_kernels()
-    step = GraphedTrainStep(pipe, host[0], warmup=3)
-    launches_before = kern.launches
-    # count this step's own kernels once (eager replica of the captured step on the static inputs)
-    step._fresh_kjt_caches()
-    pipe.eager_step(step.static)
-    launches_per_step = kern.launches - launches_before
+    if world == 1:
+        step = GraphedTrainStep(pipe, host[0], warmup=3)
+        launches_before = kern.launches
+        # count this step's own kernels once (eager replica of the captured step on the static inputs)
+        step._fresh_kjt_caches()
+        pipe.eager_step(step.static)
+        launches_per_step = kern.launches - launches_before
+    else:
+        # sharded steps read the per-peer id counts on the host every step (split sizes of the all-to-alls),
+        # so they run eagerly instead of as one CUDA graph
+        class EagerStep:
+            def __init__(self):
+                self.cur = None
+
+            def load(self, batch, non_blocking=True):
+                self.cur = batch.to(dev, non_blocking=non_blocking) if not batch.labels[pipe.labels[0]].is_cuda else batch
+                for k, kjt in batch.sparse_features.items():
+                    self.cur.sparse_features[k]._length_per_key = kjt._length_per_key
+
+            def replay(self):
+                return pipe.eager_step(self.cur)
+
+        step = EagerStep()
+        step.load(ring[0])
+        launches_before = kern.launches
+        step.replay()
+        launches_per_step = kern.launches - launches_before
     torch.cuda.synchronize()
 
     def barrier():
@@ -240,6 +259,10 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernels (rank 0, standalone launches on the same inputs) -----------------
+    if world > 1:
+        roofline, cpu = None, None
+        _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
+        return
     ebc = pipe.model.sparse_collections()[0]
     lay = ebc.layout
     offs = [kern.lengths_to_offsets(b.sparse_features["__BASE__"].lengths()) for b in ring]
@@ -280,6 +303,10 @@ def run_ours(args):
                              f"restatement ({ms_cpu:.0f} ms/step)"}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
+
+
+def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, ring_len):
     global_batch = B * world
     h2d = host[0].nbytes()
     line = {
@@ -291,8 +318,8 @@ def run_ours(args):
                                f"row-wise over {world} rank(s), per-rank batch {B}, sparse Adagrad lr=1e-3 fused in "
                                f"backward + dense Adam, ids {args.id_dist}",
                    "global_batch": global_batch, "parallelism": f"rw{world}+dp{world}",
-                   "l2": f"inputs rotate over {len(ring)} distinct batches; tables 12.2 GiB + state 12.2 GiB >> 126 MB L2",
-                   "cuda_graph": True},
+                   "l2": f"inputs rotate over {ring_len} distinct batches; tables 12.2 GiB + state 12.2 GiB >> 126 MB L2",
+                   "cuda_graph": world == 1},
         "e2e": {"value": global_batch * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last},
         "gpu_launches": launches_per_step * K,

@@ -28,15 +28,34 @@ def _tables(weights, lay):
     return tabs, feat_table
 
 
+def _c(a):
+    return np.ascontiguousarray(_np(a)) if a is not None else None
+
+
 class OracleKernels:
+    """use_c=True routes the heavy steps through oracle/libtzk_oracle.so (C/OpenMP, same arithmetic); the CPU
+    baseline of bench.py uses that, parity tests default to the numpy restatement."""
+
     name = "oracle"
+
+    def __init__(self, use_c: bool = False) -> None:
+        self.use_c = False
+        if use_c:
+            from oracle import c_oracle
+
+            if c_oracle.available():
+                self.use_c, self.C = True, c_oracle
+                self.name = "oracle-c"
 
     def lengths_to_offsets(self, lengths):
         return torch.from_numpy(O.lengths_to_offsets(_np(lengths)))
 
     def pooled_gather_fwd(self, weights, lay, ids, offsets, B, out=None):
-        tabs, ft = _tables(weights, lay)
-        res = torch.from_numpy(O.pooled_lookup(tabs, ft, lay.pool, _np(ids), _np(offsets), B))
+        if self.use_c:
+            res = torch.from_numpy(self.C.pooled_lookup(_c(weights), lay, _c(ids), _c(offsets), B))
+        else:
+            tabs, ft = _tables(weights, lay)
+            res = torch.from_numpy(O.pooled_lookup(tabs, ft, lay.pool, _np(ids), _np(offsets), B))
         if out is not None:
             out.copy_(res)
             return out
@@ -47,6 +66,11 @@ class OracleKernels:
         return torch.from_numpy(O.seq_lookup(tabs, ft, _np(ids), _np(offsets), B))
 
     def fused_bwd(self, optimizer, pooled, grad_out, weights, state, lay, ids, offsets, B, lr, eps, grad_scale=1.0):
+        if self.use_c and pooled:
+            self.C.fused_update(optimizer, _np(grad_out), weights.detach().numpy(),
+                                None if state is None else state.numpy(), lay, _c(ids), _c(offsets), B, lr, eps,
+                                grad_scale)
+            return
         tabs, ft = _tables(weights, lay)
         states = [None] * len(tabs)
         if state is not None:
@@ -106,14 +130,23 @@ class OracleKernels:
         return torch.from_numpy(O.padded_to_jagged(_np(grad_out), _np(offsets), nnz))
 
     def fm_fwd(self, x, N, D):
+        if self.use_c:
+            return torch.from_numpy(self.C.fm_fwd(_c(x), N, D))
         return torch.from_numpy(O.fm(_np(x).reshape(-1, N, D)))
 
     def fm_bwd(self, x, dy, N, D):
+        if self.use_c:
+            return torch.from_numpy(self.C.fm_bwd(_c(x), _c(dy), N, D))
         return torch.from_numpy(O.fm_bwd(_np(x).reshape(-1, N, D), _np(dy)).reshape(-1, N * D))
 
     def dot_interact_fwd(self, dense, sparse, Ns, D, copy_dense, copy_sparse):
+        if self.use_c:
+            return torch.from_numpy(self.C.dot_interact_fwd(_c(dense), _c(sparse), Ns, D, copy_dense, copy_sparse))
         return torch.from_numpy(O.dlrm_interact(_np(dense), _np(sparse), Ns, D, copy_dense, copy_sparse))
 
     def dot_interact_bwd(self, dense, sparse, d_out, Ns, D, copy_dense, copy_sparse):
+        if self.use_c:
+            dd, ds = self.C.dot_interact_bwd(_c(dense), _c(sparse), _c(d_out), Ns, D, copy_dense, copy_sparse)
+            return (None if dd is None else torch.from_numpy(dd)), torch.from_numpy(ds)
         dd, ds = O.dlrm_interact_bwd(_np(dense), _np(sparse), _np(d_out), Ns, D, copy_dense, copy_sparse)
         return (None if dd is None else torch.from_numpy(dd)), torch.from_numpy(ds)

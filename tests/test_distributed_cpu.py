@@ -49,11 +49,18 @@ def _concat_batches(batches):
     return out
 
 
-def _worker(rank, world, port, name, sharding, rw_min_rows, result_q):
+def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.set_num_threads(1)
+    dev = f"cuda:{rank}" if use_cuda else "cpu"
+    if use_cuda:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(1)
     try:
+        import contextlib
+
         from oracle_backend import OracleKernels
 
         from torcheasyrec_b200 import functional as Fn
@@ -61,30 +68,32 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q):
         from torcheasyrec_b200.engine import Pipeline
 
         B = 48
-        with Fn.use_backend(OracleKernels()):
-            ref = Pipeline(name, device="cpu", max_rows=300, seed=5)               # unsharded twin (same on all ranks)
-            shd = Pipeline(name, device="cpu", max_rows=300, seed=5)
+        # CPU: host logic over gloo with the oracle as compute; GPU: the CUDA kernels over NCCL
+        with (contextlib.nullcontext() if use_cuda else Fn.use_backend(OracleKernels())):
+            ref = Pipeline(name, device=dev, max_rows=300, seed=5, capturable=False)   # unsharded twin
+            shd = Pipeline(name, device=dev, max_rows=300, seed=5, capturable=False)
             shd.model.load_state_dict(ref.model.state_dict())
-            sharded = shard_model(shd.model, "cpu", default=sharding, rw_min_rows=rw_min_rows, source=ref.model)
+            sharded = shard_model(shd.model, dev, default=sharding, rw_min_rows=rw_min_rows, source=ref.model)
             shd.model.set_sparse_optimizer(ref.model.sparse_collections()[0].optimizer)
             from torcheasyrec_b200.rank_models import dense_optimizer_from_config
 
             shd.dense_optimizer = dense_optimizer_from_config(shd.cfg.train_config, shd.model.dense_parameters())
             shd.grad_sync = DenseGradSync(shd.model.dense_parameters())
             batches = [ref.synthetic_batch(B, seed=77 + r) for r in range(world)]
-            glob = _concat_batches(batches)
+            glob = _concat_batches(batches).to(dev)
+            batches = [b.to(dev) for b in batches]
             # forward parity (before any update)
             with torch.no_grad():
                 p_ref = ref.model.predict(glob)
                 p_shd = shd.model.predict(batches[rank])
             for k, v in p_shd.items():
                 if k.startswith("logits"):
-                    np.testing.assert_array_equal(v.numpy(), p_ref[k][rank * B:(rank + 1) * B].numpy())
+                    np.testing.assert_array_equal(v.cpu().numpy(), p_ref[k][rank * B:(rank + 1) * B].cpu().numpy())
             # one train step on both
             for _ in range(2):
                 loss_ref = ref.eager_step(glob)
                 loss_shd = shd.eager_step(batches[rank])
-            t = torch.tensor([float(loss_shd)], dtype=torch.float64)
+            t = torch.tensor([float(loss_shd)], dtype=torch.float64, device=dev)
             dist.all_reduce(t)
             np.testing.assert_allclose(t.item() / world, float(loss_ref), rtol=1e-6)
             # updated tables: gather shards, compare with the unsharded twin
@@ -98,13 +107,13 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q):
                     full = sm.gather_full_table(c.name)
                     # dL/dlogit is 1/B per rank then /W on the owners vs 1/(W*B) in the twin: same value, one more
                     # fp32 rounding per contribution -> a few ulp after two Adagrad steps
-                    np.testing.assert_allclose(full.numpy(), ref_tables[(kind, c.name)].numpy(), rtol=5e-5, atol=1e-6,
+                    np.testing.assert_allclose(full.cpu().numpy(), ref_tables[(kind, c.name)].cpu().numpy(), rtol=5e-5, atol=1e-6,
                                                err_msg=f"{kind}.{c.name}")
             dense = lambda m: sorted((n, p) for n, p in m.named_parameters() if not n.endswith("weights"))
             for (n1, p1), (n2, p2) in zip(dense(ref.model), dense(shd.model)):
                 assert n1 == n2
                 # Adam normalises by sqrt(v): tiny gradient differences (mean over 2B vs mean of two means) are amplified
-                np.testing.assert_allclose(p2.detach().numpy(), p1.detach().numpy(), rtol=2e-4, atol=2e-6, err_msg=n1)
+                np.testing.assert_allclose(p2.detach().cpu().numpy(), p1.detach().cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=n1)
         result_q.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
         import traceback
@@ -114,11 +123,12 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q):
         dist.destroy_process_group()
 
 
-def _run(world, name, sharding, rw_min_rows=0):
+def _run(world, name, sharding, rw_min_rows=0, use_cuda=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, sharding, rw_min_rows, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, sharding, rw_min_rows, q, use_cuda))
+             for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]

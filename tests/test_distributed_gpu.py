@@ -1,0 +1,26 @@
+"""N>1 on real GPUs (needs >= 2 devices: `gpurun --gpus 2 -- python -m pytest tests/test_distributed_gpu.py`):
+the same sharded-vs-unsharded comparison as tests/test_distributed_cpu.py, but with the CUDA kernels as compute and
+NCCL all-to-alls.  Skipped on single-GPU boxes."""
+import pytest
+import torch
+
+from test_distributed_cpu import _run
+
+pytestmark = pytest.mark.gpu
+need2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+
+
+@need2
+@pytest.mark.parametrize("sharding", ["row_wise", "table_wise"])
+def test_dlrm_two_gpus(sharding):
+    _run(2, "dlrm_criteo", sharding, use_cuda=True)
+
+
+@need2
+def test_deepfm_mixed_two_gpus():
+    _run(2, "deepfm_criteo", "mixed", rw_min_rows=200, use_cuda=True)
+
+
+@need2
+def test_din_sequence_two_gpus():
+    _run(2, "multi_tower_din_taobao", "mixed", rw_min_rows=250, use_cuda=True)
