@@ -233,16 +233,23 @@ def run_ours(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     # ---- e2e: pinned host batch -> H2D -> step -> loss back on the host, every step --------------------------
+    # (N=1: the H2D of batch i+1 runs on the copy stream while step i computes; the loss of every step is read)
+    piped = world == 1
     for i in range(2):
         step.load(host[i % len(host)])
         step.replay()
     barrier()
-    t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     last = 0.0
+    if piped:
+        step.prefetch(host[0])
     for i in range(K):
-        step.load(host[i % len(host)], non_blocking=True)
+        if piped:
+            step.commit()
+            step.prefetch(host[(i + 1) % len(host)])
+        else:
+            step.load(host[i % len(host)], non_blocking=True)
         loss = step.replay()
         last = float(loss.item())          # device -> host read of the step's result
     g1.record()

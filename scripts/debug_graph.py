@@ -11,7 +11,8 @@ b = Pipeline("dlrm_criteo", device="cuda:0", max_rows=5000, seed=3)
 b.model.load_state_dict(a.model.state_dict())
 for ca, cb in zip(a.model.sparse_collections(), b.model.sparse_collections()):
     cb.opt_state.copy_(ca.opt_state)
-b.dense_optimizer.load_state_dict(a.dense_optimizer.state_dict())
+import copy
+b.dense_optimizer.load_state_dict(copy.deepcopy(a.dense_optimizer.state_dict()))
 
 
 def report(tag):

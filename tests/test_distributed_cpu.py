@@ -88,7 +88,11 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
                 p_shd = shd.model.predict(batches[rank])
             for k, v in p_shd.items():
                 if k.startswith("logits"):
-                    np.testing.assert_array_equal(v.cpu().numpy(), p_ref[k][rank * B:(rank + 1) * B].cpu().numpy())
+                    want = p_ref[k][rank * B:(rank + 1) * B].cpu().numpy()
+                    if use_cuda:   # cuBLAS may pick another kernel for batch B vs W*B: not bit-stable across shapes
+                        np.testing.assert_allclose(v.cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+                    else:
+                        np.testing.assert_array_equal(v.cpu().numpy(), want)
             # one train step on both
             for _ in range(2):
                 loss_ref = ref.eager_step(glob)

@@ -1,6 +1,7 @@
 """Model-level parity on the GPU: every BASELINE model family (small tables) stepped through the CUDA path and
 through the oracle backend from identical weights and batches: logits, loss and the embedding arenas after the
 fused update must agree (<= 1e-5 rel; BASELINE.json north_star)."""
+import copy
 import os
 import sys
 
@@ -63,7 +64,8 @@ def test_cuda_graph_step_equals_eager_step():
     b.model.load_state_dict(a.model.state_dict())
     for ca, cb in zip(a.model.sparse_collections(), b.model.sparse_collections()):
         cb.opt_state.copy_(ca.opt_state)
-    b.dense_optimizer.load_state_dict(a.dense_optimizer.state_dict())
+    # deepcopy: Optimizer.load_state_dict keeps same-device tensors by reference, the twins must not share moments
+    b.dense_optimizer.load_state_dict(copy.deepcopy(a.dense_optimizer.state_dict()))
     losses_a, losses_b = [], []
     for bt in batches[1:]:
         step.load(bt.pin_memory())

@@ -116,16 +116,37 @@ fm_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------
-// A9/A10: dot interaction.  One warp per sample.  X_b (N x D) is staged in shared memory with a row
-// stride of D+4 floats (keeps 16-B alignment, spreads rows over banks); each lane owns 4x4 blocks of the
-// Gram matrix (only blocks touching the strict upper triangle), so every k step costs 2 LDS.128 for
-// 16 FMAs.  Results are staged in shared memory and the whole output row [P | D | Ns*D] is written
-// with coalesced stores.
+// A9/A10: dot interaction.  One warp per sample, persistent over samples.
+//  * X_b (N x D) is staged in shared memory, row stride D+4 floats, 16-B chunks XOR-swizzled by (row>>3) so
+//    that the eight lanes of a quarter-warp, which read the same chunk of rows 4 apart, hit eight different
+//    bank groups (unswizzled they collide 4-way);
+//  * each lane owns 4x4 blocks of the Gram matrix (only blocks touching the strict upper triangle): every k
+//    step costs 2 LDS.128 per 16 FMAs; the (bi,bj) decode is a per-CTA lookup table, not per-sample maths;
+//  * results are staged in shared memory and the whole output row [P | D | Ns*D] leaves with coalesced stores.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kIWarps = 8;  // warps (= samples in flight) per CTA
 
 __device__ __forceinline__ int tri_index(int i, int j, int N) {  // i < j
   return i * N - (i * (i + 1)) / 2 + (j - i - 1);
+}
+__device__ __forceinline__ int swz_mask(int D4) {  // XOR range must stay inside the row's D4 chunks
+  return ((D4 & (D4 - 1)) == 0) ? (D4 - 1 < 3 ? D4 - 1 : 3) : 0;
+}
+// float offset of chunk c4 of row `row`
+__device__ __forceinline__ int xoff(int row, int c4, int DS, int swm) { return row * DS + ((c4 ^ ((row >> 3) & swm)) << 2); }
+
+__device__ __forceinline__ void stage_x(float* X, const float* dense, int64_t ld_dense, const float* sparse,
+                                        int64_t ld_sparse, int64_t b, int Ns, int N, int Np, int D4, int DS, int swm,
+                                        int lane) {
+  const int doff = dense ? 1 : 0;
+  const float* sp = sparse + b * ld_sparse;
+  for (int i = lane; i < Ns * D4; i += 32) {
+    const int r = i / D4, c4 = i - r * D4;
+    *reinterpret_cast<float4*>(X + xoff(r + doff, c4, DS, swm)) = ld_row_f4(sp + (int64_t)r * (D4 * 4) + c4 * 4);
+  }
+  if (dense)
+    for (int c4 = lane; c4 < D4; c4 += 32)
+      *reinterpret_cast<float4*>(X + xoff(0, c4, DS, swm)) = ld_row_f4(dense + b * ld_dense + c4 * 4);
 }
 
 __global__ void __launch_bounds__(kIWarps * 32)
@@ -137,53 +158,49 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
   const int Np = (N + 3) & ~3;        // rows padded to a multiple of 4 (pad rows are zero)
   const int DS = D + 4;               // row stride
   const int P = N * (N - 1) / 2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Pp = (P + 3) & ~3;        // keeps every warp's slab 16-B aligned
-  float* X = smem + (size_t)warp * (Np * DS + Pp);
-  float* O = X + Np * DS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = Np / 4;
   const int n_blocks = nb * (nb + 1) / 2;
   const int D4 = D / 4;  // D % 4 == 0 enforced by the host wrapper
+  const int swm = swz_mask(D4);
+  // CTA-wide lookup: block index -> (bi, bj)
+  unsigned short* blk_ij = reinterpret_cast<unsigned short*>(smem);
+  float* slabs = smem + ((n_blocks + 7) / 8) * 4;  // n_blocks u16 rounded up to 16 B
+  for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
+    int bi = 0, rem = blk;
+    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+    blk_ij[blk] = (unsigned short)((bi << 8) | (bi + rem));
+  }
+  float* X = slabs + (size_t)warp * (Np * DS + Pp);
+  float* O = X + Np * DS;
+  // pad rows are zero for the whole kernel
+  for (int i = lane; i < (Np - N) * D4; i += 32) {
+    const int r = N + i / D4, c4 = i % D4;
+    *reinterpret_cast<float4*>(X + xoff(r, c4, DS, swm)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int doff = dense ? 1 : 0;
 
   for (int64_t b = (int64_t)blockIdx.x * kIWarps + warp; b < B; b += (int64_t)gridDim.x * kIWarps) {
-    // ---- stage X_b ------------------------------------------------------------------------------
-    const float* sp = sparse + b * ld_sparse;
-    const int doff = dense ? 1 : 0;
-    for (int i = lane; i < Ns * D4; i += 32) {
-      const int r = i / D4, c4 = i - r * D4;
-      float4 v = ld_row_f4(sp + (int64_t)r * D + c4 * 4);
-      *reinterpret_cast<float4*>(X + (r + doff) * DS + c4 * 4) = v;
-    }
-    if (dense) {
-      for (int c4 = lane; c4 < D4; c4 += 32)
-        *reinterpret_cast<float4*>(X + c4 * 4) = ld_row_f4(dense + b * ld_dense + c4 * 4);
-    }
-    for (int i = lane; i < (Np - N) * D4; i += 32) {
-      const int r = N + i / D4, c4 = i % D4;
-      *reinterpret_cast<float4*>(X + r * DS + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    stage_x(X, dense, ld_dense, sparse, ld_sparse, b, Ns, N, Np, D4, DS, swm, lane);
     __syncwarp();
     // ---- Gram blocks ------------------------------------------------------------------------------
     for (int blk = lane; blk < n_blocks; blk += 32) {
-      // decode (bi <= bj) from the linear upper-triangular block index
-      int bi = 0, rem = blk;
-      while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
-      const int bj = bi + rem;
-      const float* xi = X + (bi * 4) * DS;
-      const float* xj = X + (bj * 4) * DS;
+      const int bi = blk_ij[blk] >> 8, bj = blk_ij[blk] & 0xff;
       float acc[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-      for (int k = 0; k < D; k += 4) {
+      for (int c4 = 0; c4 < D4; ++c4) {
         float4 a[4], bb[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          a[r] = *reinterpret_cast<const float4*>(xi + r * DS + k);
-          bb[r] = *reinterpret_cast<const float4*>(xj + r * DS + k);
+          a[r] = *reinterpret_cast<const float4*>(X + xoff(bi * 4 + r, c4, DS, swm));
+          bb[r] = *reinterpret_cast<const float4*>(X + xoff(bj * 4 + r, c4, DS, swm));
         }
-        // accumulate in k order (k, k+1, k+2, k+3) so the sum order matches a sequential dot product
+        // accumulate in k order so the sum order matches a sequential dot product
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -208,13 +225,13 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
     for (int i = lane; i < P; i += 32) orow[i] = O[i];
     int o = P;
     if (copy_dense && dense) {
-      for (int c = lane; c < D; c += 32) orow[o + c] = X[c];
+      for (int c = lane; c < D; c += 32) orow[o + c] = X[xoff(0, c >> 2, DS, swm) + (c & 3)];
       o += D;
     }
     if (copy_sparse) {
       for (int i = lane; i < Ns * D; i += 32) {
         const int r = i / D, c = i - r * D;
-        orow[o + i] = X[(r + doff) * DS + c];
+        orow[o + i] = X[xoff(r + doff, c >> 2, DS, swm) + (c & 3)];
       }
     }
     __syncwarp();
@@ -231,43 +248,38 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;
   const int DS = D + 4;
-  const int SS = Np + 4;  // stride of the symmetric grad matrix
+  const int SS = Np + 8;  // stride of the symmetric grad matrix: the transposed scatter is 4-way, not 32-way
   const int P = N * (N - 1) / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* X = smem + (size_t)warp * (Np * DS + Np * SS);
-  float* S = X + Np * DS;
   const int D4 = D / 4;
+  const int swm = swz_mask(D4);
   const int nb = Np / 4;
   const int doff = dense ? 1 : 0;
+  // CTA-wide lookup: triangular index -> (i, j)
+  unsigned short* pair_ij = reinterpret_cast<unsigned short*>(smem);
+  float* slabs = smem + ((P + 7) / 8) * 4;
+  for (int idx = threadIdx.x; idx < P; idx += blockDim.x) {
+    int i = 0, rs = 0;
+    while (idx >= rs + (N - 1 - i)) { rs += N - 1 - i; ++i; }
+    pair_ij[idx] = (unsigned short)((i << 8) | (i + 1 + (idx - rs)));
+  }
+  float* X = slabs + (size_t)warp * (Np * DS + Np * SS);
+  float* S = X + Np * DS;
+  for (int i = lane; i < (Np - N) * D4; i += 32) {
+    const int r = N + i / D4, c4 = i % D4;
+    *reinterpret_cast<float4*>(X + xoff(r, c4, DS, swm)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = lane; i < Np * SS; i += 32) S[i] = 0.f;  // diagonal + padding stay zero for the whole kernel
+  __syncthreads();
 
   for (int64_t b = (int64_t)blockIdx.x * kIWarps + warp; b < B; b += (int64_t)gridDim.x * kIWarps) {
-    const float* sp = sparse + b * ld_sparse;
-    for (int i = lane; i < Ns * D4; i += 32) {
-      const int r = i / D4, c4 = i - r * D4;
-      *reinterpret_cast<float4*>(X + (r + doff) * DS + c4 * 4) = ld_row_f4(sp + (int64_t)r * D + c4 * 4);
-    }
-    if (dense)
-      for (int c4 = lane; c4 < D4; c4 += 32)
-        *reinterpret_cast<float4*>(X + c4 * 4) = ld_row_f4(dense + b * ld_dense + c4 * 4);
-    for (int i = lane; i < (Np - N) * D4; i += 32) {
-      const int r = N + i / D4, c4 = i % D4;
-      *reinterpret_cast<float4*>(X + r * DS + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int i = lane; i < Np * SS; i += 32) S[i] = 0.f;
-    __syncwarp();
+    stage_x(X, dense, ld_dense, sparse, ld_sparse, b, Ns, N, Np, D4, DS, swm, lane);
     const float* go = d_out + b * ld_dout;
-    // scatter the P upper-triangular grads into the symmetric matrix (coalesced read of d_out)
-    {
-      // walk (i,j) incrementally: lane handles indices lane, lane+32, ...
-      for (int idx = lane; idx < P; idx += 32) {
-        // invert tri_index: find i with row_start(i) <= idx < row_start(i+1)
-        int i = 0, rs = 0;
-        while (idx >= rs + (N - 1 - i)) { rs += N - 1 - i; ++i; }
-        const int j = i + 1 + (idx - rs);
-        const float g = __ldg(go + idx);
-        S[i * SS + j] = g;
-        S[j * SS + i] = g;
-      }
+    for (int idx = lane; idx < P; idx += 32) {  // coalesced read of d_out, symmetric scatter
+      const int i = pair_ij[idx] >> 8, j = pair_ij[idx] & 0xff;
+      const float g = __ldg(go + idx);
+      S[i * SS + j] = g;
+      S[j * SS + i] = g;
     }
     __syncwarp();
     // dX[i0..i0+3][k..k+3] = sum_j S[j][i0..i0+3] * X[j][k..k+3]
@@ -279,9 +291,10 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 3
       for (int j = 0; j < N; ++j) {
         const float4 s4 = *reinterpret_cast<const float4*>(S + j * SS + bi * 4);
-        const float4 x4 = *reinterpret_cast<const float4*>(X + j * DS + c4 * 4);
+        const float4 x4 = *reinterpret_cast<const float4*>(X + xoff(j, c4, DS, swm));
         const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
         const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -289,7 +302,7 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(sv[r], xv[c], acc[r][c]);
       }
-      // pass-through grads and store
+      // pass-through grads and store (16-B vector stores; d_out offsets are not 16-B aligned -> scalar loads)
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int i = bi * 4 + r;
@@ -300,16 +313,14 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
             const float* gp = go + P + c4 * 4;
             v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
           }
-          float* dp = d_dense + b * ld_ddense + c4 * 4;
-          dp[0] = v.x; dp[1] = v.y; dp[2] = v.z; dp[3] = v.w;
+          *reinterpret_cast<float4*>(d_dense + b * ld_ddense + c4 * 4) = v;
         } else {
           const int r_s = i - doff;
           if (copy_sparse) {
             const float* gp = go + P + ((copy_dense && dense) ? D : 0) + r_s * D + c4 * 4;
             v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
           }
-          float* dp = d_sparse + b * ld_dsparse + (int64_t)r_s * D + c4 * 4;
-          dp[0] = v.x; dp[1] = v.y; dp[2] = v.z; dp[3] = v.w;
+          *reinterpret_cast<float4*>(d_sparse + b * ld_dsparse + (int64_t)r_s * D + c4 * 4) = v;
         }
       }
     }
@@ -409,7 +420,8 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
-  size_t smem = (size_t)kIWarps * (Np * (D + 4) + ((P + 3) & ~3)) * sizeof(float);
+  const int nb = Np / 4, n_blocks = nb * (nb + 1) / 2;
+  size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3) & ~3))) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(dot_interact_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dot_interact_fwd_kernel<<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>(
@@ -427,9 +439,13 @@ extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const 
   if (rc) return rc;
   if (B == 0) return 0;
   TZK_REQUIRE(d_out && d_sparse && (!dense || d_dense), "dot_interact_bwd: NULL argument");
+  TZK_REQUIRE(((uintptr_t)d_sparse % 16 == 0) && (ld_dsparse % 4 == 0) &&
+                  (!dense || (((uintptr_t)d_dense % 16 == 0) && (ld_ddense % 4 == 0))),
+              "dot_interact_bwd: gradient outputs must be 16-B aligned");
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;
-  size_t smem = (size_t)kIWarps * (Np * (D + 4) + Np * (Np + 4)) * sizeof(float);
+  const int P = N * (N - 1) / 2;
+  size_t smem = ((size_t)((P + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + Np * (Np + 8))) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(dot_interact_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dot_interact_bwd_kernel<<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>(

@@ -146,6 +146,7 @@ class GraphedTrainStep:
             self.static.sparse_features[k]._length_per_key = kjt._length_per_key
         self._static_tensors = _tensors_of(self.static)
         self.copy_stream = torch.cuda.Stream()
+        self._staging = None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -173,6 +174,28 @@ class GraphedTrainStep:
         """Copies a batch (host pinned or device) into the static buffers on the current stream."""
         for dst, src in zip(self._static_tensors, _tensors_of(batch)):
             dst.copy_(src, non_blocking=non_blocking)
+
+    # ---- double-buffered host feed (the memcpy stream of TrainPipelineSparseDist, dist_util.py:221-303) --------
+    def prefetch(self, batch: Batch) -> None:
+        """Starts the pinned-host -> device copy of the NEXT batch on the copy stream (overlaps the running step)."""
+        if self._staging is None:
+            self._staging = [torch.empty_like(t) for t in self._static_tensors]
+            self._ready = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._consumed)      # previous staged batch has been committed
+            for dst, src in zip(self._staging, _tensors_of(batch)):
+                dst.copy_(src, non_blocking=True)
+            self._ready.record(self.copy_stream)
+
+    def commit(self) -> None:
+        """Moves the staged batch into the graph's static inputs (device-to-device, on the compute stream)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready)
+        for dst, src in zip(self._static_tensors, self._staging):
+            dst.copy_(src, non_blocking=True)
+        self._consumed.record(cur)
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()
