@@ -75,3 +75,28 @@ def test_cuda_graph_step_equals_eager_step():
     wa = a.model.sparse_collections()[0].weights.detach().cpu().numpy()
     wb = b.model.sparse_collections()[0].weights.detach().cpu().numpy()
     np.testing.assert_allclose(wa, wb, rtol=1e-6, atol=1e-8)
+
+
+def test_bf16x9_linear_matches_fp32_linear():
+    """Dense-tower GEMMs on the tensor cores (cuBLASLt 12.9 BF16x9) stay within fp32 accuracy."""
+    from torcheasyrec_b200 import dense_gemm
+
+    if not dense_gemm.available():
+        pytest.skip("cuBLASLt >= 12.9 not loadable on this box")
+    torch.manual_seed(0)
+    for (B, K, N) in [(4096, 783, 64), (2048, 13, 64), (1024, 64, 1), (512, 429, 512)]:
+        x = torch.randn(B, K, device="cuda", requires_grad=True)
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).requires_grad_()
+        b = torch.randn(N, device="cuda", requires_grad=True)
+        y = dense_gemm.linear(x, w, b)
+        g = torch.randn_like(y)
+        y.backward(g)
+        got = (y.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone())
+        x.grad = w.grad = b.grad = None
+        y2 = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        y2.backward(g.double())
+        want = (y2.detach(), x.grad, w.grad, b.grad)
+        for a, e in zip(got, want):
+            scale = float(e.abs().max())
+            assert float((a.double() - e.double()).abs().max()) <= 2e-6 * max(scale, 1.0) * max(1.0, (K / 64) ** 0.5)
+    print("dense_gemm stats:", dense_gemm.stats())

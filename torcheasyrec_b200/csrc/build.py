@@ -52,7 +52,18 @@ def build(verbose: bool = False, force: bool = False) -> str:
     if force or procs or _mtime(LIB) < max(_mtime(o) for o in objs):
         cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs]
         subprocess.run(cmd, check=True)
+    build_gemm(force)
     return LIB
+
+
+def build_gemm(force: bool = False) -> str:
+    """libtzk_gemm.so: the cuBLASLt-12.9 BF16x9 wrapper for the dense towers (host C++, dlopen at run time)."""
+    src = os.path.join(HERE, "tzk_gemm.cpp")
+    lib = os.path.join(HERE, "libtzk_gemm.so")
+    if force or _mtime(lib) < _mtime(src):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include", src, "-o", lib,
+                        "-ldl"], check=True)
+    return lib
 
 
 if __name__ == "__main__":

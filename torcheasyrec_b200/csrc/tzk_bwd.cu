@@ -291,7 +291,7 @@ __device__ __forceinline__ void load_grad(const float* p, float (&g)[VEC]) {
 // sorted positions; one CTA reduces one chunk (4a).  Single-chunk runs are finished by that CTA; multi-chunk
 // runs park per-chunk partial sums that 4b adds up in chunk order — so the result does not depend on which
 // CTA ran what.
-constexpr int kChunk = 1024;
+constexpr int kChunk = 256;
 struct ChunkItem {
   int32_t start, end;   // sorted positions [start, end)
   int32_t n_chunks;     // chunks of the run
@@ -308,6 +308,9 @@ struct WorkLists {
 };
 
 // CH = float4 (or scalar) chunks per lane: dims up to G*VEC*CH are supported.
+// Each lane group owns kPos consecutive sorted positions per iteration.  Runs of length 1 (the common case on
+// big tables) take a batched path: the gradient / weight / state rows of all of them are requested before any
+// is consumed, so a group keeps 3*kPos independent 64-B requests in flight instead of one dependent chain.
 template <typename KeyT, int G, int VEC, int CH>
 __global__ void __launch_bounds__(kThreads)
 run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
@@ -319,80 +322,170 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
 
   constexpr int NG = kThreads / G;
+  constexpr int kPos = (CH == 1) ? 4 : 1;
   const int lane = threadIdx.x % G;
-  const int64_t stride = (int64_t)gridDim.x * NG;
-  // all G lanes of a group follow the same control flow (p, key, len are group-uniform)
-  for (int64_t p = (int64_t)blockIdx.x * NG + threadIdx.x / G; p < a.n; p += stride) {
-    // independent loads first: neighbours decide head / run length 1, v0 addresses the gradient row
-    const KeyT key = keys[p];
-    const KeyT kprev = p > 0 ? keys[p - 1] : (KeyT)~key;
-    const KeyT knext = p + 1 < a.n ? keys[p + 1] : (KeyT)~key;
-    const int32_t v0 = vals[p];
-    if (kprev == key) continue;  // not a run head
-    int len = 1;
-    if (knext == key) {
-      len = 2;
-      while (len <= kShortRun && p + len < a.n && keys[p + len] == key) ++len;
+  const int64_t stride = (int64_t)gridDim.x * NG * kPos;
+  // all G lanes of a group follow the same control flow (positions, keys, run lengths are group-uniform)
+  for (int64_t p0 = ((int64_t)blockIdx.x * NG + threadIdx.x / G) * kPos; p0 < a.n; p0 += stride) {
+    KeyT key[kPos + 2];  // key[0] = left neighbour, key[kPos+1] = right neighbour
+    int32_t v[kPos];
+    key[0] = p0 > 0 ? keys[p0 - 1] : (KeyT)~keys[p0];
+#pragma unroll
+    for (int u = 0; u < kPos; ++u) {
+      const int64_t p = p0 + u;
+      key[u + 1] = p < a.n ? keys[p] : (KeyT)~key[u];
+      v[u] = p < a.n ? vals[p] : 0;
     }
-    if (len > kShortRun) {
-      if (lane == 0) {
-        // gallop + binary search for the end of the run, then enqueue its chunks
-        int64_t lo = p + kShortRun, step = kShortRun;  // keys[lo] == key
-        int64_t hi = lo + step;
-        while (hi < a.n && keys[hi] == key) { lo = hi; step <<= 1; hi = lo + step; }
-        if (hi > a.n) hi = a.n;
-        while (hi - lo > 1) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (keys[mid] == key) lo = mid; else hi = mid;
-        }
-        const int64_t end = hi;
-        const int n_chunks = (int)((end - p + kChunk - 1) / kChunk);
-        const int base = atomicAdd(wl.counters + 0, n_chunks);
-        int pslot = -1;
-        if (n_chunks > 1) {
-          pslot = atomicAdd(wl.counters + 2, n_chunks);
-          LongRun lr; lr.head = (int32_t)p; lr.pslot = pslot; lr.n_chunks = n_chunks; lr.pad = 0;
-          wl.runs[atomicAdd(wl.counters + 1, 1)] = lr;
-        }
-        for (int c = 0; c < n_chunks; ++c) {
-          ChunkItem it;
-          it.start = (int32_t)(p + (int64_t)c * kChunk);
-          it.end = (int32_t)((p + (int64_t)(c + 1) * kChunk) < end ? (p + (int64_t)(c + 1) * kChunk) : end);
-          it.n_chunks = n_chunks;
-          it.pslot = n_chunks > 1 ? pslot + c : -1;
-          wl.items[base + c] = it;
-        }
-      }
-      continue;
+    {
+      const int64_t pn = p0 + kPos;
+      key[kPos + 1] = pn < a.n ? keys[pn] : (KeyT)~key[kPos];
     }
-    int f0;
-    if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
-    const BwdFeat d = fd[f0];
-    const int64_t row = (int64_t)key - d.key_base;
-
-    float acc[CH][VEC];
+    bool head[kPos], single[kPos];
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
+    for (int u = 0; u < kPos; ++u) {
+      head[u] = (p0 + u < a.n) && key[u + 1] != key[u];
+      single[u] = head[u] && ((p0 + u + 1 >= a.n) || key[u + 2] != key[u + 1]);
+    }
+    if (CH == 1) {
+      // ---- batched path: runs of length 1 -------------------------------------------------------------
+      float g[kPos][VEC], w[kPos][VEC], s[kPos][VEC];
+      float scale[kPos];
+      int f0[kPos];
+      const int c = lane * VEC;
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-    for (int j = 0; j < len; ++j) {
-      const Entry en = entry_of(a, fd, j == 0 ? v0 : vals[p + j], f0);
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        const int c = (ch * G + lane) * VEC;
+      for (int u = 0; u < kPos; ++u) {
+        f0[u] = 0;
+        scale[u] = 0.f;
+        if (!single[u]) continue;
+        f0[u] = a.pooled ? v[u] / a.B : feat_of_key<KeyT>(fd, a.F, key[u + 1]);
+        const BwdFeat& d = fd[f0[u]];
+        const Entry en = entry_of(a, fd, v[u], f0[u]);
+        scale[u] = en.scale;
         if (c < d.dim) {
-          float g[VEC];
-          load_grad<VEC>(en.g + c, g);
+          const int64_t row = (int64_t)key[u + 1] - d.key_base;
+          load_grad<VEC>(en.g + c, g[u]);
+          const float* wp = a.weights + d.w_off + row * d.dim + c;
+          if (VEC == 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp);
+            w[u][0] = w4.x; w[u][1] = w4.y; w[u][2] = w4.z; w[u][3] = w4.w;
+            if (a.optimizer == TZK_OPT_ADAGRAD) {
+              const float4 s4 = *reinterpret_cast<const float4*>(a.state + d.w_off + row * d.dim + c);
+              s[u][0] = s4.x; s[u][1] = s4.y; s[u][2] = s4.z; s[u][3] = s4.w;
+            }
+          } else {
+            w[u][0] = wp[0];
+            if (a.optimizer == TZK_OPT_ADAGRAD) s[u][0] = a.state[d.w_off + row * d.dim + c];
+          }
+        }
+      }
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) acc[ch][k] += g[k] * en.scale;
+      for (int u = 0; u < kPos; ++u) {
+        if (!single[u]) continue;
+        const BwdFeat& d = fd[f0[u]];
+        const int64_t row = (int64_t)key[u + 1] - d.key_base;
+        float gv[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) gv[k] = (c < d.dim) ? (0.f + g[u][k] * scale[u]) : 0.f;
+        float rw_denom = 1.f;
+        if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {
+          float ss = 0.f;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k)
+            if (c + k < d.dim) ss += gv[k] * gv[k];
+          ss = group_sum<G>(ss);
+          float sr = 0.f;
+          if (lane == 0) {
+            sr = a.state[key[u + 1]] + ss / (float)d.dim;
+            a.state[key[u + 1]] = sr;
+          }
+          sr = __shfl_sync(group_mask<G>(), sr, 0, G);
+          rw_denom = sqrtf(sr) + a.eps;
+        }
+        if (c < d.dim) {
+          apply_update<VEC>(a, w[u], s[u], gv, rw_denom);
+          float* wp = a.weights + d.w_off + row * d.dim + c;
+          if (VEC == 4) {
+            *reinterpret_cast<float4*>(wp) = make_float4(w[u][0], w[u][1], w[u][2], w[u][3]);
+            if (a.optimizer == TZK_OPT_ADAGRAD)
+              *reinterpret_cast<float4*>(a.state + d.w_off + row * d.dim + c) =
+                  make_float4(s[u][0], s[u][1], s[u][2], s[u][3]);
+          } else {
+            wp[0] = w[u][0];
+            if (a.optimizer == TZK_OPT_ADAGRAD) a.state[d.w_off + row * d.dim + c] = s[u][0];
+          }
         }
       }
     }
-    finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
+    // ---- general path: heads of runs of length >= 2 (and every head when CH > 1) -----------------------------
+#pragma unroll 1
+    for (int u = 0; u < kPos; ++u) {
+      if (!head[u] || (CH == 1 && single[u])) continue;
+      const int64_t p = p0 + u;
+      const KeyT k0 = key[u + 1];
+      int len = 1;
+      while (len <= kShortRun && p + len < a.n && keys[p + len] == k0) ++len;
+      if (len > kShortRun) {
+        if (lane == 0) {
+          // gallop + binary search for the end of the run, then enqueue its chunks
+          int64_t lo = p + kShortRun, step = kShortRun;  // keys[lo] == k0
+          int64_t hi = lo + step;
+          while (hi < a.n && keys[hi] == k0) { lo = hi; step <<= 1; hi = lo + step; }
+          if (hi > a.n) hi = a.n;
+          while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (keys[mid] == k0) lo = mid; else hi = mid;
+          }
+          const int64_t end = hi;
+          const int n_chunks = (int)((end - p + kChunk - 1) / kChunk);
+          const int base = atomicAdd(wl.counters + 0, n_chunks);
+          int pslot = -1;
+          if (n_chunks > 1) {
+            pslot = atomicAdd(wl.counters + 2, n_chunks);
+            LongRun lr; lr.head = (int32_t)p; lr.pslot = pslot; lr.n_chunks = n_chunks; lr.pad = 0;
+            wl.runs[atomicAdd(wl.counters + 1, 1)] = lr;
+          }
+          for (int cc = 0; cc < n_chunks; ++cc) {
+            ChunkItem it;
+            it.start = (int32_t)(p + (int64_t)cc * kChunk);
+            it.end = (int32_t)((p + (int64_t)(cc + 1) * kChunk) < end ? (p + (int64_t)(cc + 1) * kChunk) : end);
+            it.n_chunks = n_chunks;
+            it.pslot = n_chunks > 1 ? pslot + cc : -1;
+            wl.items[base + cc] = it;
+          }
+        }
+        continue;
+      }
+      const int32_t v0 = v[u];
+      int f00;
+      if (a.pooled) f00 = v0 / a.B; else f00 = feat_of_key<KeyT>(fd, a.F, k0);
+      const BwdFeat d = fd[f00];
+      const int64_t row = (int64_t)k0 - d.key_base;
+      float acc[CH][VEC];
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+      for (int j = 0; j < len; ++j) {
+        const Entry en = entry_of(a, fd, j == 0 ? v0 : vals[p + j], f00);
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          const int c = (ch * G + lane) * VEC;
+          if (c < d.dim) {
+            float gg[VEC];
+            load_grad<VEC>(en.g + c, gg);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[ch][k] += gg[k] * en.scale;
+          }
+        }
+      }
+      finish_run<G, VEC, CH>(a, d, row, (int64_t)k0, acc, lane);
+    }
   }
 }
 
-// ---- 4a. one CTA per chunk of a long run -----------------------------------------------------------------
+// ---- 4a. one WARP per chunk of a long run ---------------------------------------------------------------
+// 32/G lane groups stride over the chunk with kLU gradient rows in flight each, then a fixed-order shuffle tree
+// folds the groups' partial sums into group 0, which either finishes the run or parks the chunk's partial.
 template <typename KeyT, int G, int VEC, int CH>
 __global__ void __launch_bounds__(kThreads)
 long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
@@ -400,18 +493,19 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
                   const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
                   const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NG = kThreads / G;
+  constexpr int GW = 32 / G;          // lane groups per warp
   constexpr int ROWF = CH * G * VEC;  // floats per partial row
-  constexpr int U = 4;                // independent gradient rows in flight per lane group
+  constexpr int kLU = 4;              // independent gradient rows in flight per lane group
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
-  float* part = reinterpret_cast<float*>(smem_raw + align16((size_t)a.F * sizeof(BwdFeat)));
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
 
   const int lane = threadIdx.x % G;
-  const int g = threadIdx.x / G;
+  const int gw = (threadIdx.x & 31) / G;
+  const int warp = threadIdx.x >> 5;
+  constexpr int WPC = kThreads / 32;
   const int n_items = wl.counters[0];
 
-  for (int r = blockIdx.x; r < n_items; r += gridDim.x) {
+  for (int r = blockIdx.x * WPC + warp; r < n_items; r += gridDim.x * WPC) {
     const ChunkItem it = wl.items[r];
     const KeyT key = keys[it.start];
     const int32_t v0 = vals[it.start];
@@ -425,12 +519,12 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-    for (int q0 = it.start + g; q0 < it.end; q0 += NG * U) {
-      Entry en[U];
-      bool ok[U];
+    for (int q0 = it.start + gw; q0 < it.end; q0 += GW * kLU) {
+      Entry en[kLU];
+      bool ok[kLU];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int q = q0 + u * NG;
+      for (int u = 0; u < kLU; ++u) {
+        const int q = q0 + u * GW;
         ok[u] = q < it.end;
         en[u] = entry_of(a, fd, ok[u] ? vals[q] : v0, f0);
       }
@@ -438,11 +532,11 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
       for (int ch = 0; ch < CH; ++ch) {
         const int c = (ch * G + lane) * VEC;
         if (c < d.dim) {
-          float gr[U][VEC];
+          float gr[kLU][VEC];
 #pragma unroll
-          for (int u = 0; u < U; ++u) load_grad<VEC>(en[u].g + c, gr[u]);
+          for (int u = 0; u < kLU; ++u) load_grad<VEC>(en[u].g + c, gr[u]);
 #pragma unroll
-          for (int u = 0; u < U; ++u)
+          for (int u = 0; u < kLU; ++u)
             if (ok[u]) {
 #pragma unroll
               for (int k = 0; k < VEC; ++k) acc[ch][k] += gr[u][k] * en[u].scale;
@@ -450,40 +544,26 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
         }
       }
     }
-    // fixed-order tree over the NG lane groups
+    // fixed-order tree over the GW lane groups of the warp (whole warp participates)
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
+    for (int off = GW / 2; off >= 1; off >>= 1) {
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) part[g * ROWF + (ch * G + lane) * VEC + k] = acc[ch][k];
-    __syncthreads();
-    for (int half = NG / 2; half >= 1; half >>= 1) {
-      if (g < half) {
+      for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            const int o = (ch * G + lane) * VEC + k;
-            part[g * ROWF + o] += part[(g + half) * ROWF + o];
-          }
-      }
-      __syncthreads();
+        for (int k = 0; k < VEC; ++k) acc[ch][k] += __shfl_down_sync(0xffffffffu, acc[ch][k], off * G);
     }
-    if (g == 0) {
+    if (gw == 0) {
       if (it.n_chunks == 1) {
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) acc[ch][k] = part[(ch * G + lane) * VEC + k];
         finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
       } else {
         float* dst = wl.partials + (int64_t)it.pslot * ROWF;
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) dst[(ch * G + lane) * VEC + k] = part[(ch * G + lane) * VEC + k];
+          for (int k = 0; k < VEC; ++k) dst[(ch * G + lane) * VEC + k] = acc[ch][k];
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -544,7 +624,7 @@ cudaError_t cub_sort(void* tmp, size_t& tmp_bytes, const KeyT* kin, KeyT* kout, 
 }
 
 inline int64_t max_items(int64_t n) { return n / kShortRun + n / kChunk + 2; }   // every long run has > 32 ids
-inline int64_t max_pslots(int64_t n) { return 2 * (n / kChunk) + 2; }            // multi-chunk runs have > 1024
+inline int64_t max_pslots(int64_t n) { return 2 * (n / kChunk) + 2; }            // multi-chunk runs have > kChunk
 
 WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
   WsLayout L;
@@ -583,8 +663,7 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
         a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
         vals_out, wl);                                                                                \
     TZK_CHECK_LAUNCH("run_update_kernel");                                                            \
-    size_t smem_l = tzk::align16((size_t)F * sizeof(BwdFeat)) +                                       \
-                    (size_t)(kThreads / G_) * (CH_ * G_ * VEC_) * sizeof(float);                      \
+    size_t smem_l = (size_t)F * sizeof(BwdFeat);                                                      \
     if (smem_l > 48 * 1024)                                                                           \
       cudaFuncSetAttribute(long_chunk_kernel<KeyT, G_, VEC_, CH_>,                                    \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);                 \

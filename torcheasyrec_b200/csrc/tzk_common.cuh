@@ -37,9 +37,11 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16;
 
 // 128-bit streaming loads/stores.  Table rows are random-access and re-used only through L2, so they
 // bypass L1 allocation; index lists / outputs are touched once.
+// (not volatile: independent row loads must be free to issue back to back — the whole point is to keep many
+// 64-B requests in flight per lane group)
 __device__ __forceinline__ float4 ld_row_f4(const float* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;

@@ -149,11 +149,15 @@ __device__ __forceinline__ void stage_x(float* X, const float* dense, int64_t ld
       *reinterpret_cast<float4*>(X + xoff(0, c4, DS, swm)) = ld_row_f4(dense + b * ld_dense + c4 * 4);
 }
 
+// DT = compile-time embedding dim (0 = take the runtime value): with DT known every /D, %D and swizzle offset
+// folds into shifts and the k loop unrolls — the kernel is issue-bound, not bandwidth-bound, otherwise.
+template <int DT>
 __global__ void __launch_bounds__(kIWarps * 32)
 dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
-                        int64_t ld_sparse, int64_t B, int Ns, int D, int copy_dense, int copy_sparse,
+                        int64_t ld_sparse, int64_t B, int Ns, int D_rt, int copy_dense, int copy_sparse,
                         float* __restrict__ out, int64_t ld_out) {
   extern __shared__ __align__(16) float smem[];
+  const int D = DT ? DT : D_rt;
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;        // rows padded to a multiple of 4 (pad rows are zero)
   const int DS = D + 4;               // row stride
@@ -193,12 +197,24 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      // row bases / swizzles of the 8 rows this block touches (rows bi*4..+3 share (row>>3) pairwise)
+      const float* arow[4];
+      const float* brow[4];
+      int asw[4], bsw[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        arow[r] = X + (bi * 4 + r) * DS;
+        brow[r] = X + (bj * 4 + r) * DS;
+        asw[r] = ((bi * 4 + r) >> 3) & swm;
+        bsw[r] = ((bj * 4 + r) >> 3) & swm;
+      }
+#pragma unroll DT ? DT / 4 : 1
       for (int c4 = 0; c4 < D4; ++c4) {
         float4 a[4], bb[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          a[r] = *reinterpret_cast<const float4*>(X + xoff(bi * 4 + r, c4, DS, swm));
-          bb[r] = *reinterpret_cast<const float4*>(X + xoff(bj * 4 + r, c4, DS, swm));
+          a[r] = *reinterpret_cast<const float4*>(arow[r] + ((c4 ^ asw[r]) << 2));
+          bb[r] = *reinterpret_cast<const float4*>(brow[r] + ((c4 ^ bsw[r]) << 2));
         }
         // accumulate in k order so the sum order matches a sequential dot product
 #pragma unroll
@@ -239,12 +255,14 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
 }
 
 // backward: dX = (G + G^T) X (+ pass-through grads); lane owns 4 rows x 4 cols blocks of dX.
+template <int DT>
 __global__ void __launch_bounds__(kIWarps * 32)
 dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
                         int64_t ld_sparse, const float* __restrict__ d_out, int64_t ld_dout, int64_t B,
-                        int Ns, int D, int copy_dense, int copy_sparse, float* __restrict__ d_dense,
+                        int Ns, int D_rt, int copy_dense, int copy_sparse, float* __restrict__ d_dense,
                         int64_t ld_ddense, float* __restrict__ d_sparse, int64_t ld_dsparse) {
   extern __shared__ __align__(16) float smem[];
+  const int D = DT ? DT : D_rt;
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;
   const int DS = D + 4;
@@ -422,10 +440,21 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int P = N * (N - 1) / 2;
   const int nb = Np / 4, n_blocks = nb * (nb + 1) / 2;
   size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3) & ~3))) * sizeof(float);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(dot_interact_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dot_interact_fwd_kernel<<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>(
-      dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, out, ld_out);
+#define TZK_IFWD(DT_)                                                                                         \
+  do {                                                                                                       \
+    if (smem > 48 * 1024)                                                                                    \
+      cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    dot_interact_fwd_kernel<DT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>( \
+        dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, out, ld_out);                 \
+  } while (0)
+  switch (D) {
+    case 8: TZK_IFWD(8); break;
+    case 16: TZK_IFWD(16); break;
+    case 32: TZK_IFWD(32); break;
+    case 64: TZK_IFWD(64); break;
+    default: TZK_IFWD(0); break;
+  }
+#undef TZK_IFWD
   TZK_CHECK_LAUNCH("dot_interact_fwd_kernel");
   return 0;
 }
@@ -446,11 +475,22 @@ extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const 
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
   size_t smem = ((size_t)((P + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + Np * (Np + 8))) * sizeof(float);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(dot_interact_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dot_interact_bwd_kernel<<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>(
-      dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, Ns, D, copy_dense, copy_sparse, d_dense, ld_ddense,
-      d_sparse, ld_dsparse);
+#define TZK_IBWD(DT_)                                                                                         \
+  do {                                                                                                       \
+    if (smem > 48 * 1024)                                                                                    \
+      cudaFuncSetAttribute(dot_interact_bwd_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    dot_interact_bwd_kernel<DT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>( \
+        dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, Ns, D, copy_dense, copy_sparse, d_dense, ld_ddense, \
+        d_sparse, ld_dsparse);                                                                               \
+  } while (0)
+  switch (D) {
+    case 8: TZK_IBWD(8); break;
+    case 16: TZK_IBWD(16); break;
+    case 32: TZK_IBWD(32); break;
+    case 64: TZK_IBWD(64); break;
+    default: TZK_IBWD(0); break;
+  }
+#undef TZK_IBWD
   TZK_CHECK_LAUNCH("dot_interact_bwd_kernel");
   return 0;
 }

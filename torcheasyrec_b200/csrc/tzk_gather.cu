@@ -26,7 +26,20 @@ struct FeatDesc {
 
 constexpr int kThreads = 256;
 constexpr int kTB = 32;  // samples per tile
-constexpr int kU = 4;    // bags in flight per lane group
+constexpr int kU = 8;    // bags in flight per lane group
+
+// Two phases per (sample tile x feature chunk), both with many independent requests in flight:
+//   A. every thread loads the bag bounds, then the first id, of its <= kItemsPerCta/256 bags into shared memory
+//      (the per-sample index lists are staged once, coalesced: ids are key-major so a tile's ids of one feature
+//      are one contiguous run);
+//   B. every lane group walks its bags out of shared memory and keeps kU row loads in flight before it pools /
+//      stores — the offsets -> id -> row dependency chain no longer serialises one bag at a time.
+constexpr int kItemsPerCta = 1024;  // bags staged per chunk (20 KB of shared memory)
+
+struct BagStage {
+  int64_t start;   // position of the bag's first id
+  int64_t id0;     // first id (valid when len > 0)
+};
 
 template <int G, int VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -37,6 +50,8 @@ pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __res
                          float* __restrict__ out, int64_t ld_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FeatDesc* fd = reinterpret_cast<FeatDesc*>(smem_raw);
+  BagStage* st = reinterpret_cast<BagStage*>(smem_raw + align16((size_t)F * sizeof(FeatDesc)));
+  int32_t* st_len = reinterpret_cast<int32_t*>(st + kItemsPerCta);
   for (int f = threadIdx.x; f < F; f += kThreads) {
     fd[f].w_off = feat_w_off[f];
     fd[f].rows = feat_rows[f];
@@ -47,65 +62,111 @@ pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __res
   __syncthreads();
 
   constexpr int NG = kThreads / G;  // lane groups per CTA
+  constexpr int FC = kItemsPerCta / kTB;  // features per chunk
   const int g = threadIdx.x / G;
   const int lane = threadIdx.x % G;
   const int n_tiles = (B + kTB - 1) / kTB;
-  const int items = F * kTB;
+  const int n_chunks = (F + FC - 1) / FC;
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int work = blockIdx.x; work < n_tiles * n_chunks; work += gridDim.x) {
+    const int tile = work / n_chunks, chunk = work - tile * n_chunks;
     const int b0 = tile * kTB;
-    for (int i0 = g; i0 < items; i0 += NG * kU) {
-      int64_t s[kU], e[kU];
-      int fidx[kU], bidx[kU];
-      bool ok[kU];
+    const int f0 = chunk * FC;
+    const int nf = (F - f0) < FC ? (F - f0) : FC;
+    const int items = nf * kTB;
+    // ---- phase A --------------------------------------------------------------------------------------
+    {
+      constexpr int PT = kItemsPerCta / kThreads;  // items per thread
+      int64_t s[PT];
+      int32_t len[PT];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = i0 + u * NG;
-        fidx[u] = i / kTB;
-        bidx[u] = b0 + (i % kTB);
-        ok[u] = (i < items) && (bidx[u] < B);
-        s[u] = 0;
-        e[u] = 0;
-        if (ok[u]) {
-          const int64_t bag = (int64_t)fidx[u] * B + bidx[u];
-          s[u] = __ldg(offsets + bag);
-          e[u] = __ldg(offsets + bag + 1);
+      for (int k = 0; k < PT; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        const int b = b0 + (i % kTB);
+        s[k] = 0;
+        len[k] = -1;
+        if (i < items && b < B) {
+          const int64_t bag = (int64_t)(f0 + i / kTB) * B + b;
+          s[k] = __ldg(offsets + bag);
+          len[k] = (int32_t)(__ldg(offsets + bag + 1) - s[k]);
         }
       }
-      // first id of every bag (the L=1 fast path keeps kU row loads in flight)
-      int64_t id0[kU];
+      int64_t id0[PT];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) id0[u] = (ok[u] && e[u] > s[u]) ? __ldg(ids + s[u]) : 0;
-
+      for (int k = 0; k < PT; ++k) id0[k] = len[k] > 0 ? __ldg(ids + s[k]) : 0;
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        if (!ok[u]) continue;
-        const FeatDesc d = fd[fidx[u]];
-        const int64_t L = e[u] - s[u];
-        float* orow = out + (int64_t)bidx[u] * ld_out + d.col;
-        for (int c = lane * VEC; c < d.dim; c += G * VEC) {
-          if (VEC == 4) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < PT; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        if (i < items) {
+          st[i].start = s[k];
+          st[i].id0 = id0[k];
+          st_len[i] = len[k];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase B --------------------------------------------------------------------------------------
+    for (int i0 = g; i0 < items; i0 += NG * kU) {
+      if (VEC == 4) {
+        float4 acc[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int i = i0 + u * NG;
+          acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < items && st_len[i] > 0) {
+            const FeatDesc& d = fd[f0 + i / kTB];
+            int64_t id = st[i].id0;
+            if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
+            if (lane * 4 < d.dim) acc[u] = ld_row_f4(weights + d.w_off + id * d.dim + lane * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int i = i0 + u * NG;
+          if (i >= items) continue;
+          const int L = st_len[i];
+          if (L < 0) continue;  // sample beyond B
+          const FeatDesc d = fd[f0 + i / kTB];
+          float* orow = out + (int64_t)(b0 + (i % kTB)) * ld_out + d.col;
+          for (int c = lane * 4; c < d.dim; c += G * 4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (L > 0) {
-              int64_t id = id0[u];
-              if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-              acc = ld_row_f4(weights + d.w_off + id * d.dim + c);
-              for (int64_t l = s[u] + 1; l < e[u]; ++l) {
-                int64_t idl = __ldg(ids + l);
-                if ((uint64_t)idl >= (uint64_t)d.rows) idl = 0;
-                acc = f4_add(acc, ld_row_f4(weights + d.w_off + idl * d.dim + c));
+              if (c == lane * 4) {
+                a = acc[u];
+              } else {
+                int64_t id = st[i].id0;
+                if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
+                a = ld_row_f4(weights + d.w_off + id * d.dim + c);
               }
-              if (d.pool == TZK_POOL_MEAN) acc = f4_scale(acc, 1.0f / (float)L);
+              const int64_t s0 = st[i].start;
+              for (int l = 1; l < L; ++l) {
+                int64_t idl = __ldg(ids + s0 + l);
+                if ((uint64_t)idl >= (uint64_t)d.rows) idl = 0;
+                a = f4_add(a, ld_row_f4(weights + d.w_off + idl * d.dim + c));
+              }
+              if (d.pool == TZK_POOL_MEAN) a = f4_scale(a, 1.0f / (float)L);
             }
-            st_stream_f4(orow + c, acc);
-          } else {
+            st_stream_f4(orow + c, a);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int u = 0; u < kU; ++u) {
+          const int i = i0 + u * NG;
+          if (i >= items) continue;
+          const int L = st_len[i];
+          if (L < 0) continue;
+          const FeatDesc d = fd[f0 + i / kTB];
+          float* orow = out + (int64_t)(b0 + (i % kTB)) * ld_out + d.col;
+          const int64_t s0 = st[i].start;
+          for (int c = lane; c < d.dim; c += G) {
             float acc = 0.f;
             if (L > 0) {
-              int64_t id = id0[u];
+              int64_t id = st[i].id0;
               if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
               acc = __ldg(weights + d.w_off + id * d.dim + c);
-              for (int64_t l = s[u] + 1; l < e[u]; ++l) {
-                int64_t idl = __ldg(ids + l);
+              for (int l = 1; l < L; ++l) {
+                int64_t idl = __ldg(ids + s0 + l);
                 if ((uint64_t)idl >= (uint64_t)d.rows) idl = 0;
                 acc += __ldg(weights + d.w_off + idl * d.dim + c);
               }
@@ -116,6 +177,7 @@ pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __res
         }
       }
     }
+    __syncthreads();  // the stage buffer is reused by the next (tile, chunk)
   }
 }
 
@@ -191,8 +253,10 @@ extern "C" int tzk_pooled_gather_fwd(const float* weights, const int64_t* feat_w
   const int G = pick_lanes(max_dim, vec);
   cudaStream_t st = as_stream(stream);
   const int n_tiles = (B + kTB - 1) / kTB;
-  int grid = n_tiles < kSmCountB200 * 8 ? n_tiles : kSmCountB200 * 8;
-  size_t smem = (size_t)F * sizeof(FeatDesc);
+  const int n_work = n_tiles * ((F + kItemsPerCta / kTB - 1) / (kItemsPerCta / kTB));
+  int grid = n_work < kSmCountB200 * 8 ? n_work : kSmCountB200 * 8;
+  size_t smem = align16((size_t)F * sizeof(FeatDesc)) + (size_t)kItemsPerCta * (sizeof(BagStage) + sizeof(int32_t));
+  TZK_REQUIRE(smem <= 48 * 1024, "pooled_gather_fwd: F=%d keys need %zu B of shared memory (> 48 KB)", F, smem);
   if (vec == 4) {
     TZK_DISPATCH_G(G, 4, pooled_gather_fwd_kernel, weights, feat_w_off, feat_rows, feat_dim, feat_col,
                    feat_pool, ids, offsets, F, B, out, ld_out)

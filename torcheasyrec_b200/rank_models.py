@@ -13,6 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import functional as Fn
+from .dense_gemm import Linear as _Linear
 from .batch import Batch
 from .config import Message, config_to_kwargs
 from .embedding_group import EmbeddingGroup
@@ -39,7 +40,7 @@ class Perceptron(nn.Module):
         super().__init__()
         if use_bn and use_ln:
             raise ValueError("Could not use_bn and use_ln at the same time in Perceptron.")
-        self.perceptron = nn.Sequential(nn.Linear(in_features, out_features, bias=False if use_bn else bias))
+        self.perceptron = nn.Sequential(_Linear(in_features, out_features, bias=False if use_bn else bias))
         if use_bn:
             assert dim == 2, "3-D batch norm towers are out of scope"
             self.perceptron.append(nn.BatchNorm1d(out_features))
@@ -141,7 +142,7 @@ class TaskTower(nn.Module):
         if mlp is not None:
             self.tower_mlp = MLP(tower_feature_in, **mlp)
             linear_in = self.tower_mlp.output_dim()
-        self.linear = nn.Linear(linear_in, num_class)
+        self.linear = _Linear(linear_in, num_class)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.tower_mlp is not None:
@@ -271,7 +272,7 @@ class DLRM(RankModel):
         if self._model_config.arch_with_sparse:
             feature_dim += sparse_dim
         self.final_mlp = MLP(feature_dim, **config_to_kwargs(self._model_config.final))
-        self.output_mlp = nn.Linear(self.final_mlp.output_dim(), self._num_class)
+        self.output_mlp = _Linear(self.final_mlp.output_dim(), self._num_class)
 
     def predict(self, batch: Batch) -> Dict[str, torch.Tensor]:
         grouped = self.build_input(batch)
@@ -301,7 +302,7 @@ class DeepFM(RankModel):
             self.final_mlp = MLP(in_features=1 + self._fm_feature_dims[0] + final_dim,
                                  **config_to_kwargs(self._model_config.final))
             final_dim = self.final_mlp.output_dim()
-        self.output_mlp = nn.Linear(final_dim, self._num_class)
+        self.output_mlp = _Linear(final_dim, self._num_class)
 
     def predict(self, batch: Batch) -> Dict[str, torch.Tensor]:
         grouped = self.build_input(batch)
@@ -340,7 +341,7 @@ class MultiTowerDIN(RankModel):
         if self._model_config.HasField("final"):
             self.final_mlp = MLP(in_features=total, **config_to_kwargs(self._model_config.final))
             final_dim = self.final_mlp.output_dim()
-        self.output_mlp = nn.Linear(final_dim, self._num_class)
+        self.output_mlp = _Linear(final_dim, self._num_class)
 
     def predict(self, batch: Batch) -> Dict[str, torch.Tensor]:
         grouped = self.build_input(batch)
