@@ -21,6 +21,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # CPU baseline: idle OpenMP workers must not spin
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+if "--impl" in sys.argv and "reference" in sys.argv:
+    os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 32)))
+
 import torch  # noqa: E402
 
 METRIC = "samples/sec (DLRM-Criteo synth, train step fwd+bwd+optimizer)"
@@ -105,8 +110,11 @@ def cpu_step_rate(model: str, batch: int, steps: int, warmup: int, max_rows: int
     from torcheasyrec_b200 import functional as Fn
     from torcheasyrec_b200.engine import Pipeline
 
-    cores = os.cpu_count() or 1
+    # thread scan on a 128-core host (scripts/cpu_threads.py, profiles/README.md): 8 -> 237k, 16 -> 307k,
+    # 32 -> 313k, 64 -> 271k, 128 -> 31k samples/s; beyond 32 the two OpenMP pools fight each other
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     pipe = Pipeline(model, device="cpu", max_rows=max_rows or None)
     batches = [pipe.synthetic_batch(batch, seed=100 + i, id_dist=id_dist) for i in range(2)]
     backend = OracleKernels(use_c=True)   # C/OpenMP restatement when oracle/libtzk_oracle.so is built

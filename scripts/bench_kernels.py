@@ -1,0 +1,40 @@
+"""Standalone timings of the sparse kernels at DLRM-Criteo shape (full hash sizes, B=65536), CUDA events.
+Usage: python scripts/bench_kernels.py            -> runs every variant in a subprocess and prints one JSON line each
+       TZK_RUN_UPDATE_KPOS=2 python scripts/bench_kernels.py one"""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+if len(sys.argv) > 1:
+    import torch
+    from torcheasyrec_b200.example_configs import CRITEO_HASH_SIZES
+    from torcheasyrec_b200.kernels import OPT_ADAGRAD, build_layout, default_kernels
+    dev, B, F, D = "cuda", 65536, 26, 16
+    k = default_kernels()
+    lay = build_layout(CRITEO_HASH_SIZES, [D] * F, list(range(F)), [0] * F).to(dev)
+    arena = torch.rand(lay.arena_elems, device=dev) * 0.01
+    state = torch.zeros(lay.arena_elems, device=dev)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    R = 4
+    ids = [torch.cat([torch.randint(0, h, (B,), device=dev, generator=g) for h in CRITEO_HASH_SIZES]) for _ in range(R)]
+    offs = torch.arange(F * B + 1, device=dev, dtype=torch.int64)
+    out = torch.empty((B, F * D), device=dev)
+    grad = torch.randn((B, F * D), device=dev) * 1e-3
+
+    def timeit(fn, n=20):
+        for i in range(3): fn(i)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        torch.cuda.synchronize()
+        for i in range(n):
+            ev[i][0].record(); fn(i); ev[i][1].record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        return ts[len(ts) // 2] * 1e3
+    res = {"kpos": os.environ.get("TZK_RUN_UPDATE_KPOS", "1")}
+    res["gather_us"] = timeit(lambda i: k.pooled_gather_fwd(arena, lay, ids[i % R], offs, B, out))
+    res["fused_bwd_us"] = timeit(lambda i: k.fused_bwd(OPT_ADAGRAD, True, grad, arena, state, lay, ids[i % R], offs, B, 1e-3, 1e-8, 1.0))
+    print(json.dumps(res))
+else:
+    for kp in ("1", "2", "4"):
+        env = dict(os.environ, TZK_RUN_UPDATE_KPOS=kp)
+        subprocess.run([sys.executable, __file__, "one"], env=env)

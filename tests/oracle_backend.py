@@ -139,10 +139,15 @@ class OracleKernels:
             return torch.from_numpy(self.C.fm_bwd(_c(x), _c(dy), N, D))
         return torch.from_numpy(O.fm_bwd(_np(x).reshape(-1, N, D), _np(dy)).reshape(-1, N * D))
 
-    def dot_interact_fwd(self, dense, sparse, Ns, D, copy_dense, copy_sparse):
+    def dot_interact_fwd(self, dense, sparse, Ns, D, copy_dense, copy_sparse, pad_to=1):
         if self.use_c:
-            return torch.from_numpy(self.C.dot_interact_fwd(_c(dense), _c(sparse), Ns, D, copy_dense, copy_sparse))
-        return torch.from_numpy(O.dlrm_interact(_np(dense), _np(sparse), Ns, D, copy_dense, copy_sparse))
+            res = self.C.dot_interact_fwd(_c(dense), _c(sparse), Ns, D, copy_dense, copy_sparse)
+        else:
+            res = O.dlrm_interact(_np(dense), _np(sparse), Ns, D, copy_dense, copy_sparse)
+        pad = (-res.shape[1]) % pad_to
+        if pad:
+            res = np.concatenate([res, np.zeros((res.shape[0], pad), np.float32)], axis=1)
+        return torch.from_numpy(np.ascontiguousarray(res))
 
     def dot_interact_bwd(self, dense, sparse, d_out, Ns, D, copy_dense, copy_sparse):
         if self.use_c:

@@ -11,6 +11,7 @@
 //   4. long-run kernel: one CTA per long run (tiny tables / hot ids), strided partial sums per lane group
 //      + fixed-order tree in shared memory, then the update.
 #include <algorithm>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "tzk_common.cuh"
@@ -311,7 +312,7 @@ struct WorkLists {
 // Each lane group owns kPos consecutive sorted positions per iteration.  Runs of length 1 (the common case on
 // big tables) take a batched path: the gradient / weight / state rows of all of them are requested before any
 // is consumed, so a group keeps 3*kPos independent 64-B requests in flight instead of one dependent chain.
-template <typename KeyT, int G, int VEC, int CH>
+template <typename KeyT, int G, int VEC, int CH, int KP>
 __global__ void __launch_bounds__(kThreads)
 run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
                   const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
@@ -322,7 +323,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
 
   constexpr int NG = kThreads / G;
-  constexpr int kPos = (CH == 1) ? 4 : 1;
+  constexpr int kPos = (CH == 1) ? KP : 1;
   const int lane = threadIdx.x % G;
   const int64_t stride = (int64_t)gridDim.x * NG * kPos;
   // all G lanes of a group follow the same control flow (positions, keys, run lengths are group-uniform)
@@ -346,7 +347,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
       head[u] = (p0 + u < a.n) && key[u + 1] != key[u];
       single[u] = head[u] && ((p0 + u + 1 >= a.n) || key[u + 2] != key[u + 1]);
     }
-    if (CH == 1) {
+    if (CH == 1 && KP > 1) {
       // ---- batched path: runs of length 1 -------------------------------------------------------------
       float g[kPos][VEC], w[kPos][VEC], s[kPos][VEC];
       float scale[kPos];
@@ -419,7 +420,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
     // ---- general path: heads of runs of length >= 2 (and every head when CH > 1) -----------------------------
 #pragma unroll 1
     for (int u = 0; u < kPos; ++u) {
-      if (!head[u] || (CH == 1 && single[u])) continue;
+      if (!head[u] || (CH == 1 && KP > 1 && single[u])) continue;
       const int64_t p = p0 + u;
       const KeyT k0 = key[u + 1];
       int len = 1;
@@ -653,15 +654,22 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
 
 }  // namespace
 
+#define TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, KP_)                                                     \
+  do {                                                                                                \
+    if (smem_s > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(run_update_kernel<KeyT, G_, VEC_, CH_, KP_>,                               \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
+    run_update_kernel<KeyT, G_, VEC_, CH_, KP_><<<grid_s, kThreads, smem_s, st>>>(                    \
+        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
+        vals_out, wl);                                                                                \
+  } while (0)
+
 #define TZK_BWD_LAUNCH(KeyT, G_, VEC_, CH_)                                                          \
   do {                                                                                                \
     size_t smem_s = (size_t)F * sizeof(BwdFeat);                                                      \
-    if (smem_s > 48 * 1024)                                                                           \
-      cudaFuncSetAttribute(run_update_kernel<KeyT, G_, VEC_, CH_>,                                    \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
-    run_update_kernel<KeyT, G_, VEC_, CH_><<<grid_s, kThreads, smem_s, st>>>(                         \
-        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
-        vals_out, wl);                                                                                \
+    if (CH_ == 1 && kpos == 4) TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, 4);                                \
+    else if (CH_ == 1 && kpos == 2) TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, 2);                           \
+    else TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, 1);                                                      \
     TZK_CHECK_LAUNCH("run_update_kernel");                                                            \
     size_t smem_l = (size_t)F * sizeof(BwdFeat);                                                      \
     if (smem_l > 48 * 1024)                                                                           \
@@ -776,6 +784,13 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
               max_dim, ch);
   const int NG = kThreads / G;
   int grid_s = (int)std::min<int64_t>(ceil_div64(nnz, NG), kSmCountB200 * 16);
+  // positions per lane group per iteration in run_update (1 = one dependent chain per group, 2/4 = batched
+  // single-run path).  Tunable for experiments: TZK_RUN_UPDATE_KPOS=1|2|4.
+  static const int kpos = [] {
+    const char* e = getenv("TZK_RUN_UPDATE_KPOS");
+    const int v = e ? atoi(e) : 1;
+    return (v == 2 || v == 4) ? v : 1;
+  }();
 
   // CH is compiled for 1 (D <= 128 aligned), 2 and 8
   if (k64) {

@@ -77,27 +77,43 @@ def _mm(a: torch.Tensor, ta: bool, b: torch.Tensor, tb: bool, M: int, N: int, K:
 
 
 class _LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b.  `x` may carry zero columns beyond W's in_features (width rounded up to a multiple of 4 by
+    the producer): 16-B aligned rows are what lets cuBLASLt pick the tensor-core (BF16x9) kernels instead of the
+    align1 SIMT ones — e.g. DLRM's 783-wide final-MLP input travels as [B, 784]."""
+
     @staticmethod
     def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+        K, Kx = weight.shape[1], x.shape[1]
+        w = weight
+        if Kx != K:      # zero-padded input: pad the weight the same way (N x Kx, a few hundred KB)
+            w = torch.zeros((weight.shape[0], Kx), dtype=weight.dtype, device=weight.device)
+            w[:, :K].copy_(weight)
+        ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
-        y = _mm(x, False, weight, True, x.shape[0], weight.shape[0], x.shape[1])
+        ctx.K = K
+        y = _mm(x, False, w, True, x.shape[0], w.shape[0], Kx)
         if bias is not None:
             y.add_(bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, w = ctx.saved_tensors
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _mm(dy, False, weight, False, dy.shape[0], weight.shape[1], weight.shape[0])
+            dx = _mm(dy, False, w, False, dy.shape[0], w.shape[1], w.shape[0])
         if ctx.needs_input_grad[1]:
-            dw = _mm(dy, True, x, False, weight.shape[0], weight.shape[1], dy.shape[0])
+            dw = _mm(dy, True, x, False, w.shape[0], w.shape[1], dy.shape[0])
+            if w.shape[1] != ctx.K:
+                dw = dw[:, :ctx.K].contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0)
         return dx, dw, db
+
+
+def padded_width(n: int) -> int:
+    return (n + 3) // 4 * 4
 
 
 def _usable(x: torch.Tensor, weight: torch.Tensor) -> bool:
@@ -107,6 +123,13 @@ def _usable(x: torch.Tensor, weight: torch.Tensor) -> bool:
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """F.linear; accepts `x` zero-padded to padded_width(in_features) columns."""
+    K = weight.shape[1]
+    if x.dim() == 2 and x.shape[1] != K:
+        if x.shape[1] != padded_width(K):
+            raise RuntimeError(f"linear: input width {x.shape[1]} does not match in_features {K}")
+        if not _usable(x, weight):
+            x = x[:, :K]
     if _usable(x, weight):
         return _LinearFn.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)

@@ -166,12 +166,18 @@ def jagged_to_padded_dense(values: torch.Tensor, offsets: torch.Tensor, T: int) 
 
 
 # ------------------------------------------------------------------------------------------------ K2
+_perm_cache = {}
+
+
 def kjt_permute(kjt, indices: List[int]):
     from .sparse import KeyedJaggedTensor
 
     B = kjt.stride()
     dev = kjt.values().device
-    perm = torch.tensor(indices, dtype=torch.int32, device=dev)
+    pk = (tuple(indices), str(dev))
+    perm = _perm_cache.get(pk)
+    if perm is None:      # cached: no host->device copy inside a captured step
+        perm = _perm_cache[pk] = torch.tensor(indices, dtype=torch.int32, device=dev)
     new_len = backend().permute_lengths(kjt.lengths().contiguous(), perm, B)
     new_off = backend().lengths_to_offsets(new_len)
     lpk = kjt.length_per_key()
@@ -206,19 +212,19 @@ def factorization_machine(feature: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------ A9/A10
 class _DotInteract(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dense, sparse, Ns, D, copy_dense, copy_sparse):
+    def forward(ctx, dense, sparse, Ns, D, copy_dense, copy_sparse, pad_to=1):
         dense_c = None if dense is None else _rows_contig(dense)
         sparse_c = _rows_contig(sparse)
         ctx.save_for_backward(dense_c, sparse_c)
         ctx.cfg = (Ns, D, copy_dense, copy_sparse)
-        return backend().dot_interact_fwd(dense_c, sparse_c, Ns, D, copy_dense, copy_sparse)
+        return backend().dot_interact_fwd(dense_c, sparse_c, Ns, D, copy_dense, copy_sparse, pad_to)
 
     @staticmethod
     def backward(ctx, d_out):
         dense, sparse = ctx.saved_tensors
         Ns, D, cd, cs = ctx.cfg
         d_dense, d_sparse = backend().dot_interact_bwd(dense, sparse, _rows_contig(d_out), Ns, D, cd, cs)
-        return d_dense, d_sparse, None, None, None, None
+        return d_dense, d_sparse, None, None, None, None, None
 
 
 def dot_interaction(features: torch.Tensor) -> torch.Tensor:
@@ -228,7 +234,8 @@ def dot_interaction(features: torch.Tensor) -> torch.Tensor:
 
 
 def dlrm_interaction(dense_feat: Optional[torch.Tensor], sparse_feat: torch.Tensor, num_sparse: int, dim: int,
-                     with_dense: bool = True, with_sparse: bool = True) -> torch.Tensor:
+                     with_dense: bool = True, with_sparse: bool = True, pad_to: int = 1) -> torch.Tensor:
     """Fused DLRM.predict glue (tzrec/models/dlrm.py:113-131):
-    cat([interaction(cat([dense[:,None,:], sparse.view(B,Ns,D)], 1)), dense, sparse], -1) in one pass."""
-    return _DotInteract.apply(dense_feat, sparse_feat, num_sparse, dim, with_dense, with_sparse)
+    cat([interaction(cat([dense[:,None,:], sparse.view(B,Ns,D)], 1)), dense, sparse], -1) in one pass.
+    pad_to=4 appends zero columns up to a multiple of 4 (aligned rows for the consuming GEMM)."""
+    return _DotInteract.apply(dense_feat, sparse_feat, num_sparse, dim, with_dense, with_sparse, pad_to)

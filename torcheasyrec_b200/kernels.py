@@ -332,7 +332,9 @@ class CudaKernels:
 
     # ------------------------------------------------------------------ A9 / A10
     def dot_interact_fwd(self, dense: Optional[torch.Tensor], sparse: torch.Tensor, Ns: int, D: int,
-                         copy_dense: bool, copy_sparse: bool) -> torch.Tensor:
+                         copy_dense: bool, copy_sparse: bool, pad_to: int = 1) -> torch.Tensor:
+        """pad_to > 1: the result is [B, ceil(width/pad_to)*pad_to] with zero columns at the end (16-B aligned
+        rows for the GEMM that consumes it)."""
         sparse, ld_s = _rows2d(sparse, "sparse")
         B = sparse.shape[0]
         ld_d = 0
@@ -340,9 +342,12 @@ class CudaKernels:
             dense, ld_d = _rows2d(dense, "dense")
         N = Ns + (dense is not None)
         width = N * (N - 1) // 2 + (D if (copy_dense and dense is not None) else 0) + (Ns * D if copy_sparse else 0)
-        out = torch.empty((B, width), dtype=torch.float32, device=sparse.device)
+        wp = (width + pad_to - 1) // pad_to * pad_to
+        out = torch.empty((B, wp), dtype=torch.float32, device=sparse.device)
+        if wp != width:
+            out[:, width:].zero_()
         check(self._lib.tzk_dot_interact_fwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, B, Ns, D, int(copy_dense),
-                                             int(copy_sparse), _ptr(out), width, _stream()),
+                                             int(copy_sparse), _ptr(out), wp, _stream()),
               "tzk_dot_interact_fwd")
         self.launches += 1
         return out

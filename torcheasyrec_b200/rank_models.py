@@ -279,8 +279,11 @@ class DLRM(RankModel):
         sparse = grouped[self._sparse_group_name]
         dense_feat = self.dense_mlp(grouped[self._dense_group_name]) if self.dense_mlp else None
         # interaction + both concats of dlrm.py:113-131 in one kernel
+        # (the 783-wide result is emitted as [B, 784] with a zero column: 16-B aligned rows let the first
+        #  final-MLP GEMM and its dX/dW twins run on the tensor cores, see dense_gemm.py)
         all_feat = Fn.dlrm_interaction(dense_feat, sparse, self._sparse_num, self._per_sparse_dim,
-                                       with_dense=True, with_sparse=bool(self._model_config.arch_with_sparse))
+                                       with_dense=True, with_sparse=bool(self._model_config.arch_with_sparse),
+                                       pad_to=4)
         return self._output_to_prediction(self.output_mlp(self.final_mlp(all_feat)))
 
 
