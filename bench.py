@@ -33,6 +33,8 @@ UNIT = "samples/s"
 ROW_BYTES_PER_SAMPLE = 26 * 16 * 4                       # 1664 B: SURVEY.md §8d "gather HBM GB/s" numerator
 GATHER_BYTES_PER_SAMPLE = 1664 + 1664 + 26 * 8 + 26 * 4   # rows + pooled write + ids + lengths = 3640 B
 BWD_BYTES_PER_SAMPLE = 1664 + 26 * 4 * 64 + 26 * 8        # grad read + w/state RMW (U=26) + ids = 8528 B
+NCU_TRAFFIC_BYTES = {"pooled_gather_fwd_kernel": 110.476032e6 + 58.848512e6,   # dram rd + wr, one launch
+                     "run_update_kernel": 282.46656e6 + 50.44352e6}
 
 
 def parse_args():
@@ -48,6 +50,9 @@ def parse_args():
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through the steps")
     ap.add_argument("--cpu-batch", type=int, default=8192, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded-mode", default="graph", choices=["graph", "eager"],
+                    help="N>1: 'graph' = static-capacity exchange captured in one CUDA graph, 'eager' = dynamic splits")
+    ap.add_argument("--static-capacity", type=float, default=1.5)
     return ap.parse_args()
 
 
@@ -184,13 +189,15 @@ def run_ours(args):
     from torcheasyrec_b200.kernels import default_kernels
 
     B, K, W = args.batch_size, args.steps, max(args.warmup, 3)
+    graphed = world == 1 or args.sharded_mode == "graph"
     pipe = Pipeline(args.model, device=dev, max_rows=args.max_rows or None,
-                    sharding="row_wise" if world > 1 else None)
+                    sharding="row_wise" if world > 1 else None,
+                    static_capacity=args.static_capacity if (world > 1 and graphed) else None)
     host = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + i, id_dist=args.id_dist).pin_memory()
             for i in range(args.ring)]
     ring = [hb.to(dev) for hb in host]
     kern = default_kernels()
-    if world == 1:
+    if graphed:
         step = GraphedTrainStep(pipe, host[0], warmup=3)
         launches_before = kern.launches
         # count this step's own kernels once (eager replica of the captured step on the static inputs)
@@ -242,7 +249,7 @@ def run_ours(args):
     ms_total = e0.elapsed_time(e1)
     # ---- e2e: pinned host batch -> H2D -> step -> loss back on the host, every step --------------------------
     # (N=1: the H2D of batch i+1 runs on the copy stream while step i computes; the loss of every step is read)
-    piped = world == 1
+    piped = graphed
     for i in range(2):
         step.load(host[i % len(host)])
         step.replay()
@@ -264,6 +271,7 @@ def run_ours(args):
     barrier()
     ms_e2e = g0.elapsed_time(g1)
     clk = clocks.stop() if clocks else None
+    pipe.check_overflow()      # static-capacity exchange: no peer needed more than its wire capacity
     if world > 1:
         import torch.distributed as dist
 
@@ -295,9 +303,17 @@ def run_ours(args):
     bwd_gbs = BWD_BYTES_PER_SAMPLE * B / (bwd_ms * 1e-3) / 1e9
     dominant = "tzk_fused_bwd (linearize + radix sort + run_update)" if bwd_ms > fwd_ms else "pooled_gather_fwd_kernel"
     ach = bwd_gbs if bwd_ms > fwd_ms else fwd_gbs
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture
+    # (profiles/r1_ncu_full_top_kernels.csv; only valid for the workload it was captured on)
+    std = (args.model == "dlrm_criteo" and B == 65536 and not args.max_rows and args.id_dist == "uniform")
+    traffic = None
+    if std:
+        traffic = (NCU_TRAFFIC_BYTES["run_update_kernel"] if bwd_ms > fwd_ms else NCU_TRAFFIC_BYTES["pooled_gather_fwd_kernel"])
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "traffic_note": "bytes/launch of run_update_kernel (the dominant kernel of the fused "
+        "backward) from profiles/r1_ncu_full_top_kernels.csv" if (std and bwd_ms > fwd_ms) else None,
+        "peak_source": peak_src,
         "kernels": {
             "pooled_gather_fwd": {"ms": fwd_ms, "algorithmic_GBps": fwd_gbs, "frac": fwd_gbs / peak,
                                   "row_read_GBps": ROW_BYTES_PER_SAMPLE * B / (fwd_ms * 1e-3) / 1e9,
@@ -334,7 +350,10 @@ def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step,
                                f"backward + dense Adam, ids {args.id_dist}",
                    "global_batch": global_batch, "parallelism": f"rw{world}+dp{world}",
                    "l2": f"inputs rotate over {ring_len} distinct batches; tables 12.2 GiB + state 12.2 GiB >> 126 MB L2",
-                   "cuda_graph": world == 1},
+                   "cuda_graph": bool(args.sharded_mode == "graph" or world == 1),
+                   "exchange": ("none" if world == 1 else
+                                (f"static capacity {args.static_capacity}x, in-graph NCCL all-to-all"
+                                 if args.sharded_mode == "graph" else "dynamic splits (host read per step)"))},
         "e2e": {"value": global_batch * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last},
         "gpu_launches": launches_per_step * K,

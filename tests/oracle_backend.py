@@ -96,7 +96,7 @@ class OracleKernels:
         return (torch.from_numpy(ol), torch.from_numpy(oo), torch.from_numpy(oi),
                 torch.from_numpy(op) if want_pos else None, inv)
 
-    def bag_grad_expand(self, grad_out, lay, offsets, slot, B, n_rows):
+    def bag_grad_expand(self, grad_out, lay, offsets, slot, B, n_rows, zero=False):
         return torch.from_numpy(O.bag_grad_expand(_np(grad_out), lay.col, lay.pool, _np(offsets), _np(slot),
                                                   lay.num_features, B, lay.dim[0], n_rows))
 

@@ -49,7 +49,7 @@ def _concat_batches(batches):
     return out
 
 
-def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=False):
+def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=False, static_capacity=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dev = f"cuda:{rank}" if use_cuda else "cpu"
     if use_cuda:
@@ -73,7 +73,8 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
             ref = Pipeline(name, device=dev, max_rows=300, seed=5, capturable=False)   # unsharded twin
             shd = Pipeline(name, device=dev, max_rows=300, seed=5, capturable=False)
             shd.model.load_state_dict(ref.model.state_dict())
-            sharded = shard_model(shd.model, dev, default=sharding, rw_min_rows=rw_min_rows, source=ref.model)
+            sharded = shard_model(shd.model, dev, default=sharding, rw_min_rows=rw_min_rows, source=ref.model,
+                                  static_capacity=static_capacity)
             shd.model.set_sparse_optimizer(ref.model.sparse_collections()[0].optimizer)
             from torcheasyrec_b200.rank_models import dense_optimizer_from_config
 
@@ -97,6 +98,8 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
             for _ in range(2):
                 loss_ref = ref.eager_step(glob)
                 loss_shd = shd.eager_step(batches[rank])
+            for sm in sharded:
+                sm.check_overflow()
             t = torch.tensor([float(loss_shd)], dtype=torch.float64, device=dev)
             dist.all_reduce(t)
             np.testing.assert_allclose(t.item() / world, float(loss_ref), rtol=1e-6)
@@ -127,11 +130,11 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
         dist.destroy_process_group()
 
 
-def _run(world, name, sharding, rw_min_rows=0, use_cuda=False):
+def _run(world, name, sharding, rw_min_rows=0, use_cuda=False, static_capacity=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, sharding, rw_min_rows, q, use_cuda))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, sharding, rw_min_rows, q, use_cuda, static_capacity))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -145,6 +148,11 @@ def _run(world, name, sharding, rw_min_rows=0, use_cuda=False):
 @pytest.mark.parametrize("sharding", ["row_wise", "table_wise"])
 def test_dlrm_two_ranks(sharding):
     _run(2, "dlrm_criteo", sharding)
+
+
+def test_dlrm_static_capacity_exchange_two_ranks():
+    # fixed-shape (graph-capturable) exchange: padded wire slots, zero-gradient padding, same results
+    _run(2, "dlrm_criteo", "row_wise", static_capacity=2.5)
 
 
 def test_deepfm_mixed_three_ranks():

@@ -116,6 +116,16 @@ class _DimGroup:
             w_off=lay.w_off * world, rows=lay.rows * world, dim=lay.dim * world, col=[0] * (F * world),
             pool=[POOL_SUM] * (F * world), key_base=lay.key_base * world, total_keys=lay.total_keys,
             total_dim=self.dim, arena_elems=lay.arena_elems).to(device)
+        # static-capacity variant (graph-capturable step): per source rank F feature slots + one padding slot
+        padw = lambda xs, v: [x for r in range(world) for x in (list(xs) + [v])]
+        self.owner_layout_static = FeatureLayout(
+            w_off=padw(lay.w_off, 0), rows=padw(lay.rows, 1), dim=padw(lay.dim, self.dim),
+            col=[0] * ((F + 1) * world), pool=[POOL_SUM] * ((F + 1) * world), key_base=padw(lay.key_base, 0),
+            total_keys=lay.total_keys, total_dim=self.dim, arena_elems=lay.arena_elems).to(device)
+        self.static_alpha: Optional[float] = None     # set by shard_model(static_capacity=...)
+        self.static_cap: Optional[int] = None
+        self.static_nnz: Optional[int] = None
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         # sample-owner layout over the returned row buffer ("table" = rows in wire order)
         self._ret_layout_cache: Dict[int, FeatureLayout] = {}
         self._pool = list(lay.pool)
@@ -161,6 +171,7 @@ class _Dispatch:
                              self.in_splits, group)
         self.bounds = k.lengths_to_offsets(recv_counts.reshape(-1).to(torch.int32))   # [W*F+1], B=1 "bags"
         self.n_recv = n_recv
+        self.n_slots = self.nnz
 
     def rows_forward(self) -> torch.Tensor:
         g, k = self.g, Fn.backend()
@@ -180,21 +191,89 @@ class _Dispatch:
                         self.recv_ids, self.bounds, 1, spec.lr, spec.eps, 1.0 / g.world)   # App. A.6: /W
 
 
+class _StaticDispatch:
+    """Same exchange with STATIC shapes (no host read, CUDA-graph capturable): every (src -> dest) message has a
+    fixed capacity `cap` = ceil(alpha * nnz / W) ids; unused slots carry id 0 of a per-source padding slot and
+    zero gradient rows, so they change nothing at the owner.  Counts travel as data; an overflow (a peer needs more
+    than `cap`) raises the device flag `g.overflow`, which the caller checks after the step(s).
+    Only for fixed-nnz workloads (one id per bag, like Criteo / Taobao non-sequence features)."""
+
+    def __init__(self, g: _DimGroup, kjt: KeyedJaggedTensor, group) -> None:
+        k = Fn.backend()
+        W, F, B = g.world, g.F, kjt.stride()
+        self.g, self.B, self.group = g, B, group
+        ids, offsets = kjt.values(), kjt.offsets()
+        dev = ids.device
+        self.offsets = offsets
+        self.nnz = nnz = ids.numel()
+        if g.static_cap is None:
+            g.static_nnz = nnz
+            g.static_cap = (int(g.static_alpha * nnz / W) + 8) // 8 * 8
+        if nnz != g.static_nnz:
+            raise RuntimeError(f"static-capacity sharding was sized for {g.static_nnz} ids per step, got {nnz}")
+        cap = g.static_cap
+        self.n_slots = W * cap
+        _, oo, oids, _, inv = k.bucketize_rw(ids, offsets, F, B, W, g.feat_block, feat_owner=g.feat_owner,
+                                             want_inv=True)
+        seg = oo[::B]                                              # [W*F+1]
+        counts = (seg[1:] - seg[:-1]).view(W, F)
+        dest_start = oo[::F * B]                                   # [W+1] compact start of every destination
+        per_dest = dest_start[1:] - dest_start[:-1]
+        g.overflow.add_((per_dest > cap).any().to(torch.int32))
+        # compact wire slot -> padded wire slot
+        slot = torch.arange(nnz, device=dev)
+        r_of = torch.searchsorted(dest_start[1:].contiguous(), slot, right=True).clamp_(max=W - 1)
+        pslot = (slot + r_of * cap - dest_start[r_of]).clamp_(max=self.n_slots - 1)
+        send_ids = torch.zeros(self.n_slots, dtype=torch.int64, device=dev)
+        send_ids.index_copy_(0, pslot, oids)
+        self.inv = pslot[inv.to(torch.int64)]                      # padded slot of every original id position
+        recv_counts = torch.empty_like(counts)
+        dist.all_to_all_single(recv_counts, counts, group=group)   # [src, F], equal splits
+        self.recv_ids = torch.empty_like(send_ids)
+        dist.all_to_all_single(self.recv_ids, send_ids, group=group)
+        # owner-side "bags": per source its F feature runs, then the padding run up to cap
+        tot = recv_counts.sum(1, keepdim=True)
+        lens = torch.cat([recv_counts, (cap - tot).clamp_(min=0)], dim=1).reshape(-1).to(torch.int32)
+        self.bounds = k.lengths_to_offsets(lens)                   # [W*(F+1)+1]
+
+    def rows_forward(self) -> torch.Tensor:
+        g, k = self.g, Fn.backend()
+        rows = k.seq_gather_fwd(g.local.weights.data, g.owner_layout_static, self.recv_ids, self.bounds, 1)
+        ret = torch.empty_like(rows)
+        dist.all_to_all_single(ret, rows, group=self.group)
+        return ret
+
+    def rows_backward(self, g_rows: torch.Tensor) -> None:
+        g, k = self.g, Fn.backend()
+        recv_g = torch.empty_like(g_rows)
+        dist.all_to_all_single(recv_g, g_rows, group=self.group)
+        spec = g.local.optimizer
+        if spec is None:
+            raise RuntimeError("sharded collection: no sparse optimizer set (call set_optimizer)")
+        k.fused_bwd(spec.kind, False, recv_g, g.local.weights.data, g.local.opt_state, g.owner_layout_static,
+                    self.recv_ids, self.bounds, 1, spec.lr, spec.eps, 1.0 / g.world)
+
+
+def _dispatch(g: _DimGroup, kjt: KeyedJaggedTensor, group):
+    return _StaticDispatch(g, kjt, group) if g.static_alpha else _Dispatch(g, kjt, group)
+
+
 class _ShardedPooled(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hook, g: _DimGroup, kjt: KeyedJaggedTensor, group):
-        d = _Dispatch(g, kjt, group)
+        d = _dispatch(g, kjt, group)
         ret = d.rows_forward()
-        out = Fn.backend().pooled_gather_fwd(ret.view(-1), g.ret_layout(d.nnz), d.inv.to(torch.int64), d.offsets,
-                                             d.B)
+        out = Fn.backend().pooled_gather_fwd(ret.view(-1), g.ret_layout(d.n_slots), d.inv.to(torch.int64),
+                                             d.offsets, d.B)
         ctx.d = d
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         d = ctx.d
-        g_rows = Fn.backend().bag_grad_expand(Fn._rows_contig(grad_out), d.g.ret_layout(d.nnz), d.offsets, d.inv,
-                                              d.B, d.nnz)
+        static = isinstance(d, _StaticDispatch)
+        g_rows = Fn.backend().bag_grad_expand(Fn._rows_contig(grad_out), d.g.ret_layout(d.n_slots), d.offsets,
+                                              d.inv.to(torch.int32), d.B, d.n_slots, zero=static)
         d.rows_backward(g_rows)
         return None, None, None, None
 
@@ -245,6 +324,14 @@ class _ShardedBase(nn.Module):
 
     def sparse_arenas(self) -> List[_ArenaCollection]:
         return [g.local for g in self.groups]
+
+    def check_overflow(self) -> None:
+        """Static-capacity mode: raises if any step since the last check needed more than the wire capacity."""
+        for g in self.groups:
+            if g.static_alpha and int(g.overflow.item()):
+                g.overflow.zero_()
+                raise RuntimeError(f"static-capacity all-to-all overflowed (cap={g.static_cap} ids per peer); raise "
+                                   "static_capacity or use the dynamic exchange")
 
     def _hook_tensor(self, device) -> Optional[torch.Tensor]:
         if not torch.is_grad_enabled():
@@ -352,7 +439,7 @@ class DenseGradSync:
 
 
 def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows: int = 0, source=None,
-                constraints: Optional[Dict[str, Sequence[str]]] = None):
+                constraints: Optional[Dict[str, Sequence[str]]] = None, static_capacity: Optional[float] = None):
     """Swaps every arena collection of `model.embedding_group` for its sharded twin (tzrec/main.py:799).
 
     The model may have been built with its embedding collections on the meta device (as the reference does,
@@ -368,6 +455,9 @@ def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows:
         plan = make_plan(coll._configs, world, default, dict(constraints or {}), rw_min_rows)
         cls = ShardedEmbeddingBagCollection if isinstance(coll, EmbeddingBagCollection) else ShardedEmbeddingCollection
         new = cls(coll._configs, plan, device, group)
+        if static_capacity and isinstance(new, ShardedEmbeddingBagCollection):
+            for g in new.groups:       # fixed-shape exchange (see _StaticDispatch); pooled collections only
+                g.static_alpha = float(static_capacity)
         if coll.optimizer is not None:
             new.set_optimizer(coll.optimizer)
         seed = src_coll if src_coll is not None else (coll if coll.weights.device.type != "meta" else None)

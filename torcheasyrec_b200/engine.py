@@ -41,7 +41,8 @@ class Pipeline:
 
     def __init__(self, config: str, device="cuda", max_rows: Optional[int] = None,
                  edits: Optional[Dict[str, Any]] = None, seed: int = 1234, capturable: bool = True,
-                 sharding: Optional[str] = None, group=None, rw_min_rows: int = 0) -> None:
+                 sharding: Optional[str] = None, group=None, rw_min_rows: int = 0,
+                 static_capacity: Optional[float] = None) -> None:
         """`config`: path of a pipeline .config/.json, or the name of a built-in example
         (example_configs.GENERATORS: dlrm_criteo, deepfm_criteo, mmoe_taobao, multi_tower_din_taobao)."""
         from . import example_configs
@@ -70,7 +71,8 @@ class Pipeline:
 
             self.model = create_model(self.cfg.model_config, self.features, self.labels, device=torch.device("meta"))
             self.sharded = shard_model(self.model, self.device, default=sharding, group=group,
-                                       rw_min_rows=rw_min_rows, constraints=self._table_constraints())
+                                       rw_min_rows=rw_min_rows, constraints=self._table_constraints(),
+                                       static_capacity=static_capacity)
         self.model.to(self.device)
         if sharding is not None:
             self.grad_sync = DenseGradSync(self.model.dense_parameters(), group)
@@ -110,17 +112,25 @@ class Pipeline:
             kjt.length_per_key()  # host-side, before the copy: keeps the device path free of syncs
         return b
 
-    def eager_step(self, batch: Batch) -> torch.Tensor:
+    def step_body(self, batch: Batch) -> torch.Tensor:
+        """forward + backward (fused sparse update inside) + dense gradient sync + dense optimizer step."""
         if self.grad_sync is not None:
             self.grad_sync.zero()
-        else:
-            self.dense_optimizer.zero_grad(set_to_none=True)
         loss, _ = self.train_wrapper(batch)
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync.sync()
         self.dense_optimizer.step()
         return loss.detach()
+
+    def eager_step(self, batch: Batch) -> torch.Tensor:
+        if self.grad_sync is None:
+            self.dense_optimizer.zero_grad(set_to_none=True)
+        return self.step_body(batch)
+
+    def check_overflow(self) -> None:
+        for m in self.sharded:
+            m.check_overflow()
 
 
 def _tensors_of(batch: Batch) -> List[torch.Tensor]:
@@ -156,13 +166,11 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        pipe.dense_optimizer.zero_grad(set_to_none=True)
+        if pipe.grad_sync is None:
+            pipe.dense_optimizer.zero_grad(set_to_none=True)
         self._fresh_kjt_caches()
         with torch.cuda.graph(self.graph):
-            loss, _ = pipe.train_wrapper(self.static)
-            loss.backward()
-            pipe.dense_optimizer.step()
-            self.loss = loss.detach()
+            self.loss = pipe.step_body(self.static)
         torch.cuda.synchronize()
 
     def _fresh_kjt_caches(self) -> None:

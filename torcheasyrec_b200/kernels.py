@@ -84,7 +84,8 @@ def build_layout(table_rows: Sequence[int], table_dim: Sequence[int], feat_table
     return FeatureLayout(
         w_off=[t_off[t] for t in feat_table], rows=[table_rows[t] for t in feat_table],
         dim=[table_dim[t] for t in feat_table], col=col, pool=list(feat_pool),
-        key_base=[t_key[t] for t in feat_table], total_keys=max(k, 1), total_dim=c, arena_elems=max(o, 1))
+        key_base=[t_key[t] for t in feat_table], total_keys=max(k, 1), total_dim=c,
+        arena_elems=max(o, 128))   # never smaller than one (widest) row: padding slots read row 0
 
 
 def _stream() -> int:
@@ -232,7 +233,7 @@ class CudaKernels:
         return out_lengths, out_offsets, out_ids, out_pos, out_inv
 
     def bag_grad_expand(self, grad_out: torch.Tensor, lay: FeatureLayout, offsets: torch.Tensor, slot: torch.Tensor,
-                        B: int, n_rows: int) -> torch.Tensor:
+                        B: int, n_rows: int, zero: bool = False) -> torch.Tensor:
         """g_rows[slot[l]] = grad_out[b, col_f:+D] (/L for MEAN) for every id position l of bag (f,b)."""
         grad_out, ld = _rows2d(grad_out, "grad_out")
         _need(offsets, torch.int64, "offsets")
@@ -240,7 +241,7 @@ class CudaKernels:
         D = lay.dim[0]
         if any(d != D for d in lay.dim):
             raise TzkError("bag_grad_expand: all features must share one dim")
-        out = torch.empty((n_rows, D), dtype=torch.float32, device=grad_out.device)
+        out = (torch.zeros if zero else torch.empty)((n_rows, D), dtype=torch.float32, device=grad_out.device)
         check(self._lib.tzk_bag_grad_expand(_ptr(grad_out), ld, _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(offsets),
                                             _ptr(slot), lay.num_features, B, D, _ptr(out), _stream()),
               "tzk_bag_grad_expand")
