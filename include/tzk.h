@@ -90,6 +90,7 @@ int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_off, const in
  * `state`: ADAGRAD -> same layout as `weights`; ROWWISE_ADAGRAD -> one float per key (state[key]);
  * SGD -> ignored (may be NULL).
  * pooled == 0 selects the un-pooled (sequence) layout: grad_out is [nnz, D] indexed by id position.
+ * A feature with feat_rows[f] == 0 is wire padding: its ids are sorted behind every real key and ignored.
  * total_keys = one past the largest sort key (sum of physical rows).  Requires nnz < 2^31. */
 size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys, int32_t max_dim);
 int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,

@@ -96,6 +96,8 @@ def seq_lookup(tables: Sequence[np.ndarray], feat_table: Sequence[int], ids: np.
     for f in range(F):
         W = tables[feat_table[f]]
         s, e = offsets[f * B], offsets[(f + 1) * B]
+        if W.shape[0] == 0:       # padding feature: whatever is read is never used
+            continue
         out[s:e] = W[_clamp_ids(ids[s:e], W.shape[0])]
     return out
 
@@ -121,6 +123,9 @@ def fused_update(optimizer: int, tables: List[np.ndarray], states: List[Optional
         W = tables[t]
         D = W.shape[1]
         s, e = offsets[f * B], offsets[(f + 1) * B]
+        if W.shape[0] == 0:       # zero-row feature = wire padding of the static-capacity exchange: ignored
+            col += D
+            continue
         fid = _clamp_ids(ids[s:e], W.shape[0])
         if pooled:
             bag = _bag_of_position(offsets[f * B:(f + 1) * B + 1] - s)

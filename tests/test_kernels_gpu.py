@@ -329,3 +329,32 @@ def test_dlrm_fused_interaction_vs_reference_golden_and_oracle(kernels):
     wd, ws = O.dlrm_interact_bwd(dense_feat, sparse, d_out, 26, 16)
     np.testing.assert_allclose(dd.cpu().numpy(), wd, rtol=1e-5, atol=2e-5)
     np.testing.assert_allclose(ds.cpu().numpy(), ws, rtol=1e-5, atol=2e-5)
+
+
+def test_fused_bwd_ignores_zero_row_padding_features(kernels):
+    """Static-capacity exchange: ids of a zero-row feature are wire padding — sorted last, never applied."""
+    from torcheasyrec_b200.kernels import FeatureLayout
+
+    rng = np.random.default_rng(77)
+    rows, D, B = [400, 0, 50, 0], 16, 1            # B=1 "bags" = whole (source, feature) runs, as on the owner side
+    lens = np.array([300, 5000, 200, 4000], dtype=np.int32)
+    offsets = O.lengths_to_offsets(lens)
+    ids = np.concatenate([rng.integers(0, max(r, 1), size=n) for r, n in zip(rows, lens)]).astype(np.int64)
+    tables = [O.default_table_init(max(r, 1), D, rng)[:r] for r in rows]
+    real = build_layout([400, 50], [D, D], [0, 1], [0, 0])
+    lay = FeatureLayout(w_off=[real.w_off[0], 0, real.w_off[1], 0], rows=rows, dim=[D] * 4, col=[0] * 4, pool=[0] * 4,
+                        key_base=[real.key_base[0], 0, real.key_base[1], 0], total_keys=real.total_keys,
+                        total_dim=D, arena_elems=real.arena_elems).to(DEV)
+    arena_np = np.zeros(real.arena_elems, np.float32)
+    arena_np[real.w_off[0]:real.w_off[0] + 400 * D] = tables[0].ravel()
+    arena_np[real.w_off[1]:real.w_off[1] + 50 * D] = tables[2].ravel()
+    arena = cu(arena_np)
+    state = torch.zeros_like(arena)
+    grad = rng.standard_normal((len(ids), D)).astype(np.float32)
+    kernels.fused_bwd(O.OPT_ADAGRAD, False, cu(grad), arena, state, lay, cu(ids), cu(offsets), B, 0.05, 1e-8, 1.0)
+    want = [t.copy() for t in tables]
+    st = [np.zeros_like(t) for t in tables]
+    O.fused_update(O.OPT_ADAGRAD, want, st, [0, 1, 2, 3], [0] * 4, ids, offsets, B, grad, 0.05, 1e-8, 1.0, pooled=False)
+    got = arena.cpu().numpy()
+    np.testing.assert_allclose(got[real.w_off[0]:real.w_off[0] + 400 * D].reshape(400, D), want[0], rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(got[real.w_off[1]:real.w_off[1] + 50 * D].reshape(50, D), want[2], rtol=5e-5, atol=5e-6)

@@ -44,6 +44,7 @@ struct BwdArgs {
   int32_t optimizer;
   int32_t pooled;
   int64_t n;
+  uint64_t sentinel;  // key of ids that belong to a zero-row (padding) feature: sorted last, never updated
 };
 
 __device__ __forceinline__ void stage_feats(BwdFeat* fd, const int64_t* feat_w_off, const int64_t* feat_rows,
@@ -65,7 +66,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 linearize_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
                  const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_key_base, int F,
-                 int B, int pooled, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
+                 int B, int pooled, KeyT sentinel, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
   const int64_t n_bags = (int64_t)F * B;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t bag = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bag < n_bags; bag += stride) {
@@ -75,7 +76,7 @@ linearize_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ of
     for (int64_t l = s; l < e; ++l) {
       int64_t id = __ldg(ids + l);
       if ((uint64_t)id >= (uint64_t)rows) id = 0;
-      keys[l] = (KeyT)(base + id);
+      keys[l] = rows > 0 ? (KeyT)(base + id) : sentinel;
       vals[l] = pooled ? (int32_t)bag : (int32_t)l;
     }
   }
@@ -87,7 +88,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 linearize_seq_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
                      const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_key_base, int F,
-                     int B, int64_t n, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
+                     int B, int64_t n, KeyT sentinel, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int64_t* key_start = reinterpret_cast<int64_t*>(smem_raw);  // [F+1]
   int64_t* base = key_start + (F + 1);
@@ -107,7 +108,7 @@ linearize_seq_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict_
     }
     int64_t id = __ldg(ids + l);
     if ((uint64_t)id >= (uint64_t)rows[lo]) id = 0;
-    keys[l] = (KeyT)(base[lo] + id);
+    keys[l] = rows[lo] > 0 ? (KeyT)(base[lo] + id) : sentinel;   // zero-row feature = wire padding
     vals[l] = (int32_t)l;
   }
 }
@@ -344,7 +345,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
     bool head[kPos], single[kPos];
 #pragma unroll
     for (int u = 0; u < kPos; ++u) {
-      head[u] = (p0 + u < a.n) && key[u + 1] != key[u];
+      head[u] = (p0 + u < a.n) && key[u + 1] != key[u] && key[u + 1] != (KeyT)a.sentinel;
       single[u] = head[u] && ((p0 + u + 1 >= a.n) || key[u + 2] != key[u + 1]);
     }
     if (CH == 1 && KP > 1) {
@@ -629,7 +630,7 @@ inline int64_t max_pslots(int64_t n) { return 2 * (n / kChunk) + 2; }           
 
 WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
   WsLayout L;
-  const bool k64 = total_keys > ((int64_t)1 << 32);
+  const bool k64 = total_keys >= ((int64_t)1 << 32);
   const size_t ksz = k64 ? 8 : 4;
   const int64_t n = nnz < 1 ? 1 : nnz;
   size_t o = 0;
@@ -643,7 +644,7 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
   const size_t rowf = (size_t)((max_dim + 127) / 128 * 128 < 128 ? 128 : (max_dim + 127) / 128 * 128) * 4;
   L.partials = o; o = align_up(o + max_pslots(n) * rowf * sizeof(float), 256);
   size_t tb = 0;
-  const int bits = bits_for(total_keys);
+  const int bits = bits_for(total_keys + 1);
   if (k64) cub_sort<uint64_t>(nullptr, tb, nullptr, nullptr, nullptr, nullptr, n, bits, 0);
   else cub_sort<uint32_t>(nullptr, tb, nullptr, nullptr, nullptr, nullptr, n, bits, 0);
   L.cub_bytes = tb;
@@ -735,8 +736,9 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
   wl.runs = reinterpret_cast<LongRun*>(ws + L.runs);
   wl.counters = reinterpret_cast<int32_t*>(ws + L.counters);
   wl.partials = reinterpret_cast<float*>(ws + L.partials);
-  const bool k64 = total_keys > ((int64_t)1 << 32);
-  const int bits = bits_for(total_keys);
+  const bool k64 = total_keys >= ((int64_t)1 << 32);
+  const int bits = bits_for(total_keys + 1);   // one spare value above the largest key = padding sentinel
+  const uint64_t sentinel = ((uint64_t)1 << bits) - 1;
 
   zero_counters<<<1, 1, 0, st>>>(wl.counters);
   const int64_t n_bags = (int64_t)F * B;
@@ -748,20 +750,20 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
   if (k64) {
     if (pooled)
       linearize_kernel<uint64_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
-                                                                pooled, (uint64_t*)keys_in, vals_in);
+                                                                pooled, (uint64_t)sentinel, (uint64_t*)keys_in, vals_in);
     else
-      linearize_seq_kernel<uint64_t><<<grid_seq, kThreads, smem_lin, st>>>(ids, offsets, feat_rows, feat_key_base,
-                                                                           F, B, nnz, (uint64_t*)keys_in, vals_in);
+      linearize_seq_kernel<uint64_t><<<grid_seq, kThreads, smem_lin, st>>>(
+          ids, offsets, feat_rows, feat_key_base, F, B, nnz, (uint64_t)sentinel, (uint64_t*)keys_in, vals_in);
     TZK_CHECK_LAUNCH("linearize_kernel");
     ce = cub_sort<uint64_t>(ws + L.cub_tmp, cub_bytes, (const uint64_t*)keys_in, (uint64_t*)keys_out, vals_in,
                             vals_out, nnz, bits, st);
   } else {
     if (pooled)
       linearize_kernel<uint32_t><<<grid_lin, kThreads, 0, st>>>(ids, offsets, feat_rows, feat_key_base, F, B,
-                                                                pooled, (uint32_t*)keys_in, vals_in);
+                                                                pooled, (uint32_t)sentinel, (uint32_t*)keys_in, vals_in);
     else
-      linearize_seq_kernel<uint32_t><<<grid_seq, kThreads, smem_lin, st>>>(ids, offsets, feat_rows, feat_key_base,
-                                                                           F, B, nnz, (uint32_t*)keys_in, vals_in);
+      linearize_seq_kernel<uint32_t><<<grid_seq, kThreads, smem_lin, st>>>(
+          ids, offsets, feat_rows, feat_key_base, F, B, nnz, (uint32_t)sentinel, (uint32_t*)keys_in, vals_in);
     TZK_CHECK_LAUNCH("linearize_kernel");
     ce = cub_sort<uint32_t>(ws + L.cub_tmp, cub_bytes, (const uint32_t*)keys_in, (uint32_t*)keys_out, vals_in,
                             vals_out, nnz, bits, st);
@@ -771,7 +773,7 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
   BwdArgs a;
   a.grad_out = grad_out; a.ld_grad = ld_grad; a.offsets = offsets; a.weights = weights; a.state = state;
   a.lr = lr; a.eps = eps; a.grad_scale = grad_scale; a.F = F; a.B = B; a.optimizer = optimizer;
-  a.pooled = pooled; a.n = nnz;
+  a.pooled = pooled; a.n = nnz; a.sentinel = sentinel;
 
   const int vec = (vec_ok && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)grad_out % 16 == 0) &&
                    (ld_grad % 4 == 0) && (optimizer != TZK_OPT_ADAGRAD || (uintptr_t)state % 16 == 0))

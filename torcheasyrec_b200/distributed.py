@@ -119,7 +119,7 @@ class _DimGroup:
         # static-capacity variant (graph-capturable step): per source rank F feature slots + one padding slot
         padw = lambda xs, v: [x for r in range(world) for x in (list(xs) + [v])]
         self.owner_layout_static = FeatureLayout(
-            w_off=padw(lay.w_off, 0), rows=padw(lay.rows, 1), dim=padw(lay.dim, self.dim),
+            w_off=padw(lay.w_off, 0), rows=padw(lay.rows, 0), dim=padw(lay.dim, self.dim),   # rows 0 = padding slot
             col=[0] * ((F + 1) * world), pool=[POOL_SUM] * ((F + 1) * world), key_base=padw(lay.key_base, 0),
             total_keys=lay.total_keys, total_dim=self.dim, arena_elems=lay.arena_elems).to(device)
         self.static_alpha: Optional[float] = None     # set by shard_model(static_capacity=...)
