@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--sharded-mode", default="graph", choices=["graph", "eager"],
                     help="N>1: 'graph' = static-capacity exchange captured in one CUDA graph, 'eager' = dynamic splits")
     ap.add_argument("--static-capacity", type=float, default=1.5)
+    ap.add_argument("--force-sharded", action="store_true",
+                    help="N=1 only: still go through bucketize / all-to-all / owner gather (1-rank process group)")
     return ap.parse_args()
 
 
@@ -181,18 +183,24 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    sharded = world > 1 or args.force_sharded
+    if sharded:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     from torcheasyrec_b200.engine import GraphedTrainStep, Pipeline
     from torcheasyrec_b200.kernels import default_kernels
 
     B, K, W = args.batch_size, args.steps, max(args.warmup, 3)
     graphed = world == 1 or args.sharded_mode == "graph"
     pipe = Pipeline(args.model, device=dev, max_rows=args.max_rows or None,
-                    sharding="row_wise" if world > 1 else None,
-                    static_capacity=args.static_capacity if (world > 1 and graphed) else None)
+                    sharding="row_wise" if sharded else None,
+                    static_capacity=args.static_capacity if (sharded and graphed) else None)
     host = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + i, id_dist=args.id_dist).pin_memory()
             for i in range(args.ring)]
     ring = [hb.to(dev) for hb in host]
@@ -282,7 +290,7 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernels (rank 0, standalone launches on the same inputs) -----------------
-    if world > 1:
+    if sharded:
         roofline, cpu = None, None
         _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
         return
@@ -351,7 +359,7 @@ def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step,
                    "global_batch": global_batch, "parallelism": f"rw{world}+dp{world}",
                    "l2": f"inputs rotate over {ring_len} distinct batches; tables 12.2 GiB + state 12.2 GiB >> 126 MB L2",
                    "cuda_graph": bool(args.sharded_mode == "graph" or world == 1),
-                   "exchange": ("none" if world == 1 else
+                   "exchange": ("none" if (world == 1 and not args.force_sharded) else
                                 (f"static capacity {args.static_capacity}x, in-graph NCCL all-to-all"
                                  if args.sharded_mode == "graph" else "dynamic splits (host read per step)"))},
         "e2e": {"value": global_batch * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -380,7 +388,7 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
-    if int(os.environ.get("WORLD_SIZE", 1)) > 1 and torch.distributed.is_initialized():
+    if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 
 

@@ -121,12 +121,16 @@ int tzk_bag_grad_expand(const float* grad_out, int64_t ld_grad, const int32_t* f
  *   out_ids                       local ids in that order; relative order inside a bag is kept
  *                                 (bucketize_pos = false)
  *   out_pos (nullable)            out_pos[o] = input position of output slot o ("unbucketize permute")
- *   out_inv (nullable)            out_inv[l] = output slot of input position l (its inverse) */
+ *   out_inv (nullable)            out_inv[l] = output slot of input position l (its inverse)
+ * wire_capacity = 0: compact layout as above.  wire_capacity = C > 0: fixed-capacity wire layout — the ids of
+ * destination r occupy out_ids[r*C ...] (out_ids / out_pos then hold W*C slots, unused ones are left untouched,
+ * so pre-fill them); ids that do not fit are dropped and the caller detects that from the counts. */
 size_t tzk_bucketize_rw_workspace_bytes(int32_t F, int32_t B, int32_t W, int64_t nnz);
 int tzk_bucketize_rw(const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t W,
                      const int64_t* feat_block, const int32_t* feat_owner, int64_t nnz,
-                     int32_t* out_lengths, int64_t* out_offsets, int64_t* out_ids, int32_t* out_pos,
-                     int32_t* out_inv, void* workspace, size_t workspace_bytes, tzk_stream_t stream);
+                     int64_t wire_capacity, int32_t* out_lengths, int64_t* out_offsets, int64_t* out_ids,
+                     int32_t* out_pos, int32_t* out_inv, void* workspace, size_t workspace_bytes,
+                     tzk_stream_t stream);
 
 /* ---- K2: KJT segment permute  ([EXT] fbgemm::permute_2D_sparse_data, KeyedJaggedTensor.permute;
  * used by the TW input-dist, App. A.5) ----------------------------------------------------------------

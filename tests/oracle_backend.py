@@ -85,14 +85,27 @@ class OracleKernels:
         O.fused_update(optimizer, tabs, states, ft, lay.pool, _np(ids), _np(offsets), B, _np(grad_out), lr, eps,
                        grad_scale, pooled=bool(pooled))
 
-    def bucketize_rw(self, ids, offsets, F, B, W, feat_block, want_pos=False, feat_owner=None, want_inv=False):
+    def bucketize_rw(self, ids, offsets, F, B, W, feat_block, want_pos=False, feat_owner=None, want_inv=False,
+                     wire_capacity=0):
         ol, oo, oi, op = O.bucketize_rw(_np(ids), _np(offsets), F, B, W, _np(feat_block).tolist(),
                                         None if feat_owner is None else _np(feat_owner).tolist())
-        inv = None
-        if want_inv:
-            inv = np.empty(len(op), dtype=np.int32)
-            inv[op] = np.arange(len(op), dtype=np.int32)
-            inv = torch.from_numpy(inv)
+        inv = np.empty(len(op), dtype=np.int32)
+        inv[op] = np.arange(len(op), dtype=np.int32)
+        if wire_capacity:      # fixed-capacity wire layout: destination r starts at r*C
+            C = wire_capacity
+            dest_start = oo[::F * B]
+            slot = np.arange(len(oi))
+            r_of = np.searchsorted(dest_start[1:], slot, side="right").clip(max=W - 1)
+            rel = slot - dest_start[r_of]
+            keep = rel < C
+            pslot = (r_of * C + rel)
+            pid = np.zeros(W * C, dtype=np.int64)
+            ppos = np.zeros(W * C, dtype=np.int32)
+            pid[pslot[keep]] = oi[keep]
+            ppos[pslot[keep]] = op[keep]
+            inv = np.where(keep, pslot, r_of * C)[inv].astype(np.int32)
+            oi, op = pid, ppos
+        inv = torch.from_numpy(inv) if want_inv else None
         return (torch.from_numpy(ol), torch.from_numpy(oo), torch.from_numpy(oi),
                 torch.from_numpy(op) if want_pos else None, inv)
 

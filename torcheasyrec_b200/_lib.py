@@ -34,7 +34,7 @@ SIGNATURES = {
     "tzk_bucketize_rw_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int64]),
     "tzk_bucketize_rw": (
         c_int32,
-        [P, P, c_int32, c_int32, c_int32, P, P, c_int64, P, P, P, P, P, P, c_size_t, P],
+        [P, P, c_int32, c_int32, c_int32, P, P, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P],
     ),
     "tzk_bag_grad_expand": (c_int32, [P, c_int64, P, P, P, P, c_int32, c_int32, c_int32, P, P]),
     "tzk_permute_lengths": (c_int32, [P, P, c_int32, c_int32, P, P]),

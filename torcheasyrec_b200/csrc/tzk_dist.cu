@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(kThreads)
 bucketize_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
                          const int64_t* __restrict__ feat_block, const int32_t* __restrict__ feat_owner, int F,
                          int B, int W, const int64_t* __restrict__ out_offsets, int64_t* __restrict__ out_ids,
-                         int32_t* __restrict__ out_pos, int32_t* __restrict__ out_inv) {
+                         int32_t* __restrict__ out_pos, int32_t* __restrict__ out_inv, int64_t cap) {
+  // cap > 0: destination r's ids start at r*cap instead of right after destination r-1 (fixed-capacity wire
+  // layout of the graph-capturable exchange); slots beyond cap are dropped (the caller checks the counts).
   const int64_t n_bags = (int64_t)F * B;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t bag = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bag < n_bags; bag += stride) {
@@ -60,7 +62,12 @@ bucketize_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restr
     int64_t loc;
     if (e - s == 1) {
       const int r = dest_of(__ldg(ids + s), blk, own, W, &loc);
-      const int64_t o = __ldg(out_offsets + ((int64_t)r * F + f) * B + b);
+      int64_t o = __ldg(out_offsets + ((int64_t)r * F + f) * B + b);
+      if (cap > 0) {
+        o = o - __ldg(out_offsets + (int64_t)r * F * B);
+        if (o >= cap) { if (out_inv) out_inv[s] = (int32_t)(r * cap); continue; }
+        o += (int64_t)r * cap;
+      }
       out_ids[o] = loc;
       if (out_pos) out_pos[o] = (int32_t)s;
       if (out_inv) out_inv[s] = (int32_t)o;
@@ -69,7 +76,12 @@ bucketize_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restr
       for (int w = 0; w < W; ++w) cnt[w] = 0;
       for (int64_t l = s; l < e; ++l) {
         const int r = dest_of(__ldg(ids + l), blk, own, W, &loc);
-        const int64_t o = __ldg(out_offsets + ((int64_t)r * F + f) * B + b) + cnt[r]++;
+        int64_t o = __ldg(out_offsets + ((int64_t)r * F + f) * B + b) + cnt[r]++;
+        if (cap > 0) {
+          o = o - __ldg(out_offsets + (int64_t)r * F * B);
+          if (o >= cap) { if (out_inv) out_inv[l] = (int32_t)(r * cap); continue; }
+          o += (int64_t)r * cap;
+        }
         out_ids[o] = loc;
         if (out_pos) out_pos[o] = (int32_t)l;
         if (out_inv) out_inv[l] = (int32_t)o;
@@ -112,9 +124,10 @@ extern "C" size_t tzk_bucketize_rw_workspace_bytes(int32_t F, int32_t B, int32_t
 
 extern "C" int tzk_bucketize_rw(const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t W,
                                 const int64_t* feat_block, const int32_t* feat_owner, int64_t nnz,
-                                int32_t* out_lengths, int64_t* out_offsets, int64_t* out_ids, int32_t* out_pos,
-                                int32_t* out_inv, void* workspace, size_t workspace_bytes,
+                                int64_t wire_capacity, int32_t* out_lengths, int64_t* out_offsets, int64_t* out_ids,
+                                int32_t* out_pos, int32_t* out_inv, void* workspace, size_t workspace_bytes,
                                 tzk_stream_t stream) {
+  TZK_REQUIRE(wire_capacity >= 0 && wire_capacity * W < ((int64_t)1 << 31), "bucketize_rw: bad wire_capacity");
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0, "bucketize_rw: negative size");
   TZK_REQUIRE(W >= 1 && W <= kMaxW, "bucketize_rw: W=%d out of range [1,%d]", W, kMaxW);
   TZK_REQUIRE(nnz < ((int64_t)1 << 31), "bucketize_rw: nnz >= 2^31");
@@ -132,7 +145,7 @@ extern "C" int tzk_bucketize_rw(const int64_t* ids, const int64_t* offsets, int3
   if (rc) return rc;
   if (nnz > 0) {
     bucketize_scatter_kernel<<<grid, kThreads, 0, st>>>(ids, offsets, feat_block, feat_owner, F, B, W,
-                                                        out_offsets, out_ids, out_pos, out_inv);
+                                                        out_offsets, out_ids, out_pos, out_inv, wire_capacity);
     TZK_CHECK_LAUNCH("bucketize_scatter_kernel");
   }
   return 0;

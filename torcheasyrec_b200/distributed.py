@@ -213,20 +213,14 @@ class _StaticDispatch:
             raise RuntimeError(f"static-capacity sharding was sized for {g.static_nnz} ids per step, got {nnz}")
         cap = g.static_cap
         self.n_slots = W * cap
-        _, oo, oids, _, inv = k.bucketize_rw(ids, offsets, F, B, W, g.feat_block, feat_owner=g.feat_owner,
-                                             want_inv=True)
+        # bucketize straight into the fixed-capacity wire layout (destination r starts at slot r*cap)
+        _, oo, send_ids, _, inv = k.bucketize_rw(ids, offsets, F, B, W, g.feat_block, feat_owner=g.feat_owner,
+                                                 want_inv=True, wire_capacity=cap)
         seg = oo[::B]                                              # [W*F+1]
         counts = (seg[1:] - seg[:-1]).view(W, F)
         dest_start = oo[::F * B]                                   # [W+1] compact start of every destination
-        per_dest = dest_start[1:] - dest_start[:-1]
-        g.overflow.add_((per_dest > cap).any().to(torch.int32))
-        # compact wire slot -> padded wire slot
-        slot = torch.arange(nnz, device=dev)
-        r_of = torch.searchsorted(dest_start[1:].contiguous(), slot, right=True).clamp_(max=W - 1)
-        pslot = (slot + r_of * cap - dest_start[r_of]).clamp_(max=self.n_slots - 1)
-        send_ids = torch.zeros(self.n_slots, dtype=torch.int64, device=dev)
-        send_ids.index_copy_(0, pslot, oids)
-        self.inv = pslot[inv.to(torch.int64)]                      # padded slot of every original id position
+        g.overflow.add_(((dest_start[1:] - dest_start[:-1]) > cap).any().to(torch.int32))
+        self.inv = inv                                             # padded slot of every original id position
         recv_counts = torch.empty_like(counts)
         dist.all_to_all_single(recv_counts, counts, group=group)   # [src, F], equal splits
         self.recv_ids = torch.empty_like(send_ids)

@@ -210,8 +210,9 @@ class CudaKernels:
     # ------------------------------------------------------------------ K1 / K2
     def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
                      feat_block: torch.Tensor, want_pos: bool = False, feat_owner: Optional[torch.Tensor] = None,
-                     want_inv: bool = False):
-        """-> (out_lengths [W*F*B], out_offsets [W*F*B+1], out_ids [nnz], out_pos|None, out_inv|None)."""
+                     want_inv: bool = False, wire_capacity: int = 0):
+        """-> (out_lengths [W*F*B], out_offsets [W*F*B+1], out_ids [nnz], out_pos|None, out_inv|None).
+        wire_capacity = C > 0: out_ids / out_pos have W*C slots (zero-filled), destination r starts at r*C."""
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         _need(feat_block, torch.int64, "feat_block")
@@ -221,13 +222,15 @@ class CudaKernels:
         nnz = ids.numel()
         out_lengths = torch.empty(W * F * B, dtype=torch.int32, device=dev)
         out_offsets = torch.empty(W * F * B + 1, dtype=torch.int64, device=dev)
-        out_ids = torch.empty(nnz, dtype=torch.int64, device=dev)
-        out_pos = torch.empty(nnz, dtype=torch.int32, device=dev) if want_pos else None
+        n_out = W * wire_capacity if wire_capacity else nnz
+        out_ids = (torch.zeros if wire_capacity else torch.empty)(n_out, dtype=torch.int64, device=dev)
+        out_pos = (torch.zeros if wire_capacity else torch.empty)(n_out, dtype=torch.int32, device=dev) \
+            if want_pos else None
         out_inv = torch.empty(nnz, dtype=torch.int32, device=dev) if want_inv else None
         nb = self._lib.tzk_bucketize_rw_workspace_bytes(F, B, W, nnz)
         ws = self._workspace("bucketize", nb, dev)
         check(self._lib.tzk_bucketize_rw(_ptr(ids), _ptr(offsets), F, B, W, _ptr(feat_block), _ptr(feat_owner), nnz,
-                                         _ptr(out_lengths), _ptr(out_offsets), _ptr(out_ids), _ptr(out_pos),
+                                         wire_capacity, _ptr(out_lengths), _ptr(out_offsets), _ptr(out_ids), _ptr(out_pos),
                                          _ptr(out_inv), _ptr(ws), ws.numel(), _stream()), "tzk_bucketize_rw")
         self.launches += 5
         return out_lengths, out_offsets, out_ids, out_pos, out_inv
