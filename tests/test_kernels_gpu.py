@@ -360,8 +360,8 @@ def test_fused_bwd_ignores_zero_row_padding_features(kernels):
     np.testing.assert_allclose(got[real.w_off[1]:real.w_off[1] + 50 * D].reshape(50, D), want[2], rtol=5e-5, atol=5e-6)
 
 
-@pytest.mark.parametrize("W", [2, 8])
-def test_bucketize_fixed_capacity_wire_layout(kernels, W):
+@pytest.mark.parametrize("W,factor", [(2, 1.5), (8, 2.5), (8, 1.2)])
+def test_bucketize_fixed_capacity_wire_layout(kernels, W, factor):
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from oracle_backend import OracleKernels
@@ -371,7 +371,7 @@ def test_bucketize_fixed_capacity_wire_layout(kernels, W):
     rows = [100000, 3, 77, 40000]
     ids, lengths, offsets = random_kjt(rng, F, B, rows, 1, fixed_len=1)
     blocks = np.asarray([O.rw_block_size(r, W) for r in rows], np.int64)
-    C = int(1.5 * len(ids) / W) // 8 * 8 + 8
+    C = int(factor * len(ids) / W) // 8 * 8 + 8      # factor 1.2 overflows on purpose (tiny tables skew the ranks)
     ol, oo, oi, op, inv = kernels.bucketize_rw(cu(ids), cu(offsets), F, B, W, cu(blocks), want_pos=True, want_inv=True,
                                                wire_capacity=C)
     wl, wo, wi, wp, winv = OracleKernels().bucketize_rw(torch.from_numpy(ids), torch.from_numpy(offsets), F, B, W,
@@ -381,7 +381,10 @@ def test_bucketize_fixed_capacity_wire_layout(kernels, W):
     np.testing.assert_array_equal(oi.cpu().numpy(), wi.numpy())
     np.testing.assert_array_equal(op.cpu().numpy(), wp.numpy())
     np.testing.assert_array_equal(inv.cpu().numpy(), winv.numpy())
-    # every id is recoverable from its padded slot
-    dest = inv.cpu().numpy() // C
-    f_of = np.repeat(np.arange(F), B)
-    np.testing.assert_array_equal(oi.cpu().numpy()[inv.cpu().numpy()] + dest * blocks[f_of], ids)
+    per_dest = np.diff(wo.numpy()[::F * B])
+    if (per_dest <= C).all():      # no overflow: every id is recoverable from its padded slot
+        dest = inv.cpu().numpy() // C
+        f_of = np.repeat(np.arange(F), B)
+        np.testing.assert_array_equal(oi.cpu().numpy()[inv.cpu().numpy()] + dest * blocks[f_of], ids)
+    else:
+        assert factor < 1.5
