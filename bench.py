@@ -21,6 +21,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the ONE JSON line (NCCL prints its version banner there)
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # CPU baseline: idle OpenMP workers must not spin
 os.environ.setdefault("GOMP_SPINCOUNT", "0")
 if "--impl" in sys.argv and "reference" in sys.argv:
