@@ -179,15 +179,30 @@ int tzk_fm_bwd(const float* x, int64_t ld_x, const float* dy, int64_t ld_dy, int
  * out[b, 0:P]          = strict upper triangle of X_b X_b^T, row-major (triu_indices(N,N,1)), P=N(N-1)/2
  * out[b, P:P+D]        = dense[b]          (only if copy_dense  != 0)
  * out[b, .. : +Ns*D]   = sparse[b]         (only if copy_sparse != 0)
- * i.e. with both flags it emits the whole `final_mlp` input of DLRM in one pass. N <= 64, D <= 128. */
+ * i.e. with both flags it emits the whole `final_mlp` input of DLRM in one pass. N <= 64, D <= 128.
+ * p_pad in [0,3]: that many zero columns are inserted right after the P interaction terms, so that with
+ * p_pad = (4 - P % 4) % 4 the dense and sparse blocks start on 16-B boundaries (128-bit stores, and 16-B aligned
+ * rows for the GEMM that consumes the result; its weight gets matching zero columns). */
 int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const float* sparse, int64_t ld_sparse,
                          int64_t B, int32_t Ns, int32_t D, int32_t copy_dense, int32_t copy_sparse,
-                         float* out, int64_t ld_out, tzk_stream_t stream);
+                         int32_t p_pad, float* out, int64_t ld_out, tzk_stream_t stream);
 /* d_dense (nullable iff dense == NULL), d_sparse from d_out (same layout as `out`). */
 int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const float* sparse, int64_t ld_sparse,
                          const float* d_out, int64_t ld_dout, int64_t B, int32_t Ns, int32_t D,
-                         int32_t copy_dense, int32_t copy_sparse, float* d_dense, int64_t ld_ddense,
-                         float* d_sparse, int64_t ld_dsparse, tzk_stream_t stream);
+                         int32_t copy_dense, int32_t copy_sparse, int32_t p_pad, float* d_dense,
+                         int64_t ld_ddense, float* d_sparse, int64_t ld_dsparse, tzk_stream_t stream);
+
+/* ---- dense-tower helpers (callers of the path: tzrec/modules/mlp.py:20-84, Perceptron = Linear -> ReLU) ----
+ * The tower GEMMs stay library calls; these fuse the element-wise passes around them.
+ *   tzk_bias_act        : y[r, 0:N] = act(y[r, 0:N] + bias)            (in place; bias nullable; relu 0/1)
+ *   tzk_act_bwd_colsum  : dz = dy * (y > 0) (or dy if !relu; dz nullable), colsum[c] = sum_r dz[r,c]
+ *                         deterministic two-stage column sum; N must divide 256. */
+int tzk_bias_act(float* y, int64_t ld_y, const float* bias, int64_t M, int32_t N, int32_t relu,
+                 tzk_stream_t stream);
+size_t tzk_act_bwd_colsum_workspace_bytes(int64_t M, int32_t N);
+int tzk_act_bwd_colsum(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int64_t M, int32_t N,
+                       int32_t relu, float* dz, int64_t ld_dz, float* colsum, void* workspace,
+                       size_t workspace_bytes, tzk_stream_t stream);
 
 #ifdef __cplusplus
 }

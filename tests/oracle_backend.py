@@ -152,17 +152,25 @@ class OracleKernels:
             return torch.from_numpy(self.C.fm_bwd(_c(x), _c(dy), N, D))
         return torch.from_numpy(O.fm_bwd(_np(x).reshape(-1, N, D), _np(dy)).reshape(-1, N * D))
 
-    def dot_interact_fwd(self, dense, sparse, Ns, D, copy_dense, copy_sparse, pad_to=1):
+    def dot_interact_fwd(self, dense, sparse, Ns, D, copy_dense, copy_sparse, pad_to=1, p_pad=0):
         if self.use_c:
             res = self.C.dot_interact_fwd(_c(dense), _c(sparse), Ns, D, copy_dense, copy_sparse)
         else:
             res = O.dlrm_interact(_np(dense), _np(sparse), Ns, D, copy_dense, copy_sparse)
+        if p_pad:
+            N = Ns + (dense is not None)
+            P = N * (N - 1) // 2
+            res = np.concatenate([res[:, :P], np.zeros((res.shape[0], p_pad), np.float32), res[:, P:]], axis=1)
         pad = (-res.shape[1]) % pad_to
         if pad:
             res = np.concatenate([res, np.zeros((res.shape[0], pad), np.float32)], axis=1)
         return torch.from_numpy(np.ascontiguousarray(res))
 
-    def dot_interact_bwd(self, dense, sparse, d_out, Ns, D, copy_dense, copy_sparse):
+    def dot_interact_bwd(self, dense, sparse, d_out, Ns, D, copy_dense, copy_sparse, p_pad=0):
+        if p_pad:
+            N = Ns + (dense is not None)
+            P = N * (N - 1) // 2
+            d_out = torch.cat([d_out[:, :P], d_out[:, P + p_pad:]], dim=1)
         if self.use_c:
             dd, ds = self.C.dot_interact_bwd(_c(dense), _c(sparse), _c(d_out), Ns, D, copy_dense, copy_sparse)
             return (None if dd is None else torch.from_numpy(dd)), torch.from_numpy(ds)

@@ -388,3 +388,39 @@ def test_bucketize_fixed_capacity_wire_layout(kernels, W, factor):
         np.testing.assert_array_equal(oi.cpu().numpy()[inv.cpu().numpy()] + dest * blocks[f_of], ids)
     else:
         assert factor < 1.5
+
+
+def test_dlrm_interaction_aligned_layout_matches_reference_layout(kernels):
+    """[P | 1 zero | dense | sparse] (784 wide) carries exactly the reference's 783 columns; same for the backward."""
+    sparse, all_feat = GOLD["dlrm_sparse"], GOLD["dlrm_all_feat"]
+    dense_feat = all_feat[:, 351:367]
+    got = kernels.dot_interact_fwd(cu(dense_feat), cu(sparse), 26, 16, True, True, pad_to=4, p_pad=1).cpu().numpy()
+    assert got.shape == (all_feat.shape[0], 784)
+    np.testing.assert_allclose(got[:, :351], all_feat[:, :351], rtol=1e-5, atol=1e-5)
+    assert (got[:, 351] == 0).all()
+    np.testing.assert_array_equal(got[:, 352:], all_feat[:, 351:])
+    rng = np.random.default_rng(2)
+    d_out = rng.standard_normal(all_feat.shape).astype(np.float32)
+    d_pad = np.concatenate([d_out[:, :351], rng.standard_normal((d_out.shape[0], 1)).astype(np.float32), d_out[:, 351:]], 1)
+    dd, ds = kernels.dot_interact_bwd(cu(dense_feat), cu(sparse), cu(d_pad), 26, 16, True, True, p_pad=1)
+    wd, ws = O.dlrm_interact_bwd(dense_feat, sparse, d_out, 26, 16)
+    np.testing.assert_allclose(dd.cpu().numpy(), wd, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(ds.cpu().numpy(), ws, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("N", [1, 16, 64, 256])
+def test_tower_helpers_bias_act_and_relu_bwd_colsum(kernels, N):
+    torch.manual_seed(N)
+    M = 5000
+    y = torch.randn(M, N, device=DEV)
+    b = torch.randn(N, device=DEV)
+    want = torch.relu(y + b)
+    got = kernels.bias_act(y.clone(), b, True)
+    assert torch.equal(got, want)
+    dy = torch.randn(M, N, device=DEV)
+    dz, colsum = kernels.act_bwd_colsum(dy, want, True)
+    assert torch.equal(dz, dy * (want > 0))
+    ref = (dy * (want > 0)).double().sum(0)
+    np.testing.assert_allclose(colsum.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-4)
+    _, cs2 = kernels.act_bwd_colsum(dy, None, False, want_dz=False)
+    np.testing.assert_allclose(cs2.cpu().numpy(), dy.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)

@@ -46,11 +46,14 @@ SIGNATURES = {
     "tzk_fm_bwd": (c_int32, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, c_int64, P]),
     "tzk_dot_interact_fwd": (
         c_int32,
-        [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, P, c_int64, P],
+        [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, P, c_int64, P],
     ),
+    "tzk_bias_act": (c_int32, [P, c_int64, P, c_int64, c_int32, c_int32, P]),
+    "tzk_act_bwd_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "tzk_act_bwd_colsum": (c_int32, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, c_int64, P, P, c_size_t, P]),
     "tzk_dot_interact_bwd": (
         c_int32,
-        [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, P, c_int64, P,
+        [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, P, c_int64, P,
          c_int64, P],
     ),
 }

@@ -154,15 +154,15 @@ __device__ __forceinline__ void stage_x(float* X, const float* dense, int64_t ld
 template <int DT>
 __global__ void __launch_bounds__(kIWarps * 32)
 dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
-                        int64_t ld_sparse, int64_t B, int Ns, int D_rt, int copy_dense, int copy_sparse,
-                        float* __restrict__ out, int64_t ld_out) {
+                        int64_t ld_sparse, int64_t B, int Ns, int D_rt, int copy_dense, int copy_sparse, int p_pad,
+                        int aligned, float* __restrict__ out, int64_t ld_out) {
   extern __shared__ __align__(16) float smem[];
   const int D = DT ? DT : D_rt;
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;        // rows padded to a multiple of 4 (pad rows are zero)
   const int DS = D + 4;               // row stride
   const int P = N * (N - 1) / 2;
-  const int Pp = (P + 3) & ~3;        // keeps every warp's slab 16-B aligned
+  const int Pp = (P + 3 + 4) & ~3;    // room for p_pad zeros; keeps every warp's slab 16-B aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = Np / 4;
   const int n_blocks = nb * (nb + 1) / 2;
@@ -238,16 +238,36 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
     __syncwarp();
     // ---- coalesced output row ---------------------------------------------------------------------
     float* orow = out + b * ld_out;
-    for (int i = lane; i < P; i += 32) orow[i] = O[i];
-    int o = P;
-    if (copy_dense && dense) {
-      for (int c = lane; c < D; c += 32) orow[o + c] = X[xoff(0, c >> 2, DS, swm) + (c & 3)];
-      o += D;
-    }
-    if (copy_sparse) {
-      for (int i = lane; i < Ns * D; i += 32) {
-        const int r = i / D, c = i - r * D;
-        orow[o + i] = X[xoff(r + doff, c >> 2, DS, swm) + (c & 3)];
+    int o = P + p_pad;   // layout: [P interactions | p_pad zeros | D dense | Ns*D sparse]
+    if (aligned) {
+      // rows, the dense block and the sparse block all start on 16-B boundaries: 128-bit stores throughout
+      if (lane < p_pad) O[P + lane] = 0.f;
+      __syncwarp();
+      for (int i = lane; i < (o >> 2); i += 32)
+        st_stream_f4(orow + i * 4, *reinterpret_cast<const float4*>(O + i * 4));
+      if (copy_dense && dense) {
+        for (int c4 = lane; c4 < D4; c4 += 32)
+          st_stream_f4(orow + o + c4 * 4, *reinterpret_cast<const float4*>(X + xoff(0, c4, DS, swm)));
+        o += D;
+      }
+      if (copy_sparse) {
+        for (int i = lane; i < Ns * D4; i += 32) {
+          const int r = i / D4, c4 = i - r * D4;
+          st_stream_f4(orow + o + i * 4, *reinterpret_cast<const float4*>(X + xoff(r + doff, c4, DS, swm)));
+        }
+      }
+    } else {
+      for (int i = lane; i < P; i += 32) orow[i] = O[i];
+      for (int i = lane; i < p_pad; i += 32) orow[P + i] = 0.f;
+      if (copy_dense && dense) {
+        for (int c = lane; c < D; c += 32) orow[o + c] = X[xoff(0, c >> 2, DS, swm) + (c & 3)];
+        o += D;
+      }
+      if (copy_sparse) {
+        for (int i = lane; i < Ns * D; i += 32) {
+          const int r = i / D, c = i - r * D;
+          orow[o + i] = X[xoff(r + doff, c >> 2, DS, swm) + (c & 3)];
+        }
       }
     }
     __syncwarp();
@@ -259,8 +279,9 @@ template <int DT>
 __global__ void __launch_bounds__(kIWarps * 32)
 dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
                         int64_t ld_sparse, const float* __restrict__ d_out, int64_t ld_dout, int64_t B,
-                        int Ns, int D_rt, int copy_dense, int copy_sparse, float* __restrict__ d_dense,
-                        int64_t ld_ddense, float* __restrict__ d_sparse, int64_t ld_dsparse) {
+                        int Ns, int D_rt, int copy_dense, int copy_sparse, int p_pad, int aligned,
+                        float* __restrict__ d_dense, int64_t ld_ddense, float* __restrict__ d_sparse,
+                        int64_t ld_dsparse) {
   extern __shared__ __align__(16) float smem[];
   const int D = DT ? DT : D_rt;
   const int N = Ns + (dense != nullptr);
@@ -328,15 +349,23 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
         float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         if (dense && i == 0) {
           if (copy_dense) {
-            const float* gp = go + P + c4 * 4;
-            v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
+            const float* gp = go + P + p_pad + c4 * 4;
+            if (aligned) {
+              v = f4_add(v, ld_row_f4(gp));
+            } else {
+              v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
+            }
           }
           *reinterpret_cast<float4*>(d_dense + b * ld_ddense + c4 * 4) = v;
         } else {
           const int r_s = i - doff;
           if (copy_sparse) {
-            const float* gp = go + P + ((copy_dense && dense) ? D : 0) + r_s * D + c4 * 4;
-            v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
+            const float* gp = go + P + p_pad + ((copy_dense && dense) ? D : 0) + r_s * D + c4 * 4;
+            if (aligned) {
+              v = f4_add(v, ld_row_f4(gp));
+            } else {
+              v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
+            }
           }
           *reinterpret_cast<float4*>(d_sparse + b * ld_dsparse + (int64_t)r_s * D + c4 * 4) = v;
         }
@@ -430,7 +459,8 @@ static int interact_check(const char* who, const float* dense, int64_t ld_dense,
 
 extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const float* sparse,
                                     int64_t ld_sparse, int64_t B, int32_t Ns, int32_t D, int32_t copy_dense,
-                                    int32_t copy_sparse, float* out, int64_t ld_out, tzk_stream_t stream) {
+                                    int32_t copy_sparse, int32_t p_pad, float* out, int64_t ld_out,
+                                    tzk_stream_t stream) {
   int rc = interact_check("dot_interact_fwd", dense, ld_dense, sparse, ld_sparse, B, Ns, D);
   if (rc) return rc;
   if (B == 0) return 0;
@@ -438,14 +468,16 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
+  TZK_REQUIRE(p_pad >= 0 && p_pad < 4, "dot_interact_fwd: p_pad must be in [0,3]");
+  const int aligned = (((P + p_pad) % 4) == 0) && (ld_out % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const int nb = Np / 4, n_blocks = nb * (nb + 1) / 2;
-  size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3) & ~3))) * sizeof(float);
+  size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3 + 4) & ~3))) * sizeof(float);
 #define TZK_IFWD(DT_)                                                                                         \
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
       cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     dot_interact_fwd_kernel<DT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>( \
-        dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, out, ld_out);                 \
+        dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, p_pad, aligned, out, ld_out); \
   } while (0)
   switch (D) {
     case 8: TZK_IFWD(8); break;
@@ -461,7 +493,7 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
 
 extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const float* sparse,
                                     int64_t ld_sparse, const float* d_out, int64_t ld_dout, int64_t B,
-                                    int32_t Ns, int32_t D, int32_t copy_dense, int32_t copy_sparse,
+                                    int32_t Ns, int32_t D, int32_t copy_dense, int32_t copy_sparse, int32_t p_pad,
                                     float* d_dense, int64_t ld_ddense, float* d_sparse, int64_t ld_dsparse,
                                     tzk_stream_t stream) {
   int rc = interact_check("dot_interact_bwd", dense, ld_dense, sparse, ld_sparse, B, Ns, D);
@@ -474,14 +506,16 @@ extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const 
   const int N = Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
+  TZK_REQUIRE(p_pad >= 0 && p_pad < 4, "dot_interact_bwd: p_pad must be in [0,3]");
+  const int aligned = (((P + p_pad) % 4) == 0) && (ld_dout % 4 == 0) && ((uintptr_t)d_out % 16 == 0);
   size_t smem = ((size_t)((P + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + Np * (Np + 8))) * sizeof(float);
 #define TZK_IBWD(DT_)                                                                                         \
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
       cudaFuncSetAttribute(dot_interact_bwd_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     dot_interact_bwd_kernel<DT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>( \
-        dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, Ns, D, copy_dense, copy_sparse, d_dense, ld_ddense, \
-        d_sparse, ld_dsparse);                                                                               \
+        dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, Ns, D, copy_dense, copy_sparse, p_pad, aligned,     \
+        d_dense, ld_ddense, d_sparse, ld_dsparse);                                                                               \
   } while (0)
   switch (D) {
     case 8: TZK_IBWD(8); break;
@@ -492,5 +526,94 @@ extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const 
   }
 #undef TZK_IBWD
   TZK_CHECK_LAUNCH("dot_interact_bwd_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Dense-tower helpers (caller-side of the hot path: tzrec/modules/mlp.py Perceptron = Linear -> ReLU).
+// The GEMMs are library calls (dense_gemm.py); these two kernels fuse what PyTorch runs as four separate
+// passes around them: bias add + ReLU, and ReLU backward + bias gradient (column sum).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(kThreads)
+bias_act_kernel(float* __restrict__ y, int64_t ld, const float* __restrict__ bias, int64_t M, int N, int relu) {
+  const int64_t n = M * N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / N;
+    const int c = (int)(i - r * N);
+    float v = y[r * ld + c] + (bias ? __ldg(bias + c) : 0.f);
+    if (relu) v = v > 0.f ? v : 0.f;
+    y[r * ld + c] = v;
+  }
+}
+
+constexpr int kSlabRows = 512;
+// N divides 256: thread (tid / N, tid % N) walks its rows of the slab; fixed-order reduction over row groups
+__global__ void __launch_bounds__(kThreads)
+act_bwd_colsum_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y, int64_t ld_y,
+                      int64_t M, int N, int relu, float* __restrict__ dz, int64_t ld_dz,
+                      float* __restrict__ partial) {
+  __shared__ float red[kThreads];
+  const int rg = kThreads / N;           // row groups per pass
+  const int c = threadIdx.x % N, r0 = threadIdx.x / N;
+  const int64_t row_lo = (int64_t)blockIdx.x * kSlabRows;
+  const int64_t row_hi = row_lo + kSlabRows < M ? row_lo + kSlabRows : M;
+  float acc = 0.f;
+  for (int64_t r = row_lo + r0; r < row_hi; r += rg) {
+    float g = __ldg(dy + r * ld_dy + c);
+    if (relu && !(__ldg(y + r * ld_y + c) > 0.f)) g = 0.f;
+    if (dz) dz[r * ld_dz + c] = g;
+    acc += g;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (r0 == 0) {
+    float s = 0.f;
+    for (int k = 0; k < rg; ++k) s += red[k * N + c];
+    partial[(int64_t)blockIdx.x * N + c] = s;
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t n_blocks, int N,
+                                    float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int64_t b = 0; b < n_blocks; ++b) s += partial[b * N + c];   // fixed order: deterministic
+  out[c] = s;
+}
+}  // namespace
+
+extern "C" int tzk_bias_act(float* y, int64_t ld_y, const float* bias, int64_t M, int32_t N, int32_t relu,
+                            tzk_stream_t stream) {
+  TZK_REQUIRE(M >= 0 && N >= 1, "bias_act: bad sizes");
+  if (M == 0) return 0;
+  TZK_REQUIRE(y != nullptr, "bias_act: y is NULL");
+  bias_act_kernel<<<grid_for(M * N, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(y, ld_y, bias,
+                                                                                                  M, N, relu);
+  TZK_CHECK_LAUNCH("bias_act_kernel");
+  return 0;
+}
+
+extern "C" size_t tzk_act_bwd_colsum_workspace_bytes(int64_t M, int32_t N) {
+  return (size_t)ceil_div64(M < 1 ? 1 : M, kSlabRows) * (size_t)(N < 1 ? 1 : N) * sizeof(float);
+}
+
+extern "C" int tzk_act_bwd_colsum(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int64_t M,
+                                  int32_t N, int32_t relu, float* dz, int64_t ld_dz, float* colsum,
+                                  void* workspace, size_t workspace_bytes, tzk_stream_t stream) {
+  TZK_REQUIRE(M >= 1 && N >= 1, "act_bwd_colsum: bad sizes");
+  TZK_REQUIRE(N <= kThreads && kThreads % N == 0, "act_bwd_colsum: N=%d must divide %d", N, kThreads);
+  TZK_REQUIRE(dy && colsum && (!relu || y), "act_bwd_colsum: NULL argument");
+  TZK_REQUIRE(workspace && workspace_bytes >= tzk_act_bwd_colsum_workspace_bytes(M, N),
+              "act_bwd_colsum: workspace too small");
+  const int64_t nb = ceil_div64(M, kSlabRows);
+  float* partial = static_cast<float*>(workspace);
+  act_bwd_colsum_kernel<<<(unsigned)nb, kThreads, 0, as_stream(stream)>>>(dy, ld_dy, y, ld_y, M, N, relu, dz, ld_dz,
+                                                                          partial);
+  TZK_CHECK_LAUNCH("act_bwd_colsum_kernel");
+  colsum_final_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(partial, nb, N, colsum);
+  TZK_CHECK_LAUNCH("colsum_final_kernel");
   return 0;
 }

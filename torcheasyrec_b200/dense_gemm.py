@@ -77,39 +77,58 @@ def _mm(a: torch.Tensor, ta: bool, b: torch.Tensor, tb: bool, M: int, N: int, K:
 
 
 class _LinearFn(torch.autograd.Function):
-    """y = x @ W^T + b.  `x` may carry zero columns beyond W's in_features (width rounded up to a multiple of 4 by
-    the producer): 16-B aligned rows are what lets cuBLASLt pick the tensor-core (BF16x9) kernels instead of the
-    align1 SIMT ones — e.g. DLRM's 783-wide final-MLP input travels as [B, 784]."""
+    """y = act(x @ W^T + b), act = ReLU or identity (tzrec/modules/mlp.py Perceptron).  GEMMs: cuBLASLt BF16x9;
+    bias+ReLU and ReLU-backward+bias-gradient are one tzk kernel each instead of four ATen passes.
+    `x` may carry zero columns beyond W's in_features (width rounded up to a multiple of 4 by the producer):
+    16-B aligned rows are what lets cuBLASLt pick the tensor-core kernels instead of the align1 SIMT ones —
+    e.g. DLRM's 783-wide final-MLP input travels as [B, 784]."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, relu, in_map):
+        from .kernels import default_kernels
+
         K, Kx = weight.shape[1], x.shape[1]
         w = weight
         if Kx != K:      # zero-padded input: pad the weight the same way (N x Kx, a few hundred KB)
             w = torch.zeros((weight.shape[0], Kx), dtype=weight.dtype, device=weight.device)
-            w[:, :K].copy_(weight)
-        ctx.save_for_backward(x, w)
-        ctx.has_bias = bias is not None
-        ctx.K = K
+            for (src, dst, n) in (in_map or ((0, 0, K),)):
+                w[:, dst:dst + n].copy_(weight[:, src:src + n])
+        ctx.in_map = in_map
         y = _mm(x, False, w, True, x.shape[0], w.shape[0], Kx)
-        if bias is not None:
-            y.add_(bias)
+        if bias is not None or relu:
+            default_kernels().bias_act(y, bias, relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.has_bias, ctx.relu, ctx.K = bias is not None, relu, K
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
-        dy = dy.contiguous()
+        from .kernels import default_kernels
+
+        x, w, y = ctx.saved_tensors
+        dy = dy if (dy.stride(1) == 1 and dy.stride(0) >= dy.shape[1]) else dy.contiguous()
+        N = w.shape[0]
         dx = dw = db = None
+        fused = (256 % N == 0) and (ctx.has_bias or ctx.relu)
+        if fused:       # dz = dy * (y > 0) and db = sum_rows(dz) in one pass
+            dz, colsum = default_kernels().act_bwd_colsum(dy, y, ctx.relu, want_dz=ctx.relu)
+            if not ctx.relu:
+                dz = dy.contiguous()
+            db = colsum if ctx.has_bias else None
+        else:
+            dz = dy * (y > 0) if ctx.relu else dy.contiguous()
+            db = dz.sum(0) if ctx.has_bias else None
         if ctx.needs_input_grad[0]:
-            dx = _mm(dy, False, w, False, dy.shape[0], w.shape[1], w.shape[0])
+            dx = _mm(dz, False, w, False, dz.shape[0], w.shape[1], N)
         if ctx.needs_input_grad[1]:
-            dw = _mm(dy, True, x, False, w.shape[0], w.shape[1], dy.shape[0])
+            dw = _mm(dz, True, x, False, N, w.shape[1], dz.shape[0])
             if w.shape[1] != ctx.K:
-                dw = dw[:, :ctx.K].contiguous()
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(0)
-        return dx, dw, db
+                segs = ctx.in_map or ((0, 0, ctx.K),)
+                dw = torch.cat([dw[:, dst:dst + n] for (_, dst, n) in segs], dim=1) if len(segs) > 1 \
+                    else dw[:, :ctx.K].contiguous()
+        if not ctx.needs_input_grad[2]:
+            db = None
+        return dx, dw, db, None, None
 
 
 def padded_width(n: int) -> int:
@@ -122,17 +141,22 @@ def _usable(x: torch.Tensor, weight: torch.Tensor) -> bool:
             and not torch.backends.cuda.matmul.allow_tf32 and available())
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """F.linear; accepts `x` zero-padded to padded_width(in_features) columns."""
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
+           in_map=None) -> torch.Tensor:
+    """act(F.linear(x, weight, bias)).  `x` may be wider than in_features: zero-padded at the end (width =
+    padded_width(in_features)) or, with `in_map` = ((src_col, dst_col, n), ...), with zero columns in between —
+    column src of the weight multiplies column dst of x."""
     K = weight.shape[1]
-    if x.dim() == 2 and x.shape[1] != K:
-        if x.shape[1] != padded_width(K):
+    if x.dim() == 2 and (x.shape[1] != K or in_map is not None):
+        if in_map is None and x.shape[1] != padded_width(K):
             raise RuntimeError(f"linear: input width {x.shape[1]} does not match in_features {K}")
-        if not _usable(x, weight):
-            x = x[:, :K]
+        if not _usable(x, weight):       # fallback: drop the padding columns
+            x = x[:, :K] if in_map is None else torch.cat([x[:, d:d + n] for (_, d, n) in in_map], dim=1)
+            in_map = None
     if _usable(x, weight):
-        return _LinearFn.apply(x, weight, bias)
-    return torch.nn.functional.linear(x, weight, bias)
+        return _LinearFn.apply(x, weight, bias, relu, in_map)
+    y = torch.nn.functional.linear(x, weight, bias)
+    return torch.relu(y) if relu else y
 
 
 class Linear(nn.Linear):

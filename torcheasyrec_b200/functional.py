@@ -212,19 +212,19 @@ def factorization_machine(feature: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------ A9/A10
 class _DotInteract(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dense, sparse, Ns, D, copy_dense, copy_sparse, pad_to=1):
+    def forward(ctx, dense, sparse, Ns, D, copy_dense, copy_sparse, pad_to=1, p_pad=0):
         dense_c = None if dense is None else _rows_contig(dense)
         sparse_c = _rows_contig(sparse)
         ctx.save_for_backward(dense_c, sparse_c)
-        ctx.cfg = (Ns, D, copy_dense, copy_sparse)
-        return backend().dot_interact_fwd(dense_c, sparse_c, Ns, D, copy_dense, copy_sparse, pad_to)
+        ctx.cfg = (Ns, D, copy_dense, copy_sparse, p_pad)
+        return backend().dot_interact_fwd(dense_c, sparse_c, Ns, D, copy_dense, copy_sparse, pad_to, p_pad)
 
     @staticmethod
     def backward(ctx, d_out):
         dense, sparse = ctx.saved_tensors
-        Ns, D, cd, cs = ctx.cfg
-        d_dense, d_sparse = backend().dot_interact_bwd(dense, sparse, _rows_contig(d_out), Ns, D, cd, cs)
-        return d_dense, d_sparse, None, None, None, None, None
+        Ns, D, cd, cs, p_pad = ctx.cfg
+        d_dense, d_sparse = backend().dot_interact_bwd(dense, sparse, _rows_contig(d_out), Ns, D, cd, cs, p_pad)
+        return d_dense, d_sparse, None, None, None, None, None, None
 
 
 def dot_interaction(features: torch.Tensor) -> torch.Tensor:
@@ -234,8 +234,19 @@ def dot_interaction(features: torch.Tensor) -> torch.Tensor:
 
 
 def dlrm_interaction(dense_feat: Optional[torch.Tensor], sparse_feat: torch.Tensor, num_sparse: int, dim: int,
-                     with_dense: bool = True, with_sparse: bool = True, pad_to: int = 1) -> torch.Tensor:
+                     with_dense: bool = True, with_sparse: bool = True, aligned: bool = False):
     """Fused DLRM.predict glue (tzrec/models/dlrm.py:113-131):
     cat([interaction(cat([dense[:,None,:], sparse.view(B,Ns,D)], 1)), dense, sparse], -1) in one pass.
-    pad_to=4 appends zero columns up to a multiple of 4 (aligned rows for the consuming GEMM)."""
-    return _DotInteract.apply(dense_feat, sparse_feat, num_sparse, dim, with_dense, with_sparse, pad_to)
+
+    aligned=False -> the reference's exact column layout [P | dense | sparse].
+    aligned=True  -> (tensor, in_map): zero columns are inserted after the P interaction terms and at the row end so
+    that every block and every row starts on a 16-B boundary; `in_map` = [(src_col, dst_col, length), ...] tells the
+    consuming Linear where the reference's columns live (dense_gemm.linear pads its weight accordingly)."""
+    if not aligned:
+        return _DotInteract.apply(dense_feat, sparse_feat, num_sparse, dim, with_dense, with_sparse, 1, 0)
+    n = num_sparse + (dense_feat is not None)
+    P = n * (n - 1) // 2
+    p_pad = (-P) % 4
+    rest = (dim if (with_dense and dense_feat is not None) else 0) + (num_sparse * dim if with_sparse else 0)
+    out = _DotInteract.apply(dense_feat, sparse_feat, num_sparse, dim, with_dense, with_sparse, 4, p_pad)
+    return out, ((0, 0, P), (P, P + p_pad, rest))

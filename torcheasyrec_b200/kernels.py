@@ -336,28 +336,28 @@ class CudaKernels:
 
     # ------------------------------------------------------------------ A9 / A10
     def dot_interact_fwd(self, dense: Optional[torch.Tensor], sparse: torch.Tensor, Ns: int, D: int,
-                         copy_dense: bool, copy_sparse: bool, pad_to: int = 1) -> torch.Tensor:
-        """pad_to > 1: the result is [B, ceil(width/pad_to)*pad_to] with zero columns at the end (16-B aligned
-        rows for the GEMM that consumes it)."""
+                         copy_dense: bool, copy_sparse: bool, pad_to: int = 1, p_pad: int = 0) -> torch.Tensor:
+        """Layout [P | p_pad zeros | dense D | sparse Ns*D | tail zeros up to a multiple of pad_to]."""
         sparse, ld_s = _rows2d(sparse, "sparse")
         B = sparse.shape[0]
         ld_d = 0
         if dense is not None:
             dense, ld_d = _rows2d(dense, "dense")
         N = Ns + (dense is not None)
-        width = N * (N - 1) // 2 + (D if (copy_dense and dense is not None) else 0) + (Ns * D if copy_sparse else 0)
+        width = N * (N - 1) // 2 + p_pad + (D if (copy_dense and dense is not None) else 0) + \
+            (Ns * D if copy_sparse else 0)
         wp = (width + pad_to - 1) // pad_to * pad_to
         out = torch.empty((B, wp), dtype=torch.float32, device=sparse.device)
         if wp != width:
             out[:, width:].zero_()
         check(self._lib.tzk_dot_interact_fwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, B, Ns, D, int(copy_dense),
-                                             int(copy_sparse), _ptr(out), wp, _stream()),
+                                             int(copy_sparse), p_pad, _ptr(out), wp, _stream()),
               "tzk_dot_interact_fwd")
         self.launches += 1
         return out
 
     def dot_interact_bwd(self, dense: Optional[torch.Tensor], sparse: torch.Tensor, d_out: torch.Tensor,
-                         Ns: int, D: int, copy_dense: bool, copy_sparse: bool):
+                         Ns: int, D: int, copy_dense: bool, copy_sparse: bool, p_pad: int = 0):
         sparse, ld_s = _rows2d(sparse, "sparse")
         d_out, ld_o = _rows2d(d_out, "d_out")
         B = sparse.shape[0]
@@ -368,10 +368,34 @@ class CudaKernels:
             d_dense = torch.empty((B, D), dtype=torch.float32, device=sparse.device)
         d_sparse = torch.empty((B, Ns * D), dtype=torch.float32, device=sparse.device)
         check(self._lib.tzk_dot_interact_bwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, _ptr(d_out), ld_o, B, Ns, D,
-                                             int(copy_dense), int(copy_sparse), _ptr(d_dense), D,
+                                             int(copy_dense), int(copy_sparse), p_pad, _ptr(d_dense), D,
                                              _ptr(d_sparse), Ns * D, _stream()), "tzk_dot_interact_bwd")
         self.launches += 1
         return d_dense, d_sparse
+
+
+    # ------------------------------------------------------------------ dense-tower helpers
+    def bias_act(self, y: torch.Tensor, bias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+        y, ld = _rows2d(y, "y")
+        check(self._lib.tzk_bias_act(_ptr(y), ld, _ptr(bias), y.shape[0], y.shape[1], int(relu), _stream()),
+              "tzk_bias_act")
+        self.launches += 1
+        return y
+
+    def act_bwd_colsum(self, dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, want_dz: bool = True):
+        dy, ld_dy = _rows2d(dy, "dy")
+        M, N = dy.shape
+        ld_y = 0
+        if y is not None:
+            y, ld_y = _rows2d(y, "y")
+        dz = torch.empty((M, N), dtype=torch.float32, device=dy.device) if want_dz else None
+        colsum = torch.empty(N, dtype=torch.float32, device=dy.device)
+        nb = self._lib.tzk_act_bwd_colsum_workspace_bytes(M, N)
+        ws = self._workspace("colsum", nb, dy.device)
+        check(self._lib.tzk_act_bwd_colsum(_ptr(dy), ld_dy, _ptr(y), ld_y, M, N, int(relu), _ptr(dz), N, _ptr(colsum),
+                                           _ptr(ws), ws.numel(), _stream()), "tzk_act_bwd_colsum")
+        self.launches += 2
+        return dz, colsum
 
 
 @dataclass
