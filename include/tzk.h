@@ -204,6 +204,26 @@ int tzk_act_bwd_colsum(const float* dy, int64_t ld_dy, const float* y, int64_t l
                        int32_t relu, float* dz, int64_t ld_dz, float* colsum, void* workspace,
                        size_t workspace_bytes, tzk_stream_t stream);
 
+/* ---- narrow fully-connected layers (K, N <= 64) and the BCE head — the layers either side of the interaction
+ * in every rank model (tzrec/modules/mlp.py:20-84; DLRM bottom MLP 13->64->16 and the 64->32->1 end of its final
+ * MLP, tzrec/models/dlrm.py:60-99; BCEWithLogitsLoss tzrec/models/rank_model.py:190-216).  One launch per layer
+ * forward, one (+ a fixed-order partial reduction) backward; fp32 FFMA in ascending-k order.
+ *   fwd : y[M,N]  = act(x[M,K] @ w[N,K]^T + bias)                      (bias nullable; relu 0/1)
+ *   bwd : dz = dy * (y > 0) (or dy if !relu);  dx[M,K] = dz @ w (dx nullable);  dw[N,K] = dz^T @ x;
+ *         db[N] = column sums of dz (db nullable).  Deterministic.
+ *   bce : loss[0] = mean_i( max(z,0) - z*t + log1p(exp(-|z|)) ),  dlogits[i] = (sigmoid(z_i) - t_i) / M
+ *         (dlogits nullable). */
+int tzk_small_linear_fwd(const float* x, int64_t ld_x, const float* w, const float* bias, int64_t M, int32_t K,
+                         int32_t N, int32_t relu, float* y, int64_t ld_y, tzk_stream_t stream);
+size_t tzk_small_linear_bwd_workspace_bytes(int64_t M, int32_t K, int32_t N);
+int tzk_small_linear_bwd(const float* x, int64_t ld_x, const float* w, const float* y, int64_t ld_y,
+                         const float* dy, int64_t ld_dy, int64_t M, int32_t K, int32_t N, int32_t relu, float* dx,
+                         int64_t ld_dx, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                         tzk_stream_t stream);
+size_t tzk_bce_logits_workspace_bytes(int64_t M);
+int tzk_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t M, float* loss, float* dlogits,
+                           void* workspace, size_t workspace_bytes, tzk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

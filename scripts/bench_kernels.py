@@ -1,6 +1,6 @@
 """Standalone timings of the sparse kernels at DLRM-Criteo shape (full hash sizes, B=65536), CUDA events.
 Usage: python scripts/bench_kernels.py            -> runs every variant in a subprocess and prints one JSON line each
-       TZK_RUN_UPDATE_KPOS=2 python scripts/bench_kernels.py one"""
+       TZK_BWD_TILE=0 python scripts/bench_kernels.py one   (general backward kernels instead of the tile path)"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -30,11 +30,16 @@ if len(sys.argv) > 1:
         torch.cuda.synchronize()
         ts = sorted(a.elapsed_time(b) for a, b in ev)
         return ts[len(ts) // 2] * 1e3
-    res = {"kpos": os.environ.get("TZK_RUN_UPDATE_KPOS", "1")}
+    res = {"bwd_tile": os.environ.get("TZK_BWD_TILE", "1"), "id_dist": os.environ.get("TZK_ID_DIST", "uniform")}
+    if res["id_dist"] == "zipf":       # Zipf(1.05)-like skew: hot ids repeat inside a batch
+        def zipf(h):
+            u = torch.rand(B, device=dev, generator=g)
+            return (torch.floor((h ** u) - 1).clamp_(0, h - 1)).to(torch.int64)
+        ids = [torch.cat([zipf(float(h)) for h in CRITEO_HASH_SIZES]) for _ in range(R)]
     res["gather_us"] = timeit(lambda i: k.pooled_gather_fwd(arena, lay, ids[i % R], offs, B, out))
     res["fused_bwd_us"] = timeit(lambda i: k.fused_bwd(OPT_ADAGRAD, True, grad, arena, state, lay, ids[i % R], offs, B, 1e-3, 1e-8, 1.0))
     print(json.dumps(res))
 else:
-    for kp in ("1", "2", "4"):
-        env = dict(os.environ, TZK_RUN_UPDATE_KPOS=kp)
+    for tile, dist in (("1", "uniform"), ("0", "uniform"), ("1", "zipf"), ("0", "zipf")):
+        env = dict(os.environ, TZK_BWD_TILE=tile, TZK_ID_DIST=dist)
         subprocess.run([sys.executable, __file__, "one"], env=env)

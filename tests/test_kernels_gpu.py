@@ -70,6 +70,10 @@ CASES = {
     "unaligned_dims": ([30, 70], [13, 6], [0, 1], 77, 4),
     "tiny_tables_long_runs": ([3, 4, 10], [16, 16, 16], [0, 1, 2], 2000, 2),
     "multi_hot_33": ([5000], [16], [0], 50, 33),
+    # tile path of the fused backward: runs that cross many tiles at the smallest (D=128 -> 32 positions) and the
+    # largest (D=4 -> 1024 positions) tile size, next to short runs
+    "long_runs_wide_rows": ([2, 300], [128, 128], [0, 1], 700, 2),
+    "long_runs_d4": ([3, 20000], [4, 4], [0, 1], 3000, 2),
 }
 
 
@@ -139,7 +143,7 @@ def test_fused_bwd(kernels, case, opt, pool):
     # Runs longer than 32 contributions are summed as 64 strided partials + a fixed tree (fbgemm's long-row
     # path is a tree too), the oracle adds sequentially: with ~700 cancelling terms per row both are ~1e-5
     # from the exact sum, and the accumulator s += g*g doubles the relative gap.  Weights stay within 1e-5.
-    long_runs = case == "tiny_tables_long_runs"
+    long_runs = case in ("tiny_tables_long_runs", "long_runs_wide_rows", "long_runs_d4")
     state_rtol = 3e-4 if long_runs else 2e-5
     w_rtol, w_atol = (5e-5, 5e-6) if long_runs else (1e-5, 1e-6)
     want = [t.copy() for t in tables]
@@ -424,3 +428,76 @@ def test_tower_helpers_bias_act_and_relu_bwd_colsum(kernels, N):
     np.testing.assert_allclose(colsum.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-4)
     _, cs2 = kernels.act_bwd_colsum(dy, None, False, want_dz=False)
     np.testing.assert_allclose(cs2.cpu().numpy(), dy.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(1, 13, 64, True), (127, 64, 16, True), (128, 64, 32, True),
+                                        (129, 32, 1, False), (1000, 3, 5, True), (4099, 64, 64, True),
+                                        (300, 17, 33, False), (2500, 40, 2, True)])
+def test_small_linear_fwd_bwd_vs_fp64_reference(kernels, M, K, N, relu):
+    """tzk_small_linear_{fwd,bwd} (the narrow tower layers) against a float64 restatement of
+    tzrec/modules/mlp.py Perceptron: Linear -> ReLU and its autograd."""
+    rng = np.random.default_rng(M * 7 + K * 3 + N)
+    wide = rng.standard_normal((M, K + 5)).astype(np.float32)     # x is a column slice of a wider buffer
+    x = cu(wide)[:, 2:2 + K]
+    w = rng.standard_normal((N, K)).astype(np.float32) / np.sqrt(K)
+    b = rng.standard_normal(N).astype(np.float32)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    x64, w64, b64, dy64 = wide[:, 2:2 + K].astype(np.float64), w.astype(np.float64), b.astype(np.float64), dy.astype(np.float64)
+    z = x64 @ w64.T + b64
+    y64 = np.maximum(z, 0) if relu else z
+    got = kernels.small_linear_fwd(x, cu(w), cu(b), relu)
+    np.testing.assert_allclose(got.cpu().numpy(), y64, rtol=1e-5, atol=1e-5)
+    dx, dw, db = kernels.small_linear_bwd(x, cu(w), got if relu else None, cu(dy), relu, True, True)
+    dz = dy64 * (got.cpu().numpy() > 0) if relu else dy64
+    np.testing.assert_allclose(dx.cpu().numpy(), dz @ w64, rtol=1e-5, atol=1e-5)
+    scale = np.sqrt(M)
+    np.testing.assert_allclose(dw.cpu().numpy(), dz.T @ x64, rtol=2e-5, atol=2e-5 * scale)
+    np.testing.assert_allclose(db.cpu().numpy(), dz.sum(0), rtol=2e-5, atol=2e-5 * scale)
+    # no-bias / no-dx variant and run-to-run determinism of the partial reduction
+    y2 = kernels.small_linear_fwd(x, cu(w), None, relu)
+    np.testing.assert_allclose(y2.cpu().numpy(), np.maximum(x64 @ w64.T, 0) if relu else x64 @ w64.T, rtol=1e-5, atol=1e-5)
+    dx2, dw2, db2 = kernels.small_linear_bwd(x, cu(w), got if relu else None, cu(dy), relu, False, False)
+    assert dx2 is None and db2 is None
+    assert torch.equal(dw2, dw)
+
+
+@pytest.mark.parametrize("M", [1, 5, 1023, 1024, 1025, 65536 + 3])
+def test_bce_logits_fwd_bwd_matches_torch(kernels, M):
+    torch.manual_seed(M)
+    z = (torch.randn(M, device=DEV) * 6).requires_grad_(True)
+    z.data[:min(M, 3)] = torch.tensor([40.0, -40.0, 0.0], device=DEV)[:min(M, 3)]
+    t = (torch.rand(M, device=DEV) < 0.3).float()
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(z.double(), t.double())
+    (gref,) = torch.autograd.grad(ref, z)
+    loss, dz = kernels.bce_logits_fwd_bwd(z.detach(), t)
+    np.testing.assert_allclose(float(loss), float(ref), rtol=1e-6)
+    np.testing.assert_allclose(dz.cpu().numpy(), gref.float().cpu().numpy(), rtol=1e-5, atol=1e-9)
+
+
+def test_linear_dispatch_and_bce_autograd_match_torch():
+    """dense_gemm.linear / bce_with_logits (what the model shells call) against torch autograd, fp32."""
+    from torcheasyrec_b200 import dense_gemm as G
+
+    torch.manual_seed(5)
+    B = 777
+    x = torch.randn(B, 13, device=DEV)
+    l1, l2, l3 = torch.nn.Linear(13, 64).to(DEV), torch.nn.Linear(64, 16).to(DEV), torch.nn.Linear(16, 1).to(DEV)
+    t = (torch.rand(B, device=DEV) < 0.4).float()
+
+    def run(fused):
+        for m in (l1, l2, l3):
+            m.zero_grad()
+        if fused:
+            h = G.linear(G.linear(x, l1.weight, l1.bias, relu=True), l2.weight, l2.bias, relu=True)
+            loss = G.bce_with_logits(G.linear(h, l3.weight, l3.bias).squeeze(1), t)
+        else:
+            h = torch.relu(l2(torch.relu(l1(x))))
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(l3(h).squeeze(1), t)
+        loss.backward()
+        return float(loss), [p.grad.clone() for m in (l1, l2, l3) for p in m.parameters()]
+
+    la, ga = run(True)
+    lb, gb = run(False)
+    assert abs(la - lb) <= 1e-6 * max(1.0, abs(lb))
+    for a, b in zip(ga, gb):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-5, atol=1e-6)

@@ -51,6 +51,14 @@ SIGNATURES = {
     "tzk_bias_act": (c_int32, [P, c_int64, P, c_int64, c_int32, c_int32, P]),
     "tzk_act_bwd_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "tzk_act_bwd_colsum": (c_int32, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, c_int64, P, P, c_size_t, P]),
+    "tzk_small_linear_fwd": (c_int32, [P, c_int64, P, P, c_int64, c_int32, c_int32, c_int32, P, c_int64, P]),
+    "tzk_small_linear_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "tzk_small_linear_bwd": (
+        c_int32,
+        [P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_int64, P, P, P, c_size_t, P],
+    ),
+    "tzk_bce_logits_workspace_bytes": (c_size_t, [c_int64]),
+    "tzk_bce_logits_fwd_bwd": (c_int32, [P, P, c_int64, P, P, P, c_size_t, P]),
     "tzk_dot_interact_bwd": (
         c_int32,
         [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, P, c_int64, P,

@@ -606,6 +606,194 @@ long_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int
   }
 }
 
+// ---- 3'. tile path: rows of <= 128 floats, 16-B aligned (vec4, one chunk per lane) -------------------------
+// The sorted positions are cut into tiles of TP = 4096 / ROWF positions (ROWF = 4*G floats per padded row), one CTA
+// per tile:
+//   A. keys (+ both neighbours) and vals of the tile -> shared memory (coalesced);
+//   B. every lane group loads the gradient rows of its U = 4 positions (independent 16-B loads, scaled) into a
+//      shared-memory tile AND, for positions that head a run which lives entirely inside the tile, the weight and
+//      state rows — so all global requests of a tile are in flight together instead of one dependent chain per run;
+//   C. run heads add their run up from shared memory in sorted (= ascending bag) order and apply ONE update.
+// A run that crosses a tile border leaves its partial sum in carry_first[t] (run entered from the left and ends
+// here) or carry_last[t] (run leaves to the right; a tile that is one single key from border to border counts as
+// "leaves to the right"); carry_combine_kernel adds the partials of such a run in tile order and updates the row.
+// No atomics, summation order fixed by the sort -> run-to-run deterministic.
+template <int G>
+struct TileCfg {
+  static constexpr int ROWF = G * 4;
+  static constexpr int TP = 4096 / ROWF;
+  static constexpr int NG = kThreads / G;
+  static constexpr int U = TP / NG;  // = 4 for every G
+};
+
+inline int64_t tile_carry_floats(int64_t n, int rowf) {  // per carry array
+  const int tp = 4096 / rowf;
+  return ((n + tp - 1) / tp + 1) * rowf;
+}
+
+template <typename KeyT, int G>
+__global__ void __launch_bounds__(kThreads)
+tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
+                   const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
+                   const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                   const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
+                   float* __restrict__ carry_first, float* __restrict__ carry_last) {
+  using C = TileCfg<G>;
+  constexpr int ROWF = C::ROWF, TP = C::TP, NG = C::NG, U = C::U;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* rows = reinterpret_cast<float*>(smem_raw);                      // [TP][ROWF]
+  KeyT* sk = reinterpret_cast<KeyT*>(rows + TP * ROWF);                   // [TP + 2]: left nb, tile, right nb
+  int32_t* sv = reinterpret_cast<int32_t*>(sk + (TP + 2));                // [TP]
+  BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw + align16((size_t)TP * ROWF * 4 + (TP + 2) * sizeof(KeyT) + TP * 4));
+  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+
+  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+  const int c = lane * 4;
+  const KeyT sentinel = (KeyT)a.sentinel;
+  const int64_t n_tiles = (a.n + TP - 1) / TP;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t base = t * TP;
+    const int cnt = (int)((a.n - base) < TP ? (a.n - base) : TP);
+    // ---- A ---------------------------------------------------------------------------------------
+    for (int i = threadIdx.x; i < cnt + 2; i += kThreads) {
+      const int64_t p = base + i - 1;
+      sk[i] = (p >= 0 && p < a.n) ? keys[p] : sentinel;
+    }
+    for (int i = threadIdx.x; i < cnt; i += kThreads) sv[i] = vals[base + i];
+    __syncthreads();
+    const KeyT k_first = sk[1], k_last = sk[cnt];
+    const bool first_cont = (t > 0) && sk[0] == k_first;
+    const bool last_cont = (base + cnt < a.n) && sk[cnt + 1] == k_last;
+    // ---- B ---------------------------------------------------------------------------------------
+    float4 w4[U], s4[U];
+    int kind[U], fx[U];  // kind: 0 none, 1 -> carry_first, 2 -> carry_last, 3 -> update here
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = grp + NG * u;
+      kind[u] = 0;
+      fx[u] = 0;
+      w4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s4[u] = w4[u];
+      if (i >= cnt) continue;
+      const KeyT key = sk[i + 1];
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (key != sentinel) {
+        const int32_t v = sv[i];
+        const int f = a.pooled ? v / a.B : feat_of_key<KeyT>(fd, a.F, key);
+        fx[u] = f;
+        const int dim = fd[f].dim;
+        const Entry en = entry_of(a, fd, v, f);
+        if (c < dim) g = f4_scale(ld_row_f4(en.g + c), en.scale);
+        if (i == 0 || sk[i] != key) {
+          const bool cl = (i == 0) && first_cont;
+          const bool cr = (key == k_last) && last_cont;
+          kind[u] = cr ? 2 : (cl ? 1 : 3);
+          if (kind[u] == 3 && c < dim) {
+            const int64_t off = fd[f].w_off + ((int64_t)key - fd[f].key_base) * dim + c;
+            w4[u] = *reinterpret_cast<const float4*>(a.weights + off);
+            if (a.optimizer == TZK_OPT_ADAGRAD) s4[u] = *reinterpret_cast<const float4*>(a.state + off);
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(rows + i * ROWF + c) = g;
+    }
+    __syncthreads();
+    // ---- C ---------------------------------------------------------------------------------------
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (kind[u] == 0) continue;
+      const int i = grp + NG * u;
+      const KeyT key = sk[i + 1];
+      float4 acc = *reinterpret_cast<const float4*>(rows + i * ROWF + c);
+      for (int j = i + 1; j < cnt && sk[j + 1] == key; ++j)
+        acc = f4_add(acc, *reinterpret_cast<const float4*>(rows + j * ROWF + c));
+      if (kind[u] == 1) {
+        *reinterpret_cast<float4*>(carry_first + t * ROWF + c) = acc;
+      } else if (kind[u] == 2) {
+        *reinterpret_cast<float4*>(carry_last + t * ROWF + c) = acc;
+      } else {
+        const BwdFeat& d = fd[fx[u]];
+        float g[4] = {acc.x, acc.y, acc.z, acc.w};
+        float rw_denom = 1.f;
+        if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {  // lanes beyond the row hold zeros
+          float ss = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3];
+          ss = group_sum<G>(ss);
+          float sr = 0.f;
+          if (lane == 0) {
+            sr = a.state[key] + ss / (float)d.dim;
+            a.state[key] = sr;
+          }
+          sr = __shfl_sync(group_mask<G>(), sr, 0, G);
+          rw_denom = sqrtf(sr) + a.eps;
+        }
+        if (c < d.dim) {
+          float w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+          float s[4] = {s4[u].x, s4[u].y, s4[u].z, s4[u].w};
+          apply_update<4>(a, w, s, g, rw_denom);
+          const int64_t off = d.w_off + ((int64_t)key - d.key_base) * d.dim + c;
+          *reinterpret_cast<float4*>(a.weights + off) = make_float4(w[0], w[1], w[2], w[3]);
+          if (a.optimizer == TZK_OPT_ADAGRAD)
+            *reinterpret_cast<float4*>(a.state + off) = make_float4(s[0], s[1], s[2], s[3]);
+        }
+      }
+    }
+    __syncthreads();  // the next tile overwrites sk / sv / rows
+  }
+}
+
+// one lane group per tile border: if a run crosses it and STARTS in the tile left of it, add the run's per-tile
+// partials in tile order (carry_last[t], carry_last of every tile the key fills completely, carry_first of the
+// tile it ends in) and update the row.
+template <typename KeyT, int G>
+__global__ void __launch_bounds__(kThreads)
+carry_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
+                     const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
+                     const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                     const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
+                     const float* __restrict__ carry_first, const float* __restrict__ carry_last) {
+  using C = TileCfg<G>;
+  constexpr int ROWF = C::ROWF, TP = C::TP, NG = C::NG;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
+  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  const int lane = threadIdx.x % G;
+  const int c = lane * 4;
+  const KeyT sentinel = (KeyT)a.sentinel;
+  const int64_t n_tiles = (a.n + TP - 1) / TP;
+  for (int64_t t = (int64_t)blockIdx.x * NG + threadIdx.x / G; t + 1 < n_tiles; t += (int64_t)gridDim.x * NG) {
+    const int64_t pe = (t + 1) * TP;  // first position of tile t+1 (< n)
+    const KeyT k0 = keys[pe - 1];
+    if (keys[pe] != k0 || k0 == sentinel) continue;
+    const int64_t ps = t * TP;
+    if (t > 0 && keys[ps] == k0 && keys[ps - 1] == k0) continue;  // the run started further left
+    // end of the run: gallop over tiles, then binary search
+    int64_t lo = pe, step = TP, hi = lo + step;
+    while (hi < a.n && keys[hi] == k0) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > a.n) hi = a.n;
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] == k0) lo = mid; else hi = mid;
+    }
+    const int64_t te = (hi - 1) / TP;  // tile holding the run's last position (> t)
+    float4 acc = *reinterpret_cast<const float4*>(carry_last + t * ROWF + c);
+    int64_t tt = t + 1;
+    for (; tt + 4 <= te; tt += 4) {
+      float4 r[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] = *reinterpret_cast<const float4*>(carry_last + (tt + q) * ROWF + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc = f4_add(acc, r[q]);
+    }
+    for (; tt < te; ++tt) acc = f4_add(acc, *reinterpret_cast<const float4*>(carry_last + tt * ROWF + c));
+    acc = f4_add(acc, *reinterpret_cast<const float4*>(carry_first + te * ROWF + c));
+    const int32_t v0 = vals[pe - 1];
+    const int f0 = a.pooled ? v0 / a.B : feat_of_key<KeyT>(fd, a.F, k0);
+    const BwdFeat d = fd[f0];
+    float accv[1][4] = {{acc.x, acc.y, acc.z, acc.w}};
+    finish_run<G, 4, 1>(a, d, (int64_t)k0 - d.key_base, (int64_t)k0, accv, lane);
+  }
+}
+
 __global__ void zero_counters(int32_t* c) { c[0] = 0; c[1] = 0; c[2] = 0; }
 
 inline int bits_for(int64_t total_keys) {
@@ -615,8 +803,8 @@ inline int bits_for(int64_t total_keys) {
 }
 
 struct WsLayout {
-  size_t keys_in, keys_out, vals_in, vals_out, items, runs, counters, partials, cub_tmp, total;
-  size_t cub_bytes;
+  size_t keys_in, keys_out, vals_in, vals_out, items, runs, counters, partials, carry, cub_tmp, total;
+  size_t cub_bytes, carry_floats;
 };
 
 template <typename KeyT>
@@ -643,6 +831,12 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
   L.counters = o; o = align_up(o + 256, 256);
   const size_t rowf = (size_t)((max_dim + 127) / 128 * 128 < 128 ? 128 : (max_dim + 127) / 128 * 128) * 4;
   L.partials = o; o = align_up(o + max_pslots(n) * rowf * sizeof(float), 256);
+  {  // tile path (dims <= 128): carry_first | carry_last
+    int g = 1;
+    while (g * 4 < max_dim && g < 32) g <<= 1;
+    L.carry_floats = (size_t)tile_carry_floats(n, g * 4);
+    L.carry = o; o = align_up(o + 2 * L.carry_floats * sizeof(float), 256);
+  }
   size_t tb = 0;
   const int bits = bits_for(total_keys + 1);
   if (k64) cub_sort<uint64_t>(nullptr, tb, nullptr, nullptr, nullptr, nullptr, n, bits, 0);
@@ -740,7 +934,6 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
   const int bits = bits_for(total_keys + 1);   // one spare value above the largest key = padding sentinel
   const uint64_t sentinel = ((uint64_t)1 << bits) - 1;
 
-  zero_counters<<<1, 1, 0, st>>>(wl.counters);
   const int64_t n_bags = (int64_t)F * B;
   int grid_lin = (int)std::min<int64_t>(ceil_div64(n_bags, kThreads), kSmCountB200 * 16);
   size_t cub_bytes = L.cub_bytes;
@@ -794,7 +987,57 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
     return (v == 2 || v == 4) ? v : 1;
   }();
 
-  // CH is compiled for 1 (D <= 128 aligned), 2 and 8
+  static const bool tile_path = [] {   // TZK_BWD_TILE=0 keeps the general kernels (A/B timing, debugging)
+    const char* e = getenv("TZK_BWD_TILE");
+    return !(e && e[0] == '0');
+  }();
+  if (vec == 4 && ch == 1 && tile_path) {
+    // tile path: every gradient / weight / state row of a tile is requested at once, runs are reduced in shared memory
+    float* carry_first = reinterpret_cast<float*>(ws + L.carry);
+    float* carry_last = carry_first + L.carry_floats;
+#define TZK_TILE_LAUNCH(KeyT, G_)                                                                               \
+  do {                                                                                                          \
+    using C = TileCfg<G_>;                                                                                      \
+    const int64_t n_tiles = ceil_div64(nnz, C::TP);                                                             \
+    const size_t smem_t = align16((size_t)C::TP * C::ROWF * 4 + (C::TP + 2) * sizeof(KeyT) + C::TP * 4) +       \
+                          (size_t)F * sizeof(BwdFeat);                                                          \
+    if (smem_t > 48 * 1024)                                                                                     \
+      cudaFuncSetAttribute(tile_update_kernel<KeyT, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                           (int)smem_t);                                                                        \
+    const int grid_t = (int)std::min<int64_t>(n_tiles, kSmCountB200 * 8);                                       \
+    tile_update_kernel<KeyT, G_><<<grid_t, kThreads, smem_t, st>>>(                                             \
+        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, vals_out, \
+        carry_first, carry_last);                                                                               \
+    TZK_CHECK_LAUNCH("tile_update_kernel");                                                                     \
+    if (n_tiles > 1) {                                                                                          \
+      const size_t smem_c = (size_t)F * sizeof(BwdFeat);                                                        \
+      if (smem_c > 48 * 1024)                                                                                   \
+        cudaFuncSetAttribute(carry_combine_kernel<KeyT, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                             (int)smem_c);                                                                      \
+      const int grid_c = (int)std::min<int64_t>(ceil_div64(n_tiles - 1, C::NG), kSmCountB200 * 8);              \
+      carry_combine_kernel<KeyT, G_><<<grid_c, kThreads, smem_c, st>>>(                                         \
+          a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out,        \
+          vals_out, carry_first, carry_last);                                                                   \
+      TZK_CHECK_LAUNCH("carry_combine_kernel");                                                                 \
+    }                                                                                                           \
+  } while (0)
+#define TZK_TILE_DISPATCH(KeyT)                      \
+  switch (G) {                                       \
+    case 1: TZK_TILE_LAUNCH(KeyT, 1); break;         \
+    case 2: TZK_TILE_LAUNCH(KeyT, 2); break;         \
+    case 4: TZK_TILE_LAUNCH(KeyT, 4); break;         \
+    case 8: TZK_TILE_LAUNCH(KeyT, 8); break;         \
+    case 16: TZK_TILE_LAUNCH(KeyT, 16); break;       \
+    default: TZK_TILE_LAUNCH(KeyT, 32); break;       \
+  }
+    if (k64) { TZK_TILE_DISPATCH(uint64_t) } else { TZK_TILE_DISPATCH(uint32_t) }
+#undef TZK_TILE_DISPATCH
+#undef TZK_TILE_LAUNCH
+    return 0;
+  }
+
+  // general path (unaligned rows or rows wider than 128 floats): CH is compiled for 1, 2 and 8
+  zero_counters<<<1, 1, 0, st>>>(wl.counters);
   if (k64) {
     if (vec == 4) { if (ch == 1) { TZK_BWD_DISPATCH_G(uint64_t, 4, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint64_t, 32, 4, 2); } else { TZK_BWD_LAUNCH(uint64_t, 32, 4, 8); } }
     else { if (ch == 1) { TZK_BWD_DISPATCH_G(uint64_t, 1, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint64_t, 32, 1, 2); } else { TZK_BWD_LAUNCH(uint64_t, 32, 1, 8); } }

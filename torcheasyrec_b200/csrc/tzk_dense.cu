@@ -351,7 +351,7 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
           if (copy_dense) {
             const float* gp = go + P + p_pad + c4 * 4;
             if (aligned) {
-              v = f4_add(v, ld_row_f4(gp));
+              v = f4_add(v, __ldg(reinterpret_cast<const float4*>(gp)));  // not the asm load: a non-volatile asm may be speculated above `aligned`
             } else {
               v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
             }
@@ -362,7 +362,7 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
           if (copy_sparse) {
             const float* gp = go + P + p_pad + ((copy_dense && dense) ? D : 0) + r_s * D + c4 * 4;
             if (aligned) {
-              v = f4_add(v, ld_row_f4(gp));
+              v = f4_add(v, __ldg(reinterpret_cast<const float4*>(gp)));  // not the asm load: a non-volatile asm may be speculated above `aligned`
             } else {
               v.x += __ldg(gp); v.y += __ldg(gp + 1); v.z += __ldg(gp + 2); v.w += __ldg(gp + 3);
             }
@@ -548,7 +548,28 @@ bias_act_kernel(float* __restrict__ y, int64_t ld, const float* __restrict__ bia
   }
 }
 
-constexpr int kSlabRows = 512;
+// 16-B variant: N % 4 == 0, ld % 4 == 0, y 16-B aligned, M * N / 4 < 2^31
+__global__ void __launch_bounds__(kThreads)
+bias_act_vec_kernel(float* __restrict__ y, int64_t ld, const float* __restrict__ bias, int n4_total, int N4,
+                    int relu) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4_total; i += stride) {
+    const int r = i / N4, c4 = i - r * N4;
+    float4* p = reinterpret_cast<float4*>(y + (int64_t)r * ld) + c4;
+    float4 v = *p;
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (relu) {
+      v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+      v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+    }
+    *p = v;
+  }
+}
+
+constexpr int kSlabRows = 128;
 // N divides 256: thread (tid / N, tid % N) walks its rows of the slab; fixed-order reduction over row groups
 __global__ void __launch_bounds__(kThreads)
 act_bwd_colsum_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y, int64_t ld_y,
@@ -590,8 +611,14 @@ extern "C" int tzk_bias_act(float* y, int64_t ld_y, const float* bias, int64_t M
   TZK_REQUIRE(M >= 0 && N >= 1, "bias_act: bad sizes");
   if (M == 0) return 0;
   TZK_REQUIRE(y != nullptr, "bias_act: y is NULL");
-  bias_act_kernel<<<grid_for(M * N, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(y, ld_y, bias,
-                                                                                                  M, N, relu);
+  const bool vec = (N % 4 == 0) && (ld_y % 4 == 0) && ((uintptr_t)y % 16 == 0) &&
+                   (!bias || (uintptr_t)bias % 16 == 0) && (M * N / 4 < ((int64_t)1 << 31));
+  if (vec)
+    bias_act_vec_kernel<<<grid_for(M * N / 4, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(
+        y, ld_y, bias, (int)(M * N / 4), N / 4, relu);
+  else
+    bias_act_kernel<<<grid_for(M * N, kThreads, kSmCountB200 * 16), kThreads, 0, as_stream(stream)>>>(y, ld_y, bias,
+                                                                                                    M, N, relu);
   TZK_CHECK_LAUNCH("bias_act_kernel");
   return 0;
 }

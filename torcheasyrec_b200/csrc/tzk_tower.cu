@@ -1,0 +1,373 @@
+// tzk_tower.cu — narrow fully-connected layers and the BCE head of the rank models (callers of the hot path:
+// tzrec/modules/mlp.py:20-84 Perceptron = Linear -> ReLU, tzrec/models/rank_model.py:190-216 BCEWithLogitsLoss).
+//
+// A DLRM / DeepFM step runs a handful of layers whose weight matrix is at most 64 x 64 (13->64->16 bottom MLP,
+// 64->32->1 top of the final MLP, every tower's Linear(64, 1)).  As library GEMMs each of them costs 3-6 launches
+// forward and 6-10 backward (GEMM, split-K reduce, bias add, clamp, ReLU mask, column sums) and every launch is
+// latency-bound at these sizes.  Here a layer is ONE launch forward and one (+ a tiny fixed-order reduction)
+// backward: the weight matrix lives in shared memory, a CTA walks 128-row tiles, one thread owns one row.
+// Plain fp32 FFMA in ascending-k order (the reference runs these layers as fp32 SIMT GEMMs, TF32 off).
+// Weight / bias gradients are summed per CTA and then across CTAs in a fixed order: run-to-run deterministic.
+#include "tzk_common.cuh"
+
+using namespace tzk;
+
+namespace {
+constexpr int kTM = 128;  // rows per tile == threads per CTA
+
+__device__ __forceinline__ int odd(int v) { return v | 1; }  // odd row stride: thread-per-row reads are conflict-free
+
+// ---------------------------------------------------------------------------------------------------
+// forward: y = act(x @ W^T + b)          x [M,K]  W [N,K]  y [M,N]      K, N <= 64
+// ---------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(kTM)
+small_linear_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
+                        const float* __restrict__ bias, int64_t M, int K, int N, int relu,
+                        float* __restrict__ y, int64_t ld_y) {
+  extern __shared__ __align__(16) float sm[];
+  float* Wt = sm;             // [K][NP], zero beyond N
+  float* bs = Wt + K * NP;    // [NP]
+  float* tile = bs + NP;      // [kTM][TS]
+  const int TS = odd(K > N ? K : N);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * NP; i += kTM) {
+    const int k = i / NP, n = i - k * NP;
+    Wt[i] = n < N ? __ldg(w + (int64_t)n * K + k) : 0.f;
+  }
+  for (int i = tid; i < NP; i += kTM) bs[i] = (bias && i < N) ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  const int64_t n_tiles = ceil_div64(M, kTM);
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t row0 = t * kTM;
+    const int rows = (int)((M - row0) < kTM ? (M - row0) : kTM);
+    for (int i = tid; i < rows * K; i += kTM) {
+      const int r = i / K, k = i - r * K;
+      tile[r * TS + k] = __ldg(x + (row0 + r) * ld_x + k);
+    }
+    __syncthreads();
+    float acc[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[n] = 0.f;
+    if (tid < rows) {
+      const float* xr = tile + tid * TS;
+      for (int k = 0; k < K; ++k) {
+        const float xv = xr[k];
+        const float4* wr = reinterpret_cast<const float4*>(Wt + k * NP);
+#pragma unroll
+        for (int n4 = 0; n4 < NP / 4; ++n4) {
+          const float4 w4 = wr[n4];
+          acc[n4 * 4 + 0] = fmaf(xv, w4.x, acc[n4 * 4 + 0]);
+          acc[n4 * 4 + 1] = fmaf(xv, w4.y, acc[n4 * 4 + 1]);
+          acc[n4 * 4 + 2] = fmaf(xv, w4.z, acc[n4 * 4 + 2]);
+          acc[n4 * 4 + 3] = fmaf(xv, w4.w, acc[n4 * 4 + 3]);
+        }
+      }
+    }
+    __syncthreads();  // every thread is done reading the x tile
+    if (tid < rows) {
+      float* yr = tile + tid * TS;
+#pragma unroll
+      for (int n = 0; n < NP; ++n)
+        if (n < N) {
+          float v = acc[n] + bs[n];
+          if (relu) v = v > 0.f ? v : 0.f;
+          yr[n] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < rows * N; i += kTM) {
+      const int r = i / N, n = i - r * N;
+      y[(row0 + r) * ld_y + n] = tile[r * TS + n];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward: dz = dy * (relu ? y > 0 : 1);  dx = dz @ W;  dW = dz^T @ x;  db = colsum(dz)
+// per-CTA partial dW / db -> `partial[cta][N*K + N]`, reduced in CTA order by small_linear_reduce_kernel.
+// ---------------------------------------------------------------------------------------------------
+template <int KP, int NP>
+__global__ void __launch_bounds__(kTM)
+small_linear_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
+                        const float* __restrict__ y, int64_t ld_y, const float* __restrict__ dy, int64_t ld_dy,
+                        int64_t M, int K, int N, int relu, float* __restrict__ dx, int64_t ld_dx,
+                        float* __restrict__ partial) {
+  // dW micro-tiles: TN x TK threads, each NB x KB outputs
+  constexpr int TN = NP >= 8 ? 8 : NP;
+  constexpr int TK = kTM / TN;
+  constexpr int NB = NP / TN;
+  constexpr int KB = KP / TK > 0 ? KP / TK : 1;
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                  // [N][KP] (row n of W, zero beyond K)
+  const int KS = odd(K), NS = odd(N);
+  float* xt = Ws + N * KP;         // [kTM][KS]
+  float* dzt = xt + kTM * KS;      // [kTM][NS]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N * KP; i += kTM) {
+    const int n = i / KP, k = i - n * KP;
+    Ws[i] = k < K ? __ldg(w + (int64_t)n * K + k) : 0.f;
+  }
+  const int tn = tid / TK, tk = tid - tn * TK;
+  const int n0 = tn * NB, k0 = tk * KB;
+  float accW[NB][KB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < KB; ++j) accW[i][j] = 0.f;
+  float accB = 0.f;
+  __syncthreads();
+  const int64_t n_tiles = ceil_div64(M, kTM);
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t row0 = t * kTM;
+    const int rows = (int)((M - row0) < kTM ? (M - row0) : kTM);
+    for (int i = tid; i < rows * K; i += kTM) {
+      const int r = i / K, k = i - r * K;
+      xt[r * KS + k] = __ldg(x + (row0 + r) * ld_x + k);
+    }
+    for (int i = tid; i < rows * N; i += kTM) {
+      const int r = i / N, n = i - r * N;
+      float g = __ldg(dy + (row0 + r) * ld_dy + n);
+      if (relu && !(__ldg(y + (row0 + r) * ld_y + n) > 0.f)) g = 0.f;
+      dzt[r * NS + n] = g;
+    }
+    __syncthreads();
+    // ---- dW += dz^T x over the tile's rows (ascending), db likewise ---------------------------------
+    if (k0 < K && n0 < N) {
+      for (int r = 0; r < rows; ++r) {
+        float a[NB], b[KB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) a[i] = (n0 + i < N) ? dzt[r * NS + n0 + i] : 0.f;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) b[j] = (k0 + j < K) ? xt[r * KS + k0 + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+          for (int j = 0; j < KB; ++j) accW[i][j] = fmaf(a[i], b[j], accW[i][j]);
+      }
+    }
+    if (tid < N)
+      for (int r = 0; r < rows; ++r) accB += dzt[r * NS + tid];
+    // ---- dx = dz @ W : one thread per row ------------------------------------------------------------
+    if (dx) {
+      float acc[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+      if (tid < rows) {
+        const float* dr = dzt + tid * NS;
+        for (int n = 0; n < N; ++n) {
+          const float dv = dr[n];
+          const float4* wr = reinterpret_cast<const float4*>(Ws + n * KP);
+#pragma unroll
+          for (int k4 = 0; k4 < KP / 4; ++k4) {
+            const float4 w4 = wr[k4];
+            acc[k4 * 4 + 0] = fmaf(dv, w4.x, acc[k4 * 4 + 0]);
+            acc[k4 * 4 + 1] = fmaf(dv, w4.y, acc[k4 * 4 + 1]);
+            acc[k4 * 4 + 2] = fmaf(dv, w4.z, acc[k4 * 4 + 2]);
+            acc[k4 * 4 + 3] = fmaf(dv, w4.w, acc[k4 * 4 + 3]);
+          }
+        }
+      }
+      __syncthreads();  // dW / db loops are done with the x tile
+      if (tid < rows) {
+        float* xr = xt + tid * KS;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          if (k < K) xr[k] = acc[k];
+      }
+      __syncthreads();
+      for (int i = tid; i < rows * K; i += kTM) {
+        const int r = i / K, k = i - r * K;
+        dx[(row0 + r) * ld_dx + k] = xt[r * KS + k];
+      }
+    }
+    __syncthreads();
+  }
+  float* p = partial + (int64_t)blockIdx.x * (N * K + N);
+  if (k0 < K && n0 < N) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+      for (int j = 0; j < KB; ++j)
+        if (n0 + i < N && k0 + j < K) p[(n0 + i) * K + k0 + j] = accW[i][j];
+  }
+  if (tid < N) p[N * K + tid] = accB;
+}
+
+__global__ void __launch_bounds__(256)
+small_linear_reduce_kernel(const float* __restrict__ partial, int n_parts, int NK, int N, float* __restrict__ dw,
+                           float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NK + N) return;
+  float s = 0.f;
+  for (int c = 0; c < n_parts; ++c) s += partial[(int64_t)c * (NK + N) + i];  // fixed order
+  if (i < NK) dw[i] = s;
+  else if (db) db[i - NK] = s;
+}
+
+inline int pad_pow(int v, int lo) {  // smallest of {lo, 16, 32, 64} >= v
+  int p = lo;
+  while (p < v) p = p < 16 ? 16 : p * 2;
+  return p;
+}
+inline int bwd_grid(int64_t M) {
+  const int64_t t = ceil_div64(M < 1 ? 1 : M, kTM);
+  return (int)(t < kSmCountB200 * 2 ? t : kSmCountB200 * 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BCE with logits, mean reduction, forward and dloss/dlogits in one pass
+//   loss_i = max(z,0) - z*t + log1p(exp(-|z|))        d_i = (sigmoid(z) - t) / M
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBceThreads = 256;
+constexpr int kBcePerThread = 4;
+__global__ void __launch_bounds__(kBceThreads)
+bce_fwd_bwd_kernel(const float* __restrict__ z, const float* __restrict__ t, int64_t M, float inv_m,
+                   float* __restrict__ dz, float* __restrict__ partial) {
+  __shared__ float red[kBceThreads / 32];
+  float acc = 0.f;
+  const int64_t base = (int64_t)blockIdx.x * (kBceThreads * kBcePerThread);
+#pragma unroll
+  for (int u = 0; u < kBcePerThread; ++u) {
+    const int64_t i = base + u * kBceThreads + threadIdx.x;
+    if (i < M) {
+      const float zi = __ldg(z + i), ti = __ldg(t + i);
+      const float e = expf(-fabsf(zi));
+      acc += fmaxf(zi, 0.f) - zi * ti + log1pf(e);
+      const float sig = zi >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+      if (dz) dz[i] = (sig - ti) * inv_m;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < kBceThreads / 32; ++k) s += red[k];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256)
+bce_final_kernel(const float* __restrict__ partial, int n, float inv_m, float* __restrict__ loss) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += partial[i];  // fixed assignment, fixed tree below
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 128; d >= 1; d >>= 1) {
+    if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = red[0] * inv_m;
+}
+}  // namespace
+
+static int small_linear_check(const char* who, int64_t M, int32_t K, int32_t N) {
+  TZK_REQUIRE(M >= 0, "%s: negative M", who);
+  TZK_REQUIRE(K >= 1 && K <= 64 && N >= 1 && N <= 64, "%s: K=%d, N=%d outside [1,64]", who, K, N);
+  return 0;
+}
+
+extern "C" int tzk_small_linear_fwd(const float* x, int64_t ld_x, const float* w, const float* bias, int64_t M,
+                                    int32_t K, int32_t N, int32_t relu, float* y, int64_t ld_y,
+                                    tzk_stream_t stream) {
+  int rc = small_linear_check("small_linear_fwd", M, K, N);
+  if (rc) return rc;
+  if (M == 0) return 0;
+  TZK_REQUIRE(x && w && y, "small_linear_fwd: NULL argument");
+  TZK_REQUIRE(ld_x >= K && ld_y >= N, "small_linear_fwd: leading dimension smaller than the row");
+  const int NP = pad_pow(N, 4);
+  const int TS = (K > N ? K : N) | 1;
+  const size_t smem = ((size_t)K * NP + NP + (size_t)kTM * TS) * sizeof(float);
+  const int64_t tiles = ceil_div64(M, kTM);
+  const int grid = (int)(tiles < kSmCountB200 * 4 ? tiles : kSmCountB200 * 4);
+#define TZK_SLF(NP_)                                                                                              \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      cudaFuncSetAttribute(small_linear_fwd_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    small_linear_fwd_kernel<NP_><<<grid, kTM, smem, as_stream(stream)>>>(x, ld_x, w, bias, M, K, N, relu, y, ld_y); \
+  } while (0)
+  switch (NP) {
+    case 4: TZK_SLF(4); break;
+    case 16: TZK_SLF(16); break;
+    case 32: TZK_SLF(32); break;
+    default: TZK_SLF(64); break;
+  }
+#undef TZK_SLF
+  TZK_CHECK_LAUNCH("small_linear_fwd_kernel");
+  return 0;
+}
+
+extern "C" size_t tzk_small_linear_bwd_workspace_bytes(int64_t M, int32_t K, int32_t N) {
+  return (size_t)bwd_grid(M) * ((size_t)(N < 1 ? 1 : N) * (K < 1 ? 1 : K) + (N < 1 ? 1 : N)) * sizeof(float);
+}
+
+extern "C" int tzk_small_linear_bwd(const float* x, int64_t ld_x, const float* w, const float* y, int64_t ld_y,
+                                    const float* dy, int64_t ld_dy, int64_t M, int32_t K, int32_t N, int32_t relu,
+                                    float* dx, int64_t ld_dx, float* dw, float* db, void* workspace,
+                                    size_t workspace_bytes, tzk_stream_t stream) {
+  int rc = small_linear_check("small_linear_bwd", M, K, N);
+  if (rc) return rc;
+  TZK_REQUIRE(M >= 1, "small_linear_bwd: empty batch");
+  TZK_REQUIRE(x && w && dy && dw && (!relu || y), "small_linear_bwd: NULL argument");
+  TZK_REQUIRE(ld_x >= K && ld_dy >= N && (!relu || ld_y >= N) && (!dx || ld_dx >= K),
+              "small_linear_bwd: leading dimension smaller than the row");
+  TZK_REQUIRE(workspace && workspace_bytes >= tzk_small_linear_bwd_workspace_bytes(M, K, N),
+              "small_linear_bwd: workspace too small");
+  const int KP = pad_pow(K, 16), NP = pad_pow(N, 4);
+  const int grid = bwd_grid(M);
+  const size_t smem = ((size_t)N * KP + (size_t)kTM * (K | 1) + (size_t)kTM * (N | 1)) * sizeof(float);
+  float* partial = static_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+#define TZK_SLB(KP_, NP_)                                                                                          \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      cudaFuncSetAttribute(small_linear_bwd_kernel<KP_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                           (int)smem);                                                                             \
+    small_linear_bwd_kernel<KP_, NP_><<<grid, kTM, smem, st>>>(x, ld_x, w, y, ld_y, dy, ld_dy, M, K, N, relu, dx,   \
+                                                               ld_dx, partial);                                    \
+  } while (0)
+#define TZK_SLB_N(KP_)                      \
+  switch (NP) {                             \
+    case 4: TZK_SLB(KP_, 4); break;         \
+    case 16: TZK_SLB(KP_, 16); break;       \
+    case 32: TZK_SLB(KP_, 32); break;       \
+    default: TZK_SLB(KP_, 64); break;       \
+  }
+  switch (KP) {
+    case 16: TZK_SLB_N(16) break;
+    case 32: TZK_SLB_N(32) break;
+    default: TZK_SLB_N(64) break;
+  }
+#undef TZK_SLB_N
+#undef TZK_SLB
+  TZK_CHECK_LAUNCH("small_linear_bwd_kernel");
+  const int total = N * K + N;
+  small_linear_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, grid, N * K, N, dw, db);
+  TZK_CHECK_LAUNCH("small_linear_reduce_kernel");
+  return 0;
+}
+
+extern "C" size_t tzk_bce_logits_workspace_bytes(int64_t M) {
+  return (size_t)ceil_div64(M < 1 ? 1 : M, kBceThreads * kBcePerThread) * sizeof(float);
+}
+
+extern "C" int tzk_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t M, float* loss,
+                                      float* dlogits, void* workspace, size_t workspace_bytes,
+                                      tzk_stream_t stream) {
+  TZK_REQUIRE(M >= 1, "bce_logits: empty batch");
+  TZK_REQUIRE(logits && labels && loss, "bce_logits: NULL argument");
+  TZK_REQUIRE(workspace && workspace_bytes >= tzk_bce_logits_workspace_bytes(M), "bce_logits: workspace too small");
+  const int64_t nb = ceil_div64(M, kBceThreads * kBcePerThread);
+  TZK_REQUIRE(nb < ((int64_t)1 << 31), "bce_logits: batch too large");
+  float* partial = static_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  const float inv_m = 1.0f / (float)M;
+  bce_fwd_bwd_kernel<<<(unsigned)nb, kBceThreads, 0, st>>>(logits, labels, M, inv_m, dlogits, partial);
+  TZK_CHECK_LAUNCH("bce_fwd_bwd_kernel");
+  bce_final_kernel<<<1, 256, 0, st>>>(partial, (int)nb, inv_m, loss);
+  TZK_CHECK_LAUNCH("bce_final_kernel");
+  return 0;
+}

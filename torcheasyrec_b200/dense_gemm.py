@@ -131,6 +131,68 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class _SmallLinearFn(torch.autograd.Function):
+    """y = act(x @ W^T + b) for K, N <= 64: one tzk launch forward, one (+ partial reduction) backward
+    (csrc/tzk_tower.cu) instead of the 4-10 library launches such a layer costs as GEMM + element-wise passes."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        from .kernels import default_kernels
+
+        w = weight.contiguous()
+        y = default_kernels().small_linear_fwd(x, w, bias, relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .kernels import default_kernels
+
+        x, w, y = ctx.saved_tensors
+        dy = dy if (dy.stride(1) == 1 and dy.stride(0) >= dy.shape[1]) else dy.contiguous()
+        dx, dw, db = default_kernels().small_linear_bwd(
+            x, w, y, dy, ctx.relu, want_dx=ctx.needs_input_grad[0],
+            want_db=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, (dw if ctx.needs_input_grad[1] else None), db, None
+
+
+SMALL_MAX = 64      # tzk_small_linear_*: K, N <= 64
+
+
+def _small(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and weight.shape[0] <= SMALL_MAX and weight.shape[1] <= SMALL_MAX and x.shape[1] == weight.shape[1]
+            and x.shape[0] >= 1 and x.stride(1) == 1 and x.stride(0) >= x.shape[1]
+            and os.environ.get("TZK_SMALL_LINEAR", "1") != "0")
+
+
+class _BceFn(torch.autograd.Function):
+    """mean BCE-with-logits; the forward kernel also writes dloss/dlogits, backward only scales it."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        from .kernels import default_kernels
+
+        loss, dz = default_kernels().bce_logits_fwd_bwd(logits.contiguous(), labels.contiguous())
+        ctx.save_for_backward(dz)
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return (dz * g).view(ctx.shape), None
+
+
+def bce_with_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """F.binary_cross_entropy_with_logits(logits, labels) (mean); fused fwd+bwd kernel on CUDA fp32 inputs."""
+    if (logits.is_cuda and logits.dtype == torch.float32 and labels.dtype == torch.float32 and logits.numel() >= 1
+            and os.environ.get("TZK_SMALL_LINEAR", "1") != "0"):
+        return _BceFn.apply(logits, labels)
+    return torch.nn.functional.binary_cross_entropy_with_logits(logits, labels)
+
+
 def padded_width(n: int) -> int:
     return (n + 3) // 4 * 4
 
@@ -147,6 +209,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     padded_width(in_features)) or, with `in_map` = ((src_col, dst_col, n), ...), with zero columns in between —
     column src of the weight multiplies column dst of x."""
     K = weight.shape[1]
+    if in_map is None and _small(x, weight):
+        return _SmallLinearFn.apply(x, weight, bias, relu)
     if x.dim() == 2 and (x.shape[1] != K or in_map is not None):
         if in_map is None and x.shape[1] != padded_width(K):
             raise RuntimeError(f"linear: input width {x.shape[1]} does not match in_features {K}")

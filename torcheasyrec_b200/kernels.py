@@ -205,7 +205,9 @@ class CudaKernels:
             _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets), F, B, nnz,
             lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
             _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
-        self.launches += 5  # zero_counters, linearize, run_update, long_chunk, long_combine (+ CUB radix sort)
+        # own launches next to CUB's radix sort: tile path = linearize, tile_update, carry_combine;
+        # general path (unaligned / > 128 floats) = zero_counters, linearize, run_update, long_chunk, long_combine
+        self.launches += 3 if (lay.vec_ok and lay.max_dim <= 128) else 5
 
     # ------------------------------------------------------------------ K1 / K2
     def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
@@ -396,6 +398,59 @@ class CudaKernels:
                                            _ptr(ws), ws.numel(), _stream()), "tzk_act_bwd_colsum")
         self.launches += 2
         return dz, colsum
+    # ------------------------------------------------------------------ narrow layers + BCE head
+    def small_linear_fwd(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
+                         relu: bool) -> torch.Tensor:
+        x, ld_x = _rows2d(x, "x")
+        _need(w, torch.float32, "w")
+        M, K = x.shape
+        N = w.shape[0]
+        if w.shape[1] != K:
+            raise TzkError(f"small_linear_fwd: x has {K} columns, w expects {w.shape[1]}")
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        if M:
+            check(self._lib.tzk_small_linear_fwd(_ptr(x), ld_x, _ptr(w), _ptr(bias), M, K, N, int(relu), _ptr(y), N,
+                                                 _stream()), "tzk_small_linear_fwd")
+            self.launches += 1
+        return y
+
+    def small_linear_bwd(self, x: torch.Tensor, w: torch.Tensor, y: Optional[torch.Tensor], dy: torch.Tensor,
+                         relu: bool, want_dx: bool, want_db: bool):
+        """-> (dx | None, dw [N,K], db [N] | None)."""
+        x, ld_x = _rows2d(x, "x")
+        dy, ld_dy = _rows2d(dy, "dy")
+        _need(w, torch.float32, "w")
+        M, K = x.shape
+        N = w.shape[0]
+        ld_y = 0
+        if relu:
+            y, ld_y = _rows2d(y, "y")
+        dx = torch.empty((M, K), dtype=torch.float32, device=x.device) if want_dx else None
+        dw = torch.empty((N, K), dtype=torch.float32, device=x.device)
+        db = torch.empty(N, dtype=torch.float32, device=x.device) if want_db else None
+        nb = self._lib.tzk_small_linear_bwd_workspace_bytes(M, K, N)
+        ws = self._workspace(("slb", K, N), nb, x.device)
+        check(self._lib.tzk_small_linear_bwd(_ptr(x), ld_x, _ptr(w), _ptr(y) if relu else None, ld_y, _ptr(dy), ld_dy,
+                                             M, K, N, int(relu), _ptr(dx), K, _ptr(dw), _ptr(db), _ptr(ws),
+                                             ws.numel(), _stream()), "tzk_small_linear_bwd")
+        self.launches += 2
+        return dx, dw, db
+
+    def bce_logits_fwd_bwd(self, logits: torch.Tensor, labels: torch.Tensor, want_grad: bool = True):
+        """-> (loss [scalar tensor], dloss/dlogits [M] | None); mean reduction."""
+        _need(logits, torch.float32, "logits")
+        _need(labels, torch.float32, "labels")
+        M = logits.numel()
+        if labels.numel() != M:
+            raise TzkError("bce_logits: logits and labels differ in size")
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        dz = torch.empty(M, dtype=torch.float32, device=logits.device) if want_grad else None
+        nb = self._lib.tzk_bce_logits_workspace_bytes(M)
+        ws = self._workspace("bce", nb, logits.device)
+        check(self._lib.tzk_bce_logits_fwd_bwd(_ptr(logits), _ptr(labels), M, _ptr(loss), _ptr(dz), _ptr(ws),
+                                               ws.numel(), _stream()), "tzk_bce_logits_fwd_bwd")
+        self.launches += 2
+        return loss, dz
 
 
 @dataclass

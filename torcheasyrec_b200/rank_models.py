@@ -242,7 +242,9 @@ class RankModel(nn.Module):
     def loss(self, predictions: Dict[str, torch.Tensor], batch: Batch) -> Dict[str, torch.Tensor]:
         """rank_model.py:181-287: BCEWithLogitsLoss(mean) on the first label."""
         label = batch.labels[self._label_name].to(torch.float32)
-        return {"binary_cross_entropy": F.binary_cross_entropy_with_logits(predictions["logits"], label)}
+        from .dense_gemm import bce_with_logits
+
+        return {"binary_cross_entropy": bce_with_logits(predictions["logits"], label)}
 
     def sparse_collections(self):
         return list(self.embedding_group.sparse_collections())
@@ -398,10 +400,12 @@ class MMoE(RankModel):
         return preds
 
     def loss(self, predictions, batch):
+        from .dense_gemm import bce_with_logits
+
         out = {}
         for cfg in self._task_tower_cfgs:
             label = batch.labels[cfg.label_name].to(torch.float32)
-            out[f"binary_cross_entropy_{cfg.tower_name}"] = cfg.weight * F.binary_cross_entropy_with_logits(
+            out[f"binary_cross_entropy_{cfg.tower_name}"] = cfg.weight * bce_with_logits(
                 predictions[f"logits_{cfg.tower_name}"], label)
         return out
 
