@@ -100,6 +100,19 @@ int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int6
                   int64_t total_keys, int32_t max_dim, int32_t vec_ok, float* weights, float* state,
                   float lr, float eps, float grad_scale, void* workspace, size_t workspace_bytes,
                   tzk_stream_t stream);
+/* The same update in two calls that share `workspace` (tzk_fused_bwd_workspace_bytes): _sort needs only the ids, so
+ * the host can enqueue it on a side stream as soon as the batch is on the device — it then overlaps the forward
+ * pass (what TrainPipelineSparseDist does for the input dist, tzrec/utils/dist_util.py:221-303) — and _apply,
+ * ordered after it, consumes the gradient.  tzk_fused_bwd == _sort followed by _apply on one stream. */
+int tzk_fused_bwd_sort(int32_t pooled, const int64_t* feat_rows, const int64_t* feat_key_base, const int64_t* ids,
+                       const int64_t* offsets, int32_t F, int32_t B, int64_t nnz, int64_t total_keys,
+                       int32_t max_dim, void* workspace, size_t workspace_bytes, tzk_stream_t stream);
+int tzk_fused_bwd_apply(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                        const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                        const int32_t* feat_col, const int32_t* feat_pool, const int64_t* feat_key_base,
+                        const int64_t* offsets, int32_t F, int32_t B, int64_t nnz, int64_t total_keys,
+                        int32_t max_dim, int32_t vec_ok, float* weights, float* state, float lr, float eps,
+                        float grad_scale, void* workspace, size_t workspace_bytes, tzk_stream_t stream);
 
 /* ---- pooled-lookup backward w.r.t. a row buffer in which every row is referenced exactly once (the
  * sample owner's half of the sharded backward; our replacement of [EXT] PooledEmbeddingsAllToAll /

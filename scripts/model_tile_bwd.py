@@ -21,6 +21,41 @@ def run(keys, g, TP, sentinel):
         k_first, k_last = sk[1], sk[cnt]
         first_cont = t > 0 and sk[0] == k_first
         last_cont = base + cnt < n and sk[cnt + 1] == k_last
+        rows = [g[base + i] for i in range(cnt)]
+        # level 1 (blocks of 8) and level 2 (blocks of 64), in place like the kernel (reads of a level see only the
+        # previous level's values: emulate the barrier with a copy)
+        prev = list(rows)
+        for i in range(cnt):
+            key = sk[i + 1]
+            if key == sentinel:
+                continue
+            head = i == 0 or sk[i] != key
+            if not (head or i % 8 == 0):
+                continue
+            if not (i + 1 < cnt and (i + 1) % 8 != 0 and sk[i + 2] == key):
+                continue
+            acc = prev[i]
+            j = i + 1
+            while j < cnt and j % 8 != 0 and sk[j + 1] == key:
+                acc += prev[j]
+                j += 1
+            rows[i] = acc
+        prev = list(rows)
+        for i in range(cnt):
+            key = sk[i + 1]
+            if key == sentinel:
+                continue
+            head = i == 0 or sk[i] != key
+            if not (head or i % 64 == 0):
+                continue
+            j = (i | 7) + 1
+            if not (j < cnt and j % 64 != 0 and sk[j + 1] == key):
+                continue
+            acc = prev[i]
+            while j < cnt and j % 64 != 0 and sk[j + 1] == key:
+                acc += prev[j]
+                j += 8
+            rows[i] = acc
         for i in range(cnt):
             key = sk[i + 1]
             if key == sentinel:
@@ -29,11 +64,11 @@ def run(keys, g, TP, sentinel):
                 c_l = i == 0 and first_cont
                 c_r = key == k_last and last_cont
                 kind = 2 if c_r else (1 if c_l else 3)
-                acc = g[base + i]
-                j = i + 1
+                acc = rows[i]
+                j = (i | 63) + 1
                 while j < cnt and sk[j + 1] == key:
-                    acc += g[base + j]
-                    j += 1
+                    acc += rows[j]
+                    j += 64
                 if kind == 1:
                     assert cf[t] is None
                     cf[t] = acc
@@ -73,9 +108,9 @@ def run(keys, g, TP, sentinel):
 
 
 rng = np.random.default_rng(0)
-for trial in range(3000):
-    TP = int(rng.choice([2, 4, 8, 32]))
-    n = int(rng.integers(1, 40 * TP))
+for trial in range(2000):
+    TP = int(rng.choice([2, 4, 8, 32, 256]))
+    n = int(rng.integers(1, (40 if TP < 256 else 6) * TP))
     nk = int(rng.choice([1, 2, 3, 5, 50, 1000]))
     keys = np.sort(rng.integers(0, nk, size=n))
     n_pad = int(rng.integers(0, 3 * TP)) if rng.random() < 0.5 else 0

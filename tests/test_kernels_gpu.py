@@ -439,7 +439,7 @@ def test_small_linear_fwd_bwd_vs_fp64_reference(kernels, M, K, N, relu):
     rng = np.random.default_rng(M * 7 + K * 3 + N)
     wide = rng.standard_normal((M, K + 5)).astype(np.float32)     # x is a column slice of a wider buffer
     x = cu(wide)[:, 2:2 + K]
-    w = rng.standard_normal((N, K)).astype(np.float32) / np.sqrt(K)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     b = rng.standard_normal(N).astype(np.float32)
     dy = rng.standard_normal((M, N)).astype(np.float32)
     x64, w64, b64, dy64 = wide[:, 2:2 + K].astype(np.float64), w.astype(np.float64), b.astype(np.float64), dy.astype(np.float64)

@@ -31,6 +31,12 @@ SIGNATURES = {
         [c_int32, c_int32, P, c_int64, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int64, c_int64, c_int32,
          c_int32, P, P, c_float, c_float, c_float, P, c_size_t, P],
     ),
+    "tzk_fused_bwd_sort": (c_int32, [c_int32, P, P, P, P, c_int32, c_int32, c_int64, c_int64, c_int32, P, c_size_t, P]),
+    "tzk_fused_bwd_apply": (
+        c_int32,
+        [c_int32, c_int32, P, c_int64, P, P, P, P, P, P, P, c_int32, c_int32, c_int64, c_int64, c_int32,
+         c_int32, P, P, c_float, c_float, c_float, P, c_size_t, P],
+    ),
     "tzk_bucketize_rw_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int64]),
     "tzk_bucketize_rw": (
         c_int32,

@@ -632,7 +632,7 @@ inline int64_t tile_carry_floats(int64_t n, int rowf) {  // per carry array
 }
 
 template <typename KeyT, int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
                    const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
                    const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
@@ -640,6 +640,8 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
                    float* __restrict__ carry_first, float* __restrict__ carry_last) {
   using C = TileCfg<G>;
   constexpr int ROWF = C::ROWF, TP = C::TP, NG = C::NG, U = C::U;
+  constexpr int KPT = (TP + 2 + kThreads - 1) / kThreads;  // keys per thread (tile + both neighbours)
+  constexpr int VPT = (TP + kThreads - 1) / kThreads;      // vals per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* rows = reinterpret_cast<float*>(smem_raw);                      // [TP][ROWF]
   KeyT* sk = reinterpret_cast<KeyT*>(rows + TP * ROWF);                   // [TP + 2]: left nb, tile, right nb
@@ -651,62 +653,126 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
   const int c = lane * 4;
   const KeyT sentinel = (KeyT)a.sentinel;
   const int64_t n_tiles = (a.n + TP - 1) / TP;
+
+  // keys / vals of a tile travel global -> registers -> shared memory; the loads of tile t+grid are issued before
+  // tile t is processed, so their latency hides behind phases B and C
+  KeyT pk[KPT];
+  int32_t pv[VPT];
+  auto prefetch = [&](int64_t t) {
+    const int64_t base = t * TP;
+#pragma unroll
+    for (int q = 0; q < KPT; ++q) {
+      const int64_t p = base + threadIdx.x + q * kThreads - 1;
+      pk[q] = (t < n_tiles && threadIdx.x + q * kThreads < TP + 2 && p >= 0 && p < a.n) ? keys[p] : sentinel;
+    }
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      const int64_t p = base + threadIdx.x + q * kThreads;
+      pv[q] = (t < n_tiles && threadIdx.x + q * kThreads < TP && p < a.n) ? vals[p] : 0;
+    }
+  };
+  prefetch(blockIdx.x);
+
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t base = t * TP;
     const int cnt = (int)((a.n - base) < TP ? (a.n - base) : TP);
-    // ---- A ---------------------------------------------------------------------------------------
-    for (int i = threadIdx.x; i < cnt + 2; i += kThreads) {
-      const int64_t p = base + i - 1;
-      sk[i] = (p >= 0 && p < a.n) ? keys[p] : sentinel;
-    }
-    for (int i = threadIdx.x; i < cnt; i += kThreads) sv[i] = vals[base + i];
+    // ---- A: registers -> shared memory ----------------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < KPT; ++q)
+      if (threadIdx.x + q * kThreads < TP + 2) sk[threadIdx.x + q * kThreads] = pk[q];
+#pragma unroll
+    for (int q = 0; q < VPT; ++q)
+      if (threadIdx.x + q * kThreads < TP) sv[threadIdx.x + q * kThreads] = pv[q];
     __syncthreads();
+    prefetch(t + gridDim.x);
     const KeyT k_first = sk[1], k_last = sk[cnt];
     const bool first_cont = (t > 0) && sk[0] == k_first;
     const bool last_cont = (base + cnt < a.n) && sk[cnt + 1] == k_last;
-    // ---- B ---------------------------------------------------------------------------------------
-    float4 w4[U], s4[U];
-    int kind[U], fx[U];  // kind: 0 none, 1 -> carry_first, 2 -> carry_last, 3 -> update here
+    // ---- B: all global requests of the tile ------------------------------------------------------------
+    float4 w4[U], s4[U], g4[U];
+    int kind[U], fx[U];    // kind: 0 none, 1 -> carry_first, 2 -> carry_last, 3 -> update here
+    bool multi[U];         // run head whose run has more than one position inside the tile
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = grp + NG * u;
       kind[u] = 0;
       fx[u] = 0;
+      multi[u] = false;
       w4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       s4[u] = w4[u];
+      g4[u] = w4[u];
       if (i >= cnt) continue;
       const KeyT key = sk[i + 1];
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (key != sentinel) {
-        const int32_t v = sv[i];
-        const int f = a.pooled ? v / a.B : feat_of_key<KeyT>(fd, a.F, key);
-        fx[u] = f;
-        const int dim = fd[f].dim;
-        const Entry en = entry_of(a, fd, v, f);
-        if (c < dim) g = f4_scale(ld_row_f4(en.g + c), en.scale);
-        if (i == 0 || sk[i] != key) {
-          const bool cl = (i == 0) && first_cont;
-          const bool cr = (key == k_last) && last_cont;
-          kind[u] = cr ? 2 : (cl ? 1 : 3);
-          if (kind[u] == 3 && c < dim) {
-            const int64_t off = fd[f].w_off + ((int64_t)key - fd[f].key_base) * dim + c;
-            w4[u] = *reinterpret_cast<const float4*>(a.weights + off);
-            if (a.optimizer == TZK_OPT_ADAGRAD) s4[u] = *reinterpret_cast<const float4*>(a.state + off);
-          }
+      if (key == sentinel) continue;
+      const int32_t v = sv[i];
+      const int f = a.pooled ? v / a.B : feat_of_key<KeyT>(fd, a.F, key);
+      fx[u] = f;
+      const int dim = fd[f].dim;
+      const Entry en = entry_of(a, fd, v, f);
+      if (c < dim) g4[u] = f4_scale(ld_row_f4(en.g + c), en.scale);
+      if (i == 0 || sk[i] != key) {
+        const bool cl = (i == 0) && first_cont;
+        const bool cr = (key == k_last) && last_cont;
+        kind[u] = cr ? 2 : (cl ? 1 : 3);
+        multi[u] = (i + 1 < cnt) && sk[i + 2] == key;
+        if (kind[u] == 3 && c < dim) {
+          const int64_t off = fd[f].w_off + ((int64_t)key - fd[f].key_base) * dim + c;
+          w4[u] = *reinterpret_cast<const float4*>(a.weights + off);
+          if (a.optimizer == TZK_OPT_ADAGRAD) s4[u] = *reinterpret_cast<const float4*>(a.state + off);
         }
       }
-      *reinterpret_cast<float4*>(rows + i * ROWF + c) = g;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = grp + NG * u;
+      if (i < cnt) *reinterpret_cast<float4*>(rows + i * ROWF + c) = g4[u];
     }
     __syncthreads();
-    // ---- C ---------------------------------------------------------------------------------------
+    // ---- C: in-tile segmented reduction, three levels (8 / 64 / tile), fixed order -------------------------
+    // level 1: positions that start a run or an aligned block of 8 add up their block-of-8 part of the run
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = grp + NG * u;
+      if (i >= cnt) continue;
+      const KeyT key = sk[i + 1];
+      if (key == sentinel) continue;
+      const bool head = (i == 0) || sk[i] != key;
+      if (!(head || (i & 7) == 0)) continue;
+      if (!(i + 1 < cnt && ((i + 1) & 7) != 0 && sk[i + 2] == key)) continue;
+      float4 acc = *reinterpret_cast<const float4*>(rows + i * ROWF + c);
+      for (int j = i + 1; j < cnt && (j & 7) != 0 && sk[j + 1] == key; ++j)
+        acc = f4_add(acc, *reinterpret_cast<const float4*>(rows + j * ROWF + c));
+      *reinterpret_cast<float4*>(rows + i * ROWF + c) = acc;
+    }
+    __syncthreads();
+    // level 2: run starts / aligned blocks of 64 add the block-of-8 partials of their part of the run
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = grp + NG * u;
+      if (i >= cnt) continue;
+      const KeyT key = sk[i + 1];
+      if (key == sentinel) continue;
+      const bool head = (i == 0) || sk[i] != key;
+      if (!(head || (i & 63) == 0)) continue;
+      int j = (i | 7) + 1;
+      if (!(j < cnt && (j & 63) != 0 && sk[j + 1] == key)) continue;
+      float4 acc = *reinterpret_cast<const float4*>(rows + i * ROWF + c);
+      for (; j < cnt && (j & 63) != 0 && sk[j + 1] == key; j += 8)
+        acc = f4_add(acc, *reinterpret_cast<const float4*>(rows + j * ROWF + c));
+      *reinterpret_cast<float4*>(rows + i * ROWF + c) = acc;
+    }
+    __syncthreads();
+    // level 3: run heads add the block-of-64 partials, then update / park the sum
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (kind[u] == 0) continue;
       const int i = grp + NG * u;
       const KeyT key = sk[i + 1];
       float4 acc = *reinterpret_cast<const float4*>(rows + i * ROWF + c);
-      for (int j = i + 1; j < cnt && sk[j + 1] == key; ++j)
-        acc = f4_add(acc, *reinterpret_cast<const float4*>(rows + j * ROWF + c));
+      if (multi[u]) {
+        for (int j = (i | 63) + 1; j < cnt && sk[j + 1] == key; j += 64)
+          acc = f4_add(acc, *reinterpret_cast<const float4*>(rows + j * ROWF + c));
+      }
       if (kind[u] == 1) {
         *reinterpret_cast<float4*>(carry_first + t * ROWF + c) = acc;
       } else if (kind[u] == 2) {
@@ -897,23 +963,27 @@ extern "C" size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys,
   return ws_layout(nnz, total_keys, max_dim < 1 ? 1 : max_dim).total;
 }
 
-extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
-                             const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
-                             const int32_t* feat_col, const int32_t* feat_pool,
-                             const int64_t* feat_key_base, const int64_t* ids, const int64_t* offsets,
-                             int32_t F, int32_t B, int64_t nnz, int64_t total_keys, int32_t max_dim,
-                             int32_t vec_ok, float* weights, float* state, float lr, float eps,
-                             float grad_scale, void* workspace, size_t workspace_bytes,
-                             tzk_stream_t stream) {
+// phases: 1 = linearize + sort (needs ids / offsets only), 2 = reduce runs + update (needs the gradient)
+static int fused_bwd_impl(int phases, int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                          const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                          const int32_t* feat_col, const int32_t* feat_pool,
+                          const int64_t* feat_key_base, const int64_t* ids, const int64_t* offsets,
+                          int32_t F, int32_t B, int64_t nnz, int64_t total_keys, int32_t max_dim,
+                          int32_t vec_ok, float* weights, float* state, float lr, float eps,
+                          float grad_scale, void* workspace, size_t workspace_bytes,
+                          tzk_stream_t stream) {
   TZK_REQUIRE(optimizer >= 0 && optimizer <= 2, "fused_bwd: unknown optimizer %d", optimizer);
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0, "fused_bwd: negative size");
   if (F == 0 || B == 0 || nnz == 0) return 0;
   TZK_REQUIRE(nnz < ((int64_t)1 << 31) && (int64_t)F * std::max(B, 1) < ((int64_t)1 << 31),
               "fused_bwd: nnz or F*B >= 2^31 not supported");
-  TZK_REQUIRE(grad_out && feat_w_off && feat_rows && feat_dim && feat_key_base && ids && offsets && weights,
-              "fused_bwd: NULL argument");
-  TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
-  TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
+  TZK_REQUIRE(feat_rows && feat_key_base && offsets, "fused_bwd: NULL argument");
+  TZK_REQUIRE(!(phases & 1) || ids, "fused_bwd: ids is NULL");
+  if (phases & 2) {
+    TZK_REQUIRE(grad_out && feat_w_off && feat_dim && weights, "fused_bwd: NULL argument");
+    TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
+    TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
+  }
   TZK_REQUIRE(F <= 2048, "fused_bwd: F=%d > 2048 keys per collection", F);
   TZK_REQUIRE(max_dim >= 1 && max_dim <= 1024, "fused_bwd: max_dim=%d out of range [1,1024]", max_dim);
   WsLayout L = ws_layout(nnz, total_keys, max_dim);
@@ -934,6 +1004,7 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
   const int bits = bits_for(total_keys + 1);   // one spare value above the largest key = padding sentinel
   const uint64_t sentinel = ((uint64_t)1 << bits) - 1;
 
+  if (phases & 1) {
   const int64_t n_bags = (int64_t)F * B;
   int grid_lin = (int)std::min<int64_t>(ceil_div64(n_bags, kThreads), kSmCountB200 * 16);
   size_t cub_bytes = L.cub_bytes;
@@ -962,6 +1033,8 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
                             vals_out, nnz, bits, st);
   }
   TZK_REQUIRE(ce == cudaSuccess, "fused_bwd: radix sort failed: %s", cudaGetErrorString(ce));
+  }
+  if (!(phases & 2)) return 0;
 
   BwdArgs a;
   a.grad_out = grad_out; a.ld_grad = ld_grad; a.offsets = offsets; a.weights = weights; a.state = state;
@@ -1046,6 +1119,40 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
     else { if (ch == 1) { TZK_BWD_DISPATCH_G(uint32_t, 1, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint32_t, 32, 1, 2); } else { TZK_BWD_LAUNCH(uint32_t, 32, 1, 8); } }
   }
   return 0;
+}
+
+extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                             const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                             const int32_t* feat_col, const int32_t* feat_pool,
+                             const int64_t* feat_key_base, const int64_t* ids, const int64_t* offsets,
+                             int32_t F, int32_t B, int64_t nnz, int64_t total_keys, int32_t max_dim,
+                             int32_t vec_ok, float* weights, float* state, float lr, float eps,
+                             float grad_scale, void* workspace, size_t workspace_bytes,
+                             tzk_stream_t stream) {
+  return fused_bwd_impl(3, optimizer, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
+                        feat_key_base, ids, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, state, lr, eps,
+                        grad_scale, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tzk_fused_bwd_sort(int32_t pooled, const int64_t* feat_rows, const int64_t* feat_key_base,
+                                  const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int64_t nnz,
+                                  int64_t total_keys, int32_t max_dim, void* workspace, size_t workspace_bytes,
+                                  tzk_stream_t stream) {
+  return fused_bwd_impl(1, TZK_OPT_SGD, pooled, nullptr, 0, nullptr, feat_rows, nullptr, nullptr, nullptr,
+                        feat_key_base, ids, offsets, F, B, nnz, total_keys, max_dim, 0, nullptr, nullptr, 0.f, 0.f,
+                        0.f, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tzk_fused_bwd_apply(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                                   const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                                   const int32_t* feat_col, const int32_t* feat_pool,
+                                   const int64_t* feat_key_base, const int64_t* offsets, int32_t F, int32_t B,
+                                   int64_t nnz, int64_t total_keys, int32_t max_dim, int32_t vec_ok, float* weights,
+                                   float* state, float lr, float eps, float grad_scale, void* workspace,
+                                   size_t workspace_bytes, tzk_stream_t stream) {
+  return fused_bwd_impl(2, optimizer, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
+                        feat_key_base, nullptr, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, state, lr,
+                        eps, grad_scale, workspace, workspace_bytes, stream);
 }
 
 extern "C" int tzk_bag_grad_expand(const float* grad_out, int64_t ld_grad, const int32_t* feat_col,

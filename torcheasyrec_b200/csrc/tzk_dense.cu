@@ -581,6 +581,7 @@ act_bwd_colsum_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* 
   const int64_t row_lo = (int64_t)blockIdx.x * kSlabRows;
   const int64_t row_hi = row_lo + kSlabRows < M ? row_lo + kSlabRows : M;
   float acc = 0.f;
+#pragma unroll 4
   for (int64_t r = row_lo + r0; r < row_hi; r += rg) {
     float g = __ldg(dy + r * ld_dy + c);
     if (relu && !(__ldg(y + r * ld_y + c) > 0.f)) g = 0.f;
@@ -596,13 +597,30 @@ act_bwd_colsum_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* 
   }
 }
 
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t n_blocks, int N,
-                                    float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+// 32 columns x 8 partial-groups per CTA, fixed-order fold: deterministic
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int64_t n_blocks, int N, float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + o;
   float s = 0.f;
-  for (int64_t b = 0; b < n_blocks; ++b) s += partial[b * N + c];   // fixed order: deterministic
-  out[c] = s;
+  if (c < N) {
+    int64_t b = g;
+    for (; b + 24 < n_blocks; b += 32) {
+      const float a0 = partial[b * N + c], a1 = partial[(b + 8) * N + c];
+      const float a2 = partial[(b + 16) * N + c], a3 = partial[(b + 24) * N + c];
+      s += a0; s += a1; s += a2; s += a3;
+    }
+    for (; b < n_blocks; b += 8) s += partial[b * N + c];
+  }
+  red[g][o] = s;
+  __syncthreads();
+  if (g == 0 && c < N) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[k][o];
+    out[c] = r;
+  }
 }
 }  // namespace
 
@@ -640,7 +658,7 @@ extern "C" int tzk_act_bwd_colsum(const float* dy, int64_t ld_dy, const float* y
   act_bwd_colsum_kernel<<<(unsigned)nb, kThreads, 0, as_stream(stream)>>>(dy, ld_dy, y, ld_y, M, N, relu, dz, ld_dz,
                                                                           partial);
   TZK_CHECK_LAUNCH("act_bwd_colsum_kernel");
-  colsum_final_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(partial, nb, N, colsum);
+  colsum_final_kernel<<<(N + 31) / 32, 256, 0, as_stream(stream)>>>(partial, nb, N, colsum);
   TZK_CHECK_LAUNCH("colsum_final_kernel");
   return 0;
 }

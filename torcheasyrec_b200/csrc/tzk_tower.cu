@@ -16,6 +16,45 @@ namespace {
 constexpr int kTM = 128;  // rows per tile == threads per CTA
 
 __device__ __forceinline__ int odd(int v) { return v | 1; }  // odd row stride: thread-per-row reads are conflict-free
+constexpr int kNW = kTM / 32;  // warps per CTA
+constexpr int kLU = 8;         // rows in flight per warp while a tile is loaded
+
+// global [rows x C] (row stride ld, C <= 64) -> shared [rows x S]: a warp per row, lanes over columns, kLU rows'
+// worth of independent loads issued before the first is consumed.  `mask` (nullable, row stride ld_m): values whose
+// mask entry is <= 0 are stored as 0 (ReLU backward).
+__device__ __forceinline__ void load_tile(float* dst, int S, const float* __restrict__ src, int64_t ld,
+                                          const float* __restrict__ mask, int64_t ld_m, int rows, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r0 = warp; r0 < rows; r0 += kNW * kLU) {
+    float v[kLU][2], m[kLU][2];
+#pragma unroll
+    for (int q = 0; q < kLU; ++q) {
+      const int r = r0 + q * kNW;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = lane + 32 * h;
+        const bool ok = r < rows && cc < C;
+        v[q][h] = ok ? __ldg(src + (int64_t)r * ld + cc) : 0.f;
+        m[q][h] = (ok && mask) ? __ldg(mask + (int64_t)r * ld_m + cc) : 1.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kLU; ++q) {
+      const int r = r0 + q * kNW;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = lane + 32 * h;
+        if (r < rows && cc < C) dst[r * S + cc] = m[q][h] > 0.f ? v[q][h] : 0.f;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void store_tile(float* __restrict__ dst, int64_t ld, const float* src, int S, int rows,
+                                           int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < rows; r += kNW)
+    for (int cc = lane; cc < C; cc += 32) dst[(int64_t)r * ld + cc] = src[r * S + cc];
+}
 
 // ---------------------------------------------------------------------------------------------------
 // forward: y = act(x @ W^T + b)          x [M,K]  W [N,K]  y [M,N]      K, N <= 64
@@ -41,16 +80,14 @@ small_linear_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t row0 = t * kTM;
     const int rows = (int)((M - row0) < kTM ? (M - row0) : kTM);
-    for (int i = tid; i < rows * K; i += kTM) {
-      const int r = i / K, k = i - r * K;
-      tile[r * TS + k] = __ldg(x + (row0 + r) * ld_x + k);
-    }
+    load_tile(tile, TS, x + row0 * ld_x, ld_x, nullptr, 0, rows, K);
     __syncthreads();
     float acc[NP];
 #pragma unroll
     for (int n = 0; n < NP; ++n) acc[n] = 0.f;
     if (tid < rows) {
       const float* xr = tile + tid * TS;
+#pragma unroll 4
       for (int k = 0; k < K; ++k) {
         const float xv = xr[k];
         const float4* wr = reinterpret_cast<const float4*>(Wt + k * NP);
@@ -76,10 +113,7 @@ small_linear_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
         }
     }
     __syncthreads();
-    for (int i = tid; i < rows * N; i += kTM) {
-      const int r = i / N, n = i - r * N;
-      y[(row0 + r) * ld_y + n] = tile[r * TS + n];
-    }
+    store_tile(y + row0 * ld_y, ld_y, tile, TS, rows, N);
     __syncthreads();
   }
 }
@@ -122,19 +156,12 @@ small_linear_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t row0 = t * kTM;
     const int rows = (int)((M - row0) < kTM ? (M - row0) : kTM);
-    for (int i = tid; i < rows * K; i += kTM) {
-      const int r = i / K, k = i - r * K;
-      xt[r * KS + k] = __ldg(x + (row0 + r) * ld_x + k);
-    }
-    for (int i = tid; i < rows * N; i += kTM) {
-      const int r = i / N, n = i - r * N;
-      float g = __ldg(dy + (row0 + r) * ld_dy + n);
-      if (relu && !(__ldg(y + (row0 + r) * ld_y + n) > 0.f)) g = 0.f;
-      dzt[r * NS + n] = g;
-    }
+    load_tile(xt, KS, x + row0 * ld_x, ld_x, nullptr, 0, rows, K);
+    load_tile(dzt, NS, dy + row0 * ld_dy, ld_dy, relu ? y + row0 * ld_y : nullptr, ld_y, rows, N);
     __syncthreads();
     // ---- dW += dz^T x over the tile's rows (ascending), db likewise ---------------------------------
     if (k0 < K && n0 < N) {
+#pragma unroll 4
       for (int r = 0; r < rows; ++r) {
         float a[NB], b[KB];
 #pragma unroll
@@ -147,8 +174,10 @@ small_linear_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
           for (int j = 0; j < KB; ++j) accW[i][j] = fmaf(a[i], b[j], accW[i][j]);
       }
     }
-    if (tid < N)
+    if (tid < N) {
+#pragma unroll 8
       for (int r = 0; r < rows; ++r) accB += dzt[r * NS + tid];
+    }
     // ---- dx = dz @ W : one thread per row ------------------------------------------------------------
     if (dx) {
       float acc[KP];
@@ -156,6 +185,7 @@ small_linear_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
       for (int k = 0; k < KP; ++k) acc[k] = 0.f;
       if (tid < rows) {
         const float* dr = dzt + tid * NS;
+#pragma unroll 2
         for (int n = 0; n < N; ++n) {
           const float dv = dr[n];
           const float4* wr = reinterpret_cast<const float4*>(Ws + n * KP);
@@ -177,10 +207,7 @@ small_linear_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
           if (k < K) xr[k] = acc[k];
       }
       __syncthreads();
-      for (int i = tid; i < rows * K; i += kTM) {
-        const int r = i / K, k = i - r * K;
-        dx[(row0 + r) * ld_dx + k] = xt[r * KS + k];
-      }
+      store_tile(dx + row0 * ld_dx, ld_dx, xt, KS, rows, K);
     }
     __syncthreads();
   }
@@ -195,15 +222,34 @@ small_linear_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
   if (tid < N) p[N * K + tid] = accB;
 }
 
+// out[i] = sum_c partial[c][i]: 32 outputs x 8 partial-groups per CTA; each thread adds its partials (c = g, g+8, ...)
+// with 4 loads in flight, the 8 group sums are folded in a fixed order -> deterministic.
 __global__ void __launch_bounds__(256)
 small_linear_reduce_kernel(const float* __restrict__ partial, int n_parts, int NK, int N, float* __restrict__ dw,
                            float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NK + N) return;
+  __shared__ float red[8][32];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;
+  const int total = NK + N;
   float s = 0.f;
-  for (int c = 0; c < n_parts; ++c) s += partial[(int64_t)c * (NK + N) + i];  // fixed order
-  if (i < NK) dw[i] = s;
-  else if (db) db[i - NK] = s;
+  if (i < total) {
+    int c = g;
+    for (; c + 24 < n_parts; c += 32) {
+      const float a0 = partial[(int64_t)c * total + i], a1 = partial[(int64_t)(c + 8) * total + i];
+      const float a2 = partial[(int64_t)(c + 16) * total + i], a3 = partial[(int64_t)(c + 24) * total + i];
+      s += a0; s += a1; s += a2; s += a3;
+    }
+    for (; c < n_parts; c += 8) s += partial[(int64_t)c * total + i];
+  }
+  red[g][o] = s;
+  __syncthreads();
+  if (g == 0 && i < total) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[k][o];
+    if (i < NK) dw[i] = r;
+    else if (db) db[i - NK] = r;
+  }
 }
 
 inline int pad_pow(int v, int lo) {  // smallest of {lo, 16, 32, 64} >= v
@@ -345,7 +391,7 @@ extern "C" int tzk_small_linear_bwd(const float* x, int64_t ld_x, const float* w
 #undef TZK_SLB
   TZK_CHECK_LAUNCH("small_linear_bwd_kernel");
   const int total = N * K + N;
-  small_linear_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, grid, N * K, N, dw, db);
+  small_linear_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(partial, grid, N * K, N, dw, db);
   TZK_CHECK_LAUNCH("small_linear_reduce_kernel");
   return 0;
 }

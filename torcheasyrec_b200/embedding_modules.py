@@ -13,6 +13,8 @@ from dataclasses import dataclass, field
 from enum import Enum
 from typing import Callable, Dict, List, Optional, Sequence
 
+import os
+
 import torch
 from torch import nn
 
@@ -201,6 +203,22 @@ class _ArenaCollection(nn.Module):
     def feature_names(self) -> List[str]:
         return self._feature_names
 
+    def _bwd_workspace(self, k, nnz: int) -> torch.Tensor:
+        """Private fused-backward workspace (the sorted keys live here between forward and backward)."""
+        need = k.fused_bwd_workspace_bytes(self.layout, nnz)
+        ws = getattr(self, "_bwd_ws", None)
+        if ws is None or ws.numel() < need or ws.device != self.weights.device:
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.weights.device)
+            self._bwd_ws = ws
+        return ws
+
+    def _side_stream(self) -> "torch.cuda.Stream":
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = torch.cuda.Stream(device=self.weights.device)
+            self._side = st
+        return st
+
     def _hook_tensor(self) -> torch.Tensor:
         # autograd needs one differentiable input to schedule the fused backward
         if self._hook is None or self._hook.device != self.weights.device:
@@ -216,25 +234,58 @@ class _ArenaCollection(nn.Module):
         return kjt.permute([pos[f] for f in self._feature_names])
 
 
+def _early_sort(ctx, mod, pooled: bool, ids, offsets, B) -> None:
+    """Enqueue the id-only half of the fused backward (linearize + radix sort) on the module's side stream right
+    away: it overlaps the rest of the forward pass and the dense backward instead of sitting on the critical path
+    (the role TrainPipelineSparseDist's data-dist stream plays in the reference, tzrec/utils/dist_util.py:221-303).
+    The backward then only joins the stream and runs the gradient-dependent half."""
+    ctx.early = None
+    k = Fn.backend()
+    if (mod.training and torch.is_grad_enabled() and ids.is_cuda and ids.numel() > 0
+            and hasattr(k, "fused_bwd_sort") and mod.optimizer is not None
+            and not getattr(mod, "_early_busy", False)      # one outstanding lookup per module owns the workspace
+            and os.environ.get("TZK_EARLY_SORT", "1") != "0"):
+        ws = mod._bwd_workspace(k, ids.numel())
+        side = mod._side_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            k.fused_bwd_sort(pooled, mod.layout, ids, offsets, B, ws)
+        ctx.early = (ws, side)
+        mod._early_busy = True
+
+
+def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> None:
+    spec = mod.optimizer
+    if spec is None:
+        raise RuntimeError(f"{who}.backward: no sparse optimizer set (call set_optimizer); tables are updated "
+                           "inside the backward kernel like the reference's fused TBE")
+    if not ids.numel():
+        return
+    k = Fn.backend()
+    if ctx.early is not None:
+        ws, side = ctx.early
+        mod._early_busy = False
+        torch.cuda.current_stream().wait_stream(side)
+        k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,
+                          ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws)
+    else:
+        k.fused_bwd(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, ids, offsets, ctx.B,
+                    spec.lr, spec.eps, mod.grad_scale)
+
+
 class _PooledLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hook, mod, ids, offsets, B):
         out = Fn.backend().pooled_gather_fwd(mod.weights.data, mod.layout, ids, offsets, B)
         ctx.mod, ctx.B = mod, B
         ctx.save_for_backward(ids, offsets)
+        _early_sort(ctx, mod, True, ids, offsets, B)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        mod = ctx.mod
         ids, offsets = ctx.saved_tensors
-        spec = mod.optimizer
-        if spec is None:
-            raise RuntimeError("EmbeddingBagCollection.backward: no sparse optimizer set (call set_optimizer); "
-                               "tables are updated inside the backward kernel like the reference's fused TBE")
-        if ids.numel():
-            Fn.backend().fused_bwd(spec.kind, True, Fn._rows_contig(grad_out), mod.weights.data, mod.opt_state,
-                                   mod.layout, ids, offsets, ctx.B, spec.lr, spec.eps, mod.grad_scale)
+        _fused_backward(ctx, ctx.mod, True, Fn._rows_contig(grad_out), ids, offsets, "EmbeddingBagCollection")
         return None, None, None, None, None
 
 
@@ -244,18 +295,13 @@ class _SeqLookup(torch.autograd.Function):
         out = Fn.backend().seq_gather_fwd(mod.weights.data, mod.layout, ids, offsets, B)
         ctx.mod, ctx.B = mod, B
         ctx.save_for_backward(ids, offsets)
+        _early_sort(ctx, mod, False, ids, offsets, B)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        mod = ctx.mod
         ids, offsets = ctx.saved_tensors
-        spec = mod.optimizer
-        if spec is None:
-            raise RuntimeError("EmbeddingCollection.backward: no sparse optimizer set (call set_optimizer)")
-        if ids.numel():
-            Fn.backend().fused_bwd(spec.kind, False, grad_out.contiguous(), mod.weights.data, mod.opt_state,
-                                   mod.layout, ids, offsets, ctx.B, spec.lr, spec.eps, mod.grad_scale)
+        _fused_backward(ctx, ctx.mod, False, grad_out.contiguous(), ids, offsets, "EmbeddingCollection")
         return None, None, None, None, None
 
 

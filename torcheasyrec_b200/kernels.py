@@ -209,6 +209,38 @@ class CudaKernels:
         # general path (unaligned / > 128 floats) = zero_counters, linearize, run_update, long_chunk, long_combine
         self.launches += 3 if (lay.vec_ok and lay.max_dim <= 128) else 5
 
+    def fused_bwd_workspace_bytes(self, lay: FeatureLayout, nnz: int) -> int:
+        return int(self._lib.tzk_fused_bwd_workspace_bytes(nnz, lay.total_keys, lay.max_dim))
+
+    def fused_bwd_sort(self, pooled: bool, lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor, B: int,
+                       ws: torch.Tensor) -> None:
+        """First half of fused_bwd (linearize + radix sort of (table,row) keys): needs only the ids, so callers run
+        it on a side stream while the forward pass is still going.  `ws` must stay untouched until fused_bwd_apply."""
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        nnz = ids.numel()
+        if ws.numel() < self.fused_bwd_workspace_bytes(lay, nnz):
+            raise TzkError("fused_bwd_sort: workspace too small")
+        check(self._lib.tzk_fused_bwd_sort(int(pooled), _ptr(lay.d_rows), _ptr(lay.d_key_base), _ptr(ids),
+                                           _ptr(offsets), lay.num_features, B, nnz, lay.total_keys, lay.max_dim,
+                                           _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_sort")
+        self.launches += 1
+
+    def fused_bwd_apply(self, optimizer: int, pooled: bool, grad_out: torch.Tensor, weights: torch.Tensor,
+                        state: Optional[torch.Tensor], lay: FeatureLayout, offsets: torch.Tensor, nnz: int, B: int,
+                        lr: float, eps: float, grad_scale: float, ws: torch.Tensor) -> None:
+        _need(weights, torch.float32, "weights")
+        _need(offsets, torch.int64, "offsets")
+        grad_out, ld = _rows2d(grad_out, "grad_out")
+        if state is not None:
+            _need(state, torch.float32, "state")
+        check(self._lib.tzk_fused_bwd_apply(
+            optimizer, int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
+            _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(offsets), lay.num_features, B, nnz,
+            lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
+            _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_apply")
+        self.launches += 2 if (lay.vec_ok and lay.max_dim <= 128) else 4
+
     # ------------------------------------------------------------------ K1 / K2
     def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
                      feat_block: torch.Tensor, want_pos: bool = False, feat_owner: Optional[torch.Tensor] = None,
