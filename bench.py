@@ -32,11 +32,10 @@ import torch  # noqa: E402
 
 METRIC = "samples/sec (DLRM-Criteo synth, train step fwd+bwd+optimizer)"
 UNIT = "samples/s"
-ROW_BYTES_PER_SAMPLE = 26 * 16 * 4                       # 1664 B: SURVEY.md §8d "gather HBM GB/s" numerator
-GATHER_BYTES_PER_SAMPLE = 1664 + 1664 + 26 * 8 + 26 * 4   # rows + pooled write + ids + lengths = 3640 B
-BWD_BYTES_PER_SAMPLE = 1664 + 26 * 4 * 64 + 26 * 8        # grad read + w/state RMW (U=26) + ids = 8528 B
-NCU_TRAFFIC_BYTES = {"pooled_gather_fwd_kernel": 110.476032e6 + 58.848512e6,   # dram rd + wr, one launch
-                     "run_update_kernel": 282.46656e6 + 50.44352e6}
+# DLRM-Criteo (F=26, L=1, D=16) per-sample algorithmic bytes, SURVEY.md §8d — computed from the layout at run time:
+#   gather 1664 rows + 1664 pooled write + 208 ids + 104 lengths = 3640 B; backward 1664 grad + 26*4*64 RMW + 208 = 8528 B
+NCU_TRAFFIC_BYTES = {"pooled_gather_fwd_kernel": 111.339008e6 + 55.679232e6,   # dram rd + wr, one launch (ncu --set full)
+                     "tile_update_kernel": None}
 
 
 def parse_args():
@@ -52,6 +51,7 @@ def parse_args():
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through the steps")
     ap.add_argument("--cpu-batch", type=int, default=8192, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-zipf", action="store_true", help="skip the second (Zipf-id) timing of the same step")
     ap.add_argument("--sharded-mode", default="graph", choices=["graph", "eager"],
                     help="N>1: 'graph' = static-capacity exchange captured in one CUDA graph, 'eager' = dynamic splits")
     ap.add_argument("--static-capacity", type=float, default=1.5)
@@ -139,6 +139,7 @@ def cpu_step_rate(model: str, batch: int, steps: int, warmup: int, max_rows: int
 
 def run_reference(args):
     rank, _, world = dist_env()
+    args._zipf_ms = zipf
     if rank != 0:
         return
     import psutil
@@ -257,6 +258,24 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    # ---- second id distribution (SURVEY.md §8d reports both): the same captured step on Zipf(1.05) ids -------
+    zipf = None
+    if args.id_dist == "uniform" and not args.no_zipf and not sharded:   # (row-wise blocks + Zipf overflow a fixed wire capacity)
+        zring = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + 500 + i, id_dist="zipf").to(dev)
+                 for i in range(min(args.ring, 4))]
+        for i in range(3):
+            step.load(zring[i % len(zring)])
+            step.replay()
+        barrier()
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record()
+        for i in range(K):
+            step.load(zring[i % len(zring)])
+            step.replay()
+        z1.record()
+        barrier()
+        zipf = z0.elapsed_time(z1)
+        del zring
     # ---- e2e: pinned host batch -> H2D -> step -> loss back on the host, every step --------------------------
     # (N=1: the H2D of batch i+1 runs on the copy stream while step i computes; the loss of every step is read)
     piped = graphed
@@ -285,9 +304,10 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, zipf or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = t.tolist()
+        ms_total, ms_e2e, zz = t.tolist()
+        zipf = zz if zipf is not None else None
     if rank != 0:
         return
 
@@ -298,40 +318,76 @@ def run_ours(args):
         return
     ebc = pipe.model.sparse_collections()[0]
     lay = ebc.layout
-    offs = [kern.lengths_to_offsets(b.sparse_features["__BASE__"].lengths()) for b in ring]
-    ids = [b.sparse_features["__BASE__"].values() for b in ring]
+    dg = sorted(ring[0].sparse_features)[0]
+    kjts = [ebc._select(b.sparse_features[dg]) for b in ring]
+    offs = [kern.lengths_to_offsets(k.lengths()) for k in kjts]
+    ids = [k.values() for k in kjts]
     out = torch.empty((B, lay.total_dim), device=dev)
     grad = torch.randn((B, lay.total_dim), device=dev) * 1e-3
     R = len(ring)
     it = max(K, 10)
-    fwd_ms = time_kernel(lambda i: kern.pooled_gather_fwd(ebc.weights.data, lay, ids[i % R], offs[i % R], B, out), it)
+    # algorithmic bytes per sample of THIS collection and batch: rows + pooled write + ids + lengths;
+    # backward: gradient read + weight/state read+write of every looked-up row (U = upper bound: no duplicates) + ids
+    nnz_f = [float(k.length_per_key()[f]) / B for f in range(lay.num_features)]
+    row_b = sum(l * d * 4 for l, d in zip(nnz_f, lay.dim))
+    gather_b = row_b + sum(d * 4 for d in lay.dim) + sum(l * 8 for l in nnz_f) + 4 * lay.num_features
     spec = ebc.optimizer
+    state_mult = {0: 2, 1: 4, 2: 2}[spec.kind]          # SGD w r+w; Adagrad w+state r+w; row-wise: w r+w (+8 B/row)
+    bwd_b = sum(d * 4 for d in lay.dim) + state_mult * row_b + sum(l * 8 for l in nnz_f) + \
+        (8 * sum(nnz_f) if spec.kind == 2 else 0)
+    fwd_ms = time_kernel(lambda i: kern.pooled_gather_fwd(ebc.weights.data, lay, ids[i % R], offs[i % R], B, out), it)
     bwd_ms = time_kernel(lambda i: kern.fused_bwd(spec.kind, True, grad, ebc.weights.data, ebc.opt_state, lay,
                                                   ids[i % R], offs[i % R], B, spec.lr, spec.eps, 1.0), it)
+    # the same backward in its two halves: the id-only half (linearize + radix sort) runs on a side stream during
+    # the forward pass inside the step, the gradient half is what sits on the step's critical path
+    ws_b = torch.empty(kern.fused_bwd_workspace_bytes(lay, ids[0].numel()), dtype=torch.uint8, device=dev)
+    sort_ms = time_kernel(lambda i: kern.fused_bwd_sort(True, lay, ids[i % R], offs[i % R], B, ws_b), it)
+    kern.fused_bwd_sort(True, lay, ids[0], offs[0], B, ws_b)
+    apply_ms = time_kernel(lambda i: kern.fused_bwd_apply(spec.kind, True, grad, ebc.weights.data, ebc.opt_state, lay,
+                                                          offs[0], ids[0].numel(), B, spec.lr, spec.eps, 1.0, ws_b), it)
     peak, peak_src = measured_peak_gbs()
-    fwd_gbs = GATHER_BYTES_PER_SAMPLE * B / (fwd_ms * 1e-3) / 1e9
-    bwd_gbs = BWD_BYTES_PER_SAMPLE * B / (bwd_ms * 1e-3) / 1e9
-    dominant = "tzk_fused_bwd (linearize + radix sort + run_update)" if bwd_ms > fwd_ms else "pooled_gather_fwd_kernel"
+    fwd_gbs = gather_b * B / (fwd_ms * 1e-3) / 1e9
+    bwd_gbs = bwd_b * B / (bwd_ms * 1e-3) / 1e9
+    dominant = ("tzk_fused_bwd (linearize + radix sort + tile_update + carry_combine)" if bwd_ms > fwd_ms
+                else "pooled_gather_fwd_kernel")
     ach = bwd_gbs if bwd_ms > fwd_ms else fwd_gbs
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture
-    # (profiles/r1_ncu_full_top_kernels.csv; only valid for the workload it was captured on)
+    # (profiles/; only valid for the workload it was captured on)
     std = (args.model == "dlrm_criteo" and B == 65536 and not args.max_rows and args.id_dist == "uniform")
     traffic = None
     if std:
-        traffic = (NCU_TRAFFIC_BYTES["run_update_kernel"] if bwd_ms > fwd_ms else NCU_TRAFFIC_BYTES["pooled_gather_fwd_kernel"])
+        traffic = (NCU_TRAFFIC_BYTES["tile_update_kernel"] if bwd_ms > fwd_ms else NCU_TRAFFIC_BYTES["pooled_gather_fwd_kernel"])
+    kernels = {
+        "pooled_gather_fwd": {"ms": fwd_ms, "algorithmic_GBps": fwd_gbs, "frac": fwd_gbs / peak,
+                              "row_read_GBps": row_b * B / (fwd_ms * 1e-3) / 1e9, "bytes_per_sample": gather_b},
+        "fused_bwd": {"ms": bwd_ms, "algorithmic_GBps": bwd_gbs, "frac": bwd_gbs / peak, "bytes_per_sample": bwd_b,
+                      "sort_ms": sort_ms, "apply_ms": apply_ms,
+                      "apply_frac": bwd_b * B / (apply_ms * 1e-3) / 1e9 / peak,
+                      "note": "sort_ms overlaps the forward pass inside the step (side stream); apply_ms is the part on "
+                              "the critical path"},
+    }
+    if args.model == "dlrm_criteo":
+        Ns, D = lay.num_features, lay.dim[0]
+        N = Ns + 1
+        P = N * (N - 1) // 2
+        dense16 = torch.randn(B, D, device=dev)
+        sp = torch.randn(B, Ns * D, device=dev)
+        d_out = torch.randn(B, P + 1 + D + Ns * D, device=dev)
+        if_ms = time_kernel(lambda i: kern.dot_interact_fwd(dense16, sp, Ns, D, True, True, 4, 1), it)
+        ib_ms = time_kernel(lambda i: kern.dot_interact_bwd(dense16, sp, d_out, Ns, D, True, True, 1), it)
+        if_b = (N * D + P + D + Ns * D) * 4           # X in, [P | D | Ns*D] out  (1728 + 3132)
+        ib_b = (N * D) * 4 * 2 + (P + D + Ns * D) * 4  # X in, d_out in, dX out
+        kernels["dot_interact_fwd"] = {"ms": if_ms, "algorithmic_GBps": if_b * B / (if_ms * 1e-3) / 1e9,
+                                       "frac": if_b * B / (if_ms * 1e-3) / 1e9 / peak, "bytes_per_sample": if_b}
+        kernels["dot_interact_bwd"] = {"ms": ib_ms, "algorithmic_GBps": ib_b * B / (ib_ms * 1e-3) / 1e9,
+                                       "frac": ib_b * B / (ib_ms * 1e-3) / 1e9 / peak, "bytes_per_sample": ib_b}
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": traffic, "traffic_note": "bytes/launch of run_update_kernel (the dominant kernel of the fused "
-        "backward) from profiles/r1_ncu_full_top_kernels.csv" if (std and bwd_ms > fwd_ms) else None,
+        "traffic": traffic, "traffic_note": "dram bytes/launch of the dominant kernel from the ncu --set full capture "
+        "summarised in profiles/" if traffic else None,
         "peak_source": peak_src,
-        "kernels": {
-            "pooled_gather_fwd": {"ms": fwd_ms, "algorithmic_GBps": fwd_gbs, "frac": fwd_gbs / peak,
-                                  "row_read_GBps": ROW_BYTES_PER_SAMPLE * B / (fwd_ms * 1e-3) / 1e9,
-                                  "bytes_per_sample": GATHER_BYTES_PER_SAMPLE},
-            "fused_bwd_adagrad": {"ms": bwd_ms, "algorithmic_GBps": bwd_gbs, "frac": bwd_gbs / peak,
-                                  "bytes_per_sample": BWD_BYTES_PER_SAMPLE},
-        },
-        "share_of_step": {"pooled_gather_fwd": fwd_ms / (ms_total / K), "fused_bwd_adagrad": bwd_ms / (ms_total / K)},
+        "kernels": kernels,
+        "share_of_step": {k: v["ms"] / (ms_total / K) for k, v in kernels.items()},
     }
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -366,6 +422,9 @@ def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step,
                                  if args.sharded_mode == "graph" else "dynamic splits (host read per step)"))},
         "e2e": {"value": global_batch * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last},
+        "zipf_ids": (None if getattr(args, "_zipf_ms", None) is None else
+                     {"value": global_batch * K / (args._zipf_ms * 1e-3), "unit": UNIT,
+                      "ms_per_step": args._zipf_ms / K, "note": "same step, ids ~ Zipf(1.05) clipped to each table"}),
         "gpu_launches": launches_per_step * K,
         "gpu_launches_per_step": launches_per_step,
         "clocks": clk,

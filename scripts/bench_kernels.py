@@ -5,7 +5,7 @@ import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] == "one":
     import torch
     from torcheasyrec_b200.example_configs import CRITEO_HASH_SIZES
     from torcheasyrec_b200.kernels import OPT_ADAGRAD, build_layout, default_kernels
@@ -21,8 +21,10 @@ if len(sys.argv) > 1:
     out = torch.empty((B, F * D), device=dev)
     grad = torch.randn((B, F * D), device=dev) * 1e-3
 
-    def timeit(fn, n=20):
-        for i in range(3): fn(i)
+    ITERS = int(os.environ.get("TZK_BENCH_ITERS", "20"))      # 1 = a single launch of everything (ncu captures)
+
+    def timeit(fn, n=ITERS):
+        for i in range(3 if n > 1 else 0): fn(i)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         torch.cuda.synchronize()
         for i in range(n):
@@ -30,7 +32,7 @@ if len(sys.argv) > 1:
         torch.cuda.synchronize()
         ts = sorted(a.elapsed_time(b) for a, b in ev)
         return ts[len(ts) // 2] * 1e3
-    res = {"bwd_tile": os.environ.get("TZK_BWD_TILE", "1"), "id_dist": os.environ.get("TZK_ID_DIST", "uniform")}
+    res = {"bwd_tile": os.environ.get("TZK_BWD_TILE", "0"), "id_dist": os.environ.get("TZK_ID_DIST", "uniform")}
     if res["id_dist"] == "zipf":       # Zipf(1.05)-like skew: hot ids repeat inside a batch
         def zipf(h):
             u = torch.rand(B, device=dev, generator=g)
@@ -38,8 +40,23 @@ if len(sys.argv) > 1:
         ids = [torch.cat([zipf(float(h)) for h in CRITEO_HASH_SIZES]) for _ in range(R)]
     res["gather_us"] = timeit(lambda i: k.pooled_gather_fwd(arena, lay, ids[i % R], offs, B, out))
     res["fused_bwd_us"] = timeit(lambda i: k.fused_bwd(OPT_ADAGRAD, True, grad, arena, state, lay, ids[i % R], offs, B, 1e-3, 1e-8, 1.0))
+    if os.environ.get("TZK_BENCH_MIN"):
+        print(json.dumps(res)); sys.exit(0)
+    # DLRM interaction (fwd / bwd) at the bench shape, and the narrow tower layers
+    dense16 = torch.randn(B, 16, device=dev)
+    sparse = torch.randn(B, F * D, device=dev)
+    res["interact_occ"] = os.environ.get("TZK_INTERACT_OCC", "4")
+    res["small_fwd"] = os.environ.get("TZK_SMALL_FWD", "rows")
+    res["interact_fwd_us"] = timeit(lambda i: k.dot_interact_fwd(dense16, sparse, F, D, True, True, 4, 1))
+    d_out = torch.randn(B, 784, device=dev)
+    res["interact_bwd_us"] = timeit(lambda i: k.dot_interact_bwd(dense16, sparse, d_out, F, D, True, True, 1))
+    for (K, N) in ((13, 64), (64, 16), (64, 32), (32, 1)):
+        x = torch.randn(B, K, device=dev); w = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
+        y = k.small_linear_fwd(x, w, b, True); dy = torch.randn(B, N, device=dev)
+        res[f"lin{K}x{N}_fwd_us"] = timeit(lambda i: k.small_linear_fwd(x, w, b, True))
+        res[f"lin{K}x{N}_bwd_us"] = timeit(lambda i: k.small_linear_bwd(x, w, y, dy, True, True, True))
     print(json.dumps(res))
 else:
-    for tile, dist in (("1", "uniform"), ("0", "uniform"), ("1", "zipf"), ("0", "zipf")):
-        env = dict(os.environ, TZK_BWD_TILE=tile, TZK_ID_DIST=dist)
+    for tile, dist, occ, fwd in (("0", "uniform", "4", "rows"), ("1", "uniform", "3", "tile"), ("0", "zipf", "4", "rows")):
+        env = dict(os.environ, TZK_BWD_TILE=tile, TZK_ID_DIST=dist, TZK_INTERACT_OCC=occ, TZK_SMALL_FWD=fwd)
         subprocess.run([sys.executable, __file__, "one"], env=env)

@@ -60,6 +60,14 @@ def test_lengths_to_offsets_bit_exact(kernels, n):
     np.testing.assert_array_equal(got, O.lengths_to_offsets(lengths))
 
 
+@pytest.fixture(params=["general", "tile"])
+def bwd_path(request, monkeypatch):
+    """Both implementations of the gradient half of tzk_fused_bwd (csrc/tzk_bwd.cu): the general run kernels
+    (default) and the shared-memory tile path (TZK_BWD_TILE=1)."""
+    monkeypatch.setenv("TZK_BWD_TILE", "1" if request.param == "tile" else "0")
+    return request.param
+
+
 CASES = {
     # name: (rows, dims, feat_table, B, max_len)
     "criteo_like_L1": ([1000] * 6, [16] * 6, list(range(6)), 300, None),
@@ -120,7 +128,7 @@ def test_seq_gather_fwd(kernels):
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("opt", [O.OPT_SGD, O.OPT_ADAGRAD, O.OPT_ROWWISE_ADAGRAD])
 @pytest.mark.parametrize("pool", [O.POOL_SUM, O.POOL_MEAN])
-def test_fused_bwd(kernels, case, opt, pool):
+def test_fused_bwd(kernels, case, opt, pool, bwd_path):
     rows, dims, feat_table, B, max_len = CASES[case]
     rng = np.random.default_rng(zlib.crc32(case.encode()) % 1000 + 17)
     tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
@@ -161,7 +169,7 @@ def test_fused_bwd(kernels, case, opt, pool):
         np.testing.assert_allclose(state.cpu().numpy(), np.concatenate(st_np), rtol=state_rtol, atol=1e-7)
 
 
-def test_fused_bwd_is_run_to_run_deterministic(kernels):
+def test_fused_bwd_is_run_to_run_deterministic(kernels, bwd_path):
     rng = np.random.default_rng(9)
     rows, dims, feat_table, B = [3, 7, 5000], [16, 16, 16], [0, 1, 2], 4096
     tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
@@ -178,7 +186,7 @@ def test_fused_bwd_is_run_to_run_deterministic(kernels):
     np.testing.assert_array_equal(res[0], res[2])
 
 
-def test_fused_bwd_sequence_layout(kernels):
+def test_fused_bwd_sequence_layout(kernels, bwd_path):
     rng = np.random.default_rng(21)
     rows, dims, feat_table, B = [400, 30, 400], [16, 16, 16], [0, 1, 2], 64
     tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
@@ -335,7 +343,7 @@ def test_dlrm_fused_interaction_vs_reference_golden_and_oracle(kernels):
     np.testing.assert_allclose(ds.cpu().numpy(), ws, rtol=1e-5, atol=2e-5)
 
 
-def test_fused_bwd_ignores_zero_row_padding_features(kernels):
+def test_fused_bwd_ignores_zero_row_padding_features(kernels, bwd_path):
     """Static-capacity exchange: ids of a zero-row feature are wire padding — sorted last, never applied."""
     from torcheasyrec_b200.kernels import FeatureLayout
 

@@ -1,6 +1,8 @@
 // tzk_dense.cu — K6 regroup (column gather-sum), K7 jagged<->padded, A7 FM, A9/A10 DLRM dot interaction.
 // All HBM-bound fp32 movers; the interaction is 7.4 FLOP/B so it is written as a
 // register-tiled FFMA kernel that reads each pooled row once and emits the whole final-MLP input.
+#include <cstdlib>
+
 #include "tzk_common.cuh"
 
 using namespace tzk;
@@ -135,24 +137,43 @@ __device__ __forceinline__ int swz_mask(int D4) {  // XOR range must stay inside
 // float offset of chunk c4 of row `row`
 __device__ __forceinline__ int xoff(int row, int c4, int DS, int swm) { return row * DS + ((c4 ^ ((row >> 3) & swm)) << 2); }
 
+// All row loads of a sample are issued before the first one is consumed (4 float4 per lane cover Ns*D/4 <= 128
+// chunks in one batch): one exposed memory latency per sample instead of one per 32 chunks.
 __device__ __forceinline__ void stage_x(float* X, const float* dense, int64_t ld_dense, const float* sparse,
                                         int64_t ld_sparse, int64_t b, int Ns, int N, int Np, int D4, int DS, int swm,
                                         int lane) {
   const int doff = dense ? 1 : 0;
   const float* sp = sparse + b * ld_sparse;
-  for (int i = lane; i < Ns * D4; i += 32) {
-    const int r = i / D4, c4 = i - r * D4;
-    *reinterpret_cast<float4*>(X + xoff(r + doff, c4, DS, swm)) = ld_row_f4(sp + (int64_t)r * (D4 * 4) + c4 * 4);
+  const int n_chunks = Ns * D4;
+  float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool has_dv = dense && lane < D4;
+  if (has_dv) dv = ld_row_f4(dense + b * ld_dense + lane * 4);
+  for (int i0 = lane; i0 < n_chunks; i0 += 128) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + 32 * q;
+      if (i < n_chunks) v[q] = ld_row_f4(sp + (int64_t)i * 4);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + 32 * q;
+      if (i < n_chunks) {
+        const int r = i / D4, c4 = i - r * D4;
+        *reinterpret_cast<float4*>(X + xoff(r + doff, c4, DS, swm)) = v[q];
+      }
+    }
   }
+  if (has_dv) *reinterpret_cast<float4*>(X + xoff(0, lane, DS, swm)) = dv;
   if (dense)
-    for (int c4 = lane; c4 < D4; c4 += 32)
+    for (int c4 = lane + 32; c4 < D4; c4 += 32)
       *reinterpret_cast<float4*>(X + xoff(0, c4, DS, swm)) = ld_row_f4(dense + b * ld_dense + c4 * 4);
 }
 
 // DT = compile-time embedding dim (0 = take the runtime value): with DT known every /D, %D and swizzle offset
 // folds into shifts and the k loop unrolls — the kernel is issue-bound, not bandwidth-bound, otherwise.
-template <int DT>
-__global__ void __launch_bounds__(kIWarps * 32)
+template <int DT, bool ONE, int OCC>
+__global__ void __launch_bounds__(kIWarps * 32, OCC)
 dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
                         int64_t ld_sparse, int64_t B, int Ns, int D_rt, int copy_dense, int copy_sparse, int p_pad,
                         int aligned, float* __restrict__ out, int64_t ld_out) {
@@ -185,11 +206,69 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
   }
   __syncthreads();
   const int doff = dense ? 1 : 0;
+  // lane-constant block description (used when the triangle has at most 32 blocks, e.g. N = 27 -> 28)
+  constexpr bool one_block = ONE;   // host guarantees n_blocks <= 32 when ONE
+  int lb_a = 0, lb_b = 0, lb_asw = 0, lb_bsw = 0, lb_o[4] = {0, 0, 0, 0};
+  unsigned lb_valid = 0;
+  if (one_block && lane < n_blocks) {
+    const int bi = blk_ij[lane] >> 8, bj = blk_ij[lane] & 0xff;
+    lb_a = bi * 4 * DS;
+    lb_b = bj * 4 * DS;
+    lb_asw = ((bi * 4) >> 3) & swm;   // the 4 rows of a block share (row >> 3)
+    lb_bsw = ((bj * 4) >> 3) & swm;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = bi * 4 + r;
+      lb_o[r] = i * N - (i * (i + 1)) / 2 + (bj * 4 - i - 1);   // tri_index(i, bj*4 + c) = lb_o[r] + c
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = bj * 4 + c;
+        if (i < j && j < N) lb_valid |= 1u << (r * 4 + c);
+      }
+    }
+  }
 
   for (int64_t b = (int64_t)blockIdx.x * kIWarps + warp; b < B; b += (int64_t)gridDim.x * kIWarps) {
     stage_x(X, dense, ld_dense, sparse, ld_sparse, b, Ns, N, Np, D4, DS, swm, lane);
     __syncwarp();
     // ---- Gram blocks ------------------------------------------------------------------------------
+    if constexpr (one_block) {
+      // every lane owns at most ONE block for the whole kernel: addresses, swizzles and output slots were
+      // computed once before the sample loop
+      if (lane < n_blocks) {
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        const float* pa = X + lb_a;
+        const float* pb = X + lb_b;
+#pragma unroll DT ? DT / 4 : 1
+        for (int c4 = 0; c4 < D4; ++c4) {
+          const int oa = (c4 ^ lb_asw) << 2, ob = (c4 ^ lb_bsw) << 2;
+          float4 a[4], bb[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            a[r] = *reinterpret_cast<const float4*>(pa + r * DS + oa);
+            bb[r] = *reinterpret_cast<const float4*>(pb + r * DS + ob);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              acc[r][c] = fmaf(a[r].x, bb[c].x, acc[r][c]);
+              acc[r][c] = fmaf(a[r].y, bb[c].y, acc[r][c]);
+              acc[r][c] = fmaf(a[r].z, bb[c].z, acc[r][c]);
+              acc[r][c] = fmaf(a[r].w, bb[c].w, acc[r][c]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if ((lb_valid >> (r * 4 + c)) & 1) O[lb_o[r] + c] = acc[r][c];
+      }
+    } else {
     for (int blk = lane; blk < n_blocks; blk += 32) {
       const int bi = blk_ij[blk] >> 8, bj = blk_ij[blk] & 0xff;
       float acc[4][4];
@@ -235,6 +314,7 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
           if (i < j && j < N) O[tri_index(i, j, N)] = acc[r][c];
         }
     }
+    }
     __syncwarp();
     // ---- coalesced output row ---------------------------------------------------------------------
     float* orow = out + b * ld_out;
@@ -276,7 +356,7 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
 
 // backward: dX = (G + G^T) X (+ pass-through grads); lane owns 4 rows x 4 cols blocks of dX.
 template <int DT>
-__global__ void __launch_bounds__(kIWarps * 32)
+__global__ void __launch_bounds__(kIWarps * 32, 4)
 dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
                         int64_t ld_sparse, const float* __restrict__ d_out, int64_t ld_dout, int64_t B,
                         int Ns, int D_rt, int copy_dense, int copy_sparse, int p_pad, int aligned,
@@ -314,11 +394,22 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
   for (int64_t b = (int64_t)blockIdx.x * kIWarps + warp; b < B; b += (int64_t)gridDim.x * kIWarps) {
     stage_x(X, dense, ld_dense, sparse, ld_sparse, b, Ns, N, Np, D4, DS, swm, lane);
     const float* go = d_out + b * ld_dout;
-    for (int idx = lane; idx < P; idx += 32) {  // coalesced read of d_out, symmetric scatter
-      const int i = pair_ij[idx] >> 8, j = pair_ij[idx] & 0xff;
-      const float g = __ldg(go + idx);
-      S[i * SS + j] = g;
-      S[j * SS + i] = g;
+    for (int idx0 = lane; idx0 < P; idx0 += 32 * 6) {  // coalesced read of d_out (6 loads in flight), symmetric scatter
+      float gv[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int idx = idx0 + 32 * q;
+        gv[q] = idx < P ? __ldg(go + idx) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int idx = idx0 + 32 * q;
+        if (idx < P) {
+          const int i = pair_ij[idx] >> 8, j = pair_ij[idx] & 0xff;
+          S[i * SS + j] = gv[q];
+          S[j * SS + i] = gv[q];
+        }
+      }
     }
     __syncwarp();
     // dX[i0..i0+3][k..k+3] = sum_j S[j][i0..i0+3] * X[j][k..k+3]
@@ -472,13 +563,31 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int aligned = (((P + p_pad) % 4) == 0) && (ld_out % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const int nb = Np / 4, n_blocks = nb * (nb + 1) / 2;
   size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3 + 4) & ~3))) * sizeof(float);
-#define TZK_IFWD(DT_)                                                                                         \
+#define TZK_IFWD3(DT_, ONE_, OCC_)                                                                             \
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
-      cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    dot_interact_fwd_kernel<DT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>( \
+      cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_, ONE_, OCC_>,                                         \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+    dot_interact_fwd_kernel<DT_, ONE_, OCC_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem,    \
+                                               as_stream(stream)>>>(                                         \
         dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, p_pad, aligned, out, ld_out); \
   } while (0)
+#define TZK_IFWD2(DT_, ONE_)                    \
+  do {                                          \
+    if (occ4) TZK_IFWD3(DT_, ONE_, 4);          \
+    else TZK_IFWD3(DT_, ONE_, 3);               \
+  } while (0)
+#define TZK_IFWD(DT_)                          \
+  do {                                         \
+    if (n_blocks <= 32) TZK_IFWD2(DT_, true);  \
+    else TZK_IFWD2(DT_, false);                \
+  } while (0)
+  // occupancy target of the forward kernel: 3 CTAs/SM (80 registers) or 4 (64 registers, a few spills; default); tunable for
+  // experiments with TZK_INTERACT_OCC=3|4
+  static const bool occ4 = [] {
+    const char* e = getenv("TZK_INTERACT_OCC");
+    return !(e && e[0] == '3');      // measured: 105 us (4 CTAs/SM) vs 127 us (3) at B=65536, N=27, D=16
+  }();
   switch (D) {
     case 8: TZK_IFWD(8); break;
     case 16: TZK_IFWD(16); break;
@@ -487,6 +596,8 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
     default: TZK_IFWD(0); break;
   }
 #undef TZK_IFWD
+#undef TZK_IFWD2
+#undef TZK_IFWD3
   TZK_CHECK_LAUNCH("dot_interact_fwd_kernel");
   return 0;
 }

@@ -8,6 +8,8 @@
 // backward: the weight matrix lives in shared memory, a CTA walks 128-row tiles, one thread owns one row.
 // Plain fp32 FFMA in ascending-k order (the reference runs these layers as fp32 SIMT GEMMs, TF32 off).
 // Weight / bias gradients are summed per CTA and then across CTAs in a fixed order: run-to-run deterministic.
+#include <cstdlib>
+
 #include "tzk_common.cuh"
 
 using namespace tzk;
@@ -17,7 +19,7 @@ constexpr int kTM = 128;  // rows per tile == threads per CTA
 
 __device__ __forceinline__ int odd(int v) { return v | 1; }  // odd row stride: thread-per-row reads are conflict-free
 constexpr int kNW = kTM / 32;  // warps per CTA
-constexpr int kLU = 8;         // rows in flight per warp while a tile is loaded
+constexpr int kLU = 16;        // rows in flight per warp while a tile is loaded
 
 // global [rows x C] (row stride ld, C <= 64) -> shared [rows x S]: a warp per row, lanes over columns, kLU rows'
 // worth of independent loads issued before the first is consumed.  `mask` (nullable, row stride ld_m): values whose
@@ -70,9 +72,11 @@ small_linear_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
   float* tile = bs + NP;      // [kTM][TS]
   const int TS = odd(K > N ? K : N);
   const int tid = threadIdx.x;
-  for (int i = tid; i < K * NP; i += kTM) {
-    const int k = i / NP, n = i - k * NP;
-    Wt[i] = n < N ? __ldg(w + (int64_t)n * K + k) : 0.f;
+  for (int i = tid; i < K * NP; i += kTM) Wt[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < N * K; i += kTM) {   // coalesced read of w[N][K], transposed into Wt[K][NP]
+    const int n = i / K, k = i - n * K;
+    Wt[k * NP + n] = __ldg(w + i);
   }
   for (int i = tid; i < NP; i += kTM) bs[i] = (bias && i < N) ? __ldg(bias + i) : 0.f;
   __syncthreads();
@@ -115,6 +119,92 @@ small_linear_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
     __syncthreads();
     store_tile(y + row0 * ld_y, ld_y, tile, TS, rows, N);
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward, warp-independent variant: one thread per row, no tile staging and no barrier after the weight matrix is
+// in shared memory.  A thread reads its own row straight from global memory (the 32 rows of a warp are one
+// contiguous 32*K*4-byte span, so every sector that is fetched is fully consumed through L1 over the k loop) and
+// writes its own output row with 16-B stores.  Many independent warps per SM hide the load latency.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRowThreads = 128;
+template <int NP, bool VEC>
+__global__ void __launch_bounds__(kRowThreads, 5)
+small_linear_fwd_rows_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
+                             const float* __restrict__ bias, int64_t M, int K, int N, int relu,
+                             float* __restrict__ y, int64_t ld_y) {
+  constexpr int NH = NP < 32 ? NP : 32;   // outputs per pass: 32 accumulators keep 6 CTAs (24 warps) per SM resident
+  extern __shared__ __align__(16) float sm[];
+  float* Wt = sm;             // [K][NP], zero beyond N
+  float* bs = Wt + K * NP;    // [NP]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * NP; i += kRowThreads) Wt[i] = 0.f;
+  for (int i = tid; i < NP; i += kRowThreads) bs[i] = (bias && i < N) ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  for (int i = tid; i < N * K; i += kRowThreads) {
+    const int n = i / K, k = i - n * K;
+    Wt[k * NP + n] = __ldg(w + i);
+  }
+  __syncthreads();
+  const bool vec_out = (N & 3) == 0 && (ld_y & 3) == 0 && ((uintptr_t)y & 15) == 0;
+  for (int64_t row = (int64_t)blockIdx.x * kRowThreads + tid; row < M; row += (int64_t)gridDim.x * kRowThreads) {
+    const float* xr = x + row * ld_x;
+    float* yr = y + row * ld_y;
+#pragma unroll 1
+    for (int n0 = 0; n0 < NP; n0 += NH) {   // second pass re-reads the row from L1
+      if (n0 >= N) break;
+      float acc[NH];
+#pragma unroll
+      for (int n = 0; n < NH; ++n) acc[n] = bs[n0 + n];
+      if (VEC) {   // K % 4 == 0, rows 16-B aligned
+        for (int k0 = 0; k0 < K; k0 += 4) {
+          const float4 xv4 = *reinterpret_cast<const float4*>(xr + k0);
+          const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float4* wr = reinterpret_cast<const float4*>(Wt + (k0 + kk) * NP + n0);
+#pragma unroll
+            for (int n4 = 0; n4 < NH / 4; ++n4) {
+              const float4 w4 = wr[n4];
+              acc[n4 * 4 + 0] = fmaf(xv[kk], w4.x, acc[n4 * 4 + 0]);
+              acc[n4 * 4 + 1] = fmaf(xv[kk], w4.y, acc[n4 * 4 + 1]);
+              acc[n4 * 4 + 2] = fmaf(xv[kk], w4.z, acc[n4 * 4 + 2]);
+              acc[n4 * 4 + 3] = fmaf(xv[kk], w4.w, acc[n4 * 4 + 3]);
+            }
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+          const float xv = xr[k];
+          const float4* wr = reinterpret_cast<const float4*>(Wt + k * NP + n0);
+#pragma unroll
+          for (int n4 = 0; n4 < NH / 4; ++n4) {
+            const float4 w4 = wr[n4];
+            acc[n4 * 4 + 0] = fmaf(xv, w4.x, acc[n4 * 4 + 0]);
+            acc[n4 * 4 + 1] = fmaf(xv, w4.y, acc[n4 * 4 + 1]);
+            acc[n4 * 4 + 2] = fmaf(xv, w4.z, acc[n4 * 4 + 2]);
+            acc[n4 * 4 + 3] = fmaf(xv, w4.w, acc[n4 * 4 + 3]);
+          }
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int n = 0; n < NH; ++n) acc[n] = acc[n] > 0.f ? acc[n] : 0.f;
+      }
+      if (vec_out) {
+#pragma unroll
+        for (int n4 = 0; n4 < NH / 4; ++n4)
+          if (n0 + n4 * 4 < N)
+            *reinterpret_cast<float4*>(yr + n0 + n4 * 4) =
+                make_float4(acc[n4 * 4], acc[n4 * 4 + 1], acc[n4 * 4 + 2], acc[n4 * 4 + 3]);
+      } else {
+#pragma unroll
+        for (int n = 0; n < NH; ++n)
+          if (n0 + n < N) yr[n0 + n] = acc[n];
+      }
+    }
   }
 }
 
@@ -257,9 +347,9 @@ inline int pad_pow(int v, int lo) {  // smallest of {lo, 16, 32, 64} >= v
   while (p < v) p = p < 16 ? 16 : p * 2;
   return p;
 }
-inline int bwd_grid(int64_t M) {
+inline int bwd_grid(int64_t M) {   // = number of weight-gradient partials; 4 CTAs (16 warps) per SM hide the tile loads
   const int64_t t = ceil_div64(M < 1 ? 1 : M, kTM);
-  return (int)(t < kSmCountB200 * 2 ? t : kSmCountB200 * 2);
+  return (int)(t < kSmCountB200 * 4 ? t : kSmCountB200 * 4);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -325,6 +415,31 @@ extern "C" int tzk_small_linear_fwd(const float* x, int64_t ld_x, const float* w
   TZK_REQUIRE(x && w && y, "small_linear_fwd: NULL argument");
   TZK_REQUIRE(ld_x >= K && ld_y >= N, "small_linear_fwd: leading dimension smaller than the row");
   const int NP = pad_pow(N, 4);
+  const char* fwd_env = getenv("TZK_SMALL_FWD");
+  if (!(fwd_env && fwd_env[0] == 't')) {   // default: warp-independent rows kernel (TZK_SMALL_FWD=tile: staged tiles)
+    const size_t smem_r = ((size_t)K * NP + NP) * sizeof(float);
+    const bool vec = (K % 4 == 0) && (ld_x % 4 == 0) && ((uintptr_t)x % 16 == 0);
+    const int64_t blocks = ceil_div64(M, kRowThreads);
+    const int grid_r = (int)(blocks < kSmCountB200 * 16 ? blocks : kSmCountB200 * 16);
+#define TZK_SLR(NP_)                                                                                                \
+  do {                                                                                                              \
+    if (vec)                                                                                                        \
+      small_linear_fwd_rows_kernel<NP_, true><<<grid_r, kRowThreads, smem_r, as_stream(stream)>>>(                  \
+          x, ld_x, w, bias, M, K, N, relu, y, ld_y);                                                                \
+    else                                                                                                            \
+      small_linear_fwd_rows_kernel<NP_, false><<<grid_r, kRowThreads, smem_r, as_stream(stream)>>>(                 \
+          x, ld_x, w, bias, M, K, N, relu, y, ld_y);                                                                \
+  } while (0)
+    switch (NP) {
+      case 4: TZK_SLR(4); break;
+      case 16: TZK_SLR(16); break;
+      case 32: TZK_SLR(32); break;
+      default: TZK_SLR(64); break;
+    }
+#undef TZK_SLR
+    TZK_CHECK_LAUNCH("small_linear_fwd_rows_kernel");
+    return 0;
+  }
   const int TS = (K > N ? K : N) | 1;
   const size_t smem = ((size_t)K * NP + NP + (size_t)kTM * TS) * sizeof(float);
   const int64_t tiles = ceil_div64(M, kTM);

@@ -101,6 +101,9 @@ class _TableView(nn.Module):
     def weight(self) -> torch.Tensor:
         return self._owner[0].table_weight(self._t)
 
+    def _load_from_state_dict(self, *args, **kwargs) -> None:
+        return None      # `<table>.weight` is consumed by the owning collection (it writes into the arena)
+
 
 class _ArenaCollection(nn.Module):
     """Shared machinery: arena, layout, optimizer state, key mapping."""
@@ -177,6 +180,70 @@ class _ArenaCollection(nn.Module):
     def set_table_weight(self, t: int, w: torch.Tensor) -> None:
         with torch.no_grad():
             self.table_weight(t).copy_(w)
+
+    # ---- checkpoint keys ------------------------------------------------------------------
+    # The reference's state_dict holds one entry per table, `<prefix>embedding_bags.<table>.weight` (EBC) or
+    # `<prefix>embeddings.<table>.weight` (EC) (tzrec/utils/checkpoint_util_test.py:375-396), and its fused optimizer
+    # state is keyed `state.<that key>.<table>.momentum1`.  The arena is an implementation detail: it never appears
+    # in a state_dict, and both directions go through per-table views.
+    def _table_attr(self) -> str:
+        return "embedding_bags" if self._pooled else "embeddings"
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for t, c in enumerate(self._configs):
+            if t in self._table_off:
+                w = self.table_weight(t)
+                destination[f"{prefix}{self._table_attr()}.{c.name}.weight"] = w if keep_vars else w.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        arena_key = prefix + "weights"          # checkpoints written by earlier versions of this package
+        if arena_key in state_dict:
+            w = state_dict[arena_key]
+            if w.numel() != self.weights.numel():
+                error_msgs.append(f"size mismatch for {arena_key}: {tuple(w.shape)} vs {tuple(self.weights.shape)}")
+            else:
+                with torch.no_grad():
+                    self.weights.data.copy_(w.reshape(-1))
+            return
+        for t, c in enumerate(self._configs):
+            if t not in self._table_off:
+                continue
+            key = f"{prefix}{self._table_attr()}.{c.name}.weight"
+            if key not in state_dict:
+                if strict:
+                    missing_keys.append(key)
+                continue
+            w = state_dict[key]
+            want = (self._table_rows[t], self._table_dim[t])
+            if tuple(w.shape) != want:
+                error_msgs.append(f"size mismatch for {key}: checkpoint {tuple(w.shape)}, table {want}")
+                continue
+            self.set_table_weight(t, w.to(self.weights.device))
+
+    def fused_optimizer_state_dict(self, prefix: str = "") -> Dict[str, torch.Tensor]:
+        """`state.<param key>.<table>.momentum1` per table (the reference's `model.fused_optimizer.state_dict()` keys,
+        checkpoint_util_test.py:387-390).  Element-wise Adagrad: [rows, dim]; row-wise Adagrad: [rows]; SGD: empty."""
+        out: Dict[str, torch.Tensor] = {}
+        for t, c in enumerate(self._configs):
+            st = self.table_state(t) if t in self._table_off else None
+            if st is not None:
+                out[f"state.{prefix}{self._table_attr()}.{c.name}.weight.{c.name}.momentum1"] = st
+        return out
+
+    def load_fused_optimizer_state_dict(self, state: Dict[str, torch.Tensor], prefix: str = "",
+                                        strict: bool = True) -> None:
+        for t, c in enumerate(self._configs):
+            dst = self.table_state(t) if t in self._table_off else None
+            if dst is None:
+                continue
+            key = f"state.{prefix}{self._table_attr()}.{c.name}.weight.{c.name}.momentum1"
+            if key not in state:
+                if strict:
+                    raise KeyError(key)
+                continue
+            with torch.no_grad():
+                dst.copy_(state[key].to(dst.device).reshape(dst.shape))
 
     # ---- fused optimizer ------------------------------------------------------------------------------
     def set_optimizer(self, spec: SparseOptimizerSpec) -> None:

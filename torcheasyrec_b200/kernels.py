@@ -120,6 +120,12 @@ def _rows2d(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
     return t, ld
 
 
+def _tile_path(lay: "FeatureLayout") -> bool:
+    import os
+
+    return os.environ.get("TZK_BWD_TILE", "0") == "1" and bool(lay.vec_ok) and lay.max_dim <= 128
+
+
 class CudaKernels:
     """sm_100a implementation of the hot path.  Stateless apart from cached workspaces."""
 
@@ -207,7 +213,7 @@ class CudaKernels:
             _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
         # own launches next to CUB's radix sort: tile path = linearize, tile_update, carry_combine;
         # general path (unaligned / > 128 floats) = zero_counters, linearize, run_update, long_chunk, long_combine
-        self.launches += 3 if (lay.vec_ok and lay.max_dim <= 128) else 5
+        self.launches += 3 if _tile_path(lay) else 5
 
     def fused_bwd_workspace_bytes(self, lay: FeatureLayout, nnz: int) -> int:
         return int(self._lib.tzk_fused_bwd_workspace_bytes(nnz, lay.total_keys, lay.max_dim))
@@ -239,7 +245,7 @@ class CudaKernels:
             _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(offsets), lay.num_features, B, nnz,
             lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
             _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_apply")
-        self.launches += 2 if (lay.vec_ok and lay.max_dim <= 128) else 4
+        self.launches += 2 if _tile_path(lay) else 4
 
     # ------------------------------------------------------------------ K1 / K2
     def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
