@@ -35,7 +35,8 @@ UNIT = "samples/s"
 # DLRM-Criteo (F=26, L=1, D=16) per-sample algorithmic bytes, SURVEY.md §8d — computed from the layout at run time:
 #   gather 1664 rows + 1664 pooled write + 208 ids + 104 lengths = 3640 B; backward 1664 grad + 26*4*64 RMW + 208 = 8528 B
 NCU_TRAFFIC_BYTES = {"pooled_gather_fwd_kernel": 111.339008e6 + 55.679232e6,   # dram rd + wr, one launch (ncu --set full)
-                     "tile_update_kernel": None}
+                     "run_update_kernel": 282.46656e6 + 50.44352e6,     # largest kernel of the fused backward (default path)
+                     "tile_update_kernel": 344.51072e6 + 52.342784e6}   # TZK_BWD_TILE=1 path
 
 
 def parse_args():
@@ -328,7 +329,8 @@ def run_ours(args):
     it = max(K, 10)
     # algorithmic bytes per sample of THIS collection and batch: rows + pooled write + ids + lengths;
     # backward: gradient read + weight/state read+write of every looked-up row (U = upper bound: no duplicates) + ids
-    nnz_f = [float(k.length_per_key()[f]) / B for f in range(lay.num_features)]
+    lpk = kjts[0].length_per_key()
+    nnz_f = [float(lpk[f]) / B for f in range(lay.num_features)]
     row_b = sum(l * d * 4 for l, d in zip(nnz_f, lay.dim))
     gather_b = row_b + sum(d * 4 for d in lay.dim) + sum(l * 8 for l in nnz_f) + 4 * lay.num_features
     spec = ebc.optimizer
@@ -348,7 +350,7 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     fwd_gbs = gather_b * B / (fwd_ms * 1e-3) / 1e9
     bwd_gbs = bwd_b * B / (bwd_ms * 1e-3) / 1e9
-    dominant = ("tzk_fused_bwd (linearize + radix sort + tile_update + carry_combine)" if bwd_ms > fwd_ms
+    dominant = ("tzk_fused_bwd (linearize + radix sort + run_update / long-run kernels)" if bwd_ms > fwd_ms
                 else "pooled_gather_fwd_kernel")
     ach = bwd_gbs if bwd_ms > fwd_ms else fwd_gbs
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture
@@ -356,7 +358,7 @@ def run_ours(args):
     std = (args.model == "dlrm_criteo" and B == 65536 and not args.max_rows and args.id_dist == "uniform")
     traffic = None
     if std:
-        traffic = (NCU_TRAFFIC_BYTES["tile_update_kernel"] if bwd_ms > fwd_ms else NCU_TRAFFIC_BYTES["pooled_gather_fwd_kernel"])
+        traffic = (NCU_TRAFFIC_BYTES["run_update_kernel"] if bwd_ms > fwd_ms else NCU_TRAFFIC_BYTES["pooled_gather_fwd_kernel"])
     kernels = {
         "pooled_gather_fwd": {"ms": fwd_ms, "algorithmic_GBps": fwd_gbs, "frac": fwd_gbs / peak,
                               "row_read_GBps": row_b * B / (fwd_ms * 1e-3) / 1e9, "bytes_per_sample": gather_b},
@@ -383,8 +385,8 @@ def run_ours(args):
                                        "frac": ib_b * B / (ib_ms * 1e-3) / 1e9 / peak, "bytes_per_sample": ib_b}
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": traffic, "traffic_note": "dram bytes/launch of the dominant kernel from the ncu --set full capture "
-        "summarised in profiles/" if traffic else None,
+        "traffic": traffic, "traffic_note": "dram read+write bytes per launch of the dominant kernel's largest launch (run_update_kernel, or "
+        "the gather itself) from the ncu --set full captures summarised in profiles/" if traffic else None,
         "peak_source": peak_src,
         "kernels": kernels,
         "share_of_step": {k: v["ms"] / (ms_total / K) for k, v in kernels.items()},

@@ -44,6 +44,27 @@ extern "C" {
 #define TZK_OPT_SGD 0             /* w -= lr*g                                   (App. A.10) */
 #define TZK_OPT_ADAGRAD 1         /* s += g*g ; w -= lr*g/(sqrt(s)+eps)          (EXACT_ADAGRAD) */
 #define TZK_OPT_ROWWISE_ADAGRAD 2 /* s_row += mean_d(g*g) ; w -= lr*g/(sqrt(s_row)+eps) */
+/* the next two only through tzk_fused_bwd_ex / tzk_fused_bwd_apply_ex (they need tzk_opt_args) */
+#define TZK_OPT_ADAM 3            /* m=b1 m+(1-b1)g ; v=b2 v+(1-b2)g*g ; w -= lr*(m^/(sqrt(v^)+eps) + wd*w)  (ADAM) */
+#define TZK_OPT_PARTIAL_ROWWISE_ADAM 4 /* m element-wise, v one value per row from mean_d(g*g)  (PARTIAL_ROWWISE_ADAM) */
+
+/* Optimizer description for the _ex entry points (what tzrec/optim/optimizer_builder.py:30-97 passes to
+ * apply_optimizer_in_backward; field names follow tzrec/protos/optimizer.proto:76-139).  Host struct, device
+ * pointers inside.
+ *   state  : SGD unused; ADAGRAD / ADAM / PARTIAL_ROWWISE_ADAM: same layout as `weights` (accumulator / first
+ *            moment); ROWWISE_ADAGRAD: one float per key.
+ *   state2 : ADAM: second moment, same layout as `weights`; PARTIAL_ROWWISE_ADAM: one float per key.
+ *   step   : device scalar holding the 1-based iteration count of this update as a float (bias correction
+ *            1 - beta^t is evaluated on the device, so a captured CUDA graph can keep replaying).
+ *   max_gradient > 0 clamps every element of the summed row gradient to [-max_gradient, max_gradient]
+ *   (gradient_clipping = true); weight_decay is fbgemm's: w -= lr * weight_decay * w inside the same update. */
+typedef struct tzk_opt_args {
+  int32_t optimizer;
+  float lr, eps, beta1, beta2, weight_decay, max_gradient;
+  float* state;
+  float* state2;
+  const float* step;
+} tzk_opt_args;
 
 typedef void* tzk_stream_t; /* cudaStream_t */
 
@@ -104,6 +125,18 @@ int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int6
  * the host can enqueue it on a side stream as soon as the batch is on the device — it then overlaps the forward
  * pass (what TrainPipelineSparseDist does for the input dist, tzrec/utils/dist_util.py:221-303) — and _apply,
  * ordered after it, consumes the gradient.  tzk_fused_bwd == _sort followed by _apply on one stream. */
+int tzk_fused_bwd_ex(const tzk_opt_args* opt, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                     const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                     const int32_t* feat_col, const int32_t* feat_pool, const int64_t* feat_key_base,
+                     const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int64_t nnz,
+                     int64_t total_keys, int32_t max_dim, int32_t vec_ok, float* weights, float grad_scale,
+                     void* workspace, size_t workspace_bytes, tzk_stream_t stream);
+int tzk_fused_bwd_apply_ex(const tzk_opt_args* opt, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                           const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                           const int32_t* feat_col, const int32_t* feat_pool, const int64_t* feat_key_base,
+                           const int64_t* offsets, int32_t F, int32_t B, int64_t nnz, int64_t total_keys,
+                           int32_t max_dim, int32_t vec_ok, float* weights, float grad_scale, void* workspace,
+                           size_t workspace_bytes, tzk_stream_t stream);
 int tzk_fused_bwd_sort(int32_t pooled, const int64_t* feat_rows, const int64_t* feat_key_base, const int64_t* ids,
                        const int64_t* offsets, int32_t F, int32_t B, int64_t nnz, int64_t total_keys,
                        int32_t max_dim, void* workspace, size_t workspace_bytes, tzk_stream_t stream);

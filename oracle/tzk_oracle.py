@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 POOL_SUM, POOL_MEAN = 0, 1
-OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD = 0, 1, 2
+OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM = 0, 1, 2, 3, 4
 
 f32 = np.float32
 
@@ -108,10 +108,16 @@ def seq_lookup(tables: Sequence[np.ndarray], feat_table: Sequence[int], ids: np.
 def fused_update(optimizer: int, tables: List[np.ndarray], states: List[Optional[np.ndarray]],
                  feat_table: Sequence[int], feat_pool: Sequence[int], ids: np.ndarray, offsets: np.ndarray, B: int,
                  grad_out: np.ndarray, lr: float, eps: float = 1e-8, grad_scale: float = 1.0,
-                 pooled: bool = True) -> None:
+                 pooled: bool = True, states2: Optional[List[Optional[np.ndarray]]] = None, step: int = 1,
+                 beta1: float = 0.9, beta2: float = 0.999, weight_decay: float = 0.0,
+                 max_gradient: float = 0.0) -> None:
     """In-place EXACT update: per touched row g = sum of its contributions (stable order), one update.
 
-    states[t]: ADAGRAD -> array like tables[t]; ROWWISE_ADAGRAD -> [rows]; SGD -> ignored.
+    states[t]: ADAGRAD -> array like tables[t]; ROWWISE_ADAGRAD -> [rows]; SGD -> ignored;
+    ADAM / PARTIAL_ROWWISE_ADAM -> first moment like tables[t], states2[t] = second moment (like tables[t] / [rows]).
+    `step` = 1-based iteration count (bias correction).  max_gradient > 0 clamps the summed row gradient
+    (gradient_clipping, tzrec/protos/optimizer.proto:76-139); weight_decay as in fbgemm's Adam:
+    w -= lr * (m^ / (sqrt(v^) + eps) + weight_decay * w).  Only touched rows move (lazy / sparse semantics).
     pooled=False: grad_out is [nnz, D] (sequence / EmbeddingCollection layout)."""
     F = len(feat_table)
     lr, eps, grad_scale = f32(lr), f32(eps), f32(grad_scale)
@@ -148,6 +154,8 @@ def fused_update(optimizer: int, tables: List[np.ndarray], states: List[Optional
         uniq, inv = np.unique(rows, return_inverse=True)
         gsum = np.zeros((len(uniq), W.shape[1]), dtype=f32)
         np.add.at(gsum, inv, grads)
+        if max_gradient > 0:
+            gsum = np.clip(gsum, -f32(max_gradient), f32(max_gradient)).astype(f32)
         if optimizer == OPT_SGD:
             W[uniq] = W[uniq] - lr * gsum
         elif optimizer == OPT_ADAGRAD:
@@ -160,6 +168,22 @@ def fused_update(optimizer: int, tables: List[np.ndarray], states: List[Optional
             s_new = S[uniq] + (gsum * gsum).sum(axis=1, dtype=f32) / f32(W.shape[1])
             S[uniq] = s_new
             W[uniq] = W[uniq] - lr * gsum / (np.sqrt(s_new) + eps)[:, None]
+        elif optimizer in (OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM):
+            b1, b2, wd = f32(beta1), f32(beta2), f32(weight_decay)
+            bc1 = f32(1.0) - f32(np.power(np.float32(beta1), np.float32(step)))
+            bc2 = f32(1.0) - f32(np.power(np.float32(beta2), np.float32(step)))
+            M, V = states[t], states2[t]
+            m_new = b1 * M[uniq] + (f32(1.0) - b1) * gsum
+            M[uniq] = m_new
+            if optimizer == OPT_ADAM:
+                v_new = b2 * V[uniq] + (f32(1.0) - b2) * gsum * gsum
+                V[uniq] = v_new
+                denom = np.sqrt(v_new / bc2) + eps
+            else:
+                v_new = b2 * V[uniq] + (f32(1.0) - b2) * ((gsum * gsum).sum(axis=1, dtype=f32) / f32(W.shape[1]))
+                V[uniq] = v_new
+                denom = (np.sqrt(v_new / bc2) + eps)[:, None]
+            W[uniq] = W[uniq] - lr * ((m_new / bc1) / denom + wd * W[uniq])
         else:
             raise ValueError(optimizer)
 

@@ -65,8 +65,9 @@ class OracleKernels:
         tabs, ft = _tables(weights, lay)
         return torch.from_numpy(O.seq_lookup(tabs, ft, _np(ids), _np(offsets), B))
 
-    def fused_bwd(self, optimizer, pooled, grad_out, weights, state, lay, ids, offsets, B, lr, eps, grad_scale=1.0):
-        if self.use_c and pooled:
+    def fused_bwd(self, optimizer, pooled, grad_out, weights, state, lay, ids, offsets, B, lr, eps, grad_scale=1.0,
+                  **ex):
+        if self.use_c and pooled and not ex:
             self.C.fused_update(optimizer, _np(grad_out), weights.detach().numpy(),
                                 None if state is None else state.numpy(), lay, _c(ids), _c(offsets), B, lr, eps,
                                 grad_scale)
@@ -78,12 +79,27 @@ class OracleKernels:
             for f in range(lay.num_features):
                 t = ft[f]
                 if states[t] is None:
-                    if optimizer == O.OPT_ADAGRAD:
+                    if optimizer in (O.OPT_ADAGRAD, O.OPT_ADAM, O.OPT_PARTIAL_ROWWISE_ADAM):
                         states[t] = sarr[lay.w_off[f]:lay.w_off[f] + lay.rows[f] * lay.dim[f]].reshape(lay.rows[f], lay.dim[f])
                     else:
                         states[t] = sarr[lay.key_base[f]:lay.key_base[f] + lay.rows[f]]
+        states2, kw = None, {}
+        if ex:
+            kw = dict(beta1=ex.get("beta1", 0.9), beta2=ex.get("beta2", 0.999), weight_decay=ex.get("weight_decay", 0.0),
+                      max_gradient=ex.get("max_gradient", 0.0))
+            if ex.get("state2") is not None:
+                s2 = ex["state2"].numpy()
+                states2 = [None] * len(tabs)
+                for f in range(lay.num_features):
+                    t = ft[f]
+                    if states2[t] is None:
+                        if optimizer == O.OPT_ADAM:
+                            states2[t] = s2[lay.w_off[f]:lay.w_off[f] + lay.rows[f] * lay.dim[f]].reshape(lay.rows[f], lay.dim[f])
+                        else:
+                            states2[t] = s2[lay.key_base[f]:lay.key_base[f] + lay.rows[f]]
+                kw["step"] = int(round(float(ex["step"])))
         O.fused_update(optimizer, tabs, states, ft, lay.pool, _np(ids), _np(offsets), B, _np(grad_out), lr, eps,
-                       grad_scale, pooled=bool(pooled))
+                       grad_scale, pooled=bool(pooled), states2=states2, **kw)
 
     def bucketize_rw(self, ids, offsets, F, B, W, feat_block, want_pos=False, feat_owner=None, want_inv=False,
                      wire_capacity=0):

@@ -160,6 +160,16 @@ def test_deepfm_mixed_three_ranks():
     _run(3, "deepfm_criteo", "mixed", rw_min_rows=200)
 
 
+@pytest.mark.parametrize("world,name,sharding,rw_min", [
+    (4, "deepfm_criteo", "table_wise", 0),        # cfg3's sharding (SURVEY §8c golden (2): W in {1,2,4,8} x {TW,RW,mixed})
+    (4, "dlrm_criteo", "row_wise", 0),
+    (8, "dlrm_criteo", "row_wise", 0),            # cfg2's world size: tables smaller than W leave ranks empty
+    (4, "mmoe_taobao", "mixed", 250),             # cfg5: big tables row-wise, small ones table-wise, two task towers
+])
+def test_w_invariance_at_larger_world_sizes(world, name, sharding, rw_min):
+    _run(world, name, sharding, rw_min_rows=rw_min)
+
+
 def test_din_sequence_two_ranks():
     _run(2, "multi_tower_din_taobao", "mixed", rw_min_rows=250)
 

@@ -509,3 +509,56 @@ def test_linear_dispatch_and_bce_autograd_match_torch():
     assert abs(la - lb) <= 1e-6 * max(1.0, abs(lb))
     for a, b in zip(ga, gb):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("opt", [O.OPT_ADAM, O.OPT_PARTIAL_ROWWISE_ADAM])
+@pytest.mark.parametrize("case", ["deepfm_mixed_dims", "tiny_tables_long_runs", "wide_rows", "unaligned_dims"])
+def test_fused_bwd_adam_variants(kernels, case, opt, bwd_path):
+    """tzk_fused_bwd_ex: Adam / partial row-wise Adam with weight decay and gradient clipping, three steps (the
+    device-side step counter drives the bias correction), against the oracle (pinned to torch.optim.SparseAdam)."""
+    rows, dims, feat_table, B, max_len = CASES[case]
+    rng = np.random.default_rng(zlib.crc32(case.encode()) % 1000 + opt)
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    F = len(feat_table)
+    frows = [rows[t] for t in feat_table]
+    lay = build_layout(rows, dims, feat_table, [O.POOL_SUM] * F).to(DEV)
+    arena = cu(make_arena(lay, tables, feat_table))
+    m1 = torch.zeros_like(arena)
+    m2 = torch.zeros_like(arena) if opt == O.OPT_ADAM else torch.zeros(lay.total_keys, device=DEV)
+    step = torch.zeros((), device=DEV)
+    want = [t.copy() for t in tables]
+    s1 = [np.zeros_like(t) for t in tables]
+    s2 = [np.zeros_like(t) if opt == O.OPT_ADAM else np.zeros(t.shape[0], np.float32) for t in tables]
+    lr, eps, b1, b2, wd, mg = 0.02, 1e-8, 0.9, 0.999, 0.01, 0.7
+    for it in range(1, 4):
+        ids, lengths, offsets = random_kjt(rng, F, B, frows, max_len or 1, fixed_len=1 if max_len is None else None)
+        grad = rng.standard_normal((B, lay.total_dim)).astype(np.float32)
+        step.add_(1.0)
+        kernels.fused_bwd(opt, True, cu(grad), arena, m1, lay, cu(ids), cu(offsets), B, lr, eps, 1.0, state2=m2,
+                          step=step, beta1=b1, beta2=b2, weight_decay=wd, max_gradient=mg)
+        O.fused_update(opt, want, s1, feat_table, [O.POOL_SUM] * F, ids, offsets, B, grad, lr, eps, 1.0, states2=s2,
+                       step=it, beta1=b1, beta2=b2, weight_decay=wd, max_gradient=mg)
+    got = split_arena(arena.cpu().numpy(), lay, tables, feat_table)
+    for t in range(len(tables)):
+        np.testing.assert_allclose(got[t], want[t], rtol=5e-5, atol=5e-6, err_msg=f"table {t}")
+    gm = split_arena(m1.cpu().numpy(), lay, tables, feat_table)
+    for t in range(len(tables)):
+        np.testing.assert_allclose(gm[t], s1[t], rtol=5e-5, atol=1e-6)
+
+
+def test_gradient_clipping_on_classic_optimizers(kernels, bwd_path):
+    rng = np.random.default_rng(123)
+    rows, dims, feat_table, B = [7, 300], [16, 16], [0, 1], 400
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    ids, lengths, offsets = random_kjt(rng, 2, B, rows, 3)
+    lay = build_layout(rows, dims, feat_table, [0, 0]).to(DEV)
+    arena = cu(make_arena(lay, tables, feat_table))
+    state = torch.zeros_like(arena)
+    grad = rng.standard_normal((B, 32)).astype(np.float32)
+    kernels.fused_bwd(O.OPT_ADAGRAD, True, cu(grad), arena, state, lay, cu(ids), cu(offsets), B, 0.1, 1e-8, 1.0,
+                      max_gradient=0.5)
+    want, st = [t.copy() for t in tables], [np.zeros_like(t) for t in tables]
+    O.fused_update(O.OPT_ADAGRAD, want, st, feat_table, [0, 0], ids, offsets, B, grad, 0.1, 1e-8, 1.0, max_gradient=0.5)
+    got = split_arena(arena.cpu().numpy(), lay, tables, feat_table)
+    for t in range(2):
+        np.testing.assert_allclose(got[t], want[t], rtol=2e-5, atol=2e-6)

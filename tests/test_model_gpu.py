@@ -56,6 +56,27 @@ def test_train_steps_match_oracle(name):
             np.testing.assert_allclose(cg.opt_state.cpu().numpy(), cc.opt_state.numpy(), rtol=1e-4, atol=1e-10)
 
 
+@pytest.mark.parametrize("kind", ["adam", "partial_rowwise_adam"])
+def test_train_steps_with_sparse_adam_match_oracle(kind):
+    """train_config.sparse_optimizer { adam_optimizer / partial_rowwise_adam_optimizer } end to end (device-side step
+    counter, second state, clipping) on the sequence model: pooled and un-pooled collections both update."""
+    from torcheasyrec_b200.embedding_modules import SparseOptimizerSpec
+
+    gpu, cpu = _pair("multi_tower_din_taobao", 500)
+    spec = SparseOptimizerSpec.from_name(kind, lr=0.01, weight_decay=0.001, max_gradient=0.05)
+    gpu.model.set_sparse_optimizer(spec)
+    cpu.model.set_sparse_optimizer(spec)
+    for it in range(3):
+        batch = gpu.synthetic_batch(128, seed=50 + it)
+        gpu.eager_step(batch.to("cuda:0"))
+        with Fn.use_backend(OracleKernels()):
+            cpu.eager_step(batch)
+    for cg, cc in zip(gpu.model.sparse_collections(), cpu.model.sparse_collections()):
+        assert float(cg.opt_step) == 3.0 and float(cc.opt_step) == 3.0
+        np.testing.assert_allclose(cg.weights.detach().cpu().numpy(), cc.weights.detach().numpy(), rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(cg.opt_state.cpu().numpy(), cc.opt_state.numpy(), rtol=2e-4, atol=1e-8)
+
+
 def test_cuda_graph_step_equals_eager_step():
     a = Pipeline("dlrm_criteo", device="cuda:0", max_rows=5000, seed=3)
     batches = [a.synthetic_batch(1024, seed=40 + i) for i in range(4)]

@@ -13,6 +13,14 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtzk.so")
 
 P = c_void_p  # every device pointer crosses the ABI as a plain address
 
+class TzkOptArgs(ctypes.Structure):
+    """struct tzk_opt_args (include/tzk.h)."""
+
+    _fields_ = [("optimizer", c_int32), ("lr", c_float), ("eps", c_float), ("beta1", c_float), ("beta2", c_float),
+                ("weight_decay", c_float), ("max_gradient", c_float), ("state", c_void_p), ("state2", c_void_p),
+                ("step", c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/tzk.h one to one (tests/test_abi.py checks both directions)
 SIGNATURES = {
     "tzk_abi_version": (c_int32, []),
@@ -30,6 +38,16 @@ SIGNATURES = {
         c_int32,
         [c_int32, c_int32, P, c_int64, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int64, c_int64, c_int32,
          c_int32, P, P, c_float, c_float, c_float, P, c_size_t, P],
+    ),
+    "tzk_fused_bwd_ex": (
+        c_int32,
+        [P, c_int32, P, c_int64, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32, P,
+         c_float, P, c_size_t, P],
+    ),
+    "tzk_fused_bwd_apply_ex": (
+        c_int32,
+        [P, c_int32, P, c_int64, P, P, P, P, P, P, P, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32, P,
+         c_float, P, c_size_t, P],
     ),
     "tzk_fused_bwd_sort": (c_int32, [c_int32, P, P, P, P, c_int32, c_int32, c_int64, c_int64, c_int32, P, c_size_t, P]),
     "tzk_fused_bwd_apply": (

@@ -80,6 +80,7 @@ SCHEMA: Dict[str, Dict[str, Tuple[str, bool, Any]]] = {
     "SparseOptimizer": {
         "sgd_optimizer": _f("FusedSGDOptimizer"), "adagrad_optimizer": _f("FusedAdagradOptimizer"),
         "adam_optimizer": _f("FusedAdamOptimizer"), "rowwise_adagrad_optimizer": _f("FusedRowWiseAdagradOptimizer"),
+        "partial_rowwise_adam_optimizer": _f("FusedAdamOptimizer"),     # same fields (optimizer.proto:124-131)
         "constant_learning_rate": _f("ConstantLR"),
     },
     "DenseOptimizer": {

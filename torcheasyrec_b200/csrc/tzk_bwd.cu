@@ -45,7 +45,21 @@ struct BwdArgs {
   int32_t pooled;
   int64_t n;
   uint64_t sentinel;  // key of ids that belong to a zero-row (padding) feature: sorted last, never updated
+  // extended optimizers (tzk_opt_args): second state, Adam constants, clipping
+  float* state2;
+  const float* step;  // device scalar: iteration count t >= 1 of this update (bias correction)
+  float beta1, beta2, weight_decay, max_gradient;
+  float bc1, bc2;     // 1 - beta^t, filled in by init_bias_correction() at kernel start
 };
+
+__device__ __forceinline__ void init_bias_correction(BwdArgs& a) {
+  a.bc1 = a.bc2 = 1.f;
+  if (a.optimizer >= TZK_OPT_ADAM) {
+    const float t = a.step ? __ldg(a.step) : 1.f;
+    a.bc1 = 1.f - powf(a.beta1, t);
+    a.bc2 = 1.f - powf(a.beta2, t);
+  }
+}
 
 __device__ __forceinline__ void stage_feats(BwdFeat* fd, const int64_t* feat_w_off, const int64_t* feat_rows,
                                             const int64_t* feat_key_base, const int32_t* feat_dim,
@@ -193,9 +207,13 @@ __device__ __forceinline__ int feat_of_key(const BwdFeat* fd, int F, KeyT key) {
   return best;
 }
 
-// apply the optimizer to one float4 chunk; for row-wise Adagrad `rw_state` is the already updated row sum
+// apply the optimizer to one chunk of a row.  `s` = first state (Adagrad accumulator / Adam first moment), `s2` =
+// Adam second moment; `rw_denom` = the already computed per-row denominator of the row-wise variants.
+// fbgemm formulas (App. A.10 and [EXT] split_embedding_optimizer_codegen):
+//   ADAM                 m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; w -= lr (m^/(sqrt(v^)+eps) + wd w)
+//   PARTIAL_ROWWISE_ADAM m element-wise as above, v one value per row from mean_d(g^2) (-> rw_denom)
 template <int VEC>
-__device__ __forceinline__ void apply_update(const BwdArgs& a, float* w, float* s, const float* g,
+__device__ __forceinline__ void apply_update(const BwdArgs& a, float* w, float* s, float* s2, const float* g,
                                              float rw_denom) {
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
@@ -206,10 +224,53 @@ __device__ __forceinline__ void apply_update(const BwdArgs& a, float* w, float* 
       const float sk = s[k] + gk * gk;
       s[k] = sk;
       w[k] = w[k] - a.lr * gk / (sqrtf(sk) + a.eps);
-    } else {
+    } else if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {
       w[k] = w[k] - a.lr * gk / rw_denom;
+    } else if (a.optimizer == TZK_OPT_ADAM) {
+      const float m = a.beta1 * s[k] + (1.f - a.beta1) * gk;
+      const float v = a.beta2 * s2[k] + (1.f - a.beta2) * gk * gk;
+      s[k] = m;
+      s2[k] = v;
+      w[k] = w[k] - a.lr * ((m / a.bc1) / (sqrtf(v / a.bc2) + a.eps) + a.weight_decay * w[k]);
+    } else {  // TZK_OPT_PARTIAL_ROWWISE_ADAM
+      const float m = a.beta1 * s[k] + (1.f - a.beta1) * gk;
+      s[k] = m;
+      w[k] = w[k] - a.lr * ((m / a.bc1) / rw_denom + a.weight_decay * w[k]);
     }
   }
+}
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask_of();
+__device__ __forceinline__ float clip_grad(const BwdArgs& a, float g) {
+  return a.max_gradient > 0.f ? fminf(fmaxf(g, -a.max_gradient), a.max_gradient) : g;
+}
+__device__ __forceinline__ bool has_elem_state(const BwdArgs& a) {   // first state laid out like the weights
+  return a.optimizer == TZK_OPT_ADAGRAD || a.optimizer >= TZK_OPT_ADAM;
+}
+// per-row denominator of the row-wise variants; `ss` = sum over the row of g^2 (already reduced over the lane group),
+// lane 0 of the group owns the state element
+template <int G>
+__device__ __forceinline__ float rowwise_denom(const BwdArgs& a, int64_t key, float ss, int dim, int lane) {
+  float d = 1.f;
+  if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {
+    float sr = 0.f;
+    if (lane == 0) {
+      sr = a.state[key] + ss / (float)dim;
+      a.state[key] = sr;
+    }
+    sr = __shfl_sync(group_mask_of<G>(), sr, 0, G);
+    d = sqrtf(sr) + a.eps;
+  } else if (a.optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM) {
+    float v = 0.f;
+    if (lane == 0) {
+      v = a.beta2 * a.state2[key] + (1.f - a.beta2) * (ss / (float)dim);
+      a.state2[key] = v;
+    }
+    v = __shfl_sync(group_mask_of<G>(), v, 0, G);
+    d = sqrtf(v / a.bc2) + a.eps;
+  }
+  return d;
 }
 
 // mask of the G lanes of this thread's lane group inside its warp (groups diverge independently)
@@ -219,6 +280,8 @@ __device__ __forceinline__ unsigned group_mask() {
   const unsigned lane_in_warp = threadIdx.x & 31u;
   return ((1u << G) - 1u) << (lane_in_warp / G * G);
 }
+template <int G>
+__device__ __forceinline__ unsigned group_mask_of() { return group_mask<G>(); }
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
   const unsigned m = group_mask<G>();
@@ -232,8 +295,14 @@ __device__ __forceinline__ float group_sum(float v) {
 template <int G, int VEC, int CH>
 __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, int64_t row, int64_t key,
                                            float (&acc)[CH][VEC], int lane) {
+  if (a.max_gradient > 0.f) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[ch][k] = clip_grad(a, acc[ch][k]);
+  }
   float rw_denom = 1.f;
-  if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {
+  if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD || a.optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM) {
     float ss = 0.f;
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
@@ -243,37 +312,43 @@ __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, i
         if (c + k < d.dim) ss += acc[ch][k] * acc[ch][k];
     }
     ss = group_sum<G>(ss);
-    float sr = 0.f;
-    if (lane == 0) {
-      sr = a.state[key] + ss / (float)d.dim;
-      a.state[key] = sr;
-    }
-    sr = __shfl_sync(group_mask<G>(), sr, 0, G);
-    rw_denom = sqrtf(sr) + a.eps;
+    rw_denom = rowwise_denom<G>(a, key, ss, d.dim, lane);
   }
+  const bool es = has_elem_state(a);
+  const bool es2 = a.optimizer == TZK_OPT_ADAM;
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
     const int c = (ch * G + lane) * VEC;
     if (c >= d.dim) continue;
-    float* wp = a.weights + d.w_off + row * d.dim + c;
-    float* sp = (a.optimizer == TZK_OPT_ADAGRAD) ? a.state + d.w_off + row * d.dim + c : nullptr;
+    const int64_t off = d.w_off + row * d.dim + c;
+    float* wp = a.weights + off;
+    float* sp = es ? a.state + off : nullptr;
+    float* sp2 = es2 ? a.state2 + off : nullptr;
     if (VEC == 4) {
       float4 w4 = *reinterpret_cast<float4*>(wp);
       float w[4] = {w4.x, w4.y, w4.z, w4.w};
       float s[4] = {0.f, 0.f, 0.f, 0.f};
+      float s2[4] = {0.f, 0.f, 0.f, 0.f};
       if (sp) {
         float4 s4 = *reinterpret_cast<float4*>(sp);
         s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
       }
-      apply_update<4>(a, w, s, acc[ch], rw_denom);
+      if (sp2) {
+        float4 s4 = *reinterpret_cast<float4*>(sp2);
+        s2[0] = s4.x; s2[1] = s4.y; s2[2] = s4.z; s2[3] = s4.w;
+      }
+      apply_update<4>(a, w, s, s2, acc[ch], rw_denom);
       *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
       if (sp) *reinterpret_cast<float4*>(sp) = make_float4(s[0], s[1], s[2], s[3]);
+      if (sp2) *reinterpret_cast<float4*>(sp2) = make_float4(s2[0], s2[1], s2[2], s2[3]);
     } else {
       float w[1] = {wp[0]};
       float s[1] = {sp ? sp[0] : 0.f};
-      apply_update<1>(a, w, s, acc[ch], rw_denom);
+      float s2[1] = {sp2 ? sp2[0] : 0.f};
+      apply_update<1>(a, w, s, s2, acc[ch], rw_denom);
       wp[0] = w[0];
       if (sp) sp[0] = s[0];
+      if (sp2) sp2[0] = s2[0];
     }
   }
 }
@@ -322,6 +397,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  init_bias_correction(a);
 
   constexpr int NG = kThreads / G;
   constexpr int kPos = (CH == 1) ? KP : 1;
@@ -404,7 +480,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
           rw_denom = sqrtf(sr) + a.eps;
         }
         if (c < d.dim) {
-          apply_update<VEC>(a, w[u], s[u], gv, rw_denom);
+          apply_update<VEC>(a, w[u], s[u], s[u], gv, rw_denom);   // (batched path: SGD / Adagrad kinds only)
           float* wp = a.weights + d.w_off + row * d.dim + c;
           if (VEC == 4) {
             *reinterpret_cast<float4*>(wp) = make_float4(w[u][0], w[u][1], w[u][2], w[u][3]);
@@ -500,6 +576,7 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   constexpr int kLU = 4;              // independent gradient rows in flight per lane group
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  init_bias_correction(a);
 
   const int lane = threadIdx.x % G;
   const int gw = (threadIdx.x & 31) / G;
@@ -581,6 +658,7 @@ long_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int
   constexpr int ROWF = CH * G * VEC;
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  init_bias_correction(a);
   const int lane = threadIdx.x % G;
   const int n_runs = wl.counters[1];
   for (int r = blockIdx.x * NG + threadIdx.x / G; r < n_runs; r += gridDim.x * NG) {
@@ -648,6 +726,7 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
   int32_t* sv = reinterpret_cast<int32_t*>(sk + (TP + 2));                // [TP]
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw + align16((size_t)TP * ROWF * 4 + (TP + 2) * sizeof(KeyT) + TP * 4));
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  init_bias_correction(a);
 
   const int lane = threadIdx.x % G, grp = threadIdx.x / G;
   const int c = lane * 4;
@@ -718,7 +797,7 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
         if (kind[u] == 3 && c < dim) {
           const int64_t off = fd[f].w_off + ((int64_t)key - fd[f].key_base) * dim + c;
           w4[u] = ld_rw_f4(a.weights + off);
-          if (a.optimizer == TZK_OPT_ADAGRAD) s4[u] = ld_rw_f4(a.state + off);
+          if (has_elem_state(a)) s4[u] = ld_rw_f4(a.state + off);
         }
       }
     }
@@ -779,27 +858,28 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
         *reinterpret_cast<float4*>(carry_last + t * ROWF + c) = acc;
       } else {
         const BwdFeat& d = fd[fx[u]];
-        float g[4] = {acc.x, acc.y, acc.z, acc.w};
+        float g[4] = {clip_grad(a, acc.x), clip_grad(a, acc.y), clip_grad(a, acc.z), clip_grad(a, acc.w)};
         float rw_denom = 1.f;
-        if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {  // lanes beyond the row hold zeros
-          float ss = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3];
+        if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD || a.optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM) {
+          float ss = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3];  // lanes beyond the row hold zeros
           ss = group_sum<G>(ss);
-          float sr = 0.f;
-          if (lane == 0) {
-            sr = a.state[key] + ss / (float)d.dim;
-            a.state[key] = sr;
-          }
-          sr = __shfl_sync(group_mask<G>(), sr, 0, G);
-          rw_denom = sqrtf(sr) + a.eps;
+          rw_denom = rowwise_denom<G>(a, (int64_t)key, ss, d.dim, lane);
         }
         if (c < d.dim) {
+          const int64_t off = d.w_off + ((int64_t)key - d.key_base) * d.dim + c;
           float w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
           float s[4] = {s4[u].x, s4[u].y, s4[u].z, s4[u].w};
-          apply_update<4>(a, w, s, g, rw_denom);
-          const int64_t off = d.w_off + ((int64_t)key - d.key_base) * d.dim + c;
+          float s2[4] = {0.f, 0.f, 0.f, 0.f};
+          if (a.optimizer == TZK_OPT_ADAM) {
+            const float4 v4 = ld_rw_f4(a.state2 + off);
+            s2[0] = v4.x; s2[1] = v4.y; s2[2] = v4.z; s2[3] = v4.w;
+          }
+          apply_update<4>(a, w, s, s2, g, rw_denom);
           *reinterpret_cast<float4*>(a.weights + off) = make_float4(w[0], w[1], w[2], w[3]);
-          if (a.optimizer == TZK_OPT_ADAGRAD)
+          if (has_elem_state(a))
             *reinterpret_cast<float4*>(a.state + off) = make_float4(s[0], s[1], s[2], s[3]);
+          if (a.optimizer == TZK_OPT_ADAM)
+            *reinterpret_cast<float4*>(a.state2 + off) = make_float4(s2[0], s2[1], s2[2], s2[3]);
         }
       }
     }
@@ -822,6 +902,7 @@ carry_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const in
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  init_bias_correction(a);
   const int lane = threadIdx.x % G;
   const int c = lane * 4;
   const KeyT sentinel = (KeyT)a.sentinel;
@@ -964,15 +1045,18 @@ extern "C" size_t tzk_fused_bwd_workspace_bytes(int64_t nnz, int64_t total_keys,
 }
 
 // phases: 1 = linearize + sort (needs ids / offsets only), 2 = reduce runs + update (needs the gradient)
-static int fused_bwd_impl(int phases, int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
-                          const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
-                          const int32_t* feat_col, const int32_t* feat_pool,
+static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, const float* grad_out,
+                          int64_t ld_grad, const int64_t* feat_w_off, const int64_t* feat_rows,
+                          const int32_t* feat_dim, const int32_t* feat_col, const int32_t* feat_pool,
                           const int64_t* feat_key_base, const int64_t* ids, const int64_t* offsets,
                           int32_t F, int32_t B, int64_t nnz, int64_t total_keys, int32_t max_dim,
-                          int32_t vec_ok, float* weights, float* state, float lr, float eps,
-                          float grad_scale, void* workspace, size_t workspace_bytes,
-                          tzk_stream_t stream) {
-  TZK_REQUIRE(optimizer >= 0 && optimizer <= 2, "fused_bwd: unknown optimizer %d", optimizer);
+                          int32_t vec_ok, float* weights, float grad_scale, void* workspace,
+                          size_t workspace_bytes, tzk_stream_t stream) {
+  const int32_t optimizer = opt.optimizer;
+  float* state = opt.state;
+  const float lr = opt.lr, eps = opt.eps;
+  TZK_REQUIRE(optimizer >= 0 && optimizer <= TZK_OPT_PARTIAL_ROWWISE_ADAM, "fused_bwd: unknown optimizer %d",
+              optimizer);
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0, "fused_bwd: negative size");
   if (F == 0 || B == 0 || nnz == 0) return 0;
   TZK_REQUIRE(nnz < ((int64_t)1 << 31) && (int64_t)F * std::max(B, 1) < ((int64_t)1 << 31),
@@ -983,6 +1067,8 @@ static int fused_bwd_impl(int phases, int32_t optimizer, int32_t pooled, const f
     TZK_REQUIRE(grad_out && feat_w_off && feat_dim && weights, "fused_bwd: NULL argument");
     TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
     TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
+    TZK_REQUIRE(optimizer < TZK_OPT_ADAM || (opt.state2 && opt.step),
+                "fused_bwd: Adam variants need state2 and the device step counter");
   }
   TZK_REQUIRE(F <= 2048, "fused_bwd: F=%d > 2048 keys per collection", F);
   TZK_REQUIRE(max_dim >= 1 && max_dim <= 1024, "fused_bwd: max_dim=%d out of range [1,1024]", max_dim);
@@ -1040,9 +1126,13 @@ static int fused_bwd_impl(int phases, int32_t optimizer, int32_t pooled, const f
   a.grad_out = grad_out; a.ld_grad = ld_grad; a.offsets = offsets; a.weights = weights; a.state = state;
   a.lr = lr; a.eps = eps; a.grad_scale = grad_scale; a.F = F; a.B = B; a.optimizer = optimizer;
   a.pooled = pooled; a.n = nnz; a.sentinel = sentinel;
+  a.state2 = opt.state2; a.step = opt.step; a.beta1 = opt.beta1; a.beta2 = opt.beta2;
+  a.weight_decay = opt.weight_decay; a.max_gradient = opt.max_gradient; a.bc1 = a.bc2 = 1.f;
 
   const int vec = (vec_ok && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)grad_out % 16 == 0) &&
-                   (ld_grad % 4 == 0) && (optimizer != TZK_OPT_ADAGRAD || (uintptr_t)state % 16 == 0))
+                   (ld_grad % 4 == 0) &&
+                   (!(optimizer == TZK_OPT_ADAGRAD || optimizer >= TZK_OPT_ADAM) || (uintptr_t)state % 16 == 0) &&
+                   (optimizer != TZK_OPT_ADAM || (uintptr_t)opt.state2 % 16 == 0))
                       ? 4 : 1;
   int need = (max_dim + vec - 1) / vec;  // chunks per row
   int G = 1;
@@ -1054,11 +1144,12 @@ static int fused_bwd_impl(int phases, int32_t optimizer, int32_t pooled, const f
   int grid_s = (int)std::min<int64_t>(ceil_div64(nnz, NG), kSmCountB200 * 16);
   // positions per lane group per iteration in run_update (1 = one dependent chain per group, 2/4 = batched
   // single-run path).  Tunable for experiments: TZK_RUN_UPDATE_KPOS=1|2|4.
-  static const int kpos = [] {
+  static const int kpos_env = [] {
     const char* e = getenv("TZK_RUN_UPDATE_KPOS");
     const int v = e ? atoi(e) : 1;
     return (v == 2 || v == 4) ? v : 1;
   }();
+  const int kpos = optimizer >= TZK_OPT_ADAM ? 1 : kpos_env;   // the batched single-run path knows the classic kinds only
 
   // TZK_BWD_TILE=1 selects the tile path.  Measured on DLRM-Criteo (B200, 1.7 M ids): both paths spend ~200 us in
   // the gradient half — the random 64-B weight/state/gradient accesses top out near 2-2.3 TB/s of DRAM traffic either
@@ -1122,6 +1213,13 @@ static int fused_bwd_impl(int phases, int32_t optimizer, int32_t pooled, const f
   return 0;
 }
 
+static tzk_opt_args classic_opt(int32_t optimizer, float* state, float lr, float eps) {
+  tzk_opt_args o;
+  o.optimizer = optimizer; o.lr = lr; o.eps = eps; o.beta1 = 0.9f; o.beta2 = 0.999f; o.weight_decay = 0.f;
+  o.max_gradient = 0.f; o.state = state; o.state2 = nullptr; o.step = nullptr;
+  return o;
+}
+
 extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
                              const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
                              const int32_t* feat_col, const int32_t* feat_pool,
@@ -1130,18 +1228,32 @@ extern "C" int tzk_fused_bwd(int32_t optimizer, int32_t pooled, const float* gra
                              int32_t vec_ok, float* weights, float* state, float lr, float eps,
                              float grad_scale, void* workspace, size_t workspace_bytes,
                              tzk_stream_t stream) {
-  return fused_bwd_impl(3, optimizer, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
-                        feat_key_base, ids, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, state, lr, eps,
-                        grad_scale, workspace, workspace_bytes, stream);
+  TZK_REQUIRE(optimizer >= 0 && optimizer <= TZK_OPT_ROWWISE_ADAGRAD,
+              "fused_bwd: optimizer %d needs tzk_fused_bwd_ex", optimizer);
+  return fused_bwd_impl(3, classic_opt(optimizer, state, lr, eps), pooled, grad_out, ld_grad, feat_w_off, feat_rows,
+                        feat_dim, feat_col, feat_pool, feat_key_base, ids, offsets, F, B, nnz, total_keys, max_dim,
+                        vec_ok, weights, grad_scale, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tzk_fused_bwd_ex(const tzk_opt_args* opt, int32_t pooled, const float* grad_out, int64_t ld_grad,
+                                const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                                const int32_t* feat_col, const int32_t* feat_pool, const int64_t* feat_key_base,
+                                const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int64_t nnz,
+                                int64_t total_keys, int32_t max_dim, int32_t vec_ok, float* weights,
+                                float grad_scale, void* workspace, size_t workspace_bytes, tzk_stream_t stream) {
+  TZK_REQUIRE(opt != nullptr, "fused_bwd_ex: opt is NULL");
+  return fused_bwd_impl(3, *opt, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
+                        feat_key_base, ids, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, grad_scale,
+                        workspace, workspace_bytes, stream);
 }
 
 extern "C" int tzk_fused_bwd_sort(int32_t pooled, const int64_t* feat_rows, const int64_t* feat_key_base,
                                   const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int64_t nnz,
                                   int64_t total_keys, int32_t max_dim, void* workspace, size_t workspace_bytes,
                                   tzk_stream_t stream) {
-  return fused_bwd_impl(1, TZK_OPT_SGD, pooled, nullptr, 0, nullptr, feat_rows, nullptr, nullptr, nullptr,
-                        feat_key_base, ids, offsets, F, B, nnz, total_keys, max_dim, 0, nullptr, nullptr, 0.f, 0.f,
-                        0.f, workspace, workspace_bytes, stream);
+  return fused_bwd_impl(1, classic_opt(TZK_OPT_SGD, nullptr, 0.f, 0.f), pooled, nullptr, 0, nullptr, feat_rows,
+                        nullptr, nullptr, nullptr, feat_key_base, ids, offsets, F, B, nnz, total_keys, max_dim, 0,
+                        nullptr, 0.f, workspace, workspace_bytes, stream);
 }
 
 extern "C" int tzk_fused_bwd_apply(int32_t optimizer, int32_t pooled, const float* grad_out, int64_t ld_grad,
@@ -1151,9 +1263,24 @@ extern "C" int tzk_fused_bwd_apply(int32_t optimizer, int32_t pooled, const floa
                                    int64_t nnz, int64_t total_keys, int32_t max_dim, int32_t vec_ok, float* weights,
                                    float* state, float lr, float eps, float grad_scale, void* workspace,
                                    size_t workspace_bytes, tzk_stream_t stream) {
-  return fused_bwd_impl(2, optimizer, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
-                        feat_key_base, nullptr, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, state, lr,
-                        eps, grad_scale, workspace, workspace_bytes, stream);
+  TZK_REQUIRE(optimizer >= 0 && optimizer <= TZK_OPT_ROWWISE_ADAGRAD,
+              "fused_bwd_apply: optimizer %d needs tzk_fused_bwd_apply_ex", optimizer);
+  return fused_bwd_impl(2, classic_opt(optimizer, state, lr, eps), pooled, grad_out, ld_grad, feat_w_off, feat_rows,
+                        feat_dim, feat_col, feat_pool, feat_key_base, nullptr, offsets, F, B, nnz, total_keys,
+                        max_dim, vec_ok, weights, grad_scale, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tzk_fused_bwd_apply_ex(const tzk_opt_args* opt, int32_t pooled, const float* grad_out,
+                                      int64_t ld_grad, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                      const int32_t* feat_dim, const int32_t* feat_col, const int32_t* feat_pool,
+                                      const int64_t* feat_key_base, const int64_t* offsets, int32_t F, int32_t B,
+                                      int64_t nnz, int64_t total_keys, int32_t max_dim, int32_t vec_ok,
+                                      float* weights, float grad_scale, void* workspace, size_t workspace_bytes,
+                                      tzk_stream_t stream) {
+  TZK_REQUIRE(opt != nullptr, "fused_bwd_apply_ex: opt is NULL");
+  return fused_bwd_impl(2, *opt, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
+                        feat_key_base, nullptr, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, grad_scale,
+                        workspace, workspace_bytes, stream);
 }
 
 extern "C" int tzk_bag_grad_expand(const float* grad_out, int64_t ld_grad, const int32_t* feat_col,

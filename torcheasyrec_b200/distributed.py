@@ -188,7 +188,8 @@ class _Dispatch:
             raise RuntimeError("sharded collection: no sparse optimizer set (call set_optimizer)")
         if self.n_recv:
             k.fused_bwd(spec.kind, False, recv_g, g.local.weights.data, g.local.opt_state, g.owner_layout,
-                        self.recv_ids, self.bounds, 1, spec.lr, spec.eps, 1.0 / g.world)   # App. A.6: /W
+                        self.recv_ids, self.bounds, 1, spec.lr, spec.eps, 1.0 / g.world,   # App. A.6: /W
+                        **g.local.opt_extras())
 
 
 class _StaticDispatch:
@@ -245,7 +246,7 @@ class _StaticDispatch:
         if spec is None:
             raise RuntimeError("sharded collection: no sparse optimizer set (call set_optimizer)")
         k.fused_bwd(spec.kind, False, recv_g, g.local.weights.data, g.local.opt_state, g.owner_layout_static,
-                    self.recv_ids, self.bounds, 1, spec.lr, spec.eps, 1.0 / g.world)
+                    self.recv_ids, self.bounds, 1, spec.lr, spec.eps, 1.0 / g.world, **g.local.opt_extras())
 
 
 def _dispatch(g: _DimGroup, kjt: KeyedJaggedTensor, group):

@@ -19,7 +19,8 @@ import torch
 from torch import nn
 
 from . import functional as Fn
-from .kernels import OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_SGD, POOL_MEAN, POOL_SUM, FeatureLayout, build_layout
+from .kernels import (OPT_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM, OPT_ROWWISE_ADAGRAD, OPT_SGD, POOL_MEAN, POOL_SUM,
+                      FeatureLayout, build_layout)
 from .sparse import JaggedTensor, KeyedJaggedTensor, KeyedTensor
 
 
@@ -65,11 +66,16 @@ class SparseOptimizerSpec:
     lr: float = 0.001
     eps: float = 1e-8                      # fbgemm TBE default (App. A.10)
     initial_accumulator_value: float = 0.0  # optimizer_builder.py:57-61
+    beta1: float = 0.9                      # Adam variants (optimizer.proto:89-131)
+    beta2: float = 0.999
+    weight_decay: float = 0.0
+    max_gradient: float = 0.0               # > 0 <=> gradient_clipping: clamp the summed row gradient
 
     @staticmethod
     def from_name(name: str, **kw) -> "SparseOptimizerSpec":
         kinds = {"sgd": OPT_SGD, "adagrad": OPT_ADAGRAD, "rowwise_adagrad": OPT_ROWWISE_ADAGRAD,
-                 "row_wise_adagrad": OPT_ROWWISE_ADAGRAD}
+                 "row_wise_adagrad": OPT_ROWWISE_ADAGRAD, "adam": OPT_ADAM,
+                 "partial_rowwise_adam": OPT_PARTIAL_ROWWISE_ADAM}
         return SparseOptimizerSpec(kind=kinds[name.lower()], **kw)
 
 
@@ -146,6 +152,8 @@ class _ArenaCollection(nn.Module):
                                     requires_grad=False)
         self._opt: Optional[SparseOptimizerSpec] = None
         self.register_buffer("opt_state", None, persistent=False)
+        self.register_buffer("opt_state2", None, persistent=False)
+        self.register_buffer("opt_step", None, persistent=False)
         self._hook = None
         self.grad_scale = 1.0  # sharded wrappers set 1/W here (App. A.6)
         if self._device.type != "meta":
@@ -171,7 +179,7 @@ class _ArenaCollection(nn.Module):
     def table_state(self, t: int) -> Optional[torch.Tensor]:
         if self.opt_state is None:
             return None
-        if self._opt.kind == OPT_ADAGRAD:
+        if self._opt.kind in (OPT_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM):
             o = self._table_off[t]
             return self.opt_state[o:o + self._table_rows[t] * self._table_dim[t]].view(self._table_rows[t], -1)
         k = self._table_key[t]
@@ -256,8 +264,31 @@ class _ArenaCollection(nn.Module):
         elif spec.kind == OPT_ROWWISE_ADAGRAD:
             self.opt_state = torch.full((self.layout.total_keys,), spec.initial_accumulator_value,
                                         dtype=torch.float32, device=dev)
+        elif spec.kind in (OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM):
+            self.opt_state = torch.zeros(self.layout.arena_elems, dtype=torch.float32, device=dev)    # momentum1
+            n2 = self.layout.arena_elems if spec.kind == OPT_ADAM else self.layout.total_keys
+            self.opt_state2 = torch.zeros(n2, dtype=torch.float32, device=dev)                        # momentum2
+            self.opt_step = torch.zeros((), dtype=torch.float32, device=dev)                          # iteration t
         else:
             self.opt_state = None
+        if spec.kind not in (OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM):
+            self.opt_state2, self.opt_step = None, None
+
+    def opt_extras(self, bump: bool = True) -> dict:
+        """Keyword arguments of the extended update (tzk_opt_args) — empty for the classic kinds without clipping.
+        `bump` advances the device-side step counter first (one call per backward)."""
+        spec = self._opt
+        if spec is None:
+            return {}
+        ex = {}
+        if spec.kind in (OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM):
+            if bump:
+                self.opt_step.add_(1.0)
+            ex.update(state2=self.opt_state2, step=self.opt_step, beta1=spec.beta1, beta2=spec.beta2,
+                      weight_decay=spec.weight_decay)
+        if spec.max_gradient > 0 or ex:
+            ex["max_gradient"] = spec.max_gradient
+        return ex
 
     @property
     def optimizer(self) -> Optional[SparseOptimizerSpec]:
@@ -334,10 +365,10 @@ def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> Non
         mod._early_busy = False
         torch.cuda.current_stream().wait_stream(side)
         k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,
-                          ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws)
+                          ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws, **mod.opt_extras())
     else:
         k.fused_bwd(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, ids, offsets, ctx.B,
-                    spec.lr, spec.eps, mod.grad_scale)
+                    spec.lr, spec.eps, mod.grad_scale, **mod.opt_extras())
 
 
 class _PooledLookup(torch.autograd.Function):

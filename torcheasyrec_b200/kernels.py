@@ -15,7 +15,7 @@ import torch
 from ._lib import TzkError, check, lib
 
 POOL_SUM, POOL_MEAN = 0, 1
-OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD = 0, 1, 2
+OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM = 0, 1, 2, 3, 4
 
 
 @dataclass
@@ -126,6 +126,21 @@ def _tile_path(lay: "FeatureLayout") -> bool:
     return os.environ.get("TZK_BWD_TILE", "0") == "1" and bool(lay.vec_ok) and lay.max_dim <= 128
 
 
+def _opt_args(optimizer: int, state, lr: float, eps: float, ex: dict):
+    """tzk_opt_args (include/tzk.h) for the _ex entry points; keeps the tensors it points to alive via the caller."""
+    from ._lib import TzkOptArgs
+
+    st2, step = ex.get("state2"), ex.get("step")
+    if optimizer >= OPT_ADAM and (st2 is None or step is None):
+        raise TzkError("Adam variants need state2 and the device step counter")
+    for t, nm in ((st2, "state2"), (step, "step")):
+        if t is not None:
+            _need(t, torch.float32, nm)
+    return TzkOptArgs(optimizer, lr, eps, float(ex.get("beta1", 0.9)), float(ex.get("beta2", 0.999)),
+                      float(ex.get("weight_decay", 0.0)), float(ex.get("max_gradient", 0.0)),
+                      _ptr(state), _ptr(st2), _ptr(step))
+
+
 class CudaKernels:
     """sm_100a implementation of the hot path.  Stateless apart from cached workspaces."""
 
@@ -195,7 +210,8 @@ class CudaKernels:
     # ------------------------------------------------------------------ K5
     def fused_bwd(self, optimizer: int, pooled: bool, grad_out: torch.Tensor, weights: torch.Tensor,
                   state: Optional[torch.Tensor], lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
-                  B: int, lr: float, eps: float, grad_scale: float = 1.0) -> None:
+                  B: int, lr: float, eps: float, grad_scale: float = 1.0, **ex) -> None:
+        """`ex` (optional): state2, step, beta1, beta2, weight_decay, max_gradient -> tzk_fused_bwd_ex."""
         _need(weights, torch.float32, "weights")
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
@@ -206,11 +222,19 @@ class CudaKernels:
         nnz = ids.numel()
         nb = self._lib.tzk_fused_bwd_workspace_bytes(nnz, lay.total_keys, lay.max_dim)
         ws = self._workspace("bwd", nb, weights.device)
-        check(self._lib.tzk_fused_bwd(
-            optimizer, int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
-            _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets), F, B, nnz,
-            lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
-            _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
+        if ex:
+            oa = _opt_args(optimizer, state, lr, eps, ex)
+            check(self._lib.tzk_fused_bwd_ex(
+                ctypes.byref(oa), int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows),
+                _ptr(lay.d_dim), _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets),
+                F, B, nnz, lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), grad_scale, _ptr(ws), ws.numel(),
+                _stream()), "tzk_fused_bwd_ex")
+        else:
+            check(self._lib.tzk_fused_bwd(
+                optimizer, int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
+                _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets), F, B, nnz,
+                lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
+                _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
         # own launches next to CUB's radix sort: tile path = linearize, tile_update, carry_combine;
         # general path (unaligned / > 128 floats) = zero_counters, linearize, run_update, long_chunk, long_combine
         self.launches += 3 if _tile_path(lay) else 5
@@ -234,17 +258,25 @@ class CudaKernels:
 
     def fused_bwd_apply(self, optimizer: int, pooled: bool, grad_out: torch.Tensor, weights: torch.Tensor,
                         state: Optional[torch.Tensor], lay: FeatureLayout, offsets: torch.Tensor, nnz: int, B: int,
-                        lr: float, eps: float, grad_scale: float, ws: torch.Tensor) -> None:
+                        lr: float, eps: float, grad_scale: float, ws: torch.Tensor, **ex) -> None:
         _need(weights, torch.float32, "weights")
         _need(offsets, torch.int64, "offsets")
         grad_out, ld = _rows2d(grad_out, "grad_out")
         if state is not None:
             _need(state, torch.float32, "state")
-        check(self._lib.tzk_fused_bwd_apply(
-            optimizer, int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
-            _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(offsets), lay.num_features, B, nnz,
-            lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
-            _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_apply")
+        if ex:
+            oa = _opt_args(optimizer, state, lr, eps, ex)
+            check(self._lib.tzk_fused_bwd_apply_ex(
+                ctypes.byref(oa), int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows),
+                _ptr(lay.d_dim), _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(offsets),
+                lay.num_features, B, nnz, lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), grad_scale,
+                _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_apply_ex")
+        else:
+            check(self._lib.tzk_fused_bwd_apply(
+                optimizer, int(pooled), _ptr(grad_out), ld, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
+                _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(offsets), lay.num_features, B, nnz,
+                lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
+                _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_apply")
         self.launches += 2 if _tile_path(lay) else 4
 
     # ------------------------------------------------------------------ K1 / K2

@@ -19,7 +19,7 @@ from .config import Message, config_to_kwargs
 from .embedding_group import EmbeddingGroup
 from .embedding_modules import SparseOptimizerSpec
 from .features import BaseFeature
-from .kernels import OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_SGD
+from .kernels import OPT_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM, OPT_ROWWISE_ADAGRAD, OPT_SGD
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -427,13 +427,21 @@ def sparse_optimizer_from_config(train_config: Message) -> SparseOptimizerSpec:
     so = train_config.sparse_optimizer
     kind = so.WhichOneof("optimizer")
     cfg = getattr(so, kind)
+    clip = dict(max_gradient=float(cfg.max_gradient) if cfg.gradient_clipping else 0.0)
     if kind == "sgd_optimizer":
-        return SparseOptimizerSpec(kind=OPT_SGD, lr=cfg.lr)
+        return SparseOptimizerSpec(kind=OPT_SGD, lr=cfg.lr, **clip)
     if kind == "adagrad_optimizer":
-        return SparseOptimizerSpec(kind=OPT_ADAGRAD, lr=cfg.lr, initial_accumulator_value=cfg.initial_accumulator_value)
+        return SparseOptimizerSpec(kind=OPT_ADAGRAD, lr=cfg.lr, initial_accumulator_value=cfg.initial_accumulator_value,
+                                   **clip)
     if kind == "rowwise_adagrad_optimizer":
-        return SparseOptimizerSpec(kind=OPT_ROWWISE_ADAGRAD, lr=cfg.lr)
-    raise NotImplementedError(f"sparse optimizer {kind} is not implemented (sgd / adagrad / rowwise_adagrad are)")
+        if cfg.weight_decay:
+            raise NotImplementedError("rowwise_adagrad weight_decay modes are not implemented")
+        return SparseOptimizerSpec(kind=OPT_ROWWISE_ADAGRAD, lr=cfg.lr, **clip)
+    if kind in ("adam_optimizer", "partial_rowwise_adam_optimizer"):
+        return SparseOptimizerSpec(kind=OPT_ADAM if kind == "adam_optimizer" else OPT_PARTIAL_ROWWISE_ADAM, lr=cfg.lr,
+                                   beta1=cfg.beta1, beta2=cfg.beta2, weight_decay=cfg.weight_decay, **clip)
+    raise NotImplementedError(f"sparse optimizer {kind} is not implemented (sgd / adagrad / rowwise_adagrad / adam / "
+                              "partial_rowwise_adam are; lars_sgd, lamb, partial_rowwise_lamb, adadelta, rmsprop are not)")
 
 
 def dense_optimizer_from_config(train_config: Message, params, **kw) -> torch.optim.Optimizer:
