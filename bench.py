@@ -140,7 +140,6 @@ def cpu_step_rate(model: str, batch: int, steps: int, warmup: int, max_rows: int
 
 def run_reference(args):
     rank, _, world = dist_env()
-    args._zipf_ms = zipf
     if rank != 0:
         return
     import psutil
@@ -172,6 +171,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 def time_kernel(fn, iters: int):
     """Average duration (ms) of `fn` launches, CUDA events on the launching (current) stream."""
+    for i in range(3):          # untimed: lazy module loads, first-touch allocations of the outputs
+        fn(i)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     torch.cuda.synchronize()
     for i in range(iters):
@@ -259,24 +260,6 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    # ---- second id distribution (SURVEY.md §8d reports both): the same captured step on Zipf(1.05) ids -------
-    zipf = None
-    if args.id_dist == "uniform" and not args.no_zipf and not sharded:   # (row-wise blocks + Zipf overflow a fixed wire capacity)
-        zring = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + 500 + i, id_dist="zipf").to(dev)
-                 for i in range(min(args.ring, 4))]
-        for i in range(3):
-            step.load(zring[i % len(zring)])
-            step.replay()
-        barrier()
-        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        z0.record()
-        for i in range(K):
-            step.load(zring[i % len(zring)])
-            step.replay()
-        z1.record()
-        barrier()
-        zipf = z0.elapsed_time(z1)
-        del zring
     # ---- e2e: pinned host batch -> H2D -> step -> loss back on the host, every step --------------------------
     # (N=1: the H2D of batch i+1 runs on the copy stream while step i computes; the loss of every step is read)
     piped = graphed
@@ -300,6 +283,24 @@ def run_ours(args):
     g1.record()
     barrier()
     ms_e2e = g0.elapsed_time(g1)
+    # ---- second id distribution (SURVEY.md §8d reports both): the same captured step on Zipf(1.05) ids -------
+    zipf = None
+    if args.id_dist == "uniform" and not args.no_zipf and not sharded:   # (row-wise blocks + Zipf overflow a fixed wire capacity)
+        zring = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + 500 + i, id_dist="zipf").to(dev)
+                 for i in range(min(args.ring, 4))]
+        for i in range(3):
+            step.load(zring[i % len(zring)])
+            step.replay()
+        barrier()
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record()
+        for i in range(K):
+            step.load(zring[i % len(zring)])
+            step.replay()
+        z1.record()
+        barrier()
+        zipf = z0.elapsed_time(z1)
+        del zring
     clk = clocks.stop() if clocks else None
     pipe.check_overflow()      # static-capacity exchange: no peer needed more than its wire capacity
     if world > 1:
@@ -309,6 +310,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e, zz = t.tolist()
         zipf = zz if zipf is not None else None
+    args._zipf_ms = zipf
     if rank != 0:
         return
 

@@ -332,14 +332,15 @@ class _ArenaCollection(nn.Module):
         return kjt.permute([pos[f] for f in self._feature_names])
 
 
-def _early_sort(ctx, mod, pooled: bool, ids, offsets, B) -> None:
+def _early_sort(ctx, mod, pooled: bool, ids, offsets, B, want_grad: bool) -> None:
     """Enqueue the id-only half of the fused backward (linearize + radix sort) on the module's side stream right
     away: it overlaps the rest of the forward pass and the dense backward instead of sitting on the critical path
     (the role TrainPipelineSparseDist's data-dist stream plays in the reference, tzrec/utils/dist_util.py:221-303).
     The backward then only joins the stream and runs the gradient-dependent half."""
     ctx.early = None
     k = Fn.backend()
-    if (mod.training and torch.is_grad_enabled() and ids.is_cuda and ids.numel() > 0
+    # (`want_grad` comes from the caller: inside autograd.Function.forward grad mode is always off)
+    if (mod.training and want_grad and ids.is_cuda and ids.numel() > 0
             and hasattr(k, "fused_bwd_sort") and mod.optimizer is not None
             and not getattr(mod, "_early_busy", False)      # one outstanding lookup per module owns the workspace
             and os.environ.get("TZK_EARLY_SORT", "1") != "0"):
@@ -377,7 +378,7 @@ class _PooledLookup(torch.autograd.Function):
         out = Fn.backend().pooled_gather_fwd(mod.weights.data, mod.layout, ids, offsets, B)
         ctx.mod, ctx.B = mod, B
         ctx.save_for_backward(ids, offsets)
-        _early_sort(ctx, mod, True, ids, offsets, B)
+        _early_sort(ctx, mod, True, ids, offsets, B, hook is not None)
         return out
 
     @staticmethod
@@ -393,7 +394,7 @@ class _SeqLookup(torch.autograd.Function):
         out = Fn.backend().seq_gather_fwd(mod.weights.data, mod.layout, ids, offsets, B)
         ctx.mod, ctx.B = mod, B
         ctx.save_for_backward(ids, offsets)
-        _early_sort(ctx, mod, False, ids, offsets, B)
+        _early_sort(ctx, mod, False, ids, offsets, B, hook is not None)
         return out
 
     @staticmethod
