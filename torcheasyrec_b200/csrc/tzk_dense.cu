@@ -172,14 +172,15 @@ __device__ __forceinline__ void stage_x(float* X, const float* dense, int64_t ld
 
 // DT = compile-time embedding dim (0 = take the runtime value): with DT known every /D, %D and swizzle offset
 // folds into shifts and the k loop unrolls — the kernel is issue-bound, not bandwidth-bound, otherwise.
-template <int DT, bool ONE, int OCC>
+template <int DT, bool ONE, int OCC, int NT>
 __global__ void __launch_bounds__(kIWarps * 32, OCC)
 dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
                         int64_t ld_sparse, int64_t B, int Ns, int D_rt, int copy_dense, int copy_sparse, int p_pad,
                         int aligned, float* __restrict__ out, int64_t ld_out) {
   extern __shared__ __align__(16) float smem[];
   const int D = DT ? DT : D_rt;
-  const int N = Ns + (dense != nullptr);
+  if (NT) Ns = NT - 1;                // NT > 0: compile-time feature count incl. the dense row (dense != NULL)
+  const int N = NT ? NT : Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;        // rows padded to a multiple of 4 (pad rows are zero)
   const int DS = D + 4;               // row stride
   const int P = N * (N - 1) / 2;
@@ -355,7 +356,9 @@ dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
 }
 
 // backward: dX = (G + G^T) X (+ pass-through grads); lane owns 4 rows x 4 cols blocks of dX.
-template <int DT>
+// NT = compile-time feature count INCLUDING the dense row (0 = runtime; NT > 0 requires dense != NULL): the j loop
+// unrolls completely and every shared-memory address becomes base register + immediate.
+template <int DT, int NT>
 __global__ void __launch_bounds__(kIWarps * 32, 4)
 dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
                         int64_t ld_sparse, const float* __restrict__ d_out, int64_t ld_dout, int64_t B,
@@ -364,7 +367,8 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
                         int64_t ld_dsparse) {
   extern __shared__ __align__(16) float smem[];
   const int D = DT ? DT : D_rt;
-  const int N = Ns + (dense != nullptr);
+  if (NT) Ns = NT - 1;
+  const int N = NT ? NT : Ns + (dense != nullptr);
   const int Np = (N + 3) & ~3;
   const int DS = D + 4;
   const int SS = Np + 8;  // stride of the symmetric grad matrix: the transposed scatter is 4-way, not 32-way
@@ -421,16 +425,34 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      const float* Sb = S + bi * 4;
+      if (NT) {
+        int xo[4];  // swizzled chunk offset for (j >> 3) & 3 = 0..3
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xo[q] = (c4 ^ (q & swm)) << 2;
+#pragma unroll
+        for (int j = 0; j < (NT ? NT : 1); ++j) {
+          const float4 s4 = *reinterpret_cast<const float4*>(Sb + j * SS);
+          const float4 x4 = *reinterpret_cast<const float4*>(X + j * DS + xo[(j >> 3) & 3]);
+          const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(sv[r], xv[c], acc[r][c]);
+        }
+      } else {
 #pragma unroll 3
-      for (int j = 0; j < N; ++j) {
-        const float4 s4 = *reinterpret_cast<const float4*>(S + j * SS + bi * 4);
-        const float4 x4 = *reinterpret_cast<const float4*>(X + xoff(j, c4, DS, swm));
-        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        for (int j = 0; j < N; ++j) {
+          const float4 s4 = *reinterpret_cast<const float4*>(Sb + j * SS);
+          const float4 x4 = *reinterpret_cast<const float4*>(X + xoff(j, c4, DS, swm));
+          const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(sv[r], xv[c], acc[r][c]);
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(sv[r], xv[c], acc[r][c]);
+        }
       }
       // pass-through grads and store (16-B vector stores; d_out offsets are not 16-B aligned -> scalar loads)
 #pragma unroll
@@ -563,14 +585,19 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int aligned = (((P + p_pad) % 4) == 0) && (ld_out % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const int nb = Np / 4, n_blocks = nb * (nb + 1) / 2;
   size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3 + 4) & ~3))) * sizeof(float);
-#define TZK_IFWD3(DT_, ONE_, OCC_)                                                                             \
+#define TZK_IFWD4(DT_, ONE_, OCC_, NT_)                                                                        \
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
-      cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_, ONE_, OCC_>,                                         \
+      cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_, ONE_, OCC_, NT_>,                                    \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-    dot_interact_fwd_kernel<DT_, ONE_, OCC_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem,    \
-                                               as_stream(stream)>>>(                                         \
+    dot_interact_fwd_kernel<DT_, ONE_, OCC_, NT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32,     \
+                                                    smem, as_stream(stream)>>>(                              \
         dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, p_pad, aligned, out, ld_out); \
+  } while (0)
+#define TZK_IFWD3(DT_, ONE_, OCC_)                                                       \
+  do {                                                                                   \
+    if (DT_ == 16 && ONE_ && OCC_ == 4 && N == 27 && dense) TZK_IFWD4(16, true, 4, 27);  \
+    else TZK_IFWD4(DT_, ONE_, OCC_, 0);                                                  \
   } while (0)
 #define TZK_IFWD2(DT_, ONE_)                    \
   do {                                          \
@@ -598,6 +625,7 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
 #undef TZK_IFWD
 #undef TZK_IFWD2
 #undef TZK_IFWD3
+#undef TZK_IFWD4
   TZK_CHECK_LAUNCH("dot_interact_fwd_kernel");
   return 0;
 }
@@ -620,20 +648,25 @@ extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const 
   TZK_REQUIRE(p_pad >= 0 && p_pad < 4, "dot_interact_bwd: p_pad must be in [0,3]");
   const int aligned = (((P + p_pad) % 4) == 0) && (ld_dout % 4 == 0) && ((uintptr_t)d_out % 16 == 0);
   size_t smem = ((size_t)((P + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + Np * (Np + 8))) * sizeof(float);
-#define TZK_IBWD(DT_)                                                                                         \
+#define TZK_IBWD(DT_, NT_)                                                                                    \
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
-      cudaFuncSetAttribute(dot_interact_bwd_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    dot_interact_bwd_kernel<DT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem, as_stream(stream)>>>( \
-        dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, Ns, D, copy_dense, copy_sparse, p_pad, aligned,     \
-        d_dense, ld_ddense, d_sparse, ld_dsparse);                                                                               \
+      cudaFuncSetAttribute(dot_interact_bwd_kernel<DT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           (int)smem);                                                                       \
+    dot_interact_bwd_kernel<DT_, NT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem,           \
+                                        as_stream(stream)>>>(                                                \
+        dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, Ns, D, copy_dense, copy_sparse, p_pad, aligned, \
+        d_dense, ld_ddense, d_sparse, ld_dsparse);                                                           \
   } while (0)
   switch (D) {
-    case 8: TZK_IBWD(8); break;
-    case 16: TZK_IBWD(16); break;
-    case 32: TZK_IBWD(32); break;
-    case 64: TZK_IBWD(64); break;
-    default: TZK_IBWD(0); break;
+    case 8: TZK_IBWD(8, 0); break;
+    case 16:
+      if (N == 27 && dense) TZK_IBWD(16, 27);   // DLRM-Criteo: 26 sparse + the dense row, fully unrolled
+      else TZK_IBWD(16, 0);
+      break;
+    case 32: TZK_IBWD(32, 0); break;
+    case 64: TZK_IBWD(64, 0); break;
+    default: TZK_IBWD(0, 0); break;
   }
 #undef TZK_IBWD
   TZK_CHECK_LAUNCH("dot_interact_bwd_kernel");
