@@ -163,7 +163,7 @@ def run_reference(args):
                                    "needs torchrec/fbgemm wheels that are not installable offline"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _print_line(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -435,7 +435,7 @@ def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    _print_line(line)
 
 
 def _small_host() -> bool:
@@ -447,8 +447,29 @@ def _small_host() -> bool:
         return True
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything that libraries print to fd 1 while the benchmark runs (NCCL's version banner, cuBLAS notices) goes
+    to stderr; the ONE JSON line is written to the real stdout by _print_line()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _print_line(line: dict) -> None:
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
