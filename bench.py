@@ -26,7 +26,10 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # CPU baseline: idle OpenMP workers must not spin
 os.environ.setdefault("GOMP_SPINCOUNT", "0")
 if "--impl" in sys.argv and "reference" in sys.argv:
-    os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 32)))
+    # the CPU arm uses all the host threads it can use; torchrun's blanket OMP_NUM_THREADS=1 is a launcher default,
+    # not a user choice (libgomp reads the variable once, when torch loads it below)
+    if "OMP_NUM_THREADS" not in os.environ or "TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(min(os.cpu_count() or 1, 32))
 
 import torch  # noqa: E402
 
@@ -146,7 +149,7 @@ def run_reference(args):
 
     # full hash sizes need 2 x 12.2 GiB of host RAM (tables + Adagrad state); cap them if the box is small
     max_rows = args.max_rows
-    note = "full hash sizes"
+    note = f"tables capped at {max_rows} rows" if max_rows else "full hash sizes"
     if not max_rows and psutil.virtual_memory().available < 40 * 2 ** 30:
         max_rows, note = 4_000_000, "tables capped at 4M rows (host RAM < 40 GiB)"
     steps = max(1, min(args.steps, 3))
