@@ -69,3 +69,25 @@ def test_text_format_features():
     assert cfg.unknown_block.inner == [3, 4]
     edit_config(cfg, {"train_config.num_steps": 5, "model_config.feature_groups[0].group_name": "h"})
     assert cfg.train_config.num_steps == 5 and cfg.model_config.feature_groups[0].group_name == "h"
+
+
+def test_sparse_optimizer_mapping_from_train_config():
+    """tzrec/optim/optimizer_builder.py:30-97: every fused optimizer the kernels implement, with clipping."""
+    from torcheasyrec_b200.config import parse_text
+    from torcheasyrec_b200.kernels import OPT_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM, OPT_ROWWISE_ADAGRAD, OPT_SGD
+    from torcheasyrec_b200.rank_models import sparse_optimizer_from_config
+
+    def spec(body):
+        return sparse_optimizer_from_config(parse_text("train_config { sparse_optimizer { %s } }" % body).train_config)
+
+    s = spec("adagrad_optimizer { lr: 0.001 }")
+    assert (s.kind, s.max_gradient) == (OPT_ADAGRAD, 0.0) and abs(s.lr - 0.001) < 1e-9
+    s = spec("sgd_optimizer { lr: 0.1 gradient_clipping: true max_gradient: 0.5 }")
+    assert (s.kind, s.max_gradient) == (OPT_SGD, 0.5)
+    s = spec("rowwise_adagrad_optimizer { lr: 0.02 }")
+    assert s.kind == OPT_ROWWISE_ADAGRAD
+    s = spec("adam_optimizer { lr: 0.01 beta1: 0.8 beta2: 0.95 weight_decay: 0.001 gradient_clipping: true }")
+    assert s.kind == OPT_ADAM and abs(s.beta1 - 0.8) < 1e-6 and abs(s.beta2 - 0.95) < 1e-6
+    assert abs(s.weight_decay - 0.001) < 1e-9 and s.max_gradient == 1.0        # proto default max_gradient
+    s = spec("partial_rowwise_adam_optimizer { lr: 0.01 }")
+    assert s.kind == OPT_PARTIAL_ROWWISE_ADAM and s.max_gradient == 0.0

@@ -364,9 +364,28 @@ def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> Non
     if ctx.early is not None:
         ws, side = ctx.early
         mod._early_busy = False
-        torch.cuda.current_stream().wait_stream(side)
-        k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,
-                          ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws, **mod.opt_extras())
+        cur = torch.cuda.current_stream()
+        extras = mod.opt_extras()          # (advances the device step counter on `cur`)
+        if os.environ.get("TZK_ASYNC_APPLY", "1") != "0":
+            # The gradient half stays on the side stream (it is already ordered after the sort there) and the rest of
+            # the backward pass — whatever autograd schedules after this node, e.g. the bottom MLP of DLRM — runs
+            # next to it; the stream is joined when the backward pass ends.  Nothing between here and the join reads
+            # or writes the tables.
+            side.wait_stream(cur)          # the gradient (and the step counter) were produced on `cur`
+            with torch.cuda.stream(side):
+                k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,
+                                  ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws, **extras)
+            mod._pending_apply = grad      # keeps the gradient buffer away from the allocator until the join
+
+            def _join(mod=mod, cur=cur, side=side):
+                cur.wait_stream(side)
+                mod._pending_apply = None
+
+            torch.autograd.Variable._execution_engine.queue_callback(_join)
+        else:
+            cur.wait_stream(side)
+            k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,
+                              ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws, **extras)
     else:
         k.fused_bwd(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, ids, offsets, ctx.B,
                     spec.lr, spec.eps, mod.grad_scale, **mod.opt_extras())

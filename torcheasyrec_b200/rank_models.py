@@ -291,9 +291,15 @@ class DLRM(RankModel):
         self.output_mlp = _Linear(self.final_mlp.output_dim(), self._num_class)
 
     def predict(self, batch: Batch) -> Dict[str, torch.Tensor]:
+        # The bottom MLP only needs the raw dense features.  Running it BEFORE the lookups gives its autograd nodes
+        # the lower sequence numbers, so in the backward pass the lookups' node — which launches the fused sparse
+        # update on the collection's side stream — is scheduled first and the bottom-MLP backward overlaps it.
+        dense_in = self._dense_group_input(batch) if self.dense_mlp else None
+        dense_feat = self.dense_mlp(dense_in) if dense_in is not None else None
         grouped = self.build_input(batch)
         sparse = grouped[self._sparse_group_name]
-        dense_feat = self.dense_mlp(grouped[self._dense_group_name]) if self.dense_mlp else None
+        if self.dense_mlp and dense_feat is None:
+            dense_feat = self.dense_mlp(grouped[self._dense_group_name])
         # interaction + both concats of dlrm.py:113-131 in one kernel
         # the 783-wide result travels as [B, 784]: one zero column after the 351 interaction terms puts the dense
         # and sparse blocks (and every row) on 16-B boundaries -> 128-bit stores in the kernel and tensor-core
@@ -302,6 +308,21 @@ class DLRM(RankModel):
                                                with_dense=True,
                                                with_sparse=bool(self._model_config.arch_with_sparse), aligned=True)
         return self._output_to_prediction(self.output_mlp(self.final_mlp(all_feat, in_map)))
+
+
+    def _dense_group_input(self, batch: Batch) -> Optional[torch.Tensor]:
+        """[B, 13]-style input of the `dense` group when it consists of raw dense features only (the usual DLRM
+        config); None -> fall back to the grouped dictionary."""
+        eg = self.embedding_group
+        impl = next(iter(eg.emb_impls.values())) if len(eg.emb_impls) == 1 else None
+        if impl is None or not impl.has_dense:
+            return None
+        key = next(iter(eg.emb_impls.keys()))
+        kt = batch.dense_features.get(key)
+        names = impl._group_to_shared_feature_names.get(self._dense_group_name)
+        if kt is None or names is None or list(kt.keys()) != list(names):
+            return None
+        return kt.values()
 
 
 class DeepFM(RankModel):
