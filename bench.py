@@ -37,8 +37,8 @@ METRIC = "samples/sec (DLRM-Criteo synth, train step fwd+bwd+optimizer)"
 UNIT = "samples/s"
 # DLRM-Criteo (F=26, L=1, D=16) per-sample algorithmic bytes, SURVEY.md §8d — computed from the layout at run time:
 #   gather 1664 rows + 1664 pooled write + 208 ids + 104 lengths = 3640 B; backward 1664 grad + 26*4*64 RMW + 208 = 8528 B
-NCU_TRAFFIC_BYTES = {"pooled_gather_fwd_kernel": 111.339008e6 + 55.679232e6,   # dram rd + wr, one launch (ncu --set full)
-                     "run_update_kernel": 282.46656e6 + 50.44352e6,     # largest kernel of the fused backward (default path)
+NCU_TRAFFIC_BYTES = {"pooled_gather_fwd_kernel": 111.276e6 + 56.952e6,          # dram rd + wr, one launch (ncu --set full)
+                     "run_update_kernel": 282.823e6 + 50.973e6,         # largest kernel of the fused backward (default path)
                      "tile_update_kernel": 344.51072e6 + 52.342784e6}   # TZK_BWD_TILE=1 path
 
 
