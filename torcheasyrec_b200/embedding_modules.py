@@ -14,6 +14,7 @@ from enum import Enum
 from typing import Callable, Dict, List, Optional, Sequence
 
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -339,6 +340,14 @@ def _early_sort(ctx, mod, pooled: bool, ids, offsets, B, want_grad: bool) -> Non
     The backward then only joins the stream and runs the gradient-dependent half."""
     ctx.early = None
     k = Fn.backend()
+    owner = getattr(mod, "_early_owner", None)
+    if getattr(mod, "_early_busy", False) and (owner is None or owner() is None):
+        # the lookup that owns the workspace is gone without a backward (e.g. a prediction made with grad enabled, its
+        # graph already freed): its sort is orphaned on the side stream — join it and release the workspace.  A
+        # lookup that is still alive (second lookup of the same module inside one forward pass) keeps ownership and
+        # this one takes the one-stream path.
+        torch.cuda.current_stream().wait_stream(mod._side_stream())
+        mod._early_busy = False
     # (`want_grad` comes from the caller: inside autograd.Function.forward grad mode is always off)
     if (mod.training and want_grad and ids.is_cuda and ids.numel() > 0
             and hasattr(k, "fused_bwd_sort") and mod.optimizer is not None
@@ -351,6 +360,7 @@ def _early_sort(ctx, mod, pooled: bool, ids, offsets, B, want_grad: bool) -> Non
             k.fused_bwd_sort(pooled, mod.layout, ids, offsets, B, ws)
         ctx.early = (ws, side)
         mod._early_busy = True
+        mod._early_owner = weakref.ref(ctx)
 
 
 def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> None:
