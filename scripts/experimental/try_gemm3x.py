@@ -1,0 +1,65 @@
+"""First contact of scripts/experimental/tzk_gemm3x.cu with hardware (round-2 groundwork).
+
+    timeout 120 python scripts/experimental/try_gemm3x.py [M]
+
+Builds the kernel next to its source, runs y = relu(x @ w^T + b) for x [M, 784] against a float64 reference and
+prints the error (target: fp32-GEMM level, <= 1e-6 relative to |x||w| row norms) and the CUDA-event time.  ALWAYS run
+it under `timeout`: a wrong mbarrier phase or descriptor hangs the kernel."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libtzk_gemm3x.so")
+SRC = os.path.join(HERE, "tzk_gemm3x.cu")
+
+
+def build():
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+                        "-std=c++17", "-Xcompiler", "-fPIC", "-shared", SRC, "-o", LIB, "-lcuda"], check=True)
+    return ctypes.CDLL(LIB)
+
+
+def main():
+    M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    K, N = 784, 64
+    lib = build()
+    P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    lib.tzk_gemm3x_fwd.argtypes = [P, I64, P, I64, P, I64, I32, I32, P, I64, P, P, P]
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    y = torch.empty(M, N, device="cuda")
+    w_hi, w_lo = torch.empty_like(w), torch.empty_like(w)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        rc = lib.tzk_gemm3x_fwd(x.data_ptr(), K, w.data_ptr(), K, b.data_ptr(), M, K, 1, y.data_ptr(), N,
+                                w_hi.data_ptr(), w_lo.data_ptr(), st)
+        assert rc == 0, rc
+
+    run()
+    torch.cuda.synchronize()
+    ref = torch.relu(x.double() @ w.double().T + b.double())
+    err = (y.double() - ref).abs().max().item()
+    scale = (x.double().norm(dim=1).max() * w.double().norm(dim=1).max()).item()
+    fp32 = (torch.relu(torch.nn.functional.linear(x, w, b)).double() - ref).abs().max().item()
+    print(f"M={M}: max abs err {err:.3e} (fp32 F.linear: {fp32:.3e}), relative to |x||w| {err / scale:.3e}")
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{e0.elapsed_time(e1) / 10 * 1e3:.1f} us per call (incl. the W split and three tensor-map encodes)")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,345 @@
+// tzk_gemm3x.cu — EXPERIMENTAL, NOT PART OF libtzk.so, NOT YET RUN ON HARDWARE.
+//
+// Round-2 groundwork: the one wide tower layer of DLRM's final MLP,
+//     Y[M,64] = act(X[M,K] @ W[64,K]^T + bias)            (tzrec/modules/mlp.py:20-84, K = 784)
+// as a hand-written sm_100a kernel with fp32-equivalent accuracy on the 5th-gen tensor cores: tcgen05.mma kind::tf32
+// with the 3xTF32 split  x*w ~= hi(x)*hi(w) + lo(x)*hi(w) + hi(x)*lo(w),  hi = cvt.rna.tf32, lo = v - hi.
+// It replaces cuBLASLt's BF16x9 path (100 us GEMM + 97 us inf/nan scan + 6.5 us bias/ReLU at B = 65536).
+//
+// Structure (one CTA per SM, persistent over 128-row tiles, 192 threads):
+//   warp 0      TMA producer: per K-chunk of 32 columns, X[128x32] -> smem (SWIZZLE_128B), W_hi / W_lo[64x32] -> smem
+//   warp 1      MMA issuer (one elected lane) + TMEM allocation: per chunk 4 k-steps x 3 products into a
+//               128 x 64 fp32 accumulator in TMEM; two accumulators so the epilogue overlaps the next tile
+//   warps 2..5  transform: rewrite the landed X chunk in place as hi and write lo to a second buffer (same swizzled
+//               addresses -> no layout knowledge needed), fence.proxy.async, signal the MMA warp;
+//               epilogue: tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..), + bias, ReLU, coalesced-enough row stores
+// Barriers per stage: full (TMA -> transform), ready (transform -> MMA), empty (MMA commit -> TMA);
+// per accumulator: acc_full (MMA commit -> epilogue), acc_empty (epilogue -> MMA).
+//
+// Build + try (next round, on a B200):  python scripts/experimental/try_gemm3x.py
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile (UMMA M)
+constexpr int BN = 64;           // output width (UMMA N)
+constexpr int BK = 32;           // K-chunk: 32 floats = one 128-B swizzled row
+constexpr int UK = 8;            // UMMA K for tf32 (32 bytes)
+constexpr int STAGES = 4;
+constexpr int X_BYTES = BM * BK * 4;       // 16 KB
+constexpr int W_BYTES = BN * BK * 4;       //  8 KB
+constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_BYTES;   // X(hi) | X lo | W hi | W lo = 48 KB
+constexpr int TMEM_COLS = 128;   // two 64-column accumulators
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// ---- TMA ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ---- tcgen05 -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_free(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of fp32 -> 32 registers per lane (lane i of the warp reads TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major: 1) | [32,46) SBO >> 4 (1024 B between
+//   8-row groups) | [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format TF32 = 2 @ [7,10) / [10,13),
+// K-major A and B (bits 15, 16 = 0), n_dim = N >> 3 @ [17,23), m_dim = M >> 4 @ [24,29)
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct Params {
+  const float* bias;   // [64] or NULL
+  float* y;            // [M, ld_y]
+  int64_t ld_y;
+  int64_t M;
+  int K;               // multiple of 32 after padding (the caller's X / W carry zero columns up to it)
+  int relu;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm3x_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                  const __grid_constant__ CUtensorMap map_wlo, Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stage_base = smem;                                        // STAGES x 48 KB, each buffer 1024-B aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES] TMA -> transform   (1 arrival + tx bytes)
+  uint64_t* ready = bars + STAGES;       // [STAGES] transform -> MMA   (4 arrivals: one per transform warp)
+  uint64_t* empty = bars + 2 * STAGES;   // [STAGES] MMA -> TMA         (1 arrival via tcgen05.commit)
+  uint64_t* acc_full = bars + 3 * STAGES;        // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 3 * STAGES + 2;   // [2] epilogue -> MMA (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.K / BK;
+  const int64_t num_tiles = (p.M + BM - 1) / BM;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, 4);
+      mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full + a, 1);
+      mbar_init(acc_empty + a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer ======================================================================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sb = stage_base + stage * STAGE_BYTES;
+          mbar_expect_tx(full + stage, X_BYTES + 2 * W_BYTES);
+          tma_load_2d(sb, &map_x, full + stage, kb * BK, (int)(t * BM));
+          tma_load_2d(sb + 2 * X_BYTES, &map_whi, full + stage, kb * BK, 0);
+          tma_load_2d(sb + 2 * X_BYTES + W_BYTES, &map_wlo, full + stage, kb * BK, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ==========================================================================================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr uint32_t idesc = make_idesc();
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(acc_empty + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(ready + stage, phase);              // hi / lo of this chunk are in shared memory
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sb = smem_u32(stage_base + stage * STAGE_BYTES);
+          const uint32_t a_hi = sb, a_lo = sb + X_BYTES, b_hi = sb + 2 * X_BYTES, b_lo = b_hi + W_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint32_t ko = k * UK * 4;           // 32 B per k-step inside the 128-B swizzled row
+            const uint32_t first = (kb | k) ? 1u : 0u;
+            mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+            mma_tf32(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1u);
+            mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          }
+          tc_commit(empty + stage);                    // shared-memory slot is free once these MMAs retire
+          if (kb == num_k - 1) tc_commit(acc_full + acc);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===== transform + epilogue warps (2..5) =====================================================================
+    const int tw = warp - 2;                 // 0..3
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full + stage, phase);
+        float4* hi = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES + X_BYTES);
+        // 1024 float4 per X chunk, 128 transform threads -> 8 each; element-wise, so the swizzle is irrelevant
+#pragma unroll
+        for (int q = 0; q < X_BYTES / 16 / 128; ++q) {
+          const int i = q * 128 + tw * 32 + lane;
+          const float4 x = hi[i];
+          float4 h, l;
+          h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+          hi[i] = h;
+          lo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready + stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      // ---- epilogue of this tile ---------------------------------------------------------------------------
+      mbar_wait(acc_full + acc, acc_phase);
+      tc_fence_after();
+      const int64_t row = t * BM + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      float v[32];
+#pragma unroll
+      for (int half = 0; half < BN / 32; ++half) {
+        tmem_ld32(taddr + half * 32, v);
+        if (row < p.M) {
+          float* yr = p.y + row * p.ld_y + half * 32;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 o;
+            o.x = v[c] + (p.bias ? __ldg(p.bias + half * 32 + c) : 0.f);
+            o.y = v[c + 1] + (p.bias ? __ldg(p.bias + half * 32 + c + 1) : 0.f);
+            o.z = v[c + 2] + (p.bias ? __ldg(p.bias + half * 32 + c + 2) : 0.f);
+            o.w = v[c + 3] + (p.bias ? __ldg(p.bias + half * 32 + c + 3) : 0.f);
+            if (p.relu) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(yr + c) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_free(tmem_base, TMEM_COLS);
+}
+
+// ---- host: tensor maps -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  static EncodeTiled encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 1;
+    encode = reinterpret_cast<EncodeTiled>(fn);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};          // innermost first
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};                       // bytes, dims 1..rank-1
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 2;
+}
+
+__global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float h = tf32_rna(w[i]);
+    hi[i] = h;
+    lo[i] = w[i] - h;
+  }
+}
+}  // namespace
+
+// y[M,64] = act(x[M,K] @ w[64,K]^T + bias).  x rows 16-B aligned with ld_x % 4 == 0; columns beyond K up to a
+// multiple of 32 are out of bounds for the tensor map and read as zeros.  w_hi / w_lo: [64, ld_w] scratch written here.
+extern "C" int tzk_gemm3x_fwd(const float* x, int64_t ld_x, const float* w, int64_t ld_w, const float* bias, int64_t M,
+                              int32_t K, int32_t relu, float* y, int64_t ld_y, float* w_hi, float* w_lo,
+                              void* stream) {
+  if (M <= 0 || K <= 0 || (ld_x % 4) || (ld_w % 4) || (ld_y % 4)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t nw = (int64_t)BN * ld_w;
+  split_w_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, nw, w_hi, w_lo);
+  CUtensorMap mx, mh, ml;
+  if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, w_hi, BN, K, ld_w, BN) || make_map(&ml, w_lo, BN, K, ld_w, BN))
+    return 2;
+  Params p;
+  p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.relu = relu;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 256;
+  cudaFuncSetAttribute(gemm3x_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (M + BM - 1) / BM;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  gemm3x_fwd_kernel<<<grid, NUM_THREADS, smem, st>>>(mx, mh, ml, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
