@@ -388,7 +388,7 @@ struct WorkLists {
 // Each lane group owns kPos consecutive sorted positions per iteration.  Runs of length 1 (the common case on
 // big tables) take a batched path: the gradient / weight / state rows of all of them are requested before any
 // is consumed, so a group keeps 3*kPos independent 64-B requests in flight instead of one dependent chain.
-template <typename KeyT, int G, int VEC, int CH, int KP>
+template <typename KeyT, int G, int VEC, int CH>
 __global__ void __launch_bounds__(kThreads)
 run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
                   const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
@@ -400,7 +400,8 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   init_bias_correction(a);
 
   constexpr int NG = kThreads / G;
-  constexpr int kPos = (CH == 1) ? KP : 1;
+  constexpr int kPos = 1;   // positions per lane group per iteration (2 and 4 with a batched single-run path were
+                            // measured slower: 349 / 375 / 461 us for 1 / 2 / 4 on DLRM-Criteo)
   const int lane = threadIdx.x % G;
   const int64_t stride = (int64_t)gridDim.x * NG * kPos;
   // all G lanes of a group follow the same control flow (positions, keys, run lengths are group-uniform)
@@ -424,80 +425,10 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
       head[u] = (p0 + u < a.n) && key[u + 1] != key[u] && key[u + 1] != (KeyT)a.sentinel;
       single[u] = head[u] && ((p0 + u + 1 >= a.n) || key[u + 2] != key[u + 1]);
     }
-    if (CH == 1 && KP > 1) {
-      // ---- batched path: runs of length 1 -------------------------------------------------------------
-      float g[kPos][VEC], w[kPos][VEC], s[kPos][VEC];
-      float scale[kPos];
-      int f0[kPos];
-      const int c = lane * VEC;
-#pragma unroll
-      for (int u = 0; u < kPos; ++u) {
-        f0[u] = 0;
-        scale[u] = 0.f;
-        if (!single[u]) continue;
-        f0[u] = a.pooled ? v[u] / a.B : feat_of_key<KeyT>(fd, a.F, key[u + 1]);
-        const BwdFeat& d = fd[f0[u]];
-        const Entry en = entry_of(a, fd, v[u], f0[u]);
-        scale[u] = en.scale;
-        if (c < d.dim) {
-          const int64_t row = (int64_t)key[u + 1] - d.key_base;
-          load_grad<VEC>(en.g + c, g[u]);
-          const float* wp = a.weights + d.w_off + row * d.dim + c;
-          if (VEC == 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wp);
-            w[u][0] = w4.x; w[u][1] = w4.y; w[u][2] = w4.z; w[u][3] = w4.w;
-            if (a.optimizer == TZK_OPT_ADAGRAD) {
-              const float4 s4 = *reinterpret_cast<const float4*>(a.state + d.w_off + row * d.dim + c);
-              s[u][0] = s4.x; s[u][1] = s4.y; s[u][2] = s4.z; s[u][3] = s4.w;
-            }
-          } else {
-            w[u][0] = wp[0];
-            if (a.optimizer == TZK_OPT_ADAGRAD) s[u][0] = a.state[d.w_off + row * d.dim + c];
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kPos; ++u) {
-        if (!single[u]) continue;
-        const BwdFeat& d = fd[f0[u]];
-        const int64_t row = (int64_t)key[u + 1] - d.key_base;
-        float gv[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) gv[k] = (c < d.dim) ? (0.f + g[u][k] * scale[u]) : 0.f;
-        float rw_denom = 1.f;
-        if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {
-          float ss = 0.f;
-#pragma unroll
-          for (int k = 0; k < VEC; ++k)
-            if (c + k < d.dim) ss += gv[k] * gv[k];
-          ss = group_sum<G>(ss);
-          float sr = 0.f;
-          if (lane == 0) {
-            sr = a.state[key[u + 1]] + ss / (float)d.dim;
-            a.state[key[u + 1]] = sr;
-          }
-          sr = __shfl_sync(group_mask<G>(), sr, 0, G);
-          rw_denom = sqrtf(sr) + a.eps;
-        }
-        if (c < d.dim) {
-          apply_update<VEC>(a, w[u], s[u], s[u], gv, rw_denom);   // (batched path: SGD / Adagrad kinds only)
-          float* wp = a.weights + d.w_off + row * d.dim + c;
-          if (VEC == 4) {
-            *reinterpret_cast<float4*>(wp) = make_float4(w[u][0], w[u][1], w[u][2], w[u][3]);
-            if (a.optimizer == TZK_OPT_ADAGRAD)
-              *reinterpret_cast<float4*>(a.state + d.w_off + row * d.dim + c) =
-                  make_float4(s[u][0], s[u][1], s[u][2], s[u][3]);
-          } else {
-            wp[0] = w[u][0];
-            if (a.optimizer == TZK_OPT_ADAGRAD) a.state[d.w_off + row * d.dim + c] = s[u][0];
-          }
-        }
-      }
-    }
-    // ---- general path: heads of runs of length >= 2 (and every head when CH > 1) -----------------------------
+    // ---- every run head: sum the run (<= kShortRun) in sorted order and update, or hand it to the long-run kernels
 #pragma unroll 1
     for (int u = 0; u < kPos; ++u) {
-      if (!head[u] || (CH == 1 && KP > 1 && single[u])) continue;
+      if (!head[u]) continue;
       const int64_t p = p0 + u;
       const KeyT k0 = key[u + 1];
       int len = 1;
@@ -996,22 +927,15 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
 
 }  // namespace
 
-#define TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, KP_)                                                     \
-  do {                                                                                                \
-    if (smem_s > 48 * 1024)                                                                           \
-      cudaFuncSetAttribute(run_update_kernel<KeyT, G_, VEC_, CH_, KP_>,                               \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
-    run_update_kernel<KeyT, G_, VEC_, CH_, KP_><<<grid_s, kThreads, smem_s, st>>>(                    \
-        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
-        vals_out, wl);                                                                                \
-  } while (0)
-
 #define TZK_BWD_LAUNCH(KeyT, G_, VEC_, CH_)                                                          \
   do {                                                                                                \
     size_t smem_s = (size_t)F * sizeof(BwdFeat);                                                      \
-    if (CH_ == 1 && kpos == 4) TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, 4);                                \
-    else if (CH_ == 1 && kpos == 2) TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, 2);                           \
-    else TZK_RUN_UPDATE(KeyT, G_, VEC_, CH_, 1);                                                      \
+    if (smem_s > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(run_update_kernel<KeyT, G_, VEC_, CH_>,                                    \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
+    run_update_kernel<KeyT, G_, VEC_, CH_><<<grid_s, kThreads, smem_s, st>>>(                         \
+        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
+        vals_out, wl);                                                                                \
     TZK_CHECK_LAUNCH("run_update_kernel");                                                            \
     size_t smem_l = (size_t)F * sizeof(BwdFeat);                                                      \
     if (smem_l > 48 * 1024)                                                                           \
@@ -1142,15 +1066,6 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
               max_dim, ch);
   const int NG = kThreads / G;
   int grid_s = (int)std::min<int64_t>(ceil_div64(nnz, NG), kSmCountB200 * 16);
-  // positions per lane group per iteration in run_update (1 = one dependent chain per group, 2/4 = batched
-  // single-run path).  Tunable for experiments: TZK_RUN_UPDATE_KPOS=1|2|4.
-  static const int kpos_env = [] {
-    const char* e = getenv("TZK_RUN_UPDATE_KPOS");
-    const int v = e ? atoi(e) : 1;
-    return (v == 2 || v == 4) ? v : 1;
-  }();
-  const int kpos = optimizer >= TZK_OPT_ADAM ? 1 : kpos_env;   // the batched single-run path knows the classic kinds only
-
   // TZK_BWD_TILE=1 selects the tile path.  Measured on DLRM-Criteo (B200, 1.7 M ids): both paths spend ~200 us in
   // the gradient half — the random 64-B weight/state/gradient accesses top out near 2-2.3 TB/s of DRAM traffic either
   // way — and the general kernels execute fewer instructions (74 M vs 87 M warp-instructions) without the three
