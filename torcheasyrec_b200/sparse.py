@@ -203,6 +203,14 @@ class KeyedTensor:
         return {k: self._values[:, off[i]:off[i + 1]] for i, k in enumerate(self._keys)}
 
     @staticmethod
+    def from_tensor_list(keys: Sequence[str], tensors: List[torch.Tensor], key_dim: int = 1,
+                         cat_dim: int = 1) -> "KeyedTensor":
+        """[EXT] torchrec KeyedTensor.from_tensor_list (used by tzrec/datasets/utils.py and every embedding test):
+        concatenates `[B, d_i]` blocks along the key dimension."""
+        assert key_dim == 1 and cat_dim == 1 and len(keys) == len(tensors)
+        return KeyedTensor(list(keys), [int(t.shape[1]) for t in tensors], torch.cat(list(tensors), dim=1))
+
+    @staticmethod
     def regroup_as_dict(keyed_tensors: List["KeyedTensor"], groups: List[List[str]], keys: List[str]
                         ) -> Dict[str, torch.Tensor]:
         """{group name: [B, sum D]} — call site tzrec/modules/embedding.py:972-976 (K6, App. A.13)."""
