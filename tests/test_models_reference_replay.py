@@ -99,3 +99,30 @@ model_config {
         y_fm = torch.from_numpy(O.fm(grouped["fm"].numpy().reshape(2, 2, 16)))
         ref = model.output_mlp(model.final_mlp(torch.cat([y_wide, y_fm, y_deep], dim=1))).squeeze(1)
     np.testing.assert_allclose(pred["logits"].numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_mmoe():
+    """tzrec/models/mmoe_test.py:38-119: two feature groups feeding the experts, gate MLP, two task towers."""
+    cfg = parse_text("""
+feature_configs { id_feature { feature_name: "cat_a" embedding_dim: 16 num_buckets: 100 } }
+feature_configs { id_feature { feature_name: "cat_b" embedding_dim: 8 num_buckets: 1000 } }
+feature_configs { raw_feature { feature_name: "int_a" } }
+model_config {
+  feature_groups { group_name: "t1" feature_names: "cat_a" feature_names: "cat_b" group_type: DEEP }
+  feature_groups { group_name: "t2" feature_names: "cat_a" feature_names: "int_a" group_type: DEEP }
+  mmoe {
+    expert_mlp { hidden_units: [16, 8] }
+    num_expert: 3
+    gate_mlp { hidden_units: [4] }
+    task_towers { tower_name: "t1" label_name: "label1" mlp { hidden_units: [8, 4] } losses { binary_cross_entropy {} } }
+    task_towers { tower_name: "t2" label_name: "label2" mlp { hidden_units: [12, 6] } losses { binary_cross_entropy {} } }
+  }
+}""")
+    torch.manual_seed(0)
+    features = create_features(list(cfg.feature_configs))
+    model = create_model(cfg.model_config, features, ["label"], device=torch.device("cpu"))
+    with Fn.use_backend(OracleKernels()), torch.no_grad():
+        pred = model.predict(_batch())
+    for k in ("logits_t1", "probs_t1", "logits_t2", "probs_t2"):
+        assert pred[k].size() == (2,), k
+    assert torch.all((pred["probs_t1"] > 0) & (pred["probs_t1"] < 1))
