@@ -100,3 +100,54 @@ def test_sequence_embedding_group_impl():
         assert tuple(result[k].size()) == shp, (k, tuple(result[k].size()))
         assert not torch.any(torch.isnan(result[k].float())).item(), k
     assert "deep___click_no_query.query" not in result
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("pooling", ["sum", "mean"])
+def test_sequence_embedding_group_impl_mulval(pooling):
+    """embedding_test.py:273-425 with has_mulval=True: cat_a carries several ids per value (value_dim 0) both as a
+    plain feature and inside the sequences; per-step pooling through sequence_mulval_lengths
+    (`values=[1,0,3,1,2,2,1,2,2,2], lengths=[3,3,2,2]`), ids `range(30)`."""
+    feats = SEQ_FEATURES.replace('feature_name: "cat_a" embedding_dim: 16 expression: "item:cat_a" num_buckets: 100',
+                                 f'feature_name: "cat_a" embedding_dim: 16 expression: "item:cat_a" num_buckets: 100 '
+                                 f'value_dim: 0 pooling: "{pooling}"')
+    feats = feats.replace('feature_name: "cat_a" expression: "item:cat_a" embedding_dim: 16 num_buckets: 100',
+                          f'feature_name: "cat_a" expression: "item:cat_a" embedding_dim: 16 num_buckets: 100 '
+                          f'value_dim: 0 pooling: "{pooling}"')
+    assert feats.count("value_dim: 0") == 3
+    cfg = parse_text(feats + "model_config { " +
+                     _fg("click", ["cat_a", "cat_b", "int_a", "click_seq__cat_a", "click_seq__cat_b", "click_seq__int_a"],
+                         "SEQUENCE") +
+                     _fg("buy", ["cat_a", "int_a", "buy_seq__cat_a", "buy_seq__int_a"], "SEQUENCE") + " }")
+    features = create_features(list(cfg.feature_configs))
+    eg = SequenceEmbeddingGroupImpl(features, list(cfg.model_config.feature_groups), device=torch.device("cpu"))
+    assert eg.has_mulval_seq
+    sparse = KeyedJaggedTensor.from_lengths_sync(
+        keys=["cat_a", "cat_b", "click_seq__cat_a", "click_seq__cat_b", "buy_seq__cat_a", "buy_seq__cat_b"],
+        values=torch.tensor(list(range(30))),
+        lengths=torch.tensor([2, 0, 1, 1, 4, 5, 3, 3, 3, 4, 2, 2], dtype=torch.int32))
+    mulval = KeyedJaggedTensor.from_lengths_sync(keys=["click_seq__cat_a", "buy_seq__cat_a"],
+                                                 values=torch.tensor([1, 0, 3, 1, 2, 2, 1, 2, 2, 2]),
+                                                 lengths=torch.tensor([3, 3, 2, 2], dtype=torch.int32))
+    dense = KeyedTensor.from_tensor_list(keys=["int_a"], tensors=[torch.tensor([[0.2], [0.3]])])
+    seq_dense = KeyedJaggedTensor.from_lengths_sync(
+        keys=["click_seq__int_a", "buy_seq__int_a"], values=torch.tensor([[x] for x in range(10)], dtype=torch.float32),
+        lengths=torch.tensor([3, 3, 2, 2], dtype=torch.int32)).to_dict()
+    with Fn.use_backend(OracleKernels()), torch.no_grad():
+        result = eg(sparse, dense, seq_dense, mulval)
+    for k, shp in {"click.query": (2, 25), "click.sequence": (2, 3, 25), "click.sequence_length": (2,),
+                   "buy.query": (2, 17), "buy.sequence": (2, 2, 17), "buy.sequence_length": (2,)}.items():
+        assert tuple(result[k].size()) == shp, (k, tuple(result[k].size()))
+        assert not torch.any(torch.isnan(result[k].float())).item(), k
+    # values: click_seq__cat_a of sample 0 holds ids 4..7 in steps of [1, 0, 3] ids: step 0 = row 4, step 1 has no id
+    # -> zeros, step 2 pools rows 5, 6, 7
+    ec = eg.ec_dict["16"]
+    t = [c.name for c in ec.embedding_configs()].index("click_seq__cat_a_emb")
+    w = ec.table_weight(t)
+    got = result["click.sequence"][0, :, :16]
+    assert torch.count_nonzero(got[1]) == 0
+    want = w[[5, 6, 7]].sum(0) if pooling == "sum" else w[[5, 6, 7]].mean(0)
+    torch.testing.assert_close(got[2], want, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(got[0], w[4], rtol=1e-6, atol=1e-7)

@@ -213,9 +213,7 @@ class SequenceEmbeddingGroupImpl(nn.Module):
                     if const is not None:
                         self._dim_to_emb_constraints[cfg.embedding_dim][cfg.name] = const
                     if feature.is_sequence and feature.value_dim != 1:
-                        raise NotImplementedError(
-                            f"sequence feature {name}: multi-value ids inside a sequence (value_dim != 1) are "
-                            "outside the hot-path scope (K8, SURVEY.md §2.3)")
+                        self.has_mulval_seq = True      # embedding.py:1150-1155: pooled per step in forward
                 else:
                     if feature.is_sequence:
                         self.has_sequence_dense = True
@@ -274,7 +272,8 @@ class SequenceEmbeddingGroupImpl(nn.Module):
         return group_name.split(".")[0] in self._group_output_dims
 
     def forward(self, sparse_feature: Optional[KeyedJaggedTensor], dense_feature: Optional[KeyedTensor],
-                sequence_dense_features: Optional[Dict[str, JaggedTensor]] = None, *unused) -> Dict[str, torch.Tensor]:
+                sequence_dense_features: Optional[Dict[str, JaggedTensor]] = None,
+                sequence_mulval_lengths: Optional[KeyedJaggedTensor] = None, *unused) -> Dict[str, torch.Tensor]:
         jt_dict: Dict[str, JaggedTensor] = {}
         if self.has_sparse:
             for pairs, ec in zip(self.ec_dict_features.values(), self.ec_dict.values()):
@@ -282,10 +281,29 @@ class SequenceEmbeddingGroupImpl(nn.Module):
                 for okey, shared in pairs:
                     jt_dict[shared] = d_jt[okey]
         dense_t = dense_feature.to_dict() if self.has_dense else {}
+        mulval_len = sequence_mulval_lengths.to_dict() if (self.has_mulval_seq and sequence_mulval_lengths is not None) \
+            else {}
+        done = set()
         for infos in self._group_to_shared_sequence.values():
             for info in infos:
+                if info.name in done:
+                    continue
+                done.add(info.name)
                 if not info.is_sparse:
                     jt_dict[info.name] = sequence_dense_features[info.name]
+                elif info.value_dim != 1:
+                    # several ids per sequence step (embedding.py:1354-1366): the un-pooled rows of the step's ids are
+                    # reduced with the same ATen op the reference calls; `values` of the length JT = ids per step,
+                    # its `lengths` = steps per sample
+                    if info.raw_name not in mulval_len:
+                        raise ValueError(f"sequence feature {info.raw_name} is multi-value: the batch must carry "
+                                         "sequence_mulval_lengths for it")
+                    length_jt = mulval_len[info.raw_name]
+                    jt = jt_dict[info.name]
+                    vals = torch.segment_reduce(jt.values(), info.pooling, lengths=length_jt.values().to(torch.int64))
+                    if info.pooling == "mean":
+                        vals = torch.nan_to_num(vals, nan=0.0)
+                    jt_dict[info.name] = JaggedTensor(values=vals, lengths=length_jt.lengths())
 
         results: Dict[str, torch.Tensor] = {}
         query_cache: Dict[str, torch.Tensor] = {}
@@ -503,7 +521,8 @@ class EmbeddingGroup(nn.Module):
         for key, impl in self.seq_emb_impls.items():
             result.update(impl(batch.sparse_features[key] if impl.has_sparse else None,
                                batch.dense_features[key] if impl.has_dense else None,
-                               batch.sequence_dense_features))
+                               batch.sequence_dense_features,
+                               batch.sequence_mulval_lengths.get(key) if impl.has_mulval_seq else None))
         for gname, encs in self._group_name_to_seq_encoders.items():
             new = torch.cat([enc(result) for enc in encs], dim=-1)
             result[gname] = torch.cat([result[gname], new], dim=-1) if gname in result else new
