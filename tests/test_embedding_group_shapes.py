@@ -151,3 +151,27 @@ def test_sequence_embedding_group_impl_mulval(pooling):
     want = w[[5, 6, 7]].sum(0) if pooling == "sum" else w[[5, 6, 7]].mean(0)
     torch.testing.assert_close(got[2], want, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(got[0], w[4], rtol=1e-6, atol=1e-7)
+
+
+def test_batch_flattening_example_of_the_reference():
+    """tzrec/datasets/utils.py:311-321: the multi-value sequence `click_seq` = [[[3, 4], [5]], [6, [7, 8]]] travels as
+    values [3..8], accumulated lengths [3, 3], key_lengths [2, 1, 1, 2], seq_lengths [2, 2]; the sequence output must
+    be the per-step sums of the table rows."""
+    cfg = parse_text("""
+feature_configs { sequence_feature { sequence_name: "click_seq"
+    features { id_feature { feature_name: "item" embedding_dim: 4 num_buckets: 10 value_dim: 0 pooling: "sum" } } } }
+model_config { feature_groups { group_name: "g" feature_names: "click_seq__item" group_type: SEQUENCE } }""")
+    features = create_features(list(cfg.feature_configs))
+    eg = SequenceEmbeddingGroupImpl(features, list(cfg.model_config.feature_groups), device=torch.device("cpu"))
+    sparse = KeyedJaggedTensor.from_lengths_sync(keys=["click_seq__item"], values=torch.tensor([3, 4, 5, 6, 7, 8]),
+                                                 lengths=torch.tensor([3, 3], dtype=torch.int32))
+    mulval = KeyedJaggedTensor.from_lengths_sync(keys=["click_seq__item"], values=torch.tensor([2, 1, 1, 2]),
+                                                 lengths=torch.tensor([2, 2], dtype=torch.int32))
+    with Fn.use_backend(OracleKernels()), torch.no_grad():
+        res = eg(sparse, None, {}, mulval)
+    w = eg.ec_dict["4"].table_weight(0)
+    assert res["g.sequence"].shape == (2, 2, 4) and res["g.sequence_length"].tolist() == [2, 2]
+    torch.testing.assert_close(res["g.sequence"][0, 0], w[3] + w[4])
+    torch.testing.assert_close(res["g.sequence"][0, 1], w[5])
+    torch.testing.assert_close(res["g.sequence"][1, 0], w[6])
+    torch.testing.assert_close(res["g.sequence"][1, 1], w[7] + w[8])
