@@ -91,3 +91,29 @@ def test_sparse_optimizer_mapping_from_train_config():
     assert abs(s.weight_decay - 0.001) < 1e-9 and s.max_gradient == 1.0        # proto default max_gradient
     s = spec("partial_rowwise_adam_optimizer { lr: 0.01 }")
     assert s.kind == OPT_PARTIAL_ROWWISE_ADAM and s.max_gradient == 0.0
+
+
+@have_ref
+@pytest.mark.parametrize("name", ["dlrm_criteo", "deepfm_criteo", "mmoe_taobao", "multi_tower_din_taobao",
+                                  "multi_tower_taobao"])
+def test_reference_example_config_runs_unchanged(name):
+    """north_star: `examples/*.config` runs unchanged — the reference's own file is loaded from its checkout (only the
+    table sizes are capped, like the reference's --edit_config_json), the model is built and stepped twice on the CPU
+    with the oracle as compute; the loss must be finite and move."""
+    import sys
+
+    import torch
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_backend import OracleKernels
+
+    from torcheasyrec_b200 import functional as Fn
+    from torcheasyrec_b200.engine import Pipeline
+
+    pipe = Pipeline(os.path.join(REF_EXAMPLES, name + ".config"), device="cpu", max_rows=200, seed=3)
+    batch = pipe.synthetic_batch(24, seed=1)
+    with Fn.use_backend(OracleKernels()):
+        l0 = float(pipe.eager_step(batch))
+        l1 = float(pipe.eager_step(batch))
+    assert torch.isfinite(torch.tensor([l0, l1])).all()
+    assert l1 < l0          # same batch twice: the sparse (Adagrad) and dense (Adam) updates reduce the loss

@@ -372,7 +372,7 @@ class MultiTowerDIN(RankModel):
             self.towers[tower.input] = MLP(eg.group_total_dim(tower.input), **config_to_kwargs(tower.mlp))
             total += self.towers[tower.input].output_dim()
         self.din_towers = nn.ModuleList()
-        for tower in self._model_config.din_towers:
+        for tower in (self._model_config.din_towers if self._model_type == "multi_tower_din" else []):
             g = tower.input
             enc = DINEncoder(eg.group_total_dim(f"{g}.sequence"), eg.group_total_dim(f"{g}.query"), g,
                              attn_mlp=config_to_kwargs(tower.attn_mlp))
@@ -431,7 +431,12 @@ class MMoE(RankModel):
         return out
 
 
-MODEL_CLASSES = {"dlrm": DLRM, "deepfm": DeepFM, "multi_tower_din": MultiTowerDIN, "mmoe": MMoE}
+class MultiTower(MultiTowerDIN):
+    """tzrec/models/multi_tower.py:27-85: the same towers + final MLP without attention towers."""
+
+
+MODEL_CLASSES = {"dlrm": DLRM, "deepfm": DeepFM, "multi_tower_din": MultiTowerDIN, "multi_tower": MultiTower,
+                 "mmoe": MMoE}
 
 
 def create_model(model_config: Message, features: List[BaseFeature], labels: List[str], device=None) -> RankModel:
