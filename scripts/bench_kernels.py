@@ -45,7 +45,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "one":
     # DLRM interaction (fwd / bwd) at the bench shape, and the narrow tower layers
     dense16 = torch.randn(B, 16, device=dev)
     sparse = torch.randn(B, F * D, device=dev)
-    res["interact_occ"] = os.environ.get("TZK_INTERACT_OCC", "4")
     res["interact_fwd_us"] = timeit(lambda i: k.dot_interact_fwd(dense16, sparse, F, D, True, True, 4, 1))
     d_out = torch.randn(B, 784, device=dev)
     res["interact_bwd_us"] = timeit(lambda i: k.dot_interact_bwd(dense16, sparse, d_out, F, D, True, True, 1))
@@ -56,6 +55,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "one":
         res[f"lin{K}x{N}_bwd_us"] = timeit(lambda i: k.small_linear_bwd(x, w, y, dy, True, True, True))
     print(json.dumps(res))
 else:
-    for tile, dist, occ in (("0", "uniform", "4"), ("1", "uniform", "3"), ("0", "zipf", "4")):
-        env = dict(os.environ, TZK_BWD_TILE=tile, TZK_ID_DIST=dist, TZK_INTERACT_OCC=occ)
+    for tile, dist in (("0", "uniform"), ("1", "uniform"), ("0", "zipf")):
+        env = dict(os.environ, TZK_BWD_TILE=tile, TZK_ID_DIST=dist)
         subprocess.run([sys.executable, __file__, "one"], env=env)

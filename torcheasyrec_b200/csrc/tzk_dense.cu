@@ -172,8 +172,9 @@ __device__ __forceinline__ void stage_x(float* X, const float* dense, int64_t ld
 
 // DT = compile-time embedding dim (0 = take the runtime value): with DT known every /D, %D and swizzle offset
 // folds into shifts and the k loop unrolls — the kernel is issue-bound, not bandwidth-bound, otherwise.
-template <int DT, bool ONE, int OCC, int NT>
-__global__ void __launch_bounds__(kIWarps * 32, OCC)
+// 4 CTAs/SM (64 registers, a few spilled words) measured 105 us against 127 us at 3 CTAs/SM (80 registers).
+template <int DT, bool ONE, int NT>
+__global__ void __launch_bounds__(kIWarps * 32, 4)
 dot_interact_fwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const float* __restrict__ sparse,
                         int64_t ld_sparse, int64_t B, int Ns, int D_rt, int copy_dense, int copy_sparse, int p_pad,
                         int aligned, float* __restrict__ out, int64_t ld_out) {
@@ -585,36 +586,25 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int aligned = (((P + p_pad) % 4) == 0) && (ld_out % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const int nb = Np / 4, n_blocks = nb * (nb + 1) / 2;
   size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3 + 4) & ~3))) * sizeof(float);
-#define TZK_IFWD4(DT_, ONE_, OCC_, NT_)                                                                        \
+#define TZK_IFWD3(DT_, ONE_, NT_)                                                                              \
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
-      cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_, ONE_, OCC_, NT_>,                                    \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-    dot_interact_fwd_kernel<DT_, ONE_, OCC_, NT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32,     \
-                                                    smem, as_stream(stream)>>>(                              \
+      cudaFuncSetAttribute(dot_interact_fwd_kernel<DT_, ONE_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem);                                                                       \
+    dot_interact_fwd_kernel<DT_, ONE_, NT_><<<grid_for(B, kIWarps, kSmCountB200 * 8), kIWarps * 32, smem,     \
+                                              as_stream(stream)>>>(                                          \
         dense, ld_dense, sparse, ld_sparse, B, Ns, D, copy_dense, copy_sparse, p_pad, aligned, out, ld_out); \
   } while (0)
-#define TZK_IFWD3(DT_, ONE_, OCC_)                                                       \
-  do {                                                                                   \
-    if (DT_ == 16 && ONE_ && OCC_ == 4 && N == 27 && dense) TZK_IFWD4(16, true, 4, 27);  \
-    else TZK_IFWD4(DT_, ONE_, OCC_, 0);                                                  \
-  } while (0)
-#define TZK_IFWD2(DT_, ONE_)                    \
-  do {                                          \
-    if (occ4) TZK_IFWD3(DT_, ONE_, 4);          \
-    else TZK_IFWD3(DT_, ONE_, 3);               \
+#define TZK_IFWD2(DT_, ONE_)                                                   \
+  do {                                                                         \
+    if (DT_ == 16 && ONE_ && N == 27 && dense) TZK_IFWD3(16, true, 27);        \
+    else TZK_IFWD3(DT_, ONE_, 0);                                              \
   } while (0)
 #define TZK_IFWD(DT_)                          \
   do {                                         \
     if (n_blocks <= 32) TZK_IFWD2(DT_, true);  \
     else TZK_IFWD2(DT_, false);                \
   } while (0)
-  // occupancy target of the forward kernel: 3 CTAs/SM (80 registers) or 4 (64 registers, a few spills; default); tunable for
-  // experiments with TZK_INTERACT_OCC=3|4
-  static const bool occ4 = [] {
-    const char* e = getenv("TZK_INTERACT_OCC");
-    return !(e && e[0] == '3');      // measured: 105 us (4 CTAs/SM) vs 127 us (3) at B=65536, N=27, D=16
-  }();
   switch (D) {
     case 8: TZK_IFWD(8); break;
     case 16: TZK_IFWD(16); break;
@@ -625,7 +615,6 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
 #undef TZK_IFWD
 #undef TZK_IFWD2
 #undef TZK_IFWD3
-#undef TZK_IFWD4
   TZK_CHECK_LAUNCH("dot_interact_fwd_kernel");
   return 0;
 }
