@@ -385,7 +385,9 @@ def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> Non
             with torch.cuda.stream(side):
                 k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,
                                   ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws, **extras)
-            mod._pending_apply = grad      # keeps the gradient buffer away from the allocator until the join
+            # keeps the buffers the side-stream kernel reads away from the allocator until the join (autograd drops
+            # the saved tensors as soon as this node returns)
+            mod._pending_apply = (grad, offsets)
 
             def _join(mod=mod, cur=cur, side=side):
                 cur.wait_stream(side)
