@@ -387,7 +387,7 @@ def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> Non
                                   ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws, **extras)
             # keeps the buffers the side-stream kernel reads away from the allocator until the join (autograd drops
             # the saved tensors as soon as this node returns)
-            mod._pending_apply = (grad, offsets)
+            mod._pending_apply = (grad, offsets, ids)
 
             def _join(mod=mod, cur=cur, side=side):
                 cur.wait_stream(side)
