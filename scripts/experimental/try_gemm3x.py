@@ -1,6 +1,6 @@
 """First contact of scripts/experimental/tzk_gemm3x.cu with hardware (round-2 groundwork).
 
-    timeout 120 python scripts/experimental/try_gemm3x.py [M]
+    timeout 120 python scripts/experimental/try_gemm3x.py [M] [fwd|dgrad]
 
 Builds the kernel next to its source, runs y = relu(x @ w^T + b) for x [M, 784] against a float64 reference and
 prints the error (target: fp32-GEMM level, <= 1e-6 relative to |x||w| row norms) and the CUDA-event time.  ALWAYS run
@@ -26,29 +26,33 @@ def build():
 
 def main():
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    K, N = 784, 64
+    # "fwd": y = relu(x[M,784] @ w[64,784]^T + b);  "dgrad": dx[M,784] = dz[M,64] @ wT[784,64]^T
+    mode = sys.argv[2] if len(sys.argv) > 2 else "fwd"
+    K, N = (784, 64) if mode == "fwd" else (64, 784)
     lib = build()
     P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
-    lib.tzk_gemm3x_fwd.argtypes = [P, I64, P, I64, P, I64, I32, I32, P, I64, P, P, P]
+    lib.tzk_gemm3x.argtypes = [P, I64, P, I64, P, I64, I32, I32, I32, P, I64, P, P, P]
     torch.manual_seed(0)
     x = torch.randn(M, K, device="cuda")
     w = torch.randn(N, K, device="cuda") / K ** 0.5
-    b = torch.randn(N, device="cuda")
+    b = torch.randn(N, device="cuda") if mode == "fwd" else None
     y = torch.empty(M, N, device="cuda")
     w_hi, w_lo = torch.empty_like(w), torch.empty_like(w)
     st = torch.cuda.current_stream().cuda_stream
 
     def run():
-        rc = lib.tzk_gemm3x_fwd(x.data_ptr(), K, w.data_ptr(), K, b.data_ptr(), M, K, 1, y.data_ptr(), N,
-                                w_hi.data_ptr(), w_lo.data_ptr(), st)
+        rc = lib.tzk_gemm3x(x.data_ptr(), K, w.data_ptr(), K, b.data_ptr() if b is not None else None, M, N, K,
+                            1 if mode == "fwd" else 0, y.data_ptr(), N, w_hi.data_ptr(), w_lo.data_ptr(), st)
         assert rc == 0, rc
 
     run()
     torch.cuda.synchronize()
-    ref = torch.relu(x.double() @ w.double().T + b.double())
+    ref = x.double() @ w.double().T
+    ref = torch.relu(ref + b.double()) if mode == "fwd" else ref
     err = (y.double() - ref).abs().max().item()
     scale = (x.double().norm(dim=1).max() * w.double().norm(dim=1).max()).item()
-    fp32 = (torch.relu(torch.nn.functional.linear(x, w, b)).double() - ref).abs().max().item()
+    lin = torch.nn.functional.linear(x, w, b)
+    fp32 = ((torch.relu(lin) if mode == "fwd" else lin).double() - ref).abs().max().item()
     print(f"M={M}: max abs err {err:.3e} (fp32 F.linear: {fp32:.3e}), relative to |x||w| {err / scale:.3e}")
     for _ in range(3):
         run()

@@ -25,15 +25,20 @@
 namespace {
 
 constexpr int BM = 128;          // rows per tile (UMMA M)
-constexpr int BN = 64;           // output width (UMMA N)
 constexpr int BK = 32;           // K-chunk: 32 floats = one 128-B swizzled row
 constexpr int UK = 8;            // UMMA K for tf32 (32 bytes)
-constexpr int STAGES = 4;
 constexpr int X_BYTES = BM * BK * 4;       // 16 KB
-constexpr int W_BYTES = BN * BK * 4;       //  8 KB
-constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_BYTES;   // X(hi) | X lo | W hi | W lo = 48 KB
-constexpr int TMEM_COLS = 128;   // two 64-column accumulators
 constexpr int NUM_THREADS = 192;
+// BN = output columns per tile (UMMA N, multiple of 16, <= 128): 64 for the forward pass (N = 64), 112 for the
+// input-gradient pass (N = 784 = 7 x 112).  Per stage: X(hi) | X lo | W hi | W lo, each buffer 1024-B aligned.
+template <int BN>
+struct Cfg {
+  static constexpr int W_BYTES = BN * BK * 4;
+  static constexpr int W_PAD = (W_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_PAD;
+  static constexpr int TMEM_COLS = BN <= 64 ? 128 : 256;   // two accumulators, power of two
+  static constexpr int STAGES = BN <= 64 ? 4 : 3;          // 4 x 48 KB / 3 x 60 KB of shared memory
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,17 +92,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
       "r"(accumulate)
       : "memory");
 }
-// 32 lanes x 32 columns of fp32 -> 32 registers per lane (lane i of the warp reads TMEM lane base+i)
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, float* v) {
+// 32 lanes x 16 columns of fp32 -> 16 registers per lane (lane i of the warp reads TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(addr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -116,6 +118,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format TF32 = 2 @ [7,10) / [10,13),
 // K-major A and B (bits 15, 16 = 0), n_dim = N >> 3 @ [17,23), m_dim = M >> 4 @ [24,29)
+template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -132,12 +135,16 @@ struct Params {
   int64_t ld_y;
   int64_t M;
   int K;               // multiple of 32 after padding (the caller's X / W carry zero columns up to it)
+  int N;               // output columns (multiple of BN)
   int relu;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm3x_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
-                  const __grid_constant__ CUtensorMap map_wlo, Params p) {
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+              const __grid_constant__ CUtensorMap map_wlo, Params p) {
+  constexpr int W_BYTES = Cfg<BN>::W_BYTES, W_PAD = Cfg<BN>::W_PAD, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+  constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS, STAGES = Cfg<BN>::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage_base = smem;                                        // STAGES x 48 KB, each buffer 1024-B aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -150,7 +157,8 @@ gemm3x_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.K / BK;
-  const int64_t num_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = p.N / BN;                            // a tile = (128 rows) x (BN columns); n fastest so that the
+  const int64_t num_tiles = (p.M + BM - 1) / BM * n_tiles; // X rows of an m-tile are re-read from L2, not from HBM
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -179,10 +187,10 @@ gemm3x_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* sb = stage_base + stage * STAGE_BYTES;
-          mbar_expect_tx(full + stage, X_BYTES + 2 * W_BYTES);
-          tma_load_2d(sb, &map_x, full + stage, kb * BK, (int)(t * BM));
-          tma_load_2d(sb + 2 * X_BYTES, &map_whi, full + stage, kb * BK, 0);
-          tma_load_2d(sb + 2 * X_BYTES + W_BYTES, &map_wlo, full + stage, kb * BK, 0);
+          mbar_expect_tx(full + stage, X_BYTES + 2 * W_BYTES);   // W_BYTES, not W_PAD: the box is BN rows
+          tma_load_2d(sb, &map_x, full + stage, kb * BK, (int)(t / n_tiles * BM));
+          tma_load_2d(sb + 2 * X_BYTES, &map_whi, full + stage, kb * BK, (int)(t % n_tiles) * BN);
+          tma_load_2d(sb + 2 * X_BYTES + W_PAD, &map_wlo, full + stage, kb * BK, (int)(t % n_tiles) * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -193,7 +201,7 @@ gemm3x_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr uint32_t idesc = make_idesc();
+    constexpr uint32_t idesc = make_idesc<BN>();
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       mbar_wait(acc_empty + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
@@ -203,7 +211,7 @@ gemm3x_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sb = smem_u32(stage_base + stage * STAGE_BYTES);
-          const uint32_t a_hi = sb, a_lo = sb + X_BYTES, b_hi = sb + 2 * X_BYTES, b_lo = b_hi + W_BYTES;
+          const uint32_t a_hi = sb, a_lo = sb + X_BYTES, b_hi = sb + 2 * X_BYTES, b_lo = b_hi + W_PAD;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint32_t ko = k * UK * 4;           // 32 B per k-step inside the 128-B swizzled row
@@ -253,21 +261,22 @@ gemm3x_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       // ---- epilogue of this tile ---------------------------------------------------------------------------
       mbar_wait(acc_full + acc, acc_phase);
       tc_fence_after();
-      const int64_t row = t * BM + quarter * 32 + lane;
+      const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
+      const int col0 = (int)(t % n_tiles) * BN;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-      float v[32];
+      float v[16];
 #pragma unroll
-      for (int half = 0; half < BN / 32; ++half) {
-        tmem_ld32(taddr + half * 32, v);
+      for (int part = 0; part < BN / 16; ++part) {
+        tmem_ld16(taddr + part * 16, v);
         if (row < p.M) {
-          float* yr = p.y + row * p.ld_y + half * 32;
+          float* yr = p.y + row * p.ld_y + col0 + part * 16;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          for (int c = 0; c < 16; c += 4) {
             float4 o;
-            o.x = v[c] + (p.bias ? __ldg(p.bias + half * 32 + c) : 0.f);
-            o.y = v[c + 1] + (p.bias ? __ldg(p.bias + half * 32 + c + 1) : 0.f);
-            o.z = v[c + 2] + (p.bias ? __ldg(p.bias + half * 32 + c + 2) : 0.f);
-            o.w = v[c + 3] + (p.bias ? __ldg(p.bias + half * 32 + c + 3) : 0.f);
+            o.x = v[c] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c) : 0.f);
+            o.y = v[c + 1] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 1) : 0.f);
+            o.z = v[c + 2] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 2) : 0.f);
+            o.w = v[c + 3] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 3) : 0.f);
             if (p.relu) {
               o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
             }
@@ -319,27 +328,36 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 }
 }  // namespace
 
-// y[M,64] = act(x[M,K] @ w[64,K]^T + bias).  x rows 16-B aligned with ld_x % 4 == 0; columns beyond K up to a
-// multiple of 32 are out of bounds for the tensor map and read as zeros.  w_hi / w_lo: [64, ld_w] scratch written here.
-extern "C" int tzk_gemm3x_fwd(const float* x, int64_t ld_x, const float* w, int64_t ld_w, const float* bias, int64_t M,
-                              int32_t K, int32_t relu, float* y, int64_t ld_y, float* w_hi, float* w_lo,
-                              void* stream) {
-  if (M <= 0 || K <= 0 || (ld_x % 4) || (ld_w % 4) || (ld_y % 4)) return 1;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int64_t nw = (int64_t)BN * ld_w;
-  split_w_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, nw, w_hi, w_lo);
-  CUtensorMap mx, mh, ml;
-  if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, w_hi, BN, K, ld_w, BN) || make_map(&ml, w_lo, BN, K, ld_w, BN))
-    return 2;
-  Params p;
-  p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.relu = relu;
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 256;
-  cudaFuncSetAttribute(gemm3x_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int BN>
+static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
+  const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
+  cudaFuncSetAttribute(gemm3x_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t tiles = (M + BM - 1) / BM;
+  const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  gemm3x_fwd_kernel<<<grid, NUM_THREADS, smem, st>>>(mx, mh, ml, p);
+  gemm3x_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+// y[M,N] = act(x[M,K] @ w[N,K]^T + bias) with fp32-equivalent accuracy (3xTF32).  N = 64 (forward of the wide tower
+// layer, K = 784) or a multiple of 112 (its input gradient: x = dZ [M,64], w = W^T [784,64], no bias / ReLU).
+// Rows 16-B aligned, ld % 4 == 0; K columns beyond the tensor are read as zeros up to the next multiple of 32.
+// w_hi / w_lo: [N, ld_w] scratch written here.
+extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t ld_w, const float* bias, int64_t M,
+                          int32_t N, int32_t K, int32_t relu, float* y, int64_t ld_y, float* w_hi, float* w_lo,
+                          void* stream) {
+  if (M <= 0 || K <= 0 || (ld_x % 4) || (ld_w % 4) || (ld_y % 4)) return 1;
+  if (N != 64 && N % 112 != 0) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int BN = N == 64 ? 64 : 112;
+  const int64_t nw = (int64_t)N * ld_w;
+  split_w_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, nw, w_hi, w_lo);
+  CUtensorMap mx, mh, ml;
+  if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, w_hi, N, K, ld_w, BN) || make_map(&ml, w_lo, N, K, ld_w, BN))
+    return 2;
+  Params p;
+  p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.N = N; p.relu = relu;
+  return BN == 64 ? launch<64>(mx, mh, ml, p, st) : launch<112>(mx, mh, ml, p, st);
 }
