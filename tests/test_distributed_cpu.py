@@ -49,7 +49,8 @@ def _concat_batches(batches):
     return out
 
 
-def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=False, static_capacity=None):
+def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=False, static_capacity=None,
+            sparse_opt=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dev = f"cuda:{rank}" if use_cuda else "cpu"
     if use_cuda:
@@ -75,6 +76,10 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
             shd.model.load_state_dict(ref.model.state_dict())
             sharded = shard_model(shd.model, dev, default=sharding, rw_min_rows=rw_min_rows, source=ref.model,
                                   static_capacity=static_capacity)
+            if sparse_opt is not None:     # e.g. "adam": second state + device-side step counter on every shard
+                from torcheasyrec_b200.embedding_modules import SparseOptimizerSpec
+
+                ref.model.set_sparse_optimizer(SparseOptimizerSpec.from_name(sparse_opt, lr=0.01))
             shd.model.set_sparse_optimizer(ref.model.sparse_collections()[0].optimizer)
             from torcheasyrec_b200.rank_models import dense_optimizer_from_config
 
@@ -130,11 +135,12 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
         dist.destroy_process_group()
 
 
-def _run(world, name, sharding, rw_min_rows=0, use_cuda=False, static_capacity=None):
+def _run(world, name, sharding, rw_min_rows=0, use_cuda=False, static_capacity=None, sparse_opt=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, sharding, rw_min_rows, q, use_cuda, static_capacity))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, sharding, rw_min_rows, q, use_cuda, static_capacity,
+                                               sparse_opt))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -168,6 +174,13 @@ def test_deepfm_mixed_three_ranks():
 ])
 def test_w_invariance_at_larger_world_sizes(world, name, sharding, rw_min):
     _run(world, name, sharding, rw_min_rows=rw_min)
+
+
+@pytest.mark.parametrize("opt", ["adam", "partial_rowwise_adam"])
+def test_sharded_adam_two_ranks(opt):
+    # the Adam variants on the owners (tzk_fused_bwd_ex path): every shard keeps both moments and its own step counter;
+    # W-invariance of the updated tables as for Adagrad
+    _run(2, "dlrm_criteo", "row_wise", sparse_opt=opt)
 
 
 def test_din_sequence_two_ranks():
