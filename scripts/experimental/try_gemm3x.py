@@ -1,6 +1,6 @@
 """First contact of scripts/experimental/tzk_gemm3x.cu with hardware (round-2 groundwork).
 
-    timeout 120 python scripts/experimental/try_gemm3x.py [M] [fwd|dgrad]
+    timeout 120 python scripts/experimental/try_gemm3x.py [M] [fwd|dgrad|wgrad]
 
 Builds the kernel next to its source, runs y = relu(x @ w^T + b) for x [M, 784] against a float64 reference and
 prints the error (target: fp32-GEMM level, <= 1e-6 relative to |x||w| row norms) and the CUDA-event time.  ALWAYS run
@@ -28,9 +28,11 @@ def main():
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     # "fwd": y = relu(x[M,784] @ w[64,784]^T + b);  "dgrad": dx[M,784] = dz[M,64] @ wT[784,64]^T
     mode = sys.argv[2] if len(sys.argv) > 2 else "fwd"
-    K, N = (784, 64) if mode == "fwd" else (64, 784)
     lib = build()
     P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    if mode == "wgrad":
+        return wgrad(lib, M)
+    K, N = (784, 64) if mode == "fwd" else (64, 784)
     lib.tzk_gemm3x.argtypes = [P, I64, P, I64, P, I64, I32, I32, I32, P, I64, P, P, P]
     torch.manual_seed(0)
     x = torch.randn(M, K, device="cuda")
@@ -63,6 +65,43 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print(f"{e0.elapsed_time(e1) / 10 * 1e3:.1f} us per call (incl. the W split and three tensor-map encodes)")
+
+
+def wgrad(lib, M, K=784, slabs=21):
+    """dw[64, K] = dz[M, 64]^T @ x[M, K]: 7 column tiles x 21 row slabs = 147 CTAs at K = 784."""
+    P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    lib.tzk_wgrad3x.argtypes = [P, I64, P, I64, I64, I32, I32, P, P, I64, P]
+    lib.tzk_wgrad3x_partial_floats.restype = I64
+    lib.tzk_wgrad3x_partial_floats.argtypes = [I32, I32]
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device="cuda")
+    dz = torch.randn(M, 64, device="cuda") / M ** 0.5
+    dw = torch.empty(64, K, device="cuda")
+    partial = torch.empty(lib.tzk_wgrad3x_partial_floats(K, slabs), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        rc = lib.tzk_wgrad3x(x.data_ptr(), K, dz.data_ptr(), 64, M, K, slabs, partial.data_ptr(), dw.data_ptr(), K, st)
+        assert rc == 0, rc
+
+    run()
+    torch.cuda.synchronize()
+    ref = dz.double().T @ x.double()
+    err = (dw.double() - ref).abs().max().item()
+    fp32 = ((dz.T @ x).double() - ref).abs().max().item()
+    first = dw.clone()
+    run()
+    torch.cuda.synchronize()
+    print(f"wgrad M={M}: max abs err {err:.3e} (fp32 matmul: {fp32:.3e}); bitwise repeatable: {torch.equal(first, dw)}")
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{e0.elapsed_time(e1) / 10 * 1e3:.1f} us per call (incl. two tensor-map encodes and the slab reduction)")
 
 
 if __name__ == "__main__":

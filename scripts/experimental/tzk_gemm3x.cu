@@ -116,11 +116,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major, SWIZZLE_128B operand (canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-B units, mma_traits_sm100.hpp
+// make_umma_desc<Major::MN>): a swizzle atom is 8 k-rows x 128 B of MN (= what one TMA SWIZZLE_128B box row group
+// holds); LBO = bytes between consecutive 32-float MN groups, SBO = bytes between consecutive 8-row k groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor (InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format TF32 = 2 @ [7,10) / [10,13),
 // K-major A and B (bits 15, 16 = 0), n_dim = N >> 3 @ [17,23), m_dim = M >> 4 @ [24,29)
-template <int BN>
+template <int BN, bool MN_MAJOR = false>
 __host__ __device__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | (MN_MAJOR ? (1u << 15) | (1u << 16) : 0u) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -296,6 +309,155 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   if (warp == 1) tmem_free(tmem_base, TMEM_COLS);
 }
 
+// ======================================================================================================================
+// Weight gradient of the same layer:  dW[n, k] = sum_m dZ[m, n] * X[m, k]   (n < 64, k < K = 784, m < M = batch).
+// The reduction runs over the batch, so both operands are MN-major as they lie in memory: A = X^T (UMMA M = 128 of
+// X's columns), B = dZ^T (UMMA N = 64).  Work item = (column tile j of 128, row slab s); each CTA owns one item, streams
+// its slab in chunks of 32 rows (4 k-steps of 8), and writes a partial [128 x 64] block; wgrad_reduce_kernel adds the
+// slabs in a fixed order and transposes into dW[64, K].  X is read exactly once over all items (tiles read disjoint
+// columns); dZ is re-read by the 7 column tiles from L2.
+// Per stage: A hi (4 boxes of 32 rows x 128 B = 16 KB) | A lo | B hi (2 boxes = 8 KB) | B lo.
+constexpr int WG_ROWS = 32;                         // batch rows per chunk = 4 k-steps
+constexpr int WG_BOX = WG_ROWS * 128;               // one TMA box: 32 rows x 32 floats = 4 KB
+constexpr int WG_A = 4 * WG_BOX, WG_B = 2 * WG_BOX; // 16 KB, 8 KB
+constexpr int WG_STAGE = 2 * WG_A + 2 * WG_B;       // 48 KB
+constexpr int WG_STAGES = 4;
+
+struct WgParams {
+  float* partial;      // [slabs, k_tiles * 128, 64]
+  int64_t M;           // batch rows
+  int64_t slab_rows;   // multiple of 32
+  int k_tiles;         // ceil(K / 128)
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE);
+  uint64_t* full = bars;                    // TMA -> transform
+  uint64_t* ready = bars + WG_STAGES;       // transform -> MMA (4 arrivals)
+  uint64_t* empty = bars + 2 * WG_STAGES;   // MMA -> TMA
+  uint64_t* acc_full = bars + 3 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WG_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x % p.k_tiles;                  // column tile of X
+  const int64_t slab = blockIdx.x / p.k_tiles;
+  const int64_t row0 = slab * p.slab_rows;
+  const int64_t rows = (p.M - row0 < p.slab_rows) ? p.M - row0 : p.slab_rows;
+  const int num_c = (int)((rows + WG_ROWS - 1) / WG_ROWS);  // rows past M are zero-filled by the TMA
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, 4);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < num_c; ++c) {
+        mbar_wait(empty + stage, phase ^ 1);
+        uint8_t* sb = smem + stage * WG_STAGE;
+        mbar_expect_tx(full + stage, WG_A + WG_B);
+        const int r = (int)(row0 + (int64_t)c * WG_ROWS);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(sb + b * WG_BOX, &map_x, full + stage, jt * 128 + b * 32, r);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) tma_load_2d(sb + 2 * WG_A + b * WG_BOX, &map_dz, full + stage, b * 32, r);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    constexpr uint32_t idesc = make_idesc<64, true>();
+    for (int c = 0; c < num_c; ++c) {
+      mbar_wait(ready + stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sb = smem_u32(smem + stage * WG_STAGE);
+        const uint32_t a_hi = sb, a_lo = sb + WG_A, b_hi = sb + 2 * WG_A, b_lo = b_hi + WG_B;
+#pragma unroll
+        for (int k = 0; k < WG_ROWS / UK; ++k) {
+          const uint32_t ko = k * 1024;             // next group of 8 batch rows inside every box
+          const uint32_t first = (c | k) ? 1u : 0u;
+          mma_tf32(tmem_base, make_desc_mn(a_hi + ko, WG_BOX, 1024), make_desc_mn(b_hi + ko, WG_BOX, 1024), idesc, first);
+          mma_tf32(tmem_base, make_desc_mn(a_lo + ko, WG_BOX, 1024), make_desc_mn(b_hi + ko, WG_BOX, 1024), idesc, 1u);
+          mma_tf32(tmem_base, make_desc_mn(a_hi + ko, WG_BOX, 1024), make_desc_mn(b_lo + ko, WG_BOX, 1024), idesc, 1u);
+        }
+        tc_commit(empty + stage);
+        if (c == num_c - 1) tc_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int tw = warp - 2, quarter = warp & 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < num_c; ++c) {
+      mbar_wait(full + stage, phase);
+      uint8_t* sb = smem + stage * WG_STAGE;
+      // A: 1024 float4 (hi at +0, lo at +WG_A); B: 512 float4 (hi at +2*WG_A, lo at +2*WG_A+WG_B); element-wise.
+#pragma unroll
+      for (int q = 0; q < (WG_A + WG_B) / 16 / 128; ++q) {
+        const int i = q * 128 + tw * 32 + lane;                       // 0..1535
+        float4* hi = reinterpret_cast<float4*>(i < WG_A / 16 ? sb : sb + 2 * WG_A) + (i < WG_A / 16 ? i : i - WG_A / 16);
+        float4* lo = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(hi) + (i < WG_A / 16 ? WG_A : WG_B));
+        const float4 x = *hi;
+        float4 h, l;
+        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+        l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+        *hi = h;
+        *lo = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready + stage);
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    // epilogue: TMEM lane = X column inside the tile, TMEM column = n
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int krow = jt * 128 + quarter * 32 + lane;
+    float* out = p.partial + ((int64_t)slab * p.k_tiles * 128 + krow) * 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float v[16];
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      tmem_ld16(taddr + part * 16, v);
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        *reinterpret_cast<float4*>(out + part * 16 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_free(tmem_base, 64);
+}
+
+// dW[n, k] = sum over slabs (fixed order) of partial[s, k, n]; one thread per (k, n), n fastest for the reads
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slabs, int k_pad, int K, float* __restrict__ dw,
+                                    int64_t ld_dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * 64) return;
+  const int k = i >> 6, n = i & 63;
+  float acc = 0.f;
+  for (int s = 0; s < slabs; ++s) acc += partial[((int64_t)s * k_pad + k) * 64 + n];
+  dw[(int64_t)n * ld_dw + k] = acc;
+}
+
 // ---- host: tensor maps -------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -360,4 +522,28 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   Params p;
   p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.N = N; p.relu = relu;
   return BN == 64 ? launch<64>(mx, mh, ml, p, st) : launch<112>(mx, mh, ml, p, st);
+}
+
+// dw[64, K] = dz[M, 64]^T @ x[M, K]  (3xTF32; fixed-order reduction over `slabs` row slabs -> run-to-run deterministic).
+// partial: scratch of slabs * ceil(K/128)*128 * 64 floats.  slabs <= 0 picks one work item per SM.
+extern "C" int64_t tzk_wgrad3x_partial_floats(int32_t K, int32_t slabs) {
+  return (int64_t)slabs * ((K + 127) / 128 * 128) * 64;
+}
+extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_t ld_dz, int64_t M, int32_t K,
+                           int32_t slabs, float* partial, float* dw, int64_t ld_dw, void* stream) {
+  if (M <= 0 || K <= 0 || slabs <= 0 || (ld_x % 4) || (ld_dz % 4)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap mx, mz;
+  if (make_map(&mx, x, M, K, ld_x, WG_ROWS) || make_map(&mz, dz, M, 64, ld_dz, WG_ROWS)) return 2;
+  WgParams p;
+  p.partial = partial;
+  p.M = M;
+  p.k_tiles = (K + 127) / 128;
+  p.slab_rows = ((M + slabs - 1) / slabs + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+  const int used = (int)((M + p.slab_rows - 1) / p.slab_rows);           // slabs that hold rows (<= slabs)
+  const size_t smem = (size_t)WG_STAGES * WG_STAGE + 256;
+  cudaFuncSetAttribute(wgrad3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  wgrad3x_kernel<<<used * p.k_tiles, NUM_THREADS, smem, st>>>(mx, mz, p);
+  wgrad_reduce_kernel<<<(K * 64 + 255) / 256, 256, 0, st>>>(partial, used, p.k_tiles * 128, K, dw, ld_dw);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
