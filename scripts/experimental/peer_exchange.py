@@ -43,13 +43,18 @@ def load_lib():
                         "-std=c++17", "-Xcompiler", "-fPIC", "-shared", src, "-o", lib], check=True)
     if dist.is_initialized():
         dist.barrier()
-    L = ctypes.CDLL(lib)
+    _LIB = declare(ctypes.CDLL(lib))
+    return _LIB
+
+
+def declare(L):
+    """ctypes signatures of tzk_peer.cu's entry points (also used for the host-compiled copy in the CPU tests)."""
     P, I32, I64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
     L.tzk_peer_pooled_gather_fwd.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P, I64, P]
-    L.tzk_peer_barrier.argtypes = [P, I32, I32, P, P]
+    if hasattr(L, "tzk_peer_barrier"):
+        L.tzk_peer_barrier.argtypes = [P, I32, I32, P, P]
     L.tzk_peer_pull_counts.argtypes = [P, I32, I32, I32, P, P]
     L.tzk_peer_pull.argtypes = [P, P, P, I32, I32, I32, I32, I32, I32, P, P, I64, P, P, P]
-    _LIB = L
     return L
 
 
@@ -59,7 +64,7 @@ def _check(rc: int, what: str) -> None:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0
 
 
 class _Symm:

@@ -18,7 +18,14 @@
 //
 // Build + try (next round, 2 GPUs):
 //   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 scripts/experimental/try_peer.py
+#ifdef TZK_CPU_SHIM
+#include "cuda_cpu_shim.h"   // host execution for tests/test_experimental_kernels_cpu.py (not the barrier kernel)
+#else
 #include <cuda_runtime.h>
+#define TZK_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define TZK_UNPAREN(...) __VA_ARGS__
+#define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) TZK_UNPAREN kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
 #include <stdint.h>
 
 namespace {
@@ -50,7 +57,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
                               const int64_t* __restrict__ offsets, int F, int B, int W, float* __restrict__ out,
                               int64_t ld_out) {
   constexpr int NG = kThreads / G, TB = 32, U = 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TZK_DYN_SMEM(unsigned char, smem_raw);
   FeatDesc* fd = reinterpret_cast<FeatDesc*>(smem_raw);
   int64_t* w_off = reinterpret_cast<int64_t*>(fd + F);                      // [W * F] arena offsets per (rank, feature)
   unsigned long long* base = reinterpret_cast<unsigned long long*>(w_off + (size_t)W * F);   // [W]
@@ -130,6 +137,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
   }
 }
 
+#ifndef TZK_CPU_SHIM
 // ---- barrier over the NVSwitch domain ------------------------------------------------------------------------------
 // pads.p[r] -> rank r's flag array (uint32 [W]) in symmetric memory; flag[src] on rank dst = last epoch src reached.
 __global__ void peer_barrier_kernel(const __grid_constant__ Peers pads, int me, int W, uint32_t* __restrict__ epoch) {
@@ -150,6 +158,8 @@ __global__ void peer_barrier_kernel(const __grid_constant__ Peers pads, int me, 
     } while ((int32_t)(v - e) < 0);
   }
 }
+
+#endif  // TZK_CPU_SHIM
 
 // ---- backward: owner-side pull ----------------------------------------------------------------------------------
 // recv_counts[src, f] = counts of rank src for destination `me`
@@ -222,9 +232,8 @@ extern "C" int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int6
   const size_t smem = (size_t)F * sizeof(FeatDesc) + (size_t)W * F * 8 + (size_t)W * 8;
   const int grid = grid_for((B + 31) / 32);
 #define TZK_PEER_LAUNCH(G)                                                                                             \
-  peer_pooled_gather_fwd_kernel<G><<<grid, kThreads, smem, st>>>(t, rf_w_off, feat_rows, feat_block, feat_owner,       \
-                                                                 feat_dim, feat_col, feat_pool, ids, offsets, F, B, W, \
-                                                                 out, ld_out)
+  TZK_LAUNCH((peer_pooled_gather_fwd_kernel<G>), grid, kThreads, smem, st, t, rf_w_off, feat_rows, feat_block,         \
+             feat_owner, feat_dim, feat_col, feat_pool, ids, offsets, F, B, W, out, ld_out)
   if (max_dim <= 16) TZK_PEER_LAUNCH(4);
   else if (max_dim <= 32) TZK_PEER_LAUNCH(8);
   else if (max_dim <= 64) TZK_PEER_LAUNCH(16);
@@ -233,19 +242,21 @@ extern "C" int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int6
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
+#ifndef TZK_CPU_SHIM
 extern "C" int tzk_peer_barrier(const uint64_t* pad_ptrs, int32_t me, int32_t W, uint32_t* epoch, void* stream) {
   Peers p;
   if (fill(&p, pad_ptrs, W) || me < 0 || me >= W) return 1;
   peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, me, W, epoch);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
+#endif
 
 extern "C" int tzk_peer_pull_counts(const uint64_t* counts_ptrs, int32_t me, int32_t W, int32_t F, int32_t* recv_counts,
                                     void* stream) {
   Peers p;
   if (fill(&p, counts_ptrs, W) || F <= 0) return 1;
-  peer_pull_counts_kernel<<<(W * F + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, me, W, F,
-                                                                                                   recv_counts);
+  TZK_LAUNCH((peer_pull_counts_kernel), (W * F + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream), p, me, W, F,
+             recv_counts);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -258,8 +269,8 @@ extern "C" int tzk_peer_pull(const uint64_t* ids_ptrs, const uint64_t* pos_ptrs,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t slots = (int64_t)W * cap;
 #define TZK_PEER_LAUNCH(G)                                                                                          \
-  peer_pull_kernel<G><<<grid_for((slots + kThreads / G - 1) / (kThreads / G)), kThreads, 0, st>>>(                  \
-      pi, pp, pg, me, W, cap, F, B, D, feat_col, bounds, ld_grad, recv_ids, recv_g)
+  TZK_LAUNCH((peer_pull_kernel<G>), grid_for((slots + kThreads / G - 1) / (kThreads / G)), kThreads, 0, st, pi, pp, pg, \
+             me, W, cap, F, B, D, feat_col, bounds, ld_grad, recv_ids, recv_g)
   if (D <= 16) TZK_PEER_LAUNCH(4);
   else if (D <= 32) TZK_PEER_LAUNCH(8);
   else if (D <= 64) TZK_PEER_LAUNCH(16);

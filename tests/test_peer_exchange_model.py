@@ -1,13 +1,19 @@
 """Host logic and index algebra of the peer-memory sparse step (scripts/experimental/peer_exchange.py, round-2
 groundwork — its CUDA kernels in scripts/experimental/tzk_peer.cu have not run on hardware yet).
 
-W ranks live in one process as threads; "symmetric memory" is a registry of per-rank tensors every rank can see, the
-device barrier is a threading.Barrier, and each peer kernel is replaced by a loop-level restatement of what the CUDA
-kernel does (same owner rule, same wire / slot arithmetic).  Everything above the kernels — `PeerState` itself, the
-wire capacity, `bounds`, `owner_layout_static`, the call into the fused update — is the real code.  Checked against the
+W ranks live in one process as threads; "symmetric memory" is a registry of per-rank tensors every rank can see and the
+device barrier is a threading.Barrier.  The peer kernels run in two flavours:
+  * "model":  a loop-level restatement of what each CUDA kernel does (same owner rule, same wire / slot arithmetic);
+  * "source": tzk_peer.cu ITSELF, compiled for the host with scripts/experimental/cuda_cpu_shim.h (one std::thread per
+              CUDA thread, real __syncthreads) and called through the same ctypes signatures and pointer tables as on
+              the GPU — index arithmetic, guards and argument marshalling of the real source, minus PTX and timing.
+Everything above the kernels — `PeerState` itself, the wire capacity, `bounds`, `owner_layout_static`, the call into
+the fused update — is the real code.  Checked against the
 UNSHARDED collection on the same ids: pooled outputs bit-equal, updated tables equal to 1e-6 (the owners apply the
 1/W gradient scale, one more rounding than the unsharded twin)."""
+import ctypes
 import os
+import subprocess
 import sys
 import threading
 
@@ -33,6 +39,36 @@ peer_exchange = pytest.importorskip("peer_exchange")
 class _SimSymm:
     def __init__(self, t, everyone):
         self.t, self.everyone = t, everyone      # everyone[r] -> rank r's tensor of the same allocation
+
+    @property
+    def ptrs(self):                              # the pointer table the kernels get (complete after the host barrier)
+        W = len(self.everyone)
+        return (ctypes.c_uint64 * W)(*[self.everyone[r].data_ptr() for r in range(W)])
+
+
+@pytest.fixture(scope="module")
+def host_compiled_peer_lib(tmp_path_factory):
+    exp = os.path.join(os.path.dirname(HERE), "scripts", "experimental")
+    out = str(tmp_path_factory.mktemp("shim") / "libtzk_peer_cpu.so")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-x", "c++",
+                    os.path.join(exp, "tzk_peer.cu"), "-shared", "-fPIC", "-o", out], check=True)
+    return peer_exchange.declare(ctypes.CDLL(out))
+
+
+def _make_source_state(registry, tbar, lib):
+    """PeerState with its own _k_gather / _k_pull_counts / _k_pull (ctypes calls into the host-compiled CUDA source)."""
+    Model = _make_sim_state(registry, tbar)
+
+    class SourcePeerState(Model):
+        def _init_io(self):
+            super()._init_io()
+            self.lib = lib
+
+        _k_gather = peer_exchange.PeerState._k_gather
+        _k_pull_counts = peer_exchange.PeerState._k_pull_counts
+        _k_pull = peer_exchange.PeerState._k_pull
+
+    return SourcePeerState
 
 
 def _make_sim_state(registry, tbar):
@@ -118,8 +154,9 @@ def _configs():
             mk("t_mean", 301, ["e"], PoolingType.MEAN), mk("t_tw", 150, ["f"])]
 
 
+@pytest.mark.parametrize("kernels", ["model", "source"])
 @pytest.mark.parametrize("W", [2, 3, 4])
-def test_peer_step_matches_unsharded(W):
+def test_peer_step_matches_unsharded(W, kernels, host_compiled_peer_lib):
     torch.manual_seed(0)
     rng = np.random.default_rng(7)
     cfgs = _configs()
@@ -151,7 +188,8 @@ def test_peer_step_matches_unsharded(W):
             groups.append(g)
 
         registry, tbar = {}, threading.Barrier(W)
-        Sim = _make_sim_state(registry, tbar)
+        Sim = (_make_sim_state(registry, tbar) if kernels == "model"
+               else _make_source_state(registry, tbar, host_compiled_peer_lib))
         states, outs, errors = [None] * W, [None] * W, []
 
         def rank_main(r):
