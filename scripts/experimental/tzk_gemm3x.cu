@@ -22,9 +22,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "tzk_umma_desc.h"
+
 namespace {
 
-constexpr int BM = 128;          // rows per tile (UMMA M)
 constexpr int BK = 32;           // K-chunk: 32 floats = one 128-B swizzled row
 constexpr int UK = 8;            // UMMA K for tf32 (32 bytes)
 constexpr int X_BYTES = BM * BK * 4;       // 16 KB
@@ -102,38 +103,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(addr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory operand descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major: 1) | [32,46) SBO >> 4 (1024 B between
-//   8-row groups) | [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// MN-major, SWIZZLE_128B operand (canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-B units, mma_traits_sm100.hpp
-// make_umma_desc<Major::MN>): a swizzle atom is 8 k-rows x 128 B of MN (= what one TMA SWIZZLE_128B box row group
-// holds); LBO = bytes between consecutive 32-float MN groups, SBO = bytes between consecutive 8-row k groups.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format TF32 = 2 @ [7,10) / [10,13),
-// K-major A and B (bits 15, 16 = 0), n_dim = N >> 3 @ [17,23), m_dim = M >> 4 @ [24,29)
-template <int BN, bool MN_MAJOR = false>
-__host__ __device__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (MN_MAJOR ? (1u << 15) | (1u << 16) : 0u) | ((uint32_t)(BN >> 3) << 17) |
-         ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ float tf32_rna(float x) {
