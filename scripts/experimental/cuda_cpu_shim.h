@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -41,6 +42,7 @@ namespace tzk_shim {
 inline thread_local dim3 t_thread, t_block, t_bdim, t_gdim;
 inline thread_local std::barrier<>* t_bar = nullptr;   // per emulated thread: launches may run concurrently
 inline thread_local unsigned char* t_dyn = nullptr;
+inline thread_local std::barrier<>* t_wbar = nullptr;  // the thread's warp (32 consecutive linear thread ids)
 
 template <class Body>
 void launch(dim3 grid, dim3 block, size_t smem, Body body) {
@@ -51,6 +53,8 @@ void launch(dim3 grid, dim3 block, size_t smem, Body body) {
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         std::barrier<> bar(n);
+        std::vector<std::unique_ptr<std::barrier<>>> warps;
+        for (unsigned w = 0; w * 32 < n; ++w) warps.emplace_back(new std::barrier<>(n - w * 32 < 32 ? n - w * 32 : 32));
         std::vector<std::thread> threads;
         threads.reserve(n);
         for (unsigned t = 0; t < n; ++t)
@@ -61,8 +65,10 @@ void launch(dim3 grid, dim3 block, size_t smem, Body body) {
             t_gdim = grid;
             t_bar = &bar;
             t_dyn = base;
+            t_wbar = warps[t / 32].get();
             body();
             bar.arrive_and_drop();   // a thread that returned early must not strand the others at a barrier
+            t_wbar->arrive_and_drop();
           });
         for (auto& th : threads) th.join();
       }
@@ -82,6 +88,7 @@ void launch(dim3 grid, dim3 block, size_t smem, Body body) {
 #define __align__(n) alignas(n)
 #define __shared__ static
 #define __syncthreads() tzk_shim::t_bar->arrive_and_wait()
+#define __syncwarp() tzk_shim::t_wbar->arrive_and_wait()
 template <class T> inline T __ldg(const T* p) { return *p; }
 #define TZK_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(tzk_shim::t_dyn)
 #define TZK_UNPAREN(...) __VA_ARGS__

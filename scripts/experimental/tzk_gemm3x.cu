@@ -3,7 +3,7 @@
 // Round-2 groundwork: the one wide tower layer of DLRM's final MLP,
 //     Y[M,64] = act(X[M,K] @ W[64,K]^T + bias)            (tzrec/modules/mlp.py:20-84, K = 784)
 // as a hand-written sm_100a kernel with fp32-equivalent accuracy on the 5th-gen tensor cores: tcgen05.mma kind::tf32
-// with the 3xTF32 split  x*w ~= hi(x)*hi(w) + lo(x)*hi(w) + hi(x)*lo(w),  hi = cvt.rna.tf32, lo = v - hi.
+// with the 3xTF32 split  x*w ~= hi(x)*hi(w) + lo(x)*hi(w) + hi(x)*lo(w),  hi = cvt.rna.tf32(v), lo = cvt.rna.tf32(v - hi).
 // It replaces cuBLASLt's BF16x9 path (100 us GEMM + 97 us inf/nan scan + 6.5 us bias/ReLU at B = 65536).
 //
 // Structure (one CTA per SM, persistent over 128-row tiles, 192 threads):
@@ -17,14 +17,25 @@
 // per accumulator: acc_full (MMA commit -> epilogue), acc_empty (epilogue -> MMA).
 //
 // Build + try (next round, on a B200):  python scripts/experimental/try_gemm3x.py
-#include <cuda.h>
-#include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 #include "tzk_umma_desc.h"
+#ifdef TZK_CPU_SHIM
+#include "cuda_cpu_shim.h"      // host execution for tests/test_experimental_gemm3x_emu.py:
+#include "tcgen05_cpu_emu.h"    // TMA / tcgen05 / mbarrier / TMEM emulated from their documented semantics
+#else
+#include <cuda.h>
+#include <cuda_runtime.h>
+#define TZK_DYN_SMEM(type, name) extern __shared__ __align__(1024) type name[]
+#define TZK_UNPAREN(...) __VA_ARGS__
+#define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) TZK_UNPAREN kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
 
 namespace {
+#ifndef TZK_CPU_SHIM
+#include "tzk_tcgen05_ptx.h"
+#endif
 
 constexpr int BK = 32;           // K-chunk: 32 floats = one 128-B swizzled row
 constexpr int UK = 8;            // UMMA K for tf32 (32 bytes)
@@ -40,76 +51,6 @@ struct Cfg {
   static constexpr int TMEM_COLS = BN <= 64 ? 128 : 256;   // two accumulators, power of two
   static constexpr int STAGES = BN <= 64 ? 4 : 3;          // 4 x 48 KB / 3 x 60 KB of shared memory
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ---- mbarrier ------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-
-// ---- TMA ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// ---- tcgen05 -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-}
-__device__ __forceinline__ void tmem_free(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
-      "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 16 columns of fp32 -> 16 registers per lane (lane i of the warp reads TMEM lane base+i)
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(addr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 struct Params {
   const float* bias;   // [64] or NULL
@@ -127,7 +68,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
               const __grid_constant__ CUtensorMap map_wlo, Params p) {
   constexpr int W_BYTES = Cfg<BN>::W_BYTES, W_PAD = Cfg<BN>::W_PAD, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS, STAGES = Cfg<BN>::STAGES;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  TZK_DYN_SMEM(uint8_t, smem);
   uint8_t* stage_base = smem;                                        // STAGES x 48 KB, each buffer 1024-B aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;                 // [STAGES] TMA -> transform   (1 arrival + tx bytes)
@@ -152,7 +93,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_init(acc_full + a, 1);
       mbar_init(acc_empty + a, 4);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -231,11 +172,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const float4 x = hi[i];
           float4 h, l;
           h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+          l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
           hi[i] = h;
           lo[i] = l;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        fence_proxy_async();   // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive(ready + stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -301,7 +242,7 @@ struct WgParams {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, WgParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  TZK_DYN_SMEM(uint8_t, smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE);
   uint64_t* full = bars;                    // TMA -> transform
   uint64_t* ready = bars + WG_STAGES;       // transform -> MMA (4 arrivals)
@@ -323,7 +264,7 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       mbar_init(empty + s, 1);
     }
     mbar_init(acc_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 64);
   tc_fence_before();
@@ -387,11 +328,11 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const float4 x = *hi;
         float4 h, l;
         h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-        l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+        l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
         *hi = h;
         *lo = l;
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(ready + stage);
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
@@ -428,6 +369,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slabs
 }
 
 // ---- host: tensor maps -------------------------------------------------------------------------------------
+#ifdef TZK_CPU_SHIM
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  map->base = base; map->rows = rows; map->cols = cols; map->ld = ld; map->box_rows = box_rows;
+  return 0;
+}
+#else
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -448,13 +395,14 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 2;
 }
+#endif
 
 __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const float h = tf32_rna(w[i]);
     hi[i] = h;
-    lo[i] = w[i] - h;
+    lo[i] = tf32_rna(w[i] - h);   // exactly representable: the tensor core would truncate, not round
   }
 }
 }  // namespace
@@ -462,13 +410,15 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 template <int BN>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
+#ifndef TZK_CPU_SHIM
   cudaFuncSetAttribute(gemm3x_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  gemm3x_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(mx, mh, ml, p);
+  TZK_LAUNCH((gemm3x_kernel<BN>), grid, NUM_THREADS, smem, st, mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -484,7 +434,7 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int BN = N == 64 ? 64 : 112;
   const int64_t nw = (int64_t)N * ld_w;
-  split_w_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, nw, w_hi, w_lo);
+  TZK_LAUNCH((split_w_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_hi, w_lo);
   CUtensorMap mx, mh, ml;
   if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, w_hi, N, K, ld_w, BN) || make_map(&ml, w_lo, N, K, ld_w, BN))
     return 2;
@@ -511,8 +461,10 @@ extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_
   p.slab_rows = ((M + slabs - 1) / slabs + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
   const int used = (int)((M + p.slab_rows - 1) / p.slab_rows);           // slabs that hold rows (<= slabs)
   const size_t smem = (size_t)WG_STAGES * WG_STAGE + 256;
+#ifndef TZK_CPU_SHIM
   cudaFuncSetAttribute(wgrad3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  wgrad3x_kernel<<<used * p.k_tiles, NUM_THREADS, smem, st>>>(mx, mz, p);
-  wgrad_reduce_kernel<<<(K * 64 + 255) / 256, 256, 0, st>>>(partial, used, p.k_tiles * 128, K, dw, ld_dw);
+#endif
+  TZK_LAUNCH((wgrad3x_kernel), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
+  TZK_LAUNCH((wgrad_reduce_kernel), (K * 64 + 255) / 256, 256, 0, st, partial, used, p.k_tiles * 128, K, dw, ld_dw);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

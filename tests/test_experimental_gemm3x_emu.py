@@ -1,0 +1,95 @@
+"""The tcgen05 3xTF32 GEMM draft (scripts/experimental/tzk_gemm3x.cu) executed on the CPU from its actual source.
+
+`cuda_cpu_shim.h` runs the kernels with one std::thread per CUDA thread (192 per CTA: TMA producer, MMA issuer, four
+transform / epilogue warps) and `tcgen05_cpu_emu.h` stands in for the hardware: mbarriers with transaction counts,
+TMA box loads with SWIZZLE_128B and out-of-bounds zero fill, tcgen05.mma decoded from the instruction and
+shared-memory descriptors (K-major and MN-major canonical layouts, TF32 operand truncation), TMEM with the
+per-warp lane-ownership rule, tcgen05.ld.  What this proves: control flow, barrier protocol, descriptor arithmetic
+(k-step advance inside the swizzle atom, LBO / SBO), tile -> (row, column) mapping, K-tail and M-tail handling and the
+epilogues are consistent with those semantics and produce fp32-accurate results.  What it cannot prove: that the
+hardware agrees with the emulation (the descriptor FIELDS are checked against CuTe in test_experimental_umma_desc.py)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+EXP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "experimental")
+P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libtzk_gemm3x_cpu.so")
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-x", "c++",
+                    os.path.join(EXP, "tzk_gemm3x.cu"), "-shared", "-fPIC", "-o", out], check=True)
+    L = ctypes.CDLL(out)
+    L.tzk_gemm3x.argtypes = [P, I64, P, I64, P, I64, I32, I32, I32, P, I64, P, P, P]
+    L.tzk_wgrad3x.argtypes = [P, I64, P, I64, I64, I32, I32, P, P, I64, P]
+    L.tzk_wgrad3x_partial_floats.restype = I64
+    L.tzk_wgrad3x_partial_floats.argtypes = [I32, I32]
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+# error budget: the emulated tensor core adds ~2400 fp32 products one after another (a plain running sum), which costs
+# more than the split itself; numpy's blocked fp32 matmul sits at ~2e-6 on the same data
+TOL = 2e-5
+
+
+@pytest.mark.parametrize("M,relu,bias", [(200, 1, True), (1, 0, False), (128, 1, True)])
+def test_forward_784_to_64(lib, M, relu, bias):
+    """K = 784 = 24.5 chunks of 32 (zero-filled tail), rows past M zero-filled and not stored, bias + ReLU epilogue."""
+    rng = np.random.default_rng(M)
+    K, N = 784, 64
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32) if bias else None
+    y = np.full((M + 1, N), np.nan, np.float32)                  # one guard row
+    wh, wl = np.empty_like(w), np.empty_like(w)
+    assert lib.tzk_gemm3x(_p(x), K, _p(w), K, _p(b), M, N, K, relu, _p(y), N, _p(wh), _p(wl), None) == 0
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + (b if bias else 0.0)
+    ref = np.maximum(ref, 0) if relu else ref
+    np.testing.assert_allclose(y[:M], ref, rtol=0, atol=TOL)
+    assert np.isnan(y[M]).all()
+    # the split really is hi + lo with hi on the TF32 grid
+    assert (wh.view(np.uint32) & 0x1FFF == 0).all() and (wl.view(np.uint32) & 0x1FFF == 0).all()
+    np.testing.assert_allclose(wh.astype(np.float64) + wl, w, rtol=2 ** -21)
+    # plain TF32 (hi x hi only) would be ~1000x worse: the lo terms are doing their job
+    tf = lambda a: (a.view(np.uint32) & 0xFFFFE000).view(np.float32)
+    plain = np.abs(tf(x).astype(np.float64) @ tf(w).astype(np.float64).T + (b if bias else 0.0) -
+                   (x.astype(np.float64) @ w.astype(np.float64).T + (b if bias else 0.0))).max()
+    assert plain > 20 * TOL or M == 1
+
+
+def test_dgrad_64_to_784(lib):
+    """The input-gradient pass: BN = 112, seven column tiles per row tile, two k-chunks, three stages."""
+    rng = np.random.default_rng(1)
+    M, K, N = 130, 64, 784
+    dz = rng.standard_normal((M, K)).astype(np.float32)
+    wt = (rng.standard_normal((N, K)) / 8).astype(np.float32)     # W^T [784, 64]
+    dx = np.full((M, N), np.nan, np.float32)
+    wh, wl = np.empty_like(wt), np.empty_like(wt)
+    assert lib.tzk_gemm3x(_p(dz), K, _p(wt), K, None, M, N, K, 0, _p(dx), N, _p(wh), _p(wl), None) == 0
+    np.testing.assert_allclose(dx, dz.astype(np.float64) @ wt.astype(np.float64).T, rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("M,slabs", [(200, 2), (70, 3), (31, 1)])
+def test_wgrad_mn_major(lib, M, slabs):
+    """dW = dZ^T X with both operands MN-major straight from the row-major tensors; row slabs (the last one short or
+    empty), 7 column tiles (the last one 16 of 128 columns), fixed-order slab reduction + transpose."""
+    rng = np.random.default_rng(M + slabs)
+    K = 784
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    dz = (rng.standard_normal((M, 64)) / np.sqrt(M)).astype(np.float32)
+    dw = np.full((64, K), np.nan, np.float32)
+    part = np.zeros(lib.tzk_wgrad3x_partial_floats(K, slabs), np.float32)
+    assert lib.tzk_wgrad3x(_p(x), K, _p(dz), 64, M, K, slabs, _p(part), _p(dw), K, None) == 0
+    np.testing.assert_allclose(dw, dz.astype(np.float64).T @ x.astype(np.float64), rtol=0, atol=TOL)
+    dw2 = np.empty_like(dw)
+    assert lib.tzk_wgrad3x(_p(x), K, _p(dz), 64, M, K, slabs, _p(part), _p(dw2), K, None) == 0
+    np.testing.assert_array_equal(dw, dw2)
