@@ -65,6 +65,19 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print(f"{e0.elapsed_time(e1) / 10 * 1e3:.1f} us per call (incl. the W split and three tensor-map encodes)")
+    if os.environ.get("TZK_GEMM3X_STACK") != "1":      # second variant: two MMAs per k-step (stacked W_hi / W_lo)
+        os.environ["TZK_GEMM3X_STACK"] = "1"
+        run()
+        torch.cuda.synchronize()
+        err2 = (y.double() - ref).abs().max().item()
+        for _ in range(3):
+            run()
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"stacked-B variant: max abs err {err2:.3e}, {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per call")
 
 
 def wgrad(lib, M, K=784, slabs=21):

@@ -19,6 +19,7 @@
 // Build + try (next round, on a B200):  python scripts/experimental/try_gemm3x.py
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "tzk_umma_desc.h"
 #ifdef TZK_CPU_SHIM
@@ -49,6 +50,7 @@ struct Cfg {
   static constexpr int W_PAD = (W_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_PAD;
   static constexpr int TMEM_COLS = BN <= 64 ? 128 : 256;   // two accumulators, power of two
+  static constexpr int TMEM_COLS_STACKED = BN <= 64 ? 256 : 512;   // STACK: each accumulator is 2 * BN columns wide
   static constexpr int STAGES = BN <= 64 ? 4 : 3;          // 4 x 48 KB / 3 x 60 KB of shared memory
 };
 
@@ -62,12 +64,18 @@ struct Params {
   int relu;
 };
 
-template <int BN>
+// STACK: W_hi and W_lo lie back to back in shared memory (whole 8-row groups), so hi(x) * [W_hi ; W_lo] is ONE MMA with
+// N = 2 * BN (columns [0, BN) collect hi*hi, columns [BN, 2 BN) hi*lo) and lo(x) * W_hi a second one with N = BN into
+// the first half; the epilogue adds the halves.  Two MMAs and 14 KB of operand reads per k-step instead of three and
+// 18 KB — at N = 64 the MMA is bound by operand reads, not flops.
+template <int BN, bool STACK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
               const __grid_constant__ CUtensorMap map_wlo, Params p) {
   constexpr int W_BYTES = Cfg<BN>::W_BYTES, W_PAD = Cfg<BN>::W_PAD, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
-  constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS, STAGES = Cfg<BN>::STAGES;
+  constexpr int TMEM_COLS = STACK ? Cfg<BN>::TMEM_COLS_STACKED : Cfg<BN>::TMEM_COLS, STAGES = Cfg<BN>::STAGES;
+  constexpr int ACC_COLS = STACK ? 2 * BN : BN;            // TMEM columns per accumulator
+  static_assert(!STACK || W_PAD == W_BYTES, "stacked B needs W_hi and W_lo contiguous");
   TZK_DYN_SMEM(uint8_t, smem);
   uint8_t* stage_base = smem;                                        // STAGES x 48 KB, each buffer 1024-B aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -125,10 +133,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr uint32_t idesc = make_idesc<BN>();
+    constexpr uint32_t idesc2 = make_idesc<2 * BN>();    // STACK only
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       mbar_wait(acc_empty + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(ready + stage, phase);              // hi / lo of this chunk are in shared memory
         tc_fence_after();
@@ -139,9 +148,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           for (int k = 0; k < BK / UK; ++k) {
             const uint32_t ko = k * UK * 4;           // 32 B per k-step inside the 128-B swizzled row
             const uint32_t first = (kb | k) ? 1u : 0u;
-            mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
-            mma_tf32(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1u);
-            mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+            if (STACK) {
+              mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc2, first);   // B = [W_hi ; W_lo]
+              mma_tf32(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1u);
+            } else {
+              mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+              mma_tf32(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1u);
+              mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+            }
           }
           tc_commit(empty + stage);                    // shared-memory slot is free once these MMAs retire
           if (kb == num_k - 1) tc_commit(acc_full + acc);
@@ -186,11 +200,17 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       tc_fence_after();
       const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
       const int col0 = (int)(t % n_tiles) * BN;
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       float v[16];
 #pragma unroll
       for (int part = 0; part < BN / 16; ++part) {
         tmem_ld16(taddr + part * 16, v);
+        if (STACK) {
+          float v2[16];
+          tmem_ld16(taddr + BN + part * 16, v2);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] += v2[c];
+        }
         if (row < p.M) {
           float* yr = p.y + row * p.ld_y + col0 + part * 16;
 #pragma unroll
@@ -407,18 +427,18 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 }
 }  // namespace
 
-template <int BN>
+template <int BN, bool STACK>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(gemm3x_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  TZK_LAUNCH((gemm3x_kernel<BN>), grid, NUM_THREADS, smem, st, mx, mh, ml, p);
+  TZK_LAUNCH((gemm3x_kernel<BN, STACK>), grid, NUM_THREADS, smem, st, mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -440,7 +460,9 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
     return 2;
   Params p;
   p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.N = N; p.relu = relu;
-  return BN == 64 ? launch<64>(mx, mh, ml, p, st) : launch<112>(mx, mh, ml, p, st);
+  const char* e = getenv("TZK_GEMM3X_STACK");     // 1: two MMAs per k-step (see gemm3x_kernel); default: three
+  if (e && e[0] == '1') return BN == 64 ? launch<64, true>(mx, mh, ml, p, st) : launch<112, true>(mx, mh, ml, p, st);
+  return BN == 64 ? launch<64, false>(mx, mh, ml, p, st) : launch<112, false>(mx, mh, ml, p, st);
 }
 
 // dw[64, K] = dz[M, 64]^T @ x[M, K]  (3xTF32; fixed-order reduction over `slabs` row slabs -> run-to-run deterministic).

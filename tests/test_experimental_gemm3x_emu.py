@@ -41,8 +41,15 @@ def _p(a):
 TOL = 2e-5
 
 
+@pytest.fixture(params=["0", "1"], ids=["3mma", "stacked"])
+def stack(request, monkeypatch):
+    """TZK_GEMM3X_STACK=1: hi(x) * [W_hi ; W_lo] as one N = 2*BN MMA + lo(x) * W_hi, halves added in the epilogue."""
+    monkeypatch.setenv("TZK_GEMM3X_STACK", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("M,relu,bias", [(200, 1, True), (1, 0, False), (128, 1, True)])
-def test_forward_784_to_64(lib, M, relu, bias):
+def test_forward_784_to_64(lib, stack, M, relu, bias):
     """K = 784 = 24.5 chunks of 32 (zero-filled tail), rows past M zero-filled and not stored, bias + ReLU epilogue."""
     rng = np.random.default_rng(M)
     K, N = 784, 64
@@ -66,7 +73,7 @@ def test_forward_784_to_64(lib, M, relu, bias):
     assert plain > 20 * TOL or M == 1
 
 
-def test_dgrad_64_to_784(lib):
+def test_dgrad_64_to_784(lib, stack):
     """The input-gradient pass: BN = 112, seven column tiles per row tile, two k-chunks, three stages."""
     rng = np.random.default_rng(1)
     M, K, N = 130, 64, 784
