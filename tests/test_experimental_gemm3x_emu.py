@@ -100,3 +100,41 @@ def test_wgrad_mn_major(lib, M, slabs):
     dw2 = np.empty_like(dw)
     assert lib.tzk_wgrad3x(_p(x), K, _p(dz), 64, M, K, slabs, _p(part), _p(dw2), K, None) == 0
     np.testing.assert_array_equal(dw, dw2)
+
+
+def test_autograd_wiring_of_the_wide_layer(lib, monkeypatch):
+    """scripts/experimental/gemm3x_linear.py (the drop-in for dense_gemm._LinearFn on DLRM's 783 -> 64 layer) on CPU
+    tensors through the emulated kernels: forward, input gradient, weight gradient (column-mapped 783 -> 784 input)
+    and bias gradient against torch autograd."""
+    import sys
+
+    import torch
+
+    sys.path.insert(0, EXP)
+    import gemm3x_linear as G
+
+    G.declare(lib)
+    monkeypatch.setattr(G, "SLABS", 2)
+    torch.manual_seed(0)
+    M, K, Kx, N = 150, 783, 784, 64
+    in_map = ((0, 0, 16), (16, 17, 767))          # dense block, one zero column, the pair block (as DLRM lays it out)
+    xs = torch.randn(M, K)
+    x = torch.zeros(M, Kx)
+    for src, dst, n in in_map:
+        x[:, dst:dst + n] = xs[:, src:src + n]
+    x.requires_grad_(True)
+    xr = xs.clone().requires_grad_(True)
+    w = (torch.randn(N, K) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, requires_grad=True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    y = G.Gemm3xLinearFn.apply(lib, x, w, b, True, in_map)
+    ref = torch.relu(torch.nn.functional.linear(xr.double(), wr.double(), br.double()))
+    g = torch.randn(M, N)
+    y.backward(g)
+    ref.backward(g.double())
+    np.testing.assert_allclose(y.detach().numpy(), ref.detach().numpy(), atol=TOL)
+    np.testing.assert_allclose(b.grad.numpy(), br.grad.numpy(), atol=1e-4)
+    np.testing.assert_allclose(w.grad.numpy(), wr.grad.numpy(), atol=1e-4)
+    dx = torch.cat([x.grad[:, dst:dst + n] for _, dst, n in in_map], dim=1)
+    np.testing.assert_allclose(dx.numpy(), xr.grad.numpy(), atol=TOL)
+    assert float(x.grad[:, 16].abs().max()) == 0.0       # the padding column's weight is zero -> zero gradient
