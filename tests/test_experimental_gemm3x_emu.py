@@ -41,12 +41,14 @@ def _p(a):
 TOL = 2e-5
 
 
-@pytest.fixture(params=[("0", "4"), ("1", "4"), ("0", "8"), ("1", "8")], ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8"])
+@pytest.fixture(params=[("0", "4", "0"), ("1", "4", "0"), ("0", "8", "0"), ("1", "8", "0"), ("0", "4", "1"), ("1", "8", "1")],
+                ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8", "3mma-raw", "stacked-tw8-raw"])
 def stack(request, monkeypatch):
     """TZK_GEMM3X_STACK=1: hi(x) * [W_hi ; W_lo] as one N = 2*BN MMA + lo(x) * W_hi, halves added in the epilogue.
     TZK_GEMM3X_TW=8: eight transform / epilogue warps (two per TMEM lane quarter) instead of four."""
     monkeypatch.setenv("TZK_GEMM3X_STACK", request.param[0])
     monkeypatch.setenv("TZK_GEMM3X_TW", request.param[1])
+    monkeypatch.setenv("TZK_GEMM3X_RAW", request.param[2])      # raw fp32 as hi (the tensor core truncates), lo only
     return request.param
 
 
@@ -65,9 +67,9 @@ def test_forward_784_to_64(lib, stack, M, relu, bias):
     ref = np.maximum(ref, 0) if relu else ref
     np.testing.assert_allclose(y[:M], ref, rtol=0, atol=TOL)
     assert np.isnan(y[M]).all()
-    # the split really is hi + lo with hi on the TF32 grid
-    assert (wh.view(np.uint32) & 0x1FFF == 0).all() and (wl.view(np.uint32) & 0x1FFF == 0).all()
-    np.testing.assert_allclose(wh.astype(np.float64) + wl, w, rtol=2 ** -21)
+    if stack[2] == "0":     # the split really is hi + lo with hi on the TF32 grid (raw mode writes lo only)
+        assert (wh.view(np.uint32) & 0x1FFF == 0).all() and (wl.view(np.uint32) & 0x1FFF == 0).all()
+        np.testing.assert_allclose(wh.astype(np.float64) + wl, w, rtol=2 ** -21)
     # plain TF32 (hi x hi only) would be ~1000x worse: the lo terms are doing their job
     tf = lambda a: (a.view(np.uint32) & 0xFFFFE000).view(np.float32)
     plain = np.abs(tf(x).astype(np.float64) @ tf(w).astype(np.float64).T + (b if bias else 0.0) -
