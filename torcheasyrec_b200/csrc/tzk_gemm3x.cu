@@ -153,12 +153,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     constexpr uint32_t idesc = make_idesc<BN>();
     constexpr uint32_t idesc2 = make_idesc<2 * BN>();    // STACK only
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait(acc_empty + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+      mbar_wait_all(acc_empty + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       uint32_t started = 0;                           // bit p: partial p holds data of this tile (bit P: the small terms)
       for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(ready + stage, phase);              // hi / lo of this chunk are in shared memory
+        mbar_wait_all(ready + stage, phase);              // hi / lo of this chunk are in shared memory
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sb = smem_u32(stage_base + stage * STAGE_BYTES);
@@ -199,7 +199,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(full + stage, phase);
+        mbar_wait_all(full + stage, phase);
         float4* hi = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES + X_BYTES);
         // 1024 float4 per X chunk over the TW * 32 transform threads; element-wise, so the swizzle is irrelevant
@@ -223,7 +223,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       // ---- epilogue of this tile ---------------------------------------------------------------------------
-      mbar_wait(acc_full + acc, acc_phase);
+      mbar_wait_all(acc_full + acc, acc_phase);
       tc_fence_after();
       const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
       const int col0 = (int)(t % n_tiles) * BN;
@@ -359,7 +359,7 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     constexpr uint32_t idesc = make_idesc<64, true>();
     uint32_t started = 0;
     for (int c = 0; c < num_c; ++c) {
-      mbar_wait(ready + stage, phase);
+      mbar_wait_all(ready + stage, phase);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sb = smem_u32(smem + stage * WG_STAGE);
@@ -387,7 +387,7 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int c = 0; c < num_c; ++c) {
-      mbar_wait(full + stage, phase);
+      mbar_wait_all(full + stage, phase);
       uint8_t* sb = smem + stage * WG_STAGE;
       // A: 1024 float4 (hi at +0, lo at +WG_A); B: 512 float4 (hi at +2*WG_A, lo at +2*WG_A+WG_B); element-wise.
 #pragma unroll
@@ -408,7 +408,7 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
     // epilogue: TMEM lane = X column inside the tile, TMEM column = n
-    mbar_wait(acc_full, 0);
+    mbar_wait_all(acc_full, 0);
     tc_fence_after();
     const int krow = jt * 128 + quarter * 32 + lane;
     float* out = p.partial + ((int64_t)slab * p.k_tiles * 128 + krow) * 64;
