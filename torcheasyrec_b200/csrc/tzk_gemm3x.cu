@@ -83,8 +83,11 @@ struct Params {
 // bits, so the hardware multiplies trunc(x) — and only lo = rna(x - trunc(x)) is computed and stored (one shared-memory
 // write stream and one conversion per element less).  If the hardware rounded instead of truncating, the error would
 // jump to ~1e-3: the accuracy tests decide.
-template <int BN, bool STACK, int TW, bool RAW>
-__global__ void __launch_bounds__(64 + 32 * TW, 1)
+// SPLIT (TZK_GEMM3X_SPLIT=1): four dedicated epilogue warps after the TW transform warps, so that draining tile i (TMEM ->
+// registers -> global, the dominant cost of the input-gradient pass) overlaps the transform + MMA work of tile i+1 —
+// which is what the two accumulator sets are for; without it the same warps do both, one after the other.
+template <int BN, bool STACK, int TW, bool RAW, bool SPLIT>
+__global__ void __launch_bounds__(64 + 32 * TW + (SPLIT ? 128 : 0), 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
               const __grid_constant__ CUtensorMap map_wlo, Params p) {
   constexpr int W_BYTES = Cfg<BN>::W_BYTES, W_PAD = Cfg<BN>::W_PAD, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
@@ -117,7 +120,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full + a, 1);
-      mbar_init(acc_empty + a, TW);
+      mbar_init(acc_empty + a, SPLIT ? 4 : TW);
     }
     fence_mbarrier_init();
   }
@@ -190,15 +193,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ===== transform + epilogue warps (2..5) =====================================================================
-    const int tw = warp - 2;                 // 0..TW-1
+    // ===== transform warps (2 .. 2+TW-1) and epilogue warps (the same ones, or with SPLIT the four after them) ==========
+    const int tw = warp - 2;                 // 0..TW-1 transform; TW..TW+3 epilogue-only (SPLIT)
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const bool do_transform = !SPLIT || tw < TW;
+    const bool do_epilogue = !SPLIT || tw >= TW;
+    const int part0 = SPLIT ? 0 : tw / 4, part_step = SPLIT ? 1 : TW / 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int kb = 0; kb < num_k; ++kb) {
+      for (int kb = 0; do_transform && kb < num_k; ++kb) {
         mbar_wait_all(full + stage, phase);
         float4* hi = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES + X_BYTES);
@@ -223,6 +229,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       // ---- epilogue of this tile ---------------------------------------------------------------------------
+      if (!do_epilogue) continue;
       mbar_wait_all(acc_full + acc, acc_phase);
       tc_fence_after();
       const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
@@ -230,7 +237,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       float v[16];
 #pragma unroll
-      for (int part = tw / 4; part < BN / 16; part += TW / 4) {   // TW = 8: the two warps of a lane quarter alternate
+      for (int part = part0; part < BN / 16; part += part_step) {   // TW = 8 without SPLIT: the two warps of a lane quarter alternate
         // small terms first, then the partials (fp32 round-to-nearest adds)
         float v2[16];
         if (STACK) {
@@ -493,18 +500,18 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 }
 }  // namespace
 
-template <int BN, bool STACK, int TW, bool RAW>
+template <int BN, bool STACK, int TW, bool RAW, bool SPLIT>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW>), grid, 64 + 32 * TW, smem, st, mx, mh, ml, p);
+  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW, SPLIT>), grid, 64 + 32 * TW + (SPLIT ? 128 : 0), smem, st, mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -532,11 +539,15 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   const char* e = getenv("TZK_GEMM3X_STACK");     // 1: two MMAs per k-step (see gemm3x_kernel); default: three
   const char* t = getenv("TZK_GEMM3X_TW");        // 8: eight transform / epilogue warps; default: four
   const bool stack = e && e[0] == '1', tw8 = t && t[0] == '8';
-#define TZK_G3R(BN_, S_, T_) (raw ? launch<BN_, S_, T_, true>(mx, mh, ml, p, st) : launch<BN_, S_, T_, false>(mx, mh, ml, p, st))
+  const char* sp = getenv("TZK_GEMM3X_SPLIT");    // 1: dedicated epilogue warps (see gemm3x_kernel); default: shared
+  const bool split = sp && sp[0] == '1';
+#define TZK_G3S(BN_, S_, T_, R_) (split ? launch<BN_, S_, T_, R_, true>(mx, mh, ml, p, st) : launch<BN_, S_, T_, R_, false>(mx, mh, ml, p, st))
+#define TZK_G3R(BN_, S_, T_) (raw ? TZK_G3S(BN_, S_, T_, true) : TZK_G3S(BN_, S_, T_, false))
 #define TZK_G3(BN_) (stack ? (tw8 ? TZK_G3R(BN_, true, 8) : TZK_G3R(BN_, true, 4)) \
                            : (tw8 ? TZK_G3R(BN_, false, 8) : TZK_G3R(BN_, false, 4)))
   return BN == 64 ? TZK_G3(64) : TZK_G3(112);
 #undef TZK_G3R
+#undef TZK_G3S
 #undef TZK_G3
 }
 
