@@ -41,10 +41,11 @@ def gemm(L, M, K, N, relu, bias, tag):
     ref = torch.relu(ref) if relu else ref
     f32 = torch.nn.functional.linear(x, w, b)
     f32 = ((torch.relu(f32) if relu else f32).double() - ref).abs().max().item()
-    for stack, tw, raw, split in (("0", "4", "0", "0"), ("1", "4", "0", "0"), ("1", "8", "0", "0"), ("1", "4", "1", "0"),
-                                  ("1", "4", "0", "1"), ("1", "8", "0", "1"), ("1", "8", "1", "1")):
-        for var, val in zip(("TZK_GEMM3X_STACK", "TZK_GEMM3X_TW", "TZK_GEMM3X_RAW", "TZK_GEMM3X_SPLIT"),
-                            (stack, tw, raw, split)):
+    for stack, tw, raw, split, pf in (("0", "4", "0", "0", "0"), ("1", "4", "0", "0", "0"), ("1", "8", "0", "0", "0"),
+                                      ("1", "4", "1", "0", "0"), ("1", "4", "0", "1", "0"), ("1", "4", "0", "0", "1"),
+                                      ("1", "4", "1", "1", "1"), ("1", "8", "1", "1", "1")):
+        for var, val in zip(("TZK_GEMM3X_STACK", "TZK_GEMM3X_TW", "TZK_GEMM3X_RAW", "TZK_GEMM3X_SPLIT",
+                             "TZK_GEMM3X_PREFETCH"), (stack, tw, raw, split, pf)):
             os.environ[var] = val
 
         def run():
@@ -56,7 +57,7 @@ def gemm(L, M, K, N, relu, bias, tag):
         run()
         torch.cuda.synchronize()
         err = (y.double() - ref).abs().max().item()
-        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}{' raw' if raw == '1' else ''}{' split' if split == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), "
+        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}{' raw' if raw == '1' else ''}{' split' if split == '1' else ''}{' pf' if pf == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), "
               f"{timed(run):.1f} us", flush=True)
 
 

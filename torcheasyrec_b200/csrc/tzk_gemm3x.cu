@@ -86,7 +86,12 @@ struct Params {
 // SPLIT (TZK_GEMM3X_SPLIT=1): four dedicated epilogue warps after the TW transform warps, so that draining tile i (TMEM ->
 // registers -> global, the dominant cost of the input-gradient pass) overlaps the transform + MMA work of tile i+1 —
 // which is what the two accumulator sets are for; without it the same warps do both, one after the other.
-template <int BN, bool STACK, int TW, bool RAW, bool SPLIT>
+// PF (TZK_GEMM3X_PREFETCH=1): the producer asks L2 for the X boxes PF_DIST chunks ahead (cp.async.bulk.prefetch.tensor).
+// The first hardware numbers (same ~0.9 us per 16-KB chunk in the forward and the weight-gradient pass, 2.6 TB/s) are
+// what four 16-KB stages in flight per SM give at an HBM -> shared-memory latency of ~3.7 us (Little's law); shared
+// memory for deeper stages is gone, the 126 MB L2 is not.
+constexpr int PF_DIST = 12;
+template <int BN, bool STACK, int TW, bool RAW, bool SPLIT, bool PF>
 __global__ void __launch_bounds__(64 + 32 * TW + (SPLIT ? 128 : 0), 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
               const __grid_constant__ CUtensorMap map_wlo, Params p) {
@@ -135,16 +140,33 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(empty + stage, phase ^ 1);
-          uint8_t* sb = stage_base + stage * STAGE_BYTES;
-          mbar_expect_tx(full + stage, X_BYTES + 2 * W_BYTES);   // W_BYTES, not W_PAD: the box is BN rows
-          tma_load_2d(sb, &map_x, full + stage, kb * BK, (int)(t / n_tiles * BM));
-          tma_load_2d(sb + 2 * X_BYTES, &map_whi, full + stage, kb * BK, (int)(t % n_tiles) * BN);
-          tma_load_2d(sb + 2 * X_BYTES + W_PAD, &map_wlo, full + stage, kb * BK, (int)(t % n_tiles) * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+      auto load_chunk = [&](int64_t t, int kb) {
+        mbar_wait(empty + stage, phase ^ 1);
+        uint8_t* sb = stage_base + stage * STAGE_BYTES;
+        mbar_expect_tx(full + stage, X_BYTES + 2 * W_BYTES);   // W_BYTES, not W_PAD: the box is BN rows
+        tma_load_2d(sb, &map_x, full + stage, kb * BK, (int)(t / n_tiles * BM));
+        tma_load_2d(sb + 2 * X_BYTES, &map_whi, full + stage, kb * BK, (int)(t % n_tiles) * BN);
+        tma_load_2d(sb + 2 * X_BYTES + W_PAD, &map_wlo, full + stage, kb * BK, (int)(t % n_tiles) * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      if constexpr (PF) {
+        int64_t pt = blockIdx.x;                // prefetch cursor: (tile, k-block) PF_DIST chunks ahead of the loads
+        int pkb = 0;
+        auto prefetch_next = [&] {
+          if (pt < num_tiles) {
+            tma_prefetch_2d(&map_x, pkb * BK, (int)(pt / n_tiles * BM));
+            if (++pkb == num_k) { pkb = 0; pt += gridDim.x; }
+          }
+        };
+        for (int i = 0; i < PF_DIST; ++i) prefetch_next();
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
+          for (int kb = 0; kb < num_k; ++kb) {
+            prefetch_next();
+            load_chunk(t, kb);
+          }
+      } else {
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
+          for (int kb = 0; kb < num_k; ++kb) load_chunk(t, kb);
       }
     }
   } else if (warp == 1) {
@@ -500,18 +522,18 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 }
 }  // namespace
 
-template <int BN, bool STACK, int TW, bool RAW, bool SPLIT>
+template <int BN, bool STACK, int TW, bool RAW, bool SPLIT, bool PF>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW, SPLIT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW, SPLIT>), grid, 64 + 32 * TW + (SPLIT ? 128 : 0), smem, st, mx, mh, ml, p);
+  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW, SPLIT, PF>), grid, 64 + 32 * TW + (SPLIT ? 128 : 0), smem, st, mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -541,13 +563,18 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   const bool stack = e && e[0] == '1', tw8 = t && t[0] == '8';
   const char* sp = getenv("TZK_GEMM3X_SPLIT");    // 1: dedicated epilogue warps (see gemm3x_kernel); default: shared
   const bool split = sp && sp[0] == '1';
-#define TZK_G3S(BN_, S_, T_, R_) (split ? launch<BN_, S_, T_, R_, true>(mx, mh, ml, p, st) : launch<BN_, S_, T_, R_, false>(mx, mh, ml, p, st))
+  const char* pfe = getenv("TZK_GEMM3X_PREFETCH");   // 1: L2 prefetch of the X boxes ahead of the loads (stacked variant only)
+  const bool pf = pfe && pfe[0] == '1' && stack;
+#define TZK_G3P(BN_, S_, T_, R_, SP_) ((S_ && pf) ? launch<BN_, S_, T_, R_, SP_, S_>(mx, mh, ml, p, st) \
+                                                 : launch<BN_, S_, T_, R_, SP_, false>(mx, mh, ml, p, st))
+#define TZK_G3S(BN_, S_, T_, R_) (split ? TZK_G3P(BN_, S_, T_, R_, true) : TZK_G3P(BN_, S_, T_, R_, false))
 #define TZK_G3R(BN_, S_, T_) (raw ? TZK_G3S(BN_, S_, T_, true) : TZK_G3S(BN_, S_, T_, false))
 #define TZK_G3(BN_) (stack ? (tw8 ? TZK_G3R(BN_, true, 8) : TZK_G3R(BN_, true, 4)) \
                            : (tw8 ? TZK_G3R(BN_, false, 8) : TZK_G3R(BN_, false, 4)))
   return BN == 64 ? TZK_G3(64) : TZK_G3(112);
 #undef TZK_G3R
 #undef TZK_G3S
+#undef TZK_G3P
 #undef TZK_G3
 }
 
