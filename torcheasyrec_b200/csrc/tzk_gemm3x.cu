@@ -333,6 +333,7 @@ struct WgParams {
   int k_tiles;         // ceil(K / 128)
 };
 
+template <bool PF>      // PF: L2 prefetch of the X / dZ boxes PF_DIST chunks ahead (TZK_GEMM3X_PREFETCH=1), see gemm3x_kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, WgParams p) {
   TZK_DYN_SMEM(uint8_t, smem);
@@ -370,7 +371,21 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (PF) {
+        for (int c = 0; c < PF_DIST && c < num_c; ++c) {
+          const int r = (int)(row0 + (int64_t)c * WG_ROWS);
+          for (int b = 0; b < 4; ++b) tma_prefetch_2d(&map_x, jt * 128 + b * 32, r);
+          for (int b = 0; b < 2; ++b) tma_prefetch_2d(&map_dz, b * 32, r);
+        }
+      }
       for (int c = 0; c < num_c; ++c) {
+        if constexpr (PF) {
+          if (c + PF_DIST < num_c) {
+            const int r = (int)(row0 + (int64_t)(c + PF_DIST) * WG_ROWS);
+            for (int b = 0; b < 4; ++b) tma_prefetch_2d(&map_x, jt * 128 + b * 32, r);
+            for (int b = 0; b < 2; ++b) tma_prefetch_2d(&map_dz, b * 32, r);
+          }
+        }
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sb = smem + stage * WG_STAGE;
         mbar_expect_tx(full + stage, WG_A + WG_B);
@@ -597,9 +612,12 @@ extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_
   const int used = (int)((M + p.slab_rows - 1) / p.slab_rows);           // slabs that hold rows (<= slabs)
   const size_t smem = (size_t)WG_STAGES * WG_STAGE + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(wgrad3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(wgrad3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(wgrad3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  TZK_LAUNCH((wgrad3x_kernel), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
+  const char* pfe = getenv("TZK_GEMM3X_PREFETCH");
+  if (pfe && pfe[0] == '1') TZK_LAUNCH((wgrad3x_kernel<true>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
+  else TZK_LAUNCH((wgrad3x_kernel<false>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
   TZK_LAUNCH((wgrad_reduce_kernel), (K * 64 + 255) / 256, 256, 0, st, partial, used, p.k_tiles * 128, K, dw, ld_dw);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
