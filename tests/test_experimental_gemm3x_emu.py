@@ -114,7 +114,8 @@ def test_autograd_wiring_of_the_wide_layer(lib, monkeypatch):
     import gemm3x_linear as G
 
     G.declare(lib)
-    monkeypatch.setattr(G, "SLABS", 2)
+    import torcheasyrec_b200.dense_gemm as DG
+    monkeypatch.setattr(DG, "SLABS", 2)
     torch.manual_seed(0)
     M, K, Kx, N = 150, 783, 784, 64
     in_map = ((0, 0, 16), (16, 17, 767))          # dense block, one zero column, the pair block (as DLRM lays it out)

@@ -570,3 +570,39 @@ def test_gradient_clipping_on_classic_optimizers(kernels, bwd_path):
     got = split_arena(arena.cpu().numpy(), lay, tables, feat_table)
     for t in range(2):
         np.testing.assert_allclose(got[t], want[t], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("stack", ["0", "1"])
+@pytest.mark.parametrize("M", [300, 65536 + 5])
+def test_wide_layer_on_tcgen05_matches_fp64(monkeypatch, M, stack):
+    """TZK_GEMM3X=1: the 783 -> 64 tower layer (input travelling as [B, 784] with a zero column) on the hand-written
+    3xTF32 kernels — forward with fused bias + ReLU, dgrad, wgrad — against float64 autograd; fp32-level tolerance
+    (the library path it replaces, cuBLASLt BF16x9, meets the same bound)."""
+    from torcheasyrec_b200 import dense_gemm as G
+
+    if G._gemm3x_lib() is None:
+        pytest.fail("libtzk_gemm3x.so missing: build() did not produce it")
+    monkeypatch.setenv("TZK_GEMM3X", "1")
+    monkeypatch.setenv("TZK_GEMM3X_STACK", stack)
+    torch.manual_seed(M)
+    K, Kx, N = 783, 784, 64
+    in_map = ((0, 0, 16), (16, 17, 767))
+    xs = torch.randn(M, K, device=DEV)
+    x = torch.zeros(M, Kx, device=DEV)
+    for src, dst, n in in_map:
+        x[:, dst:dst + n] = xs[:, src:src + n]
+    x.requires_grad_(True)
+    lin = torch.nn.Linear(K, N).to(DEV)
+    y = G.linear(x, lin.weight, lin.bias, relu=True, in_map=in_map)
+    g = torch.randn(M, N, device=DEV)
+    y.backward(g)
+    xr = xs.double().requires_grad_(True)
+    wr, br = lin.weight.detach().double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
+    ref = torch.relu(torch.nn.functional.linear(xr, wr, br))
+    ref.backward(g.double())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), ref.detach().cpu().numpy(), atol=2e-5)
+    dx = torch.cat([x.grad[:, dst:dst + n] for _, dst, n in in_map], dim=1)
+    np.testing.assert_allclose(dx.cpu().numpy(), xr.grad.cpu().numpy(), atol=2e-5)
+    scale = float(M) ** 0.5
+    np.testing.assert_allclose(lin.weight.grad.cpu().numpy(), wr.grad.cpu().numpy(), atol=2e-5 * scale)
+    np.testing.assert_allclose(lin.bias.grad.cpu().numpy(), br.grad.cpu().numpy(), atol=2e-5 * scale)

@@ -53,7 +53,18 @@ def build(verbose: bool = False, force: bool = False) -> str:
         cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs]
         subprocess.run(cmd, check=True)
     build_gemm(force)
+    build_gemm3x(force)
     return LIB
+
+
+def build_gemm3x(force: bool = False) -> str:
+    """libtzk_gemm3x.so: hand-written tcgen05 3xTF32 GEMMs of the wide tower layer (forward, dgrad, wgrad)."""
+    src = os.path.join(HERE, "tzk_gemm3x.cu")
+    lib = os.path.join(HERE, "libtzk_gemm3x.so")
+    deps = [src] + [os.path.join(HERE, h) for h in ("tzk_umma_desc.h", "tzk_tcgen05_ptx.h")]
+    if force or _mtime(lib) < max(_mtime(d) for d in deps):
+        subprocess.run([NVCC, *FLAGS, "-shared", src, "-o", lib], check=True)
+    return lib
 
 
 def build_gemm(force: bool = False) -> str:

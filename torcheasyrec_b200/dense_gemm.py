@@ -157,6 +157,121 @@ class _SmallLinearFn(torch.autograd.Function):
         return dx, (dw if ctx.needs_input_grad[1] else None), db, None
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# The one wide layer (N = 64 outputs, input width a multiple of 112: DLRM's 783-wide final-MLP input travels as
+# [B, 784]) on hand-written tcgen05 3xTF32 kernels (csrc/tzk_gemm3x.cu -> libtzk_gemm3x.so): forward with bias + ReLU
+# in the epilogue, dgrad on W^T, wgrad with a fixed-order slab reduction.  TZK_GEMM3X=1 selects it.
+# --------------------------------------------------------------------------------------------------------------------
+_G3 = {"lib": None, "tried": False}
+
+
+def _gemm3x_lib():
+    if not _G3["tried"]:
+        _G3["tried"] = True
+        path = os.path.join(_HERE, "csrc", "libtzk_gemm3x.so")
+        if os.path.exists(path) and torch.cuda.is_available():
+            _G3["lib"] = _declare_gemm3x(ctypes.CDLL(path))
+    return _G3["lib"]
+
+
+SLABS = 21          # 7 column tiles x 21 row slabs = 147 CTAs
+
+
+def _declare_gemm3x(L):
+    P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.tzk_gemm3x.argtypes = [P, I64, P, I64, P, I64, I32, I32, I32, P, I64, P, P, P]
+    L.tzk_wgrad3x.argtypes = [P, I64, P, I64, I64, I32, I32, P, P, I64, P]
+    L.tzk_wgrad3x_partial_floats.restype = I64
+    L.tzk_wgrad3x_partial_floats.argtypes = [I32, I32]
+    return L
+
+
+def gemm3x_supported(M: int, N: int, Kx: int) -> bool:
+    return N == 64 and Kx % 112 == 0 and Kx % 4 == 0 and M >= 1
+
+
+def _g3_stream(t: torch.Tensor):
+    return torch.cuda.current_stream().cuda_stream if t.is_cuda else None
+
+
+def _g3_check(rc, what):
+    if rc:
+        raise RuntimeError(f"{what} failed with code {rc}")
+
+
+def gemm3x(lib, x, w, bias, relu):
+    """act(x [M, K] @ w [N, K]^T + bias) -> [M, N]; x rows may be strided (ld = x.stride(0))."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    w_hi, w_lo = torch.empty_like(w), torch.empty_like(w)
+    _g3_check(lib.tzk_gemm3x(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), None if bias is None else bias.data_ptr(),
+                          M, N, K, int(relu), y.data_ptr(), N, w_hi.data_ptr(), w_lo.data_ptr(), _g3_stream(x)), "tzk_gemm3x")
+    return y
+
+
+def wgrad3x(lib, x, dz, slabs=SLABS):
+    """dz [M, 64]^T @ x [M, K] -> [64, K]."""
+    M, K = x.shape
+    dw = torch.empty((64, K), dtype=torch.float32, device=x.device)
+    part = torch.empty(lib.tzk_wgrad3x_partial_floats(K, slabs), dtype=torch.float32, device=x.device)
+    _g3_check(lib.tzk_wgrad3x(x.data_ptr(), x.stride(0), dz.data_ptr(), dz.stride(0), M, K, slabs, part.data_ptr(),
+                           dw.data_ptr(), K, _g3_stream(x)), "tzk_wgrad3x")
+    return dw
+
+
+class Gemm3xLinearFn(torch.autograd.Function):
+    """Same contract as dense_gemm._LinearFn.apply(x, weight, bias, relu, in_map) with `lib` in front."""
+
+    @staticmethod
+    def forward(ctx, lib, x, weight, bias, relu, in_map):
+        K, Kx = weight.shape[1], x.shape[1]
+        w = weight.contiguous()
+        if Kx != K:      # zero-padded / column-mapped input: lay the weight out the same way
+            w = torch.zeros((weight.shape[0], Kx), dtype=weight.dtype, device=weight.device)
+            for (src, dst, n) in (in_map or ((0, 0, K),)):
+                w[:, dst:dst + n].copy_(weight[:, src:src + n])
+        if not gemm3x_supported(x.shape[0], w.shape[0], Kx):
+            raise ValueError(f"gemm3x covers N = 64 and input widths that are multiples of 112, got {tuple(w.shape)}")
+        y = gemm3x(lib, x, w, bias, relu)
+        ctx.lib, ctx.in_map, ctx.K = lib, in_map, K
+        ctx.has_bias, ctx.relu = bias is not None, relu
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        lib = ctx.lib
+        if dy.is_cuda and (ctx.has_bias or ctx.relu):
+            from .kernels import default_kernels
+
+            dz, colsum = default_kernels().act_bwd_colsum(dy.contiguous(), y, ctx.relu, want_dz=ctx.relu)
+            dz = dz if ctx.relu else dy.contiguous()
+            db = colsum if ctx.has_bias else None
+        else:
+            dz = (dy * (y > 0) if ctx.relu else dy).contiguous()
+            db = dz.sum(0) if ctx.has_bias else None
+        dx = dw = None
+        if ctx.needs_input_grad[1]:
+            dx = gemm3x(lib, dz, w.t().contiguous(), None, False)            # [M, 64] x [Kx, 64]^T
+        if ctx.needs_input_grad[2]:
+            dw = wgrad3x(lib, x, dz)
+            if w.shape[1] != ctx.K:
+                segs = ctx.in_map or ((0, 0, ctx.K),)
+                dw = torch.cat([dw[:, dst:dst + n] for (_, dst, n) in segs], dim=1) if len(segs) > 1 \
+                    else dw[:, :ctx.K].contiguous()
+        if not ctx.needs_input_grad[3]:
+            db = None
+        return None, dx, dw, db, None, None
+
+
+def _use_gemm3x(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (os.environ.get("TZK_GEMM3X", "0") == "1" and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+            and weight.dtype == torch.float32 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+            and gemm3x_supported(x.shape[0], weight.shape[0], x.shape[1]) and _gemm3x_lib() is not None)
+
+
 SMALL_MAX = 64      # tzk_small_linear_*: K, N <= 64
 
 
@@ -218,6 +333,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             x = x[:, :K] if in_map is None else torch.cat([x[:, d:d + n] for (_, d, n) in in_map], dim=1)
             in_map = None
     if _usable(x, weight):
+        if _use_gemm3x(x, weight):
+            return Gemm3xLinearFn.apply(_gemm3x_lib(), x, weight, bias, relu, in_map)
         return _LinearFn.apply(x, weight, bias, relu, in_map)
     y = torch.nn.functional.linear(x, weight, bias)
     return torch.relu(y) if relu else y
