@@ -5,7 +5,8 @@
 //   * instruction descriptors (kind::tf32, M = 128, N = 64 / 112, K-major and MN-major),
 //   * shared-memory descriptors (layout type, version, LBO, SBO) for one UMMA k-step of a K-major and an MN-major tile,
 //   * the byte offset of every element of those tiles under CuTe's canonical SWIZZLE_128B layouts vs. where the
-//     kernel's TMA boxes put it (box = 32 floats x rows, 128-B rows, 16-B chunk index XOR (row & 7)),
+//     kernel's TMA boxes put it (box = 32 floats x rows, 128-B rows; K-major: 16-B chunk index XOR (row & 7),
+//     MN-major 32-bit: SWIZZLE_128B_ATOM_32B, 32-B chunk index XOR (row & 3)),
 //   * the start offset of the second k-step.
 // Exit code = number of disagreements.  Build: nvcc -std=c++17 -I<cutlass/include> --expt-relaxed-constexpr.
 #include <cstdio>
@@ -57,22 +58,22 @@ int main() {
     auto s1 = local_tile(t, Shape<_128, _8>{}, make_coord(0, 1));
     expect("K-major  k-step 1 start offset (bytes)", (int)(&s1(0, 0) - &t(0, 0)) * 4, 8 * 4);
   }
-  {  // MN-major operand tile: logical (MN = 128, K = 32 batch rows) = 4 TMA boxes [32 floats x 32 rows], box b at b * 4096
-    auto layout = tile_to_shape(UMMA::Layout_MN_SW128_Atom<T>{}, Shape<_128, _32>{}, Step<_2, _1>{});
+  {  // MN-major operand tile: logical (MN = 128, K = 32 batch rows) = 4 TMA boxes [32 floats x 32 rows], box b at b * 4096,
+     // written with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; CuTe's only layout for 32-bit MN-major operands
+    auto layout = tile_to_shape(UMMA::Layout_MN_SW128_32B_Atom<T>{}, Shape<_128, _32>{}, Step<_2, _1>{});
     auto t = make_tensor(make_smem_ptr(reinterpret_cast<T*>(buf)), layout);
     uint64_t c = UMMA::make_umma_desc<UMMA::Major::MN>(local_tile(t, Shape<_128, _8>{}, make_coord(0, 0)));
-    uint64_t m = make_desc_mn(0, 4096, 1024);
-    expect("MN-major smem desc: layout type", lay(c), lay(m));
+    uint64_t m = make_desc_mn(0, 4096, 512);
+    expect("MN-major smem desc: layout type (BASE32B)", lay(c), lay(m));
     expect("MN-major smem desc: version", ver(c), ver(m));
     expect("MN-major smem desc: LBO >> 4", lbo(c), lbo(m));
-    printf("%-44s cute %8x  mine %8x  (one 8-row group per instruction: field unused)\n", "MN-major smem desc: SBO >> 4",
-           sbo(c), sbo(m));
+    expect("MN-major smem desc: SBO >> 4", sbo(c), sbo(m));
     int diff = 0;
     for (int mn = 0; mn < 128; ++mn)
       for (int k = 0; k < 32; ++k) {
         const int off = (int)(&t(mn, k) - &t(0, 0)) * 4;
         const int b = mn / 32, cb = (mn % 32) * 4;
-        const int tma = b * 4096 + k * 128 + (((cb >> 4) ^ (k & 7)) << 4) + (cb & 15);
+        const int tma = b * 4096 + k * 128 + (((cb >> 5) ^ (k & 3)) << 5) + (cb & 31);
         diff += off != tma;
       }
     expect("MN-major element offsets differing from TMA", 0, diff);

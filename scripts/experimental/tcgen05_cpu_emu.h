@@ -5,11 +5,13 @@
 //   mbarrier      arrival count + outstanding transaction bytes per phase; try_wait.parity(P) succeeds iff the
 //                 current parity != P.
 //   TMA 2-D load  box [32 floats x box_rows] from a row-major global tensor, out-of-bounds elements = 0, written to
-//                 shared memory as 128-B rows with SWIZZLE_128B (16-B chunk index ^= bits [7,10) of the shared address),
+//                 shared memory as 128-B rows with SWIZZLE_128B (16-B chunk index ^= bits [7,10) of the shared address)
+//                 or SWIZZLE_128B_ATOM_32B (32-B chunk index ^= bits [7,9)),
 //                 then complete_tx(box bytes) on the barrier.
 //   tcgen05.mma   kind::tf32, cta_group::1: decodes the instruction descriptor (M, N, operand majors) and both
-//                 shared-memory descriptors (start address, LBO, SBO, SWIZZLE_128B), reads A [M x 8] and B [N x 8]
-//                 through the canonical K-major / MN-major layouts, truncates the operands to TF32 (10 mantissa bits) and
+//                 shared-memory descriptors (start address, LBO, SBO, layout type), reads A [M x 8] and B [N x 8]
+//                 through the canonical layouts — K-major SWIZZLE_128B, MN-major SWIZZLE_128B_BASE32B (the only one
+//                 the hardware accepts for 32-bit MN-major operands; anything else aborts) — truncates the operands to TF32 (10 mantissa bits) and
 //                 accumulates D[m][n] (+)= sum_k a*b in fp32 into TMEM lane m, column base + n.  Executes synchronously,
 //                 so tcgen05.commit is a plain arrival.
 //   TMEM          128 lanes x 512 columns per CTA; tcgen05.ld 32x32b.x16: thread `lane` of the warp reads TMEM lane
@@ -30,6 +32,7 @@ struct CUtensorMap {            // host stand-in: what cuTensorMapEncodeTiled wa
   const float* base;
   int64_t rows, cols, ld;
   int box_rows;
+  bool atom32;                  // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B instead of SWIZZLE_128B
 };
 
 namespace tzk_emu {
@@ -47,6 +50,7 @@ inline void maybe_flip(Bar& b) {
   if (b.pending == 0 && b.tx == 0) { b.parity ^= 1; b.pending = b.count; }
 }
 inline uint32_t swz(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }   // SWIZZLE_128B on a shared-memory address
+inline uint32_t swz32(uint32_t a) { return a ^ (((a >> 7) & 3u) << 5); }  // SWIZZLE_128B_ATOM_32B / _BASE32B
 inline float tf32_trunc(float x) {
   uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; memcpy(&x, &u, 4); return x;
 }
@@ -99,7 +103,8 @@ inline void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0
     for (int c = 0; c < 32; ++c) {
       const int64_t gr = (int64_t)c1 + r, gc = (int64_t)c0 + c;
       const float v = (gr >= 0 && gr < map->rows && gc >= 0 && gc < map->cols) ? map->base[gr * map->ld + gc] : 0.f;
-      const uint32_t a = tzk_emu::swz(d0 + (uint32_t)r * 128u + (uint32_t)c * 4u);
+      const uint32_t lin = d0 + (uint32_t)r * 128u + (uint32_t)c * 4u;
+      const uint32_t a = map->atom32 ? tzk_emu::swz32(lin) : tzk_emu::swz(lin);
       memcpy(sm + a, &v, 4);
     }
   auto& ct = tzk_emu::cta();
@@ -131,14 +136,22 @@ inline void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t
   if (M != 128 || N < 16 || N > 256 || (N & 15)) tzk_emu::fail("unsupported UMMA shape for cta_group::1 (M = 128, N % 16 == 0)");
   const uint8_t* sm = tzk_emu::smem_base();
   auto elem = [&](uint64_t desc, bool mn_major, int r, int k) -> float {
-    if (((desc >> 61) & 7) != 2 || ((desc >> 46) & 3) != 1) tzk_emu::fail("smem descriptor: expected SWIZZLE_128B, version 1");
+    const uint32_t type = (uint32_t)((desc >> 61) & 7);
+    if (((desc >> 46) & 3) != 1) tzk_emu::fail("smem descriptor: version must be 1 on sm_100");
     const uint32_t start = (uint32_t)(desc & 0x3fff) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fff) << 4,
                    sbo = (uint32_t)((desc >> 32) & 0x3fff) << 4;
     uint32_t a;
-    if (!mn_major) a = start + (uint32_t)(r / 8) * sbo + (uint32_t)(r % 8) * 128u + (uint32_t)k * 4u;   // ((8,m),(T,2)):((8T,SBO),(1,T))
-    else a = start + (uint32_t)(r / 32) * lbo + (uint32_t)(k / 8) * sbo + (uint32_t)(k % 8) * 128u + (uint32_t)(r % 32) * 4u;
+    if (!mn_major) {     // K-major, SWIZZLE_128B: ((8,m),(T,2)):((8T,SBO),(1,T))
+      if (type != 2) tzk_emu::fail("K-major operand: expected layout type 2 (SWIZZLE_128B)");
+      a = tzk_emu::swz(start + (uint32_t)(r / 8) * sbo + (uint32_t)(r % 8) * 128u + (uint32_t)k * 4u);
+    } else {             // MN-major 32-bit elements: SWIZZLE_128B_BASE32B is the only layout the hardware takes
+      if (type != 1)
+        tzk_emu::fail("MN-major tf32 operand: layout type must be 1 (SWIZZLE_128B_BASE32B; CUTLASS sm100_smem_selector)");
+      a = tzk_emu::swz32(start + (uint32_t)(r / 32) * lbo + (uint32_t)(k / 4) * sbo + (uint32_t)(k % 4) * 128u +
+                         (uint32_t)(r % 32) * 4u);
+    }
     float v;
-    memcpy(&v, sm + tzk_emu::swz(a), 4);
+    memcpy(&v, sm + a, 4);
     return tzk_emu::tf32_trunc(v);
   };
   auto& ct = tzk_emu::cta();

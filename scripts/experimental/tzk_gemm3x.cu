@@ -242,7 +242,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 // ======================================================================================================================
 // Weight gradient of the same layer:  dW[n, k] = sum_m dZ[m, n] * X[m, k]   (n < 64, k < K = 784, m < M = batch).
 // The reduction runs over the batch, so both operands are MN-major as they lie in memory: A = X^T (UMMA M = 128 of
-// X's columns), B = dZ^T (UMMA N = 64).  Work item = (column tile j of 128, row slab s); each CTA owns one item, streams
+// X's columns), B = dZ^T (UMMA N = 64) — for 32-bit elements that means the SWIZZLE_128B_BASE32B shared-memory layout
+// (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; see tzk_umma_desc.h), 4-row k groups 512 B apart.  Work item = (column tile j of 128, row slab s); each CTA owns one item, streams
 // its slab in chunks of 32 rows (4 k-steps of 8), and writes a partial [128 x 64] block; wgrad_reduce_kernel adds the
 // slabs in a fixed order and transposes into dW[64, K].  X is read exactly once over all items (tiles read disjoint
 // columns); dZ is re-read by the 7 column tiles from L2.
@@ -322,9 +323,9 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int k = 0; k < WG_ROWS / UK; ++k) {
           const uint32_t ko = k * 1024;             // next group of 8 batch rows inside every box
           const uint32_t first = (c | k) ? 1u : 0u;
-          mma_tf32(tmem_base, make_desc_mn(a_hi + ko, WG_BOX, 1024), make_desc_mn(b_hi + ko, WG_BOX, 1024), idesc, first);
-          mma_tf32(tmem_base, make_desc_mn(a_lo + ko, WG_BOX, 1024), make_desc_mn(b_hi + ko, WG_BOX, 1024), idesc, 1u);
-          mma_tf32(tmem_base, make_desc_mn(a_hi + ko, WG_BOX, 1024), make_desc_mn(b_lo + ko, WG_BOX, 1024), idesc, 1u);
+          mma_tf32(tmem_base, make_desc_mn(a_hi + ko, WG_BOX, 512), make_desc_mn(b_hi + ko, WG_BOX, 512), idesc, first);
+          mma_tf32(tmem_base, make_desc_mn(a_lo + ko, WG_BOX, 512), make_desc_mn(b_hi + ko, WG_BOX, 512), idesc, 1u);
+          mma_tf32(tmem_base, make_desc_mn(a_hi + ko, WG_BOX, 512), make_desc_mn(b_lo + ko, WG_BOX, 512), idesc, 1u);
         }
         tc_commit(empty + stage);
         if (c == num_c - 1) tc_commit(acc_full);
@@ -390,8 +391,10 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slabs
 
 // ---- host: tensor maps -------------------------------------------------------------------------------------
 #ifdef TZK_CPU_SHIM
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+             bool atom32 = false) {
   map->base = base; map->rows = rows; map->cols = cols; map->ld = ld; map->box_rows = box_rows;
+  map->atom32 = atom32;
   return 0;
 }
 #else
@@ -399,7 +402,9 @@ typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-B chunks swizzled) for MN-major 32-bit operands, else SWIZZLE_128B
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+             bool atom32 = false) {
   static EncodeTiled encode = nullptr;
   if (!encode) {
     cudaDriverEntryPointQueryResult q;
@@ -412,7 +417,8 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 2;
 }
 #endif
@@ -475,7 +481,7 @@ extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_
   if (M <= 0 || K <= 0 || slabs <= 0 || (ld_x % 4) || (ld_dz % 4)) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap mx, mz;
-  if (make_map(&mx, x, M, K, ld_x, WG_ROWS) || make_map(&mz, dz, M, 64, ld_dz, WG_ROWS)) return 2;
+  if (make_map(&mx, x, M, K, ld_x, WG_ROWS, true) || make_map(&mz, dz, M, 64, ld_dz, WG_ROWS, true)) return 2;
   WgParams p;
   p.partial = partial;
   p.M = M;

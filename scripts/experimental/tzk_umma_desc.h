@@ -26,16 +26,19 @@ TZK_HD uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// MN-major, SWIZZLE_128B operand (canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-B units, mma_traits_sm100.hpp
-// make_umma_desc<Major::MN>): a swizzle atom is 8 k-rows x 128 B of MN (= what one TMA SWIZZLE_128B box row group
-// holds); LBO = bytes between consecutive 32-float MN groups, SBO = bytes between consecutive 8-row k groups.
+// MN-major operand of 32-bit elements: the only shared-memory layout tcgen05 accepts is SWIZZLE_128B_BASE32B (layout
+// type 1; CUTLASS sm100_common.inl sm100_smem_selector: "for mn-major tf32 operands, SW128_32B is the only available
+// smem layout") = 128-B rows whose 32-B chunks are XOR-ed with (row & 3) — what a TMA box written with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B holds.  Canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-B units
+// (mma_traits_sm100.hpp make_umma_desc<Major::MN>): a swizzle atom is 4 k-rows x 128 B of MN; LBO = bytes between
+// consecutive 32-float MN groups, SBO = bytes between consecutive 4-row k groups (one tf32 MMA, K = 8, spans two).
 TZK_HD uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;      // SWIZZLE_128B_BASE32B
   return d;
 }
 // instruction descriptor (InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format TF32 = 2 @ [7,10) / [10,13),

@@ -171,6 +171,8 @@ def test_deepfm_mixed_three_ranks():
     (4, "dlrm_criteo", "row_wise", 0),
     (8, "dlrm_criteo", "row_wise", 0),            # cfg2's world size: tables smaller than W leave ranks empty
     (4, "mmoe_taobao", "mixed", 250),             # cfg5: big tables row-wise, small ones table-wise, two task towers
+    (8, "deepfm_criteo", "table_wise", 0),        # W = 8 x {TW, mixed}: completes the W in {1,2,4,8} x {TW,RW,mixed} grid
+    (8, "dlrm_criteo", "mixed", 200),
 ])
 def test_w_invariance_at_larger_world_sizes(world, name, sharding, rw_min):
     _run(world, name, sharding, rw_min_rows=rw_min)
