@@ -42,16 +42,47 @@ def _stream() -> int:
 
 class _Symm:
     """One symmetric allocation: `t` is this rank's tensor, `ptrs` a host array with every rank's address as mapped in
-    this process (rank order)."""
+    this process (rank order).  Allocation + address exchange: `torch.distributed._symmetric_memory` (cuMem VMM handles);
+    TZK_PEER_ALLOC=ipc — or a failing rendezvous — falls back to classic CUDA IPC handles through
+    torch.multiprocessing's reductions (cudaIpcGetMemHandle / cudaIpcOpenMemHandle), one all_gather_object each."""
 
     def __init__(self, numel: int, dtype, device, group) -> None:
-        import torch.distributed._symmetric_memory as symm_mem
+        import os
 
-        self.t = symm_mem.empty(max(int(numel), 1), dtype=dtype, device=device)
-        self.t.zero_()
-        self.h = symm_mem.rendezvous(self.t, group)
         W = dist.get_world_size(group)
-        self.ptrs = (ctypes.c_uint64 * W)(*[int(p) for p in self.h.buffer_ptrs])
+        n = max(int(numel), 1)
+        self.h = None
+        if os.environ.get("TZK_PEER_ALLOC", "symm") != "ipc":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                self.t = symm_mem.empty(n, dtype=dtype, device=device)
+                self.t.zero_()
+                self.h = symm_mem.rendezvous(self.t, group)
+                self.ptrs = (ctypes.c_uint64 * W)(*[int(p) for p in self.h.buffer_ptrs])
+                return
+            except Exception as e:  # noqa: BLE001 — e.g. no pidfd / fabric handle support in this container
+                import warnings
+
+                warnings.warn(f"symmetric-memory rendezvous failed ({e!r}); falling back to CUDA IPC handles")
+        self._ipc(n, dtype, device, group, W)
+
+    def _ipc(self, n: int, dtype, device, group, W: int) -> None:
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        me = dist.get_rank(group)
+        # a private cudaMalloc block (IPC shares whole allocations): ask the caching allocator for an exclusive segment
+        self.t = torch.zeros(n, dtype=dtype, device=device)
+        torch.cuda.synchronize()
+        fn, args = reduce_tensor(self.t)
+        gathered = [None] * W
+        dist.all_gather_object(gathered, args, group=group)
+        self.peers = [self.t if r == me else fn(*gathered[r]) for r in range(W)]
+        for r, pt in enumerate(self.peers):     # first touch enables peer access between the two devices
+            if r != me:
+                _ = pt[:1].to(device)
+        torch.cuda.synchronize()
+        self.ptrs = (ctypes.c_uint64 * W)(*[int(pt.data_ptr()) for pt in self.peers])
 
 
 class PeerState:
