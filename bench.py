@@ -422,6 +422,12 @@ def run_ours(args):
         draft = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "experimental", "try_tower_bwd2.py")
         if os.path.exists(draft):
             extras["tower_bwd2_draft"] = _run_draft(draft, [str(B)], 180)
+        # the same step with the wide tower layer on the hand-written tcgen05 kernels (opt-in until its autograd glue
+        # has run on hardware — this subprocess IS that run): ms/step and the last loss next to this run's
+        extras["gemm3x_step"] = _run_variant({"TZK_GEMM3X": "1", "TZK_GEMM3X_STACK": "1"}, args, 300)
+        model_try = os.path.join(os.path.dirname(draft), "try_gemm3x_model.py")
+        if os.path.exists(model_try):   # parity of that path inside the model (two seeded pipelines, switch off / on)
+            extras["gemm3x_model_parity"] = _run_draft(model_try, ["8192"], 240)
         args._extras = extras
     _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
 
@@ -456,6 +462,26 @@ def _e2e_pipelined(step, host, K, batch):
     ms = t0.elapsed_time(t1)
     return {"value": batch * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "last_loss": last,
             "note": "loss of step i-1 read on the host while step i runs (pinned D2H + event), same H2D feed as e2e"}
+
+
+def _run_variant(env, args, timeout):
+    """This benchmark again in a subprocess with extra environment switches (short, no CPU baseline / Zipf / extras)."""
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--steps", "12", "--warmup", "4", "--no-cpu-baseline", "--no-zipf",
+               "--no-extras", "--batch-size", str(args.batch_size), "--model", args.model]
+        if args.max_rows:
+            cmd += ["--max-rows", str(args.max_rows)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env={**os.environ, **env})
+        lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"rc": r.returncode, "err": [ln.strip() for ln in r.stderr.splitlines() if ln.strip()][-3:]}
+        d = json.loads(lines[-1])
+        return {"env": env, "ms_per_step": d["ms_per_step"], "value": d["value"], "e2e_ms_per_step": d["e2e"]["ms_per_step"],
+                "last_loss": d["e2e"].get("last_loss")}
+    except subprocess.TimeoutExpired:
+        return {"rc": "timeout"}
+    except Exception as e:   # noqa: BLE001 — an extra is never allowed to fail the bench
+        return {"rc": repr(e)[:200]}
 
 
 def _run_draft(path, argv, timeout):

@@ -50,3 +50,19 @@ def test_product_has_no_cpu_fallback():
     # and the package never imports the oracle
     import sys
     assert not any(m == "oracle" or m.startswith("oracle.") for m in sys.modules if "torcheasyrec" in m)
+
+
+def test_gemm3x_library_exports_its_header():
+    """include/tzk_gemm3x.h <-> libtzk_gemm3x.so (the tcgen05 GEMMs of the wide tower layer)."""
+    src = open(os.path.join(ROOT, "include", "tzk_gemm3x.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = set(re.findall(r"\b(tzk_[a-z0-9_]+)\s*\(", src))
+    assert declared == {"tzk_gemm3x", "tzk_wgrad3x", "tzk_wgrad3x_partial_floats"}
+    lib = os.path.join(ROOT, "torcheasyrec_b200", "csrc", "libtzk_gemm3x.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    assert set(re.findall(r" T (tzk_[a-z0-9_]+)", out)) == declared
+    import ctypes
+
+    h = ctypes.CDLL(lib)
+    h.tzk_wgrad3x_partial_floats.restype = ctypes.c_int64
+    assert h.tzk_wgrad3x_partial_floats(784, 21) == 21 * 896 * 64

@@ -574,16 +574,46 @@ def test_gradient_clipping_on_classic_optimizers(kernels, bwd_path):
 
 @pytest.mark.parametrize("stack", ["0", "1"])
 @pytest.mark.parametrize("M", [300, 65536 + 5])
-def test_wide_layer_on_tcgen05_matches_fp64(monkeypatch, M, stack):
-    """TZK_GEMM3X=1: the 783 -> 64 tower layer (input travelling as [B, 784] with a zero column) on the hand-written
-    3xTF32 kernels — forward with fused bias + ReLU, dgrad, wgrad — against float64 autograd; fp32-level tolerance
-    (the library path it replaces, cuBLASLt BF16x9, meets the same bound)."""
+def test_gemm3x_kernels_match_fp64(monkeypatch, M, stack):
+    """csrc/tzk_gemm3x.cu (libtzk_gemm3x.so), the three passes of the 783 -> 64 tower layer on hand-written tcgen05
+    kind::tf32 kernels with the 3xTF32 split: forward (bias + ReLU epilogue), dgrad (W^T), wgrad (MN-major operands,
+    bit-repeatable slab reduction).  fp32-level error against float64 — the same bound torch's fp32 SIMT GEMM meets."""
+    from torcheasyrec_b200 import dense_gemm as G
+
+    lib = G._gemm3x_lib()
+    if lib is None:
+        pytest.fail("libtzk_gemm3x.so missing: build() did not produce it")
+    monkeypatch.setenv("TZK_GEMM3X_STACK", stack)
+    torch.manual_seed(M)
+    K, N = 784, 64
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    b = torch.randn(N, device=DEV)
+    y = G.gemm3x(lib, x, w, b, True)
+    ref = torch.relu(x.double() @ w.double().T + b.double())
+    np.testing.assert_allclose(y.cpu().numpy(), ref.cpu().numpy(), atol=1.5e-5)
+    dz = torch.randn(M, N, device=DEV)
+    dx = G.gemm3x(lib, dz, w.t().contiguous(), None, False)
+    np.testing.assert_allclose(dx.cpu().numpy(), (dz.double() @ w.double()).cpu().numpy(), atol=1.5e-5)
+    if stack == "0":
+        dzs = dz / max(M, 1) ** 0.5
+        dw = G.wgrad3x(lib, x, dzs)
+        np.testing.assert_allclose(dw.cpu().numpy(), (dzs.double().T @ x.double()).cpu().numpy(), atol=1.5e-5)
+        assert torch.equal(dw, G.wgrad3x(lib, x, dzs))
+
+
+@pytest.mark.skipif(os.environ.get("TZK_TEST_GEMM3X_GLUE", "0") != "1",
+                    reason="autograd glue of TZK_GEMM3X=1 (dense_gemm.Gemm3xLinearFn): covered on the CPU through the "
+                           "emulated kernels; its first run on hardware is opted into with TZK_TEST_GEMM3X_GLUE=1")
+@pytest.mark.parametrize("M", [300, 65536 + 5])
+def test_wide_layer_on_tcgen05_matches_fp64(monkeypatch, M):
+    """TZK_GEMM3X=1: the 783 -> 64 tower layer (input travelling as [B, 784] with a zero column) through
+    dense_gemm.linear — forward with fused bias + ReLU, dgrad, wgrad — against float64 autograd."""
     from torcheasyrec_b200 import dense_gemm as G
 
     if G._gemm3x_lib() is None:
         pytest.fail("libtzk_gemm3x.so missing: build() did not produce it")
     monkeypatch.setenv("TZK_GEMM3X", "1")
-    monkeypatch.setenv("TZK_GEMM3X_STACK", stack)
     torch.manual_seed(M)
     K, Kx, N = 783, 784, 64
     in_map = ((0, 0, 16), (16, 17, 767))
