@@ -415,19 +415,24 @@ def run_ours(args):
     # ---- measurement-only extras (N=1): not part of value / e2e / roofline, and never allowed to fail the run ----
     if not args.no_extras and graphed:
         extras = {"note": "measurement-only; no reported number above depends on these"}
+        deadline = time.time() + 210.0          # all extras together: bounded, so that the line below is never at risk
+
+        def left(cap):
+            return max(5.0, min(cap, deadline - time.time()))
+
         try:
             extras["e2e_pipelined"] = _e2e_pipelined(step, host, K, B)
         except Exception as e:
             extras["e2e_pipelined"] = {"failed": repr(e)[:200]}
-        draft = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "experimental", "try_tower_bwd2.py")
-        if os.path.exists(draft):
-            extras["tower_bwd2_draft"] = _run_draft(draft, [str(B)], 180)
-        # the same step with the wide tower layer on the hand-written tcgen05 kernels (opt-in until its autograd glue
-        # has run on hardware — this subprocess IS that run): ms/step and the last loss next to this run's
-        extras["gemm3x_step"] = _run_variant({"TZK_GEMM3X": "1", "TZK_GEMM3X_STACK": "1"}, args, 300)
-        model_try = os.path.join(os.path.dirname(draft), "try_gemm3x_model.py")
-        if os.path.exists(model_try):   # parity of that path inside the model (two seeded pipelines, switch off / on)
-            extras["gemm3x_model_parity"] = _run_draft(model_try, ["8192"], 240)
+        exp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "experimental")
+        # the wide tower layer on the hand-written tcgen05 kernels (opt-in until its autograd glue has run on hardware —
+        # these subprocesses ARE that run): model-level parity first, then this benchmark with the switch on
+        if os.path.exists(os.path.join(exp, "try_gemm3x_model.py")) and time.time() < deadline - 30:
+            extras["gemm3x_model_parity"] = _run_draft(os.path.join(exp, "try_gemm3x_model.py"), ["8192"], left(90))
+        if time.time() < deadline - 45:
+            extras["gemm3x_step"] = _run_variant({"TZK_GEMM3X": "1", "TZK_GEMM3X_STACK": "1"}, args, left(120))
+        if os.path.exists(os.path.join(exp, "try_tower_bwd2.py")) and time.time() < deadline - 30:
+            extras["tower_bwd2_draft"] = _run_draft(os.path.join(exp, "try_tower_bwd2.py"), [str(B)], left(90))
         args._extras = extras
     _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
 

@@ -41,10 +41,12 @@ def _p(a):
 TOL = 2e-5
 
 
-@pytest.fixture(params=["0", "1"], ids=["3mma", "stacked"])
+@pytest.fixture(params=[("0", "4"), ("1", "4"), ("0", "8"), ("1", "8")], ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8"])
 def stack(request, monkeypatch):
-    """TZK_GEMM3X_STACK=1: hi(x) * [W_hi ; W_lo] as one N = 2*BN MMA + lo(x) * W_hi, halves added in the epilogue."""
-    monkeypatch.setenv("TZK_GEMM3X_STACK", request.param)
+    """TZK_GEMM3X_STACK=1: hi(x) * [W_hi ; W_lo] as one N = 2*BN MMA + lo(x) * W_hi, halves added in the epilogue.
+    TZK_GEMM3X_TW=8: eight transform / epilogue warps (two per TMEM lane quarter) instead of four."""
+    monkeypatch.setenv("TZK_GEMM3X_STACK", request.param[0])
+    monkeypatch.setenv("TZK_GEMM3X_TW", request.param[1])
     return request.param
 
 

@@ -75,8 +75,10 @@ struct Params {
 // N = 2 * BN (columns [0, BN) collect hi*hi, columns [BN, 2 BN) hi*lo) and lo(x) * W_hi a second one with N = BN into
 // the first half; the epilogue adds the halves.  Two MMAs and 14 KB of operand reads per k-step instead of three and
 // 18 KB — at N = 64 the MMA is bound by operand reads, not flops.
-template <int BN, bool STACK>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// TW = transform / epilogue warps (4 or 8; TZK_GEMM3X_TW): two warps share a TMEM lane quarter when TW = 8 and split the
+// tile's column groups between them.
+template <int BN, bool STACK, int TW>
+__global__ void __launch_bounds__(64 + 32 * TW, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
               const __grid_constant__ CUtensorMap map_wlo, Params p) {
   constexpr int W_BYTES = Cfg<BN>::W_BYTES, W_PAD = Cfg<BN>::W_PAD, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
@@ -104,12 +106,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(ready + s, 4);
+      mbar_init(ready + s, TW);
       mbar_init(empty + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full + a, 1);
-      mbar_init(acc_empty + a, 4);
+      mbar_init(acc_empty + a, TW);
     }
     fence_mbarrier_init();
   }
@@ -183,7 +185,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
   } else {
     // ===== transform + epilogue warps (2..5) =====================================================================
-    const int tw = warp - 2;                 // 0..3
+    const int tw = warp - 2;                 // 0..TW-1
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
     int stage = 0;
     uint32_t phase = 0;
@@ -194,10 +196,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         mbar_wait(full + stage, phase);
         float4* hi = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES + X_BYTES);
-        // 1024 float4 per X chunk, 128 transform threads -> 8 each; element-wise, so the swizzle is irrelevant
+        // 1024 float4 per X chunk over the TW * 32 transform threads; element-wise, so the swizzle is irrelevant
 #pragma unroll
-        for (int q = 0; q < X_BYTES / 16 / 128; ++q) {
-          const int i = q * 128 + tw * 32 + lane;
+        for (int q = 0; q < X_BYTES / 16 / (TW * 32); ++q) {
+          const int i = q * (TW * 32) + tw * 32 + lane;
           const float4 x = hi[i];
           float4 h, l;
           h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
@@ -218,7 +220,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       float v[16];
 #pragma unroll
-      for (int part = 0; part < BN / 16; ++part) {
+      for (int part = tw / 4; part < BN / 16; part += TW / 4) {   // TW = 8: the two warps of a lane quarter alternate
         // small terms first, then the partials (fp32 round-to-nearest adds)
         float v2[16];
         if (STACK) {
@@ -475,18 +477,18 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 }
 }  // namespace
 
-template <int BN, bool STACK>
+template <int BN, bool STACK, int TW>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  TZK_LAUNCH((gemm3x_kernel<BN, STACK>), grid, NUM_THREADS, smem, st, mx, mh, ml, p);
+  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW>), grid, 64 + 32 * TW, smem, st, mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -509,8 +511,12 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   Params p;
   p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.N = N; p.relu = relu;
   const char* e = getenv("TZK_GEMM3X_STACK");     // 1: two MMAs per k-step (see gemm3x_kernel); default: three
-  if (e && e[0] == '1') return BN == 64 ? launch<64, true>(mx, mh, ml, p, st) : launch<112, true>(mx, mh, ml, p, st);
-  return BN == 64 ? launch<64, false>(mx, mh, ml, p, st) : launch<112, false>(mx, mh, ml, p, st);
+  const char* t = getenv("TZK_GEMM3X_TW");        // 8: eight transform / epilogue warps; default: four
+  const bool stack = e && e[0] == '1', tw8 = t && t[0] == '8';
+#define TZK_G3(BN_) (stack ? (tw8 ? launch<BN_, true, 8>(mx, mh, ml, p, st) : launch<BN_, true, 4>(mx, mh, ml, p, st)) \
+                           : (tw8 ? launch<BN_, false, 8>(mx, mh, ml, p, st) : launch<BN_, false, 4>(mx, mh, ml, p, st)))
+  return BN == 64 ? TZK_G3(64) : TZK_G3(112);
+#undef TZK_G3
 }
 
 // dw[64, K] = dz[M, 64]^T @ x[M, K]  (3xTF32; fixed-order reduction over `slabs` row slabs -> run-to-run deterministic).
