@@ -90,6 +90,8 @@ void launch(dim3 grid, dim3 block, size_t smem, Body body) {
 #define __syncthreads() tzk_shim::t_bar->arrive_and_wait()
 #define __syncwarp() tzk_shim::t_wbar->arrive_and_wait()
 template <class T> inline T __ldg(const T* p) { return *p; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 #define TZK_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(tzk_shim::t_dyn)
 #define TZK_UNPAREN(...) __VA_ARGS__
 #define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) \

@@ -95,6 +95,15 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     tzk_emu::fail("mbarrier wait timed out (deadlock in the pipeline protocol)");
 }
 
+// warp-uniform wait (all 32 lanes call it): lane 0 waits, the warp follows — the lockstep real lanes have.  Without it a
+// lane thread that the OS descheduled inside the wait can sleep through TWO phase flips of a barrier whose next phase
+// does not depend on that lane (the MMA warp's `ready` wait) and then waits forever: an artefact of modelling lanes as
+// threads, observed once per ~5000 emulated CTAs.
+inline void mbar_wait_all(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 // ---- TMA --------------------------------------------------------------------------------------------------------------
 inline void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   const uint32_t d0 = smem_u32(dst);

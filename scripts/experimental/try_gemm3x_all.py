@@ -41,8 +41,8 @@ def gemm(L, M, K, N, relu, bias, tag):
     ref = torch.relu(ref) if relu else ref
     f32 = torch.nn.functional.linear(x, w, b)
     f32 = ((torch.relu(f32) if relu else f32).double() - ref).abs().max().item()
-    for stack, tw in (("0", "4"), ("1", "4"), ("0", "8"), ("1", "8")):
-        os.environ["TZK_GEMM3X_STACK"], os.environ["TZK_GEMM3X_TW"] = stack, tw
+    for stack, tw, raw in (("0", "4", "0"), ("1", "4", "0"), ("0", "8", "0"), ("1", "8", "0"), ("1", "4", "1"), ("1", "8", "1")):
+        os.environ["TZK_GEMM3X_STACK"], os.environ["TZK_GEMM3X_TW"], os.environ["TZK_GEMM3X_RAW"] = stack, tw, raw
 
         def run():
             rc = L.tzk_gemm3x(x.data_ptr(), K, w.data_ptr(), K, b.data_ptr() if bias else None, M, N, K, int(relu),
@@ -53,7 +53,7 @@ def gemm(L, M, K, N, relu, bias, tag):
         run()
         torch.cuda.synchronize()
         err = (y.double() - ref).abs().max().item()
-        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}: max err {err:.2e} (torch fp32 {f32:.2e}), "
+        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}{' raw' if raw == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), "
               f"{timed(run):.1f} us", flush=True)
 
 

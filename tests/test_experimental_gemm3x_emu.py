@@ -11,6 +11,7 @@ hardware agrees with the emulation (the descriptor FIELDS are checked against Cu
 import ctypes
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -19,17 +20,46 @@ EXP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
 
 
-@pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("emu") / "libtzk_gemm3x_cpu.so")
-    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-x", "c++",
-                    os.path.join(EXP, "tzk_gemm3x.cu"), "-shared", "-fPIC", "-o", out], check=True)
-    L = ctypes.CDLL(out)
+CHILD = os.environ.get("TZK_EMU_CHILD") == "1"
+
+
+def _declare(L):
     L.tzk_gemm3x.argtypes = [P, I64, P, I64, P, I64, I32, I32, I32, P, I64, P, P, P]
     L.tzk_wgrad3x.argtypes = [P, I64, P, I64, I64, I32, I32, P, P, I64, P]
     L.tzk_wgrad3x_partial_floats.restype = I64
     L.tzk_wgrad3x_partial_floats.argtypes = [I32, I32]
     return L
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    """Parent: compiles the host build once and hands its path to the children.  Child: loads it."""
+    if CHILD:
+        return _declare(ctypes.CDLL(os.environ["TZK_EMU_LIB"]))
+    out = str(tmp_path_factory.mktemp("emu") / "libtzk_gemm3x_cpu.so")
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-x", "c++",
+                    os.path.join(EXP, "tzk_gemm3x.cu"), "-shared", "-fPIC", "-o", out], check=True)
+    return out
+
+
+def _delegate(request, lib) -> bool:
+    """Every case runs in a child pytest process: the emulation aborts the process on a protocol violation or a
+    deadlock (192-320 real threads per emulated CTA), and that must fail ONE test, not take the whole suite down.
+    An abnormal exit is retried once (thread-scheduling artefacts of the emulation have been seen once in thousands of
+    CTAs); an ordinary assertion failure is not."""
+    if CHILD:
+        return False
+    env = {**os.environ, "TZK_EMU_CHILD": "1", "TZK_EMU_LIB": lib}
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", request.node.nodeid]
+    for attempt in (1, 2):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        if r.returncode == 0:
+            return True
+        crashed = r.returncode < 0 or r.returncode > 5        # pytest's own exit codes are 0..5
+        if not crashed or attempt == 2:
+            pytest.fail(f"child exited with {r.returncode} (attempt {attempt}):\n{r.stdout[-3000:]}\n{r.stderr[-2000:]}")
+    return True
 
 
 def _p(a):
@@ -41,18 +71,22 @@ def _p(a):
 TOL = 2e-5
 
 
-@pytest.fixture(params=[("0", "4"), ("1", "4"), ("0", "8"), ("1", "8")], ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8"])
+@pytest.fixture(params=[("0", "4", "0"), ("1", "4", "0"), ("0", "8", "0"), ("1", "8", "0"), ("0", "4", "1"), ("1", "8", "1")],
+                ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8", "3mma-raw", "stacked-tw8-raw"])
 def stack(request, monkeypatch):
     """TZK_GEMM3X_STACK=1: hi(x) * [W_hi ; W_lo] as one N = 2*BN MMA + lo(x) * W_hi, halves added in the epilogue.
     TZK_GEMM3X_TW=8: eight transform / epilogue warps (two per TMEM lane quarter) instead of four."""
     monkeypatch.setenv("TZK_GEMM3X_STACK", request.param[0])
     monkeypatch.setenv("TZK_GEMM3X_TW", request.param[1])
+    monkeypatch.setenv("TZK_GEMM3X_RAW", request.param[2])      # raw fp32 as hi (the tensor core truncates), lo only
     return request.param
 
 
 @pytest.mark.parametrize("M,relu,bias", [(200, 1, True), (1, 0, False), (128, 1, True)])
-def test_forward_784_to_64(lib, stack, M, relu, bias):
+def test_forward_784_to_64(request, lib, stack, M, relu, bias):
     """K = 784 = 24.5 chunks of 32 (zero-filled tail), rows past M zero-filled and not stored, bias + ReLU epilogue."""
+    if _delegate(request, lib):
+        return
     rng = np.random.default_rng(M)
     K, N = 784, 64
     x = rng.standard_normal((M, K)).astype(np.float32)
@@ -65,9 +99,9 @@ def test_forward_784_to_64(lib, stack, M, relu, bias):
     ref = np.maximum(ref, 0) if relu else ref
     np.testing.assert_allclose(y[:M], ref, rtol=0, atol=TOL)
     assert np.isnan(y[M]).all()
-    # the split really is hi + lo with hi on the TF32 grid
-    assert (wh.view(np.uint32) & 0x1FFF == 0).all() and (wl.view(np.uint32) & 0x1FFF == 0).all()
-    np.testing.assert_allclose(wh.astype(np.float64) + wl, w, rtol=2 ** -21)
+    if stack[2] == "0":     # the split really is hi + lo with hi on the TF32 grid (raw mode writes lo only)
+        assert (wh.view(np.uint32) & 0x1FFF == 0).all() and (wl.view(np.uint32) & 0x1FFF == 0).all()
+        np.testing.assert_allclose(wh.astype(np.float64) + wl, w, rtol=2 ** -21)
     # plain TF32 (hi x hi only) would be ~1000x worse: the lo terms are doing their job
     tf = lambda a: (a.view(np.uint32) & 0xFFFFE000).view(np.float32)
     plain = np.abs(tf(x).astype(np.float64) @ tf(w).astype(np.float64).T + (b if bias else 0.0) -
@@ -75,8 +109,10 @@ def test_forward_784_to_64(lib, stack, M, relu, bias):
     assert plain > 20 * TOL or M == 1
 
 
-def test_dgrad_64_to_784(lib, stack):
+def test_dgrad_64_to_784(request, lib, stack):
     """The input-gradient pass: BN = 112, seven column tiles per row tile, two k-chunks, three stages."""
+    if _delegate(request, lib):
+        return
     rng = np.random.default_rng(1)
     M, K, N = 130, 64, 784
     dz = rng.standard_normal((M, K)).astype(np.float32)
@@ -88,9 +124,11 @@ def test_dgrad_64_to_784(lib, stack):
 
 
 @pytest.mark.parametrize("M,slabs", [(200, 2), (70, 3), (31, 1)])
-def test_wgrad_mn_major(lib, M, slabs):
+def test_wgrad_mn_major(request, lib, M, slabs):
     """dW = dZ^T X with both operands MN-major straight from the row-major tensors; row slabs (the last one short or
     empty), 7 column tiles (the last one 16 of 128 columns), fixed-order slab reduction + transpose."""
+    if _delegate(request, lib):
+        return
     rng = np.random.default_rng(M + slabs)
     K = 784
     x = rng.standard_normal((M, K)).astype(np.float32)
@@ -104,10 +142,12 @@ def test_wgrad_mn_major(lib, M, slabs):
     np.testing.assert_array_equal(dw, dw2)
 
 
-def test_autograd_wiring_of_the_wide_layer(lib, monkeypatch):
+def test_autograd_wiring_of_the_wide_layer(request, lib, monkeypatch):
     """scripts/experimental/gemm3x_linear.py (the drop-in for dense_gemm._LinearFn on DLRM's 783 -> 64 layer) on CPU
     tensors through the emulated kernels: forward, input gradient, weight gradient (column-mapped 783 -> 784 input)
     and bias gradient against torch autograd."""
+    if _delegate(request, lib):
+        return
     import sys
 
     import torch

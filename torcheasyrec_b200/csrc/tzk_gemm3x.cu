@@ -61,6 +61,8 @@ struct Cfg {
   static constexpr int STAGES = BN <= 64 ? 4 : 3;          // 4 x 48 KB / 3 x 60 KB of shared memory
 };
 
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 struct Params {
   const float* bias;   // [64] or NULL
   float* y;            // [M, ld_y]
@@ -77,7 +79,11 @@ struct Params {
 // 18 KB — at N = 64 the MMA is bound by operand reads, not flops.
 // TW = transform / epilogue warps (4 or 8; TZK_GEMM3X_TW): two warps share a TMEM lane quarter when TW = 8 and split the
 // tile's column groups between them.
-template <int BN, bool STACK, int TW>
+// RAW (TZK_GEMM3X_RAW=1): the hi operands are the raw fp32 tensors themselves — kind::tf32 ignores the low 13 mantissa
+// bits, so the hardware multiplies trunc(x) — and only lo = rna(x - trunc(x)) is computed and stored (one shared-memory
+// write stream and one conversion per element less).  If the hardware rounded instead of truncating, the error would
+// jump to ~1e-3: the accuracy tests decide.
+template <int BN, bool STACK, int TW, bool RAW>
 __global__ void __launch_bounds__(64 + 32 * TW, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
               const __grid_constant__ CUtensorMap map_wlo, Params p) {
@@ -147,12 +153,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     constexpr uint32_t idesc = make_idesc<BN>();
     constexpr uint32_t idesc2 = make_idesc<2 * BN>();    // STACK only
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait(acc_empty + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+      mbar_wait_all(acc_empty + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       uint32_t started = 0;                           // bit p: partial p holds data of this tile (bit P: the small terms)
       for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(ready + stage, phase);              // hi / lo of this chunk are in shared memory
+        mbar_wait_all(ready + stage, phase);              // hi / lo of this chunk are in shared memory
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sb = smem_u32(stage_base + stage * STAGE_BYTES);
@@ -193,7 +199,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(full + stage, phase);
+        mbar_wait_all(full + stage, phase);
         float4* hi = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES + X_BYTES);
         // 1024 float4 per X chunk over the TW * 32 transform threads; element-wise, so the swizzle is irrelevant
@@ -202,9 +208,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const int i = q * (TW * 32) + tw * 32 + lane;
           const float4 x = hi[i];
           float4 h, l;
-          h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+          if (RAW) {
+            h.x = tf32_trunc(x.x); h.y = tf32_trunc(x.y); h.z = tf32_trunc(x.z); h.w = tf32_trunc(x.w);
+          } else {
+            h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+          }
           l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-          hi[i] = h;
+          if (!RAW) hi[i] = h;
           lo[i] = l;
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the MMA
@@ -213,7 +223,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       // ---- epilogue of this tile ---------------------------------------------------------------------------
-      mbar_wait(acc_full + acc, acc_phase);
+      mbar_wait_all(acc_full + acc, acc_phase);
       tc_fence_after();
       const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
       const int col0 = (int)(t % n_tiles) * BN;
@@ -349,7 +359,7 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     constexpr uint32_t idesc = make_idesc<64, true>();
     uint32_t started = 0;
     for (int c = 0; c < num_c; ++c) {
-      mbar_wait(ready + stage, phase);
+      mbar_wait_all(ready + stage, phase);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sb = smem_u32(smem + stage * WG_STAGE);
@@ -377,7 +387,7 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int c = 0; c < num_c; ++c) {
-      mbar_wait(full + stage, phase);
+      mbar_wait_all(full + stage, phase);
       uint8_t* sb = smem + stage * WG_STAGE;
       // A: 1024 float4 (hi at +0, lo at +WG_A); B: 512 float4 (hi at +2*WG_A, lo at +2*WG_A+WG_B); element-wise.
 #pragma unroll
@@ -398,7 +408,7 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
     // epilogue: TMEM lane = X column inside the tile, TMEM column = n
-    mbar_wait(acc_full, 0);
+    mbar_wait_all(acc_full, 0);
     tc_fence_after();
     const int krow = jt * 128 + quarter * 32 + lane;
     float* out = p.partial + ((int64_t)slab * p.k_tiles * 128 + krow) * 64;
@@ -467,6 +477,12 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
 }
 #endif
 
+// RAW variant: hi is w itself (the tensor core truncates), only the residual is written
+__global__ void split_w_raw_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lo[i] = tf32_rna(w[i] - tf32_trunc(w[i]));
+}
+
 __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -477,18 +493,18 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 }
 }  // namespace
 
-template <int BN, bool STACK, int TW>
+template <int BN, bool STACK, int TW, bool RAW>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW>), grid, 64 + 32 * TW, smem, st, mx, mh, ml, p);
+  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW>), grid, 64 + 32 * TW, smem, st, mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -504,18 +520,23 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int BN = N == 64 ? 64 : 112;
   const int64_t nw = (int64_t)N * ld_w;
-  TZK_LAUNCH((split_w_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_hi, w_lo);
+  const char* r = getenv("TZK_GEMM3X_RAW");       // 1: raw fp32 as the hi operands (see gemm3x_kernel); default: rounded split
+  const bool raw = r && r[0] == '1';
+  if (raw) TZK_LAUNCH((split_w_raw_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_lo);
+  else TZK_LAUNCH((split_w_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_hi, w_lo);
   CUtensorMap mx, mh, ml;
-  if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, w_hi, N, K, ld_w, BN) || make_map(&ml, w_lo, N, K, ld_w, BN))
+  if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, raw ? w : w_hi, N, K, ld_w, BN) || make_map(&ml, w_lo, N, K, ld_w, BN))
     return 2;
   Params p;
   p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.N = N; p.relu = relu;
   const char* e = getenv("TZK_GEMM3X_STACK");     // 1: two MMAs per k-step (see gemm3x_kernel); default: three
   const char* t = getenv("TZK_GEMM3X_TW");        // 8: eight transform / epilogue warps; default: four
   const bool stack = e && e[0] == '1', tw8 = t && t[0] == '8';
-#define TZK_G3(BN_) (stack ? (tw8 ? launch<BN_, true, 8>(mx, mh, ml, p, st) : launch<BN_, true, 4>(mx, mh, ml, p, st)) \
-                           : (tw8 ? launch<BN_, false, 8>(mx, mh, ml, p, st) : launch<BN_, false, 4>(mx, mh, ml, p, st)))
+#define TZK_G3R(BN_, S_, T_) (raw ? launch<BN_, S_, T_, true>(mx, mh, ml, p, st) : launch<BN_, S_, T_, false>(mx, mh, ml, p, st))
+#define TZK_G3(BN_) (stack ? (tw8 ? TZK_G3R(BN_, true, 8) : TZK_G3R(BN_, true, 4)) \
+                           : (tw8 ? TZK_G3R(BN_, false, 8) : TZK_G3R(BN_, false, 4)))
   return BN == 64 ? TZK_G3(64) : TZK_G3(112);
+#undef TZK_G3R
 #undef TZK_G3
 }
 

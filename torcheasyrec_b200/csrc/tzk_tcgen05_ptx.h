@@ -25,6 +25,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// the same wait executed by ALL 32 lanes of a warp (warp-uniform): on hardware the lanes run the try_wait in lockstep and
+// see the same barrier state; the host emulation, where every lane is its own thread, gives this entry point that
+// lockstep (one lane waits, the warp follows) — without it a descheduled lane can sleep through two phases.
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+
 // ---- TMA ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
