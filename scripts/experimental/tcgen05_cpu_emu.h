@@ -126,6 +126,8 @@ inline void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0
   ct.cv.notify_all();
 }
 
+inline void tma_prefetch_2d(const CUtensorMap*, int, int) {}   // L2 prefetch: no architectural effect
+
 // ---- tcgen05 ----------------------------------------------------------------------------------------------------------
 inline void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   if (cols < 32 || cols > 512 || (cols & (cols - 1))) tzk_emu::fail("tcgen05.alloc: columns must be a power of two in [32, 512]");

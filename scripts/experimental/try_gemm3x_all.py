@@ -41,8 +41,12 @@ def gemm(L, M, K, N, relu, bias, tag):
     ref = torch.relu(ref) if relu else ref
     f32 = torch.nn.functional.linear(x, w, b)
     f32 = ((torch.relu(f32) if relu else f32).double() - ref).abs().max().item()
-    for stack, tw, raw in (("0", "4", "0"), ("1", "4", "0"), ("0", "8", "0"), ("1", "8", "0"), ("1", "4", "1"), ("1", "8", "1")):
-        os.environ["TZK_GEMM3X_STACK"], os.environ["TZK_GEMM3X_TW"], os.environ["TZK_GEMM3X_RAW"] = stack, tw, raw
+    for stack, tw, raw, split, pf in (("0", "4", "0", "0", "0"), ("1", "4", "0", "0", "0"), ("1", "8", "0", "0", "0"),
+                                      ("1", "4", "1", "0", "0"), ("1", "4", "0", "1", "0"), ("1", "4", "0", "0", "1"),
+                                      ("1", "4", "1", "1", "1"), ("1", "8", "1", "1", "1")):
+        for var, val in zip(("TZK_GEMM3X_STACK", "TZK_GEMM3X_TW", "TZK_GEMM3X_RAW", "TZK_GEMM3X_SPLIT",
+                             "TZK_GEMM3X_PREFETCH"), (stack, tw, raw, split, pf)):
+            os.environ[var] = val
 
         def run():
             rc = L.tzk_gemm3x(x.data_ptr(), K, w.data_ptr(), K, b.data_ptr() if bias else None, M, N, K, int(relu),
@@ -53,7 +57,7 @@ def gemm(L, M, K, N, relu, bias, tag):
         run()
         torch.cuda.synchronize()
         err = (y.double() - ref).abs().max().item()
-        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}{' raw' if raw == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), "
+        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}{' raw' if raw == '1' else ''}{' split' if split == '1' else ''}{' pf' if pf == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), "
               f"{timed(run):.1f} us", flush=True)
 
 
@@ -77,7 +81,7 @@ def wgrad(L, M, K=784, slabs=21):
     first = dw.clone()
     run()
     torch.cuda.synchronize()
-    print(f"wgrad M={M}: max err {err:.2e} (torch fp32 {f32:.2e}), repeatable {torch.equal(first, dw)}, "
+    print(f"wgrad M={M}{' pf' if os.environ.get('TZK_GEMM3X_PREFETCH') == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), repeatable {torch.equal(first, dw)}, "
           f"{timed(run):.1f} us", flush=True)
 
 
@@ -92,7 +96,10 @@ def main():
     gemm(L, 300, 784, 64, True, True, "fwd  ")
     gemm(L, M, 784, 64, True, True, "fwd  ")
     gemm(L, M, 64, 784, False, False, "dgrad")
+    os.environ["TZK_GEMM3X_PREFETCH"] = "0"
     wgrad(L, 300)
+    wgrad(L, M)
+    os.environ["TZK_GEMM3X_PREFETCH"] = "1"
     wgrad(L, M)
     print(f"done in {time.time() - t0:.1f} s", flush=True)
 

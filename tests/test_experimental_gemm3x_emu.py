@@ -71,20 +71,28 @@ def _p(a):
 TOL = 2e-5
 
 
-@pytest.fixture(params=[("0", "4", "0"), ("1", "4", "0"), ("0", "8", "0"), ("1", "8", "0"), ("0", "4", "1"), ("1", "8", "1")],
-                ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8", "3mma-raw", "stacked-tw8-raw"])
+@pytest.fixture(params=[("0", "4", "0", "0", "0"), ("1", "4", "0", "0", "0"), ("0", "8", "0", "0", "0"), ("1", "8", "0", "0", "0"),
+                        ("0", "4", "1", "0", "0"), ("1", "8", "1", "0", "0"), ("1", "4", "0", "1", "0"), ("0", "8", "1", "1", "0"),
+                        ("1", "4", "1", "1", "1")],
+                ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8", "3mma-raw", "stacked-tw8-raw", "stacked-split",
+                     "3mma-tw8-raw-split", "stacked-raw-split-prefetch"])
 def stack(request, monkeypatch):
     """TZK_GEMM3X_STACK=1: hi(x) * [W_hi ; W_lo] as one N = 2*BN MMA + lo(x) * W_hi, halves added in the epilogue.
-    TZK_GEMM3X_TW=8: eight transform / epilogue warps (two per TMEM lane quarter) instead of four."""
-    monkeypatch.setenv("TZK_GEMM3X_STACK", request.param[0])
-    monkeypatch.setenv("TZK_GEMM3X_TW", request.param[1])
-    monkeypatch.setenv("TZK_GEMM3X_RAW", request.param[2])      # raw fp32 as hi (the tensor core truncates), lo only
+    TZK_GEMM3X_TW=8: eight transform / epilogue warps (two per TMEM lane quarter) instead of four.
+    TZK_GEMM3X_RAW=1: raw fp32 as hi (the tensor core truncates), lo only.
+    TZK_GEMM3X_SPLIT=1: four dedicated epilogue warps behind the transform warps.
+    TZK_GEMM3X_PREFETCH=1: L2 prefetch of the X boxes 12 chunks ahead (no architectural effect: control flow only here)."""
+    for var, val in zip(("TZK_GEMM3X_STACK", "TZK_GEMM3X_TW", "TZK_GEMM3X_RAW", "TZK_GEMM3X_SPLIT", "TZK_GEMM3X_PREFETCH"),
+                        request.param):
+        monkeypatch.setenv(var, val)
     return request.param
 
 
 @pytest.mark.parametrize("M,relu,bias", [(200, 1, True), (1, 0, False), (128, 1, True)])
 def test_forward_784_to_64(request, lib, stack, M, relu, bias):
     """K = 784 = 24.5 chunks of 32 (zero-filled tail), rows past M zero-filled and not stored, bias + ReLU epilogue."""
+    if M != 200 and stack not in (("0", "4", "0", "0", "0"), ("1", "4", "0", "0", "0")):
+        pytest.skip("tail shapes run on the two base variants only (suite time)")
     if _delegate(request, lib):
         return
     rng = np.random.default_rng(M)
@@ -123,10 +131,11 @@ def test_dgrad_64_to_784(request, lib, stack):
     np.testing.assert_allclose(dx, dz.astype(np.float64) @ wt.astype(np.float64).T, rtol=0, atol=TOL)
 
 
-@pytest.mark.parametrize("M,slabs", [(200, 2), (70, 3), (31, 1)])
-def test_wgrad_mn_major(request, lib, M, slabs):
+@pytest.mark.parametrize("M,slabs,prefetch", [(200, 2, "0"), (70, 3, "0"), (31, 1, "0"), (520, 1, "1")])
+def test_wgrad_mn_major(request, lib, monkeypatch, M, slabs, prefetch):
     """dW = dZ^T X with both operands MN-major straight from the row-major tensors; row slabs (the last one short or
     empty), 7 column tiles (the last one 16 of 128 columns), fixed-order slab reduction + transpose."""
+    monkeypatch.setenv("TZK_GEMM3X_PREFETCH", prefetch)   # "1": 17 chunks per CTA > the 12-chunk prefetch distance
     if _delegate(request, lib):
         return
     rng = np.random.default_rng(M + slabs)

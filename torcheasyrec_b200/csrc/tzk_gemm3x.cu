@@ -83,8 +83,16 @@ struct Params {
 // bits, so the hardware multiplies trunc(x) — and only lo = rna(x - trunc(x)) is computed and stored (one shared-memory
 // write stream and one conversion per element less).  If the hardware rounded instead of truncating, the error would
 // jump to ~1e-3: the accuracy tests decide.
-template <int BN, bool STACK, int TW, bool RAW>
-__global__ void __launch_bounds__(64 + 32 * TW, 1)
+// SPLIT (TZK_GEMM3X_SPLIT=1): four dedicated epilogue warps after the TW transform warps, so that draining tile i (TMEM ->
+// registers -> global, the dominant cost of the input-gradient pass) overlaps the transform + MMA work of tile i+1 —
+// which is what the two accumulator sets are for; without it the same warps do both, one after the other.
+// PF (TZK_GEMM3X_PREFETCH=1): the producer asks L2 for the X boxes PF_DIST chunks ahead (cp.async.bulk.prefetch.tensor).
+// The first hardware numbers (same ~0.9 us per 16-KB chunk in the forward and the weight-gradient pass, 2.6 TB/s) are
+// what four 16-KB stages in flight per SM give at an HBM -> shared-memory latency of ~3.7 us (Little's law); shared
+// memory for deeper stages is gone, the 126 MB L2 is not.
+constexpr int PF_DIST = 12;
+template <int BN, bool STACK, int TW, bool RAW, bool SPLIT, bool PF>
+__global__ void __launch_bounds__(64 + 32 * TW + (SPLIT ? 128 : 0), 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
               const __grid_constant__ CUtensorMap map_wlo, Params p) {
   constexpr int W_BYTES = Cfg<BN>::W_BYTES, W_PAD = Cfg<BN>::W_PAD, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
@@ -117,7 +125,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full + a, 1);
-      mbar_init(acc_empty + a, TW);
+      mbar_init(acc_empty + a, SPLIT ? 4 : TW);
     }
     fence_mbarrier_init();
   }
@@ -132,16 +140,33 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(empty + stage, phase ^ 1);
-          uint8_t* sb = stage_base + stage * STAGE_BYTES;
-          mbar_expect_tx(full + stage, X_BYTES + 2 * W_BYTES);   // W_BYTES, not W_PAD: the box is BN rows
-          tma_load_2d(sb, &map_x, full + stage, kb * BK, (int)(t / n_tiles * BM));
-          tma_load_2d(sb + 2 * X_BYTES, &map_whi, full + stage, kb * BK, (int)(t % n_tiles) * BN);
-          tma_load_2d(sb + 2 * X_BYTES + W_PAD, &map_wlo, full + stage, kb * BK, (int)(t % n_tiles) * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+      auto load_chunk = [&](int64_t t, int kb) {
+        mbar_wait(empty + stage, phase ^ 1);
+        uint8_t* sb = stage_base + stage * STAGE_BYTES;
+        mbar_expect_tx(full + stage, X_BYTES + 2 * W_BYTES);   // W_BYTES, not W_PAD: the box is BN rows
+        tma_load_2d(sb, &map_x, full + stage, kb * BK, (int)(t / n_tiles * BM));
+        tma_load_2d(sb + 2 * X_BYTES, &map_whi, full + stage, kb * BK, (int)(t % n_tiles) * BN);
+        tma_load_2d(sb + 2 * X_BYTES + W_PAD, &map_wlo, full + stage, kb * BK, (int)(t % n_tiles) * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      if constexpr (PF) {
+        int64_t pt = blockIdx.x;                // prefetch cursor: (tile, k-block) PF_DIST chunks ahead of the loads
+        int pkb = 0;
+        auto prefetch_next = [&] {
+          if (pt < num_tiles) {
+            tma_prefetch_2d(&map_x, pkb * BK, (int)(pt / n_tiles * BM));
+            if (++pkb == num_k) { pkb = 0; pt += gridDim.x; }
+          }
+        };
+        for (int i = 0; i < PF_DIST; ++i) prefetch_next();
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
+          for (int kb = 0; kb < num_k; ++kb) {
+            prefetch_next();
+            load_chunk(t, kb);
+          }
+      } else {
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
+          for (int kb = 0; kb < num_k; ++kb) load_chunk(t, kb);
       }
     }
   } else if (warp == 1) {
@@ -190,15 +215,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ===== transform + epilogue warps (2..5) =====================================================================
-    const int tw = warp - 2;                 // 0..TW-1
+    // ===== transform warps (2 .. 2+TW-1) and epilogue warps (the same ones, or with SPLIT the four after them) ==========
+    const int tw = warp - 2;                 // 0..TW-1 transform; TW..TW+3 epilogue-only (SPLIT)
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const bool do_transform = !SPLIT || tw < TW;
+    const bool do_epilogue = !SPLIT || tw >= TW;
+    const int part0 = SPLIT ? 0 : tw / 4, part_step = SPLIT ? 1 : TW / 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int kb = 0; kb < num_k; ++kb) {
+      for (int kb = 0; do_transform && kb < num_k; ++kb) {
         mbar_wait_all(full + stage, phase);
         float4* hi = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(stage_base + stage * STAGE_BYTES + X_BYTES);
@@ -223,6 +251,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       // ---- epilogue of this tile ---------------------------------------------------------------------------
+      if (!do_epilogue) continue;
       mbar_wait_all(acc_full + acc, acc_phase);
       tc_fence_after();
       const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
@@ -230,7 +259,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       float v[16];
 #pragma unroll
-      for (int part = tw / 4; part < BN / 16; part += TW / 4) {   // TW = 8: the two warps of a lane quarter alternate
+      for (int part = part0; part < BN / 16; part += part_step) {   // TW = 8 without SPLIT: the two warps of a lane quarter alternate
         // small terms first, then the partials (fp32 round-to-nearest adds)
         float v2[16];
         if (STACK) {
@@ -304,6 +333,7 @@ struct WgParams {
   int k_tiles;         // ceil(K / 128)
 };
 
+template <bool PF>      // PF: L2 prefetch of the X / dZ boxes PF_DIST chunks ahead (TZK_GEMM3X_PREFETCH=1), see gemm3x_kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, WgParams p) {
   TZK_DYN_SMEM(uint8_t, smem);
@@ -341,7 +371,21 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (PF) {
+        for (int c = 0; c < PF_DIST && c < num_c; ++c) {
+          const int r = (int)(row0 + (int64_t)c * WG_ROWS);
+          for (int b = 0; b < 4; ++b) tma_prefetch_2d(&map_x, jt * 128 + b * 32, r);
+          for (int b = 0; b < 2; ++b) tma_prefetch_2d(&map_dz, b * 32, r);
+        }
+      }
       for (int c = 0; c < num_c; ++c) {
+        if constexpr (PF) {
+          if (c + PF_DIST < num_c) {
+            const int r = (int)(row0 + (int64_t)(c + PF_DIST) * WG_ROWS);
+            for (int b = 0; b < 4; ++b) tma_prefetch_2d(&map_x, jt * 128 + b * 32, r);
+            for (int b = 0; b < 2; ++b) tma_prefetch_2d(&map_dz, b * 32, r);
+          }
+        }
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sb = smem + stage * WG_STAGE;
         mbar_expect_tx(full + stage, WG_A + WG_B);
@@ -493,18 +537,18 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 }
 }  // namespace
 
-template <int BN, bool STACK, int TW, bool RAW>
+template <int BN, bool STACK, int TW, bool RAW, bool SPLIT, bool PF>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW, SPLIT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW>), grid, 64 + 32 * TW, smem, st, mx, mh, ml, p);
+  TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW, SPLIT, PF>), grid, 64 + 32 * TW + (SPLIT ? 128 : 0), smem, st, mx, mh, ml, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -532,11 +576,20 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   const char* e = getenv("TZK_GEMM3X_STACK");     // 1: two MMAs per k-step (see gemm3x_kernel); default: three
   const char* t = getenv("TZK_GEMM3X_TW");        // 8: eight transform / epilogue warps; default: four
   const bool stack = e && e[0] == '1', tw8 = t && t[0] == '8';
-#define TZK_G3R(BN_, S_, T_) (raw ? launch<BN_, S_, T_, true>(mx, mh, ml, p, st) : launch<BN_, S_, T_, false>(mx, mh, ml, p, st))
+  const char* sp = getenv("TZK_GEMM3X_SPLIT");    // 1: dedicated epilogue warps (see gemm3x_kernel); default: shared
+  const bool split = sp && sp[0] == '1';
+  const char* pfe = getenv("TZK_GEMM3X_PREFETCH");   // 1: L2 prefetch of the X boxes ahead of the loads (stacked variant only)
+  const bool pf = pfe && pfe[0] == '1' && stack;
+#define TZK_G3P(BN_, S_, T_, R_, SP_) ((S_ && pf) ? launch<BN_, S_, T_, R_, SP_, S_>(mx, mh, ml, p, st) \
+                                                 : launch<BN_, S_, T_, R_, SP_, false>(mx, mh, ml, p, st))
+#define TZK_G3S(BN_, S_, T_, R_) (split ? TZK_G3P(BN_, S_, T_, R_, true) : TZK_G3P(BN_, S_, T_, R_, false))
+#define TZK_G3R(BN_, S_, T_) (raw ? TZK_G3S(BN_, S_, T_, true) : TZK_G3S(BN_, S_, T_, false))
 #define TZK_G3(BN_) (stack ? (tw8 ? TZK_G3R(BN_, true, 8) : TZK_G3R(BN_, true, 4)) \
                            : (tw8 ? TZK_G3R(BN_, false, 8) : TZK_G3R(BN_, false, 4)))
   return BN == 64 ? TZK_G3(64) : TZK_G3(112);
 #undef TZK_G3R
+#undef TZK_G3S
+#undef TZK_G3P
 #undef TZK_G3
 }
 
@@ -559,9 +612,12 @@ extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_
   const int used = (int)((M + p.slab_rows - 1) / p.slab_rows);           // slabs that hold rows (<= slabs)
   const size_t smem = (size_t)WG_STAGES * WG_STAGE + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(wgrad3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(wgrad3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(wgrad3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  TZK_LAUNCH((wgrad3x_kernel), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
+  const char* pfe = getenv("TZK_GEMM3X_PREFETCH");
+  if (pfe && pfe[0] == '1') TZK_LAUNCH((wgrad3x_kernel<true>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
+  else TZK_LAUNCH((wgrad3x_kernel<false>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
   TZK_LAUNCH((wgrad_reduce_kernel), (K * 64 + 255) / 256, 256, 0, st, partial, used, p.k_tiles * 128, K, dw, ld_dw);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
