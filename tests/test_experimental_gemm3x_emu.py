@@ -71,11 +71,9 @@ def _p(a):
 TOL = 2e-5
 
 
-@pytest.fixture(params=[("0", "4", "0", "0", "0"), ("1", "4", "0", "0", "0"), ("0", "8", "0", "0", "0"), ("1", "8", "0", "0", "0"),
-                        ("0", "4", "1", "0", "0"), ("1", "8", "1", "0", "0"), ("1", "4", "0", "1", "0"), ("0", "8", "1", "1", "0"),
+@pytest.fixture(params=[("0", "4", "0", "0", "0"), ("1", "4", "0", "0", "0"), ("1", "8", "1", "0", "0"), ("0", "8", "0", "1", "0"),
                         ("1", "4", "1", "1", "1")],
-                ids=["3mma", "stacked", "3mma-tw8", "stacked-tw8", "3mma-raw", "stacked-tw8-raw", "stacked-split",
-                     "3mma-tw8-raw-split", "stacked-raw-split-prefetch"])
+                ids=["3mma", "stacked", "stacked-tw8-raw", "3mma-tw8-split", "stacked-raw-split-prefetch"])
 def stack(request, monkeypatch):
     """TZK_GEMM3X_STACK=1: hi(x) * [W_hi ; W_lo] as one N = 2*BN MMA + lo(x) * W_hi, halves added in the epilogue.
     TZK_GEMM3X_TW=8: eight transform / epilogue warps (two per TMEM lane quarter) instead of four.

@@ -540,12 +540,16 @@ __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __
 template <int BN, bool STACK, int TW, bool RAW, bool SPLIT, bool PF>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t st) {
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 256;
+  static int sms = 0;                 // once per instantiation: nothing but the launch happens inside a stream capture
+  if (sms == 0) {
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW, SPLIT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gemm3x_kernel<BN, STACK, TW, RAW, SPLIT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms = n > 0 ? n : 148;
+  }
   const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
   TZK_LAUNCH((gemm3x_kernel<BN, STACK, TW, RAW, SPLIT, PF>), grid, 64 + 32 * TW + (SPLIT ? 128 : 0), smem, st, mx, mh, ml, p);
@@ -612,8 +616,12 @@ extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_
   const int used = (int)((M + p.slab_rows - 1) / p.slab_rows);           // slabs that hold rows (<= slabs)
   const size_t smem = (size_t)WG_STAGES * WG_STAGE + 256;
 #ifndef TZK_CPU_SHIM
-  cudaFuncSetAttribute(wgrad3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(wgrad3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool configured = false;     // once: nothing but the launches happens inside a stream capture
+  if (!configured) {
+    cudaFuncSetAttribute(wgrad3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(wgrad3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
 #endif
   const char* pfe = getenv("TZK_GEMM3X_PREFETCH");
   if (pfe && pfe[0] == '1') TZK_LAUNCH((wgrad3x_kernel<true>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
