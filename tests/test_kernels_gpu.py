@@ -602,7 +602,7 @@ def test_gemm3x_kernels_match_fp64(monkeypatch, M, stack):
         assert torch.equal(dw, G.wgrad3x(lib, x, dzs))
 
 
-@pytest.mark.skipif(os.environ.get("TZK_TEST_GEMM3X_GLUE", "0") != "1",
+@pytest.mark.skipif(os.environ.get("TZK_TEST_GEMM3X_GLUE", "1") != "1",
                     reason="autograd glue of TZK_GEMM3X=1 (dense_gemm.Gemm3xLinearFn): covered on the CPU through the "
                            "emulated kernels; its first run on hardware is opted into with TZK_TEST_GEMM3X_GLUE=1")
 @pytest.mark.parametrize("M", [300, 65536 + 5])
