@@ -11,7 +11,8 @@
  *                TZK_GEMM3X_STACK=1 selects the two-MMA-per-k-step variant, TZK_GEMM3X_TW=8 eight transform /
  *                epilogue warps instead of four, TZK_GEMM3X_RAW=1 the raw fp32 tensors as hi operands,
  *                TZK_GEMM3X_SPLIT=1 four dedicated epilogue warps, TZK_GEMM3X_PREFETCH=1 (with STACK) L2 prefetch of
- *                the x boxes 12 chunks ahead of the loads.
+ *                the x boxes 12 chunks ahead of the loads, TZK_GEMM3X_RING=1 the ring kernel (x in a ring of its own,
+ *                used in place as the hi operand; implies RAW / STACK / dedicated epilogue warps).
  *   tzk_wgrad3x  dw[64,K] = dz[M,64]^T @ x[M,K], reduction over the batch split into `slabs` row slabs whose partial
  *                results (scratch `partial`, tzk_wgrad3x_partial_floats(K, slabs) floats) are added in a fixed order:
  *                bit-repeatable.

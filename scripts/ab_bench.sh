@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of environment switches on the headline step, one bench.py run per setting, results in gpurun_out/ab/.
 #
-#   gpurun --timeout 900 -- 'bash scripts/ab_bench.sh "" TZK_SMALL_LINEAR_BWD=1 TZK_GEMM3X=1 "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1" "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1 TZK_GEMM3X_TW=8" "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1 TZK_GEMM3X_SPLIT=1" "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1 TZK_GEMM3X_SPLIT=1 TZK_GEMM3X_RAW=1 TZK_GEMM3X_PREFETCH=1" TZK_L2_PERSIST=1'
+#   gpurun --timeout 900 -- 'bash scripts/ab_bench.sh "" TZK_SMALL_LINEAR_BWD=1 TZK_GEMM3X=1 "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1" "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1 TZK_GEMM3X_TW=8" "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1 TZK_GEMM3X_SPLIT=1" "TZK_GEMM3X=1 TZK_GEMM3X_STACK=1 TZK_GEMM3X_SPLIT=1 TZK_GEMM3X_RAW=1 TZK_GEMM3X_PREFETCH=1" "TZK_GEMM3X=1 TZK_GEMM3X_RING=1 TZK_GEMM3X_PREFETCH=1" TZK_L2_PERSIST=1'
 #
 # Each argument is a (possibly empty) space-separated list of VAR=value; "" is the baseline.  Prints one line per
 # setting: ms/step (inputs resident), e2e ms/step, fused_bwd apply µs.  Extras / CPU baseline / Zipf are skipped.

@@ -41,11 +41,13 @@ def gemm(L, M, K, N, relu, bias, tag):
     ref = torch.relu(ref) if relu else ref
     f32 = torch.nn.functional.linear(x, w, b)
     f32 = ((torch.relu(f32) if relu else f32).double() - ref).abs().max().item()
-    for stack, tw, raw, split, pf in (("0", "4", "0", "0", "0"), ("1", "4", "0", "0", "0"), ("1", "8", "0", "0", "0"),
-                                      ("1", "4", "1", "0", "0"), ("1", "4", "0", "1", "0"), ("1", "4", "0", "0", "1"),
-                                      ("1", "4", "1", "1", "1"), ("1", "8", "1", "1", "1")):
+    for stack, tw, raw, split, pf, ring in (("0", "4", "0", "0", "0", "0"), ("1", "4", "0", "0", "0", "0"),
+                                            ("1", "8", "0", "0", "0", "0"), ("1", "4", "1", "0", "0", "0"),
+                                            ("1", "4", "0", "1", "0", "0"), ("1", "4", "0", "0", "1", "0"),
+                                            ("1", "4", "1", "1", "1", "0"), ("1", "8", "1", "1", "1", "0"),
+                                            ("1", "4", "1", "1", "0", "1"), ("1", "4", "1", "1", "1", "1")):
         for var, val in zip(("TZK_GEMM3X_STACK", "TZK_GEMM3X_TW", "TZK_GEMM3X_RAW", "TZK_GEMM3X_SPLIT",
-                             "TZK_GEMM3X_PREFETCH"), (stack, tw, raw, split, pf)):
+                             "TZK_GEMM3X_PREFETCH", "TZK_GEMM3X_RING"), (stack, tw, raw, split, pf, ring)):
             os.environ[var] = val
 
         def run():
@@ -57,7 +59,7 @@ def gemm(L, M, K, N, relu, bias, tag):
         run()
         torch.cuda.synchronize()
         err = (y.double() - ref).abs().max().item()
-        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}{' raw' if raw == '1' else ''}{' split' if split == '1' else ''}{' pf' if pf == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), "
+        print(f"{tag} M={M} {'stacked' if stack == '1' else '3-mma  '} tw{tw}{' raw' if raw == '1' else ''}{' split' if split == '1' else ''}{' pf' if pf == '1' else ''}{' RING' if ring == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), "
               f"{timed(run):.1f} us", flush=True)
 
 
@@ -96,6 +98,7 @@ def main():
     gemm(L, 300, 784, 64, True, True, "fwd  ")
     gemm(L, M, 784, 64, True, True, "fwd  ")
     gemm(L, M, 64, 784, False, False, "dgrad")
+    os.environ["TZK_GEMM3X_RING"] = "0"
     os.environ["TZK_GEMM3X_PREFETCH"] = "0"
     wgrad(L, 300)
     wgrad(L, M)

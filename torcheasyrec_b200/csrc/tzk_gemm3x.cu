@@ -311,6 +311,227 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 }
 
 // ======================================================================================================================
+// Ring variant (TZK_GEMM3X_RING=1) of the forward / input-gradient kernel: the same math as gemm3x_kernel<BN, STACK = 1,
+// RAW = 1, SPLIT = 1>, but the X stream gets a ring of its own.  The first hardware numbers say the pipeline is bound
+// by latency x bytes in flight (four 48-KB stages = 64 KB of X per SM in flight); a stage holds X for the whole
+// TMA -> transform -> MMA chain although only X comes from HBM.  Here X lands in one of DX 16-KB slots and is used IN
+// PLACE as the hi operand (the tensor core truncates), while lo(X) and the two W operands live in a short work ring of
+// DW slots that turns over at the pace of transform + MMA: 6 x 16 KB of X in flight per SM instead of 4 x 16 KB in the
+// same shared memory.  Eleven warps: X producer, W producer, MMA issuer (+ TMEM), 4 transform, 4 epilogue.
+template <int BN>
+struct RingCfg {
+  static constexpr int W_BYTES = BN * BK * 4;                      // one of W_hi / W_lo per k-chunk
+  static constexpr int WORK_BYTES = X_BYTES + 2 * W_BYTES;         // lo(X) | W_hi | W_lo (contiguous: stacked B operand)
+  static constexpr int DX = BN <= 64 ? 6 : 5;
+  static constexpr int DW = 3;
+  static constexpr int P = BN <= 64 ? 2 : 1;                       // partial accumulators (see Cfg)
+  static constexpr int ACC_COLS = P * 2 * BN;
+  static constexpr int SMEM = DX * X_BYTES + DW * WORK_BYTES + 512;
+  static_assert(W_BYTES % 1024 == 0, "W operands must be whole 8-row groups");
+  static_assert(2 * ACC_COLS <= 512, "two tiles in flight must fit TMEM");
+};
+constexpr int RING_THREADS = 11 * 32;
+
+struct RingParams {
+  Params p;
+  int prefetch;        // > 0: L2 prefetch of the X boxes that many chunks ahead
+};
+
+template <int BN>
+__global__ void __launch_bounds__(RING_THREADS, 1)
+gemm3x_ring_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                   const __grid_constant__ CUtensorMap map_wlo, RingParams rp) {
+  using C = RingCfg<BN>;
+  constexpr int DX = C::DX, DW = C::DW, P = C::P, ACC_COLS = C::ACC_COLS, W_BYTES = C::W_BYTES;
+  const Params& p = rp.p;
+  TZK_DYN_SMEM(uint8_t, smem);
+  uint8_t* xring = smem;                                  // DX x 16 KB, raw fp32 = hi operand
+  uint8_t* wring = smem + DX * X_BYTES;                   // DW x (lo(X) 16 KB | W_hi | W_lo)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + DW * C::WORK_BYTES);
+  uint64_t* xfull = bars;                    // [DX] TMA X -> transform (and, through lo_ready, the MMA)
+  uint64_t* xempty = xfull + DX;             // [DX] MMA commit -> X producer
+  uint64_t* wfull = xempty + DX;             // [DW] TMA W -> MMA
+  uint64_t* lo_ready = wfull + DW;           // [DW] transform -> MMA (4 arrivals)
+  uint64_t* wempty = lo_ready + DW;          // [DW] MMA commit -> W producer and transform (lo slot free)
+  uint64_t* acc_full = wempty + DW;          // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2] (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.K / BK;
+  const int n_used = num_k < P ? num_k : P;
+  const int n_tiles = p.N / BN;
+  const int64_t num_tiles = (p.M + BM - 1) / BM * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < DX; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); }
+    for (int s = 0; s < DW; ++s) { mbar_init(wfull + s, 1); mbar_init(lo_ready + s, 4); mbar_init(wempty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
+    fence_mbarrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== X producer ==============================================================================================
+    if (lane == 0) {
+      int xs = 0;
+      uint32_t xph = 0;
+      int64_t pt = blockIdx.x;                // L2 prefetch cursor
+      int pkb = 0;
+      auto prefetch_next = [&] {
+        if (pt < num_tiles) {
+          tma_prefetch_2d(&map_x, pkb * BK, (int)(pt / n_tiles * BM));
+          if (++pkb == num_k) { pkb = 0; pt += gridDim.x; }
+        }
+      };
+      for (int i = 0; i < rp.prefetch; ++i) prefetch_next();
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
+        for (int kb = 0; kb < num_k; ++kb) {
+          if (rp.prefetch > 0) prefetch_next();
+          mbar_wait(xempty + xs, xph ^ 1);
+          mbar_expect_tx(xfull + xs, X_BYTES);
+          tma_load_2d(xring + xs * X_BYTES, &map_x, xfull + xs, kb * BK, (int)(t / n_tiles * BM));
+          if (++xs == DX) { xs = 0; xph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    // ===== W producer ==============================================================================================
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(wempty + ws, wph ^ 1);
+          uint8_t* wb = wring + ws * C::WORK_BYTES + X_BYTES;
+          mbar_expect_tx(wfull + ws, 2 * W_BYTES);
+          tma_load_2d(wb, &map_whi, wfull + ws, kb * BK, (int)(t % n_tiles) * BN);
+          tma_load_2d(wb + W_BYTES, &map_wlo, wfull + ws, kb * BK, (int)(t % n_tiles) * BN);
+          if (++ws == DW) { ws = 0; wph ^= 1; }
+        }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer ==============================================================================================
+    int xs = 0, ws = 0, acc = 0;
+    uint32_t xph = 0, wph = 0, acc_phase = 0;
+    (void)xph;
+    constexpr uint32_t idesc = make_idesc<BN>();
+    constexpr uint32_t idesc2 = make_idesc<2 * BN>();
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait_all(acc_empty + acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      uint32_t started = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait_all(lo_ready + ws, wph);       // lo(X) written => X landed (the transform waited for it)
+        mbar_wait_all(wfull + ws, wph);          // W_hi / W_lo landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(xring + xs * X_BYTES);
+          const uint32_t a_lo = smem_u32(wring + ws * C::WORK_BYTES), b_hi = a_lo + X_BYTES;
+          const int part = kb * n_used / num_k;
+          const uint32_t region = d_tmem + part * 2 * BN;       // [hi*hi | hi*lo + lo*hi]
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint32_t ko = k * UK * 4;
+            mma_tf32(region, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc2, (started >> part) & 1u);
+            mma_tf32(region + BN, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1u);
+            started |= 1u << part;
+          }
+          tc_commit(xempty + xs);
+          tc_commit(wempty + ws);
+          if (kb == num_k - 1) tc_commit(acc_full + acc);
+        }
+        __syncwarp();
+        if (++xs == DX) { xs = 0; xph ^= 1; }
+        if (++ws == DW) { ws = 0; wph ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp < 7) {
+    // ===== transform warps (3..6): lo(X) = rna(x - trunc(x)) into the work ring =====================================
+    const int tw = warp - 3;
+    int xs = 0, ws = 0;
+    uint32_t xph = 0, wph = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait_all(xfull + xs, xph);
+        mbar_wait_all(wempty + ws, wph ^ 1);      // the lo slot (and its W) of DW chunks ago has been consumed
+        const float4* hi = reinterpret_cast<const float4*>(xring + xs * X_BYTES);
+        float4* lo = reinterpret_cast<float4*>(wring + ws * C::WORK_BYTES);
+#pragma unroll
+        for (int q = 0; q < X_BYTES / 16 / 128; ++q) {
+          const int i = q * 128 + tw * 32 + lane;
+          const float4 x = hi[i];
+          float4 l;
+          l.x = tf32_rna(x.x - tf32_trunc(x.x)); l.y = tf32_rna(x.y - tf32_trunc(x.y));
+          l.z = tf32_rna(x.z - tf32_trunc(x.z)); l.w = tf32_rna(x.w - tf32_trunc(x.w));
+          lo[i] = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lo_ready + ws);
+        if (++xs == DX) { xs = 0; xph ^= 1; }
+        if (++ws == DW) { ws = 0; wph ^= 1; }
+      }
+  } else {
+    // ===== epilogue warps (7..10) =====================================================================================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait_all(acc_full + acc, acc_phase);
+      tc_fence_after();
+      const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
+      const int col0 = (int)(t % n_tiles) * BN;
+      const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      float v[16], v2[16];
+#pragma unroll
+      for (int part = 0; part < BN / 16; ++part) {
+        tmem_ld16(taddr + BN + part * 16, v);                 // small terms first, then the partials
+        for (int q = 1; q < n_used; ++q) {
+          tmem_ld16(taddr + q * 2 * BN + BN + part * 16, v2);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] += v2[c];
+        }
+        for (int q = 0; q < n_used; ++q) {
+          tmem_ld16(taddr + q * 2 * BN + part * 16, v2);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] += v2[c];
+        }
+        if (row < p.M) {
+          float* yr = p.y + row * p.ld_y + col0 + part * 16;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            float4 o;
+            o.x = v[c] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c) : 0.f);
+            o.y = v[c + 1] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 1) : 0.f);
+            o.z = v[c + 2] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 2) : 0.f);
+            o.w = v[c + 3] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 3) : 0.f);
+            if (p.relu) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(yr + c) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_free(tmem_base, 512);
+}
+
+// ======================================================================================================================
 // Weight gradient of the same layer:  dW[n, k] = sum_m dZ[m, n] * X[m, k]   (n < 64, k < K = 784, m < M = batch).
 // The reduction runs over the batch, so both operands are MN-major as they lie in memory: A = X^T (UMMA M = 128 of
 // X's columns), B = dZ^T (UMMA N = 64) — for 32-bit elements that means the SWIZZLE_128B_BASE32B shared-memory layout
@@ -556,6 +777,28 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMa
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
+template <int BN>
+static int launch_ring(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, int prefetch,
+                       cudaStream_t st) {
+  static int sms = 0;
+  if (sms == 0) {
+#ifndef TZK_CPU_SHIM
+    cudaFuncSetAttribute(gemm3x_ring_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<BN>::SMEM);
+#endif
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms = n > 0 ? n : 148;
+  }
+  RingParams rp;
+  rp.p = p;
+  rp.prefetch = prefetch;
+  const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  TZK_LAUNCH((gemm3x_ring_kernel<BN>), grid, RING_THREADS, (size_t)RingCfg<BN>::SMEM, st, mx, mh, ml, rp);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
 // y[M,N] = act(x[M,K] @ w[N,K]^T + bias) with fp32-equivalent accuracy (3xTF32).  N = 64 (forward of the wide tower
 // layer, K = 784) or a multiple of 112 (its input gradient: x = dZ [M,64], w = W^T [784,64], no bias / ReLU).
 // Rows 16-B aligned, ld % 4 == 0; K columns beyond the tensor are read as zeros up to the next multiple of 32.
@@ -569,7 +812,9 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   const int BN = N == 64 ? 64 : 112;
   const int64_t nw = (int64_t)N * ld_w;
   const char* r = getenv("TZK_GEMM3X_RAW");       // 1: raw fp32 as the hi operands (see gemm3x_kernel); default: rounded split
-  const bool raw = r && r[0] == '1';
+  const char* rg = getenv("TZK_GEMM3X_RING");     // 1: gemm3x_ring_kernel (implies RAW, STACK, dedicated epilogue warps)
+  const bool ring = rg && rg[0] == '1';
+  const bool raw = (r && r[0] == '1') || ring;
   if (raw) TZK_LAUNCH((split_w_raw_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_lo);
   else TZK_LAUNCH((split_w_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_hi, w_lo);
   CUtensorMap mx, mh, ml;
@@ -577,6 +822,11 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
     return 2;
   Params p;
   p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.N = N; p.relu = relu;
+  if (ring) {
+    const char* pfr = getenv("TZK_GEMM3X_PREFETCH");
+    const int pfd = (pfr && pfr[0] == '1') ? PF_DIST : 0;
+    return BN == 64 ? launch_ring<64>(mx, mh, ml, p, pfd, st) : launch_ring<112>(mx, mh, ml, p, pfd, st);
+  }
   const char* e = getenv("TZK_GEMM3X_STACK");     // 1: two MMAs per k-step (see gemm3x_kernel); default: three
   const char* t = getenv("TZK_GEMM3X_TW");        // 8: eight transform / epilogue warps; default: four
   const bool stack = e && e[0] == '1', tw8 = t && t[0] == '8';
