@@ -83,7 +83,7 @@ def wgrad(L, M, K=784, slabs=21):
     first = dw.clone()
     run()
     torch.cuda.synchronize()
-    print(f"wgrad M={M}{' pf' if os.environ.get('TZK_GEMM3X_PREFETCH') == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), repeatable {torch.equal(first, dw)}, "
+    print(f"wgrad M={M}{' pf' if os.environ.get('TZK_GEMM3X_PREFETCH') == '1' else ''}{' RING' if os.environ.get('TZK_GEMM3X_RING') == '1' else ''}: max err {err:.2e} (torch fp32 {f32:.2e}), repeatable {torch.equal(first, dw)}, "
           f"{timed(run):.1f} us", flush=True)
 
 
@@ -103,6 +103,11 @@ def main():
     wgrad(L, 300)
     wgrad(L, M)
     os.environ["TZK_GEMM3X_PREFETCH"] = "1"
+    wgrad(L, M)
+    os.environ["TZK_GEMM3X_RING"] = "1"
+    wgrad(L, 300)
+    wgrad(L, M)
+    os.environ["TZK_GEMM3X_PREFETCH"] = "0"
     wgrad(L, M)
     print(f"done in {time.time() - t0:.1f} s", flush=True)
 

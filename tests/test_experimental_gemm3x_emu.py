@@ -132,11 +132,13 @@ def test_dgrad_64_to_784(request, lib, stack):
     np.testing.assert_allclose(dx, dz.astype(np.float64) @ wt.astype(np.float64).T, rtol=0, atol=TOL)
 
 
-@pytest.mark.parametrize("M,slabs,prefetch", [(200, 2, "0"), (70, 3, "0"), (31, 1, "0"), (520, 1, "1")])
-def test_wgrad_mn_major(request, lib, monkeypatch, M, slabs, prefetch):
+@pytest.mark.parametrize("M,slabs,prefetch,ring", [(200, 2, "0", "0"), (70, 3, "0", "0"), (31, 1, "0", "0"), (520, 1, "1", "0"),
+                                                   (200, 2, "0", "1"), (520, 1, "1", "1"), (31, 1, "0", "1")])
+def test_wgrad_mn_major(request, lib, monkeypatch, M, slabs, prefetch, ring):
     """dW = dZ^T X with both operands MN-major straight from the row-major tensors; row slabs (the last one short or
     empty), 7 column tiles (the last one 16 of 128 columns), fixed-order slab reduction + transpose."""
     monkeypatch.setenv("TZK_GEMM3X_PREFETCH", prefetch)   # "1": 17 chunks per CTA > the 12-chunk prefetch distance
+    monkeypatch.setenv("TZK_GEMM3X_RING", ring)           # "1": wgrad3x_ring_kernel (X ring + work ring, raw hi operands)
     if _delegate(request, lib):
         return
     rng = np.random.default_rng(M + slabs)

@@ -697,6 +697,166 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (warp == 1) tmem_free(tmem_base, 512);
 }
 
+// Ring variant of the weight-gradient kernel (TZK_GEMM3X_RING=1), same idea as gemm3x_ring_kernel: the X boxes (the
+// only HBM stream) land in a ring of WG_DX 16-KB slots and are used in place as the hi operand; lo(X), the dZ boxes (raw
+// = hi) and lo(dZ) turn over in a work ring of WG_DW 32-KB slots.  Seven warps: X producer, dZ producer, MMA issuer,
+// four transform warps that also drain the accumulators at the end (one work item per CTA).
+constexpr int WG_DX = 6, WG_DW = 3;
+constexpr int WG_WORK = WG_A + 2 * WG_B;                 // lo(X) 16 KB | dZ raw 8 KB | lo(dZ) 8 KB
+constexpr int WG_RING_SMEM = WG_DX * WG_A + WG_DW * WG_WORK + 512;
+constexpr int WG_RING_THREADS = 7 * 32;
+
+__global__ void __launch_bounds__(WG_RING_THREADS, 1)
+wgrad3x_ring_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, WgParams p,
+                    int prefetch) {
+  TZK_DYN_SMEM(uint8_t, smem);
+  uint8_t* xring = smem;
+  uint8_t* wring = smem + WG_DX * WG_A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + WG_DW * WG_WORK);
+  uint64_t* xfull = bars;                   // [DX] TMA X -> transform
+  uint64_t* xempty = xfull + WG_DX;         // [DX] MMA commit -> X producer
+  uint64_t* wfull = xempty + WG_DX;         // [DW] TMA dZ -> transform
+  uint64_t* lo_ready = wfull + WG_DW;       // [DW] transform -> MMA (4 arrivals)
+  uint64_t* wempty = lo_ready + WG_DW;      // [DW] MMA commit -> dZ producer, transform
+  uint64_t* acc_full = wempty + WG_DW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x % p.k_tiles;
+  const int64_t slab = blockIdx.x / p.k_tiles;
+  const int64_t row0 = slab * p.slab_rows;
+  const int64_t rows = (p.M - row0 < p.slab_rows) ? p.M - row0 : p.slab_rows;
+  const int num_c = (int)((rows + WG_ROWS - 1) / WG_ROWS);
+  const int n_used = num_c < WG_P ? num_c : WG_P;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < WG_DX; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); }
+    for (int s = 0; s < WG_DW; ++s) { mbar_init(wfull + s, 1); mbar_init(lo_ready + s, 4); mbar_init(wempty + s, 1); }
+    mbar_init(acc_full, 1);
+    fence_mbarrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                          // ---- X producer
+      int xs = 0;
+      uint32_t xph = 0;
+      for (int c = 0; c < prefetch && c < num_c; ++c)
+        for (int b = 0; b < 4; ++b) tma_prefetch_2d(&map_x, jt * 128 + b * 32, (int)(row0 + (int64_t)c * WG_ROWS));
+      for (int c = 0; c < num_c; ++c) {
+        if (prefetch > 0 && c + prefetch < num_c)
+          for (int b = 0; b < 4; ++b)
+            tma_prefetch_2d(&map_x, jt * 128 + b * 32, (int)(row0 + (int64_t)(c + prefetch) * WG_ROWS));
+        mbar_wait(xempty + xs, xph ^ 1);
+        mbar_expect_tx(xfull + xs, WG_A);
+        const int r = (int)(row0 + (int64_t)c * WG_ROWS);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(xring + xs * WG_A + b * WG_BOX, &map_x, xfull + xs, jt * 128 + b * 32, r);
+        if (++xs == WG_DX) { xs = 0; xph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                          // ---- dZ producer
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int c = 0; c < num_c; ++c) {
+        mbar_wait(wempty + ws, wph ^ 1);
+        mbar_expect_tx(wfull + ws, WG_B);
+        const int r = (int)(row0 + (int64_t)c * WG_ROWS);
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+          tma_load_2d(wring + ws * WG_WORK + WG_A + b * WG_BOX, &map_dz, wfull + ws, b * 32, r);
+        if (++ws == WG_DW) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {                     // ---- MMA issuer
+    int xs = 0, ws = 0;
+    uint32_t wph = 0;
+    constexpr uint32_t idesc = make_idesc<64, true>();
+    uint32_t started = 0;
+    for (int c = 0; c < num_c; ++c) {
+      mbar_wait_all(lo_ready + ws, wph);      // lo(X), lo(dZ) written => X and dZ landed
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(xring + xs * WG_A);
+        const uint32_t a_lo = smem_u32(wring + ws * WG_WORK), b_hi = a_lo + WG_A, b_lo = b_hi + WG_B;
+        const int part = c * n_used / num_c;
+        const uint32_t d_main = tmem_base + part * 64, d_small = tmem_base + WG_P * 64;
+#pragma unroll
+        for (int k = 0; k < WG_ROWS / UK; ++k) {
+          const uint32_t ko = k * 1024;
+          mma_tf32(d_main, make_desc_mn(a_hi + ko, WG_BOX, 512), make_desc_mn(b_hi + ko, WG_BOX, 512), idesc,
+                   (started >> part) & 1u);
+          mma_tf32(d_small, make_desc_mn(a_lo + ko, WG_BOX, 512), make_desc_mn(b_hi + ko, WG_BOX, 512), idesc,
+                   (started >> WG_P) & 1u);
+          mma_tf32(d_small, make_desc_mn(a_hi + ko, WG_BOX, 512), make_desc_mn(b_lo + ko, WG_BOX, 512), idesc, 1u);
+          started |= (1u << part) | (1u << WG_P);
+        }
+        tc_commit(xempty + xs);
+        tc_commit(wempty + ws);
+        if (c == num_c - 1) tc_commit(acc_full);
+      }
+      __syncwarp();
+      if (++xs == WG_DX) xs = 0;
+      if (++ws == WG_DW) { ws = 0; wph ^= 1; }
+    }
+  } else {                                    // ---- transform warps (3..6), then the epilogue
+    const int tw = warp - 3, quarter = warp & 3;
+    int xs = 0, ws = 0;
+    uint32_t xph = 0, wph = 0;
+    for (int c = 0; c < num_c; ++c) {
+      mbar_wait_all(xfull + xs, xph);
+      mbar_wait_all(wfull + ws, wph);           // dZ landed in this work slot (its producer waited for wempty)
+      const float4* ax = reinterpret_cast<const float4*>(xring + xs * WG_A);
+      uint8_t* wb = wring + ws * WG_WORK;
+      float4* alo = reinterpret_cast<float4*>(wb);
+      const float4* bx = reinterpret_cast<const float4*>(wb + WG_A);
+      float4* blo = reinterpret_cast<float4*>(wb + WG_A + WG_B);
+#pragma unroll
+      for (int q = 0; q < (WG_A + WG_B) / 16 / 128; ++q) {
+        const int i = q * 128 + tw * 32 + lane;                       // 0..1535: X part, then dZ part
+        const bool in_a = i < WG_A / 16;
+        const float4 x = in_a ? ax[i] : bx[i - WG_A / 16];
+        float4 l;
+        l.x = tf32_rna(x.x - tf32_trunc(x.x)); l.y = tf32_rna(x.y - tf32_trunc(x.y));
+        l.z = tf32_rna(x.z - tf32_trunc(x.z)); l.w = tf32_rna(x.w - tf32_trunc(x.w));
+        if (in_a) alo[i] = l;
+        else blo[i - WG_A / 16] = l;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(lo_ready + ws);
+      if (++xs == WG_DX) { xs = 0; xph ^= 1; }
+      if (++ws == WG_DW) { ws = 0; wph ^= 1; }
+    }
+    mbar_wait_all(acc_full, 0);
+    tc_fence_after();
+    const int krow = jt * 128 + quarter * 32 + lane;
+    float* out = p.partial + ((int64_t)slab * p.k_tiles * 128 + krow) * 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float v[16], v2[16];
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      tmem_ld16(taddr + WG_P * 64 + part * 16, v);
+      for (int q = 0; q < n_used; ++q) {
+        tmem_ld16(taddr + q * 64 + part * 16, v2);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] += v2[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        *reinterpret_cast<float4*>(out + part * 16 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_free(tmem_base, 512);
+}
+
 // dW[n, k] = sum over slabs (fixed order) of partial[s, k, n]; one thread per (k, n), n fastest for the reads
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slabs, int k_pad, int K, float* __restrict__ dw,
                                     int64_t ld_dw) {
@@ -874,7 +1034,18 @@ extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_
   }
 #endif
   const char* pfe = getenv("TZK_GEMM3X_PREFETCH");
-  if (pfe && pfe[0] == '1') TZK_LAUNCH((wgrad3x_kernel<true>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
+  const char* rg = getenv("TZK_GEMM3X_RING");
+  if (rg && rg[0] == '1') {
+#ifndef TZK_CPU_SHIM
+    static bool ring_configured = false;
+    if (!ring_configured) {
+      cudaFuncSetAttribute(wgrad3x_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_RING_SMEM);
+      ring_configured = true;
+    }
+#endif
+    TZK_LAUNCH((wgrad3x_ring_kernel), used * p.k_tiles, WG_RING_THREADS, (size_t)WG_RING_SMEM, st, mx, mz, p,
+               (pfe && pfe[0] == '1') ? PF_DIST : 0);
+  } else if (pfe && pfe[0] == '1') TZK_LAUNCH((wgrad3x_kernel<true>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
   else TZK_LAUNCH((wgrad3x_kernel<false>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
   TZK_LAUNCH((wgrad_reduce_kernel), (K * 64 + 255) / 256, 256, 0, st, partial, used, p.k_tiles * 128, K, dw, ld_dw);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
