@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--sharded-mode", default="graph", choices=["graph", "eager"],
                     help="N>1: 'graph' = static-capacity exchange captured in one CUDA graph, 'eager' = dynamic splits")
     ap.add_argument("--static-capacity", type=float, default=1.5)
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="sharded runs: NCCL all-to-alls, or the peer-memory kernels of csrc/tzk_peer.cu")
     ap.add_argument("--force-sharded", action="store_true",
                     help="N=1 only: still go through bucketize / all-to-all / owner gather (1-rank process group)")
     return ap.parse_args()
@@ -210,7 +212,8 @@ def run_ours(args):
     graphed = world == 1 or args.sharded_mode == "graph"
     pipe = Pipeline(args.model, device=dev, max_rows=args.max_rows or None,
                     sharding="row_wise" if sharded else None,
-                    static_capacity=args.static_capacity if (sharded and graphed) else None)
+                    static_capacity=args.static_capacity if (sharded and graphed) else None,
+                    exchange=args.exchange if (sharded and graphed) else "nccl")
     host = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + i, id_dist=args.id_dist).pin_memory()
             for i in range(args.ring)]
     ring = [hb.to(dev) for hb in host]
@@ -514,7 +517,9 @@ def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step,
                    "l2": f"inputs rotate over {ring_len} distinct batches; tables 12.2 GiB + state 12.2 GiB >> 126 MB L2",
                    "cuda_graph": bool(args.sharded_mode == "graph" or world == 1),
                    "exchange": ("none" if (world == 1 and not args.force_sharded) else
-                                (f"static capacity {args.static_capacity}x, in-graph NCCL all-to-all"
+                                (f"static capacity {args.static_capacity}x, " + ("peer-memory kernels over NVLink, no collective"
+                                                                                  if args.exchange == "peer" else
+                                                                                  "in-graph NCCL all-to-all")
                                  if args.sharded_mode == "graph" else "dynamic splits (host read per step)"))},
         "e2e": {"value": global_batch * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last},

@@ -73,6 +73,10 @@ int tzk_abi_version(void);
 const char* tzk_last_error(void);
 /* number of SMs of the current device (used by callers to size persistent grids); <0 on error */
 int tzk_sm_count(void);
+/* L2 residency hint (cudaStreamAttributeAccessPolicyWindow on `stream`, persisting hits / streaming misses) for a
+ * buffer written by one kernel and gathered at random by the next; bytes == 0 clears the window; hit_ratio <= 0 picks
+ * persisting carve-out / bytes.  No reference counterpart (fbgemm TBE has no such hint). */
+int tzk_l2_persist(const void* base, size_t bytes, float hit_ratio, tzk_stream_t stream);
 
 /* ---- K3: lengths -> offsets  ([EXT] fbgemm::asynchronous_complete_cumsum, implicit in every
  * KeyedJaggedTensor.offsets(); reached from tzrec/modules/embedding.py:930) -------------------------
@@ -269,6 +273,31 @@ int tzk_small_linear_bwd(const float* x, int64_t ld_x, const float* w, const flo
 size_t tzk_bce_logits_workspace_bytes(int64_t M);
 int tzk_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t M, float* loss, float* dlogits,
                            void* workspace, size_t workspace_bytes, tzk_stream_t stream);
+
+/* ---- sharded sparse step over peer memory (NVSwitch domain; replaces the KJT / pooled-embedding all-to-alls of
+ * torchrec's ShardedEmbeddingBagCollection, SURVEY.md §8 A3 / App. A.4, tzrec/main.py:799).  `*_ptrs` are HOST arrays
+ * [W] of device addresses: rank r's symmetric buffer as mapped in the calling process.
+ *   peer_pooled_gather_fwd : the requester's gather reads each row from the owning rank's arena (owner = feat_owner +
+ *                            id / feat_block, as tzk_bucketize_rw) and pools locally; rf_w_off[r * F + f] = arena
+ *                            offset (elements) of feature f's table on rank r; other arrays as tzk_pooled_gather_fwd.
+ *   peer_barrier           : one CTA; flag[src] on every rank = epoch, st.release.sys / ld.acquire.sys; `epoch` is a
+ *                            device counter (graph-replayable).  Every rank must call it the same number of times.
+ *   peer_pull_counts       : recv_counts[src, f] = counts_src[me, f].
+ *   peer_pull              : slot s = (src, j) of the fixed-capacity wire layout: recv_ids[s] = src's id for me,
+ *                            recv_g[s, :] = src's gradient slice [b, col_f : col_f + D] (position = f * B + b, one id
+ *                            per bag); slots at or beyond bounds[src * (F + 1) + F] get id 0 and a zero row.
+ * Return 0, or 1 bad argument / 3 launch failure. */
+int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
+                               const int64_t* feat_block, const int32_t* feat_owner, const int32_t* feat_dim,
+                               const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
+                               const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim, float* out,
+                               int64_t ld_out, tzk_stream_t stream);
+int tzk_peer_barrier(const uint64_t* pad_ptrs, int32_t me, int32_t W, uint32_t* epoch, tzk_stream_t stream);
+int tzk_peer_pull_counts(const uint64_t* counts_ptrs, int32_t me, int32_t W, int32_t F, int32_t* recv_counts,
+                         tzk_stream_t stream);
+int tzk_peer_pull(const uint64_t* ids_ptrs, const uint64_t* pos_ptrs, const uint64_t* grad_ptrs, int32_t me, int32_t W,
+                  int32_t cap, int32_t F, int32_t B, int32_t D, const int32_t* feat_col, const int64_t* bounds,
+                  int64_t ld_grad, int64_t* recv_ids, float* recv_g, tzk_stream_t stream);
 
 #ifdef __cplusplus
 }

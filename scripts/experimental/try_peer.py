@@ -29,7 +29,7 @@ def main() -> None:
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
 
-    from peer_exchange import enable_peer_exchange
+    from torcheasyrec_b200.peer_exchange import enable_peer_exchange
 
     from torcheasyrec_b200.distributed import DenseGradSync, shard_model
     from torcheasyrec_b200.engine import Pipeline

@@ -50,7 +50,7 @@ def _concat_batches(batches):
 
 
 def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=False, static_capacity=None,
-            sparse_opt=None):
+            sparse_opt=None, exchange="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dev = f"cuda:{rank}" if use_cuda else "cpu"
     if use_cuda:
@@ -75,7 +75,7 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
             shd = Pipeline(name, device=dev, max_rows=300, seed=5, capturable=False)
             shd.model.load_state_dict(ref.model.state_dict())
             sharded = shard_model(shd.model, dev, default=sharding, rw_min_rows=rw_min_rows, source=ref.model,
-                                  static_capacity=static_capacity)
+                                  static_capacity=static_capacity, exchange=exchange)
             if sparse_opt is not None:     # e.g. "adam": second state + device-side step counter on every shard
                 from torcheasyrec_b200.embedding_modules import SparseOptimizerSpec
 
@@ -135,12 +135,12 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
         dist.destroy_process_group()
 
 
-def _run(world, name, sharding, rw_min_rows=0, use_cuda=False, static_capacity=None, sparse_opt=None):
+def _run(world, name, sharding, rw_min_rows=0, use_cuda=False, static_capacity=None, sparse_opt=None, exchange="nccl"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, name, sharding, rw_min_rows, q, use_cuda, static_capacity,
-                                               sparse_opt))
+                                               sparse_opt, exchange))
              for r in range(world)]
     for p in procs:
         p.start()

@@ -24,3 +24,12 @@ def test_deepfm_mixed_two_gpus():
 @need2
 def test_din_sequence_two_gpus():
     _run(2, "multi_tower_din_taobao", "mixed", rw_min_rows=250, use_cuda=True)
+
+
+@need2
+@pytest.mark.parametrize("sharding", ["row_wise", "mixed"])
+def test_dlrm_two_gpus_peer_memory(sharding):
+    """exchange="peer": requester-side gather over NVLink, owner-side pull, barrier kernels — same checks against the
+    unsharded twin as the NCCL path (logits, loss, updated tables, dense weights)."""
+    _run(2, "dlrm_criteo", sharding, rw_min_rows=200 if sharding == "mixed" else 0, use_cuda=True, static_capacity=2.5,
+         exchange="peer")

@@ -438,10 +438,18 @@ def test_tower_helpers_bias_act_and_relu_bwd_colsum(kernels, N):
     np.testing.assert_allclose(cs2.cpu().numpy(), dy.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
 
 
+@pytest.fixture(params=["rows", "tile"])
+def slb_path(request, monkeypatch):
+    """Both backward implementations behind tzk_small_linear_bwd: the barrier-free dx / dW kernels (default where the
+    shape is covered) and the 128-row shared-memory tile kernel (TZK_SMALL_LINEAR_BWD=1; also the fallback)."""
+    monkeypatch.setenv("TZK_SMALL_LINEAR_BWD", "1" if request.param == "tile" else "2")
+    return request.param
+
+
 @pytest.mark.parametrize("M,K,N,relu", [(1, 13, 64, True), (127, 64, 16, True), (128, 64, 32, True),
                                         (129, 32, 1, False), (1000, 3, 5, True), (4099, 64, 64, True),
-                                        (300, 17, 33, False), (2500, 40, 2, True)])
-def test_small_linear_fwd_bwd_vs_fp64_reference(kernels, M, K, N, relu):
+                                        (300, 17, 33, False), (2500, 40, 2, True), (65536 + 7, 64, 32, True)])
+def test_small_linear_fwd_bwd_vs_fp64_reference(kernels, slb_path, M, K, N, relu):
     """tzk_small_linear_{fwd,bwd} (the narrow tower layers) against a float64 restatement of
     tzrec/modules/mlp.py Perceptron: Linear -> ReLU and its autograd."""
     rng = np.random.default_rng(M * 7 + K * 3 + N)
@@ -594,7 +602,7 @@ def test_gemm3x_kernels_match_fp64(monkeypatch, M, stack):
         assert torch.equal(dw, G.wgrad3x(lib, x, dzs))
 
 
-@pytest.mark.skipif(os.environ.get("TZK_TEST_GEMM3X_GLUE", "0") != "1",
+@pytest.mark.skipif(os.environ.get("TZK_TEST_GEMM3X_GLUE", "1") != "1",
                     reason="autograd glue of TZK_GEMM3X=1 (dense_gemm.Gemm3xLinearFn): covered on the CPU through the "
                            "emulated kernels; its first run on hardware is opted into with TZK_TEST_GEMM3X_GLUE=1")
 @pytest.mark.parametrize("M", [300, 65536 + 5])

@@ -26,6 +26,7 @@ SIGNATURES = {
     "tzk_abi_version": (c_int32, []),
     "tzk_last_error": (c_char_p, []),
     "tzk_sm_count": (c_int32, []),
+    "tzk_l2_persist": (c_int32, [P, c_size_t, c_float, P]),
     "tzk_lengths_to_offsets_workspace_bytes": (c_size_t, [c_int64]),
     "tzk_lengths_to_offsets": (c_int32, [P, c_int64, P, P, c_size_t, P]),
     "tzk_pooled_gather_fwd": (
@@ -83,6 +84,11 @@ SIGNATURES = {
     ),
     "tzk_bce_logits_workspace_bytes": (c_size_t, [c_int64]),
     "tzk_bce_logits_fwd_bwd": (c_int32, [P, P, c_int64, P, P, P, c_size_t, P]),
+    "tzk_peer_pooled_gather_fwd": (
+        c_int32, [P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P]),
+    "tzk_peer_barrier": (c_int32, [P, c_int32, c_int32, P, P]),
+    "tzk_peer_pull_counts": (c_int32, [P, c_int32, c_int32, c_int32, P, P]),
+    "tzk_peer_pull": (c_int32, [P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, c_int64, P, P, P]),
     "tzk_dot_interact_bwd": (
         c_int32,
         [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, P, c_int64, P,

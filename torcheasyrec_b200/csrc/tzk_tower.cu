@@ -12,6 +12,12 @@
 
 #include "tzk_common.cuh"
 
+// second backward implementation (plain CUDA, also compiled for the host by the CPU tests)
+#define TZK_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define TZK_UNPAREN(...) __VA_ARGS__
+#define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) TZK_UNPAREN kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#include "tzk_tower_bwd2.cuh"
+
 using namespace tzk;
 
 namespace {
@@ -378,8 +384,17 @@ extern "C" int tzk_small_linear_fwd(const float* x, int64_t ld_x, const float* w
   return 0;
 }
 
+// TZK_SMALL_LINEAR_BWD=1: 128-row shared-memory tiles (small_linear_bwd_kernel); default: the barrier-free pair of
+// kernels of tzk_tower_bwd2.cuh wherever its row-group mapping covers the shape.  Read per call (tests flip it).
+static bool use_bwd2(int K, int N) {
+  const char* e = getenv("TZK_SMALL_LINEAR_BWD");
+  return !(e && e[0] == '1') && tzk_bwd2::supported(K, N);
+}
+
 extern "C" size_t tzk_small_linear_bwd_workspace_bytes(int64_t M, int32_t K, int32_t N) {
-  return (size_t)bwd_grid(M) * ((size_t)(N < 1 ? 1 : N) * (K < 1 ? 1 : K) + (N < 1 ? 1 : N)) * sizeof(float);
+  const size_t v1 = (size_t)bwd_grid(M) * ((size_t)(N < 1 ? 1 : N) * (K < 1 ? 1 : K) + (N < 1 ? 1 : N)) * sizeof(float);
+  const size_t v2 = tzk_bwd2::supported(K, N) ? tzk_bwd2::workspace_bytes(M < 1 ? 1 : M, K, N) : 0;
+  return v1 > v2 ? v1 : v2;      // either path may be selected at call time
 }
 
 extern "C" int tzk_small_linear_bwd(const float* x, int64_t ld_x, const float* w, const float* y, int64_t ld_y,
@@ -394,6 +409,12 @@ extern "C" int tzk_small_linear_bwd(const float* x, int64_t ld_x, const float* w
               "small_linear_bwd: leading dimension smaller than the row");
   TZK_REQUIRE(workspace && workspace_bytes >= tzk_small_linear_bwd_workspace_bytes(M, K, N),
               "small_linear_bwd: workspace too small");
+  if (use_bwd2(K, N)) {
+    rc = tzk_bwd2::run(x, ld_x, w, y, ld_y, dy, ld_dy, M, K, N, relu, dx, ld_dx, dw, db, workspace, workspace_bytes,
+                       as_stream(stream));
+    TZK_REQUIRE(rc == 0, "small_linear_bwd: tzk_bwd2::run failed with code %d", rc);
+    return 0;
+  }
   const int KP = pad_pow(K, 16), NP = pad_pow(N, 4);
   const int grid = bwd_grid(M);
   const size_t smem = ((size_t)N * KP + (size_t)kTM * (K | 1) + (size_t)kTM * (N | 1)) * sizeof(float);

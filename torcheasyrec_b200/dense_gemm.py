@@ -267,7 +267,7 @@ class Gemm3xLinearFn(torch.autograd.Function):
 
 
 def _use_gemm3x(x: torch.Tensor, weight: torch.Tensor) -> bool:
-    return (os.environ.get("TZK_GEMM3X", "0") == "1" and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+    return (os.environ.get("TZK_GEMM3X", "1") == "1" and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
             and weight.dtype == torch.float32 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
             and gemm3x_supported(x.shape[0], weight.shape[0], x.shape[1]) and _gemm3x_lib() is not None)
 

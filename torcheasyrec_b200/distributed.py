@@ -372,6 +372,13 @@ class ShardedEmbeddingBagCollection(_ShardedBase):
         return self._configs
 
     def forward(self, features: KeyedJaggedTensor) -> KeyedTensor:
+        if getattr(self, "_exchange", "nccl") == "peer" and getattr(self, "_peer_states", None) is None:
+            # first call: move the shards into symmetric memory, size the wire buffers for this batch and re-route
+            # forward() to the peer-memory kernels (collective: every rank gets here in its first step)
+            from .peer_exchange import enable_peer_exchange
+
+            enable_peer_exchange(self, features.stride())
+            return self.forward(features)
         keys, lens, vals = [], [], []
         for g in self.groups:
             kjt = g.local._select(features)
@@ -434,8 +441,12 @@ class DenseGradSync:
 
 
 def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows: int = 0, source=None,
-                constraints: Optional[Dict[str, Sequence[str]]] = None, static_capacity: Optional[float] = None):
+                constraints: Optional[Dict[str, Sequence[str]]] = None, static_capacity: Optional[float] = None,
+                exchange: str = "nccl"):
     """Swaps every arena collection of `model.embedding_group` for its sharded twin (tzrec/main.py:799).
+
+    `exchange="peer"` (with `static_capacity`): pooled collections exchange through peer memory of the NVSwitch
+    domain (csrc/tzk_peer.cu) instead of NCCL all-to-alls; sequence collections keep the NCCL path.
 
     The model may have been built with its embedding collections on the meta device (as the reference does,
     embedding.py:187-188): shards are materialised directly on `device`, each rank initialising its own shard
@@ -453,6 +464,8 @@ def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows:
         if static_capacity and isinstance(new, ShardedEmbeddingBagCollection):
             for g in new.groups:       # fixed-shape exchange (see _StaticDispatch); pooled collections only
                 g.static_alpha = float(static_capacity)
+            if exchange == "peer":     # peer-memory kernels instead of the NCCL all-to-alls (peer_exchange.py)
+                new._exchange = "peer"
         if coll.optimizer is not None:
             new.set_optimizer(coll.optimizer)
         seed = src_coll if src_coll is not None else (coll if coll.weights.device.type != "meta" else None)

@@ -42,7 +42,7 @@ class Pipeline:
     def __init__(self, config: str, device="cuda", max_rows: Optional[int] = None,
                  edits: Optional[Dict[str, Any]] = None, seed: int = 1234, capturable: bool = True,
                  sharding: Optional[str] = None, group=None, rw_min_rows: int = 0,
-                 static_capacity: Optional[float] = None) -> None:
+                 static_capacity: Optional[float] = None, exchange: str = "nccl") -> None:
         """`config`: path of a pipeline .config/.json, or the name of a built-in example
         (example_configs.GENERATORS: dlrm_criteo, deepfm_criteo, mmoe_taobao, multi_tower_din_taobao)."""
         from . import example_configs
@@ -72,7 +72,7 @@ class Pipeline:
             self.model = create_model(self.cfg.model_config, self.features, self.labels, device=torch.device("meta"))
             self.sharded = shard_model(self.model, self.device, default=sharding, group=group,
                                        rw_min_rows=rw_min_rows, constraints=self._table_constraints(),
-                                       static_capacity=static_capacity)
+                                       static_capacity=static_capacity, exchange=exchange)
         self.model.to(self.device)
         if sharding is not None:
             self.grad_sync = DenseGradSync(self.model.dense_parameters(), group)

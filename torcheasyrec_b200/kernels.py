@@ -7,6 +7,7 @@ implementation here: host-logic tests inject their own checker backend (tests/or
 """
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -118,6 +119,17 @@ def _rows2d(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
         raise TzkError(f"{name}: rows must be contiguous")
     ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
     return t, ld
+
+
+def _small_linear_rows_path(K: int, N: int) -> bool:
+    """Mirrors use_bwd2() of csrc/tzk_tower.cu (launch accounting only)."""
+    if os.environ.get("TZK_SMALL_LINEAR_BWD", "")[:1] == "1" or not (1 <= K <= 64 and 1 <= N <= 64):
+        return False
+    nb = 4 if N % 4 == 0 else 1
+    t = -(-N // nb) * -(-K // 4)
+    if t > 128:
+        t = -(-N // nb) * -(-K // 8)
+    return t <= 128
 
 
 def _tile_path(lay: "FeatureLayout") -> bool:
@@ -439,11 +451,24 @@ class CudaKernels:
             dense, ld_d = _rows2d(dense, "dense")
             d_dense = torch.empty((B, D), dtype=torch.float32, device=sparse.device)
         d_sparse = torch.empty((B, Ns * D), dtype=torch.float32, device=sparse.device)
+        persist = os.environ.get("TZK_L2_PERSIST", "0") == "1"
+        if persist:      # the sparse update gathers this buffer at random right after: ask L2 to keep it
+            self.l2_persist(d_sparse)
         check(self._lib.tzk_dot_interact_bwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, _ptr(d_out), ld_o, B, Ns, D,
                                              int(copy_dense), int(copy_sparse), p_pad, _ptr(d_dense), D,
                                              _ptr(d_sparse), Ns * D, _stream()), "tzk_dot_interact_bwd")
+        if persist:
+            self.l2_persist(None)
         self.launches += 1
         return d_dense, d_sparse
+
+    def l2_persist(self, t: Optional[torch.Tensor], hit_ratio: float = 0.0) -> None:
+        """L2 residency hint on the current stream for `t` (None clears it); see tzk_l2_persist in include/tzk.h."""
+        if t is None:
+            check(self._lib.tzk_l2_persist(None, 0, 0.0, _stream()), "tzk_l2_persist")
+        else:
+            check(self._lib.tzk_l2_persist(_ptr(t), t.numel() * t.element_size(), float(hit_ratio), _stream()),
+                  "tzk_l2_persist")
 
 
     # ------------------------------------------------------------------ dense-tower helpers
@@ -503,7 +528,8 @@ class CudaKernels:
         check(self._lib.tzk_small_linear_bwd(_ptr(x), ld_x, _ptr(w), _ptr(y) if relu else None, ld_y, _ptr(dy), ld_dy,
                                              M, K, N, int(relu), _ptr(dx), K, _ptr(dw), _ptr(db), _ptr(ws),
                                              ws.numel(), _stream()), "tzk_small_linear_bwd")
-        self.launches += 2
+        # tile kernel + reduction, or (tzk_tower_bwd2.cuh) dx rows kernel + dW kernel + reduction
+        self.launches += (2 + int(want_dx)) if _small_linear_rows_path(K, N) else 2
         return dx, dw, db
 
     def bce_logits_fwd_bwd(self, logits: torch.Tensor, labels: torch.Tensor, want_grad: bool = True):
