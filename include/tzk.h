@@ -73,10 +73,6 @@ int tzk_abi_version(void);
 const char* tzk_last_error(void);
 /* number of SMs of the current device (used by callers to size persistent grids); <0 on error */
 int tzk_sm_count(void);
-/* L2 residency hint (cudaStreamAttributeAccessPolicyWindow on `stream`, persisting hits / streaming misses) for a
- * buffer written by one kernel and gathered at random by the next; bytes == 0 clears the window; hit_ratio <= 0 picks
- * persisting carve-out / bytes.  No reference counterpart (fbgemm TBE has no such hint). */
-int tzk_l2_persist(const void* base, size_t bytes, float hit_ratio, tzk_stream_t stream);
 
 /* ---- K3: lengths -> offsets  ([EXT] fbgemm::asynchronous_complete_cumsum, implicit in every
  * KeyedJaggedTensor.offsets(); reached from tzrec/modules/embedding.py:930) -------------------------

@@ -2,6 +2,7 @@
 import os
 import re
 import subprocess
+import sys
 
 from torcheasyrec_b200 import _lib
 
@@ -47,9 +48,35 @@ def test_product_has_no_cpu_fallback():
     k = CudaKernels()
     with pytest.raises(TzkError):
         k.lengths_to_offsets(torch.ones(4, dtype=torch.int32))
-    # and the package never imports the oracle
-    import sys
-    assert not any(m == "oracle" or m.startswith("oracle.") for m in sys.modules if "torcheasyrec" in m)
+
+
+def test_package_import_graph_never_reaches_the_oracle():
+    """Import every module of the package in a FRESH interpreter and diff sys.modules: nothing under oracle/ (nor the
+    tests' checker backend) may be pulled in, and no file of the package may mention them."""
+    code = (
+        "import sys, pkgutil, importlib\n"
+        "before = set(sys.modules)\n"
+        "import torcheasyrec_b200\n"
+        "for m in pkgutil.walk_packages(torcheasyrec_b200.__path__, 'torcheasyrec_b200.'):\n"
+        "    if '.csrc.' in m.name:\n"
+        "        continue\n"
+        "    importlib.import_module(m.name)\n"
+        "new = set(sys.modules) - before\n"
+        "bad = sorted(n for n in new if n == 'oracle' or n.startswith('oracle.') or n.startswith('tzk_oracle')"
+        " or n.startswith('c_oracle') or n == 'oracle_backend')\n"
+        "print('BAD=' + ','.join(bad))\n"
+        "print('N=' + str(len([n for n in new if n.startswith('torcheasyrec_b200')])))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, check=True)
+    assert "BAD=\n" in r.stdout, r.stdout
+    n = int(re.search(r"N=(\d+)", r.stdout).group(1))
+    assert n >= 12, r.stdout                  # the walk really imported the package's modules
+    pkg = os.path.join(ROOT, "torcheasyrec_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+(oracle|tzk_oracle|c_oracle|oracle_backend)\b", src, re.M), fn
+                assert "libtzk_oracle" not in src, fn
 
 
 def test_gemm3x_library_exports_its_header():

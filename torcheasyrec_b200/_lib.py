@@ -26,7 +26,6 @@ SIGNATURES = {
     "tzk_abi_version": (c_int32, []),
     "tzk_last_error": (c_char_p, []),
     "tzk_sm_count": (c_int32, []),
-    "tzk_l2_persist": (c_int32, [P, c_size_t, c_float, P]),
     "tzk_lengths_to_offsets_workspace_bytes": (c_size_t, [c_int64]),
     "tzk_lengths_to_offsets": (c_int32, [P, c_int64, P, P, c_size_t, P]),
     "tzk_pooled_gather_fwd": (

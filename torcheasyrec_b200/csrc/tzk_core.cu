@@ -25,46 +25,6 @@ extern "C" int tzk_sm_count(void) {
   return n;
 }
 
-// L2 residency hint for a buffer that one kernel writes and the next one gathers from at random (the pooled-output
-// gradient between the interaction backward and the fused sparse update: 109 MB against 126 MB of L2).  Sets the
-// stream's access-policy window (captured into graph kernel nodes); bytes == 0 clears it.  The persisting carve-out
-// is raised to the device maximum on first use; hit_ratio <= 0 picks carve-out / bytes.
-extern "C" int tzk_l2_persist(const void* base, size_t bytes, float hit_ratio, tzk_stream_t stream) {
-  static size_t carve = 0;
-  cudaStream_t st = tzk::as_stream(stream);
-  cudaStreamAttrValue v;
-  memset(&v, 0, sizeof(v));
-  if (bytes == 0 || base == nullptr) {
-    v.accessPolicyWindow.num_bytes = 0;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    TZK_REQUIRE(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess,
-                "l2_persist: clearing the access-policy window failed");
-    return 0;
-  }
-  int dev = 0, max_persist = 0, max_window = 0;
-  TZK_REQUIRE(cudaGetDevice(&dev) == cudaSuccess, "l2_persist: no device");
-  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-  TZK_REQUIRE(max_persist > 0 && max_window > 0, "l2_persist: the device has no persisting L2 carve-out");
-  if (carve == 0) {
-    TZK_REQUIRE(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess,
-                "l2_persist: cudaLimitPersistingL2CacheSize failed");
-    carve = (size_t)max_persist;
-  }
-  const size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
-  float ratio = hit_ratio > 0.f ? hit_ratio : (float)carve / (float)win;
-  if (ratio > 1.f) ratio = 1.f;
-  v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-  v.accessPolicyWindow.num_bytes = win;
-  v.accessPolicyWindow.hitRatio = ratio;
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  TZK_REQUIRE(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess,
-              "l2_persist: setting the access-policy window failed");
-  return 0;
-}
-
 // ----------------------------------------------------------------------------------------------------
 // K3: lengths (int32) -> offsets (int64), exclusive scan with a trailing total.
 // Three small kernels (tile sums, scan of tile sums, tile scan + carry).  The input is F*B int32

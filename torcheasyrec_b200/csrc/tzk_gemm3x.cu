@@ -987,11 +987,11 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
     const int pfd = (pfr && pfr[0] == '1') ? PF_DIST : 0;
     return BN == 64 ? launch_ring<64>(mx, mh, ml, p, pfd, st) : launch_ring<112>(mx, mh, ml, p, pfd, st);
   }
-  const char* e = getenv("TZK_GEMM3X_STACK");     // 1: two MMAs per k-step (see gemm3x_kernel); default: three
+  const char* e = getenv("TZK_GEMM3X_STACK");     // default: two MMAs per k-step (see gemm3x_kernel); 0: three
   const char* t = getenv("TZK_GEMM3X_TW");        // 8: eight transform / epilogue warps; default: four
-  const bool stack = e && e[0] == '1', tw8 = t && t[0] == '8';
-  const char* sp = getenv("TZK_GEMM3X_SPLIT");    // 1: dedicated epilogue warps (see gemm3x_kernel); default: shared
-  const bool split = sp && sp[0] == '1';
+  const bool stack = !(e && e[0] == '0'), tw8 = t && t[0] == '8';   // measured r2: stacked + split is the fastest
+  const char* sp = getenv("TZK_GEMM3X_SPLIT");    // default: dedicated epilogue warps (see gemm3x_kernel); 0: shared
+  const bool split = !(sp && sp[0] == '0');
   const char* pfe = getenv("TZK_GEMM3X_PREFETCH");   // 1: L2 prefetch of the X boxes ahead of the loads (stacked variant only)
   const bool pf = pfe && pfe[0] == '1' && stack;
 #define TZK_G3P(BN_, S_, T_, R_, SP_) ((S_ && pf) ? launch<BN_, S_, T_, R_, SP_, S_>(mx, mh, ml, p, st) \

@@ -218,12 +218,20 @@ class _StaticDispatch:
         _, oo, send_ids, _, inv = k.bucketize_rw(ids, offsets, F, B, W, g.feat_block, feat_owner=g.feat_owner,
                                                  want_inv=True, wire_capacity=cap)
         seg = oo[::B]                                              # [W*F+1]
-        counts = (seg[1:] - seg[:-1]).view(W, F)
         dest_start = oo[::F * B]                                   # [W+1] compact start of every destination
-        g.overflow.add_(((dest_start[1:] - dest_start[:-1]) > cap).any().to(torch.int32))
+        # ids beyond `cap` are dropped by the scatter, in compact (f, b) order per destination: the counts that travel
+        # are clamped the same way, so the owner's per-source bounds always sum to <= cap and a later source's slots
+        # never shift.  The overflowing step's update is lossy (the dropped ids get no gradient); every rank learns
+        # about it in the same step because the flag rides along with the counts (column F).
+        rel_s = (seg[:-1].view(W, F) - dest_start[:-1].unsqueeze(1)).clamp_(max=cap)
+        rel_e = (seg[1:].view(W, F) - dest_start[:-1].unsqueeze(1)).clamp_(max=cap)
+        over = ((dest_start[1:] - dest_start[:-1]) > cap).any().to(seg.dtype)
+        counts = torch.cat([rel_e - rel_s, over.expand(W, 1)], dim=1)        # [dest, F + 1]
         self.inv = inv                                             # padded slot of every original id position
-        recv_counts = torch.empty_like(counts)
-        dist.all_to_all_single(recv_counts, counts, group=group)   # [src, F], equal splits
+        recv = torch.empty_like(counts)
+        dist.all_to_all_single(recv, counts, group=group)          # [src, F + 1], equal splits
+        g.overflow.add_(recv[:, F].max().to(torch.int32))          # any source overflowed -> every rank raises together
+        recv_counts = recv[:, :F].contiguous()
         self.recv_ids = torch.empty_like(send_ids)
         dist.all_to_all_single(self.recv_ids, send_ids, group=group)
         # owner-side "bags": per source its F feature runs, then the padding run up to cap
@@ -321,7 +329,8 @@ class _ShardedBase(nn.Module):
         return [g.local for g in self.groups]
 
     def check_overflow(self) -> None:
-        """Static-capacity mode: raises if any step since the last check needed more than the wire capacity."""
+        """Static-capacity mode: raises if any step since the last check needed more than the wire capacity.  The flag
+        is exchanged inside the step, so every rank raises in the same call (no rank is left inside a collective)."""
         for g in self.groups:
             if g.static_alpha and int(g.overflow.item()):
                 g.overflow.zero_()

@@ -382,14 +382,9 @@ def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> Non
             # next to it; the stream is joined when the backward pass ends.  Nothing between here and the join reads
             # or writes the tables.
             side.wait_stream(cur)          # the gradient (and the step counter) were produced on `cur`
-            persist = pooled and os.environ.get("TZK_L2_PERSIST", "0") == "1" and hasattr(k, "l2_persist")
             with torch.cuda.stream(side):
-                if persist:                # the gathers of the gradient rows should hit L2 (producer marked it too)
-                    k.l2_persist(grad)
                 k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,
                                   ids.numel(), ctx.B, spec.lr, spec.eps, mod.grad_scale, ws, **extras)
-                if persist:
-                    k.l2_persist(None)
             # keeps the buffers the side-stream kernel reads away from the allocator until the join (autograd drops
             # the saved tensors as soon as this node returns)
             mod._pending_apply = (grad, offsets, ids)

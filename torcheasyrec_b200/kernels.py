@@ -451,25 +451,11 @@ class CudaKernels:
             dense, ld_d = _rows2d(dense, "dense")
             d_dense = torch.empty((B, D), dtype=torch.float32, device=sparse.device)
         d_sparse = torch.empty((B, Ns * D), dtype=torch.float32, device=sparse.device)
-        persist = os.environ.get("TZK_L2_PERSIST", "0") == "1"
-        if persist:      # the sparse update gathers this buffer at random right after: ask L2 to keep it
-            self.l2_persist(d_sparse)
         check(self._lib.tzk_dot_interact_bwd(_ptr(dense), ld_d, _ptr(sparse), ld_s, _ptr(d_out), ld_o, B, Ns, D,
                                              int(copy_dense), int(copy_sparse), p_pad, _ptr(d_dense), D,
                                              _ptr(d_sparse), Ns * D, _stream()), "tzk_dot_interact_bwd")
-        if persist:
-            self.l2_persist(None)
         self.launches += 1
         return d_dense, d_sparse
-
-    def l2_persist(self, t: Optional[torch.Tensor], hit_ratio: float = 0.0) -> None:
-        """L2 residency hint on the current stream for `t` (None clears it); see tzk_l2_persist in include/tzk.h."""
-        if t is None:
-            check(self._lib.tzk_l2_persist(None, 0, 0.0, _stream()), "tzk_l2_persist")
-        else:
-            check(self._lib.tzk_l2_persist(_ptr(t), t.numel() * t.element_size(), float(hit_ratio), _stream()),
-                  "tzk_l2_persist")
-
 
     # ------------------------------------------------------------------ dense-tower helpers
     def bias_act(self, y: torch.Tensor, bias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
