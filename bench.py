@@ -8,6 +8,10 @@ Adagrad update -> dense Adam step.  fp32 everywhere (TF32 off, as the reference'
 Workload at N=1: BASELINE.json configs[1] (examples/dlrm_criteo.config, full hash sizes, row-wise, B=65536
 per rank) — it fits one GPU (12.2 GiB tables + 12.2 GiB Adagrad state).
 
+N>1 (torchrun): tables sharded --sharding {row_wise,table_wise,mixed}, exchange over peer memory (default) or NCCL;
+the line then carries `verify` (the sharded step against its unsharded twin, run inside this process) and an NVLink
+roofline.  Other models of BASELINE.json: --model deepfm_criteo | mmoe_taobao | multi_tower_din_taobao.
+
 Prints ONE JSON line (see DESIGN.md §7 for every field).
 """
 import argparse
@@ -37,9 +41,26 @@ METRIC = "samples/sec (DLRM-Criteo synth, train step fwd+bwd+optimizer)"
 UNIT = "samples/s"
 # DLRM-Criteo (F=26, L=1, D=16) per-sample algorithmic bytes, SURVEY.md §8d — computed from the layout at run time:
 #   gather 1664 rows + 1664 pooled write + 208 ids + 104 lengths = 3640 B; backward 1664 grad + 26*4*64 RMW + 208 = 8528 B
-NCU_TRAFFIC_BYTES = {"pooled_gather_fwd_kernel": 111.276e6 + 56.952e6,          # dram rd + wr, one launch (ncu --set full)
-                     "run_update_kernel": 282.823e6 + 50.973e6,         # largest kernel of the fused backward (default path)
-                     "tile_update_kernel": 344.51072e6 + 52.342784e6}   # TZK_BWD_TILE=1 path
+NVLINK_GBS = 900.0     # NVLink 5, per direction per GPU (nominal; B200_PROFILING.md) — the N>1 roofline's denominator
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused backward's / the gather's kernels, as
+    written by scripts/ncu_traffic.py from an `ncu --set full` capture of THIS build (the file carries a hash of the
+    kernel sources it was taken on; a stale file is ignored)."""
+    import hashlib
+
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        d = json.load(open(path))
+        h = hashlib.sha256()
+        for fn in ("tzk_bwd.cu", "tzk_gather.cu", "tzk_common.cuh"):
+            h.update(open(os.path.join(ROOT, "torcheasyrec_b200", "csrc", fn), "rb").read())
+        return d if d.get("source_sha16") == h.hexdigest()[:16] else None
+    except Exception:
+        return None
 
 
 def parse_args():
@@ -58,11 +79,17 @@ def parse_args():
     ap.add_argument("--no-zipf", action="store_true", help="skip the second (Zipf-id) timing of the same step")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the measurement-only extras (pipelined loss read, drafts under scripts/experimental)")
-    ap.add_argument("--sharded-mode", default="graph", choices=["graph", "eager"],
-                    help="N>1: 'graph' = static-capacity exchange captured in one CUDA graph, 'eager' = dynamic splits")
+    ap.add_argument("--sharded-mode", default="auto", choices=["auto", "graph", "eager"],
+                    help="N>1: 'graph' = fixed-capacity exchange captured in one CUDA graph, 'eager' = step by step "
+                         "(auto: graph unless the model has sequence features)")
     ap.add_argument("--static-capacity", type=float, default=1.5)
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
-                    help="sharded runs: NCCL all-to-alls, or the peer-memory kernels of csrc/tzk_peer.cu")
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
+                    help="sharded runs: the peer-memory kernels of csrc/tzk_peer.cu (default), or NCCL all-to-alls")
+    ap.add_argument("--sharding", default="row_wise", choices=["row_wise", "table_wise", "mixed"],
+                    help="placement of the tables at N>1 (BASELINE configs: dlrm row_wise, deepfm table_wise, mmoe mixed)")
+    ap.add_argument("--rw-min-rows", type=int, default=200000, help="mixed: tables with at least this many rows go row-wise")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="N>1: skip the in-process parity check of the sharded step against its unsharded twin")
     ap.add_argument("--force-sharded", action="store_true",
                     help="N=1 only: still go through bucketize / all-to-all / owner gather (1-rank process group)")
     return ap.parse_args()
@@ -146,6 +173,11 @@ def cpu_step_rate(model: str, batch: int, steps: int, warmup: int, max_rows: int
 
 
 def run_reference(args):
+    """The reference's CPU path of the same step (`kind: "port"`: tzrec's own path needs the torchrec / fbgemm wheels,
+    which cannot be installed offline — DESIGN.md §7): this repo's Pipeline / model shells stepped with the oracle
+    (oracle/tzk_oracle.c, OpenMP) as the sparse backend and torch-CPU dense towers, on all the host threads that help
+    (capped at 32: measured scan in profiles/README.md).  Honours --steps / --warmup; every step is a bounded sample of
+    --cpu-batch samples of the workload (a 65536-sample step takes ~0.25 s on 32 threads)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
@@ -156,21 +188,77 @@ def run_reference(args):
     note = f"tables capped at {max_rows} rows" if max_rows else "full hash sizes"
     if not max_rows and psutil.virtual_memory().available < 40 * 2 ** 30:
         max_rows, note = 4_000_000, "tables capped at 4M rows (host RAM < 40 GiB)"
-    steps = max(1, min(args.steps, 3))
-    rate, ms, cores, kind = cpu_step_rate(args.model, args.cpu_batch, steps, 1, max_rows, args.id_dist)
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 5))
+    rate, ms, cores, kind = cpu_step_rate(args.model, args.cpu_batch, steps, warm, max_rows, args.id_dist)
+    extras = {}
+    try:    # BASELINE.json configs[0]: DeepFM, 1k-row tables, batch 512 (the reference's own CPU-runnable case)
+        r0, ms0, c0, _ = cpu_step_rate("deepfm_criteo", 512, max(steps, 10), 2, 1000, "uniform")
+        extras["configs0_deepfm_1k_rows_b512"] = {"value": r0, "unit": UNIT, "ms_per_step": ms0, "cores": c0,
+                                                  "note": "examples/deepfm_criteo.config, every table 1000 rows, "
+                                                          "batch 512, world_size 1, oracle port"}
+    except Exception as e:   # noqa: BLE001
+        extras["configs0_deepfm_1k_rows_b512"] = {"failed": repr(e)[:200]}
+    try:
+        extras["embedding_bag_stock_cpu"] = _embedding_bag_line(args.cpu_batch, max_rows)
+    except Exception as e:   # noqa: BLE001
+        extras["embedding_bag_stock_cpu"] = {"failed": repr(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} (examples/{args.model}.config), {note}, Adagrad lr=1e-3 + Adam, "
-                               f"id_dist={args.id_dist}", "per_step_samples": args.cpu_batch},
+        "config": {"workload": f"{args.model}: examples/{args.model}.config, {note}, sparse Adagrad lr=1e-3 fused in "
+                               f"backward + dense Adam, ids {args.id_dist}",
+                   "per_step_samples": args.cpu_batch,
+                   "note": "bounded sample: each step is --cpu-batch samples of the GPU arm's per-rank batch"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps of {args.cpu_batch} samples; oracle restatement "
-                                   "(torch-CPU dense towers + oracle/ sparse path); the reference's own path "
-                                   "needs torchrec/fbgemm wheels that are not installable offline"},
+                         "sample": f"{steps} steps of {args.cpu_batch} samples ({warm} warm-up); this repo's model shells + "
+                                   "torch-CPU dense towers + oracle/ sparse path (C/OpenMP restatement); the reference's "
+                                   "own path needs torchrec/fbgemm wheels that are not installable offline"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extras": extras,
     }
     _print_line(line)
+
+
+def _embedding_bag_line(batch: int, max_rows: int):
+    """The 'best stock CPU kernel' line BASELINE.md §3 promised: torch.nn.functional.embedding_bag (sum) over the 26
+    Criteo tables, forward only, same ids as the oracle's pooled lookup timed beside it."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_backend import OracleKernels
+
+    from torcheasyrec_b200.engine import Pipeline
+
+    pipe = Pipeline("dlrm_criteo", device="cpu", max_rows=min(max_rows or 4_000_000, 4_000_000))
+    ebc = pipe.model.sparse_collections()[0]
+    b = pipe.synthetic_batch(batch, seed=5)
+    kjt = ebc._select(b.sparse_features[sorted(b.sparse_features)[0]])
+    ids, off = kjt.values(), kjt.offsets()
+    tabs = [ebc.table_weight(t) for t in range(len(ebc._configs))]
+    F = len(tabs)
+
+    def stock():
+        return torch.cat([torch.nn.functional.embedding_bag(ids[f * batch:(f + 1) * batch], tabs[f],
+                                                            torch.arange(batch), mode="sum") for f in range(F)], dim=1)
+
+    k = OracleKernels(use_c=True)
+
+    def ours():
+        return k.pooled_gather_fwd(ebc.weights.data, ebc.layout, ids, off, batch)
+
+    assert np.array_equal(stock().numpy(), ours().numpy())
+    res = {}
+    for name, fn in (("F.embedding_bag", stock), ("oracle pooled_lookup", ours)):
+        fn()
+        t0 = time.perf_counter()
+        n = 5
+        for _ in range(n):
+            fn()
+        dt = (time.perf_counter() - t0) / n
+        res[name] = {"ms": dt * 1e3, "lookups_per_s": F * batch / dt}
+    res["note"] = f"pooled lookup only (forward), 26 tables (<= 4M rows each), {batch} samples, {torch.get_num_threads()} threads"
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -209,11 +297,30 @@ def run_ours(args):
     from torcheasyrec_b200.kernels import default_kernels
 
     B, K, W = args.batch_size, args.steps, max(args.warmup, 3)
-    graphed = world == 1 or args.sharded_mode == "graph"
+    # ---- N>1: the sharded step against its unsharded twin, inside this process (small tables, same plan / exchange) --
+    verify = None
+    if sharded and world > 1 and not args.no_verify:
+        from torcheasyrec_b200.verify import verify_sharded
+
+        try:
+            worst = verify_sharded(args.model, dev, args.sharding, rw_min_rows=300 if args.sharding == "mixed" else 0,
+                                   static_capacity=max(args.static_capacity, 2.5), exchange=args.exchange,
+                                   max_rows=2000, batch=256)
+            verify = {"status": "ok", "max_abs_dev": worst,
+                      "what": "unsharded twin on the concatenated batch vs this sharded step (2000-row tables, 256 "
+                              "samples per rank, 2 steps): logits, loss, every table, every dense parameter"}
+        except Exception as e:   # noqa: BLE001 — reported in the line; the timing below still runs
+            verify = {"status": "FAILED", "error": repr(e)[:400]}
+        torch.cuda.synchronize()
+    probe = Pipeline(args.model, device="cpu", max_rows=8) if args.sharded_mode == "auto" else None
+    has_seq = bool(probe and any(f.is_sequence for f in probe.features))
+    mode = args.sharded_mode if args.sharded_mode != "auto" else ("eager" if has_seq else "graph")
+    graphed = mode == "graph"
+    args._mode = mode
     pipe = Pipeline(args.model, device=dev, max_rows=args.max_rows or None,
-                    sharding="row_wise" if sharded else None,
-                    static_capacity=args.static_capacity if (sharded and graphed) else None,
-                    exchange=args.exchange if (sharded and graphed) else "nccl")
+                    sharding=args.sharding if sharded else None, rw_min_rows=args.rw_min_rows,
+                    static_capacity=args.static_capacity if (sharded and (graphed or args.exchange == "peer")) else None,
+                    exchange=args.exchange if sharded else "nccl")
     host = [pipe.synthetic_batch(B, seed=20260923 + rank * 1000 + i, id_dist=args.id_dist).pin_memory()
             for i in range(args.ring)]
     ring = [hb.to(dev) for hb in host]
@@ -226,8 +333,7 @@ def run_ours(args):
         pipe.eager_step(step.static)
         launches_per_step = kern.launches - launches_before
     else:
-        # sharded steps read the per-peer id counts on the host every step (split sizes of the all-to-alls),
-        # so they run eagerly instead of as one CUDA graph
+        # variable-shape steps (sequence features; dynamic all-to-all splits) run eagerly instead of as one CUDA graph
         class EagerStep:
             def __init__(self):
                 self.cur = None
@@ -269,8 +375,11 @@ def run_ours(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     # ---- e2e: pinned host batch -> H2D -> step -> loss back on the host, every step --------------------------
-    # (N=1: the H2D of batch i+1 runs on the copy stream while step i computes; the loss of every step is read)
-    piped = graphed
+    # The H2D of batch i+1 runs on the copy stream while step i computes (graphed steps); the loss of EVERY step
+    # reaches the host inside the timed region through a pinned D2H copy + event, read one step later so that the
+    # host keeps enqueueing (what TrainPipelineSparseDist's progress() does with its batch queue).
+    pin = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
     for i in range(2):
         step.load(host[i % len(host)])
         step.replay()
@@ -278,16 +387,22 @@ def run_ours(args):
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     last = 0.0
-    if piped:
+    if graphed:
         step.prefetch(host[0])
     for i in range(K):
-        if piped:
+        if graphed:
             step.commit()
             step.prefetch(host[(i + 1) % len(host)])
         else:
             step.load(host[i % len(host)], non_blocking=True)
         loss = step.replay()
-        last = float(loss.item())          # device -> host read of the step's result
+        pin[i % 2].copy_(loss, non_blocking=True)
+        evs[i % 2].record()
+        if i:
+            evs[(i - 1) % 2].synchronize()
+            last = float(pin[(i - 1) % 2])
+    evs[(K - 1) % 2].synchronize()
+    last = float(pin[(K - 1) % 2])
     g1.record()
     barrier()
     ms_e2e = g0.elapsed_time(g1)
@@ -310,7 +425,7 @@ def run_ours(args):
         zipf = z0.elapsed_time(z1)
         del zring
     clk = clocks.stop() if clocks else None
-    pipe.check_overflow()      # static-capacity exchange: no peer needed more than its wire capacity
+    pipe.check_overflow()      # fixed-capacity exchange: no peer needed more than its wire capacity
     if world > 1:
         import torch.distributed as dist
 
@@ -319,14 +434,24 @@ def run_ours(args):
         ms_total, ms_e2e, zz = t.tolist()
         zipf = zz if zipf is not None else None
     args._zipf_ms = zipf
+    args._verify = verify
+
+    roofline, cpu = None, None
+    if sharded:
+        # ---- N>1 roofline: the requester-side gather against NVLink (rank 0 times it alone: no collective in it) ----
+        try:
+            if rank == 0:
+                roofline = _peer_roofline(pipe, kern, ring, B, world, max(K, 10), ms_total / K)
+        except Exception as e:   # noqa: BLE001
+            roofline = {"failed": repr(e)[:300]}
+        barrier()               # peers keep their symmetric buffers mapped until rank 0 is done
+        if rank == 0:
+            _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
+        return
     if rank != 0:
         return
 
     # ---- roofline of the dominant kernels (rank 0, standalone launches on the same inputs) -----------------
-    if sharded:
-        roofline, cpu = None, None
-        _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
-        return
     ebc = pipe.model.sparse_collections()[0]
     lay = ebc.layout
     dg = sorted(ring[0].sparse_features)[0]
@@ -338,15 +463,25 @@ def run_ours(args):
     R = len(ring)
     it = max(K, 10)
     # algorithmic bytes per sample of THIS collection and batch: rows + pooled write + ids + lengths;
-    # backward: gradient read + weight/state read+write of every looked-up row (U = upper bound: no duplicates) + ids
+    # backward: gradient read + weight/state read+write of every looked-up row + ids.  Two variants of the backward
+    # figure: U = every lookup hits a distinct row (SURVEY's upper bound, 26 rows/sample for Criteo) and U = the rows
+    # this batch really touches (counted on the device below).
     lpk = kjts[0].length_per_key()
     nnz_f = [float(lpk[f]) / B for f in range(lay.num_features)]
     row_b = sum(l * d * 4 for l, d in zip(nnz_f, lay.dim))
     gather_b = row_b + sum(d * 4 for d in lay.dim) + sum(l * 8 for l in nnz_f) + 4 * lay.num_features
     spec = ebc.optimizer
     state_mult = {0: 2, 1: 4, 2: 2}[spec.kind]          # SGD w r+w; Adagrad w+state r+w; row-wise: w r+w (+8 B/row)
-    bwd_b = sum(d * 4 for d in lay.dim) + state_mult * row_b + sum(l * 8 for l in nnz_f) + \
-        (8 * sum(nnz_f) if spec.kind == 2 else 0)
+    fixed_b = sum(d * 4 for d in lay.dim) + sum(l * 8 for l in nnz_f)      # gradient read + ids
+    bwd_b = fixed_b + state_mult * row_b + (8 * sum(nnz_f) if spec.kind == 2 else 0)
+    uniq_row_bytes = 0.0                                  # sum over unique (table,row) of D*4, averaged over the ring
+    for kj in kjts:
+        o = 0
+        for f in range(lay.num_features):
+            n = lpk[f]
+            uniq_row_bytes += float(torch.unique(kj.values()[o:o + n]).numel()) * lay.dim[f] * 4 / R
+            o += n
+    bwd_b_actual = fixed_b + (state_mult * uniq_row_bytes + (8 * uniq_row_bytes / (lay.dim[0] * 4) if spec.kind == 2 else 0)) / B
     fwd_ms = time_kernel(lambda i: kern.pooled_gather_fwd(ebc.weights.data, lay, ids[i % R], offs[i % R], B, out), it)
     bwd_ms = time_kernel(lambda i: kern.fused_bwd(spec.kind, True, grad, ebc.weights.data, ebc.opt_state, lay,
                                                   ids[i % R], offs[i % R], B, spec.lr, spec.eps, 1.0), it)
@@ -360,23 +495,29 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     fwd_gbs = gather_b * B / (fwd_ms * 1e-3) / 1e9
     bwd_gbs = bwd_b * B / (bwd_ms * 1e-3) / 1e9
+    bwd_gbs_actual = bwd_b_actual * B / (bwd_ms * 1e-3) / 1e9
     dominant = ("tzk_fused_bwd (linearize + radix sort + run_update / long-run kernels)" if bwd_ms > fwd_ms
                 else "pooled_gather_fwd_kernel")
     ach = bwd_gbs if bwd_ms > fwd_ms else fwd_gbs
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture
-    # (profiles/; only valid for the workload it was captured on)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, all kernels of the dominant op, from the ncu --set full
+    # capture scripts/ncu_traffic.py took on this build (profiles/ncu_traffic.json; null when absent or stale)
     std = (args.model == "dlrm_criteo" and B == 65536 and not args.max_rows and args.id_dist == "uniform")
+    nt = ncu_traffic() if std else None
     traffic = None
-    if std:
-        traffic = (NCU_TRAFFIC_BYTES["run_update_kernel"] if bwd_ms > fwd_ms else NCU_TRAFFIC_BYTES["pooled_gather_fwd_kernel"])
+    if nt:
+        traffic = nt.get("fused_bwd_bytes") if bwd_ms > fwd_ms else nt.get("pooled_gather_fwd_bytes")
     kernels = {
         "pooled_gather_fwd": {"ms": fwd_ms, "algorithmic_GBps": fwd_gbs, "frac": fwd_gbs / peak,
                               "row_read_GBps": row_b * B / (fwd_ms * 1e-3) / 1e9, "bytes_per_sample": gather_b},
         "fused_bwd": {"ms": bwd_ms, "algorithmic_GBps": bwd_gbs, "frac": bwd_gbs / peak, "bytes_per_sample": bwd_b,
+                      "frac_upper_bound_U": bwd_gbs / peak, "frac_actual_U": bwd_gbs_actual / peak,
+                      "bytes_per_sample_actual_U": bwd_b_actual,
+                      "unique_rows_per_sample": uniq_row_bytes / (lay.dim[0] * 4) / B,
                       "sort_ms": sort_ms, "apply_ms": apply_ms,
                       "apply_frac": bwd_b * B / (apply_ms * 1e-3) / 1e9 / peak,
                       "note": "sort_ms overlaps the forward pass inside the step (side stream); apply_ms is the part on "
-                              "the critical path"},
+                              "the critical path; frac uses SURVEY §8d's upper bound (every lookup a distinct row), "
+                              "frac_actual_U the rows this batch really touches"},
     }
     if args.model == "dlrm_criteo":
         Ns, D = lay.num_features, lay.dim[0]
@@ -395,13 +536,15 @@ def run_ours(args):
                                        "frac": ib_b * B / (ib_ms * 1e-3) / 1e9 / peak, "bytes_per_sample": ib_b}
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": traffic, "traffic_note": "dram read+write bytes per launch of the dominant kernel's largest launch (run_update_kernel, or "
-        "the gather itself) from the ncu --set full captures summarised in profiles/" if traffic else None,
+        "traffic": traffic,
+        "traffic_note": (f"dram read+write bytes per launch summed over the kernels of the dominant op "
+                         f"({', '.join(nt.get('kernels', []))}), ncu --set full via scripts/ncu_traffic.py "
+                         f"({nt.get('when', '?')})" if traffic else
+                         "null: no profiles/ncu_traffic.json taken on this build (scripts/ncu_traffic.py writes it)"),
         "peak_source": peak_src,
         "kernels": kernels,
         "share_of_step": {k: v["ms"] / (ms_total / K) for k, v in kernels.items()},
     }
-    cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
             steps_cpu = 2
@@ -415,34 +558,48 @@ def run_ours(args):
     # ---- measurement-only extras (N=1): not part of value / e2e / roofline, and never allowed to fail the run ----
     if not args.no_extras and graphed:
         extras = {"note": "measurement-only; no reported number above depends on these"}
-        deadline = time.time() + 210.0          # all extras together: bounded, so that the line below is never at risk
-
-        def left(cap):
-            return max(5.0, min(cap, deadline - time.time()))
-
         try:
-            extras["e2e_pipelined"] = _e2e_pipelined(step, host, K, B)
+            extras["e2e_blocking"] = _e2e_blocking(step, host, K, B)
         except Exception as e:
-            extras["e2e_pipelined"] = {"failed": repr(e)[:200]}
-        exp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "experimental")
-        # the wide tower layer on the hand-written tcgen05 kernels (opt-in until its autograd glue has run on hardware —
-        # these subprocesses ARE that run): model-level parity first, then this benchmark with the switch on
-        if os.path.exists(os.path.join(exp, "try_gemm3x_model.py")) and time.time() < deadline - 30:
-            extras["gemm3x_model_parity"] = _run_draft(os.path.join(exp, "try_gemm3x_model.py"), ["8192"], left(90))
-        if time.time() < deadline - 45:
-            extras["gemm3x_step"] = _run_variant({"TZK_GEMM3X": "1", "TZK_GEMM3X_STACK": "1"}, args, left(120))
-        if os.path.exists(os.path.join(exp, "try_tower_bwd2.py")) and time.time() < deadline - 30:
-            extras["tower_bwd2_draft"] = _run_draft(os.path.join(exp, "try_tower_bwd2.py"), [str(B)], left(90))
+            extras["e2e_blocking"] = {"failed": repr(e)[:200]}
         args._extras = extras
     _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, len(ring))
 
 
-def _e2e_pipelined(step, host, K, batch):
-    """The e2e feed again, but the host reads the loss of step i-1 (pinned D2H copy + event) while step i is already
-    enqueued, instead of blocking on step i before it enqueues step i+1.  Every step's loss still reaches the host
-    inside the timed region; what disappears is the GPU idling through the host's launch work between steps."""
-    pin = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    evs = [torch.cuda.Event() for _ in range(2)]
+def _peer_roofline(pipe, kern, ring, B, world, iters, step_ms):
+    """N>1: the requester-side gather reads (W-1)/W of its rows over NVLink — algorithmic NVLink bytes per launch over
+    the CUDA-event time of standalone launches, against 900 GB/s per direction; and the same rows against HBM."""
+    from torcheasyrec_b200.distributed import ShardedEmbeddingBagCollection
+
+    sm = next((m for m in pipe.sharded if isinstance(m, ShardedEmbeddingBagCollection)), None)
+    states = getattr(sm, "_peer_states", None) if sm is not None else None
+    if not states:
+        return None
+    st = max(states, key=lambda s: s.g.total_dim)
+    g = st.g
+    dg = sorted(ring[0].sparse_features)[0]
+    kjts = [g.local._select(b.sparse_features[dg]) for b in ring]
+    offs = [kern.lengths_to_offsets(k.lengths()) for k in kjts]
+    ids = [k.values() for k in kjts]
+    R = len(ring)
+    ms = time_kernel(lambda i: st.gather(ids[i % R], offs[i % R]), iters)
+    lay = g.local.layout
+    row_bytes = float(sum(kjts[0].length_per_key()[f] * lay.dim[f] * 4 for f in range(lay.num_features)))
+    nvl = row_bytes * (world - 1) / world
+    peak, peak_src = measured_peak_gbs()
+    ach = nvl / (ms * 1e-3) / 1e9
+    return {"bound": "nvlink", "kernel": "peer_pooled_gather_fwd_kernel (requester-side gather over peer memory)",
+            "achieved": ach, "peak": NVLINK_GBS, "unit": "GB/s", "frac": ach / NVLINK_GBS, "traffic": None,
+            "peak_source": "nominal NVLink 5 per direction per GPU (B200_PROFILING.md)",
+            "ms": ms, "nvlink_bytes_per_launch": nvl, "row_bytes_per_launch": row_bytes,
+            "share_of_step": ms / step_ms,
+            "note": "algorithmic inbound NVLink bytes = embedding-row bytes x (W-1)/W (uniform ids; 64-B reads); "
+                    "timed on rank 0 alone after the run (idle peers), CUDA events"}
+
+
+def _e2e_blocking(step, host, K, batch):
+    """The e2e feed with a BLOCKING loss read (`loss.item()`) between steps — the host cannot enqueue step i+1 before
+    step i has finished.  Kept as a measurement-only comparison for the reported (pipelined-read) e2e."""
     for i in range(2):
         step.load(host[i % len(host)])
         step.replay()
@@ -454,75 +611,49 @@ def _e2e_pipelined(step, host, K, batch):
     for i in range(K):
         step.commit()
         step.prefetch(host[(i + 1) % len(host)])
-        loss = step.replay()
-        pin[i % 2].copy_(loss, non_blocking=True)
-        evs[i % 2].record()
-        if i:
-            evs[(i - 1) % 2].synchronize()
-            last = float(pin[(i - 1) % 2])
-    evs[(K - 1) % 2].synchronize()
-    last = float(pin[(K - 1) % 2])
+        last = float(step.replay().item())
     t1.record()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1)
     return {"value": batch * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "last_loss": last,
-            "note": "loss of step i-1 read on the host while step i runs (pinned D2H + event), same H2D feed as e2e"}
-
-
-def _run_variant(env, args, timeout):
-    """This benchmark again in a subprocess with extra environment switches (short, no CPU baseline / Zipf / extras)."""
-    try:
-        cmd = [sys.executable, os.path.abspath(__file__), "--steps", "12", "--warmup", "4", "--no-cpu-baseline", "--no-zipf",
-               "--no-extras", "--batch-size", str(args.batch_size), "--model", args.model]
-        if args.max_rows:
-            cmd += ["--max-rows", str(args.max_rows)]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env={**os.environ, **env})
-        lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
-        if r.returncode != 0 or not lines:
-            return {"rc": r.returncode, "err": [ln.strip() for ln in r.stderr.splitlines() if ln.strip()][-3:]}
-        d = json.loads(lines[-1])
-        return {"env": env, "ms_per_step": d["ms_per_step"], "value": d["value"], "e2e_ms_per_step": d["e2e"]["ms_per_step"],
-                "last_loss": d["e2e"].get("last_loss")}
-    except subprocess.TimeoutExpired:
-        return {"rc": "timeout"}
-    except Exception as e:   # noqa: BLE001 — an extra is never allowed to fail the bench
-        return {"rc": repr(e)[:200]}
-
-
-def _run_draft(path, argv, timeout):
-    """Runs a scripts/experimental try-script in its own process (its failure cannot touch this one)."""
-    try:
-        r = subprocess.run([sys.executable, path] + argv, capture_output=True, text=True, timeout=timeout)
-        out = [ln.strip() for ln in r.stdout.splitlines() if ln.strip()][-8:]
-        err = [ln.strip() for ln in r.stderr.splitlines() if ln.strip()][-2:] if r.returncode else []
-        return {"rc": r.returncode, "out": out, "err": err}
-    except subprocess.TimeoutExpired:
-        return {"rc": "timeout"}
-    except Exception as e:   # noqa: BLE001 — an extra is never allowed to fail the bench
-        return {"rc": repr(e)[:200]}
+            "note": "same H2D feed, loss.item() after every step (host and device serialised)"}
 
 
 def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step, clk, roofline, cpu, ring_len):
     global_batch = B * world
     h2d = host[0].nbytes()
+    sharded = world > 1 or args.force_sharded
+    mode = getattr(args, "_mode", "graph")
+    shard_txt = {"row_wise": "row-wise", "table_wise": "table-wise", "mixed": f"mixed (row-wise from {args.rw_min_rows} rows)"}
+    if not sharded:
+        exch = "none"
+    elif args.exchange == "peer":
+        exch = (f"peer-memory kernels over NVLink (requester-side gather, owner-side pull of keys + in-place gradient "
+                f"reads, 4 flag barriers, dense gradients summed from peer buffers): no collective call in the step; "
+                f"wire capacity {args.static_capacity}x")
+    else:
+        exch = (f"static capacity {args.static_capacity}x, in-graph NCCL all-to-all" if mode == "graph"
+                else "dynamic splits (host read per step), NCCL all-to-all")
     line = {
-        "metric": METRIC, "value": global_batch * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "metric": METRIC if args.model == "dlrm_criteo" else METRIC.replace("DLRM-Criteo", args.model),
+        "value": global_batch * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.model}: examples/{args.model}.config, "
                                f"{'full hash sizes' if not args.max_rows else f'tables capped at {args.max_rows} rows'}, "
-                               f"row-wise over {world} rank(s), per-rank batch {B}, sparse Adagrad lr=1e-3 fused in "
-                               f"backward + dense Adam, ids {args.id_dist}",
-                   "global_batch": global_batch, "parallelism": f"rw{world}+dp{world}",
-                   "l2": f"inputs rotate over {ring_len} distinct batches; tables 12.2 GiB + state 12.2 GiB >> 126 MB L2",
-                   "cuda_graph": bool(args.sharded_mode == "graph" or world == 1),
-                   "exchange": ("none" if (world == 1 and not args.force_sharded) else
-                                (f"static capacity {args.static_capacity}x, " + ("peer-memory kernels over NVLink, no collective"
-                                                                                  if args.exchange == "peer" else
-                                                                                  "in-graph NCCL all-to-all")
-                                 if args.sharded_mode == "graph" else "dynamic splits (host read per step)"))},
+                               f"{shard_txt[args.sharding] + ' over ' + str(world) + ' rank(s)' if sharded else 'one GPU'}, "
+                               f"per-rank batch {B}, sparse Adagrad lr=1e-3 fused in backward + dense Adam, "
+                               f"ids {args.id_dist}",
+                   "global_batch": global_batch,
+                   "parallelism": (f"{ {'row_wise': 'rw', 'table_wise': 'tw', 'mixed': 'tw+rw'}[args.sharding] }{world}+dp{world}"
+                                   if sharded else "1 gpu"),
+                   "l2": f"inputs rotate over {ring_len} distinct batches; tables + optimizer state >> 126 MB L2",
+                   "cuda_graph": bool(mode == "graph"),
+                   "exchange": exch},
         "e2e": {"value": global_batch * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last,
+                "note": "pinned host batch -> H2D (copy stream) -> step -> loss D2H into pinned memory, every step, all "
+                        "inside the timed region; the host reads step i-1's loss while step i runs"},
         "zipf_ids": (None if getattr(args, "_zipf_ms", None) is None else
                      {"value": global_batch * K / (args._zipf_ms * 1e-3), "unit": UNIT,
                       "ms_per_step": args._zipf_ms / K, "note": "same step, ids ~ Zipf(1.05) clipped to each table"}),
@@ -532,6 +663,9 @@ def _emit(args, world, B, K, W, ms_total, ms_e2e, host, last, launches_per_step,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if getattr(args, "_verify", None) is not None:
+        line["verify"] = args._verify["status"].lower() if args._verify["status"] == "ok" else "FAILED"
+        line["verify_detail"] = args._verify
     if getattr(args, "_extras", None):
         line["extras"] = args._extras
     _print_line(line)

@@ -270,30 +270,56 @@ size_t tzk_bce_logits_workspace_bytes(int64_t M);
 int tzk_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t M, float* loss, float* dlogits,
                            void* workspace, size_t workspace_bytes, tzk_stream_t stream);
 
-/* ---- sharded sparse step over peer memory (NVSwitch domain; replaces the KJT / pooled-embedding all-to-alls of
- * torchrec's ShardedEmbeddingBagCollection, SURVEY.md §8 A3 / App. A.4, tzrec/main.py:799).  `*_ptrs` are HOST arrays
- * [W] of device addresses: rank r's symmetric buffer as mapped in the calling process.
+/* ---- sharded sparse step over peer memory (NVSwitch domain; replaces the KJT / pooled-embedding / sequence-embedding
+ * all-to-alls and the reduce-scatter of torchrec's ShardedEmbeddingBagCollection / ShardedEmbeddingCollection and the DDP
+ * all-reduce of the dense gradients: SURVEY.md §2.3 C1-C5, App. A.5-A.8, reached from tzrec/main.py:799).  `*_ptrs`
+ * are HOST arrays [W] of device addresses: rank r's symmetric buffer as mapped in the calling process (W <= 16).
  *   peer_pooled_gather_fwd : the requester's gather reads each row from the owning rank's arena (owner = feat_owner +
  *                            id / feat_block, as tzk_bucketize_rw) and pools locally; rf_w_off[r * F + f] = arena
  *                            offset (elements) of feature f's table on rank r; other arrays as tzk_pooled_gather_fwd.
+ *   peer_seq_gather_fwd    : the same for un-pooled lookups: out[l, :] = row of ids[l] (all features share D).
  *   peer_barrier           : one CTA; flag[src] on every rank = epoch, st.release.sys / ld.acquire.sys; `epoch` is a
- *                            device counter (graph-replayable).  Every rank must call it the same number of times.
- *   peer_pull_counts       : recv_counts[src, f] = counts_src[me, f].
- *   peer_pull              : slot s = (src, j) of the fixed-capacity wire layout: recv_ids[s] = src's id for me,
- *                            recv_g[s, :] = src's gradient slice [b, col_f : col_f + D] (position = f * B + b, one id
- *                            per bag); slots at or beyond bounds[src * (F + 1) + F] get id 0 and a zero row.
+ *                            device counter (graph-replayable).  Every rank must call it the same number of times per
+ *                            (pad_ptrs, epoch) pair; barrier sites that can overlap in time use different pairs.
+ *   peer_bucketize         : source side of the backward.  Stable multi-split of the local ids by destination into
+ *                            this rank's wire buffers: destination r's entries start at r * cap, in (feature, bag,
+ *                            position) order; wire_key = rf_key_base[r * F + f] + owner-local row (the owner's
+ *                            linearised sort key), wire_idx = bag index f * B + b (pooled) or id position (sequence);
+ *                            counts[r] = ids for r (clamped to cap), counts[W] = 1 if any destination overflowed.
+ *   peer_publish_grad      : dst[b, col_f : col_f + D_f] = grad[b, ...] (/ bag length for MEAN features).
+ *   peer_allreduce_mean    : out[i] = (src_0[i] + ... + src_{W-1}[i]) / W, summed in rank order.
+ *   fused_bwd_sort_peer / fused_bwd_apply_peer : owner side of the backward — tzk_fused_bwd_sort / _apply over the
+ *                            W * cap wire slots of this rank: keys pulled from the sources' wire buffers, gradient
+ *                            slices read from the sources' published gradients; idx_span > every wire_idx.
  * Return 0, or 1 bad argument / 3 launch failure. */
 int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
                                const int64_t* feat_block, const int32_t* feat_owner, const int32_t* feat_dim,
                                const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
                                const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim, float* out,
                                int64_t ld_out, tzk_stream_t stream);
+int tzk_peer_seq_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
+                            const int64_t* feat_block, const int32_t* feat_owner, const int64_t* ids,
+                            const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t D, int64_t nnz, float* out,
+                            tzk_stream_t stream);
 int tzk_peer_barrier(const uint64_t* pad_ptrs, int32_t me, int32_t W, uint32_t* epoch, tzk_stream_t stream);
-int tzk_peer_pull_counts(const uint64_t* counts_ptrs, int32_t me, int32_t W, int32_t F, int32_t* recv_counts,
-                         tzk_stream_t stream);
-int tzk_peer_pull(const uint64_t* ids_ptrs, const uint64_t* pos_ptrs, const uint64_t* grad_ptrs, int32_t me, int32_t W,
-                  int32_t cap, int32_t F, int32_t B, int32_t D, const int32_t* feat_col, const int64_t* bounds,
-                  int64_t ld_grad, int64_t* recv_ids, float* recv_g, tzk_stream_t stream);
+size_t tzk_peer_bucketize_workspace_bytes(int32_t F, int32_t B, int32_t W);
+int tzk_peer_bucketize(const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t W,
+                       const int64_t* feat_block, const int32_t* feat_owner, const int64_t* feat_rows,
+                       const int64_t* rf_key_base, int32_t pooled, int64_t cap, int64_t* wire_key, int32_t* wire_idx,
+                       int32_t* counts, void* workspace, size_t workspace_bytes, tzk_stream_t stream);
+int tzk_peer_publish_grad(const float* grad, int64_t ld_grad, const int32_t* feat_col, const int32_t* feat_dim,
+                          const int32_t* feat_pool, const int64_t* offsets, int32_t F, int32_t B, float* dst,
+                          int64_t ld_dst, tzk_stream_t stream);
+int tzk_peer_allreduce_mean(const uint64_t* src_ptrs, int32_t W, int64_t n, float* out, tzk_stream_t stream);
+int tzk_fused_bwd_sort_peer(const uint64_t* key_ptrs, const uint64_t* idx_ptrs, const uint64_t* count_ptrs, int32_t me,
+                            int32_t W, int64_t cap, int32_t idx_span, int64_t total_keys, int32_t max_dim,
+                            int32_t* overflow, void* workspace, size_t workspace_bytes, tzk_stream_t stream);
+int tzk_fused_bwd_apply_peer(const tzk_opt_args* opt, int32_t pooled, const uint64_t* grad_ptrs, int64_t ld_grad,
+                             const int64_t* feat_w_off, const int64_t* feat_rows, const int32_t* feat_dim,
+                             const int32_t* feat_col, const int32_t* feat_pool, const int64_t* feat_key_base, int32_t F,
+                             int32_t B, int32_t me, int32_t W, int64_t cap, int32_t idx_span, int64_t total_keys,
+                             int32_t max_dim, int32_t vec_ok, float* weights, float grad_scale, void* workspace,
+                             size_t workspace_bytes, tzk_stream_t stream);
 
 #ifdef __cplusplus
 }

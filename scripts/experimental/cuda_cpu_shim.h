@@ -43,6 +43,9 @@ inline thread_local dim3 t_thread, t_block, t_bdim, t_gdim;
 inline thread_local std::barrier<>* t_bar = nullptr;   // per emulated thread: launches may run concurrently
 inline thread_local unsigned char* t_dyn = nullptr;
 inline thread_local std::barrier<>* t_wbar = nullptr;  // the thread's warp (32 consecutive linear thread ids)
+struct WarpSlots { unsigned long long v[32]; unsigned n; };
+inline thread_local WarpSlots* t_wslots = nullptr;     // exchange area of the thread's warp (shuffles, ballots)
+inline thread_local unsigned t_lane = 0;
 
 template <class Body>
 void launch(dim3 grid, dim3 block, size_t smem, Body body) {
@@ -54,7 +57,11 @@ void launch(dim3 grid, dim3 block, size_t smem, Body body) {
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         std::barrier<> bar(n);
         std::vector<std::unique_ptr<std::barrier<>>> warps;
-        for (unsigned w = 0; w * 32 < n; ++w) warps.emplace_back(new std::barrier<>(n - w * 32 < 32 ? n - w * 32 : 32));
+        std::vector<WarpSlots> wslots((n + 31) / 32);
+        for (unsigned w = 0; w * 32 < n; ++w) {
+          warps.emplace_back(new std::barrier<>(n - w * 32 < 32 ? n - w * 32 : 32));
+          wslots[w].n = n - w * 32 < 32 ? n - w * 32 : 32;
+        }
         std::vector<std::thread> threads;
         threads.reserve(n);
         for (unsigned t = 0; t < n; ++t)
@@ -66,6 +73,8 @@ void launch(dim3 grid, dim3 block, size_t smem, Body body) {
             t_bar = &bar;
             t_dyn = base;
             t_wbar = warps[t / 32].get();
+            t_wslots = &wslots[t / 32];
+            t_lane = t % 32;
             body();
             bar.arrive_and_drop();   // a thread that returned early must not strand the others at a barrier
             t_wbar->arrive_and_drop();
@@ -92,6 +101,54 @@ void launch(dim3 grid, dim3 block, size_t smem, Body body) {
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+// ---- warp intrinsics: every live lane of the warp must make the call (the kernels here use full-warp collectives) ----
+namespace tzk_shim {
+template <class T> inline T warp_exchange(T v, unsigned src_lane, bool take) {
+  static_assert(sizeof(T) <= 8, "shuffle of a type wider than 64 bits");
+  unsigned long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  t_wslots->v[t_lane] = raw;
+  t_wbar->arrive_and_wait();
+  T out = v;
+  if (take && src_lane < t_wslots->n) memcpy(&out, &t_wslots->v[src_lane], sizeof(T));
+  t_wbar->arrive_and_wait();
+  return out;
+}
+}  // namespace tzk_shim
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+  const unsigned base = tzk_shim::t_lane / width * width;
+  return tzk_shim::warp_exchange(v, base + (unsigned)(src % width), true);
+}
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
+  const unsigned in = tzk_shim::t_lane % width;
+  return tzk_shim::warp_exchange(v, tzk_shim::t_lane - d, in >= d);
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) {
+  const unsigned in = tzk_shim::t_lane % width;
+  return tzk_shim::warp_exchange(v, tzk_shim::t_lane + d, in + d < (unsigned)width);
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
+  (void)width;
+  return tzk_shim::warp_exchange(v, tzk_shim::t_lane ^ (unsigned)m, true);
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  tzk_shim::t_wslots->v[tzk_shim::t_lane] = pred ? 1ull : 0ull;
+  tzk_shim::t_wbar->arrive_and_wait();
+  unsigned m = 0;
+  for (unsigned l = 0; l < tzk_shim::t_wslots->n; ++l) m |= (unsigned)tzk_shim::t_wslots->v[l] << l;
+  tzk_shim::t_wbar->arrive_and_wait();
+  return m;
+}
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+template <class T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicMax(T* p, T v) {
+  T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
 #define TZK_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(tzk_shim::t_dyn)
 #define TZK_UNPAREN(...) __VA_ARGS__
 #define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) \

@@ -192,3 +192,144 @@ class OracleKernels:
             return (None if dd is None else torch.from_numpy(dd)), torch.from_numpy(ds)
         dd, ds = O.dlrm_interact_bwd(_np(dense), _np(sparse), _np(d_out), Ns, D, copy_dense, copy_sparse)
         return (None if dd is None else torch.from_numpy(dd)), torch.from_numpy(ds)
+
+    # ------------------------------------------------------------------ sharded step over peer memory (model of tzk_peer.cu)
+    # `symm` arguments are the tests' in-process stand-ins for symmetric allocations: `.everyone[r]` = rank r's tensor.
+    @staticmethod
+    def _owner_of(i, block, owner, W):
+        q = i // block
+        r = owner + q
+        if r >= W:
+            q -= r - (W - 1)
+            r = W - 1
+        return r, i - q * block
+
+    def peer_pooled_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W,
+                               out=None):
+        F = lay.num_features
+        blocks, owners = feat_block.tolist(), feat_owner.tolist()
+        rows, w_off = feat_rows.tolist(), rf_w_off.tolist()
+        idl, off = ids.tolist(), offsets.tolist()
+        o = np.zeros((B, lay.total_dim), dtype=np.float32)
+        for f in range(F):
+            D, col = lay.dim[f], lay.col[f]
+            for b in range(B):
+                s, e = off[f * B + b], off[f * B + b + 1]
+                acc = np.zeros(D, dtype=np.float32)
+                for l in range(s, e):
+                    i = idl[l] if 0 <= idl[l] < rows[f] else 0
+                    r, loc = self._owner_of(i, blocks[f], owners[f], W)
+                    base = w_off[r * F + f] + loc * D
+                    acc = acc + tables.everyone[r].numpy()[base:base + D]
+                if lay.pool[f] == 1 and e > s:
+                    acc = acc * np.float32(1.0 / (e - s))
+                o[b, col:col + D] = acc
+        res = torch.from_numpy(o)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def peer_seq_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W):
+        F, D = lay.num_features, lay.dim[0]
+        blocks, owners = feat_block.tolist(), feat_owner.tolist()
+        rows, w_off = feat_rows.tolist(), rf_w_off.tolist()
+        idl, off = ids.tolist(), offsets.tolist()
+        o = np.zeros((len(idl), D), dtype=np.float32)
+        for f in range(F):
+            for l in range(off[f * B], off[(f + 1) * B]):
+                i = idl[l] if 0 <= idl[l] < rows[f] else 0
+                r, loc = self._owner_of(i, blocks[f], owners[f], W)
+                base = w_off[r * F + f] + loc * D
+                o[l] = tables.everyone[r].numpy()[base:base + D]
+        return torch.from_numpy(o)
+
+    def peer_bucketize(self, ids, offsets, F, B, W, feat_block, feat_owner, feat_rows, rf_key_base, pooled, cap,
+                       wire_key, wire_idx, counts):
+        blocks, owners, rows = feat_block.tolist(), feat_owner.tolist(), feat_rows.tolist()
+        kb = rf_key_base.tolist()
+        idl, off = ids.tolist(), offsets.tolist()
+        fill = [0] * W
+        for bag in range(F * B):
+            f = bag // B
+            for l in range(off[bag], off[bag + 1]):
+                i = idl[l] if 0 <= idl[l] < rows[f] else 0
+                r, loc = self._owner_of(i, blocks[f], owners[f], W)
+                if fill[r] < cap:
+                    wire_key[r * cap + fill[r]] = kb[r * F + f] + loc
+                    wire_idx[r * cap + fill[r]] = bag if pooled else l
+                fill[r] += 1
+        for r in range(W):
+            counts[r] = min(fill[r], cap)
+        counts[W] = int(any(c > cap for c in fill))
+
+    def peer_publish_grad(self, grad, lay, offsets, B, dst):
+        g = _np(grad).copy()
+        off = _np(offsets)
+        for f in range(lay.num_features):
+            if lay.pool[f] == 1:
+                L = np.diff(off[f * B:(f + 1) * B + 1]).astype(np.float32)
+                sc = np.where(L > 0, np.float32(1.0) / np.maximum(L, 1), 0).astype(np.float32)
+                g[:, lay.col[f]:lay.col[f] + lay.dim[f]] *= sc[:, None]
+        dst.copy_(torch.from_numpy(g))
+
+    def peer_allreduce_mean(self, srcs, W, n, out):
+        acc = srcs.everyone[0].numpy()[:n].copy()
+        for r in range(1, W):
+            acc = acc + srcs.everyone[r].numpy()[:n]
+        out[:n] = torch.from_numpy(acc * np.float32(1.0 / W))
+
+    def peer_barrier(self, pads, me, W, epoch):
+        raise NotImplementedError("the model's barrier is a threading.Barrier (tests swap PeerBase._barrier)")
+
+    def fused_bwd_workspace_bytes(self, lay, nnz):
+        return 256
+
+    def fused_bwd_sort_peer(self, wire_key, wire_idx, counts, me, W, cap, idx_span, lay, overflow, ws):
+        keys, vals = [], []
+        for r in range(W):
+            c = counts.everyone[r]
+            n = int(c[me])
+            keys.append(wire_key.everyone[r].numpy()[me * cap:me * cap + n].copy())
+            vals.append(r * idx_span + wire_idx.everyone[r].numpy()[me * cap:me * cap + n].astype(np.int64))
+            if overflow is not None and int(c[W]):
+                overflow |= 1
+        if not hasattr(self, "_peer_sorted"):
+            self._peer_sorted = {}
+        self._peer_sorted[ws.data_ptr()] = (np.concatenate(keys), np.concatenate(vals))   # slot order (src-major)
+
+    def fused_bwd_apply_peer(self, optimizer, pooled, grads, ld_grad, weights, state, lay, B, me, W, cap, idx_span, lr,
+                             eps, grad_scale, ws, **ex):
+        from torcheasyrec_b200.kernels import FeatureLayout
+
+        keys, vals = self._peer_sorted.pop(ws.data_ptr())
+        # one "feature" per distinct table, contributions in slot order (the update's stable sort keeps that order)
+        tabs = sorted({(lay.key_base[f], lay.w_off[f], lay.rows[f], lay.dim[f]) for f in range(lay.num_features)
+                       if lay.rows[f] > 0})
+        D = lay.dim[0]
+        col_of = {}
+        for f in range(lay.num_features):
+            col_of[f] = lay.col[f]
+        rows_out, ids_out, lens = [], [], []
+        for (kb, wo, rows, dim) in tabs:
+            sel = np.nonzero((keys >= kb) & (keys < kb + rows))[0]
+            lens.append(len(sel))
+            for s in sel:
+                v = int(vals[s])
+                r, idx = divmod(v, idx_span)
+                if pooled:
+                    f, b = divmod(idx, B)
+                    gsrc = grads.everyone[r].numpy()[:B * ld_grad].reshape(B, ld_grad)[b, col_of[f]:col_of[f] + dim]
+                else:
+                    gsrc = grads.everyone[r].numpy()[idx * ld_grad:idx * ld_grad + dim]
+                rows_out.append(gsrc.astype(np.float32))
+                ids_out.append(int(keys[s]) - kb)
+        tl = FeatureLayout(w_off=[t[1] for t in tabs], rows=[t[2] for t in tabs], dim=[t[3] for t in tabs],
+                           col=[0] * len(tabs), pool=[0] * len(tabs), key_base=[t[0] for t in tabs],
+                           total_keys=lay.total_keys, total_dim=D, arena_elems=lay.arena_elems)
+        if not ids_out:
+            return
+        recv_g = torch.from_numpy(np.stack(rows_out))
+        recv_ids = torch.tensor(ids_out, dtype=torch.int64)
+        bounds = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+        self.fused_bwd(optimizer, False, recv_g, weights, state, tl, recv_ids, bounds, 1, lr, eps, grad_scale, **ex)

@@ -26,29 +26,6 @@ def _free_port():
     return p
 
 
-def _concat_batches(batches):
-    from torcheasyrec_b200.batch import Batch
-    from torcheasyrec_b200.sparse import KeyedJaggedTensor, KeyedTensor
-
-    out = Batch()
-    b0 = batches[0]
-    for dg, kjt0 in b0.sparse_features.items():
-        F, vals, lens = len(kjt0.keys()), [], []
-        dicts = [b.sparse_features[dg].to_dict() for b in batches]
-        for k in kjt0.keys():
-            for d in dicts:
-                vals.append(d[k].values())
-                lens.append(d[k].lengths())
-        out.sparse_features[dg] = KeyedJaggedTensor(kjt0.keys(), torch.cat(vals), lengths=torch.cat(lens),
-                                                    stride=sum(b.sparse_features[dg].stride() for b in batches))
-    for dg, kt0 in b0.dense_features.items():
-        out.dense_features[dg] = KeyedTensor(kt0.keys(), kt0.length_per_key(),
-                                             torch.cat([b.dense_features[dg].values() for b in batches]))
-    for k in b0.labels:
-        out.labels[k] = torch.cat([b.labels[k] for b in batches])
-    return out
-
-
 def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=False, static_capacity=None,
             sparse_opt=None, exchange="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -65,67 +42,12 @@ def _worker(rank, world, port, name, sharding, rw_min_rows, result_q, use_cuda=F
         from oracle_backend import OracleKernels
 
         from torcheasyrec_b200 import functional as Fn
-        from torcheasyrec_b200.distributed import DenseGradSync, shard_model
-        from torcheasyrec_b200.engine import Pipeline
+        from torcheasyrec_b200.verify import verify_sharded
 
-        B = 48
-        # CPU: host logic over gloo with the oracle as compute; GPU: the CUDA kernels over NCCL
+        # CPU: host logic over gloo with the oracle as compute; GPU: the CUDA kernels over NCCL / peer memory
         with (contextlib.nullcontext() if use_cuda else Fn.use_backend(OracleKernels())):
-            ref = Pipeline(name, device=dev, max_rows=300, seed=5, capturable=False)   # unsharded twin
-            shd = Pipeline(name, device=dev, max_rows=300, seed=5, capturable=False)
-            shd.model.load_state_dict(ref.model.state_dict())
-            sharded = shard_model(shd.model, dev, default=sharding, rw_min_rows=rw_min_rows, source=ref.model,
-                                  static_capacity=static_capacity, exchange=exchange)
-            if sparse_opt is not None:     # e.g. "adam": second state + device-side step counter on every shard
-                from torcheasyrec_b200.embedding_modules import SparseOptimizerSpec
-
-                ref.model.set_sparse_optimizer(SparseOptimizerSpec.from_name(sparse_opt, lr=0.01))
-            shd.model.set_sparse_optimizer(ref.model.sparse_collections()[0].optimizer)
-            from torcheasyrec_b200.rank_models import dense_optimizer_from_config
-
-            shd.dense_optimizer = dense_optimizer_from_config(shd.cfg.train_config, shd.model.dense_parameters())
-            shd.grad_sync = DenseGradSync(shd.model.dense_parameters())
-            batches = [ref.synthetic_batch(B, seed=77 + r) for r in range(world)]
-            glob = _concat_batches(batches).to(dev)
-            batches = [b.to(dev) for b in batches]
-            # forward parity (before any update)
-            with torch.no_grad():
-                p_ref = ref.model.predict(glob)
-                p_shd = shd.model.predict(batches[rank])
-            for k, v in p_shd.items():
-                if k.startswith("logits"):
-                    want = p_ref[k][rank * B:(rank + 1) * B].cpu().numpy()
-                    if use_cuda:   # cuBLAS may pick another kernel for batch B vs W*B: not bit-stable across shapes
-                        np.testing.assert_allclose(v.cpu().numpy(), want, rtol=1e-6, atol=1e-7)
-                    else:
-                        np.testing.assert_array_equal(v.cpu().numpy(), want)
-            # one train step on both
-            for _ in range(2):
-                loss_ref = ref.eager_step(glob)
-                loss_shd = shd.eager_step(batches[rank])
-            for sm in sharded:
-                sm.check_overflow()
-            t = torch.tensor([float(loss_shd)], dtype=torch.float64, device=dev)
-            dist.all_reduce(t)
-            np.testing.assert_allclose(t.item() / world, float(loss_ref), rtol=1e-6)
-            # updated tables: gather shards, compare with the unsharded twin
-            ref_tables = {}
-            for coll in ref.model.sparse_collections():
-                for ti, c in enumerate(coll._configs):
-                    ref_tables[(type(coll).__name__, c.name)] = coll.table_weight(ti)
-            for sm in sharded:
-                kind = "EmbeddingBagCollection" if sm._pooled else "EmbeddingCollection"
-                for c in sm._configs:
-                    full = sm.gather_full_table(c.name)
-                    # dL/dlogit is 1/B per rank then /W on the owners vs 1/(W*B) in the twin: same value, one more
-                    # fp32 rounding per contribution -> a few ulp after two Adagrad steps
-                    np.testing.assert_allclose(full.cpu().numpy(), ref_tables[(kind, c.name)].cpu().numpy(), rtol=5e-5, atol=1e-6,
-                                               err_msg=f"{kind}.{c.name}")
-            dense = lambda m: sorted((n, p) for n, p in m.named_parameters() if not n.endswith("weights"))
-            for (n1, p1), (n2, p2) in zip(dense(ref.model), dense(shd.model)):
-                assert n1 == n2
-                # Adam normalises by sqrt(v): tiny gradient differences (mean over 2B vs mean of two means) are amplified
-                np.testing.assert_allclose(p2.detach().cpu().numpy(), p1.detach().cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=n1)
+            verify_sharded(name, dev, sharding, rw_min_rows=rw_min_rows, static_capacity=static_capacity,
+                           exchange=exchange, sparse_opt=sparse_opt, bit_exact_logits=not use_cuda)
         result_q.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
         import traceback

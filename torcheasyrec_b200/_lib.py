@@ -85,14 +85,19 @@ SIGNATURES = {
     "tzk_bce_logits_fwd_bwd": (c_int32, [P, P, c_int64, P, P, P, c_size_t, P]),
     "tzk_peer_pooled_gather_fwd": (
         c_int32, [P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P]),
+    "tzk_peer_seq_gather_fwd": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int64, P, P]),
     "tzk_peer_barrier": (c_int32, [P, c_int32, c_int32, P, P]),
-    "tzk_peer_pull_counts": (c_int32, [P, c_int32, c_int32, c_int32, P, P]),
-    "tzk_peer_pull": (c_int32, [P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, c_int64, P, P, P]),
-    "tzk_dot_interact_bwd": (
+    "tzk_peer_bucketize_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "tzk_peer_bucketize": (
+        c_int32, [P, P, c_int32, c_int32, c_int32, P, P, P, P, c_int32, c_int64, P, P, P, P, c_size_t, P]),
+    "tzk_peer_publish_grad": (c_int32, [P, c_int64, P, P, P, P, c_int32, c_int32, P, c_int64, P]),
+    "tzk_peer_allreduce_mean": (c_int32, [P, c_int32, c_int64, P, P]),
+    "tzk_fused_bwd_sort_peer": (
+        c_int32, [P, P, P, c_int32, c_int32, c_int64, c_int32, c_int64, c_int32, P, P, c_size_t, P]),
+    "tzk_fused_bwd_apply_peer": (
         c_int32,
-        [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, P, c_int64, P,
-         c_int64, P],
-    ),
+        [P, c_int32, P, c_int64, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int64, c_int32, c_int64,
+         c_int32, c_int32, P, c_float, P, c_size_t, P]),
 }
 
 _lib = None

@@ -50,6 +50,12 @@ struct BwdArgs {
   const float* step;  // device scalar: iteration count t >= 1 of this update (bias correction)
   float beta1, beta2, weight_decay, max_gradient;
   float bc1, bc2;     // 1 - beta^t, filled in by init_bias_correction() at kernel start
+  // peer mode (sharded step over peer memory, tzk_peer.cu): the sorted value is src_rank * idx_span + idx and the
+  // gradient row lives in the SOURCE rank's published buffer grad_peer[src_rank] (already divided by the bag length
+  // for MEAN pooling); idx = bag (pooled) or id position (sequence).  peer_w == 0: everything is local.
+  int32_t peer_w;
+  int32_t idx_span;
+  unsigned long long grad_peer[16];
 };
 
 __device__ __forceinline__ void init_bias_correction(BwdArgs& a) {
@@ -127,6 +133,43 @@ linearize_seq_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict_
   }
 }
 
+// ---- 1'. peer mode: the owner reads its chunk of every source rank's wire buffers (tzk_peer.cu: destination-major,
+// fixed capacity, counts per destination) straight into the sort's input.  Slot s = (src r, j): valid while j is below
+// the count r published for this rank; the rest are padding (sentinel key: sorted last, never updated).
+struct PeerWire {
+  unsigned long long key[16], idx[16], cnt[16];   // per source rank: wire_key / wire_idx / counts as mapped here
+  int32_t me, W;
+  int64_t cap;
+  int32_t idx_span, pad;
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads)
+peer_pull_linearize_kernel(const __grid_constant__ PeerWire pw, KeyT sentinel, KeyT* __restrict__ keys,
+                           int32_t* __restrict__ vals, int32_t* __restrict__ overflow) {
+  __shared__ int32_t cnt[16];
+  if ((int)threadIdx.x < pw.W) {
+    const int32_t* c = reinterpret_cast<const int32_t*>(pw.cnt[threadIdx.x]);
+    cnt[threadIdx.x] = c[pw.me];
+    if (blockIdx.x == 0 && overflow && c[pw.W]) atomicOr(overflow, 1);   // any source dropped ids -> every owner knows
+  }
+  __syncthreads();
+  const int64_t n = (int64_t)pw.W * pw.cap;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+    const int r = (int)(s / pw.cap);
+    const int64_t j = s - (int64_t)r * pw.cap;
+    KeyT k = sentinel;
+    int32_t v = 0;
+    if (j < cnt[r]) {
+      k = (KeyT) reinterpret_cast<const int64_t*>(pw.key[r])[(int64_t)pw.me * pw.cap + j];
+      v = r * pw.idx_span + reinterpret_cast<const int32_t*>(pw.idx[r])[(int64_t)pw.me * pw.cap + j];
+    }
+    keys[s] = k;
+    vals[s] = v;
+  }
+}
+
 // sample-owner half of the sharded backward: one gradient row per id position, written to its wire slot
 __global__ void __launch_bounds__(kThreads)
 bag_grad_expand_kernel(const float* __restrict__ grad_out, int64_t ld_grad, const int32_t* __restrict__ feat_col,
@@ -177,22 +220,34 @@ struct Entry {
 
 __device__ __forceinline__ Entry entry_of(const BwdArgs& a, const BwdFeat* fd, int32_t v, int f_hint) {
   Entry en;
+  const float* base = a.grad_out;
+  if (a.peer_w) {
+    const int r = v / a.idx_span;
+    v -= r * a.idx_span;
+    base = reinterpret_cast<const float*>(a.grad_peer[r]);
+  }
   if (a.pooled) {
     const int f = v / a.B;
     const int b = v - f * a.B;
     en.f = f;
-    en.g = a.grad_out + (int64_t)b * a.ld_grad + fd[f].col;
+    en.g = base + (int64_t)b * a.ld_grad + fd[f].col;
     en.scale = a.grad_scale;
-    if (fd[f].pool == TZK_POOL_MEAN) {
+    if (fd[f].pool == TZK_POOL_MEAN && !a.peer_w) {
       const int64_t L = __ldg(a.offsets + v + 1) - __ldg(a.offsets + v);
       en.scale = a.grad_scale / (float)L;  // L >= 1 because the entry exists
     }
   } else {
     en.f = f_hint;
-    en.g = a.grad_out + (int64_t)v * a.ld_grad;
+    en.g = base + (int64_t)v * a.ld_grad;
     en.scale = a.grad_scale;
   }
   return en;
+}
+
+// feature of a sorted entry: from the bag index for pooled layouts, from the key ranges otherwise
+__device__ __forceinline__ int bag_feat(const BwdArgs& a, int32_t v) {
+  if (a.peer_w) v %= a.idx_span;
+  return v / a.B;
 }
 
 template <typename KeyT>
@@ -354,12 +409,12 @@ __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, i
 }
 
 template <int VEC>
-__device__ __forceinline__ void load_grad(const float* p, float (&g)[VEC]) {
+__device__ __forceinline__ void load_grad(const float* p, float (&g)[VEC], int peer) {
   if (VEC == 4) {
-    float4 v = ld_row_f4(p);
+    float4 v = peer ? ld_coh_f4(p) : ld_row_f4(p);   // peer memory: not through the non-coherent path
     g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
   } else {
-    g[0] = __ldg(p);
+    g[0] = peer ? *p : __ldg(p);
   }
 }
 
@@ -466,7 +521,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
       }
       const int32_t v0 = v[u];
       int f00;
-      if (a.pooled) f00 = v0 / a.B; else f00 = feat_of_key<KeyT>(fd, a.F, k0);
+      if (a.pooled) f00 = bag_feat(a, v0); else f00 = feat_of_key<KeyT>(fd, a.F, k0);
       const BwdFeat d = fd[f00];
       const int64_t row = (int64_t)k0 - d.key_base;
       float acc[CH][VEC];
@@ -481,7 +536,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
           const int c = (ch * G + lane) * VEC;
           if (c < d.dim) {
             float gg[VEC];
-            load_grad<VEC>(en.g + c, gg);
+            load_grad<VEC>(en.g + c, gg, a.peer_w);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[ch][k] += gg[k] * en.scale;
           }
@@ -520,7 +575,7 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
     const KeyT key = keys[it.start];
     const int32_t v0 = vals[it.start];
     int f0;
-    if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
+    if (a.pooled) f0 = bag_feat(a, v0); else f0 = feat_of_key<KeyT>(fd, a.F, key);
     const BwdFeat d = fd[f0];
     const int64_t row = (int64_t)key - d.key_base;
 
@@ -544,7 +599,7 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
         if (c < d.dim) {
           float gr[kLU][VEC];
 #pragma unroll
-          for (int u = 0; u < kLU; ++u) load_grad<VEC>(en[u].g + c, gr[u]);
+          for (int u = 0; u < kLU; ++u) load_grad<VEC>(en[u].g + c, gr[u], a.peer_w);
 #pragma unroll
           for (int u = 0; u < kLU; ++u)
             if (ok[u]) {
@@ -597,7 +652,7 @@ long_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int
     const KeyT key = keys[lr.head];
     const int32_t v0 = vals[lr.head];
     int f0;
-    if (a.pooled) f0 = v0 / a.B; else f0 = feat_of_key<KeyT>(fd, a.F, key);
+    if (a.pooled) f0 = bag_feat(a, v0); else f0 = feat_of_key<KeyT>(fd, a.F, key);
     const BwdFeat d = fd[f0];
     float acc[CH][VEC];
 #pragma unroll
@@ -715,11 +770,11 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
       const KeyT key = sk[i + 1];
       if (key == sentinel) continue;
       const int32_t v = sv[i];
-      const int f = a.pooled ? v / a.B : feat_of_key<KeyT>(fd, a.F, key);
+      const int f = a.pooled ? bag_feat(a, v) : feat_of_key<KeyT>(fd, a.F, key);
       fx[u] = f;
       const int dim = fd[f].dim;
       const Entry en = entry_of(a, fd, v, f);
-      if (c < dim) g4[u] = f4_scale(ld_row_f4(en.g + c), en.scale);
+      if (c < dim) g4[u] = f4_scale(a.peer_w ? ld_coh_f4(en.g + c) : ld_row_f4(en.g + c), en.scale);
       if (i == 0 || sk[i] != key) {
         const bool cl = (i == 0) && first_cont;
         const bool cr = (key == k_last) && last_cont;
@@ -865,7 +920,7 @@ carry_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const in
     for (; tt < te; ++tt) acc = f4_add(acc, *reinterpret_cast<const float4*>(carry_last + tt * ROWF + c));
     acc = f4_add(acc, *reinterpret_cast<const float4*>(carry_first + te * ROWF + c));
     const int32_t v0 = vals[pe - 1];
-    const int f0 = a.pooled ? v0 / a.B : feat_of_key<KeyT>(fd, a.F, k0);
+    const int f0 = a.pooled ? bag_feat(a, v0) : feat_of_key<KeyT>(fd, a.F, k0);
     const BwdFeat d = fd[f0];
     float accv[1][4] = {{acc.x, acc.y, acc.z, acc.w}};
     finish_run<G, 4, 1>(a, d, (int64_t)k0 - d.key_base, (int64_t)k0, accv, lane);
@@ -975,7 +1030,10 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
                           const int64_t* feat_key_base, const int64_t* ids, const int64_t* offsets,
                           int32_t F, int32_t B, int64_t nnz, int64_t total_keys, int32_t max_dim,
                           int32_t vec_ok, float* weights, float grad_scale, void* workspace,
-                          size_t workspace_bytes, tzk_stream_t stream) {
+                          size_t workspace_bytes, tzk_stream_t stream, const PeerWire* pw = nullptr,
+                          const uint64_t* grad_ptrs = nullptr, int32_t* overflow = nullptr) {
+  // peer mode (pw != nullptr): nnz = W * cap wire slots; phase 1 pulls the keys from the sources' wire buffers instead
+  // of linearising local ids; phase 2 reads every gradient slice from grad_ptrs[src] (tzk_peer.cu)
   const int32_t optimizer = opt.optimizer;
   float* state = opt.state;
   const float lr = opt.lr, eps = opt.eps;
@@ -985,10 +1043,11 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   if (F == 0 || B == 0 || nnz == 0) return 0;
   TZK_REQUIRE(nnz < ((int64_t)1 << 31) && (int64_t)F * std::max(B, 1) < ((int64_t)1 << 31),
               "fused_bwd: nnz or F*B >= 2^31 not supported");
-  TZK_REQUIRE(feat_rows && feat_key_base && offsets, "fused_bwd: NULL argument");
-  TZK_REQUIRE(!(phases & 1) || ids, "fused_bwd: ids is NULL");
+  TZK_REQUIRE(pw || (feat_rows && feat_key_base && offsets), "fused_bwd: NULL argument");
+  TZK_REQUIRE(!(phases & 1) || ids || pw, "fused_bwd: ids is NULL");
   if (phases & 2) {
-    TZK_REQUIRE(grad_out && feat_w_off && feat_dim && weights, "fused_bwd: NULL argument");
+    TZK_REQUIRE((grad_out || grad_ptrs) && feat_w_off && feat_dim && weights && feat_rows && feat_key_base,
+                "fused_bwd: NULL argument");
     TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
     TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
     TZK_REQUIRE(optimizer < TZK_OPT_ADAM || (opt.state2 && opt.step),
@@ -1014,7 +1073,25 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   const int bits = bits_for(total_keys + 1);   // one spare value above the largest key = padding sentinel
   const uint64_t sentinel = ((uint64_t)1 << bits) - 1;
 
-  if (phases & 1) {
+  if ((phases & 1) && pw) {
+    size_t cub_bytes = L.cub_bytes;
+    cudaError_t ce;
+    const int grid_p = (int)std::min<int64_t>(ceil_div64(nnz, kThreads), kSmCountB200 * 8);
+    if (k64) {
+      peer_pull_linearize_kernel<uint64_t><<<grid_p, kThreads, 0, st>>>(*pw, (uint64_t)sentinel, (uint64_t*)keys_in,
+                                                                         vals_in, overflow);
+      TZK_CHECK_LAUNCH("peer_pull_linearize_kernel");
+      ce = cub_sort<uint64_t>(ws + L.cub_tmp, cub_bytes, (const uint64_t*)keys_in, (uint64_t*)keys_out, vals_in,
+                              vals_out, nnz, bits, st);
+    } else {
+      peer_pull_linearize_kernel<uint32_t><<<grid_p, kThreads, 0, st>>>(*pw, (uint32_t)sentinel, (uint32_t*)keys_in,
+                                                                         vals_in, overflow);
+      TZK_CHECK_LAUNCH("peer_pull_linearize_kernel");
+      ce = cub_sort<uint32_t>(ws + L.cub_tmp, cub_bytes, (const uint32_t*)keys_in, (uint32_t*)keys_out, vals_in,
+                              vals_out, nnz, bits, st);
+    }
+    TZK_REQUIRE(ce == cudaSuccess, "fused_bwd: radix sort failed: %s", cudaGetErrorString(ce));
+  } else if (phases & 1) {
   const int64_t n_bags = (int64_t)F * B;
   int grid_lin = (int)std::min<int64_t>(ceil_div64(n_bags, kThreads), kSmCountB200 * 16);
   size_t cub_bytes = L.cub_bytes;
@@ -1052,8 +1129,18 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   a.pooled = pooled; a.n = nnz; a.sentinel = sentinel;
   a.state2 = opt.state2; a.step = opt.step; a.beta1 = opt.beta1; a.beta2 = opt.beta2;
   a.weight_decay = opt.weight_decay; a.max_gradient = opt.max_gradient; a.bc1 = a.bc2 = 1.f;
+  a.peer_w = 0; a.idx_span = 1;
+  for (int r = 0; r < 16; ++r) a.grad_peer[r] = 0ull;
+  if (pw) {
+    TZK_REQUIRE(grad_ptrs, "fused_bwd: peer mode needs the published gradient pointers");
+    a.peer_w = pw->W; a.idx_span = pw->idx_span;
+    for (int r = 0; r < pw->W; ++r) a.grad_peer[r] = grad_ptrs[r];
+    a.grad_out = reinterpret_cast<const float*>(grad_ptrs[pw->me]);
+  }
 
-  const int vec = (vec_ok && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)grad_out % 16 == 0) &&
+  bool peers_aligned = true;
+  for (int r = 0; r < a.peer_w; ++r) peers_aligned = peers_aligned && (a.grad_peer[r] % 16 == 0);
+  const int vec = (vec_ok && peers_aligned && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)a.grad_out % 16 == 0) &&
                    (ld_grad % 4 == 0) &&
                    (!(optimizer == TZK_OPT_ADAGRAD || optimizer >= TZK_OPT_ADAM) || (uintptr_t)state % 16 == 0) &&
                    (optimizer != TZK_OPT_ADAM || (uintptr_t)opt.state2 % 16 == 0))
@@ -1197,6 +1284,57 @@ extern "C" int tzk_fused_bwd_apply_ex(const tzk_opt_args* opt, int32_t pooled, c
   return fused_bwd_impl(2, *opt, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
                         feat_key_base, nullptr, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, grad_scale,
                         workspace, workspace_bytes, stream);
+}
+
+static int fill_wire(PeerWire* pw, const uint64_t* key_ptrs, const uint64_t* idx_ptrs, const uint64_t* count_ptrs,
+                     int32_t me, int32_t W, int64_t cap, int32_t idx_span) {
+  if (W < 1 || W > 16 || me < 0 || me >= W || cap < 1 || idx_span < 1) return 1;
+  if ((int64_t)W * idx_span >= ((int64_t)1 << 31) || (int64_t)W * cap >= ((int64_t)1 << 31)) return 1;
+  for (int r = 0; r < 16; ++r) {
+    pw->key[r] = (r < W && key_ptrs) ? key_ptrs[r] : 0ull;
+    pw->idx[r] = (r < W && idx_ptrs) ? idx_ptrs[r] : 0ull;
+    pw->cnt[r] = (r < W && count_ptrs) ? count_ptrs[r] : 0ull;
+  }
+  pw->me = me; pw->W = W; pw->cap = cap; pw->idx_span = idx_span; pw->pad = 0;
+  return 0;
+}
+
+// Owner side of the peer-memory backward, id half: pull this rank's chunk of every source's wire buffers
+// (tzk_peer_bucketize) into the sort input and sort.  `*_ptrs`: HOST arrays [W] of device addresses (rank r's buffer as
+// mapped in this process).  The workspace must be the one later handed to tzk_fused_bwd_apply_peer
+// (tzk_fused_bwd_workspace_bytes(W * cap, total_keys, max_dim)).  `overflow` (device int32, may be NULL) is OR-ed with
+// every source's overflow flag.
+extern "C" int tzk_fused_bwd_sort_peer(const uint64_t* key_ptrs, const uint64_t* idx_ptrs, const uint64_t* count_ptrs,
+                                       int32_t me, int32_t W, int64_t cap, int32_t idx_span, int64_t total_keys,
+                                       int32_t max_dim, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                       tzk_stream_t stream) {
+  PeerWire pw;
+  TZK_REQUIRE(key_ptrs && idx_ptrs && count_ptrs && fill_wire(&pw, key_ptrs, idx_ptrs, count_ptrs, me, W, cap, idx_span) == 0,
+              "fused_bwd_sort_peer: bad wire description");
+  return fused_bwd_impl(1, classic_opt(TZK_OPT_SGD, nullptr, 0.f, 0.f), 0, nullptr, 0, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, nullptr, nullptr, 1, 1, (int64_t)W * cap, total_keys, max_dim, 0,
+                        nullptr, 0.f, workspace, workspace_bytes, stream, &pw, nullptr, overflow);
+}
+
+// Owner side, gradient half: the run kernels of tzk_fused_bwd_apply over the W * cap sorted wire slots, every gradient
+// slice fetched from the source rank's published gradient (grad_ptrs[src]: [B, ld_grad] pooled-output gradient, MEAN
+// bags already divided by their length; or [nnz, ld_grad] rows for sequence collections).  B = bags per feature of a
+// source batch (pooled) — every rank runs the same batch size.
+extern "C" int tzk_fused_bwd_apply_peer(const tzk_opt_args* opt, int32_t pooled, const uint64_t* grad_ptrs,
+                                        int64_t ld_grad, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                        const int32_t* feat_dim, const int32_t* feat_col, const int32_t* feat_pool,
+                                        const int64_t* feat_key_base, int32_t F, int32_t B, int32_t me, int32_t W,
+                                        int64_t cap, int32_t idx_span, int64_t total_keys, int32_t max_dim,
+                                        int32_t vec_ok, float* weights, float grad_scale, void* workspace,
+                                        size_t workspace_bytes, tzk_stream_t stream) {
+  TZK_REQUIRE(opt != nullptr && grad_ptrs != nullptr, "fused_bwd_apply_peer: NULL argument");
+  PeerWire pw;
+  TZK_REQUIRE(fill_wire(&pw, nullptr, nullptr, nullptr, me, W, cap, idx_span) == 0,
+              "fused_bwd_apply_peer: bad wire description");
+  TZK_REQUIRE(!pooled || (int64_t)F * B <= idx_span, "fused_bwd_apply_peer: idx_span smaller than F * B");
+  return fused_bwd_impl(2, *opt, pooled, nullptr, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
+                        feat_key_base, nullptr, nullptr, F, B, (int64_t)W * cap, total_keys, max_dim, vec_ok, weights,
+                        grad_scale, workspace, workspace_bytes, stream, &pw, grad_ptrs, nullptr);
 }
 
 extern "C" int tzk_bag_grad_expand(const float* grad_out, int64_t ld_grad, const int32_t* feat_col,

@@ -46,6 +46,12 @@ __device__ __forceinline__ float4 ld_row_f4(const float* p) {
                : "l"(p));
   return r;
 }
+// rows another GPU of the NVSwitch domain published (peer memory): coherent, no L1 allocation, free to issue back to back
+__device__ __forceinline__ float4 ld_coh_f4(const float* p) {
+  float4 r;
+  asm("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 // rows that the same kernel writes back (weights / optimizer state): coherent load
 // (measured, round 1: neither cudaLimitMaxL2FetchGranularity 32/64/128 nor the .L2::64B load hint changes the gather
 //  or fused-backward time on B200 — the default fetch granularity is already 64 B)

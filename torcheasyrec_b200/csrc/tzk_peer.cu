@@ -1,25 +1,32 @@
 // tzk_peer.cu — the sharded sparse step over peer memory (part of libtzk.so; exchange="peer" in shard_model).
 //
-// Round-2 groundwork: the sharded sparse step without a single collective call.  Every rank's
-// table arena, its bucketized wire buffers and its pooled-output gradient live in symmetric (peer-mapped) memory of
-// the NVSwitch domain, and the kernels read them in place:
+// The sharded sparse step without a collective call.  Every rank's table arena, its wire buffers and its
+// published gradient live in symmetric (peer-mapped) memory of the NVSwitch domain, and the kernels read them in place:
 //
-//   forward   peer_pooled_gather_fwd_kernel: the REQUESTER's gather reads each embedding row straight from the owning
-//             rank's arena (owner = feat_owner + id / block, the same rule as tzk_dist.cu's dest_of) and pools
-//             locally, in bag order — no id exchange, no row exchange, no staging, any bag length, same bits as the
-//             unsharded gather.  (Replaces: bucketize -> ids all-to-all -> owner gather -> rows all-to-all -> local
-//             pooling; the reference's KJTAllToAll + lookup + PooledEmbeddingsAllToAll)
-//   backward  each rank bucketizes its ids into its OWN wire buffer (tzk_bucketize_rw, fixed capacity per
-//             destination) and publishes its gradient [B, sum D]; after one barrier the OWNER pulls, per source
-//             rank, its chunk of ids / positions and the matching 64-B gradient slices (peer_pull_kernel) into the
-//             buffers tzk_fused_bwd already takes; a second barrier closes the step (tables are quiescent again).
+//   forward   peer_pooled_gather_fwd_kernel / peer_seq_gather_fwd_kernel: the REQUESTER's gather reads each embedding
+//             row straight from the owning rank's arena (owner = feat_owner + id / block, the same rule as tzk_dist.cu's
+//             dest_of) — no id exchange, no row exchange, no staging, any bag length, same bits as the unsharded
+//             gather.  (Replaces: bucketize -> ids all-to-all -> owner gather -> rows all-to-all -> local pooling; the
+//             reference's KJTAllToAll + lookup + PooledEmbeddingsAllToAll)
+//   backward  source side (tzk_peer_bucketize, on a side stream during the forward pass): a stable multi-split of the
+//             rank's ids by destination into its OWN wire buffers — per destination, in (feature, bag, position)
+//             order: wire_key = the owner-local linearised (table,row) key, wire_idx = bag (pooled) / id position
+//             (sequence) — plus the per-destination counts.  No [W*F*B] lengths array, no scan over it: per-tile
+//             destination histograms (1024 bags a tile), one scan per destination over the tiles, one scatter pass.
+//             owner side (tzk_bwd.cu: tzk_fused_bwd_sort_peer / tzk_fused_bwd_apply_peer): after a barrier the owner
+//             reads, per source, its chunk of keys / indices straight into the radix sort's input (coalesced NVLink
+//             reads), sorts, and the run kernels fetch every 64-B gradient slice from the SOURCE's published gradient
+//             buffer in place.  No gradient expansion, no gradient all-to-all, no staging copy.
 //   barrier   peer_barrier_kernel: one flag per (src, dst) pair in symmetric memory, st.release.sys / ld.acquire.sys,
-//             epoch kept on the device so the whole step replays as one CUDA graph.
+//             epoch kept on the device so the whole step replays as one CUDA graph.  Barrier sites that may run
+//             concurrently (different streams) use different flag arrays / epochs.
+//   dense     peer_allreduce_mean_kernel: the replicated dense gradients, summed in rank order straight out of every
+//             rank's published flat buffer (bit-identical on every rank; replaces the DDP all-reduce).
 //
-// Build + try (next round, 2 GPUs):
-//   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 scripts/experimental/try_peer.py
+// This file compiles for the host too (TZK_CPU_SHIM, tests/test_peer_exchange_model.py runs the kernels' source on
+// std::threads), so it uses plain CUDA + warp shuffles only; the barrier (PTX) is excluded from that build.
 #ifdef TZK_CPU_SHIM
-#include "../../scripts/experimental/cuda_cpu_shim.h"   // host execution for tests/test_experimental_kernels_cpu.py (not the barrier kernel)
+#include "cuda_cpu_shim.h"
 #else
 #include <cuda_runtime.h>
 #define TZK_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
@@ -44,6 +51,26 @@ struct FeatDesc {
 };
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// Rows that another GPU rewrote in the previous step: a coherent load (not ld.global.nc) that does not allocate in L1.
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+#ifdef TZK_CPU_SHIM
+  return *reinterpret_cast<const float4*>(p);
+#else
+  float4 r;
+  asm("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+#endif
+}
+
+// owner rank and owner-local row of a (clamped) id — tzk_dist.cu's dest_of
+__device__ __forceinline__ int owner_of(int64_t id, int64_t block, int owner, int W, int64_t* local) {
+  int64_t q = id / block;
+  int64_t r = owner + q;
+  if (r >= W) { q -= r - (W - 1); r = W - 1; }
+  *local = id - q * block;
+  return (int)r;
+}
 
 // ---- forward: requester-side gather over peer memory ------------------------------------------------------------
 // A CTA owns 32 consecutive samples x all features (its output block is contiguous); a bag is served by G lanes,
@@ -75,10 +102,9 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
 
   auto row_ptr = [&](int f, const FeatDesc& d, int64_t id) -> const float* {
     if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-    int64_t q = id / d.block;
-    int64_t r = d.owner + q;
-    if (r >= W) { q -= r - (W - 1); r = W - 1; }
-    return reinterpret_cast<const float*>(base[r]) + w_off[r * F + f] + (id - q * d.block) * d.dim;
+    int64_t loc;
+    const int r = owner_of(id, d.block, d.owner, W, &loc);
+    return reinterpret_cast<const float*>(base[r]) + w_off[r * F + f] + loc * d.dim;
   };
 
   const int g = threadIdx.x / G, lane = threadIdx.x % G;
@@ -87,7 +113,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b0 = tile * TB;
     for (int i0 = g; i0 < items; i0 += NG * U) {
-      int32_t s[U];                       // nnz < 2^31 (tzk_bucketize_rw's own limit)
+      int32_t s[U];                       // nnz < 2^31
       int32_t len[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -110,7 +136,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
         if (len[u] > 0) {
           const int f = (i0 + u * NG) / TB;
           const FeatDesc& d = fd[f];
-          if (lane * 4 < d.dim) acc[u] = __ldg(reinterpret_cast<const float4*>(row_ptr(f, d, id0[u]) + lane * 4));
+          if (lane * 4 < d.dim) acc[u] = ld_peer_f4(row_ptr(f, d, id0[u]) + lane * 4);
         }
       }
 #pragma unroll
@@ -122,9 +148,9 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
         for (int c = lane * 4; c < d.dim; c += G * 4) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
           if (len[u] > 0) {
-            a = (c == lane * 4) ? acc[u] : __ldg(reinterpret_cast<const float4*>(row_ptr(f, d, id0[u]) + c));
+            a = (c == lane * 4) ? acc[u] : ld_peer_f4(row_ptr(f, d, id0[u]) + c);
             for (int l = 1; l < len[u]; ++l)
-              a = f4_add(a, __ldg(reinterpret_cast<const float4*>(row_ptr(f, d, __ldg(ids + s[u] + l)) + c)));
+              a = f4_add(a, ld_peer_f4(row_ptr(f, d, __ldg(ids + s[u] + l)) + c));
             if (d.pool == 1) {
               const float inv = 1.0f / (float)len[u];
               a = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
@@ -134,6 +160,257 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
         }
       }
     }
+  }
+}
+
+// un-pooled (sequence) lookup: one lane group per id position, feature by binary search over the segment starts
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+peer_seq_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_t* __restrict__ rf_w_off,
+                           const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_block,
+                           const int32_t* __restrict__ feat_owner, const int64_t* __restrict__ ids,
+                           const int64_t* __restrict__ offsets, int F, int B, int W, int D, int64_t nnz,
+                           float* __restrict__ out) {
+  constexpr int NG = kThreads / G, U = 4;
+  TZK_DYN_SMEM(unsigned char, smem_raw);
+  int64_t* seg = reinterpret_cast<int64_t*>(smem_raw);   // [F + 1] first id position of every feature
+  int64_t* rows = seg + (F + 1);                          // [F]
+  int64_t* block = rows + F;                              // [F]
+  int64_t* w_off = block + F;                             // [W * F]
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(w_off + (size_t)W * F);   // [W]
+  int32_t* owner = reinterpret_cast<int32_t*>(base + W);  // [F]
+  for (int f = threadIdx.x; f <= F; f += kThreads) seg[f] = offsets[(int64_t)f * B];
+  for (int f = threadIdx.x; f < F; f += kThreads) {
+    rows[f] = feat_rows[f];
+    block[f] = feat_block[f];
+    owner[f] = feat_owner ? feat_owner[f] : 0;
+  }
+  for (int i = threadIdx.x; i < W * F; i += kThreads) w_off[i] = rf_w_off[i];
+  if (threadIdx.x < W) base[threadIdx.x] = tables.p[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x % G;
+  const int64_t stride = (int64_t)gridDim.x * NG * U;
+  for (int64_t l0 = ((int64_t)blockIdx.x * NG + threadIdx.x / G) * U; l0 < nnz; l0 += stride) {
+    const float* src[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t l = l0 + u;
+      src[u] = nullptr;
+      if (l < nnz) {
+        int lo = 0, hi = F;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (seg[mid] <= l) lo = mid; else hi = mid;
+        }
+        int64_t id = __ldg(ids + l);
+        if ((uint64_t)id >= (uint64_t)rows[lo]) id = 0;
+        int64_t loc;
+        const int r = owner_of(id, block[lo], owner[lo], W, &loc);
+        src[u] = reinterpret_cast<const float*>(base[r]) + w_off[r * F + lo] + loc * D;
+      }
+    }
+    for (int c = lane * 4; c < D; c += G * 4) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = src[u] ? ld_peer_f4(src[u] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (src[u]) *reinterpret_cast<float4*>(out + (l0 + u) * D + c) = v[u];
+    }
+  }
+}
+
+// ---- source side of the backward: stable multi-split of the ids by destination ---------------------------------------
+// A tile = kBktTile consecutive bags (key-major order), 4 per thread; order inside a destination = bag order, then the
+// order of the ids inside the bag — the order the unsharded backward's stable sort sees.
+constexpr int kBktPerThread = 4;
+constexpr int kBktTile = kThreads * kBktPerThread;
+
+struct BktFeat {
+  int64_t rows, block;
+  int32_t owner, pad;
+};
+
+__device__ __forceinline__ void bkt_stage(BktFeat* fd, const int64_t* feat_rows, const int64_t* feat_block,
+                                          const int32_t* feat_owner, int F) {
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    fd[f].rows = feat_rows[f];
+    fd[f].block = feat_block[f];
+    fd[f].owner = feat_owner ? feat_owner[f] : 0;
+    fd[f].pad = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_bkt_count_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
+                      const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_block,
+                      const int32_t* __restrict__ feat_owner, int F, int B, int W, int32_t* __restrict__ tile_counts,
+                      int32_t* __restrict__ counts) {
+  TZK_DYN_SMEM(unsigned char, smem_raw);
+  BktFeat* fd = reinterpret_cast<BktFeat*>(smem_raw);
+  int32_t* hist = reinterpret_cast<int32_t*>(fd + F);   // [W]
+  bkt_stage(fd, feat_rows, feat_block, feat_owner, F);
+  if ((int)threadIdx.x < W) hist[threadIdx.x] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[W] = 0;   // this step's overflow flag (set by the scan kernel)
+  __syncthreads();
+  const int64_t n_bags = (int64_t)F * B;
+  const int64_t bag0 = (int64_t)blockIdx.x * kBktTile + (int64_t)threadIdx.x * kBktPerThread;
+  for (int k = 0; k < kBktPerThread; ++k) {
+    const int64_t bag = bag0 + k;
+    if (bag >= n_bags) break;
+    const BktFeat d = fd[bag / B];
+    const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
+    for (int64_t l = s; l < e; ++l) {
+      int64_t id = __ldg(ids + l), loc;
+      if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
+      atomicAdd(hist + owner_of(id, d.block, d.owner, W, &loc), (int32_t)1);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < W) tile_counts[(int64_t)blockIdx.x * W + threadIdx.x] = hist[threadIdx.x];
+}
+
+// CTA w: exclusive scan over the tiles of destination w's counts (in place), total -> counts[w] (clamped to cap)
+__global__ void __launch_bounds__(1024)
+peer_bkt_scan_kernel(int32_t* __restrict__ tile_counts, int64_t n_tiles, int W, int64_t cap, int32_t* __restrict__ counts) {
+  TZK_DYN_SMEM(int32_t, warp_tot);   // [32]
+  const int w = blockIdx.x;
+  const int T = blockDim.x;
+  const int64_t per = (n_tiles + T - 1) / T;
+  const int64_t t0 = (int64_t)threadIdx.x * per, t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+  int32_t local = 0;
+  for (int64_t t = t0; t < t1; ++t) local += tile_counts[t * W + w];
+  // block-wide exclusive scan of `local`
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t inc = local;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  int32_t before = 0, total = 0;
+  for (int i = 0; i < (T + 31) / 32; ++i) {
+    const int32_t v = warp_tot[i];
+    if (i < wid) before += v;
+    total += v;
+  }
+  int32_t run = before + inc - local;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int32_t c = tile_counts[t * W + w];
+    tile_counts[t * W + w] = run;
+    run += c;
+  }
+  if (threadIdx.x == 0) {
+    counts[w] = (int64_t)total < cap ? total : (int32_t)cap;
+    if ((int64_t)total > cap) atomicOr(counts + W, (int32_t)1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_bkt_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
+                        const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ feat_block,
+                        const int32_t* __restrict__ feat_owner, const int64_t* __restrict__ rf_key_base, int F, int B,
+                        int W, int pooled, int64_t cap, const int32_t* __restrict__ tile_base,
+                        int64_t* __restrict__ wire_key, int32_t* __restrict__ wire_idx) {
+  TZK_DYN_SMEM(unsigned char, smem_raw);
+  BktFeat* fd = reinterpret_cast<BktFeat*>(smem_raw);
+  int32_t* sbase = reinterpret_cast<int32_t*>(fd + F);            // [W][kThreads]: next slot of (destination, thread)
+  int32_t* wtot = sbase + (size_t)W * kThreads;                   // [W][8] warp totals
+  bkt_stage(fd, feat_rows, feat_block, feat_owner, F);
+  for (int i = threadIdx.x; i < W * kThreads; i += kThreads) sbase[i] = 0;
+  __syncthreads();
+  const int64_t n_bags = (int64_t)F * B;
+  const int64_t bag0 = (int64_t)blockIdx.x * kBktTile + (int64_t)threadIdx.x * kBktPerThread;
+  // pass 1: this thread's count per destination
+  for (int k = 0; k < kBktPerThread; ++k) {
+    const int64_t bag = bag0 + k;
+    if (bag >= n_bags) break;
+    const BktFeat d = fd[bag / B];
+    const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
+    for (int64_t l = s; l < e; ++l) {
+      int64_t id = __ldg(ids + l), loc;
+      if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
+      sbase[owner_of(id, d.block, d.owner, W, &loc) * kThreads + threadIdx.x] += 1;
+    }
+  }
+  // exclusive scan over the threads of the tile, per destination (thread order = bag order)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t mine[kMaxPeers];
+#pragma unroll
+  for (int w = 0; w < kMaxPeers; ++w) {
+    mine[w] = 0;
+    if (w < W) {                      // (W is block-uniform: every lane takes the same branch)
+      const int32_t c = sbase[w * kThreads + threadIdx.x];
+      int32_t inc = c;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      if (lane == 31) wtot[w * 8 + wid] = inc;
+      mine[w] = inc - c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kMaxPeers; ++w) {
+    if (w < W) {
+      int32_t before = 0;
+      for (int i = 0; i < wid; ++i) before += wtot[w * 8 + i];
+      sbase[w * kThreads + threadIdx.x] = tile_base[(int64_t)blockIdx.x * W + w] + before + mine[w];
+    }
+  }
+  // (each thread only touches its own column of sbase from here on: no barrier needed)
+  // pass 2: write
+  for (int k = 0; k < kBktPerThread; ++k) {
+    const int64_t bag = bag0 + k;
+    if (bag >= n_bags) break;
+    const int f = (int)(bag / B);
+    const BktFeat d = fd[f];
+    const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
+    for (int64_t l = s; l < e; ++l) {
+      int64_t id = __ldg(ids + l), loc;
+      if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
+      const int r = owner_of(id, d.block, d.owner, W, &loc);
+      const int32_t slot = sbase[r * kThreads + threadIdx.x]++;
+      if (slot < cap) {               // ids beyond the wire capacity are dropped; the overflow flag reports it
+        wire_key[(int64_t)r * cap + slot] = __ldg(rf_key_base + (int64_t)r * F + f) + loc;
+        wire_idx[(int64_t)r * cap + slot] = pooled ? (int32_t)bag : (int32_t)l;
+      }
+    }
+  }
+}
+
+// ---- publish the pooled-output gradient: dst = grad (MEAN bags pre-divided by their length, so that the owner needs
+// nothing but the 64-B slice) ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+peer_publish_grad_kernel(const float* __restrict__ grad, int64_t ld_grad, const int32_t* __restrict__ feat_col,
+                         const int32_t* __restrict__ feat_dim, const int32_t* __restrict__ feat_pool,
+                         const int64_t* __restrict__ offsets, int F, int B, float* __restrict__ dst, int64_t ld_dst) {
+  const int64_t n = (int64_t)F * B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / F), f = (int)(i - (int64_t)b * F);       // consecutive threads: consecutive columns of a row
+    const int col = __ldg(feat_col + f), dim = __ldg(feat_dim + f);
+    float sc = 1.f;
+    if (__ldg(feat_pool + f) == 1) {
+      const int64_t bag = (int64_t)f * B + b;
+      const int64_t L = __ldg(offsets + bag + 1) - __ldg(offsets + bag);
+      sc = L > 0 ? 1.0f / (float)L : 0.f;
+    }
+    const float* s = grad + (int64_t)b * ld_grad + col;
+    float* d = dst + (int64_t)b * ld_dst + col;
+    for (int c = 0; c < dim; ++c) d[c] = s[c] * sc;
+  }
+}
+
+// ---- dense gradients: out = mean over ranks of src_r, summed in rank order (the same bits on every rank) --------------
+__global__ void __launch_bounds__(kThreads)
+peer_allreduce_mean_kernel(const __grid_constant__ Peers src, int W, int64_t n, float* __restrict__ out) {
+  const float inv = 1.0f / (float)W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = reinterpret_cast<const float*>(src.p[0])[i];
+    for (int r = 1; r < W; ++r) acc += reinterpret_cast<const float*>(src.p[r])[i];
+    out[i] = acc * inv;
   }
 }
 
@@ -158,55 +435,10 @@ __global__ void peer_barrier_kernel(const __grid_constant__ Peers pads, int me, 
     } while ((int32_t)(v - e) < 0);
   }
 }
-
 #endif  // TZK_CPU_SHIM
 
-// ---- backward: owner-side pull ----------------------------------------------------------------------------------
-// recv_counts[src, f] = counts of rank src for destination `me`
-__global__ void peer_pull_counts_kernel(const __grid_constant__ Peers counts, int me, int W, int F, int32_t* __restrict__ recv_counts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < W * F) {
-    const int r = i / F, f = i - r * F;
-    recv_counts[i] = reinterpret_cast<const int32_t*>(counts.p[r])[me * F + f];
-  }
-}
-
-// slot s = (src r, j): id / original position from r's wire chunk for me, gradient slice from r's gradient buffer.
-// bounds = the owner-side offsets tzk_fused_bwd gets ([W * (F + 1) + 1]: per source F feature runs + the padding
-// run); slots in the padding run get id 0 and a zero row (the layout marks that run rows = 0, the update skips it).
-template <int G>
-__global__ void __launch_bounds__(kThreads)
-peer_pull_kernel(const __grid_constant__ Peers wire_ids, const __grid_constant__ Peers wire_pos,
-                 const __grid_constant__ Peers grads, int me, int W, int cap, int F, int B, int D,
-                 const int32_t* __restrict__ feat_col, const int64_t* __restrict__ bounds, int64_t ld_grad,
-                 int64_t* __restrict__ recv_ids, float* __restrict__ recv_g) {
-  constexpr int NG = kThreads / G;
-  const int lane = threadIdx.x % G;
-  const int64_t n_slots = (int64_t)W * cap;
-  for (int64_t s = (int64_t)blockIdx.x * NG + threadIdx.x / G; s < n_slots; s += (int64_t)gridDim.x * NG) {
-    const int r = (int)(s / cap);
-    const int64_t j = s - (int64_t)r * cap;
-    const bool valid = s < __ldg(bounds + (int64_t)r * (F + 1) + F);
-    int64_t id = 0;
-    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      id = reinterpret_cast<const int64_t*>(wire_ids.p[r])[(int64_t)me * cap + j];
-      const int32_t pos = reinterpret_cast<const int32_t*>(wire_pos.p[r])[(int64_t)me * cap + j];
-      const int f = pos / B, b = pos - f * B;                  // one id per bag: position = f * B + b
-      const float* src = reinterpret_cast<const float*>(grads.p[r]) + (int64_t)b * ld_grad + __ldg(feat_col + f);
-      for (int c = lane * 4; c < D; c += G * 4) {
-        gv = *reinterpret_cast<const float4*>(src + c);
-        *reinterpret_cast<float4*>(recv_g + s * D + c) = gv;
-      }
-    } else {
-      for (int c = lane * 4; c < D; c += G * 4) *reinterpret_cast<float4*>(recv_g + s * D + c) = gv;
-    }
-    if (lane == 0) recv_ids[s] = id;
-  }
-}
-
 int fill(Peers* dst, const uint64_t* host_ptrs, int W) {
-  if (W < 1 || W > kMaxPeers) return 1;
+  if (W < 1 || W > kMaxPeers || !host_ptrs) return 1;
   for (int r = 0; r < kMaxPeers; ++r) dst->p[r] = r < W ? host_ptrs[r] : 0ull;
   return 0;
 }
@@ -217,6 +449,7 @@ int grid_for(int64_t work_ctas) {
   const int64_t cap = (int64_t)sms * 8;
   return (int)(work_ctas < cap ? (work_ctas > 0 ? work_ctas : 1) : cap);
 }
+inline int64_t bkt_tiles(int64_t n_bags) { return (n_bags + kBktTile - 1) / kBktTile; }
 }  // namespace
 
 // table_ptrs: HOST array [W] of device addresses (rank r's arena as mapped in THIS process); rf_w_off: device
@@ -242,39 +475,81 @@ extern "C" int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int6
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
-#ifndef TZK_CPU_SHIM
-extern "C" int tzk_peer_barrier(const uint64_t* pad_ptrs, int32_t me, int32_t W, uint32_t* epoch, void* stream) {
-  Peers p;
-  if (fill(&p, pad_ptrs, W) || me < 0 || me >= W) return 1;
-  peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, me, W, epoch);
-  return cudaGetLastError() == cudaSuccess ? 0 : 3;
-}
-#endif
-
-extern "C" int tzk_peer_pull_counts(const uint64_t* counts_ptrs, int32_t me, int32_t W, int32_t F, int32_t* recv_counts,
-                                    void* stream) {
-  Peers p;
-  if (fill(&p, counts_ptrs, W) || F <= 0) return 1;
-  TZK_LAUNCH((peer_pull_counts_kernel), (W * F + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream), p, me, W, F,
-             recv_counts);
-  return cudaGetLastError() == cudaSuccess ? 0 : 3;
-}
-
-extern "C" int tzk_peer_pull(const uint64_t* ids_ptrs, const uint64_t* pos_ptrs, const uint64_t* grad_ptrs, int32_t me,
-                             int32_t W, int32_t cap, int32_t F, int32_t B, int32_t D, const int32_t* feat_col,
-                             const int64_t* bounds, int64_t ld_grad, int64_t* recv_ids, float* recv_g, void* stream) {
-  Peers pi, pp, pg;
-  if (fill(&pi, ids_ptrs, W) || fill(&pp, pos_ptrs, W) || fill(&pg, grad_ptrs, W)) return 1;
-  if (cap <= 0 || F <= 0 || B <= 0 || D <= 0 || (D % 4) || (ld_grad % 4)) return 1;
+extern "C" int tzk_peer_seq_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
+                                       const int64_t* feat_block, const int32_t* feat_owner, const int64_t* ids,
+                                       const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t D, int64_t nnz,
+                                       float* out, void* stream) {
+  Peers t;
+  if (fill(&t, table_ptrs, W) || F <= 0 || B <= 0 || D <= 0 || (D % 4) || nnz < 0) return 1;
+  if (nnz == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int64_t slots = (int64_t)W * cap;
-#define TZK_PEER_LAUNCH(G)                                                                                          \
-  TZK_LAUNCH((peer_pull_kernel<G>), grid_for((slots + kThreads / G - 1) / (kThreads / G)), kThreads, 0, st, pi, pp, pg, \
-             me, W, cap, F, B, D, feat_col, bounds, ld_grad, recv_ids, recv_g)
+  const size_t smem = (size_t)(F + 1) * 8 + (size_t)F * 16 + (size_t)W * F * 8 + (size_t)W * 8 + (size_t)F * 4 + 16;
+#define TZK_PEER_LAUNCH(G)                                                                                            \
+  TZK_LAUNCH((peer_seq_gather_fwd_kernel<G>), grid_for((nnz + (kThreads / G) * 4 - 1) / ((kThreads / G) * 4)),        \
+             kThreads, smem, st, t, rf_w_off, feat_rows, feat_block, feat_owner, ids, offsets, F, B, W, D, nnz, out)
   if (D <= 16) TZK_PEER_LAUNCH(4);
   else if (D <= 32) TZK_PEER_LAUNCH(8);
   else if (D <= 64) TZK_PEER_LAUNCH(16);
   else TZK_PEER_LAUNCH(32);
 #undef TZK_PEER_LAUNCH
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+#ifndef TZK_CPU_SHIM
+extern "C" int tzk_peer_barrier(const uint64_t* pad_ptrs, int32_t me, int32_t W, uint32_t* epoch, void* stream) {
+  Peers p;
+  if (fill(&p, pad_ptrs, W) || me < 0 || me >= W || !epoch) return 1;
+  peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, me, W, epoch);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+#endif
+
+// workspace: per-tile destination counts / bases, int32 [tiles * W]
+extern "C" size_t tzk_peer_bucketize_workspace_bytes(int32_t F, int32_t B, int32_t W) {
+  return (size_t)(bkt_tiles((int64_t)F * B) * (W < 1 ? 1 : W) + 64) * sizeof(int32_t);
+}
+
+// ids of the local batch -> this rank's wire buffers.  Destination r's entries start at r * cap, in (feature, bag,
+// position) order; wire_key = rf_key_base[r * F + f] + owner-local row, wire_idx = bag index (pooled) or id position
+// (sequence).  counts [W + 1]: ids per destination (clamped to cap) and, in counts[W], 1 if any destination overflowed.
+extern "C" int tzk_peer_bucketize(const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t W,
+                                  const int64_t* feat_block, const int32_t* feat_owner, const int64_t* feat_rows,
+                                  const int64_t* rf_key_base, int32_t pooled, int64_t cap, int64_t* wire_key,
+                                  int32_t* wire_idx, int32_t* counts, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  if (F <= 0 || B <= 0 || W < 1 || W > kMaxPeers || cap <= 0 || cap * W >= ((int64_t)1 << 31)) return 1;
+  if (!offsets || !feat_block || !feat_rows || !rf_key_base || !wire_key || !wire_idx || !counts || !workspace)
+    return 1;
+  if (workspace_bytes < tzk_peer_bucketize_workspace_bytes(F, B, W)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t tiles = bkt_tiles((int64_t)F * B);
+  int32_t* tile_counts = static_cast<int32_t*>(workspace);
+  const size_t smem_c = (size_t)F * sizeof(BktFeat) + (size_t)W * 4;
+  TZK_LAUNCH((peer_bkt_count_kernel), (unsigned)tiles, kThreads, smem_c, st, ids, offsets, feat_rows, feat_block,
+             feat_owner, F, B, W, tile_counts, counts);
+  TZK_LAUNCH((peer_bkt_scan_kernel), (unsigned)W, 1024, (size_t)32 * 4, st, tile_counts, tiles, W, cap, counts);
+  const size_t smem_s = (size_t)F * sizeof(BktFeat) + (size_t)W * kThreads * 4 + (size_t)W * 8 * 4;
+  TZK_LAUNCH((peer_bkt_scatter_kernel), (unsigned)tiles, kThreads, smem_s, st, ids, offsets, feat_rows, feat_block,
+             feat_owner, rf_key_base, F, B, W, pooled, cap, tile_counts, wire_key, wire_idx);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+extern "C" int tzk_peer_publish_grad(const float* grad, int64_t ld_grad, const int32_t* feat_col, const int32_t* feat_dim,
+                                     const int32_t* feat_pool, const int64_t* offsets, int32_t F, int32_t B, float* dst,
+                                     int64_t ld_dst, void* stream) {
+  if (F <= 0 || B <= 0 || !grad || !dst || !feat_col || !feat_dim || !feat_pool || !offsets) return 1;
+  const int64_t n = (int64_t)F * B;
+  TZK_LAUNCH((peer_publish_grad_kernel), grid_for((n + kThreads - 1) / kThreads), kThreads, 0,
+             reinterpret_cast<cudaStream_t>(stream), grad, ld_grad, feat_col, feat_dim, feat_pool, offsets, F, B, dst,
+             ld_dst);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+extern "C" int tzk_peer_allreduce_mean(const uint64_t* src_ptrs, int32_t W, int64_t n, float* out, void* stream) {
+  Peers p;
+  if (fill(&p, src_ptrs, W) || n < 0 || !out) return 1;
+  if (n == 0) return 0;
+  TZK_LAUNCH((peer_allreduce_mean_kernel), grid_for((n + kThreads - 1) / kThreads), kThreads, 0,
+             reinterpret_cast<cudaStream_t>(stream), p, W, n, out);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

@@ -325,6 +325,19 @@ class _ShardedBase(nn.Module):
         for g in self.groups:
             g.local.set_optimizer(spec)
 
+    def _maybe_enable_peer(self, features: KeyedJaggedTensor) -> bool:
+        """exchange="peer": on the first call move the shards into symmetric memory, size the wire buffers for this
+        batch size and re-route forward() to the peer-memory kernels (collective: every rank gets here in its first
+        step).  `_ids_budget` (KJT key -> ids per bag) sizes features with more than one id per bag."""
+        if getattr(self, "_exchange", "nccl") != "peer" or getattr(self, "_peer_states", None) is not None:
+            return False
+        from .peer_exchange import enable_peer_exchange
+
+        B = features.stride()
+        per_bag = getattr(self, "_ids_budget", None) or {}
+        enable_peer_exchange(self, B, {k: int(v) * B for k, v in per_bag.items()})
+        return True
+
     def sparse_arenas(self) -> List[_ArenaCollection]:
         return [g.local for g in self.groups]
 
@@ -381,12 +394,7 @@ class ShardedEmbeddingBagCollection(_ShardedBase):
         return self._configs
 
     def forward(self, features: KeyedJaggedTensor) -> KeyedTensor:
-        if getattr(self, "_exchange", "nccl") == "peer" and getattr(self, "_peer_states", None) is None:
-            # first call: move the shards into symmetric memory, size the wire buffers for this batch and re-route
-            # forward() to the peer-memory kernels (collective: every rank gets here in its first step)
-            from .peer_exchange import enable_peer_exchange
-
-            enable_peer_exchange(self, features.stride())
+        if self._maybe_enable_peer(features):
             return self.forward(features)
         keys, lens, vals = [], [], []
         for g in self.groups:
@@ -407,6 +415,8 @@ class ShardedEmbeddingCollection(_ShardedBase):
         return [n for g in self.groups for n in g.local.embedding_names_by_table()]
 
     def forward(self, features: KeyedJaggedTensor) -> Dict[str, JaggedTensor]:
+        if self._maybe_enable_peer(features):
+            return self.forward(features)
         out: Dict[str, JaggedTensor] = {}
         for g in self.groups:
             kjt = g.local._select(features)
@@ -451,11 +461,13 @@ class DenseGradSync:
 
 def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows: int = 0, source=None,
                 constraints: Optional[Dict[str, Sequence[str]]] = None, static_capacity: Optional[float] = None,
-                exchange: str = "nccl"):
+                exchange: str = "nccl", ids_per_bag: Optional[Dict[str, int]] = None):
     """Swaps every arena collection of `model.embedding_group` for its sharded twin (tzrec/main.py:799).
 
-    `exchange="peer"` (with `static_capacity`): pooled collections exchange through peer memory of the NVSwitch
-    domain (csrc/tzk_peer.cu) instead of NCCL all-to-alls; sequence collections keep the NCCL path.
+    `exchange="peer"`: the collections exchange through peer memory of the NVSwitch domain (csrc/tzk_peer.cu,
+    peer_exchange.py) instead of NCCL all-to-alls; `static_capacity` is then the head-room factor of the wire buffers
+    (default 1.5) and `ids_per_bag` (KJT key -> most ids per bag; sequence features: their sequence_length) sizes
+    features with more than one id per bag.  Sequence collections without a budget keep the NCCL path.
 
     The model may have been built with its embedding collections on the meta device (as the reference does,
     embedding.py:187-188): shards are materialised directly on `device`, each rank initialising its own shard
@@ -470,11 +482,17 @@ def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows:
         plan = make_plan(coll._configs, world, default, dict(constraints or {}), rw_min_rows)
         cls = ShardedEmbeddingBagCollection if isinstance(coll, EmbeddingBagCollection) else ShardedEmbeddingCollection
         new = cls(coll._configs, plan, device, group)
-        if static_capacity and isinstance(new, ShardedEmbeddingBagCollection):
+        pooled = isinstance(new, ShardedEmbeddingBagCollection)
+        if exchange == "peer":         # peer-memory kernels instead of the NCCL all-to-alls (peer_exchange.py)
+            budget = {f: (ids_per_bag or {}).get(f) for g in new.groups for f in g.feature_names}
+            if pooled or all(v for v in budget.values()):
+                new._exchange = "peer"
+                new._ids_budget = {f: v for f, v in budget.items() if v}
+                for g in new.groups:
+                    g.static_alpha = float(static_capacity or 1.5)
+        elif static_capacity and pooled:
             for g in new.groups:       # fixed-shape exchange (see _StaticDispatch); pooled collections only
                 g.static_alpha = float(static_capacity)
-            if exchange == "peer":     # peer-memory kernels instead of the NCCL all-to-alls (peer_exchange.py)
-                new._exchange = "peer"
         if coll.optimizer is not None:
             new.set_optimizer(coll.optimizer)
         seed = src_coll if src_coll is not None else (coll if coll.weights.device.type != "meta" else None)

@@ -70,12 +70,19 @@ class Pipeline:
             from .distributed import DenseGradSync, shard_model
 
             self.model = create_model(self.cfg.model_config, self.features, self.labels, device=torch.device("meta"))
+            # sequence features carry up to `sequence_length` ids per bag (sizes the peer exchange's wire buffers)
+            per_bag = {f.name: int(f.sequence_length) for f in self.features if f.is_sequence and f.sequence_length}
             self.sharded = shard_model(self.model, self.device, default=sharding, group=group,
                                        rw_min_rows=rw_min_rows, constraints=self._table_constraints(),
-                                       static_capacity=static_capacity, exchange=exchange)
+                                       static_capacity=static_capacity, exchange=exchange, ids_per_bag=per_bag)
         self.model.to(self.device)
         if sharding is not None:
-            self.grad_sync = DenseGradSync(self.model.dense_parameters(), group)
+            if exchange == "peer" and self.device.type == "cuda":
+                from .peer_exchange import PeerDenseGradSync      # no NCCL call anywhere in the step
+
+                self.grad_sync = PeerDenseGradSync(self.model.dense_parameters(), group)
+            else:
+                self.grad_sync = DenseGradSync(self.model.dense_parameters(), group)
         self.model.set_sparse_optimizer(sparse_optimizer_from_config(self.cfg.train_config))
         kw = {}
         if self.device.type == "cuda" and capturable:

@@ -8,6 +8,7 @@ implementation here: host-logic tests inject their own checker backend (tests/or
 
 import ctypes
 import os
+import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -165,10 +166,12 @@ class CudaKernels:
 
     # ------------------------------------------------------------------ workspace cache
     def _workspace(self, key, nbytes: int, device) -> torch.Tensor:
-        ws = self._ws.get((key, device))
+        # (per host thread: two threads driving two streams must not share scratch memory)
+        slot = (key, device, threading.get_ident())
+        ws = self._ws.get(slot)
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
-            self._ws[(key, device)] = ws
+            self._ws[slot] = ws
         return ws
 
     # ------------------------------------------------------------------ K3
@@ -356,6 +359,105 @@ class CudaKernels:
                                         perm.numel(), B, _ptr(out), _stream()), "tzk_permute_ids")
         self.launches += 1
         return out
+
+    # ------------------------------------------------------------------ sharded step over peer memory (tzk_peer.cu)
+    # `symm` arguments: objects with `.ptrs` = ctypes array [W] of device addresses (rank r's symmetric buffer as
+    # mapped in this process) — peer_exchange._Symm.
+    def peer_pooled_gather_fwd(self, tables, rf_w_off: torch.Tensor, feat_rows: torch.Tensor, feat_block: torch.Tensor,
+                               feat_owner: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
+                               B: int, W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        F = lay.num_features
+        if offsets.numel() != F * B + 1:
+            raise TzkError(f"offsets has {offsets.numel()} entries, expected F*B+1 = {F * B + 1}")
+        if not lay.vec_ok:
+            raise TzkError("peer gather: rows must be 16-B aligned (dims and offsets multiples of 4 floats)")
+        if out is None:
+            out = torch.empty((B, lay.total_dim), dtype=torch.float32, device=ids.device)
+        out, ld = _rows2d(out, "out")
+        check(self._lib.tzk_peer_pooled_gather_fwd(
+            tables.ptrs, _ptr(rf_w_off), _ptr(feat_rows), _ptr(feat_block), _ptr(feat_owner), _ptr(lay.d_dim),
+            _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, W, (lay.max_dim + 3) // 4 * 4, _ptr(out),
+            ld, _stream()), "tzk_peer_pooled_gather_fwd")
+        self.launches += 1
+        return out
+
+    def peer_seq_gather_fwd(self, tables, rf_w_off: torch.Tensor, feat_rows: torch.Tensor, feat_block: torch.Tensor,
+                            feat_owner: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
+                            B: int, W: int) -> torch.Tensor:
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        F, D, nnz = lay.num_features, lay.dim[0], ids.numel()
+        out = torch.empty((nnz, D), dtype=torch.float32, device=ids.device)
+        check(self._lib.tzk_peer_seq_gather_fwd(tables.ptrs, _ptr(rf_w_off), _ptr(feat_rows), _ptr(feat_block),
+                                                _ptr(feat_owner), _ptr(ids), _ptr(offsets), F, B, W, D, nnz, _ptr(out),
+                                                _stream()), "tzk_peer_seq_gather_fwd")
+        self.launches += 1 if nnz else 0
+        return out
+
+    def peer_barrier(self, pads, me: int, W: int, epoch: torch.Tensor) -> None:
+        check(self._lib.tzk_peer_barrier(pads.ptrs, me, W, _ptr(epoch), _stream()), "tzk_peer_barrier")
+        self.launches += 1
+
+    def peer_bucketize(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int, feat_block: torch.Tensor,
+                       feat_owner: torch.Tensor, feat_rows: torch.Tensor, rf_key_base: torch.Tensor, pooled: bool,
+                       cap: int, wire_key: torch.Tensor, wire_idx: torch.Tensor, counts: torch.Tensor) -> None:
+        """ids of the local batch -> this rank's own wire buffers (see tzk_peer_bucketize in include/tzk.h)."""
+        _need(ids, torch.int64, "ids")
+        _need(offsets, torch.int64, "offsets")
+        _need(wire_key, torch.int64, "wire_key")
+        _need(wire_idx, torch.int32, "wire_idx")
+        _need(counts, torch.int32, "counts")
+        if wire_key.numel() < W * cap or wire_idx.numel() < W * cap or counts.numel() < W + 1:
+            raise TzkError("peer_bucketize: wire buffers smaller than W * cap")
+        nb = self._lib.tzk_peer_bucketize_workspace_bytes(F, B, W)
+        ws = self._workspace(("peer_bkt", F, B, W), nb, ids.device)
+        check(self._lib.tzk_peer_bucketize(_ptr(ids), _ptr(offsets), F, B, W, _ptr(feat_block), _ptr(feat_owner),
+                                           _ptr(feat_rows), _ptr(rf_key_base), int(pooled), cap, _ptr(wire_key),
+                                           _ptr(wire_idx), _ptr(counts), _ptr(ws), ws.numel(), _stream()),
+              "tzk_peer_bucketize")
+        self.launches += 3
+
+    def peer_publish_grad(self, grad: torch.Tensor, lay: FeatureLayout, offsets: torch.Tensor, B: int,
+                          dst: torch.Tensor) -> None:
+        grad, ld = _rows2d(grad, "grad")
+        dst, ld_dst = _rows2d(dst, "dst")
+        if POOL_MEAN not in lay.pool:        # plain copy: no per-bag scale to fold in
+            dst.copy_(grad)
+            return
+        check(self._lib.tzk_peer_publish_grad(_ptr(grad), ld, _ptr(lay.d_col), _ptr(lay.d_dim), _ptr(lay.d_pool),
+                                              _ptr(offsets), lay.num_features, B, _ptr(dst), ld_dst, _stream()),
+              "tzk_peer_publish_grad")
+        self.launches += 1
+
+    def peer_allreduce_mean(self, srcs, W: int, n: int, out: torch.Tensor) -> None:
+        _need(out, torch.float32, "out")
+        check(self._lib.tzk_peer_allreduce_mean(srcs.ptrs, W, n, _ptr(out), _stream()), "tzk_peer_allreduce_mean")
+        self.launches += 1
+
+    def fused_bwd_sort_peer(self, wire_key, wire_idx, counts, me: int, W: int, cap: int, idx_span: int,
+                            lay: FeatureLayout, overflow: Optional[torch.Tensor], ws: torch.Tensor) -> None:
+        if ws.numel() < self.fused_bwd_workspace_bytes(lay, W * cap):
+            raise TzkError("fused_bwd_sort_peer: workspace too small")
+        check(self._lib.tzk_fused_bwd_sort_peer(wire_key.ptrs, wire_idx.ptrs, counts.ptrs, me, W, cap, idx_span,
+                                                lay.total_keys, lay.max_dim, _ptr(overflow), _ptr(ws), ws.numel(),
+                                                _stream()), "tzk_fused_bwd_sort_peer")
+        self.launches += 1
+
+    def fused_bwd_apply_peer(self, optimizer: int, pooled: bool, grads, ld_grad: int, weights: torch.Tensor,
+                             state: Optional[torch.Tensor], lay: FeatureLayout, B: int, me: int, W: int, cap: int,
+                             idx_span: int, lr: float, eps: float, grad_scale: float, ws: torch.Tensor, **ex) -> None:
+        _need(weights, torch.float32, "weights")
+        if state is not None:
+            _need(state, torch.float32, "state")
+        oa = _opt_args(optimizer, state, lr, eps, ex)
+        check(self._lib.tzk_fused_bwd_apply_peer(
+            ctypes.byref(oa), int(pooled), grads.ptrs, ld_grad, _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim),
+            _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), lay.num_features, B, me, W, cap, idx_span,
+            lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), grad_scale, _ptr(ws), ws.numel(), _stream()),
+            "tzk_fused_bwd_apply_peer")
+        self.launches += 2 if _tile_path(lay) else 4
 
     # ------------------------------------------------------------------ K6
     def col_gather_sum(self, srcs: Sequence[torch.Tensor], plan: "ColPlan", rows: int,

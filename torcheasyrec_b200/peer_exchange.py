@@ -1,43 +1,37 @@
 """Host side of csrc/tzk_peer.cu: the sharded sparse step over peer memory (exchange="peer" in shard_model).
 
-`enable_peer_exchange(sharded_ebc)` re-routes a `ShardedEmbeddingBagCollection` that was built with a static wire
-capacity (`shard_model(..., static_capacity=a)`, one id per bag) from the three NCCL all-to-alls per dim group to
-peer-memory kernels over the NVSwitch domain:
+`enable_peer_exchange(sharded_collection, batch_size)` re-routes a `ShardedEmbeddingBagCollection` /
+`ShardedEmbeddingCollection` from the NCCL all-to-alls to peer-memory kernels over the NVSwitch domain.  Per dim
+group and per step:
 
-    forward    one kernel: the requester gathers rows straight out of the owners' arenas (symmetric memory) and pools.
-    backward   bucketize into the rank's own symmetric wire buffer (runs during the forward pass), publish the
-               pooled-output gradient, barrier, the owner pulls ids + gradient slices, tzk_fused_bwd as before, barrier.
+    forward    ONE kernel on the compute stream: the requester gathers rows straight out of the owners' arenas
+               (symmetric memory) and pools in bag order — bit-identical to the unsharded gather, any bag length.
+    prep       (training; side stream, overlaps the rest of the forward pass)  tzk_peer_bucketize: stable multi-split of
+               the local ids by destination into this rank's own wire buffers -> barrier A -> the owner pulls its chunk
+               of every source's keys straight into the radix sort's input and sorts (tzk_fused_bwd_sort_peer).
+    backward   publish the gradient (symmetric buffer; MEAN bags pre-divided) -> barrier B -> side stream: the run /
+               update kernels fetch every gradient slice from the SOURCE rank's buffer in place
+               (tzk_fused_bwd_apply_peer, 1/W gradient scale, App. A.6) -> barrier C (tables quiescent, wire buffers and
+               gradient reusable); the stream is joined when the backward pass ends.
+    dense      `PeerDenseGradSync`: publish the flat dense gradient -> barrier D -> every rank sums all W buffers in rank
+               order (same bits everywhere) — no NCCL call anywhere in the step.
 
-Symmetric allocations and the address exchange come from `torch.distributed._symmetric_memory` (plumbing); every
-kernel on the path is ours.  The whole step stays capturable: the barrier's epoch lives on the device.
-
-What is the same as the NCCL static path (so results are bit-identical to it): the wire layout (destination-major,
-feature runs, fixed capacity), the owner-side `bounds` / `owner_layout_static`, the update kernel and its 1/W scale.
+Symmetric allocations and the address exchange come from `torch.distributed._symmetric_memory` (plumbing, with a CUDA
+IPC fallback); every kernel on the path is ours.  The whole step stays capturable: every barrier's epoch lives on the
+device.  Wire capacity: `cap = static_capacity * max over destinations of the expected ids per step` (table-wise
+features send everything to one owner, row-wise ones 1/W to each); an overflow drops ids, raises the device flag
+`g.overflow` on EVERY rank in the same step (the owners read the sources' flags) and `check_overflow()` reports it.
 """
 import ctypes
-from typing import List
+import os
+from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 from . import functional as Fn
-from .kernels import build_layout
-from .sparse import KeyedTensor
-
-def load_lib():
-    """The package library (tzk_peer_* entry points are part of libtzk.so)."""
-    from ._lib import lib
-
-    return lib()
-
-
-def _check(rc: int, what: str) -> None:
-    if rc:
-        raise RuntimeError(f"{what} failed with code {rc}")
-
-
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0
+from .kernels import POOL_MEAN, build_layout
+from .sparse import JaggedTensor, KeyedTensor
 
 
 class _Symm:
@@ -47,8 +41,6 @@ class _Symm:
     torch.multiprocessing's reductions (cudaIpcGetMemHandle / cudaIpcOpenMemHandle), one all_gather_object each."""
 
     def __init__(self, numel: int, dtype, device, group) -> None:
-        import os
-
         W = dist.get_world_size(group)
         n = max(int(numel), 1)
         self.h = None
@@ -71,7 +63,6 @@ class _Symm:
         from torch.multiprocessing.reductions import reduce_tensor
 
         me = dist.get_rank(group)
-        # a private cudaMalloc block (IPC shares whole allocations): ask the caching allocator for an exclusive segment
         self.t = torch.zeros(n, dtype=dtype, device=device)
         torch.cuda.synchronize()
         fn, args = reduce_tensor(self.t)
@@ -85,17 +76,87 @@ class _Symm:
         self.ptrs = (ctypes.c_uint64 * W)(*[int(pt.data_ptr()) for pt in self.peers])
 
 
-class PeerState:
-    """Peer-memory state of one `_DimGroup` (all tables of one embedding dim)."""
+class _Site:
+    """One barrier site: its own flag array (symmetric) and device epoch, so that sites on different streams never
+    share a counter."""
 
-    def __init__(self, g, plan, group, batch_size: int) -> None:
-        if not g.static_alpha:
-            raise ValueError("peer exchange needs the static wire capacity (shard_model(..., static_capacity=a))")
-        self.g, self.group, self.B = g, group, int(batch_size)
-        self.W, self.me = g.world, g.rank
+    def __init__(self, owner: "PeerBase") -> None:
+        self.pads = owner._alloc(owner.W, torch.int32)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=owner.device)
+
+
+class PeerBase:
+    """Process / device plumbing shared by the sparse states and the dense gradient sync.  tests/
+    test_peer_exchange_model.py swaps `_alloc`, `_host_barrier`, `_barrier` and the stream hooks for an in-process
+    model (ranks = threads)."""
+
+    def __init__(self, group, device, world: Optional[int] = None, rank: Optional[int] = None) -> None:
+        self.group = group
+        self.device = torch.device(device)
+        self.W = int(world) if world is not None else dist.get_world_size(group)
+        self.me = int(rank) if rank is not None else dist.get_rank(group)
+
+    def _alloc(self, numel: int, dtype) -> "_Symm":
+        return _Symm(numel, dtype, self.device, self.group)
+
+    def _host_barrier(self) -> None:
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def _barrier(self, site: _Site) -> None:
+        Fn.backend().peer_barrier(site.pads, self.me, self.W, site.epoch)
+
+    # ---- streams (no-ops off CUDA) ---------------------------------------------------------------------------------
+    def _side_stream(self):
+        if self.device.type != "cuda":
+            return None
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=self.device)
+        return st
+
+    def _on_side(self, fn) -> None:
+        """Runs fn() on the side stream, ordered after everything enqueued on the current stream so far."""
+        side = self._side_stream()
+        if side is None:
+            fn()
+            return
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+
+    def _join_side(self) -> None:
+        side = self._side_stream()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+
+
+def expected_load(g, plan, ids_per_feature: Sequence[int]) -> int:
+    """max over destinations of the ids a step sends there (table-wise: everything to the owner; row-wise: 1/W each)."""
+    from .distributed import TABLE_WISE
+
+    W = g.world
+    load = [0.0] * W
+    for f, t in enumerate(g.local._feat_table):
+        sh = plan[g.configs[t].name]
+        if sh.kind == TABLE_WISE:
+            load[sh.owner] += ids_per_feature[f]
+        else:
+            blocks = min(W, -(-g.configs[t].num_embeddings // sh.block))    # ranks that hold rows of this table
+            for r in range(blocks):
+                load[r] += ids_per_feature[f] / blocks
+    return int(max(load)) + 1
+
+
+class PeerState(PeerBase):
+    """Peer-memory state of one `_DimGroup` (all tables of one embedding dim) of a pooled or sequence collection."""
+
+    def __init__(self, g, plan, group, batch_size: int, ids_per_feature: Optional[Sequence[int]] = None) -> None:
+        super().__init__(group, g.device, g.world, g.rank)
+        self.g, self.B, self.pooled = g, int(batch_size), bool(g.pooled)
         dev, F, W = g.device, g.F, g.world
-        self._init_io()
         lay = g.local.layout
+        alpha = float(g.static_alpha or 1.5)
         # every rank's arena layout (deterministic from the plan: no communication)
         from .distributed import local_rows
 
@@ -103,6 +164,7 @@ class PeerState:
                                  g.local._feat_table, list(lay.pool)) for r in range(W)]
         assert per_rank[self.me].w_off == list(lay.w_off), "local layout differs from the plan's"
         self.rf_w_off = torch.tensor([o for lr in per_rank for o in lr.w_off], dtype=torch.int64, device=dev)
+        self.rf_key_base = torch.tensor([k for lr in per_rank for k in lr.key_base], dtype=torch.int64, device=dev)
         self.feat_rows = torch.tensor([g.configs[t].num_embeddings for t in g.local._feat_table], dtype=torch.int64,
                                       device=dev)
         # the arena moves into symmetric memory (same size on every rank: the largest shard)
@@ -110,137 +172,189 @@ class PeerState:
         n = g.local.weights.numel()
         self.tables.t[:n].copy_(g.local.weights.data)
         g.local.weights.data = self.tables.t[:n]
-        # wire buffers (sized on first use: nnz = F * B for one id per bag), gradient, flags
-        nnz = F * self.B
-        self.cap = (int(g.static_alpha * nnz / W) + 8) // 8 * 8
-        g.static_nnz, g.static_cap = nnz, self.cap
-        self.wire_ids = self._alloc(W * self.cap, torch.int64)
-        self.wire_pos = self._alloc(W * self.cap, torch.int32)
-        self.counts = self._alloc(W * F, torch.int32)
-        self.grad = self._alloc(self.B * g.total_dim, torch.float32)
-        self.pads = self._alloc(W, torch.int32)
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        # id budget per step: one id per bag unless the caller knows better (sequence features: B * sequence_length)
+        per_f = list(ids_per_feature) if ids_per_feature is not None else [self.B] * F
+        self.max_nnz = int(sum(per_f))
+        self.idx_span = F * self.B if self.pooled else max(self.max_nnz, 1)
+        self.cap = (int(alpha * expected_load(g, plan, per_f)) + 8) // 8 * 8
+        self.cap = min(self.cap, (self.max_nnz + 8) // 8 * 8)          # a destination never gets more than everything
+        assert W * self.idx_span < 2 ** 31 and W * self.cap < 2 ** 31
+        g.static_nnz, g.static_cap = self.max_nnz, self.cap
+        self.wire_key = self._alloc(W * self.cap, torch.int64)
+        self.wire_idx = self._alloc(W * self.cap, torch.int32)
+        self.counts = self._alloc(W + 1, torch.int32)
+        self.grad = self._alloc(self.B * g.total_dim if self.pooled else self.max_nnz * g.dim, torch.float32)
+        self.site_a, self.site_b, self.site_c = _Site(self), _Site(self), _Site(self)
+        self._ws = None
+        self._prep_pending = False
         self._host_barrier()                 # flags are zero and tables are in place everywhere before the first step
 
-    # ---- device / process plumbing (tests/test_peer_exchange_model.py swaps these for an in-process model) ----------
-    def _init_io(self) -> None:
-        self.lib = load_lib()
-
-    def _alloc(self, numel: int, dtype) -> "_Symm":
-        return _Symm(numel, dtype, self.g.device, self.group)
-
-    def _host_barrier(self) -> None:
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
-
-    def _k_barrier(self) -> None:
-        _check(self.lib.tzk_peer_barrier(self.pads.ptrs, self.me, self.W, self.epoch.data_ptr(), _stream()), "barrier")
-
-    def _k_gather(self, ids, offsets, out) -> None:
-        g, lay = self.g, self.g.local.layout
-        _check(self.lib.tzk_peer_pooled_gather_fwd(
-            self.tables.ptrs, self.rf_w_off.data_ptr(), self.feat_rows.data_ptr(), g.feat_block.data_ptr(),
-            g.feat_owner.data_ptr(), lay.d_dim.data_ptr(), lay.d_col.data_ptr(), lay.d_pool.data_ptr(), ids.data_ptr(),
-            offsets.data_ptr(), g.F, self.B, self.W, lay.max_dim, out.data_ptr(), g.total_dim, _stream()),
-            "peer_pooled_gather_fwd")
-
-    def _k_bucketize(self, ids, offsets) -> torch.Tensor:
-        """tzk_bucketize_rw straight into this rank's wire buffers; returns out_offsets [W*F*B+1]."""
-        g, k = self.g, Fn.backend()
-        F, B, W, nnz = g.F, self.B, self.W, ids.numel()
-        out_lengths = torch.empty(W * F * B, dtype=torch.int32, device=ids.device)
-        oo = torch.empty(W * F * B + 1, dtype=torch.int64, device=ids.device)
-        ws = k._workspace("bucketize", k._lib.tzk_bucketize_rw_workspace_bytes(F, B, W, nnz), ids.device)
-        _check(k._lib.tzk_bucketize_rw(ids.data_ptr(), offsets.data_ptr(), F, B, W, g.feat_block.data_ptr(),
-                                       g.feat_owner.data_ptr(), nnz, self.cap, out_lengths.data_ptr(), oo.data_ptr(),
-                                       self.wire_ids.t.data_ptr(), self.wire_pos.t.data_ptr(), None, ws.data_ptr(),
-                                       ws.numel(), _stream()), "tzk_bucketize_rw")
-        return oo
-
-    def _k_pull_counts(self, recv_counts) -> None:
-        _check(self.lib.tzk_peer_pull_counts(self.counts.ptrs, self.me, self.W, self.g.F, recv_counts.data_ptr(),
-                                             _stream()), "peer_pull_counts")
-
-    def _k_pull(self, bounds, recv_ids, recv_g) -> None:
-        g = self.g
-        _check(self.lib.tzk_peer_pull(self.wire_ids.ptrs, self.wire_pos.ptrs, self.grad.ptrs, self.me, self.W, self.cap,
-                                      g.F, self.B, g.dim, g.local.layout.d_col.data_ptr(), bounds.data_ptr(), g.total_dim,
-                                      recv_ids.data_ptr(), recv_g.data_ptr(), _stream()), "peer_pull")
-
-    # ---- the step ------------------------------------------------------------------------------------------------
-    def barrier(self) -> None:
-        self._k_barrier()
-
+    # ---- forward ---------------------------------------------------------------------------------------------------
     def gather(self, ids: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
-        out = torch.empty((self.B, self.g.total_dim), dtype=torch.float32, device=ids.device)
-        self._k_gather(ids, offsets, out)
-        return out
-
-    def bucketize(self, ids: torch.Tensor, offsets: torch.Tensor) -> None:
-        """ids -> this rank's own wire buffers (destination r at slot r * cap) + counts[dest, f]."""
-        g = self.g
-        F, B = g.F, self.B
-        if ids.numel() != F * B:
-            raise RuntimeError(f"peer exchange is sized for one id per bag ({F * B} ids), got {ids.numel()}")
-        oo = self._k_bucketize(ids, offsets)
-        seg = oo[::B]
-        self.counts.t.copy_((seg[1:] - seg[:-1]).to(torch.int32))
-        dest_start = oo[::F * B]
-        g.overflow.add_(((dest_start[1:] - dest_start[:-1]) > self.cap).any().to(torch.int32))
-
-    def backward(self, grad_out: torch.Tensor) -> None:
         g, k = self.g, Fn.backend()
-        F, W, cap, D = g.F, self.W, self.cap, g.dim
+        if ids.numel() > self.max_nnz:
+            raise RuntimeError(f"peer exchange is sized for {self.max_nnz} ids per step, got {ids.numel()}")
+        if self.pooled:
+            return k.peer_pooled_gather_fwd(self.tables, self.rf_w_off, self.feat_rows, g.feat_block, g.feat_owner,
+                                            g.local.layout, ids, offsets, self.B, self.W)
+        return k.peer_seq_gather_fwd(self.tables, self.rf_w_off, self.feat_rows, g.feat_block, g.feat_owner,
+                                     g.local.layout, ids, offsets, self.B, self.W)
+
+    def _workspace(self) -> torch.Tensor:
+        k = Fn.backend()
+        need = k.fused_bwd_workspace_bytes(self.g.local.layout, self.W * self.cap)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def prep(self, ids: torch.Tensor, offsets: torch.Tensor) -> None:
+        """Id half of the backward (side stream): bucketize -> barrier A -> pull + sort at the owner."""
+        g, k = self.g, Fn.backend()
+
+        def run():
+            if self._prep_pending:            # a forward pass without a backward: peers may still be pulling
+                self._barrier(self.site_c)
+            k.peer_bucketize(ids, offsets, g.F, self.B, self.W, g.feat_block, g.feat_owner, self.feat_rows,
+                             self.rf_key_base, self.pooled, self.cap, self.wire_key.t, self.wire_idx.t, self.counts.t)
+            self._barrier(self.site_a)
+            k.fused_bwd_sort_peer(self.wire_key, self.wire_idx, self.counts, self.me, self.W, self.cap, self.idx_span,
+                                  g.local.layout, g.overflow, self._workspace())
+            self._prep_pending = True
+
+        self._keep = (ids, offsets)           # the side stream reads them: keep them away from the allocator
+        self._on_side(run)
+
+    # ---- backward --------------------------------------------------------------------------------------------------
+    def backward(self, grad: torch.Tensor, offsets: torch.Tensor) -> None:
+        g, k = self.g, Fn.backend()
         spec = g.local.optimizer
         if spec is None:
             raise RuntimeError("sharded collection: no sparse optimizer set (call set_optimizer)")
-        self.grad.t.view(self.B, g.total_dim).copy_(grad_out)
-        self.barrier()                                   # every rank's wire buffers and gradient are published
-        recv_counts = torch.empty((W, F), dtype=torch.int32, device=grad_out.device)
-        self._k_pull_counts(recv_counts)
-        tot = recv_counts.sum(1, keepdim=True)
-        lens = torch.cat([recv_counts, (cap - tot).clamp_(min=0)], dim=1).reshape(-1).to(torch.int32)
-        bounds = k.lengths_to_offsets(lens)              # [W * (F + 1) + 1], as in _StaticDispatch
-        recv_ids = torch.empty(W * cap, dtype=torch.int64, device=grad_out.device)
-        recv_g = torch.empty((W * cap, D), dtype=torch.float32, device=grad_out.device)
-        self._k_pull(bounds, recv_ids, recv_g)
-        k.fused_bwd(spec.kind, False, recv_g, g.local.weights.data, g.local.opt_state, g.owner_layout_static, recv_ids,
-                    bounds, 1, spec.lr, spec.eps, 1.0 / W, **g.local.opt_extras())
-        self.barrier()                                   # tables quiescent, wire buffers / gradient reusable
+        if not self._prep_pending:
+            raise RuntimeError("peer exchange: backward without the forward pass's id exchange")
+        lay = g.local.layout
+        if self.pooled:
+            ld = g.total_dim
+            k.peer_publish_grad(grad, lay, offsets, self.B, self.grad.t.view(self.B, ld))
+        else:
+            ld = g.dim
+            self.grad.t[:grad.numel()].copy_(grad.reshape(-1))
+        self._barrier(self.site_b)            # every rank's gradient is published (and, long ago, its wire buffers)
+        extras = g.local.opt_extras()
+
+        def run():
+            k.fused_bwd_apply_peer(spec.kind, self.pooled, self.grad, ld, g.local.weights.data, g.local.opt_state, lay,
+                                   self.B, self.me, self.W, self.cap, self.idx_span, spec.lr, spec.eps, 1.0 / self.W,
+                                   self._workspace(), **extras)
+            self._barrier(self.site_c)        # tables quiescent everywhere, wire buffers / gradient reusable
+            self._prep_pending = False
+
+        self._on_side(run)
+        self._keep = None
+        self._join_later()
+
+    def _join_later(self) -> None:
+        """Joins the side stream when the backward pass ends (the dense backward that autograd still has to run
+        overlaps the update); immediately when called outside a backward pass."""
+        if self._side_stream() is None:
+            return
+        cur = torch.cuda.current_stream()
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: cur.wait_stream(self._side_stream()))
+        except RuntimeError:                  # not inside a backward pass
+            cur.wait_stream(self._side_stream())
 
 
-class _PeerPooled(torch.autograd.Function):
+class _PeerLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hook, st: PeerState, ids, offsets):
         out = st.gather(ids, offsets)
-        if hook is not None:
-            st.bucketize(ids, offsets)      # only the backward needs it; TODO(side stream, like the early sort)
-        ctx.st = st
+        ctx.st = None
+        if hook is not None:                  # (also with zero local ids: the barriers are collective)
+            st.prep(ids, offsets)
+            ctx.st = st
+            ctx.save_for_backward(offsets)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        ctx.st.backward(grad_out.contiguous())
+        if ctx.st is not None:
+            (offsets,) = ctx.saved_tensors
+            ctx.st.backward(Fn._rows_contig(grad_out) if ctx.st.pooled else grad_out.contiguous(), offsets)
         return None, None, None, None
 
 
-def enable_peer_exchange(sm, batch_size: int) -> List[PeerState]:
-    """Switches `sm` (static-capacity sharded pooled collection) to the peer-memory path for local batches of
-    `batch_size` samples.  Returns the per-dim-group states (kept alive by the patched forward)."""
-    states = [PeerState(g, sm.plan, sm._group if sm._group is not None else dist.group.WORLD, batch_size)
-              for g in sm.groups]
+def enable_peer_exchange(sm, batch_size: int, ids_per_feature: Optional[Dict[str, int]] = None) -> List[PeerState]:
+    """Switches the sharded collection `sm` to the peer-memory path for local batches of `batch_size` samples.
+    `ids_per_feature` (KJT key -> ids per step): the id budget of features with more than one id per bag (sequence
+    features: batch_size * sequence_length).  Returns the per-dim-group states (kept alive by the patched forward)."""
+    grp = sm._group if sm._group is not None else dist.group.WORLD
+    states = []
+    for g in sm.groups:
+        per_f = None
+        if ids_per_feature is not None:
+            per_f = [int(ids_per_feature.get(name, batch_size)) for name in g.feature_names]
+        states.append(PeerState(g, sm.plan, grp, batch_size, per_f))
+    pooled = sm._pooled
 
     def forward(features):
         keys, lens, vals = [], [], []
+        out = {}
         for g, st in zip(sm.groups, states):
             kjt = g.local._select(features)
             if kjt.stride() != st.B:
                 raise RuntimeError(f"peer exchange was sized for batch {st.B}, got {kjt.stride()}")
-            vals.append(_PeerPooled.apply(sm._hook_tensor(kjt.values().device), st, kjt.values(), kjt.offsets()))
-            keys += g.embedding_names
-            lens += [g.dim] * g.F
+            res = _PeerLookup.apply(sm._hook_tensor(kjt.values().device), st, kjt.values(), kjt.offsets())
+            if pooled:
+                vals.append(res)
+                keys += g.embedding_names
+                lens += [g.dim] * g.F
+            else:
+                lpk, lengths, B = kjt.length_per_key(), kjt.lengths(), kjt.stride()
+                s = 0
+                for f, key in enumerate(g.embedding_names):
+                    out[key] = JaggedTensor(res[s:s + lpk[f]], lengths=lengths[f * B:(f + 1) * B])
+                    s += lpk[f]
+        if not pooled:
+            return out
         return KeyedTensor(keys, lens, vals[0] if len(vals) == 1 else torch.cat(vals, dim=1))
 
     sm.forward = forward
     sm._peer_states = states
     return states
+
+
+class PeerDenseGradSync(PeerBase):
+    """Average of the replicated dense gradients through peer memory (the reference wraps dense params in DDP,
+    dist_util.py:164-195): gradients accumulate into one flat local buffer; sync() publishes it, crosses one barrier
+    and sums all W published buffers in rank order into the flat buffer again — identical bits on every rank, one copy
+    + two small kernels, no NCCL."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], group=None, world: Optional[int] = None,
+                 rank: Optional[int] = None) -> None:
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device if self.params else "cpu"
+        super().__init__(group if (group is not None or world is not None) else dist.group.WORLD, dev, world, rank)
+        self.world = self.W
+        n = sum(p.numel() for p in self.params)
+        self.n = n
+        self.flat = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
+        self.pub = self._alloc(max(n, 1), torch.float32)
+        self.site = _Site(self)
+        self.zero()
+        self._host_barrier()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+        o = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self.flat[o:o + p.numel()].data_ptr():
+                p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def sync(self) -> None:
+        if self.W == 1 or self.n == 0:
+            return
+        self.pub.t.copy_(self.flat)
+        self._barrier(self.site)
+        Fn.backend().peer_allreduce_mean(self.pub, self.W, self.n, self.flat)
