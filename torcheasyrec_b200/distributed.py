@@ -467,7 +467,7 @@ def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows:
     `exchange="peer"`: the collections exchange through peer memory of the NVSwitch domain (csrc/tzk_peer.cu,
     peer_exchange.py) instead of NCCL all-to-alls; `static_capacity` is then the head-room factor of the wire buffers
     (default 1.5) and `ids_per_bag` (KJT key -> most ids per bag; sequence features: their sequence_length) sizes
-    features with more than one id per bag.  Sequence collections without a budget keep the NCCL path.
+    features with more than one id per bag (everything else: one id per bag).
 
     The model may have been built with its embedding collections on the meta device (as the reference does,
     embedding.py:187-188): shards are materialised directly on `device`, each rank initialising its own shard
@@ -484,12 +484,13 @@ def shard_model(model, device, default: str = ROW_WISE, group=None, rw_min_rows:
         new = cls(coll._configs, plan, device, group)
         pooled = isinstance(new, ShardedEmbeddingBagCollection)
         if exchange == "peer":         # peer-memory kernels instead of the NCCL all-to-alls (peer_exchange.py)
-            budget = {f: (ids_per_bag or {}).get(f) for g in new.groups for f in g.feature_names}
-            if pooled or all(v for v in budget.values()):
-                new._exchange = "peer"
-                new._ids_budget = {f: v for f, v in budget.items() if v}
-                for g in new.groups:
-                    g.static_alpha = float(static_capacity or 1.5)
+            # features without an entry in ids_per_bag carry one id per bag; a step with more ids than the budget
+            # raises in the lookup (host-side size check) instead of overflowing silently
+            new._exchange = "peer"
+            new._ids_budget = {f: int((ids_per_bag or {})[f]) for g in new.groups for f in g.feature_names
+                               if (ids_per_bag or {}).get(f)}
+            for g in new.groups:
+                g.static_alpha = float(static_capacity or 1.5)
         elif static_capacity and pooled:
             for g in new.groups:       # fixed-shape exchange (see _StaticDispatch); pooled collections only
                 g.static_alpha = float(static_capacity)
