@@ -202,13 +202,16 @@ def _cat_key_major(ids, offs, F, B, W):
 
 
 @pytest.mark.parametrize("kernels", ["model", "source"])
-@pytest.mark.parametrize("W,multi_hot", [(2, False), (3, False), (4, False), (2, True), (3, True)])
-def test_peer_step_matches_unsharded(W, multi_hot, kernels, host_compiled_peer_lib):
+@pytest.mark.parametrize("W,multi_hot,tiny_rw", [(2, False, False), (3, False, False), (4, False, False), (2, True, False),
+                                                 (3, True, False), (4, False, True), (8, False, True)])
+def test_peer_step_matches_unsharded(W, multi_hot, tiny_rw, kernels, host_compiled_peer_lib):
+    """tiny_rw: the 2-row table is split row-wise too (SURVEY §8c(5): a table smaller than W leaves ranks without rows;
+    997 rows over 8 ranks: hash_size % W != 0, short last shard)."""
     torch.manual_seed(0)
     rng = np.random.default_rng(7 + W)
     cfgs = _pooled_configs()
     B, D = 12, 16
-    plan = make_plan(cfgs, W, "row_wise", {"t_tw": [TABLE_WISE], "t_tiny": [TABLE_WISE]})
+    plan = make_plan(cfgs, W, "row_wise", {"t_tw": [TABLE_WISE]} if tiny_rw else {"t_tw": [TABLE_WISE], "t_tiny": [TABLE_WISE]})
     names = output_names_by_table(cfgs)
     spec = SparseOptimizerSpec(kind=OPT_ADAGRAD, lr=0.05)
     backend = OracleKernels() if kernels == "model" else SourceKernels(host_compiled_peer_lib)

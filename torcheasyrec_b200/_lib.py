@@ -83,6 +83,11 @@ SIGNATURES = {
     ),
     "tzk_bce_logits_workspace_bytes": (c_size_t, [c_int64]),
     "tzk_bce_logits_fwd_bwd": (c_int32, [P, P, c_int64, P, P, P, c_size_t, P]),
+    "tzk_dot_interact_bwd": (
+        c_int32,
+        [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, P, c_int64, P,
+         c_int64, P],
+    ),
     "tzk_peer_pooled_gather_fwd": (
         c_int32, [P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P]),
     "tzk_peer_seq_gather_fwd": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int64, P, P]),

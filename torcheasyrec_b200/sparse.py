@@ -59,8 +59,12 @@ class JaggedTensor:
 
         if desired_length is None:
             desired_length = int(self.lengths().max().item()) if self.lengths().numel() else 0
-        assert padding_value == 0.0
-        return jagged_to_padded_dense(self._values, self.offsets(), desired_length)
+        out = jagged_to_padded_dense(self._values, self.offsets(), desired_length)
+        if padding_value != 0.0:       # (the reference only pads with zeros; kept for API parity with torchrec)
+            lens = self.lengths().to(torch.int64).clamp(max=desired_length)
+            pad = torch.arange(desired_length, device=out.device)[None, :] >= lens[:, None]
+            out = out.masked_fill(pad.view(pad.shape + (1,) * (out.dim() - 2)), padding_value)
+        return out
 
 
 class KeyedJaggedTensor:
