@@ -319,6 +319,8 @@ class _ShardedBase(nn.Module):
             _DimGroup(cs, plan, self.rank, self.world, device, self._pooled, [names[c.name] for c in cs])
             for cs in by_dim.values()]
         self.shards = nn.ModuleList([g.local for g in self.groups])   # registers the local arenas
+        for g in self.groups:            # checkpoints address the tables through this module's keys only
+            g.local._load_via_owner = True
         self._hook = None
 
     def set_optimizer(self, spec: SparseOptimizerSpec) -> None:
@@ -356,6 +358,71 @@ class _ShardedBase(nn.Module):
         if self._hook is None or self._hook.device != device:
             self._hook = torch.zeros(1, device=device, requires_grad=True)
         return self._hook
+
+    # ---- checkpoint keys: the reference's per-table names, never `shards.*` -------------------------
+    def _table_attr(self) -> str:
+        return "embedding_bags" if self._pooled else "embeddings"
+
+    def _table_shard(self, name: str):
+        for g in self.groups:
+            for t, c in enumerate(g.configs):
+                if c.name == name:
+                    sh = self.plan[name]
+                    start = 0 if sh.kind == TABLE_WISE else self.rank * sh.block
+                    n = g.local._table_rows[t]
+                    return c, start, (g.local.table_weight(t) if n else None)
+        raise KeyError(name)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """One entry per table, `<prefix>embedding_bags.<table>.weight`: a ShardedTensor of the table's global
+        [rows, D] shape whose local shard views this rank's arena (what torchrec's sharded modules return and
+        torch.distributed.checkpoint re-shards on load).  Collective."""
+        from collections import OrderedDict
+
+        from .checkpoint import sharded_rows_tensor
+
+        if args:
+            destination = args[0]
+            prefix = args[1] if len(args) > 1 else prefix
+        destination = OrderedDict() if destination is None else destination
+        for c in self._configs:
+            _, start, local = self._table_shard(c.name)
+            destination[f"{prefix}{self._table_attr()}.{c.name}.weight"] = sharded_rows_tensor(
+                local, start, (c.num_embeddings, c.embedding_dim), self._group)
+        return destination
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        """Accepts, per table, the full [rows, D] tensor (a reference / W=1 checkpoint: this rank keeps its rows) or a
+        ShardedTensor whose local shard matches this rank's (the in-place DCP flow)."""
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+
+        for c in self._configs:
+            key = f"{prefix}{self._table_attr()}.{c.name}.weight"
+            if key not in state_dict:
+                if strict:
+                    missing_keys.append(key)
+                continue
+            v = state_dict[key]
+            _, start, local = self._table_shard(c.name)
+            if isinstance(v, ShardedTensor):
+                shards = v.local_shards()
+                if local is None:
+                    continue
+                if len(shards) != 1 or list(shards[0].tensor.shape) != list(local.shape) or \
+                        shards[0].metadata.shard_offsets[0] != start:
+                    error_msgs.append(f"{key}: the ShardedTensor's local shard does not match this rank's rows "
+                                      f"[{start}, {start + local.shape[0]})")
+                    continue
+                if shards[0].tensor.data_ptr() != local.data_ptr():
+                    with torch.no_grad():
+                        local.copy_(shards[0].tensor)
+            else:
+                if tuple(v.shape) != (c.num_embeddings, c.embedding_dim):
+                    error_msgs.append(f"size mismatch for {key}: checkpoint {tuple(v.shape)}, table "
+                                      f"{(c.num_embeddings, c.embedding_dim)}")
+                    continue
+                self.load_full_table(c.name, v)
 
     def load_full_table(self, name: str, full: torch.Tensor) -> None:
         """Copies this rank's rows of a full (unsharded) table into the local shard (parity tests, restore)."""

@@ -206,6 +206,8 @@ class _ArenaCollection(nn.Module):
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
+        if getattr(self, "_load_via_owner", False):     # local shard of a sharded collection: its owner loaded it
+            return
         arena_key = prefix + "weights"          # checkpoints written by earlier versions of this package
         if arena_key in state_dict:
             w = state_dict[arena_key]
