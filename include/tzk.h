@@ -270,6 +270,25 @@ size_t tzk_bce_logits_workspace_bytes(int64_t M);
 int tzk_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t M, float* loss, float* dlogits,
                            void* workspace, size_t workspace_bytes, tzk_stream_t stream);
 
+/* ---- DIN target attention over jagged sequence rows (tzrec/modules/sequence.py:65-128 without the padded
+ * [B, T, Ds] tensor of tzrec/modules/embedding.py:1466-1480).  seq [N, Ds]: the un-pooled lookup's rows,
+ * sample b owns rows offsets[b] .. offsets[b+1]; query [B, Dq] (row stride ld_q), Dq <= Ds (zero-padded to Ds).
+ *   din_attn_input_fwd : out[n, :] = [q_b | k_n | q_b - k_n | q_b * k_n]            ([N, 4 * Ds])
+ *   din_attn_input_bwd : d_seq[n] = g2 - g3 + g4 * q_b, d_query[b] = sum_n (g1 + g3 + g4 * k_n)   (rows in order)
+ *   jagged_softmax_wsum_fwd : p = softmax(scores[first min(len, max_len) rows of b]) (max_len <= 0: all), probs[n]
+ *                             (0 beyond max_len), out[b] = sum_n p_n k_n; a sample without rows gives zeros
+ *   jagged_softmax_wsum_bwd : d_scores[n] = p_n (<d_out_b, k_n> - sum_m p_m <d_out_b, k_m>), d_seq[n] = p_n d_out_b */
+int tzk_din_attn_input_fwd(const float* query, int64_t ld_q, int32_t Dq, const float* seq, const int64_t* offsets,
+                           int32_t B, int32_t Ds, int64_t N, float* out, tzk_stream_t stream);
+int tzk_din_attn_input_bwd(const float* d_in, const float* query, int64_t ld_q, int32_t Dq, const float* seq,
+                           const int64_t* offsets, int32_t B, int32_t Ds, int64_t N, float* d_query, float* d_seq,
+                           tzk_stream_t stream);
+int tzk_jagged_softmax_wsum_fwd(const float* scores, const float* seq, const int64_t* offsets, int32_t B, int32_t Ds,
+                                int32_t max_len, int64_t N, float* probs, float* out, tzk_stream_t stream);
+int tzk_jagged_softmax_wsum_bwd(const float* d_out, const float* probs, const float* seq, const int64_t* offsets,
+                                int32_t B, int32_t Ds, int32_t max_len, int64_t N, float* d_scores, float* d_seq,
+                                tzk_stream_t stream);
+
 /* ---- sharded sparse step over peer memory (NVSwitch domain; replaces the KJT / pooled-embedding / sequence-embedding
  * all-to-alls and the reduce-scatter of torchrec's ShardedEmbeddingBagCollection / ShardedEmbeddingCollection and the DDP
  * all-reduce of the dense gradients: SURVEY.md §2.3 C1-C5, App. A.5-A.8, reached from tzrec/main.py:799).  `*_ptrs`

@@ -333,3 +333,59 @@ class OracleKernels:
         recv_ids = torch.tensor(ids_out, dtype=torch.int64)
         bounds = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
         self.fused_bwd(optimizer, False, recv_g, weights, state, tl, recv_ids, bounds, 1, lr, eps, grad_scale, **ex)
+
+    # ------------------------------------------------------------------ DIN attention over jagged rows (tzk_din.cu)
+    def din_attn_input_fwd(self, query, seq, offsets):
+        q, k, off = _np(query), _np(seq), _np(offsets)
+        N, Ds = k.shape
+        B, Dq = q.shape
+        qp = np.zeros((B, Ds), dtype=np.float32)
+        qp[:, :Dq] = q
+        seg = np.repeat(np.arange(B), np.diff(off))
+        qn = qp[seg]
+        return torch.from_numpy(np.concatenate([qn, k, qn - k, qn * k], axis=1).astype(np.float32))
+
+    def din_attn_input_bwd(self, d_in, query, seq, offsets):
+        g, q, k, off = _np(d_in), _np(query), _np(seq), _np(offsets)
+        N, Ds = k.shape
+        B, Dq = q.shape
+        qp = np.zeros((B, Ds), dtype=np.float32)
+        qp[:, :Dq] = q
+        seg = np.repeat(np.arange(B), np.diff(off))
+        g1, g2, g3, g4 = g[:, :Ds], g[:, Ds:2 * Ds], g[:, 2 * Ds:3 * Ds], g[:, 3 * Ds:]
+        d_seq = (g2 - g3 + g4 * qp[seg]).astype(np.float32)
+        dq = np.zeros((B, Ds), dtype=np.float32)
+        np.add.at(dq, seg, (g1 + g3 + g4 * k).astype(np.float32))
+        return torch.from_numpy(dq[:, :Dq].copy()), torch.from_numpy(d_seq)
+
+    def jagged_softmax_wsum_fwd(self, scores, seq, offsets, max_len=0):
+        s, k, off = _np(scores), _np(seq), _np(offsets)
+        B = len(off) - 1
+        probs = np.zeros(len(s), dtype=np.float32)
+        out = np.zeros((B, k.shape[1]), dtype=np.float32)
+        for b in range(B):
+            lo, hi = off[b], off[b + 1]
+            if max_len > 0:
+                hi = min(hi, lo + max_len)
+            if hi > lo:
+                e = np.exp(s[lo:hi] - s[lo:hi].max()).astype(np.float32)
+                p = (e / e.sum(dtype=np.float32)).astype(np.float32)
+                probs[lo:hi] = p
+                out[b] = (p[:, None] * k[lo:hi]).sum(axis=0, dtype=np.float32)
+        return torch.from_numpy(probs), torch.from_numpy(out)
+
+    def jagged_softmax_wsum_bwd(self, d_out, probs, seq, offsets, max_len=0):
+        g, p, k, off = _np(d_out), _np(probs), _np(seq), _np(offsets)
+        B = len(off) - 1
+        d_s = np.zeros(len(p), dtype=np.float32)
+        d_k = np.zeros_like(k)
+        for b in range(B):
+            lo, hi = off[b], off[b + 1]
+            if max_len > 0:
+                hi = min(hi, lo + max_len)
+            if hi > lo:
+                dp = k[lo:hi] @ g[b]
+                t = (p[lo:hi] * dp).sum(dtype=np.float32)
+                d_s[lo:hi] = p[lo:hi] * (dp - t)
+                d_k[lo:hi] = p[lo:hi, None] * g[b][None, :]
+        return torch.from_numpy(d_s), torch.from_numpy(d_k)

@@ -636,3 +636,43 @@ def test_wide_layer_on_tcgen05_matches_fp64(monkeypatch, M):
     scale = float(M) ** 0.5
     np.testing.assert_allclose(lin.weight.grad.cpu().numpy(), wr.grad.cpu().numpy(), atol=2e-5 * scale)
     np.testing.assert_allclose(lin.bias.grad.cpu().numpy(), br.grad.cpu().numpy(), atol=2e-5 * scale)
+
+
+@pytest.mark.parametrize("B,Ds,Dq,max_len,max_rows", [(1, 16, 16, 0, 5), (37, 48, 48, 0, 100), (300, 24, 8, 4, 9),
+                                                      (8192, 48, 48, 0, 100), (64, 33, 33, 0, 40)])
+def test_din_jagged_kernels_match_oracle(kernels, B, Ds, Dq, max_len, max_rows):
+    """csrc/tzk_din.cu against the numpy restatement that the reference-generated DIN vectors pin
+    (tests/test_model_blocks_pinning.py::test_jagged_din_attention_matches_the_reference_module): ragged lengths incl.
+    empty samples, query narrower than the rows, max_seq_length truncation."""
+    rng = np.random.default_rng(B * 7 + Ds)
+    lens = rng.integers(0, max_rows + 1, B)
+    lens[rng.integers(0, B)] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    N = int(off[-1])
+    q = rng.standard_normal((B, Dq)).astype(np.float32)
+    k = rng.standard_normal((N, Ds)).astype(np.float32)
+    d_in = rng.standard_normal((N, 4 * Ds)).astype(np.float32)
+    sc = (rng.standard_normal(N) * 3).astype(np.float32)
+    d_out = rng.standard_normal((B, Ds)).astype(np.float32)
+    from oracle_backend import OracleKernels
+
+    ok = OracleKernels()
+    tq, tk, toff = torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(off)
+    want_in = ok.din_attn_input_fwd(tq, tk, toff)
+    got_in = kernels.din_attn_input_fwd(cu(q), cu(k), cu(off))
+    assert torch.equal(got_in.cpu(), want_in)
+    wdq, wdk = ok.din_attn_input_bwd(torch.from_numpy(d_in), tq, tk, toff)
+    gdq, gdk = kernels.din_attn_input_bwd(cu(d_in), cu(q), cu(k), cu(off))
+    np.testing.assert_allclose(gdk.cpu().numpy(), wdk.numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(gdq.cpu().numpy(), wdq.numpy(), rtol=2e-5, atol=2e-5)
+    wp, wo = ok.jagged_softmax_wsum_fwd(torch.from_numpy(sc), tk, toff, max_len)
+    gp, go = kernels.jagged_softmax_wsum_fwd(cu(sc), cu(k), cu(off), max_len)
+    np.testing.assert_allclose(gp.cpu().numpy(), wp.numpy(), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(go.cpu().numpy(), wo.numpy(), rtol=2e-5, atol=2e-6)
+    wds, wdk2 = ok.jagged_softmax_wsum_bwd(torch.from_numpy(d_out), wp, tk, toff, max_len)
+    gds, gdk2 = kernels.jagged_softmax_wsum_bwd(cu(d_out), gp, cu(k), cu(off), max_len)
+    np.testing.assert_allclose(gds.cpu().numpy(), wds.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gdk2.cpu().numpy(), wdk2.numpy(), rtol=2e-5, atol=1e-7)
+    # run-to-run deterministic
+    gp2, go2 = kernels.jagged_softmax_wsum_fwd(cu(sc), cu(k), cu(off), max_len)
+    assert torch.equal(go, go2) and torch.equal(gp, gp2)

@@ -72,3 +72,48 @@ def test_task_tower_matches_reference_module():
     y.sum().backward()
     np.testing.assert_allclose(x.grad.numpy(), GOLD["tower_dx"], rtol=2e-5, atol=2e-6)
     _check_grads(tt, "tower")
+
+
+def _to_jagged(seq: np.ndarray, lens: np.ndarray):
+    rows = np.concatenate([seq[b, :l] for b, l in enumerate(lens)] + [np.zeros((0, seq.shape[2]), np.float32)])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    return rows, off
+
+
+@pytest.mark.parametrize("tag,kw", [("din", dict(sequence_dim=24, query_dim=24, input="seq", attn_mlp={"hidden_units": [48, 16]})),
+                                    ("din2", dict(sequence_dim=16, query_dim=8, input="s", attn_mlp={"hidden_units": [32]},
+                                                  max_seq_length=4))])
+def test_jagged_din_attention_matches_the_reference_module(tag, kw):
+    """the same reference-generated vectors through the JAGGED path (rows [N, Ds] + offsets, no padded
+    tensor): output, query / row gradients on the valid positions and every parameter gradient; padded positions have
+    zero gradient in the reference (masked before the softmax) and do not exist here."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from oracle_backend import OracleKernels
+
+    from torcheasyrec_b200 import functional as Fn
+
+    enc = _load(DINEncoder(**kw), tag)
+    g = kw["input"]
+    lens = GOLD[f"{tag}_len"].astype(np.int64)
+    rows, off = _to_jagged(GOLD[f"{tag}_seq"], np.minimum(lens, GOLD[f"{tag}_seq"].shape[1]))
+    q = t(f"{tag}_q", True)
+    r = torch.from_numpy(rows.copy()).requires_grad_(True)
+    with Fn.use_backend(OracleKernels()):
+        y = enc({f"{g}.query": q, f"{g}.sequence": r, f"{g}.sequence_length": torch.from_numpy(lens),
+                 f"{g}.sequence_offsets": torch.from_numpy(off)})
+        # a sample WITHOUT rows: the reference's softmax over an all-masked row is uniform over the T padded rows, which
+        # are zeros in the real pipeline (to_padded_dense) — i.e. a zero output, as here; the fixture filled the padding
+        # with random numbers, so those samples are compared with zero instead of the fixture
+        has = lens > 0
+        np.testing.assert_allclose(y.detach().numpy()[has], GOLD[f"{tag}_y"][has], rtol=1e-5, atol=1e-6)
+        assert not y.detach().numpy()[~has].any()
+        if tag == "din":
+            y.backward(t("din_dy"))
+        else:
+            y.sum().backward()
+    np.testing.assert_allclose(q.grad.numpy(), GOLD[f"{tag}_dq"], rtol=2e-5, atol=2e-6)
+    want, _ = _to_jagged(GOLD[f"{tag}_dseq"], np.minimum(lens, GOLD[f"{tag}_seq"].shape[1]))
+    np.testing.assert_allclose(r.grad.numpy(), want, rtol=2e-5, atol=2e-6)
+    _check_grads(enc, tag)

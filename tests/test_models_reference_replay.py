@@ -126,3 +126,38 @@ model_config {
     for k in ("logits_t1", "probs_t1", "logits_t2", "probs_t2"):
         assert pred[k].size() == (2,), k
     assert torch.all((pred["probs_t1"] > 0) & (pred["probs_t1"] < 1))
+
+
+def test_din_model_jagged_attention_equals_the_padded_reference_form(monkeypatch):
+    """SURVEY §8f N3 at the model level: MultiTowerDIN with the sequence rows kept jagged (default) against the same
+    model run the reference's way (TZK_DIN_JAGGED=0: longest-length read, padded [B, T, D], masked softmax) — same
+    logits, same loss, same tables and dense weights after a train step (oracle backend on CPU)."""
+    import sys
+
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from oracle_backend import OracleKernels
+
+    from torcheasyrec_b200 import functional as Fn
+    from torcheasyrec_b200.engine import Pipeline
+
+    with Fn.use_backend(OracleKernels()):
+        monkeypatch.setenv("TZK_DIN_JAGGED", "0")
+        pad = Pipeline("multi_tower_din_taobao", device="cpu", max_rows=200, seed=3)
+        monkeypatch.setenv("TZK_DIN_JAGGED", "1")
+        jag = Pipeline("multi_tower_din_taobao", device="cpu", max_rows=200, seed=3)
+        jag.model.load_state_dict(pad.model.state_dict())
+        assert not getattr(next(iter(pad.model.embedding_group.seq_emb_impls.values())), "_jagged_for_attention", None)
+        assert next(iter(jag.model.embedding_group.seq_emb_impls.values()))._jagged_for_attention
+        batch = pad.synthetic_batch(40, seed=9)
+        with torch.no_grad():
+            a, b = pad.model.predict(batch), jag.model.predict(batch)
+        np.testing.assert_allclose(b["logits"].numpy(), a["logits"].numpy(), rtol=1e-5, atol=1e-6)
+        la, lb = pad.eager_step(batch), jag.eager_step(batch)
+        np.testing.assert_allclose(float(lb), float(la), rtol=1e-6)
+        for ca, cb in zip(pad.model.sparse_collections(), jag.model.sparse_collections()):
+            np.testing.assert_allclose(cb.weights.detach().numpy(), ca.weights.detach().numpy(), rtol=1e-5, atol=1e-7)
+        for (n, pa), (_, pb) in zip(pad.model.named_parameters(), jag.model.named_parameters()):
+            np.testing.assert_allclose(pb.detach().numpy(), pa.detach().numpy(), rtol=2e-4, atol=2e-6, err_msg=n)

@@ -331,13 +331,19 @@ class SequenceEmbeddingGroupImpl(nn.Module):
         for gname, infos in self._group_to_shared_sequence.items():
             parts = []
             T = 1
+            rows_only = self._group_to_is_jagged[gname] or gname in getattr(self, "_jagged_for_attention", ())
             for i, info in enumerate(infos):
                 jt = jt_dict[info.name]
                 if i == 0:
                     seq_len = jt.lengths()
-                    T = int(torch.max(seq_len).item()) if seq_len.numel() else 0   # host sync as in :1468
                     results[f"{gname}.sequence_length"] = seq_len
-                parts.append(jt.values() if self._group_to_is_jagged[gname] else jt.to_padded_dense(T))  # :1475-1480
+                    if gname in getattr(self, "_jagged_for_attention", ()):
+                        # the consumer (DIN attention, csrc/tzk_din.cu) works on the gather's rows as
+                        # they are: no longest-length host read (:1468), no padded [B, T, D] tensor (:1480)
+                        results[f"{gname}.sequence_offsets"] = jt.offsets()
+                    elif not rows_only:
+                        T = int(torch.max(seq_len).item()) if seq_len.numel() else 0   # host sync as in :1468
+                parts.append(jt.values() if rows_only else jt.to_padded_dense(T))  # :1475-1480
             if parts:
                 results[f"{gname}.sequence"] = torch.cat(parts, dim=-1)
         return results
@@ -505,6 +511,13 @@ class EmbeddingGroup(nn.Module):
         for k, impl in self.seq_emb_impls.items():
             out.update(impl.parameter_constraints(f"{prefix}seq_emb_impls.{k}."))
         return out
+
+    def set_jagged_for_attention(self, group_names) -> None:
+        """The named sequence groups emit `<g>.sequence` as the un-pooled gather's rows [N, D] plus `<g>.sequence_offsets`
+        [B + 1] instead of the padded [B, T, D] tensor (consumers: jagged DIN attention)."""
+        names = set(group_names)
+        for impl in self.seq_emb_impls.values():
+            impl._jagged_for_attention = names & set(impl._group_to_shared_sequence)
 
     def sparse_collections(self):
         """All arena-backed collections (what BaseModel.sparse_parameters discovers, models/model.py:162-201)."""

@@ -250,3 +250,47 @@ def dlrm_interaction(dense_feat: Optional[torch.Tensor], sparse_feat: torch.Tens
     rest = (dim if (with_dense and dense_feat is not None) else 0) + (num_sparse * dim if with_sparse else 0)
     out = _DotInteract.apply(dense_feat, sparse_feat, num_sparse, dim, with_dense, with_sparse, 4, p_pad)
     return out, ((0, 0, P), (P, P + p_pad, rest))
+
+
+# ------------------------------------------------------------------------------------------------ N3: jagged DIN
+class _DinAttnInput(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query, seq, offsets):
+        q, k = _rows_contig(query), seq.contiguous()
+        ctx.save_for_backward(q, k, offsets)
+        return backend().din_attn_input_fwd(q, k, offsets)
+
+    @staticmethod
+    def backward(ctx, d_in):
+        q, k, offsets = ctx.saved_tensors
+        d_q, d_k = backend().din_attn_input_bwd(d_in.contiguous(), q, k, offsets)
+        return d_q, d_k, None
+
+
+class _JaggedSoftmaxWsum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, seq, offsets, max_len):
+        k = seq.contiguous()
+        probs, out = backend().jagged_softmax_wsum_fwd(scores.contiguous(), k, offsets, max_len)
+        ctx.save_for_backward(probs, k, offsets)
+        ctx.max_len = max_len
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        probs, k, offsets = ctx.saved_tensors
+        d_s, d_k = backend().jagged_softmax_wsum_bwd(d_out.contiguous(), probs, k, offsets, ctx.max_len)
+        return d_s, d_k, None, None
+
+
+def din_attn_input(query: torch.Tensor, seq: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """[N, 4*Ds] input of DIN's attention MLP for jagged sequence rows: [q | k | q - k | q * k]
+    (tzrec/modules/sequence.py:113-116 without the padded [B, T, Ds] broadcast)."""
+    return _DinAttnInput.apply(query, seq, offsets)
+
+
+def jagged_softmax_weighted_sum(scores: torch.Tensor, seq: torch.Tensor, offsets: torch.Tensor,
+                                max_len: int = 0) -> torch.Tensor:
+    """[B, Ds]: per sample softmax over its (first max_len) scores, then the weighted sum of its rows
+    (tzrec/modules/sequence.py:118-128; a sample without rows gives zeros like the masked padded version)."""
+    return _JaggedSoftmaxWsum.apply(scores, seq, offsets, int(max_len))

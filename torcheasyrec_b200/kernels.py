@@ -360,6 +360,59 @@ class CudaKernels:
         self.launches += 1
         return out
 
+    # ------------------------------------------------------------------ DIN attention over jagged rows (tzk_din.cu)
+    def din_attn_input_fwd(self, query: torch.Tensor, seq: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+        query, ld_q = _rows2d(query, "query")
+        _need(seq, torch.float32, "seq")
+        _need(offsets, torch.int64, "offsets")
+        B, Dq = query.shape
+        N, Ds = seq.shape
+        out = torch.empty((N, 4 * Ds), dtype=torch.float32, device=seq.device)
+        check(self._lib.tzk_din_attn_input_fwd(_ptr(query), ld_q, Dq, _ptr(seq), _ptr(offsets), B, Ds, N, _ptr(out),
+                                               _stream()), "tzk_din_attn_input_fwd")
+        self.launches += 1 if N else 0
+        return out
+
+    def din_attn_input_bwd(self, d_in: torch.Tensor, query: torch.Tensor, seq: torch.Tensor, offsets: torch.Tensor):
+        query, ld_q = _rows2d(query, "query")
+        _need(d_in, torch.float32, "d_in")
+        _need(seq, torch.float32, "seq")
+        B, Dq = query.shape
+        N, Ds = seq.shape
+        d_query = torch.empty((B, Dq), dtype=torch.float32, device=seq.device)
+        d_seq = torch.empty((N, Ds), dtype=torch.float32, device=seq.device)
+        check(self._lib.tzk_din_attn_input_bwd(_ptr(d_in), _ptr(query), ld_q, Dq, _ptr(seq), _ptr(offsets), B, Ds, N,
+                                               _ptr(d_query), _ptr(d_seq), _stream()), "tzk_din_attn_input_bwd")
+        self.launches += 1
+        return d_query, d_seq
+
+    def jagged_softmax_wsum_fwd(self, scores: torch.Tensor, seq: torch.Tensor, offsets: torch.Tensor, max_len: int = 0):
+        _need(scores, torch.float32, "scores")
+        _need(seq, torch.float32, "seq")
+        _need(offsets, torch.int64, "offsets")
+        N, Ds = seq.shape
+        B = offsets.numel() - 1
+        probs = torch.empty(N, dtype=torch.float32, device=seq.device)
+        out = torch.empty((B, Ds), dtype=torch.float32, device=seq.device)
+        check(self._lib.tzk_jagged_softmax_wsum_fwd(_ptr(scores), _ptr(seq), _ptr(offsets), B, Ds, int(max_len), N,
+                                                    _ptr(probs), _ptr(out), _stream()), "tzk_jagged_softmax_wsum_fwd")
+        self.launches += 1
+        return probs, out
+
+    def jagged_softmax_wsum_bwd(self, d_out: torch.Tensor, probs: torch.Tensor, seq: torch.Tensor, offsets: torch.Tensor,
+                                max_len: int = 0):
+        _need(d_out, torch.float32, "d_out")
+        _need(probs, torch.float32, "probs")
+        N, Ds = seq.shape
+        B = offsets.numel() - 1
+        d_scores = torch.empty(N, dtype=torch.float32, device=seq.device)
+        d_seq = torch.empty((N, Ds), dtype=torch.float32, device=seq.device)
+        check(self._lib.tzk_jagged_softmax_wsum_bwd(_ptr(d_out), _ptr(probs), _ptr(seq), _ptr(offsets), B, Ds,
+                                                    int(max_len), N, _ptr(d_scores), _ptr(d_seq), _stream()),
+              "tzk_jagged_softmax_wsum_bwd")
+        self.launches += 1 if N else 0
+        return d_scores, d_seq
+
     # ------------------------------------------------------------------ sharded step over peer memory (tzk_peer.cu)
     # `symm` arguments: objects with `.ptrs` = ctypes array [W] of device addresses (rank r's symmetric buffer as
     # mapped in this process) — peer_exchange._Symm.

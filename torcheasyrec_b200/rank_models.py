@@ -8,6 +8,8 @@ Dense towers stay plain PyTorch exactly as in the reference (parameter names are
 
 from typing import Any, Dict, List, Optional
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -182,6 +184,16 @@ class DINEncoder(nn.Module):
 
     def forward(self, emb: Dict[str, torch.Tensor]) -> torch.Tensor:
         query, sequence, seq_len = emb[self._q], emb[self._s], emb[self._l]
+        offsets = emb.get(self._s + "_offsets")
+        if offsets is not None:
+            # the sequence rows arrive jagged ([N, Ds], sample b = rows offsets[b]..offsets[b+1]) straight
+            # from the un-pooled gather: no padded [B, T, Ds] tensor, no host read of the longest length; the attention
+            # MLP runs over the N real rows only (csrc/tzk_din.cu around the dense layers)
+            from . import functional as Fn
+
+            attn_in = Fn.din_attn_input(query, sequence, offsets)
+            scores = self.linear(self.mlp(attn_in)).squeeze(-1)
+            return Fn.jagged_softmax_weighted_sum(scores, sequence, offsets, self._max_seq_length)
         if self._max_seq_length > 0:
             seq_len = torch.clamp_max(seq_len, self._max_seq_length)
             sequence = sequence[:, : self._max_seq_length, :]
@@ -378,6 +390,10 @@ class MultiTowerDIN(RankModel):
                              attn_mlp=config_to_kwargs(tower.attn_mlp))
             self.din_towers.append(enc)
             total += enc.output_dim()
+        # groups whose only consumer is DIN attention keep their rows jagged (TZK_DIN_JAGGED=0 restores
+        # the reference's padded [B, T, D] form)
+        if len(self.din_towers) and os.environ.get("TZK_DIN_JAGGED", "1") != "0":
+            eg.set_jagged_for_attention([t.input for t in self._model_config.din_towers])
         final_dim = total
         if self._model_config.HasField("final"):
             self.final_mlp = MLP(in_features=total, **config_to_kwargs(self._model_config.final))
