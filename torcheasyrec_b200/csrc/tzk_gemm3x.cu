@@ -311,227 +311,6 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 }
 
 // ======================================================================================================================
-// Ring variant (TZK_GEMM3X_RING=1) of the forward / input-gradient kernel: the same math as gemm3x_kernel<BN, STACK = 1,
-// RAW = 1, SPLIT = 1>, but the X stream gets a ring of its own.  The first hardware numbers say the pipeline is bound
-// by latency x bytes in flight (four 48-KB stages = 64 KB of X per SM in flight); a stage holds X for the whole
-// TMA -> transform -> MMA chain although only X comes from HBM.  Here X lands in one of DX 16-KB slots and is used IN
-// PLACE as the hi operand (the tensor core truncates), while lo(X) and the two W operands live in a short work ring of
-// DW slots that turns over at the pace of transform + MMA: 6 x 16 KB of X in flight per SM instead of 4 x 16 KB in the
-// same shared memory.  Eleven warps: X producer, W producer, MMA issuer (+ TMEM), 4 transform, 4 epilogue.
-template <int BN>
-struct RingCfg {
-  static constexpr int W_BYTES = BN * BK * 4;                      // one of W_hi / W_lo per k-chunk
-  static constexpr int WORK_BYTES = X_BYTES + 2 * W_BYTES;         // lo(X) | W_hi | W_lo (contiguous: stacked B operand)
-  static constexpr int DX = BN <= 64 ? 6 : 5;
-  static constexpr int DW = 3;
-  static constexpr int P = BN <= 64 ? 2 : 1;                       // partial accumulators (see Cfg)
-  static constexpr int ACC_COLS = P * 2 * BN;
-  static constexpr int SMEM = DX * X_BYTES + DW * WORK_BYTES + 512;
-  static_assert(W_BYTES % 1024 == 0, "W operands must be whole 8-row groups");
-  static_assert(2 * ACC_COLS <= 512, "two tiles in flight must fit TMEM");
-};
-constexpr int RING_THREADS = 11 * 32;
-
-struct RingParams {
-  Params p;
-  int prefetch;        // > 0: L2 prefetch of the X boxes that many chunks ahead
-};
-
-template <int BN>
-__global__ void __launch_bounds__(RING_THREADS, 1)
-gemm3x_ring_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
-                   const __grid_constant__ CUtensorMap map_wlo, RingParams rp) {
-  using C = RingCfg<BN>;
-  constexpr int DX = C::DX, DW = C::DW, P = C::P, ACC_COLS = C::ACC_COLS, W_BYTES = C::W_BYTES;
-  const Params& p = rp.p;
-  TZK_DYN_SMEM(uint8_t, smem);
-  uint8_t* xring = smem;                                  // DX x 16 KB, raw fp32 = hi operand
-  uint8_t* wring = smem + DX * X_BYTES;                   // DW x (lo(X) 16 KB | W_hi | W_lo)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + DW * C::WORK_BYTES);
-  uint64_t* xfull = bars;                    // [DX] TMA X -> transform (and, through lo_ready, the MMA)
-  uint64_t* xempty = xfull + DX;             // [DX] MMA commit -> X producer
-  uint64_t* wfull = xempty + DX;             // [DW] TMA W -> MMA
-  uint64_t* lo_ready = wfull + DW;           // [DW] transform -> MMA (4 arrivals)
-  uint64_t* wempty = lo_ready + DW;          // [DW] MMA commit -> W producer and transform (lo slot free)
-  uint64_t* acc_full = wempty + DW;          // [2]
-  uint64_t* acc_empty = acc_full + 2;        // [2] (4 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_k = p.K / BK;
-  const int n_used = num_k < P ? num_k : P;
-  const int n_tiles = p.N / BN;
-  const int64_t num_tiles = (p.M + BM - 1) / BM * n_tiles;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < DX; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); }
-    for (int s = 0; s < DW; ++s) { mbar_init(wfull + s, 1); mbar_init(lo_ready + s, 4); mbar_init(wempty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
-    fence_mbarrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== X producer ==============================================================================================
-    if (lane == 0) {
-      int xs = 0;
-      uint32_t xph = 0;
-      int64_t pt = blockIdx.x;                // L2 prefetch cursor
-      int pkb = 0;
-      auto prefetch_next = [&] {
-        if (pt < num_tiles) {
-          tma_prefetch_2d(&map_x, pkb * BK, (int)(pt / n_tiles * BM));
-          if (++pkb == num_k) { pkb = 0; pt += gridDim.x; }
-        }
-      };
-      for (int i = 0; i < rp.prefetch; ++i) prefetch_next();
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
-        for (int kb = 0; kb < num_k; ++kb) {
-          if (rp.prefetch > 0) prefetch_next();
-          mbar_wait(xempty + xs, xph ^ 1);
-          mbar_expect_tx(xfull + xs, X_BYTES);
-          tma_load_2d(xring + xs * X_BYTES, &map_x, xfull + xs, kb * BK, (int)(t / n_tiles * BM));
-          if (++xs == DX) { xs = 0; xph ^= 1; }
-        }
-    }
-  } else if (warp == 1) {
-    // ===== W producer ==============================================================================================
-    if (lane == 0) {
-      int ws = 0;
-      uint32_t wph = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(wempty + ws, wph ^ 1);
-          uint8_t* wb = wring + ws * C::WORK_BYTES + X_BYTES;
-          mbar_expect_tx(wfull + ws, 2 * W_BYTES);
-          tma_load_2d(wb, &map_whi, wfull + ws, kb * BK, (int)(t % n_tiles) * BN);
-          tma_load_2d(wb + W_BYTES, &map_wlo, wfull + ws, kb * BK, (int)(t % n_tiles) * BN);
-          if (++ws == DW) { ws = 0; wph ^= 1; }
-        }
-    }
-  } else if (warp == 2) {
-    // ===== MMA issuer ==============================================================================================
-    int xs = 0, ws = 0, acc = 0;
-    uint32_t xph = 0, wph = 0, acc_phase = 0;
-    (void)xph;
-    constexpr uint32_t idesc = make_idesc<BN>();
-    constexpr uint32_t idesc2 = make_idesc<2 * BN>();
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait_all(acc_empty + acc, acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      uint32_t started = 0;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait_all(lo_ready + ws, wph);       // lo(X) written => X landed (the transform waited for it)
-        mbar_wait_all(wfull + ws, wph);          // W_hi / W_lo landed
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = smem_u32(xring + xs * X_BYTES);
-          const uint32_t a_lo = smem_u32(wring + ws * C::WORK_BYTES), b_hi = a_lo + X_BYTES;
-          const int part = kb * n_used / num_k;
-          const uint32_t region = d_tmem + part * 2 * BN;       // [hi*hi | hi*lo + lo*hi]
-#pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint32_t ko = k * UK * 4;
-            mma_tf32(region, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc2, (started >> part) & 1u);
-            mma_tf32(region + BN, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1u);
-            started |= 1u << part;
-          }
-          tc_commit(xempty + xs);
-          tc_commit(wempty + ws);
-          if (kb == num_k - 1) tc_commit(acc_full + acc);
-        }
-        __syncwarp();
-        if (++xs == DX) { xs = 0; xph ^= 1; }
-        if (++ws == DW) { ws = 0; wph ^= 1; }
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  } else if (warp < 7) {
-    // ===== transform warps (3..6): lo(X) = rna(x - trunc(x)) into the work ring =====================================
-    const int tw = warp - 3;
-    int xs = 0, ws = 0;
-    uint32_t xph = 0, wph = 0;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait_all(xfull + xs, xph);
-        mbar_wait_all(wempty + ws, wph ^ 1);      // the lo slot (and its W) of DW chunks ago has been consumed
-        const float4* hi = reinterpret_cast<const float4*>(xring + xs * X_BYTES);
-        float4* lo = reinterpret_cast<float4*>(wring + ws * C::WORK_BYTES);
-#pragma unroll
-        for (int q = 0; q < X_BYTES / 16 / 128; ++q) {
-          const int i = q * 128 + tw * 32 + lane;
-          const float4 x = hi[i];
-          float4 l;
-          l.x = tf32_rna(x.x - tf32_trunc(x.x)); l.y = tf32_rna(x.y - tf32_trunc(x.y));
-          l.z = tf32_rna(x.z - tf32_trunc(x.z)); l.w = tf32_rna(x.w - tf32_trunc(x.w));
-          lo[i] = l;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(lo_ready + ws);
-        if (++xs == DX) { xs = 0; xph ^= 1; }
-        if (++ws == DW) { ws = 0; wph ^= 1; }
-      }
-  } else {
-    // ===== epilogue warps (7..10) =====================================================================================
-    const int quarter = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait_all(acc_full + acc, acc_phase);
-      tc_fence_after();
-      const int64_t row = t / n_tiles * BM + quarter * 32 + lane;
-      const int col0 = (int)(t % n_tiles) * BN;
-      const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-      float v[16], v2[16];
-#pragma unroll
-      for (int part = 0; part < BN / 16; ++part) {
-        tmem_ld16(taddr + BN + part * 16, v);                 // small terms first, then the partials
-        for (int q = 1; q < n_used; ++q) {
-          tmem_ld16(taddr + q * 2 * BN + BN + part * 16, v2);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] += v2[c];
-        }
-        for (int q = 0; q < n_used; ++q) {
-          tmem_ld16(taddr + q * 2 * BN + part * 16, v2);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] += v2[c];
-        }
-        if (row < p.M) {
-          float* yr = p.y + row * p.ld_y + col0 + part * 16;
-#pragma unroll
-          for (int c = 0; c < 16; c += 4) {
-            float4 o;
-            o.x = v[c] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c) : 0.f);
-            o.y = v[c + 1] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 1) : 0.f);
-            o.z = v[c + 2] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 2) : 0.f);
-            o.w = v[c + 3] + (p.bias ? __ldg(p.bias + col0 + part * 16 + c + 3) : 0.f);
-            if (p.relu) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(yr + c) = o;
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + acc);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_free(tmem_base, 512);
-}
-
-// ======================================================================================================================
 // Weight gradient of the same layer:  dW[n, k] = sum_m dZ[m, n] * X[m, k]   (n < 64, k < K = 784, m < M = batch).
 // The reduction runs over the batch, so both operands are MN-major as they lie in memory: A = X^T (UMMA M = 128 of
 // X's columns), B = dZ^T (UMMA N = 64) — for 32-bit elements that means the SWIZZLE_128B_BASE32B shared-memory layout
@@ -697,166 +476,6 @@ wgrad3x_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (warp == 1) tmem_free(tmem_base, 512);
 }
 
-// Ring variant of the weight-gradient kernel (TZK_GEMM3X_RING=1), same idea as gemm3x_ring_kernel: the X boxes (the
-// only HBM stream) land in a ring of WG_DX 16-KB slots and are used in place as the hi operand; lo(X), the dZ boxes (raw
-// = hi) and lo(dZ) turn over in a work ring of WG_DW 32-KB slots.  Seven warps: X producer, dZ producer, MMA issuer,
-// four transform warps that also drain the accumulators at the end (one work item per CTA).
-constexpr int WG_DX = 6, WG_DW = 3;
-constexpr int WG_WORK = WG_A + 2 * WG_B;                 // lo(X) 16 KB | dZ raw 8 KB | lo(dZ) 8 KB
-constexpr int WG_RING_SMEM = WG_DX * WG_A + WG_DW * WG_WORK + 512;
-constexpr int WG_RING_THREADS = 7 * 32;
-
-__global__ void __launch_bounds__(WG_RING_THREADS, 1)
-wgrad3x_ring_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, WgParams p,
-                    int prefetch) {
-  TZK_DYN_SMEM(uint8_t, smem);
-  uint8_t* xring = smem;
-  uint8_t* wring = smem + WG_DX * WG_A;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + WG_DW * WG_WORK);
-  uint64_t* xfull = bars;                   // [DX] TMA X -> transform
-  uint64_t* xempty = xfull + WG_DX;         // [DX] MMA commit -> X producer
-  uint64_t* wfull = xempty + WG_DX;         // [DW] TMA dZ -> transform
-  uint64_t* lo_ready = wfull + WG_DW;       // [DW] transform -> MMA (4 arrivals)
-  uint64_t* wempty = lo_ready + WG_DW;      // [DW] MMA commit -> dZ producer, transform
-  uint64_t* acc_full = wempty + WG_DW;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x % p.k_tiles;
-  const int64_t slab = blockIdx.x / p.k_tiles;
-  const int64_t row0 = slab * p.slab_rows;
-  const int64_t rows = (p.M - row0 < p.slab_rows) ? p.M - row0 : p.slab_rows;
-  const int num_c = (int)((rows + WG_ROWS - 1) / WG_ROWS);
-  const int n_used = num_c < WG_P ? num_c : WG_P;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < WG_DX; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); }
-    for (int s = 0; s < WG_DW; ++s) { mbar_init(wfull + s, 1); mbar_init(lo_ready + s, 4); mbar_init(wempty + s, 1); }
-    mbar_init(acc_full, 1);
-    fence_mbarrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {                          // ---- X producer
-      int xs = 0;
-      uint32_t xph = 0;
-      for (int c = 0; c < prefetch && c < num_c; ++c)
-        for (int b = 0; b < 4; ++b) tma_prefetch_2d(&map_x, jt * 128 + b * 32, (int)(row0 + (int64_t)c * WG_ROWS));
-      for (int c = 0; c < num_c; ++c) {
-        if (prefetch > 0 && c + prefetch < num_c)
-          for (int b = 0; b < 4; ++b)
-            tma_prefetch_2d(&map_x, jt * 128 + b * 32, (int)(row0 + (int64_t)(c + prefetch) * WG_ROWS));
-        mbar_wait(xempty + xs, xph ^ 1);
-        mbar_expect_tx(xfull + xs, WG_A);
-        const int r = (int)(row0 + (int64_t)c * WG_ROWS);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(xring + xs * WG_A + b * WG_BOX, &map_x, xfull + xs, jt * 128 + b * 32, r);
-        if (++xs == WG_DX) { xs = 0; xph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {                          // ---- dZ producer
-      int ws = 0;
-      uint32_t wph = 0;
-      for (int c = 0; c < num_c; ++c) {
-        mbar_wait(wempty + ws, wph ^ 1);
-        mbar_expect_tx(wfull + ws, WG_B);
-        const int r = (int)(row0 + (int64_t)c * WG_ROWS);
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-          tma_load_2d(wring + ws * WG_WORK + WG_A + b * WG_BOX, &map_dz, wfull + ws, b * 32, r);
-        if (++ws == WG_DW) { ws = 0; wph ^= 1; }
-      }
-    }
-  } else if (warp == 2) {                     // ---- MMA issuer
-    int xs = 0, ws = 0;
-    uint32_t wph = 0;
-    constexpr uint32_t idesc = make_idesc<64, true>();
-    uint32_t started = 0;
-    for (int c = 0; c < num_c; ++c) {
-      mbar_wait_all(lo_ready + ws, wph);      // lo(X), lo(dZ) written => X and dZ landed
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_hi = smem_u32(xring + xs * WG_A);
-        const uint32_t a_lo = smem_u32(wring + ws * WG_WORK), b_hi = a_lo + WG_A, b_lo = b_hi + WG_B;
-        const int part = c * n_used / num_c;
-        const uint32_t d_main = tmem_base + part * 64, d_small = tmem_base + WG_P * 64;
-#pragma unroll
-        for (int k = 0; k < WG_ROWS / UK; ++k) {
-          const uint32_t ko = k * 1024;
-          mma_tf32(d_main, make_desc_mn(a_hi + ko, WG_BOX, 512), make_desc_mn(b_hi + ko, WG_BOX, 512), idesc,
-                   (started >> part) & 1u);
-          mma_tf32(d_small, make_desc_mn(a_lo + ko, WG_BOX, 512), make_desc_mn(b_hi + ko, WG_BOX, 512), idesc,
-                   (started >> WG_P) & 1u);
-          mma_tf32(d_small, make_desc_mn(a_hi + ko, WG_BOX, 512), make_desc_mn(b_lo + ko, WG_BOX, 512), idesc, 1u);
-          started |= (1u << part) | (1u << WG_P);
-        }
-        tc_commit(xempty + xs);
-        tc_commit(wempty + ws);
-        if (c == num_c - 1) tc_commit(acc_full);
-      }
-      __syncwarp();
-      if (++xs == WG_DX) xs = 0;
-      if (++ws == WG_DW) { ws = 0; wph ^= 1; }
-    }
-  } else {                                    // ---- transform warps (3..6), then the epilogue
-    const int tw = warp - 3, quarter = warp & 3;
-    int xs = 0, ws = 0;
-    uint32_t xph = 0, wph = 0;
-    for (int c = 0; c < num_c; ++c) {
-      mbar_wait_all(xfull + xs, xph);
-      mbar_wait_all(wfull + ws, wph);           // dZ landed in this work slot (its producer waited for wempty)
-      const float4* ax = reinterpret_cast<const float4*>(xring + xs * WG_A);
-      uint8_t* wb = wring + ws * WG_WORK;
-      float4* alo = reinterpret_cast<float4*>(wb);
-      const float4* bx = reinterpret_cast<const float4*>(wb + WG_A);
-      float4* blo = reinterpret_cast<float4*>(wb + WG_A + WG_B);
-#pragma unroll
-      for (int q = 0; q < (WG_A + WG_B) / 16 / 128; ++q) {
-        const int i = q * 128 + tw * 32 + lane;                       // 0..1535: X part, then dZ part
-        const bool in_a = i < WG_A / 16;
-        const float4 x = in_a ? ax[i] : bx[i - WG_A / 16];
-        float4 l;
-        l.x = tf32_rna(x.x - tf32_trunc(x.x)); l.y = tf32_rna(x.y - tf32_trunc(x.y));
-        l.z = tf32_rna(x.z - tf32_trunc(x.z)); l.w = tf32_rna(x.w - tf32_trunc(x.w));
-        if (in_a) alo[i] = l;
-        else blo[i - WG_A / 16] = l;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(lo_ready + ws);
-      if (++xs == WG_DX) { xs = 0; xph ^= 1; }
-      if (++ws == WG_DW) { ws = 0; wph ^= 1; }
-    }
-    mbar_wait_all(acc_full, 0);
-    tc_fence_after();
-    const int krow = jt * 128 + quarter * 32 + lane;
-    float* out = p.partial + ((int64_t)slab * p.k_tiles * 128 + krow) * 64;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    float v[16], v2[16];
-#pragma unroll
-    for (int part = 0; part < 4; ++part) {
-      tmem_ld16(taddr + WG_P * 64 + part * 16, v);
-      for (int q = 0; q < n_used; ++q) {
-        tmem_ld16(taddr + q * 64 + part * 16, v2);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] += v2[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 16; c += 4)
-        *reinterpret_cast<float4*>(out + part * 16 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_free(tmem_base, 512);
-}
-
 // dW[n, k] = sum over slabs (fixed order) of partial[s, k, n]; one thread per (k, n), n fastest for the reads
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slabs, int k_pad, int K, float* __restrict__ dw,
                                     int64_t ld_dw) {
@@ -902,12 +521,6 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
 }
 #endif
 
-// RAW variant: hi is w itself (the tensor core truncates), only the residual is written
-__global__ void split_w_raw_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ lo) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) lo[i] = tf32_rna(w[i] - tf32_trunc(w[i]));
-}
-
 __global__ void split_w_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -937,28 +550,6 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMa
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
-template <int BN>
-static int launch_ring(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, int prefetch,
-                       cudaStream_t st) {
-  static int sms = 0;
-  if (sms == 0) {
-#ifndef TZK_CPU_SHIM
-    cudaFuncSetAttribute(gemm3x_ring_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<BN>::SMEM);
-#endif
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    sms = n > 0 ? n : 148;
-  }
-  RingParams rp;
-  rp.p = p;
-  rp.prefetch = prefetch;
-  const int64_t tiles = (p.M + BM - 1) / BM * (p.N / BN);
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  TZK_LAUNCH((gemm3x_ring_kernel<BN>), grid, RING_THREADS, (size_t)RingCfg<BN>::SMEM, st, mx, mh, ml, rp);
-  return cudaGetLastError() == cudaSuccess ? 0 : 3;
-}
-
 // y[M,N] = act(x[M,K] @ w[N,K]^T + bias) with fp32-equivalent accuracy (3xTF32).  N = 64 (forward of the wide tower
 // layer, K = 784) or a multiple of 112 (its input gradient: x = dZ [M,64], w = W^T [784,64], no bias / ReLU).
 // Rows 16-B aligned, ld % 4 == 0; K columns beyond the tensor are read as zeros up to the next multiple of 32.
@@ -971,40 +562,17 @@ extern "C" int tzk_gemm3x(const float* x, int64_t ld_x, const float* w, int64_t 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int BN = N == 64 ? 64 : 112;
   const int64_t nw = (int64_t)N * ld_w;
-  const char* r = getenv("TZK_GEMM3X_RAW");       // 1: raw fp32 as the hi operands (see gemm3x_kernel); default: rounded split
-  const char* rg = getenv("TZK_GEMM3X_RING");     // 1: gemm3x_ring_kernel (implies RAW, STACK, dedicated epilogue warps)
-  const bool ring = rg && rg[0] == '1';
-  const bool raw = (r && r[0] == '1') || ring;
-  if (raw) TZK_LAUNCH((split_w_raw_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_lo);
-  else TZK_LAUNCH((split_w_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_hi, w_lo);
+  // One configuration is built (measured r2, B = 65536: 3-MMA 93 / 125 us, stacked 80 / 121, stacked + dedicated
+  // epilogue warps 76 / 99 us forward / input gradient; raw-hi, eight transform warps, L2 prefetch and the ring variant
+  // were equal or slower — profiles/r2_gemm3x_variants.txt): stacked W_hi / W_lo, four transform + four epilogue warps.
+  TZK_LAUNCH((split_w_kernel), (unsigned)((nw + 255) / 256), 256, 0, st, w, nw, w_hi, w_lo);
   CUtensorMap mx, mh, ml;
-  if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, raw ? w : w_hi, N, K, ld_w, BN) || make_map(&ml, w_lo, N, K, ld_w, BN))
+  if (make_map(&mx, x, M, K, ld_x, BM) || make_map(&mh, w_hi, N, K, ld_w, BN) || make_map(&ml, w_lo, N, K, ld_w, BN))
     return 2;
   Params p;
   p.bias = bias; p.y = y; p.ld_y = ld_y; p.M = M; p.K = (K + BK - 1) / BK * BK; p.N = N; p.relu = relu;
-  if (ring) {
-    const char* pfr = getenv("TZK_GEMM3X_PREFETCH");
-    const int pfd = (pfr && pfr[0] == '1') ? PF_DIST : 0;
-    return BN == 64 ? launch_ring<64>(mx, mh, ml, p, pfd, st) : launch_ring<112>(mx, mh, ml, p, pfd, st);
-  }
-  const char* e = getenv("TZK_GEMM3X_STACK");     // default: two MMAs per k-step (see gemm3x_kernel); 0: three
-  const char* t = getenv("TZK_GEMM3X_TW");        // 8: eight transform / epilogue warps; default: four
-  const bool stack = !(e && e[0] == '0'), tw8 = t && t[0] == '8';   // measured r2: stacked + split is the fastest
-  const char* sp = getenv("TZK_GEMM3X_SPLIT");    // default: dedicated epilogue warps (see gemm3x_kernel); 0: shared
-  const bool split = !(sp && sp[0] == '0');
-  const char* pfe = getenv("TZK_GEMM3X_PREFETCH");   // 1: L2 prefetch of the X boxes ahead of the loads (stacked variant only)
-  const bool pf = pfe && pfe[0] == '1' && stack;
-#define TZK_G3P(BN_, S_, T_, R_, SP_) ((S_ && pf) ? launch<BN_, S_, T_, R_, SP_, S_>(mx, mh, ml, p, st) \
-                                                 : launch<BN_, S_, T_, R_, SP_, false>(mx, mh, ml, p, st))
-#define TZK_G3S(BN_, S_, T_, R_) (split ? TZK_G3P(BN_, S_, T_, R_, true) : TZK_G3P(BN_, S_, T_, R_, false))
-#define TZK_G3R(BN_, S_, T_) (raw ? TZK_G3S(BN_, S_, T_, true) : TZK_G3S(BN_, S_, T_, false))
-#define TZK_G3(BN_) (stack ? (tw8 ? TZK_G3R(BN_, true, 8) : TZK_G3R(BN_, true, 4)) \
-                           : (tw8 ? TZK_G3R(BN_, false, 8) : TZK_G3R(BN_, false, 4)))
-  return BN == 64 ? TZK_G3(64) : TZK_G3(112);
-#undef TZK_G3R
-#undef TZK_G3S
-#undef TZK_G3P
-#undef TZK_G3
+  return BN == 64 ? launch<64, true, 4, false, true, false>(mx, mh, ml, p, st)
+                  : launch<112, true, 4, false, true, false>(mx, mh, ml, p, st);
 }
 
 // dw[64, K] = dz[M, 64]^T @ x[M, K]  (3xTF32; fixed-order reduction over `slabs` row slabs -> run-to-run deterministic).
@@ -1029,24 +597,10 @@ extern "C" int tzk_wgrad3x(const float* x, int64_t ld_x, const float* dz, int64_
   static bool configured = false;     // once: nothing but the launches happens inside a stream capture
   if (!configured) {
     cudaFuncSetAttribute(wgrad3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(wgrad3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
 #endif
-  const char* pfe = getenv("TZK_GEMM3X_PREFETCH");
-  const char* rg = getenv("TZK_GEMM3X_RING");
-  if (rg && rg[0] == '1') {
-#ifndef TZK_CPU_SHIM
-    static bool ring_configured = false;
-    if (!ring_configured) {
-      cudaFuncSetAttribute(wgrad3x_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_RING_SMEM);
-      ring_configured = true;
-    }
-#endif
-    TZK_LAUNCH((wgrad3x_ring_kernel), used * p.k_tiles, WG_RING_THREADS, (size_t)WG_RING_SMEM, st, mx, mz, p,
-               (pfe && pfe[0] == '1') ? PF_DIST : 0);
-  } else if (pfe && pfe[0] == '1') TZK_LAUNCH((wgrad3x_kernel<true>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
-  else TZK_LAUNCH((wgrad3x_kernel<false>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
+  TZK_LAUNCH((wgrad3x_kernel<false>), used * p.k_tiles, NUM_THREADS, smem, st, mx, mz, p);
   TZK_LAUNCH((wgrad_reduce_kernel), (K * 64 + 255) / 256, 256, 0, st, partial, used, p.k_tiles * 128, K, dw, ld_dw);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

@@ -60,6 +60,8 @@ class Pipeline:
         self.features: List[BaseFeature] = create_features(list(self.cfg.feature_configs),
                                                            fg_mode=self.cfg.data_config.fg_mode)
         self.labels = list(self.cfg.data_config.label_fields)
+        if list(self.cfg.data_config.sample_weight_fields):
+            raise NotImplementedError("data_config.sample_weight_fields: weighted losses are outside the hot-path scope")
         torch.manual_seed(seed)
         self.sharded, self.grad_sync = [], None
         if sharding is None:

@@ -225,6 +225,9 @@ class RankModel(nn.Module):
         self._num_class = model_config.num_class
         self._label_name = labels[0] if labels else None
         self._sample_weights = sample_weights or []
+        if self._sample_weights:
+            raise NotImplementedError("sample_weight_fields: weighted losses (rank_model.py:264-287 div_no_nan weighting) "
+                                      "are outside the hot-path scope")
         self._device = device
         self.embedding_group: Optional[EmbeddingGroup] = None
         for lc in model_config.losses:
@@ -425,6 +428,15 @@ class MMoE(RankModel):
             gate_mlp=config_to_kwargs(self._model_config.gate_mlp) if self._model_config.HasField("gate_mlp") else None)
         self._task_tower = nn.ModuleList()
         for cfg in self._task_tower_cfgs:
+            # what the reference honours per tower (models/multi_task_rank.py:97-125) and this repo does not: refuse it
+            # instead of silently training with plain mean BCE
+            for fld in ("sample_weight_name", "task_space_indicator_label"):
+                if cfg._spec(fld) is not None and cfg.HasField(fld) and getattr(cfg, fld):
+                    raise NotImplementedError(f"task tower {cfg.tower_name}: {fld} is outside the hot-path scope")
+            for lc in (cfg.losses if cfg._spec("losses") is not None else []):
+                if lc.WhichOneof("loss") not in (None, "binary_cross_entropy"):
+                    raise NotImplementedError(f"task tower {cfg.tower_name}: loss {lc.WhichOneof('loss')} is outside "
+                                              "the hot-path scope (BCE-with-logits only)")
             mlp = config_to_kwargs(cfg.mlp) if cfg.HasField("mlp") else None
             self._task_tower.append(TaskTower(self.mmoe.output_dim(), cfg.num_class, mlp=mlp))
 
