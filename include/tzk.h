@@ -329,6 +329,12 @@ int tzk_peer_bucketize(const int64_t* ids, const int64_t* offsets, int32_t F, in
 int tzk_peer_publish_grad(const float* grad, int64_t ld_grad, const int32_t* feat_col, const int32_t* feat_dim,
                           const int32_t* feat_pool, const int64_t* offsets, int32_t F, int32_t B, float* dst,
                           int64_t ld_dst, tzk_stream_t stream);
+/* peer_push_grad: wire slot (dest r, j) of this rank -> row me * cap + j of rank r's receive buffer [W * cap, D]
+ * (coalesced NVLink writes; MEAN bags divided by their length); the owner then sorts with idx_span = 0 ("slot mode":
+ * the sorted value is the receive-buffer row) and runs the plain sequence-layout tzk_fused_bwd_apply on that buffer. */
+int tzk_peer_push_grad(const uint64_t* recv_ptrs, const float* grad, int64_t ld_grad, const int32_t* feat_col,
+                       const int32_t* feat_pool, const int64_t* offsets, const int32_t* wire_idx, const int32_t* counts,
+                       int32_t me, int32_t W, int64_t cap, int32_t B, int32_t D, int32_t pooled, tzk_stream_t stream);
 int tzk_peer_allreduce_mean(const uint64_t* src_ptrs, int32_t W, int64_t n, float* out, tzk_stream_t stream);
 int tzk_fused_bwd_sort_peer(const uint64_t* key_ptrs, const uint64_t* idx_ptrs, const uint64_t* count_ptrs, int32_t me,
                             int32_t W, int64_t cap, int32_t idx_span, int64_t total_keys, int32_t max_dim,

@@ -25,7 +25,8 @@ def main():
     L.bench_rand_read64.argtypes = [P, P, I64, P, I32, I32, P]
     L.bench_rand_write64.argtypes = [P, P, I64, P, I32, P]
     L.bench_seq_copy.argtypes = [P, I64, P, I32, P]
-    rows = 16 * 1024 * 1024                    # 1 GiB of 64-B rows per rank
+    L.bench_rand_read64_mixed.argtypes = [P, P, P, I64, P, I32, P]
+    rows = int(os.environ.get("ROWS_M", "16")) * 1024 * 1024       # 64-B rows per rank (16 M = 1 GiB)
     tab = _Symm(rows * 16, torch.float32, dev, dist.group.WORLD)
     tab.t.normal_()
     torch.cuda.synchronize()
@@ -50,8 +51,16 @@ def main():
             return best
 
         gb = n * 64 / 1e9
-        for U in (1, 4, 8, 16):
-            for grid in (148, 148 * 4, 148 * 8, 148 * 16):
+        print(f"region: {rows * 64 / 2 ** 30:.1f} GiB per rank", flush=True)
+        n2 = 2 * n                              # a whole N = 2 gather: half of the rows local, half on the peer
+        idx2 = torch.randint(0, rows, (n2,), device=dev, dtype=torch.int32)
+        loc2 = torch.empty(n2 * 16, device=dev)
+        for grid in (148 * 4, 148 * 8):
+            ms = timed(lambda: L.bench_rand_read64_mixed(mine, peer, idx2.data_ptr(), n2, loc2.data_ptr(), grid, st))
+            print(f"rand_read64  MIXED local/peer in every warp, {n2} rows grid={grid:<5} {ms * 1e3:8.1f} us  "
+                  f"(peer half: {gb / ms * 1e3:7.1f} GB/s)", flush=True)
+        for U in (1, 8):
+            for grid in (148, 148 * 8):
                 ms = timed(lambda: L.bench_rand_read64(peer, idx.data_ptr(), n, loc.data_ptr(), U, grid, st))
                 print(f"rand_read64  peer  U={U:<2} grid={grid:<5} {ms * 1e3:8.1f} us  {gb / ms * 1e3:7.1f} GB/s", flush=True)
         ms = timed(lambda: L.bench_rand_read64(mine, idx.data_ptr(), n, loc.data_ptr(), 8, 148 * 8, st))

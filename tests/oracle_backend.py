@@ -291,12 +291,42 @@ class OracleKernels:
             c = counts.everyone[r]
             n = int(c[me])
             keys.append(wire_key.everyone[r].numpy()[me * cap:me * cap + n].copy())
-            vals.append(r * idx_span + wire_idx.everyone[r].numpy()[me * cap:me * cap + n].astype(np.int64))
+            vals.append(r * idx_span + wire_idx.everyone[r].numpy()[me * cap:me * cap + n].astype(np.int64)
+                        if idx_span else r * cap + np.arange(n, dtype=np.int64))      # slot mode: receive-buffer row
             if overflow is not None and int(c[W]):
                 overflow |= 1
         if not hasattr(self, "_peer_sorted"):
             self._peer_sorted = {}
         self._peer_sorted[ws.data_ptr()] = (np.concatenate(keys), np.concatenate(vals))   # slot order (src-major)
+
+    def peer_push_grad(self, recv, grad, lay, offsets, wire_idx, counts, me, W, cap, B, pooled):
+        g, off = _np(grad), _np(offsets)
+        D = lay.dim[0]
+        for r in range(W):
+            dst = recv.everyone[r].numpy()
+            for j in range(int(counts[r])):
+                idx = int(wire_idx[r * cap + j])
+                if pooled:
+                    f, b = divmod(idx, B)
+                    row = g[b, lay.col[f]:lay.col[f] + D]
+                    if lay.pool[f] == 1:
+                        row = row * np.float32(1.0 / (off[idx + 1] - off[idx]))
+                else:
+                    row = g[idx, :D]
+                s = (me * cap + j) * D
+                dst[s:s + D] = row
+
+    def fused_bwd_apply(self, optimizer, pooled, grad_out, weights, state, lay, offsets, nnz, B, lr, eps, grad_scale, ws,
+                        **ex):
+        """Only the slot-mode use of the peer path (after fused_bwd_sort_peer with idx_span = 0) is modelled."""
+        assert not pooled and ws.data_ptr() in getattr(self, "_peer_sorted", {})
+
+        class _Local:       # every "rank"'s gradient is the local receive buffer
+            def __init__(self, t):
+                self.everyone = {0: t}
+
+        self.fused_bwd_apply_peer(optimizer, False, _Local(grad_out.reshape(-1)), grad_out.shape[1], weights, state, lay,
+                                  B, 0, 1, nnz, nnz + 1, lr, eps, grad_scale, ws, **ex)
 
     def fused_bwd_apply_peer(self, optimizer, pooled, grads, ld_grad, weights, state, lay, B, me, W, cap, idx_span, lr,
                              eps, grad_scale, ws, **ex):

@@ -63,6 +63,7 @@ def host_compiled_peer_lib(tmp_path_factory):
     L.tzk_peer_bucketize.argtypes = [P, P, I32, I32, I32, P, P, P, P, I32, I64, P, P, P, P, ctypes.c_size_t, P]
     L.tzk_peer_publish_grad.argtypes = [P, I64, P, P, P, P, I32, I32, P, I64, P]
     L.tzk_peer_allreduce_mean.argtypes = [P, I32, I64, P, P]
+    L.tzk_peer_push_grad.argtypes = [P, P, I64, P, P, P, P, P, I32, I32, I64, I32, I32, I32, P]
     return L
 
 
@@ -120,6 +121,14 @@ class SourceKernels(OracleKernels):
 
     def peer_allreduce_mean(self, srcs, W, n, out):
         rc = self.L.tzk_peer_allreduce_mean(srcs.ptrs, W, n, out.data_ptr(), None)
+        assert rc == 0, rc
+
+    def peer_push_grad(self, recv, grad, lay, offsets, wire_idx, counts, me, W, cap, B, pooled):
+        _, col, pool = self._lay(lay)
+        grad = grad.contiguous()
+        rc = self.L.tzk_peer_push_grad(recv.ptrs, grad.data_ptr(), grad.shape[1], col.data_ptr(), pool.data_ptr(),
+                                       offsets.data_ptr(), wire_idx.data_ptr(), counts.data_ptr(), me, W, cap, B,
+                                       lay.dim[0], int(pooled), None)
         assert rc == 0, rc
 
 

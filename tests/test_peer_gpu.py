@@ -55,8 +55,11 @@ def _gathered(groups, plan, cfgs, full, t):
 
 
 @pytest.mark.parametrize("W,multi_hot,B", [(2, False, 64), (4, False, 1000), (8, False, 4099), (3, True, 257)])
-@pytest.mark.parametrize("opt", ["adagrad", "adam"])
-def test_peer_pooled_step_on_one_gpu(kernels, W, multi_hot, B, opt):
+@pytest.mark.parametrize("opt,bwd", [("adagrad", "push"), ("adam", "push"), ("adagrad", "pull")])
+def test_peer_pooled_step_on_one_gpu(kernels, monkeypatch, W, multi_hot, B, opt, bwd):
+    """bwd: gradient transport — "push" (sources write their slices into the owners' receive buffers, wire order) or
+    "pull" (the owners' update kernels read the slices from the sources' published gradients)."""
+    monkeypatch.setenv("TZK_PEER_BWD", bwd)
     M = _helpers()
     from torcheasyrec_b200 import peer_exchange
     from torcheasyrec_b200.distributed import TABLE_WISE, make_plan

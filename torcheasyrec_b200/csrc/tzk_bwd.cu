@@ -157,13 +157,15 @@ peer_pull_linearize_kernel(const __grid_constant__ PeerWire pw, KeyT sentinel, K
   const int64_t n = (int64_t)pw.W * pw.cap;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
-    const int r = (int)(s / pw.cap);
+    const int r = (int)((uint32_t)s / (uint32_t)pw.cap);          // W * cap < 2^31
     const int64_t j = s - (int64_t)r * pw.cap;
     KeyT k = sentinel;
     int32_t v = 0;
     if (j < cnt[r]) {
       k = (KeyT) reinterpret_cast<const int64_t*>(pw.key[r])[(int64_t)pw.me * pw.cap + j];
-      v = r * pw.idx_span + reinterpret_cast<const int32_t*>(pw.idx[r])[(int64_t)pw.me * pw.cap + j];
+      // idx_span == 0 ("slot mode"): the gradient row of this entry was pushed to row s of the local receive buffer
+      v = pw.idx_span > 0 ? r * pw.idx_span + reinterpret_cast<const int32_t*>(pw.idx[r])[(int64_t)pw.me * pw.cap + j]
+                          : (int32_t)s;
     }
     keys[s] = k;
     vals[s] = v;
@@ -1288,7 +1290,7 @@ extern "C" int tzk_fused_bwd_apply_ex(const tzk_opt_args* opt, int32_t pooled, c
 
 static int fill_wire(PeerWire* pw, const uint64_t* key_ptrs, const uint64_t* idx_ptrs, const uint64_t* count_ptrs,
                      int32_t me, int32_t W, int64_t cap, int32_t idx_span) {
-  if (W < 1 || W > 16 || me < 0 || me >= W || cap < 1 || idx_span < 1) return 1;
+  if (W < 1 || W > 16 || me < 0 || me >= W || cap < 1 || idx_span < 0) return 1;
   if ((int64_t)W * idx_span >= ((int64_t)1 << 31) || (int64_t)W * cap >= ((int64_t)1 << 31)) return 1;
   for (int r = 0; r < 16; ++r) {
     pw->key[r] = (r < W && key_ptrs) ? key_ptrs[r] : 0ull;
@@ -1309,7 +1311,8 @@ extern "C" int tzk_fused_bwd_sort_peer(const uint64_t* key_ptrs, const uint64_t*
                                        int32_t max_dim, int32_t* overflow, void* workspace, size_t workspace_bytes,
                                        tzk_stream_t stream) {
   PeerWire pw;
-  TZK_REQUIRE(key_ptrs && idx_ptrs && count_ptrs && fill_wire(&pw, key_ptrs, idx_ptrs, count_ptrs, me, W, cap, idx_span) == 0,
+  TZK_REQUIRE(key_ptrs && (idx_ptrs || idx_span == 0) && count_ptrs &&
+                  fill_wire(&pw, key_ptrs, idx_ptrs, count_ptrs, me, W, cap, idx_span) == 0,
               "fused_bwd_sort_peer: bad wire description");
   return fused_bwd_impl(1, classic_opt(TZK_OPT_SGD, nullptr, 0.f, 0.f), 0, nullptr, 0, nullptr, nullptr, nullptr,
                         nullptr, nullptr, nullptr, nullptr, nullptr, 1, 1, (int64_t)W * cap, total_keys, max_dim, 0,

@@ -63,9 +63,17 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
 #endif
 }
 
-// owner rank and owner-local row of a (clamped) id — tzk_dist.cu's dest_of
+// owner rank and owner-local row of a (clamped, non-negative) id — tzk_dist.cu's dest_of.  The quotient is below W <= 16:
+// a float estimate plus one exact fix-up replaces the 64-bit integer division (~100 instructions on the SM, per row,
+// which made the requester-side gather instruction-bound).
 __device__ __forceinline__ int owner_of(int64_t id, int64_t block, int owner, int W, int64_t* local) {
+#ifdef TZK_CPU_SHIM
   int64_t q = id / block;
+#else
+  int64_t q = (int64_t)__fdividef((float)id, (float)block);
+  if (q * block > id) --q;
+  else if ((q + 1) * block <= id) ++q;
+#endif
   int64_t r = owner + q;
   if (r >= W) { q -= r - (W - 1); r = W - 1; }
   *local = id - q * block;
@@ -258,7 +266,7 @@ peer_bkt_count_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict
   for (int k = 0; k < kBktPerThread; ++k) {
     const int64_t bag = bag0 + k;
     if (bag >= n_bags) break;
-    const BktFeat d = fd[bag / B];
+    const BktFeat d = fd[(uint32_t)bag / (uint32_t)B];
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     for (int64_t l = s; l < e; ++l) {
       int64_t id = __ldg(ids + l), loc;
@@ -326,7 +334,7 @@ peer_bkt_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restri
   for (int k = 0; k < kBktPerThread; ++k) {
     const int64_t bag = bag0 + k;
     if (bag >= n_bags) break;
-    const BktFeat d = fd[bag / B];
+    const BktFeat d = fd[(uint32_t)bag / (uint32_t)B];
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     for (int64_t l = s; l < e; ++l) {
       int64_t id = __ldg(ids + l), loc;
@@ -365,7 +373,7 @@ peer_bkt_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restri
   for (int k = 0; k < kBktPerThread; ++k) {
     const int64_t bag = bag0 + k;
     if (bag >= n_bags) break;
-    const int f = (int)(bag / B);
+    const int f = (int)((uint32_t)bag / (uint32_t)B);
     const BktFeat d = fd[f];
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     for (int64_t l = s; l < e; ++l) {
@@ -400,6 +408,46 @@ peer_publish_grad_kernel(const float* __restrict__ grad, int64_t ld_grad, const 
     const float* s = grad + (int64_t)b * ld_grad + col;
     float* d = dst + (int64_t)b * ld_dst + col;
     for (int c = 0; c < dim; ++c) d[c] = s[c] * sc;
+  }
+}
+
+// ---- push the gradient to the owners, in wire order -----------------------------------------------------------------
+// Wire slot (dest r, j) of this rank -> row (me * cap + j) of rank r's receive buffer: consecutive slots are consecutive
+// 64-B rows at the destination, so the NVLink writes are long coalesced bursts (posted, no round trip) while the
+// scattered 64-B reads stay in local HBM.  The slice comes straight from the pooled-output gradient (no staging copy);
+// MEAN bags are divided by their length here, so the owner's update needs nothing but the row.
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+peer_push_grad_kernel(const __grid_constant__ Peers recv, const float* __restrict__ grad, int64_t ld_grad,
+                      const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                      const int64_t* __restrict__ offsets, const int32_t* __restrict__ wire_idx,
+                      const int32_t* __restrict__ counts, int me, int W, int64_t cap, int B, int D, int pooled) {
+  constexpr int NG = kThreads / G;
+  const int lane = threadIdx.x % G;
+  const int64_t n = (int64_t)W * cap;
+  for (int64_t s = (int64_t)blockIdx.x * NG + threadIdx.x / G; s < n; s += (int64_t)gridDim.x * NG) {
+    const int r = (int)((uint32_t)s / (uint32_t)cap);          // W * cap < 2^31
+    const int64_t j = s - (int64_t)r * cap;
+    if (j >= __ldg(counts + r)) continue;
+    const int32_t idx = __ldg(wire_idx + s);
+    const float* src;
+    float sc = 1.f;
+    if (pooled) {
+      const int f = idx / B, b = idx - f * B;
+      src = grad + (int64_t)b * ld_grad + __ldg(feat_col + f);
+      if (__ldg(feat_pool + f) == 1) {
+        const int64_t L = __ldg(offsets + idx + 1) - __ldg(offsets + idx);
+        sc = 1.0f / (float)L;                       // L >= 1: the slot exists
+      }
+    } else {
+      src = grad + (int64_t)idx * ld_grad;
+    }
+    float* dst = reinterpret_cast<float*>(recv.p[r]) + ((int64_t)me * cap + j) * D;
+    for (int c = lane * 4; c < D; c += G * 4) {
+      float4 v = *reinterpret_cast<const float4*>(src + c);
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      *reinterpret_cast<float4*>(dst + c) = v;
+    }
   }
 }
 
@@ -542,6 +590,28 @@ extern "C" int tzk_peer_publish_grad(const float* grad, int64_t ld_grad, const i
   TZK_LAUNCH((peer_publish_grad_kernel), grid_for((n + kThreads - 1) / kThreads), kThreads, 0,
              reinterpret_cast<cudaStream_t>(stream), grad, ld_grad, feat_col, feat_dim, feat_pool, offsets, F, B, dst,
              ld_dst);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+// grad: this rank's pooled-output gradient [B, ld_grad] (pooled) or row gradient [nnz, ld_grad] (sequence);
+// recv_ptrs[r]: rank r's receive buffer [W * cap, D]; wire_idx / counts: this rank's own wire buffers (tzk_peer_bucketize).
+extern "C" int tzk_peer_push_grad(const uint64_t* recv_ptrs, const float* grad, int64_t ld_grad, const int32_t* feat_col,
+                                  const int32_t* feat_pool, const int64_t* offsets, const int32_t* wire_idx,
+                                  const int32_t* counts, int32_t me, int32_t W, int64_t cap, int32_t B, int32_t D,
+                                  int32_t pooled, void* stream) {
+  Peers p;
+  if (fill(&p, recv_ptrs, W) || me < 0 || me >= W || cap <= 0 || B <= 0 || D <= 0 || (D % 4) || (ld_grad % 4)) return 1;
+  if (!grad || !wire_idx || !counts || (pooled && (!feat_col || !feat_pool || !offsets))) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t slots = (int64_t)W * cap;
+#define TZK_PEER_LAUNCH(G)                                                                                           \
+  TZK_LAUNCH((peer_push_grad_kernel<G>), grid_for((slots + kThreads / G - 1) / (kThreads / G)), kThreads, 0, st, p,  \
+             grad, ld_grad, feat_col, feat_pool, offsets, wire_idx, counts, me, W, cap, B, D, pooled)
+  if (D <= 16) TZK_PEER_LAUNCH(4);
+  else if (D <= 32) TZK_PEER_LAUNCH(8);
+  else if (D <= 64) TZK_PEER_LAUNCH(16);
+  else TZK_PEER_LAUNCH(32);
+#undef TZK_PEER_LAUNCH
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

@@ -484,6 +484,17 @@ class CudaKernels:
               "tzk_peer_publish_grad")
         self.launches += 1
 
+    def peer_push_grad(self, recv, grad: torch.Tensor, lay: FeatureLayout, offsets: torch.Tensor, wire_idx: torch.Tensor,
+                       counts: torch.Tensor, me: int, W: int, cap: int, B: int, pooled: bool) -> None:
+        """This rank's gradient slices -> the owners' receive buffers, wire order (see tzk_peer_push_grad)."""
+        grad, ld = _rows2d(grad, "grad")
+        _need(wire_idx, torch.int32, "wire_idx")
+        _need(counts, torch.int32, "counts")
+        check(self._lib.tzk_peer_push_grad(recv.ptrs, _ptr(grad), ld, _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(offsets),
+                                           _ptr(wire_idx), _ptr(counts), me, W, cap, B, lay.dim[0], int(pooled),
+                                           _stream()), "tzk_peer_push_grad")
+        self.launches += 1
+
     def peer_allreduce_mean(self, srcs, W: int, n: int, out: torch.Tensor) -> None:
         _need(out, torch.float32, "out")
         check(self._lib.tzk_peer_allreduce_mean(srcs.ptrs, W, n, _ptr(out), _stream()), "tzk_peer_allreduce_mean")
@@ -493,7 +504,9 @@ class CudaKernels:
                             lay: FeatureLayout, overflow: Optional[torch.Tensor], ws: torch.Tensor) -> None:
         if ws.numel() < self.fused_bwd_workspace_bytes(lay, W * cap):
             raise TzkError("fused_bwd_sort_peer: workspace too small")
-        check(self._lib.tzk_fused_bwd_sort_peer(wire_key.ptrs, wire_idx.ptrs, counts.ptrs, me, W, cap, idx_span,
+        # idx_span == 0: "slot mode" (the gradient rows are pushed to this rank's receive buffer: value = its row)
+        check(self._lib.tzk_fused_bwd_sort_peer(wire_key.ptrs, wire_idx.ptrs if idx_span else None, counts.ptrs, me, W,
+                                                cap, idx_span,
                                                 lay.total_keys, lay.max_dim, _ptr(overflow), _ptr(ws), ws.numel(),
                                                 _stream()), "tzk_fused_bwd_sort_peer")
         self.launches += 1

@@ -183,7 +183,15 @@ class PeerState(PeerBase):
         self.wire_key = self._alloc(W * self.cap, torch.int64)
         self.wire_idx = self._alloc(W * self.cap, torch.int32)
         self.counts = self._alloc(W + 1, torch.int32)
-        self.grad = self._alloc(self.B * g.total_dim if self.pooled else self.max_nnz * g.dim, torch.float32)
+        # backward transport: "push" (default) = every source writes its gradient slices into the owners' receive
+        # buffers in wire order (coalesced NVLink writes, the update then runs on local memory); "pull" = the sources
+        # publish their gradient and the owners' update kernels read the 64-B slices over NVLink in place
+        self.bwd_mode = os.environ.get("TZK_PEER_BWD", "push")
+        if self.bwd_mode == "push":
+            self.recv = self._alloc(W * self.cap * g.dim, torch.float32)
+            self._dummy_off = torch.zeros(2, dtype=torch.int64, device=dev)
+        else:
+            self.grad = self._alloc(self.B * g.total_dim if self.pooled else self.max_nnz * g.dim, torch.float32)
         self.site_a, self.site_b, self.site_c = _Site(self), _Site(self), _Site(self)
         self._ws = None
         self._prep_pending = False
@@ -217,8 +225,9 @@ class PeerState(PeerBase):
             k.peer_bucketize(ids, offsets, g.F, self.B, self.W, g.feat_block, g.feat_owner, self.feat_rows,
                              self.rf_key_base, self.pooled, self.cap, self.wire_key.t, self.wire_idx.t, self.counts.t)
             self._barrier(self.site_a)
-            k.fused_bwd_sort_peer(self.wire_key, self.wire_idx, self.counts, self.me, self.W, self.cap, self.idx_span,
-                                  g.local.layout, g.overflow, self._workspace())
+            k.fused_bwd_sort_peer(self.wire_key, self.wire_idx, self.counts, self.me, self.W, self.cap,
+                                  0 if self.bwd_mode == "push" else self.idx_span, g.local.layout, g.overflow,
+                                  self._workspace())
             self._prep_pending = True
 
         self._keep = (ids, offsets)           # the side stream reads them: keep them away from the allocator
@@ -233,20 +242,31 @@ class PeerState(PeerBase):
         if not self._prep_pending:
             raise RuntimeError("peer exchange: backward without the forward pass's id exchange")
         lay = g.local.layout
-        if self.pooled:
+        push = self.bwd_mode == "push"
+        if push:
+            if not self.pooled:
+                grad = grad.reshape(-1, g.dim)
+            k.peer_push_grad(self.recv, grad, lay, offsets, self.wire_idx.t, self.counts.t, self.me, self.W, self.cap,
+                             self.B, self.pooled)
+        elif self.pooled:
             ld = g.total_dim
             k.peer_publish_grad(grad, lay, offsets, self.B, self.grad.t.view(self.B, ld))
         else:
             ld = g.dim
             self.grad.t[:grad.numel()].copy_(grad.reshape(-1))
-        self._barrier(self.site_b)            # every rank's gradient is published (and, long ago, its wire buffers)
+        self._barrier(self.site_b)            # every rank's gradient has arrived / is published
         extras = g.local.opt_extras()
 
         def run():
-            k.fused_bwd_apply_peer(spec.kind, self.pooled, self.grad, ld, g.local.weights.data, g.local.opt_state, lay,
-                                   self.B, self.me, self.W, self.cap, self.idx_span, spec.lr, spec.eps, 1.0 / self.W,
-                                   self._workspace(), **extras)
-            self._barrier(self.site_c)        # tables quiescent everywhere, wire buffers / gradient reusable
+            if push:    # the plain sequence-layout update over the local receive buffer (sorted value = its row)
+                k.fused_bwd_apply(spec.kind, False, self.recv.t.view(self.W * self.cap, g.dim), g.local.weights.data,
+                                  g.local.opt_state, lay, self._dummy_off, self.W * self.cap, 1, spec.lr, spec.eps,
+                                  1.0 / self.W, self._workspace(), **extras)
+            else:
+                k.fused_bwd_apply_peer(spec.kind, self.pooled, self.grad, ld, g.local.weights.data, g.local.opt_state,
+                                       lay, self.B, self.me, self.W, self.cap, self.idx_span, spec.lr, spec.eps,
+                                       1.0 / self.W, self._workspace(), **extras)
+            self._barrier(self.site_c)        # tables quiescent everywhere, wire / receive buffers reusable
             self._prep_pending = False
 
         self._on_side(run)
