@@ -315,10 +315,17 @@ int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_o
                                const int64_t* feat_block, const int32_t* feat_owner, const int32_t* feat_dim,
                                const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
                                const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim, float* out,
-                               int64_t ld_out, tzk_stream_t stream);
+                               int64_t ld_out, const float* mirror, const int64_t* feat_mirror_off, tzk_stream_t stream);
 int tzk_peer_seq_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
                             const int64_t* feat_block, const int32_t* feat_owner, const int64_t* ids,
                             const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t D, int64_t nnz, float* out,
+                            const float* mirror, const int64_t* feat_mirror_off, tzk_stream_t stream);
+/* mirror / feat_mirror_off (both may be NULL): features with feat_mirror_off[f] >= 0 read row id at
+ * mirror[feat_mirror_off[f] + id * D_f] — this rank's per-step copy of the WHOLE (small) table, refreshed by
+ * peer_mirror_refresh from n_seg contiguous pieces (rank seg_rank[s], arena offset seg_src[s], mirror offset seg_dst[s],
+ * seg_n[s] floats; device arrays). */
+int tzk_peer_mirror_refresh(const uint64_t* table_ptrs, int32_t W, const int32_t* seg_rank, const int64_t* seg_src,
+                            const int64_t* seg_dst, const int64_t* seg_n, int32_t n_seg, float* mirror,
                             tzk_stream_t stream);
 int tzk_peer_barrier(const uint64_t* pad_ptrs, int32_t me, int32_t W, uint32_t* epoch, tzk_stream_t stream);
 size_t tzk_peer_bucketize_workspace_bytes(int32_t F, int32_t B, int32_t W);

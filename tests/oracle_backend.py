@@ -204,8 +204,15 @@ class OracleKernels:
             r = W - 1
         return r, i - q * block
 
+    def peer_mirror_refresh(self, tables, W, seg_rank, seg_src, seg_dst, seg_n, mirror):
+        m = mirror.numpy()
+        for r, s, d, n in zip(seg_rank.tolist(), seg_src.tolist(), seg_dst.tolist(), seg_n.tolist()):
+            m[d:d + n] = tables.everyone[r].numpy()[s:s + n]
+
     def peer_pooled_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W,
-                               out=None):
+                               out=None, mirror=None, feat_mirror_off=None):
+        if mirror is not None:       # the model keeps reading the owners (the mirror is checked to be an exact copy)
+            self._check_mirror(tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, W, mirror, feat_mirror_off)
         F = lay.num_features
         blocks, owners = feat_block.tolist(), feat_owner.tolist()
         rows, w_off = feat_rows.tolist(), rf_w_off.tolist()
@@ -230,7 +237,26 @@ class OracleKernels:
             return out
         return res
 
-    def peer_seq_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W):
+    def _check_mirror(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, W, mirror, feat_mirror_off):
+        F = lay.num_features
+        m, mo = mirror.numpy(), feat_mirror_off.tolist()
+        blocks, owners, rows, w_off = feat_block.tolist(), feat_owner.tolist(), feat_rows.tolist(), rf_w_off.tolist()
+        for f in range(F):
+            if mo[f] < 0:
+                continue
+            D, i = lay.dim[f], 0
+            while i < rows[f]:            # one contiguous piece per owning rank
+                r, loc = self._owner_of(i, blocks[f], owners[f], W)
+                n = min(rows[f] - i, blocks[f] - loc) if r < W - 1 else rows[f] - i
+                base = w_off[r * F + f] + loc * D
+                assert np.array_equal(m[mo[f] + i * D:mo[f] + (i + n) * D],
+                                      tables.everyone[r].numpy()[base:base + n * D]), (f, i)
+                i += n
+
+    def peer_seq_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W,
+                            mirror=None, feat_mirror_off=None):
+        if mirror is not None:
+            self._check_mirror(tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, W, mirror, feat_mirror_off)
         F, D = lay.num_features, lay.dim[0]
         blocks, owners = feat_block.tolist(), feat_owner.tolist()
         rows, w_off = feat_rows.tolist(), rf_w_off.tolist()

@@ -24,6 +24,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+os.environ.setdefault("TZK_PEER_MIRROR_ROWS", "200")   # these tiny collections: some tables mirrored, some read remotely
 
 from oracle_backend import OracleKernels  # noqa: E402
 
@@ -56,8 +57,9 @@ def host_compiled_peer_lib(tmp_path_factory):
                     "c++", os.path.join(os.path.dirname(HERE), "torcheasyrec_b200", "csrc", "tzk_peer.cu"), "-shared",
                     "-fPIC", "-o", out], check=True)
     L = ctypes.CDLL(out)
-    L.tzk_peer_pooled_gather_fwd.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P, I64, P]
-    L.tzk_peer_seq_gather_fwd.argtypes = [P, P, P, P, P, P, P, I32, I32, I32, I32, I64, P, P]
+    L.tzk_peer_pooled_gather_fwd.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P, I64, P, P, P]
+    L.tzk_peer_seq_gather_fwd.argtypes = [P, P, P, P, P, P, P, I32, I32, I32, I32, I64, P, P, P, P]
+    L.tzk_peer_mirror_refresh.argtypes = [P, I32, P, P, P, P, I32, P, P]
     L.tzk_peer_bucketize_workspace_bytes.restype = ctypes.c_size_t
     L.tzk_peer_bucketize_workspace_bytes.argtypes = [I32, I32, I32]
     L.tzk_peer_bucketize.argtypes = [P, P, I32, I32, I32, P, P, P, P, I32, I64, P, P, P, P, ctypes.c_size_t, P]
@@ -81,24 +83,32 @@ class SourceKernels(OracleKernels):
         i32 = lambda xs: torch.tensor(list(xs), dtype=torch.int32)
         return i32(lay.dim), i32(lay.col), i32(lay.pool)
 
+    def peer_mirror_refresh(self, tables, W, seg_rank, seg_src, seg_dst, seg_n, mirror):
+        rc = self.L.tzk_peer_mirror_refresh(tables.ptrs, W, seg_rank.data_ptr(), seg_src.data_ptr(), seg_dst.data_ptr(),
+                                            seg_n.data_ptr(), seg_rank.numel(), mirror.data_ptr(), None)
+        assert rc == 0, rc
+
     def peer_pooled_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W,
-                               out=None):
+                               out=None, mirror=None, feat_mirror_off=None):
         dim, col, pool = self._lay(lay)
         out = torch.full((B, lay.total_dim), float("nan")) if out is None else out
         rc = self.L.tzk_peer_pooled_gather_fwd(tables.ptrs, rf_w_off.data_ptr(), feat_rows.data_ptr(),
                                                feat_block.data_ptr(), feat_owner.data_ptr(), dim.data_ptr(),
                                                col.data_ptr(), pool.data_ptr(), ids.data_ptr(), offsets.data_ptr(),
                                                lay.num_features, B, W, (lay.max_dim + 3) // 4 * 4, out.data_ptr(),
-                                               lay.total_dim, None)
+                                               lay.total_dim, None if mirror is None else mirror.data_ptr(),
+                                               None if feat_mirror_off is None else feat_mirror_off.data_ptr(), None)
         assert rc == 0, rc
         return out
 
-    def peer_seq_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W):
+    def peer_seq_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W,
+                            mirror=None, feat_mirror_off=None):
         D, nnz = lay.dim[0], ids.numel()
         out = torch.full((nnz, D), float("nan"))
         rc = self.L.tzk_peer_seq_gather_fwd(tables.ptrs, rf_w_off.data_ptr(), feat_rows.data_ptr(), feat_block.data_ptr(),
                                             feat_owner.data_ptr(), ids.data_ptr(), offsets.data_ptr(), lay.num_features,
-                                            B, W, D, nnz, out.data_ptr(), None)
+                                            B, W, D, nnz, out.data_ptr(), None if mirror is None else mirror.data_ptr(),
+                                            None if feat_mirror_off is None else feat_mirror_off.data_ptr(), None)
         assert rc == 0, rc
         return out
 

@@ -93,8 +93,10 @@ SIGNATURES = {
     "tzk_jagged_softmax_wsum_fwd": (c_int32, [P, P, P, c_int32, c_int32, c_int32, c_int64, P, P, P]),
     "tzk_jagged_softmax_wsum_bwd": (c_int32, [P, P, P, P, c_int32, c_int32, c_int32, c_int64, P, P, P]),
     "tzk_peer_pooled_gather_fwd": (
-        c_int32, [P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P]),
-    "tzk_peer_seq_gather_fwd": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int64, P, P]),
+        c_int32, [P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P, P, P]),
+    "tzk_peer_seq_gather_fwd": (
+        c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int64, P, P, P, P]),
+    "tzk_peer_mirror_refresh": (c_int32, [P, c_int32, P, P, P, P, c_int32, P, P]),
     "tzk_peer_barrier": (c_int32, [P, c_int32, c_int32, P, P]),
     "tzk_peer_bucketize_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "tzk_peer_bucketize": (

@@ -418,7 +418,8 @@ class CudaKernels:
     # mapped in this process) — peer_exchange._Symm.
     def peer_pooled_gather_fwd(self, tables, rf_w_off: torch.Tensor, feat_rows: torch.Tensor, feat_block: torch.Tensor,
                                feat_owner: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
-                               B: int, W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                               B: int, W: int, out: Optional[torch.Tensor] = None, mirror: Optional[torch.Tensor] = None,
+                               feat_mirror_off: Optional[torch.Tensor] = None) -> torch.Tensor:
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         F = lay.num_features
@@ -432,22 +433,32 @@ class CudaKernels:
         check(self._lib.tzk_peer_pooled_gather_fwd(
             tables.ptrs, _ptr(rf_w_off), _ptr(feat_rows), _ptr(feat_block), _ptr(feat_owner), _ptr(lay.d_dim),
             _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, W, (lay.max_dim + 3) // 4 * 4, _ptr(out),
-            ld, _stream()), "tzk_peer_pooled_gather_fwd")
+            ld, _ptr(mirror), _ptr(feat_mirror_off), _stream()), "tzk_peer_pooled_gather_fwd")
         self.launches += 1
         return out
 
     def peer_seq_gather_fwd(self, tables, rf_w_off: torch.Tensor, feat_rows: torch.Tensor, feat_block: torch.Tensor,
                             feat_owner: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
-                            B: int, W: int) -> torch.Tensor:
+                            B: int, W: int, mirror: Optional[torch.Tensor] = None,
+                            feat_mirror_off: Optional[torch.Tensor] = None) -> torch.Tensor:
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         F, D, nnz = lay.num_features, lay.dim[0], ids.numel()
         out = torch.empty((nnz, D), dtype=torch.float32, device=ids.device)
         check(self._lib.tzk_peer_seq_gather_fwd(tables.ptrs, _ptr(rf_w_off), _ptr(feat_rows), _ptr(feat_block),
                                                 _ptr(feat_owner), _ptr(ids), _ptr(offsets), F, B, W, D, nnz, _ptr(out),
-                                                _stream()), "tzk_peer_seq_gather_fwd")
+                                                _ptr(mirror), _ptr(feat_mirror_off), _stream()),
+              "tzk_peer_seq_gather_fwd")
         self.launches += 1 if nnz else 0
         return out
+
+    def peer_mirror_refresh(self, tables, W: int, seg_rank: torch.Tensor, seg_src: torch.Tensor, seg_dst: torch.Tensor,
+                            seg_n: torch.Tensor, mirror: torch.Tensor) -> None:
+        """This step's local copy of the small tables (see tzk_peer_mirror_refresh)."""
+        _need(mirror, torch.float32, "mirror")
+        check(self._lib.tzk_peer_mirror_refresh(tables.ptrs, W, _ptr(seg_rank), _ptr(seg_src), _ptr(seg_dst), _ptr(seg_n),
+                                                seg_rank.numel(), _ptr(mirror), _stream()), "tzk_peer_mirror_refresh")
+        self.launches += 1
 
     def peer_barrier(self, pads, me: int, W: int, epoch: torch.Tensor) -> None:
         check(self._lib.tzk_peer_barrier(pads.ptrs, me, W, _ptr(epoch), _stream()), "tzk_peer_barrier")

@@ -172,6 +172,7 @@ class PeerState(PeerBase):
         n = g.local.weights.numel()
         self.tables.t[:n].copy_(g.local.weights.data)
         g.local.weights.data = self.tables.t[:n]
+        self._init_mirror(plan, per_rank)
         # id budget per step: one id per bag unless the caller knows better (sequence features: B * sequence_length)
         per_f = list(ids_per_feature) if ids_per_feature is not None else [self.B] * F
         self.max_nnz = int(sum(per_f))
@@ -197,16 +198,60 @@ class PeerState(PeerBase):
         self._prep_pending = False
         self._host_barrier()                 # flags are zero and tables are in place everywhere before the first step
 
+    # ---- small tables: a per-step local copy ---------------------------------------------------------------------
+    def _init_mirror(self, plan, per_rank) -> None:
+        """Tables of at most TZK_PEER_MIRROR_ROWS rows (default 65536; 0 switches it off) are copied whole from their
+        owners at the start of every forward pass — a few MB of long sequential NVLink reads — and looked up locally;
+        only the big tables' rows cross NVLink as random 64-B reads.  Exact: the copy is taken after the barrier that
+        closes the previous step's updates."""
+        from .distributed import local_rows
+
+        g, dev = self.g, self.device
+        thr = int(os.environ.get("TZK_PEER_MIRROR_ROWS", "65536"))
+        self.mirror = None
+        self.feat_mirror_off = None
+        if thr <= 0 or self.W == 1:
+            return
+        m_off, o = {}, 0
+        for t, c in enumerate(g.configs):
+            if c.num_embeddings <= thr:
+                m_off[t] = o
+                o += c.num_embeddings * c.embedding_dim
+        if not m_off:
+            return
+        seg_rank, seg_src, seg_dst, seg_n = [], [], [], []
+        first_feat = {}
+        for f, t in enumerate(g.local._feat_table):
+            first_feat.setdefault(t, f)
+        for t, base in m_off.items():
+            c = g.configs[t]
+            sh = plan[c.name]
+            for r in range(self.W):
+                n = local_rows(c, sh, r)
+                if n:
+                    start = 0 if sh.kind == "table_wise" else r * sh.block
+                    seg_rank.append(r)
+                    seg_src.append(per_rank[r].w_off[first_feat[t]])
+                    seg_dst.append(base + start * c.embedding_dim)
+                    seg_n.append(n * c.embedding_dim)
+        self.mirror = torch.zeros(max(o, 4), dtype=torch.float32, device=dev)
+        self.feat_mirror_off = torch.tensor([m_off.get(t, -1) for t in g.local._feat_table], dtype=torch.int64, device=dev)
+        self._seg = (torch.tensor(seg_rank, dtype=torch.int32, device=dev), torch.tensor(seg_src, dtype=torch.int64, device=dev),
+                     torch.tensor(seg_dst, dtype=torch.int64, device=dev), torch.tensor(seg_n, dtype=torch.int64, device=dev))
+
     # ---- forward ---------------------------------------------------------------------------------------------------
     def gather(self, ids: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
         g, k = self.g, Fn.backend()
         if ids.numel() > self.max_nnz:
             raise RuntimeError(f"peer exchange is sized for {self.max_nnz} ids per step, got {ids.numel()}")
+        if self.mirror is not None:
+            k.peer_mirror_refresh(self.tables, self.W, *self._seg, self.mirror)
         if self.pooled:
             return k.peer_pooled_gather_fwd(self.tables, self.rf_w_off, self.feat_rows, g.feat_block, g.feat_owner,
-                                            g.local.layout, ids, offsets, self.B, self.W)
+                                            g.local.layout, ids, offsets, self.B, self.W, None, self.mirror,
+                                            self.feat_mirror_off)
         return k.peer_seq_gather_fwd(self.tables, self.rf_w_off, self.feat_rows, g.feat_block, g.feat_owner,
-                                     g.local.layout, ids, offsets, self.B, self.W)
+                                     g.local.layout, ids, offsets, self.B, self.W, self.mirror, self.feat_mirror_off)
 
     def _workspace(self) -> torch.Tensor:
         k = Fn.backend()
