@@ -78,7 +78,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-zipf", action="store_true", help="skip the second (Zipf-id) timing of the same step")
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the measurement-only extras (pipelined loss read, drafts under scripts/experimental)")
+                    help="skip the measurement-only extras (blocking-loss-read e2e variant)")
     ap.add_argument("--sharded-mode", default="auto", choices=["auto", "graph", "eager"],
                     help="N>1: 'graph' = fixed-capacity exchange captured in one CUDA graph, 'eager' = step by step "
                          "(auto: graph unless the model has sequence features)")

@@ -20,7 +20,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from torcheasyrec_b200.peer_exchange import _Symm
 
-    L = ctypes.CDLL(os.path.join(ROOT, "scripts", "experimental", "libtzk_peer_bench.so"))
+    L = ctypes.CDLL(os.path.join(ROOT, "scripts", "libtzk_peer_bench.so"))
     P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
     L.bench_rand_read64.argtypes = [P, P, I64, P, I32, I32, P]
     L.bench_rand_write64.argtypes = [P, P, I64, P, I32, P]

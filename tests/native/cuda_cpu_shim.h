@@ -1,8 +1,8 @@
 // cuda_cpu_shim.h — compile a plain CUDA kernel (no PTX, no warp intrinsics) with g++ and run it on the host, one
 // std::thread per CUDA thread, one block at a time, __syncthreads() as a real barrier.
 //
-// TEST INFRASTRUCTURE for the drafts in this directory only (there is no GPU in the build container): it lets
-// tests/test_experimental_kernels_cpu.py execute the kernels' actual source — index arithmetic, guards, reduction
+// TEST INFRASTRUCTURE (there is no GPU in the build container): it lets
+// tests/test_tower_bwd2_cpu.py, tests/test_peer_exchange_model.py and tests/test_gemm3x_emu.py execute the kernels' actual source — index arithmetic, guards, reduction
 // order — against numpy before their first contact with hardware.  It says nothing about performance, memory
 // ordering or anything that needs PTX, and the product (libtzk.so) never sees it.
 //

@@ -17,7 +17,7 @@ mbarrier semantics modelled: `pending` arrivals per phase (+ outstanding transac
 both reach zero, flips the parity bit and re-arms; try_wait.parity(P) succeeds iff the current parity != P (so waiting
 on parity 1 of a fresh barrier falls through — the producers' first pass over the empty barriers relies on that).
 
-    python scripts/experimental/model_gemm3x_pipeline.py        # a few thousand random schedules
+    python tests/native/model_gemm3x_pipeline.py        # a few thousand random schedules
 """
 import random
 from collections import deque

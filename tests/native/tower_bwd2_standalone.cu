@@ -1,4 +1,4 @@
-// tzk_tower_bwd2.cu — stand-alone build of torcheasyrec_b200/csrc/tzk_tower_bwd2.cuh (host shim tests, try script).
+// tower_bwd2_standalone.cu — stand-alone build of torcheasyrec_b200/csrc/tzk_tower_bwd2.cuh (host shim tests, try script).
 //
 // Round-2 groundwork: the backward of the narrow tower layers (K, N <= 64) without shared-memory
 // tiles and without barriers in the row loop.  Today's small_linear_bwd_kernel walks 128-row tiles through shared
@@ -18,9 +18,9 @@
 // Same fp32 FFMA arithmetic as the library kernels; the dW summation order differs from tzk_small_linear_bwd's (rows
 // interleaved over row groups), so the two agree to rounding, not bit for bit; both are run-to-run deterministic.
 //
-// Build + try (next round):  python scripts/experimental/try_tower_bwd2.py
+// GPU tests: tests/test_kernels_gpu.py::test_small_linear_fwd_bwd_vs_fp64_reference (both backward paths)
 #ifdef TZK_CPU_SHIM
-#include "cuda_cpu_shim.h"   // host execution for tests/test_experimental_kernels_cpu.py
+#include "cuda_cpu_shim.h"   // host execution for tests/test_tower_bwd2_cpu.py
 #else
 #include <cuda_runtime.h>
 #define TZK_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]

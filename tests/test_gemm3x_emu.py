@@ -1,4 +1,4 @@
-"""The tcgen05 3xTF32 GEMM draft (scripts/experimental/tzk_gemm3x.cu) executed on the CPU from its actual source.
+"""The tcgen05 3xTF32 GEMM (torcheasyrec_b200/csrc/tzk_gemm3x.cu) executed on the CPU from its actual source.
 
 `cuda_cpu_shim.h` runs the kernels with one std::thread per CUDA thread (192 per CTA: TMA producer, MMA issuer, four
 transform / epilogue warps) and `tcgen05_cpu_emu.h` stands in for the hardware: mbarriers with transaction counts,
@@ -7,7 +7,7 @@ shared-memory descriptors (K-major and MN-major canonical layouts, TF32 operand 
 per-warp lane-ownership rule, tcgen05.ld.  What this proves: control flow, barrier protocol, descriptor arithmetic
 (k-step advance inside the swizzle atom, LBO / SBO), tile -> (row, column) mapping, K-tail and M-tail handling and the
 epilogues are consistent with those semantics and produce fp32-accurate results.  What it cannot prove: that the
-hardware agrees with the emulation (the descriptor FIELDS are checked against CuTe in test_experimental_umma_desc.py)."""
+hardware agrees with the emulation (the descriptor FIELDS are checked against CuTe in test_umma_desc.py)."""
 import ctypes
 import os
 import subprocess
@@ -16,7 +16,7 @@ import sys
 import numpy as np
 import pytest
 
-EXP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "experimental")
+EXP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native")
 P, I64, I32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
 
 
@@ -37,8 +37,9 @@ def lib(tmp_path_factory):
     if CHILD:
         return _declare(ctypes.CDLL(os.environ["TZK_EMU_LIB"]))
     out = str(tmp_path_factory.mktemp("emu") / "libtzk_gemm3x_cpu.so")
-    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-x", "c++",
-                    os.path.join(EXP, "tzk_gemm3x.cu"), "-shared", "-fPIC", "-o", out], check=True)
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "torcheasyrec_b200", "csrc")
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-I", EXP, "-x", "c++",
+                    os.path.join(csrc, "tzk_gemm3x.cu"), "-shared", "-fPIC", "-o", out], check=True)
     return out
 
 
@@ -155,7 +156,7 @@ def test_wgrad_mn_major(request, lib, monkeypatch, M, slabs, prefetch, ring):
 
 
 def test_autograd_wiring_of_the_wide_layer(request, lib, monkeypatch):
-    """scripts/experimental/gemm3x_linear.py (the drop-in for dense_gemm._LinearFn on DLRM's 783 -> 64 layer) on CPU
+    """dense_gemm.Gemm3xLinearFn (the drop-in for dense_gemm._LinearFn on DLRM's 783 -> 64 layer) on CPU
     tensors through the emulated kernels: forward, input gradient, weight gradient (column-mapped 783 -> 784 input)
     and bias gradient against torch autograd."""
     if _delegate(request, lib):
@@ -164,10 +165,9 @@ def test_autograd_wiring_of_the_wide_layer(request, lib, monkeypatch):
 
     import torch
 
-    sys.path.insert(0, EXP)
-    import gemm3x_linear as G
+    import torcheasyrec_b200.dense_gemm as G
 
-    G.declare(lib)
+    G._declare_gemm3x(lib)
     import torcheasyrec_b200.dense_gemm as DG
     monkeypatch.setattr(DG, "SLABS", 2)
     torch.manual_seed(0)

@@ -6,7 +6,7 @@ device barrier is a threading.Barrier.  The kernels run in two flavours:
   * "model":  tests/oracle_backend.py's loop-level restatement of what each CUDA kernel does (same owner rule, same
               wire / slot arithmetic);
   * "source": csrc/tzk_peer.cu ITSELF (gathers, the three bucketize kernels, gradient publish, dense all-reduce),
-              compiled for the host with scripts/experimental/cuda_cpu_shim.h (one std::thread per CUDA thread, real
+              compiled for the host with tests/native/cuda_cpu_shim.h (one std::thread per CUDA thread, real
               __syncthreads, emulated warp shuffles) and called through the same ctypes signatures and pointer tables
               as on the GPU.  The owner-side sort / update (tzk_bwd.cu: CUB + PTX loads) stays the model there.
 Everything above the kernels — `PeerState` itself, the wire capacity, barrier sites, the call order — is the real code.
@@ -51,7 +51,7 @@ class _SimSymm:
 
 @pytest.fixture(scope="module")
 def host_compiled_peer_lib(tmp_path_factory):
-    exp = os.path.join(os.path.dirname(HERE), "scripts", "experimental")
+    exp = os.path.join(HERE, "native")
     out = str(tmp_path_factory.mktemp("shim") / "libtzk_peer_cpu.so")
     subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-I", exp, "-x",
                     "c++", os.path.join(os.path.dirname(HERE), "torcheasyrec_b200", "csrc", "tzk_peer.cu"), "-shared",

@@ -1,4 +1,4 @@
-"""Round-2 drafts under scripts/experimental, executed on the CPU from their actual CUDA source.
+"""The barrier-free narrow-tower backward (csrc/tzk_tower_bwd2.cuh), executed on the CPU from their actual CUDA source.
 
 `cuda_cpu_shim.h` compiles a plain CUDA kernel (no PTX, no warp intrinsics) with g++ and runs it with one std::thread
 per CUDA thread and a real barrier for __syncthreads.  That checks what can be wrong before the first GPU minute is
@@ -11,13 +11,13 @@ import subprocess
 import numpy as np
 import pytest
 
-EXP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "experimental")
+EXP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native")
 P, I32, I64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
 
 
 def _host_compile(tmp_path_factory, name):
     out = str(tmp_path_factory.mktemp("shim") / f"lib{name}_cpu.so")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-x", "c++",
+    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-DTZK_CPU_SHIM", "-Wno-unknown-pragmas", "-I", EXP, "-x", "c++",
                     os.path.join(EXP, name + ".cu"), "-shared", "-fPIC", "-o", out], check=True)
     return ctypes.CDLL(out)
 
@@ -29,7 +29,7 @@ def _p(a):
 # ---- narrow tower layers, backward v2 ---------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def tower(tmp_path_factory):
-    L = _host_compile(tmp_path_factory, "tzk_tower_bwd2")
+    L = _host_compile(tmp_path_factory, "tower_bwd2_standalone")
     L.tzk_small_linear_bwd2_workspace_bytes.restype = ctypes.c_size_t
     L.tzk_small_linear_bwd2_workspace_bytes.argtypes = [I64, I32, I32]
     L.tzk_small_linear_bwd2.argtypes = [P, I64, P, P, I64, P, I64, I64, I32, I32, I32, P, I64, P, P, P, ctypes.c_size_t, P]
@@ -77,59 +77,3 @@ def test_small_linear_bwd2_rejects_what_it_cannot_map(tower):
     rc = tower.tzk_small_linear_bwd2(_p(z), K, _p(z), _p(z), N, _p(z), N, M, K, N, 0, None, 0, _p(z), _p(z), _p(ws),
                                      ws.nbytes, None)
     assert rc == 4
-
-
-# ---- peer gather: multi-id bags, mean pooling, wide rows (the sharded-step test covers one id per bag, D = 16) ------------
-@pytest.fixture(scope="module")
-def peer(tmp_path_factory):
-    L = _host_compile(tmp_path_factory, "tzk_peer")
-    L.tzk_peer_pooled_gather_fwd.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P, I64, P]
-    return L
-
-
-@pytest.mark.parametrize("W,D", [(1, 16), (3, 32), (4, 8), (2, 128)])
-def test_peer_gather_source_multi_id_bags(peer, W, D):
-    rng = np.random.default_rng(W * 100 + D)
-    F, B = 3, 37
-    rows = [50, 7, 211]
-    block = [(r + W - 1) // W for r in rows]
-    block[1] = 1 << 62                                  # feature 1: table-wise on the last rank
-    owner = [0, W - 1, 0]
-    pool = [0, 1, 1]                                    # sum, mean, mean
-    col = [0, D, 2 * D]
-    full = [rng.standard_normal((r, D)).astype(np.float32) for r in rows]
-    # per-rank arenas: tables back to back, row-wise blocks (some ranks hold nothing of a small table)
-    arenas, w_off = [], np.zeros((W, F), dtype=np.int64)
-    for r in range(W):
-        parts, o = [], 0
-        for f in range(F):
-            lo = 0 if block[f] >= rows[f] else min(r * block[f], rows[f])
-            hi = (rows[f] if r == owner[f] else 0) if block[f] >= rows[f] else min((r + 1) * block[f], rows[f])
-            w_off[r, f] = o
-            parts.append(full[f][lo:hi].reshape(-1))
-            o += (hi - lo) * D
-        arenas.append(np.concatenate(parts + [np.zeros(4, dtype=np.float32)]))
-    lens = rng.integers(0, 4, F * B)
-    lens[:3] = [0, 1, 3]
-    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    ids = np.concatenate([rng.integers(0, rows[i // B], n) for i, n in enumerate(lens)]).astype(np.int64)
-    ids[::7] = 10 ** 9                                  # out of range -> row 0, like the unsharded gather
-    out = np.full((B, F * D), np.nan, dtype=np.float32)
-    ptrs = (ctypes.c_uint64 * W)(*[a.ctypes.data for a in arenas])
-    arr = lambda v, t: np.asarray(v, dtype=t)
-    a_rows, a_block, a_owner = arr(rows, np.int64), arr(block, np.int64), arr(owner, np.int32)
-    a_dim, a_col, a_pool = arr([D] * F, np.int32), arr(col, np.int32), arr(pool, np.int32)
-    rc = peer.tzk_peer_pooled_gather_fwd(ptrs, _p(w_off), _p(a_rows), _p(a_block), _p(a_owner), _p(a_dim), _p(a_col),
-                                         _p(a_pool), _p(ids), _p(offsets), F, B, W, D, _p(out), F * D, None)
-    assert rc == 0
-    want = np.zeros((B, F * D), dtype=np.float32)
-    for f in range(F):
-        for b in range(B):
-            s, e = offsets[f * B + b], offsets[f * B + b + 1]
-            acc = np.zeros(D, dtype=np.float32)
-            for i in ids[s:e]:
-                acc = acc + full[f][i if 0 <= i < rows[f] else 0]       # same order, same fp32 adds
-            if pool[f] == 1 and e > s:
-                acc = acc * np.float32(1.0 / (e - s))
-            want[b, col[f]:col[f] + D] = acc
-    np.testing.assert_array_equal(out, want)

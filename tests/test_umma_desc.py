@@ -1,4 +1,4 @@
-"""tcgen05 descriptor encodings of the round-2 GEMM draft (scripts/experimental/tzk_umma_desc.h) against CuTe.
+"""tcgen05 descriptor encodings of the round-2 GEMM draft (tests/native/tzk_umma_desc.h) against CuTe.
 
 Host-only: `check_umma_desc.cu` includes the CUTLASS / CuTe headers vendored in this image, asks `make_instr_desc` /
 `make_umma_desc` what they encode for the draft's tiles (kind::tf32, 128 x 64 / 112, K-major and MN-major,
@@ -12,7 +12,7 @@ import sys
 
 import pytest
 
-EXP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "experimental")
+EXP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native")
 
 
 def _cutlass_include():
@@ -31,7 +31,8 @@ def test_umma_descriptors_match_cute(tmp_path):
     if not os.path.exists(nvcc) or inc is None:
         pytest.skip("needs nvcc and the vendored CuTe headers")
     exe = str(tmp_path / "check_umma_desc")
-    subprocess.run([nvcc, "-std=c++17", "-I" + inc, "-I" + EXP, "--expt-relaxed-constexpr", "-o", exe,
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "torcheasyrec_b200", "csrc")
+    subprocess.run([nvcc, "-std=c++17", "-I" + inc, "-I" + csrc, "--expt-relaxed-constexpr", "-o", exe,
                     os.path.join(EXP, "check_umma_desc.cu")], check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout

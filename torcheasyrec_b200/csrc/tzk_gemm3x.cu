@@ -16,15 +16,15 @@
 // Barriers per stage: full (TMA -> transform), ready (transform -> MMA), empty (MMA commit -> TMA);
 // per accumulator: acc_full (MMA commit -> epilogue), acc_empty (epilogue -> MMA).
 //
-// Build + try (next round, on a B200):  python scripts/experimental/try_gemm3x.py
+// GPU tests: tests/test_kernels_gpu.py (test_gemm3x_kernels_match_fp64, test_wide_layer_on_tcgen05_matches_fp64)
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "tzk_umma_desc.h"
 #ifdef TZK_CPU_SHIM
-#include "../../scripts/experimental/cuda_cpu_shim.h"      // host execution for tests/test_experimental_gemm3x_emu.py:
-#include "../../scripts/experimental/tcgen05_cpu_emu.h"    // TMA / tcgen05 / mbarrier / TMEM emulated from their documented semantics
+#include "cuda_cpu_shim.h"      // (tests/native, -I) host execution for tests/test_gemm3x_emu.py:
+#include "tcgen05_cpu_emu.h"    // TMA / tcgen05 / mbarrier / TMEM emulated from their documented semantics
 #else
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -11,7 +11,7 @@
 //                                                                 CTA are folded in shared memory in a fixed order,
 //                                                                 CTAs by a fixed-order reduction kernel.
 // Plain CUDA (no PTX): the includer provides TZK_DYN_SMEM(type, name) and TZK_LAUNCH((kernel), grid, block, smem,
-// stream, args...) — nvcc in libtzk.so, g++ + scripts/experimental/cuda_cpu_shim.h in tests/test_experimental_kernels_cpu.py,
+// stream, args...) — nvcc in libtzk.so, g++ + tests/native/cuda_cpu_shim.h in tests/test_tower_bwd2_cpu.py,
 // which runs this very source on the host against float64.
 #pragma once
 #include <stdint.h>

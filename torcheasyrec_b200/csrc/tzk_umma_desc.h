@@ -1,6 +1,6 @@
 // tzk_umma_desc.h — tcgen05 (UMMA) shared-memory and instruction descriptor encodings used by tzk_gemm3x.cu.
 // Kept in a header of their own so that check_umma_desc.cu can compare them, on the host, with what CuTe's
-// make_umma_desc / make_instr_desc produce for the same tiles (tests/test_experimental_umma_desc.py).
+// make_umma_desc / make_instr_desc produce for the same tiles (tests/test_umma_desc.py).
 #pragma once
 #include <stdint.h>
 
