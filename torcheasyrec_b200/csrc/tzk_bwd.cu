@@ -55,8 +55,10 @@ struct BwdArgs {
   // for MEAN pooling); idx = bag (pooled) or id position (sequence).  peer_w == 0: everything is local.
   int32_t peer_w;
   int32_t idx_span;
-  unsigned long long grad_peer[16];
 };
+// peer mode: the sources' published gradient buffers.  A kernel parameter of its own (__grid_constant__): indexing it
+// with a run-time rank must not drag the whole argument block into local memory.
+struct PeerGrads { unsigned long long p[16]; };
 
 __device__ __forceinline__ void init_bias_correction(BwdArgs& a) {
   a.bc1 = a.bc2 = 1.f;
@@ -220,13 +222,14 @@ struct Entry {
   int f;
 };
 
-__device__ __forceinline__ Entry entry_of(const BwdArgs& a, const BwdFeat* fd, int32_t v, int f_hint) {
+__device__ __forceinline__ Entry entry_of(const BwdArgs& a, const PeerGrads& gp, const BwdFeat* fd, int32_t v,
+                                          int f_hint) {
   Entry en;
   const float* base = a.grad_out;
   if (a.peer_w) {
     const int r = v / a.idx_span;
     v -= r * a.idx_span;
-    base = reinterpret_cast<const float*>(a.grad_peer[r]);
+    base = reinterpret_cast<const float*>(gp.p[r]);
   }
   if (a.pooled) {
     const int f = v / a.B;
@@ -429,40 +432,73 @@ constexpr int kChunk = 256;
 struct ChunkItem {
   int32_t start, end;   // sorted positions [start, end)
   int32_t n_chunks;     // chunks of the run
-  int32_t pslot;        // multi-chunk runs: slot of this chunk's partial sum (run base + chunk index)
-};
-struct LongRun {
-  int32_t head, pslot, n_chunks, pad;
+  int32_t pbase;        // multi-chunk runs: first partial slot of the run (-1 for single-chunk runs)
+  int32_t cc;           // index of this chunk inside its run
+  int32_t pad;
 };
 struct WorkLists {
   ChunkItem* items;
-  LongRun* runs;
-  int32_t* counters;  // [0] items, [1] multi-chunk runs, [2] partial slots
+  int32_t* run_done;  // [partial slots] per multi-chunk run (indexed by pbase): chunks finished so far
+  int32_t* counters;  // [0] items, [2] partial slots
   float* partials;    // [slots][ROWF]
 };
+
+// ---- 2'. work list of the long runs (id half: runs right after the sort, on the side stream) ---------------------------
+// A run head whose key repeats kShortRun positions further on is a long run: its end is found by gallop + binary search
+// and its chunks are appended to the list.  (The list's order depends on scheduling; the results do not: a chunk's
+// partial sum and the chunk order of the combine are fixed by the sorted positions.)
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads)
+find_long_runs_kernel(const KeyT* __restrict__ keys, int64_t n, KeyT sentinel, WorkLists wl) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const KeyT k0 = keys[p];
+    if (k0 == sentinel || (p > 0 && keys[p - 1] == k0)) continue;
+    if (p + kShortRun >= n || keys[p + kShortRun] != k0) continue;
+    int64_t lo = p + kShortRun, step = kShortRun;  // keys[lo] == k0
+    int64_t hi = lo + step;
+    while (hi < n && keys[hi] == k0) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > n) hi = n;
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] == k0) lo = mid; else hi = mid;
+    }
+    const int64_t end = hi;
+    const int n_chunks = (int)((end - p + kChunk - 1) / kChunk);
+    const int base = atomicAdd(wl.counters + 0, n_chunks);
+    int pbase = -1;
+    if (n_chunks > 1) {
+      pbase = atomicAdd(wl.counters + 2, n_chunks);
+      wl.run_done[pbase] = 0;
+    }
+    for (int cc = 0; cc < n_chunks; ++cc) {
+      ChunkItem it;
+      it.start = (int32_t)(p + (int64_t)cc * kChunk);
+      it.end = (int32_t)((p + (int64_t)(cc + 1) * kChunk) < end ? (p + (int64_t)(cc + 1) * kChunk) : end);
+      it.n_chunks = n_chunks;
+      it.pbase = pbase;
+      it.cc = cc;
+      it.pad = 0;
+      wl.items[base + cc] = it;
+    }
+  }
+}
 
 // CH = float4 (or scalar) chunks per lane: dims up to G*VEC*CH are supported.
 // Each lane group owns kPos consecutive sorted positions per iteration.  Runs of length 1 (the common case on
 // big tables) take a batched path: the gradient / weight / state rows of all of them are requested before any
 // is consumed, so a group keeps 3*kPos independent 64-B requests in flight instead of one dependent chain.
 template <typename KeyT, int G, int VEC, int CH>
-__global__ void __launch_bounds__(kThreads)
-run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
-                  const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
-                  const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
-                  const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
-  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
-  init_bias_correction(a);
-
+__device__ __forceinline__ void run_update_body(const BwdArgs& a, const PeerGrads& gp, const BwdFeat* fd,
+                                                const KeyT* __restrict__ keys,
+                                                const int32_t* __restrict__ vals, int cta, int n_ctas) {
   constexpr int NG = kThreads / G;
   constexpr int kPos = 1;   // positions per lane group per iteration (2 and 4 with a batched single-run path were
                             // measured slower: 349 / 375 / 461 us for 1 / 2 / 4 on DLRM-Criteo)
   const int lane = threadIdx.x % G;
-  const int64_t stride = (int64_t)gridDim.x * NG * kPos;
+  const int64_t stride = (int64_t)n_ctas * NG * kPos;
   // all G lanes of a group follow the same control flow (positions, keys, run lengths are group-uniform)
-  for (int64_t p0 = ((int64_t)blockIdx.x * NG + threadIdx.x / G) * kPos; p0 < a.n; p0 += stride) {
+  for (int64_t p0 = ((int64_t)cta * NG + threadIdx.x / G) * kPos; p0 < a.n; p0 += stride) {
     KeyT key[kPos + 2];  // key[0] = left neighbour, key[kPos+1] = right neighbour
     int32_t v[kPos];
     key[0] = p0 > 0 ? keys[p0 - 1] : (KeyT)~keys[p0];
@@ -490,37 +526,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
       const KeyT k0 = key[u + 1];
       int len = 1;
       while (len <= kShortRun && p + len < a.n && keys[p + len] == k0) ++len;
-      if (len > kShortRun) {
-        if (lane == 0) {
-          // gallop + binary search for the end of the run, then enqueue its chunks
-          int64_t lo = p + kShortRun, step = kShortRun;  // keys[lo] == k0
-          int64_t hi = lo + step;
-          while (hi < a.n && keys[hi] == k0) { lo = hi; step <<= 1; hi = lo + step; }
-          if (hi > a.n) hi = a.n;
-          while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (keys[mid] == k0) lo = mid; else hi = mid;
-          }
-          const int64_t end = hi;
-          const int n_chunks = (int)((end - p + kChunk - 1) / kChunk);
-          const int base = atomicAdd(wl.counters + 0, n_chunks);
-          int pslot = -1;
-          if (n_chunks > 1) {
-            pslot = atomicAdd(wl.counters + 2, n_chunks);
-            LongRun lr; lr.head = (int32_t)p; lr.pslot = pslot; lr.n_chunks = n_chunks; lr.pad = 0;
-            wl.runs[atomicAdd(wl.counters + 1, 1)] = lr;
-          }
-          for (int cc = 0; cc < n_chunks; ++cc) {
-            ChunkItem it;
-            it.start = (int32_t)(p + (int64_t)cc * kChunk);
-            it.end = (int32_t)((p + (int64_t)(cc + 1) * kChunk) < end ? (p + (int64_t)(cc + 1) * kChunk) : end);
-            it.n_chunks = n_chunks;
-            it.pslot = n_chunks > 1 ? pslot + cc : -1;
-            wl.items[base + cc] = it;
-          }
-        }
-        continue;
-      }
+      if (len > kShortRun) continue;   // long runs are on the work list (find_long_runs_kernel, id half) for the chunk CTAs
       const int32_t v0 = v[u];
       int f00;
       if (a.pooled) f00 = bag_feat(a, v0); else f00 = feat_of_key<KeyT>(fd, a.F, k0);
@@ -532,7 +538,7 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
       for (int j = 0; j < len; ++j) {
-        const Entry en = entry_of(a, fd, j == 0 ? v0 : vals[p + j], f00);
+        const Entry en = entry_of(a, gp, fd, j == 0 ? v0 : vals[p + j], f00);
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
           const int c = (ch * G + lane) * VEC;
@@ -549,30 +555,28 @@ run_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
   }
 }
 
-// ---- 4a. one WARP per chunk of a long run ---------------------------------------------------------------
-// 32/G lane groups stride over the chunk with kLU gradient rows in flight each, then a fixed-order shuffle tree
-// folds the groups' partial sums into group 0, which either finishes the run or parks the chunk's partial.
+// ---- 4. one WARP per chunk of a long run ----------------------------------------------------------------------
+// 32/G lane groups stride over the chunk with kLU gradient rows in flight each, then a fixed-order shuffle tree folds
+// the groups' partial sums into group 0, which either finishes the run or parks the chunk's partial.  The warp that
+// parks the LAST partial of a multi-chunk run (a counter per run) adds the run's partials in chunk order and applies
+// the update — the order of the additions is fixed by the sorted positions, whoever happens to execute them.
+// These CTAs ride in the same launch as the short-run CTAs (fused_apply_kernel): tiny tables / hot ids and the big
+// tables' rows are updated side by side instead of in three dependent launches.
 template <typename KeyT, int G, int VEC, int CH>
-__global__ void __launch_bounds__(kThreads)
-long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
-                  const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
-                  const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
-                  const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void long_chunk_body(const BwdArgs& a, const PeerGrads& gp, const BwdFeat* fd,
+                                                const KeyT* __restrict__ keys,
+                                                const int32_t* __restrict__ vals, const WorkLists& wl, int cta,
+                                                int n_ctas) {
   constexpr int GW = 32 / G;          // lane groups per warp
   constexpr int ROWF = CH * G * VEC;  // floats per partial row
   constexpr int kLU = 4;              // independent gradient rows in flight per lane group
-  BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
-  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
-  init_bias_correction(a);
-
   const int lane = threadIdx.x % G;
   const int gw = (threadIdx.x & 31) / G;
   const int warp = threadIdx.x >> 5;
   constexpr int WPC = kThreads / 32;
   const int n_items = wl.counters[0];
 
-  for (int r = blockIdx.x * WPC + warp; r < n_items; r += gridDim.x * WPC) {
+  for (int r = cta * WPC + warp; r < n_items; r += n_ctas * WPC) {
     const ChunkItem it = wl.items[r];
     const KeyT key = keys[it.start];
     const int32_t v0 = vals[it.start];
@@ -593,7 +597,7 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
       for (int u = 0; u < kLU; ++u) {
         const int q = q0 + u * GW;
         ok[u] = q < it.end;
-        en[u] = entry_of(a, fd, ok[u] ? vals[q] : v0, f0);
+        en[u] = entry_of(a, gp, fd, ok[u] ? vals[q] : v0, f0);
       }
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
@@ -623,53 +627,53 @@ long_chunk_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64
       if (it.n_chunks == 1) {
         finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
       } else {
-        float* dst = wl.partials + (int64_t)it.pslot * ROWF;
+        float* dst = wl.partials + (int64_t)(it.pbase + it.cc) * ROWF;
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
           for (int k = 0; k < VEC; ++k) dst[(ch * G + lane) * VEC + k] = acc[ch][k];
+        __threadfence();                                    // this chunk's partial is visible before the count moves
+        int done = 0;
+        if (lane == 0) done = atomicAdd(wl.run_done + it.pbase, 1);
+        done = __shfl_sync(group_mask<G>(), done, 0, G);
+        if (done == it.n_chunks - 1) {                      // last chunk of the run: combine in chunk order, update
+          __threadfence();
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+          for (int c = 0; c < it.n_chunks; ++c) {
+            const float* src = wl.partials + (int64_t)(it.pbase + c) * ROWF;
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) acc[ch][k] += __ldcg(src + (ch * G + lane) * VEC + k);
+          }
+          finish_run<G, VEC, CH>(a, d, row, (int64_t)key, acc, lane);
+          if (lane == 0) wl.run_done[it.pbase] = 0;         // the list can be replayed (same sort, another gradient)
+        }
       }
     }
     __syncwarp();
   }
 }
 
-// ---- 4b. multi-chunk runs: add the chunk partials in chunk order, then update ------------------------------
+// ---- 3 + 4 in one launch: CTAs [0, n_short) walk the sorted positions (short runs), the rest serve the long-run list
 template <typename KeyT, int G, int VEC, int CH>
-__global__ void __launch_bounds__(kThreads)
-long_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
-                    const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
-                    const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
-                    const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl) {
+__global__ void __launch_bounds__(kThreads, CH == 1 ? 5 : 1)     // 5 CTAs / SM like the short-run kernel had on its own
+fused_apply_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
+                   const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
+                   const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
+                   const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, WorkLists wl, int n_long,
+                   const __grid_constant__ PeerGrads gp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NG = kThreads / G;
-  constexpr int ROWF = CH * G * VEC;
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
   stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
   init_bias_correction(a);
-  const int lane = threadIdx.x % G;
-  const int n_runs = wl.counters[1];
-  for (int r = blockIdx.x * NG + threadIdx.x / G; r < n_runs; r += gridDim.x * NG) {
-    const LongRun lr = wl.runs[r];
-    const KeyT key = keys[lr.head];
-    const int32_t v0 = vals[lr.head];
-    int f0;
-    if (a.pooled) f0 = bag_feat(a, v0); else f0 = feat_of_key<KeyT>(fd, a.F, key);
-    const BwdFeat d = fd[f0];
-    float acc[CH][VEC];
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-    for (int c = 0; c < lr.n_chunks; ++c) {
-      const float* src = wl.partials + (int64_t)(lr.pslot + c) * ROWF;
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[ch][k] += src[(ch * G + lane) * VEC + k];
-    }
-    finish_run<G, VEC, CH>(a, d, (int64_t)key - d.key_base, (int64_t)key, acc, lane);
-  }
+  // the long-run CTAs come FIRST in the grid: they are few, each has a lot to do, and the hardware starts CTAs in
+  // index order — their work overlaps the whole short-run sweep instead of trailing it
+  if ((int)blockIdx.x < n_long) long_chunk_body<KeyT, G, VEC, CH>(a, gp, fd, keys, vals, wl, blockIdx.x, n_long);
+  else run_update_body<KeyT, G, VEC, CH>(a, gp, fd, keys, vals, blockIdx.x - n_long, gridDim.x - n_long);
 }
 
 // ---- 3'. tile path: rows of <= 128 floats, 16-B aligned (vec4, one chunk per lane) -------------------------
@@ -703,7 +707,8 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
                    const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
                    const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
                    const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
-                   float* __restrict__ carry_first, float* __restrict__ carry_last) {
+                   float* __restrict__ carry_first, float* __restrict__ carry_last,
+                   const __grid_constant__ PeerGrads gp) {
   using C = TileCfg<G>;
   constexpr int ROWF = C::ROWF, TP = C::TP, NG = C::NG, U = C::U;
   constexpr int KPT = (TP + 2 + kThreads - 1) / kThreads;  // keys per thread (tile + both neighbours)
@@ -775,7 +780,7 @@ tile_update_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
       const int f = a.pooled ? bag_feat(a, v) : feat_of_key<KeyT>(fd, a.F, key);
       fx[u] = f;
       const int dim = fd[f].dim;
-      const Entry en = entry_of(a, fd, v, f);
+      const Entry en = entry_of(a, gp, fd, v, f);
       if (c < dim) g4[u] = f4_scale(a.peer_w ? ld_coh_f4(en.g + c) : ld_row_f4(en.g + c), en.scale);
       if (i == 0 || sk[i] != key) {
         const bool cl = (i == 0) && first_cont;
@@ -962,7 +967,7 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
   L.vals_in = o; o = align_up(o + n * 4, 256);
   L.vals_out = o; o = align_up(o + n * 4, 256);
   L.items = o; o = align_up(o + max_items(n) * sizeof(ChunkItem), 256);
-  L.runs = o; o = align_up(o + (n / kChunk + 2) * sizeof(LongRun), 256);
+  L.runs = o; o = align_up(o + (size_t)max_pslots(n) * sizeof(int32_t), 256);        // run_done counters
   L.counters = o; o = align_up(o + 256, 256);
   const size_t rowf = (size_t)((max_dim + 127) / 128 * 128 < 128 ? 128 : (max_dim + 127) / 128 * 128) * 4;
   L.partials = o; o = align_up(o + max_pslots(n) * rowf * sizeof(float), 256);
@@ -988,27 +993,12 @@ WsLayout ws_layout(int64_t nnz, int64_t total_keys, int max_dim) {
   do {                                                                                                \
     size_t smem_s = (size_t)F * sizeof(BwdFeat);                                                      \
     if (smem_s > 48 * 1024)                                                                           \
-      cudaFuncSetAttribute(run_update_kernel<KeyT, G_, VEC_, CH_>,                                    \
+      cudaFuncSetAttribute(fused_apply_kernel<KeyT, G_, VEC_, CH_>,                                   \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
-    run_update_kernel<KeyT, G_, VEC_, CH_><<<grid_s, kThreads, smem_s, st>>>(                         \
+    fused_apply_kernel<KeyT, G_, VEC_, CH_><<<grid_s + n_long, kThreads, smem_s, st>>>(               \
         a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
-        vals_out, wl);                                                                                \
-    TZK_CHECK_LAUNCH("run_update_kernel");                                                            \
-    size_t smem_l = (size_t)F * sizeof(BwdFeat);                                                      \
-    if (smem_l > 48 * 1024)                                                                           \
-      cudaFuncSetAttribute(long_chunk_kernel<KeyT, G_, VEC_, CH_>,                                    \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);                 \
-    long_chunk_kernel<KeyT, G_, VEC_, CH_><<<kSmCountB200 * 8, kThreads, smem_l, st>>>(               \
-        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
-        vals_out, wl);                                                                                \
-    TZK_CHECK_LAUNCH("long_chunk_kernel");                                                            \
-    if (smem_s > 48 * 1024)                                                                           \
-      cudaFuncSetAttribute(long_combine_kernel<KeyT, G_, VEC_, CH_>,                                  \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                 \
-    long_combine_kernel<KeyT, G_, VEC_, CH_><<<kSmCountB200, kThreads, smem_s, st>>>(                 \
-        a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, \
-        vals_out, wl);                                                                                \
-    TZK_CHECK_LAUNCH("long_combine_kernel");                                                          \
+        vals_out, wl, n_long, gp);                                                                    \
+    TZK_CHECK_LAUNCH("fused_apply_kernel");                                                           \
   } while (0)
 
 #define TZK_BWD_DISPATCH_G(KeyT, VEC_, CH_)                 \
@@ -1068,7 +1058,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   int32_t* vals_out = reinterpret_cast<int32_t*>(ws + L.vals_out);
   WorkLists wl;
   wl.items = reinterpret_cast<ChunkItem*>(ws + L.items);
-  wl.runs = reinterpret_cast<LongRun*>(ws + L.runs);
+  wl.run_done = reinterpret_cast<int32_t*>(ws + L.runs);
   wl.counters = reinterpret_cast<int32_t*>(ws + L.counters);
   wl.partials = reinterpret_cast<float*>(ws + L.partials);
   const bool k64 = total_keys >= ((int64_t)1 << 32);
@@ -1123,6 +1113,13 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   }
   TZK_REQUIRE(ce == cudaSuccess, "fused_bwd: radix sort failed: %s", cudaGetErrorString(ce));
   }
+  if (phases & 1) {   // work list of the long runs (tiny tables, hot ids) for the gradient half's chunk CTAs
+    zero_counters<<<1, 1, 0, st>>>(wl.counters);
+    const int grid_f = (int)std::min<int64_t>(ceil_div64(nnz, kThreads), kSmCountB200 * 8);
+    if (k64) find_long_runs_kernel<uint64_t><<<grid_f, kThreads, 0, st>>>((const uint64_t*)keys_out, nnz, (uint64_t)sentinel, wl);
+    else find_long_runs_kernel<uint32_t><<<grid_f, kThreads, 0, st>>>((const uint32_t*)keys_out, nnz, (uint32_t)sentinel, wl);
+    TZK_CHECK_LAUNCH("find_long_runs_kernel");
+  }
   if (!(phases & 2)) return 0;
 
   BwdArgs a;
@@ -1132,16 +1129,17 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   a.state2 = opt.state2; a.step = opt.step; a.beta1 = opt.beta1; a.beta2 = opt.beta2;
   a.weight_decay = opt.weight_decay; a.max_gradient = opt.max_gradient; a.bc1 = a.bc2 = 1.f;
   a.peer_w = 0; a.idx_span = 1;
-  for (int r = 0; r < 16; ++r) a.grad_peer[r] = 0ull;
+  PeerGrads gp;
+  for (int r = 0; r < 16; ++r) gp.p[r] = 0ull;
   if (pw) {
     TZK_REQUIRE(grad_ptrs, "fused_bwd: peer mode needs the published gradient pointers");
     a.peer_w = pw->W; a.idx_span = pw->idx_span;
-    for (int r = 0; r < pw->W; ++r) a.grad_peer[r] = grad_ptrs[r];
+    for (int r = 0; r < pw->W; ++r) gp.p[r] = grad_ptrs[r];
     a.grad_out = reinterpret_cast<const float*>(grad_ptrs[pw->me]);
   }
 
   bool peers_aligned = true;
-  for (int r = 0; r < a.peer_w; ++r) peers_aligned = peers_aligned && (a.grad_peer[r] % 16 == 0);
+  for (int r = 0; r < a.peer_w; ++r) peers_aligned = peers_aligned && (gp.p[r] % 16 == 0);
   const int vec = (vec_ok && peers_aligned && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)a.grad_out % 16 == 0) &&
                    (ld_grad % 4 == 0) &&
                    (!(optimizer == TZK_OPT_ADAGRAD || optimizer >= TZK_OPT_ADAM) || (uintptr_t)state % 16 == 0) &&
@@ -1177,7 +1175,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
     const int grid_t = (int)std::min<int64_t>(n_tiles, kSmCountB200 * 8);                                       \
     tile_update_kernel<KeyT, G_><<<grid_t, kThreads, smem_t, st>>>(                                             \
         a, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, (const KeyT*)keys_out, vals_out, \
-        carry_first, carry_last);                                                                               \
+        carry_first, carry_last, gp);                                                                           \
     TZK_CHECK_LAUNCH("tile_update_kernel");                                                                     \
     if (n_tiles > 1) {                                                                                          \
       const size_t smem_c = (size_t)F * sizeof(BwdFeat);                                                        \
@@ -1206,8 +1204,8 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
     return 0;
   }
 
-  // general path (unaligned rows or rows wider than 128 floats): CH is compiled for 1, 2 and 8
-  zero_counters<<<1, 1, 0, st>>>(wl.counters);
+  // general path: one launch — short runs by sorted position + the long-run list's chunk CTAs (CH compiled for 1, 2, 8)
+  const int n_long = kSmCountB200 * 2;
   if (k64) {
     if (vec == 4) { if (ch == 1) { TZK_BWD_DISPATCH_G(uint64_t, 4, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint64_t, 32, 4, 2); } else { TZK_BWD_LAUNCH(uint64_t, 32, 4, 8); } }
     else { if (ch == 1) { TZK_BWD_DISPATCH_G(uint64_t, 1, 1) } else if (ch <= 2) { TZK_BWD_LAUNCH(uint64_t, 32, 1, 2); } else { TZK_BWD_LAUNCH(uint64_t, 32, 1, 8); } }

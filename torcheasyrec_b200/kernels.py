@@ -250,9 +250,9 @@ class CudaKernels:
                 _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(ids), _ptr(offsets), F, B, nnz,
                 lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
                 _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd")
-        # own launches next to CUB's radix sort: tile path = linearize, tile_update, carry_combine;
-        # general path (unaligned / > 128 floats) = zero_counters, linearize, run_update, long_chunk, long_combine
-        self.launches += 3 if _tile_path(lay) else 5
+        # own launches next to CUB's radix sort: linearize, zero_counters, find_long_runs + the gradient half:
+        # fused_apply (short runs and the long-run chunk CTAs in ONE launch), or tile_update + carry_combine
+        self.launches += 5 if _tile_path(lay) else 4
 
     def fused_bwd_workspace_bytes(self, lay: FeatureLayout, nnz: int) -> int:
         return int(self._lib.tzk_fused_bwd_workspace_bytes(nnz, lay.total_keys, lay.max_dim))
@@ -269,7 +269,7 @@ class CudaKernels:
         check(self._lib.tzk_fused_bwd_sort(int(pooled), _ptr(lay.d_rows), _ptr(lay.d_key_base), _ptr(ids),
                                            _ptr(offsets), lay.num_features, B, nnz, lay.total_keys, lay.max_dim,
                                            _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_sort")
-        self.launches += 1
+        self.launches += 3
 
     def fused_bwd_apply(self, optimizer: int, pooled: bool, grad_out: torch.Tensor, weights: torch.Tensor,
                         state: Optional[torch.Tensor], lay: FeatureLayout, offsets: torch.Tensor, nnz: int, B: int,
@@ -292,7 +292,7 @@ class CudaKernels:
                 _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), _ptr(offsets), lay.num_features, B, nnz,
                 lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), _ptr(state), lr, eps, grad_scale,
                 _ptr(ws), ws.numel(), _stream()), "tzk_fused_bwd_apply")
-        self.launches += 2 if _tile_path(lay) else 4
+        self.launches += 2 if _tile_path(lay) else 1
 
     # ------------------------------------------------------------------ K1 / K2
     def bucketize_rw(self, ids: torch.Tensor, offsets: torch.Tensor, F: int, B: int, W: int,
@@ -520,7 +520,7 @@ class CudaKernels:
                                                 cap, idx_span,
                                                 lay.total_keys, lay.max_dim, _ptr(overflow), _ptr(ws), ws.numel(),
                                                 _stream()), "tzk_fused_bwd_sort_peer")
-        self.launches += 1
+        self.launches += 3
 
     def fused_bwd_apply_peer(self, optimizer: int, pooled: bool, grads, ld_grad: int, weights: torch.Tensor,
                              state: Optional[torch.Tensor], lay: FeatureLayout, B: int, me: int, W: int, cap: int,
@@ -534,7 +534,7 @@ class CudaKernels:
             _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(lay.d_key_base), lay.num_features, B, me, W, cap, idx_span,
             lay.total_keys, lay.max_dim, lay.vec_ok, _ptr(weights), grad_scale, _ptr(ws), ws.numel(), _stream()),
             "tzk_fused_bwd_apply_peer")
-        self.launches += 2 if _tile_path(lay) else 4
+        self.launches += 2 if _tile_path(lay) else 1
 
     # ------------------------------------------------------------------ K6
     def col_gather_sum(self, srcs: Sequence[torch.Tensor], plan: "ColPlan", rows: int,
