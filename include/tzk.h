@@ -64,6 +64,9 @@ typedef struct tzk_opt_args {
   float* state;
   float* state2;
   const float* step;
+  int32_t weights_f16; /* 1: `weights` points to an arena of IEEE halfs (EmbeddingBagConfig.data_type = FP16,
+                        * tzrec/protos/feature.proto data_type): rows are widened to fp32, updated, rounded to nearest */
+  int32_t reserved;
 } tzk_opt_args;
 
 typedef void* tzk_stream_t; /* cudaStream_t */
@@ -101,6 +104,17 @@ int tzk_pooled_gather_fwd(const float* weights, const int64_t* feat_w_off, const
 int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
                        const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t D,
                        int64_t nnz, float* out, tzk_stream_t stream);
+
+/* ---- FP16 tables (tzrec/protos/feature.proto `data_type = "FP16"` -> EmbeddingBagConfig.data_type, features/feature.py:
+ * 626,652): the same lookups over an arena of IEEE halfs; pooling and outputs stay fp32.  The fused backward takes such
+ * an arena through tzk_opt_args.weights_f16 (the _ex entry points); optimizer state stays fp32. */
+int tzk_pooled_gather_fwd_f16(const void* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                              const int32_t* feat_dim, const int32_t* feat_col, const int32_t* feat_pool,
+                              const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t max_dim,
+                              int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream);
+int tzk_seq_gather_fwd_f16(const void* weights, const int64_t* feat_w_off, const int64_t* feat_rows, const int64_t* ids,
+                           const int64_t* offsets, int32_t F, int32_t B, int32_t D, int64_t nnz, float* out,
+                           tzk_stream_t stream);
 
 /* ---- K5: fused backward + sparse optimizer  ([EXT] TBE split_embedding_backward_codegen_*_exact,
  * installed by apply_optimizer_in_backward at tzrec/main.py:774-781; optimizer choice

@@ -64,3 +64,40 @@ def test_ec_keys_and_model_level_names():
     q.model.load_state_dict(p.model.state_dict())
     for a, b in zip(p.model.sparse_collections(), q.model.sparse_collections()):
         assert torch.equal(a.weights, b.weights)
+
+
+def test_fp16_tables_host_logic_with_the_checker_backend():
+    """SURVEY §8f N4 (FP16 half), host side: `data_type: "FP16"` in a feature config reaches the collection, the arena
+    and the per-table state_dict views are halfs, lookups return fp32, the fused update moves only touched rows and
+    keeps fp32 optimizer state (oracle backend as compute)."""
+    import os
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from oracle_backend import OracleKernels
+
+    from torcheasyrec_b200 import functional as Fn
+    from torcheasyrec_b200.embedding_modules import DataType
+    from torcheasyrec_b200.sparse import KeyedJaggedTensor
+
+    cfgs = [EmbeddingBagConfig(name="t", num_embeddings=50, embedding_dim=8, feature_names=["f"], data_type=DataType.FP16)]
+    with Fn.use_backend(OracleKernels()):
+        m = EmbeddingBagCollection(cfgs, device="cpu")
+        m.set_optimizer(SparseOptimizerSpec(kind=OPT_ADAGRAD, lr=0.1))
+        assert m.weights.dtype == torch.float16 and m.opt_state.dtype == torch.float32
+        assert m.state_dict()["embedding_bags.t.weight"].dtype == torch.float16
+        kjt = KeyedJaggedTensor.from_lengths_sync(["f"], torch.tensor([1, 2, 3, 4]), torch.tensor([1, 1, 2, 0], dtype=torch.int32))
+        w0 = m.table_weight(0).clone()
+        out = m(kjt).values()
+        assert out.dtype == torch.float32
+        np.testing.assert_array_equal(out[2].numpy(), (w0[3].float() + w0[4].float()).numpy())
+        out.sum().backward()
+        moved = (m.table_weight(0) != w0).any(dim=1).nonzero().flatten().tolist()
+        assert moved == [1, 2, 3, 4]
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        EmbeddingBagCollection(cfgs + [EmbeddingBagConfig(name="u", num_embeddings=5, embedding_dim=8, feature_names=["g"])],
+                               device="cpu")

@@ -676,3 +676,65 @@ def test_din_jagged_kernels_match_oracle(kernels, B, Ds, Dq, max_len, max_rows):
     # run-to-run deterministic
     gp2, go2 = kernels.jagged_softmax_wsum_fwd(cu(sc), cu(k), cu(off), max_len)
     assert torch.equal(go, go2) and torch.equal(gp, gp2)
+
+
+@pytest.mark.parametrize("opt", [O.OPT_SGD, O.OPT_ADAGRAD, O.OPT_ROWWISE_ADAGRAD, O.OPT_ADAM])
+def test_fp16_tables_gather_and_fused_update(kernels, opt):
+    """SURVEY §8f N4 (FP16 half): an arena of halfs against the oracle run on the same halfs — lookups bit-exact at L=1
+    and 1e-6 for multi-hot bags (fp32 pooling), sequence rows exact, the fused update in fp32 with the new row rounded
+    to nearest half (weights compared at half precision, fp32 state at 1e-5)."""
+    from oracle_backend import OracleKernels
+
+    from torcheasyrec_b200.embedding_modules import (DataType, EmbeddingBagCollection, EmbeddingBagConfig,
+                                                     SparseOptimizerSpec)
+
+    rng = np.random.default_rng(opt)
+    cfgs = [EmbeddingBagConfig(num_embeddings=r, embedding_dim=d, name=f"t{i}", feature_names=[f"f{i}"],
+                               data_type=DataType.FP16) for i, (r, d) in enumerate([(5000, 16), (7, 16), (300, 4), (64, 16)])]
+    gpu = EmbeddingBagCollection(cfgs, device="cuda")
+    cpu = EmbeddingBagCollection(cfgs, device="cpu")
+    assert gpu.weights.dtype == torch.float16 and gpu.table_weight(0).dtype == torch.float16
+    cpu.weights.data.copy_(gpu.weights.data.cpu())
+    kind = {O.OPT_SGD: "sgd", O.OPT_ADAGRAD: "adagrad", O.OPT_ROWWISE_ADAGRAD: "rowwise_adagrad", O.OPT_ADAM: "adam"}[opt]
+    spec = SparseOptimizerSpec.from_name(kind, lr=0.05)
+    gpu.set_optimizer(spec)
+    cpu.set_optimizer(spec)
+    F, B = 4, 700
+    lens = rng.integers(0, 4, F * B)
+    lens[:B] = 1
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    rows = [c.num_embeddings for c in cfgs]
+    ids = np.concatenate([rng.integers(0, rows[b // B], lens[b]) for b in range(F * B)]).astype(np.int64)
+    lay = gpu.layout
+    ok = OracleKernels()
+    want = ok.pooled_gather_fwd(cpu.weights.data, cpu.layout, torch.from_numpy(ids), torch.from_numpy(off), B)
+    got = kernels.pooled_gather_fwd(gpu.weights.data, lay, cu(ids), cu(off), B)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
+    assert np.array_equal(got.cpu().numpy()[:, :16], want.numpy()[:, :16])         # feature 0: one id per bag -> exact
+    grad = (rng.standard_normal((B, lay.total_dim)) * 0.1).astype(np.float32)
+    for step in range(2):
+        kernels.fused_bwd(spec.kind, True, cu(grad), gpu.weights.data, gpu.opt_state, lay, cu(ids), cu(off), B, spec.lr,
+                          spec.eps, 1.0, **gpu.opt_extras())
+        ok.fused_bwd(spec.kind, True, torch.from_numpy(grad), cpu.weights.data, cpu.opt_state, cpu.layout,
+                     torch.from_numpy(ids), torch.from_numpy(off), B, spec.lr, spec.eps, 1.0, **cpu.opt_extras())
+    gw, cw = gpu.weights.data.float().cpu().numpy(), cpu.weights.data.float().numpy()
+    # one half ulp is 2^-11 relative: a summation-order difference may flip the final rounding of a few elements
+    np.testing.assert_allclose(gw, cw, rtol=1.5e-3, atol=1e-6)
+    assert (gw != cw).mean() < 0.01
+    if gpu.opt_state is not None:
+        np.testing.assert_allclose(gpu.opt_state.cpu().numpy(), cpu.opt_state.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_fp16_sequence_collection_rows(kernels):
+    from torcheasyrec_b200.embedding_modules import DataType, EmbeddingCollection, EmbeddingConfig
+
+    rng = np.random.default_rng(1)
+    cfgs = [EmbeddingConfig(num_embeddings=900, embedding_dim=16, name="s", feature_names=["a"], data_type=DataType.FP16)]
+    ec = EmbeddingCollection(cfgs, device="cuda")
+    B = 50
+    lens = rng.integers(0, 9, B)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ids = rng.integers(0, 900, int(off[-1])).astype(np.int64)
+    rows = kernels.seq_gather_fwd(ec.weights.data, ec.layout, cu(ids), cu(off), B)
+    assert rows.dtype == torch.float32
+    assert torch.equal(rows, ec.table_weight(0)[cu(ids)].float())

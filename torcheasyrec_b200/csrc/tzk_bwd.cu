@@ -55,6 +55,8 @@ struct BwdArgs {
   // for MEAN pooling); idx = bag (pooled) or id position (sequence).  peer_w == 0: everything is local.
   int32_t peer_w;
   int32_t idx_span;
+  int32_t w_f16;      // 1: `weights` is an arena of halfs (FP16 tables): rows are widened, updated in fp32, rounded back
+  int32_t pad2;
 };
 // peer mode: the sources' published gradient buffers.  A kernel parameter of its own (__grid_constant__): indexing it
 // with a run-time rank must not drag the whole argument block into local memory.
@@ -382,10 +384,19 @@ __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, i
     if (c >= d.dim) continue;
     const int64_t off = d.w_off + row * d.dim + c;
     float* wp = a.weights + off;
+    __half* wph = reinterpret_cast<__half*>(a.weights) + off;       // (FP16 tables: same element offset, half the bytes)
     float* sp = es ? a.state + off : nullptr;
     float* sp2 = es2 ? a.state2 + off : nullptr;
     if (VEC == 4) {
-      float4 w4 = *reinterpret_cast<float4*>(wp);
+      float4 w4;
+      if (a.w_f16) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(wph);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        w4 = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        w4 = *reinterpret_cast<float4*>(wp);
+      }
       float w[4] = {w4.x, w4.y, w4.z, w4.w};
       float s[4] = {0.f, 0.f, 0.f, 0.f};
       float s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -398,15 +409,22 @@ __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, i
         s2[0] = s4.x; s2[1] = s4.y; s2[2] = s4.z; s2[3] = s4.w;
       }
       apply_update<4>(a, w, s, s2, acc[ch], rw_denom);
-      *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
+      if (a.w_f16) {      // round to nearest even (fbgemm's optional stochastic rounding is not reproduced)
+        uint2 raw;
+        *reinterpret_cast<__half2*>(&raw.x) = __floats2half2_rn(w[0], w[1]);
+        *reinterpret_cast<__half2*>(&raw.y) = __floats2half2_rn(w[2], w[3]);
+        *reinterpret_cast<uint2*>(wph) = raw;
+      } else {
+        *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
+      }
       if (sp) *reinterpret_cast<float4*>(sp) = make_float4(s[0], s[1], s[2], s[3]);
       if (sp2) *reinterpret_cast<float4*>(sp2) = make_float4(s2[0], s2[1], s2[2], s2[3]);
     } else {
-      float w[1] = {wp[0]};
+      float w[1] = {a.w_f16 ? __half2float(wph[0]) : wp[0]};
       float s[1] = {sp ? sp[0] : 0.f};
       float s2[1] = {sp2 ? sp2[0] : 0.f};
       apply_update<1>(a, w, s, s2, acc[ch], rw_denom);
-      wp[0] = w[0];
+      if (a.w_f16) wph[0] = __float2half_rn(w[0]); else wp[0] = w[0];
       if (sp) sp[0] = s[0];
       if (sp2) sp2[0] = s2[0];
     }
@@ -1128,7 +1146,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   a.pooled = pooled; a.n = nnz; a.sentinel = sentinel;
   a.state2 = opt.state2; a.step = opt.step; a.beta1 = opt.beta1; a.beta2 = opt.beta2;
   a.weight_decay = opt.weight_decay; a.max_gradient = opt.max_gradient; a.bc1 = a.bc2 = 1.f;
-  a.peer_w = 0; a.idx_span = 1;
+  a.peer_w = 0; a.idx_span = 1; a.w_f16 = opt.weights_f16 ? 1 : 0; a.pad2 = 0;
   PeerGrads gp;
   for (int r = 0; r < 16; ++r) gp.p[r] = 0ull;
   if (pw) {
@@ -1140,7 +1158,8 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
 
   bool peers_aligned = true;
   for (int r = 0; r < a.peer_w; ++r) peers_aligned = peers_aligned && (gp.p[r] % 16 == 0);
-  const int vec = (vec_ok && peers_aligned && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)a.grad_out % 16 == 0) &&
+  const int vec = (vec_ok && peers_aligned && ((uintptr_t)weights % (a.w_f16 ? 8 : 16) == 0) &&
+                   ((uintptr_t)a.grad_out % 16 == 0) &&
                    (ld_grad % 4 == 0) &&
                    (!(optimizer == TZK_OPT_ADAGRAD || optimizer >= TZK_OPT_ADAM) || (uintptr_t)state % 16 == 0) &&
                    (optimizer != TZK_OPT_ADAM || (uintptr_t)opt.state2 % 16 == 0))
@@ -1158,7 +1177,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   // way — and the general kernels execute fewer instructions (74 M vs 87 M warp-instructions) without the three
   // barriers per tile, so they stay the default.
   const char* tile_env = getenv("TZK_BWD_TILE");
-  const bool tile_path = tile_env && tile_env[0] == '1';
+  const bool tile_path = tile_env && tile_env[0] == '1' && !a.w_f16;   // (the tile kernels are fp32-table only)
   if (vec == 4 && ch == 1 && tile_path) {
     // tile path: every gradient / weight / state row of a tile is requested at once, runs are reduced in shared memory
     float* carry_first = reinterpret_cast<float*>(ws + L.carry);
@@ -1219,7 +1238,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
 static tzk_opt_args classic_opt(int32_t optimizer, float* state, float lr, float eps) {
   tzk_opt_args o;
   o.optimizer = optimizer; o.lr = lr; o.eps = eps; o.beta1 = 0.9f; o.beta2 = 0.999f; o.weight_decay = 0.f;
-  o.max_gradient = 0.f; o.state = state; o.state2 = nullptr; o.step = nullptr;
+  o.max_gradient = 0.f; o.state = state; o.state2 = nullptr; o.step = nullptr; o.weights_f16 = 0; o.reserved = 0;
   return o;
 }
 

@@ -1,5 +1,6 @@
 // Shared helpers for the tzk kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -63,6 +64,21 @@ __device__ __forceinline__ float4 ld_rw_f4(const float* p) {
                : "memory");
   return r;
 }
+// ---- FP16 tables (feature.proto data_type = "FP16"): rows are stored as halfs, every kernel computes in fp32 ------------
+__device__ __forceinline__ float4 ld_row_h4(const __half* p) {    // 4 consecutive halfs (8 B) -> float4
+  unsigned int a, b;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&b));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <typename WT> __device__ __forceinline__ float4 ld_table_f4(const WT* p);
+template <> __device__ __forceinline__ float4 ld_table_f4<float>(const float* p) { return ld_row_f4(p); }
+template <> __device__ __forceinline__ float4 ld_table_f4<__half>(const __half* p) { return ld_row_h4(p); }
+template <typename WT> __device__ __forceinline__ float ld_table_f1(const WT* p);
+template <> __device__ __forceinline__ float ld_table_f1<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_table_f1<__half>(const __half* p) { return __half2float(__ldg(p)); }
+
 __device__ __forceinline__ void st_stream_f4(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)

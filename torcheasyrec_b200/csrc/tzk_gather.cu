@@ -41,9 +41,9 @@ struct BagStage {
   int64_t id0;     // first id (valid when len > 0)
 };
 
-template <int G, int VEC>
+template <int G, int VEC, typename WT>
 __global__ void __launch_bounds__(kThreads)
-pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __restrict__ feat_w_off,
+pooled_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restrict__ feat_w_off,
                          const int64_t* __restrict__ feat_rows, const int32_t* __restrict__ feat_dim,
                          const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
                          const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets, int F, int B,
@@ -117,7 +117,7 @@ pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __res
             const FeatDesc& d = fd[f0 + i / kTB];
             int64_t id = st[i].id0;
             if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-            if (lane * 4 < d.dim) acc[u] = ld_row_f4(weights + d.w_off + id * d.dim + lane * 4);
+            if (lane * 4 < d.dim) acc[u] = ld_table_f4<WT>(weights + d.w_off + id * d.dim + lane * 4);
           }
         }
 #pragma unroll
@@ -136,13 +136,13 @@ pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __res
               } else {
                 int64_t id = st[i].id0;
                 if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-                a = ld_row_f4(weights + d.w_off + id * d.dim + c);
+                a = ld_table_f4<WT>(weights + d.w_off + id * d.dim + c);
               }
               const int64_t s0 = st[i].start;
               for (int l = 1; l < L; ++l) {
                 int64_t idl = __ldg(ids + s0 + l);
                 if ((uint64_t)idl >= (uint64_t)d.rows) idl = 0;
-                a = f4_add(a, ld_row_f4(weights + d.w_off + idl * d.dim + c));
+                a = f4_add(a, ld_table_f4<WT>(weights + d.w_off + idl * d.dim + c));
               }
               if (d.pool == TZK_POOL_MEAN) a = f4_scale(a, 1.0f / (float)L);
             }
@@ -164,11 +164,11 @@ pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __res
             if (L > 0) {
               int64_t id = st[i].id0;
               if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-              acc = __ldg(weights + d.w_off + id * d.dim + c);
+              acc = ld_table_f1<WT>(weights + d.w_off + id * d.dim + c);
               for (int l = 1; l < L; ++l) {
                 int64_t idl = __ldg(ids + s0 + l);
                 if ((uint64_t)idl >= (uint64_t)d.rows) idl = 0;
-                acc += __ldg(weights + d.w_off + idl * d.dim + c);
+                acc += ld_table_f1<WT>(weights + d.w_off + idl * d.dim + c);
               }
               if (d.pool == TZK_POOL_MEAN) acc = acc * (1.0f / (float)L);
             }
@@ -182,9 +182,9 @@ pooled_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __res
 }
 
 // one lane group per id position; f found by binary search over the key boundaries offsets[f*B]
-template <int G, int VEC>
+template <int G, int VEC, typename WT>
 __global__ void __launch_bounds__(kThreads)
-seq_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __restrict__ feat_w_off,
+seq_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restrict__ feat_w_off,
                       const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ ids,
                       const int64_t* __restrict__ offsets, int F, int B, int D, int64_t nnz,
                       float* __restrict__ out) {
@@ -209,11 +209,11 @@ seq_gather_fwd_kernel(const float* __restrict__ weights, const int64_t* __restri
     }
     int64_t id = __ldg(ids + l);
     if ((uint64_t)id >= (uint64_t)rows[lo]) id = 0;
-    const float* src = weights + w_off[lo] + id * D;
+    const WT* src = weights + w_off[lo] + id * D;
     float* dst = out + l * D;
     for (int c = lane * VEC; c < D; c += G * VEC) {
-      if (VEC == 4) st_stream_f4(dst + c, ld_row_f4(src + c));
-      else dst[c] = __ldg(src + c);
+      if (VEC == 4) st_stream_f4(dst + c, ld_table_f4<WT>(src + c));
+      else dst[c] = ld_table_f1<WT>(src + c);
     }
   }
 }
@@ -227,29 +227,29 @@ inline int pick_lanes(int max_dim, int vec) {
 
 }  // namespace
 
-#define TZK_DISPATCH_G(G_, VEC_, KERNEL, ...)                                                    \
+#define TZK_DISPATCH_G(G_, VEC_, WT_, KERNEL, ...)                                               \
   switch (G_) {                                                                                   \
-    case 1: KERNEL<1, VEC_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;                    \
-    case 2: KERNEL<2, VEC_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;                    \
-    case 4: KERNEL<4, VEC_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;                    \
-    case 8: KERNEL<8, VEC_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;                    \
-    case 16: KERNEL<16, VEC_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;                  \
-    default: KERNEL<32, VEC_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;                  \
+    case 1: KERNEL<1, VEC_, WT_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;               \
+    case 2: KERNEL<2, VEC_, WT_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;               \
+    case 4: KERNEL<4, VEC_, WT_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;               \
+    case 8: KERNEL<8, VEC_, WT_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;               \
+    case 16: KERNEL<16, VEC_, WT_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;             \
+    default: KERNEL<32, VEC_, WT_><<<grid, kThreads, smem, st>>>(__VA_ARGS__); break;             \
   }
 
-extern "C" int tzk_pooled_gather_fwd(const float* weights, const int64_t* feat_w_off,
-                                     const int64_t* feat_rows, const int32_t* feat_dim,
-                                     const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
-                                     const int64_t* offsets, int32_t F, int32_t B, int32_t max_dim,
-                                     int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream) {
+template <typename WT>
+static int pooled_gather_fwd_impl(const WT* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                  const int32_t* feat_dim, const int32_t* feat_col, const int32_t* feat_pool,
+                                  const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t max_dim,
+                                  int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream) {
   TZK_REQUIRE(F >= 0 && B >= 0, "pooled_gather_fwd: negative F/B");
   if (F == 0 || B == 0) return 0;
   TZK_REQUIRE(weights && feat_w_off && feat_rows && feat_dim && feat_col && feat_pool && offsets && out,
               "pooled_gather_fwd: NULL argument");
   TZK_REQUIRE(max_dim >= 1, "pooled_gather_fwd: max_dim < 1");
   TZK_REQUIRE(F <= 4096, "pooled_gather_fwd: F=%d > 4096 keys per collection", F);
-  const int vec = (vec_ok && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)out % 16 == 0) && (ld_out % 4 == 0))
-                      ? 4 : 1;
+  const int vec = (vec_ok && ((uintptr_t)weights % (4 * sizeof(WT)) == 0) && ((uintptr_t)out % 16 == 0) &&
+                   (ld_out % 4 == 0)) ? 4 : 1;
   const int G = pick_lanes(max_dim, vec);
   cudaStream_t st = as_stream(stream);
   const int n_tiles = (B + kTB - 1) / kTB;
@@ -258,24 +258,44 @@ extern "C" int tzk_pooled_gather_fwd(const float* weights, const int64_t* feat_w
   size_t smem = align16((size_t)F * sizeof(FeatDesc)) + (size_t)kItemsPerCta * (sizeof(BagStage) + sizeof(int32_t));
   TZK_REQUIRE(smem <= 48 * 1024, "pooled_gather_fwd: F=%d keys need %zu B of shared memory (> 48 KB)", F, smem);
   if (vec == 4) {
-    TZK_DISPATCH_G(G, 4, pooled_gather_fwd_kernel, weights, feat_w_off, feat_rows, feat_dim, feat_col,
+    TZK_DISPATCH_G(G, 4, WT, pooled_gather_fwd_kernel, weights, feat_w_off, feat_rows, feat_dim, feat_col,
                    feat_pool, ids, offsets, F, B, out, ld_out)
   } else {
-    TZK_DISPATCH_G(G, 1, pooled_gather_fwd_kernel, weights, feat_w_off, feat_rows, feat_dim, feat_col,
+    TZK_DISPATCH_G(G, 1, WT, pooled_gather_fwd_kernel, weights, feat_w_off, feat_rows, feat_dim, feat_col,
                    feat_pool, ids, offsets, F, B, out, ld_out)
   }
   TZK_CHECK_LAUNCH("pooled_gather_fwd");
   return 0;
 }
 
-extern "C" int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
-                                  const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B,
-                                  int32_t D, int64_t nnz, float* out, tzk_stream_t stream) {
+extern "C" int tzk_pooled_gather_fwd(const float* weights, const int64_t* feat_w_off,
+                                     const int64_t* feat_rows, const int32_t* feat_dim,
+                                     const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
+                                     const int64_t* offsets, int32_t F, int32_t B, int32_t max_dim,
+                                     int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream) {
+  return pooled_gather_fwd_impl<float>(weights, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool, ids, offsets, F,
+                                       B, max_dim, vec_ok, out, ld_out, stream);
+}
+
+// FP16 tables (EmbeddingBagConfig.data_type = FP16): the arena holds halfs, pooling and the output stay fp32
+extern "C" int tzk_pooled_gather_fwd_f16(const void* weights, const int64_t* feat_w_off,
+                                         const int64_t* feat_rows, const int32_t* feat_dim,
+                                         const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
+                                         const int64_t* offsets, int32_t F, int32_t B, int32_t max_dim,
+                                         int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream) {
+  return pooled_gather_fwd_impl<__half>(static_cast<const __half*>(weights), feat_w_off, feat_rows, feat_dim, feat_col,
+                                        feat_pool, ids, offsets, F, B, max_dim, vec_ok, out, ld_out, stream);
+}
+
+template <typename WT>
+static int seq_gather_fwd_impl(const WT* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                               const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t D, int64_t nnz,
+                               float* out, tzk_stream_t stream) {
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0 && D >= 1, "seq_gather_fwd: bad sizes");
   if (F == 0 || nnz == 0) return 0;
   TZK_REQUIRE(weights && feat_w_off && feat_rows && ids && offsets && out, "seq_gather_fwd: NULL argument");
   TZK_REQUIRE(F <= 2048, "seq_gather_fwd: F=%d > 2048", F);
-  const int vec = (D % 4 == 0 && ((uintptr_t)weights % 16 == 0) && ((uintptr_t)out % 16 == 0)) ? 4 : 1;
+  const int vec = (D % 4 == 0 && ((uintptr_t)weights % (4 * sizeof(WT)) == 0) && ((uintptr_t)out % 16 == 0)) ? 4 : 1;
   const int G = pick_lanes(D, vec);
   cudaStream_t st = as_stream(stream);
   const int NG = kThreads / G;
@@ -283,10 +303,23 @@ extern "C" int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_of
   int grid = blocks < kSmCountB200 * 16 ? (int)blocks : kSmCountB200 * 16;
   size_t smem = (size_t)(3 * F + 1) * sizeof(int64_t);
   if (vec == 4) {
-    TZK_DISPATCH_G(G, 4, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out)
+    TZK_DISPATCH_G(G, 4, WT, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out)
   } else {
-    TZK_DISPATCH_G(G, 1, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out)
+    TZK_DISPATCH_G(G, 1, WT, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out)
   }
   TZK_CHECK_LAUNCH("seq_gather_fwd");
   return 0;
+}
+
+extern "C" int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                  const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B,
+                                  int32_t D, int64_t nnz, float* out, tzk_stream_t stream) {
+  return seq_gather_fwd_impl<float>(weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out, stream);
+}
+
+extern "C" int tzk_seq_gather_fwd_f16(const void* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                      const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B,
+                                      int32_t D, int64_t nnz, float* out, tzk_stream_t stream) {
+  return seq_gather_fwd_impl<__half>(static_cast<const __half*>(weights), feat_w_off, feat_rows, ids, offsets, F, B, D,
+                                     nnz, out, stream);
 }

@@ -93,6 +93,10 @@ class _DimGroup:
     def __init__(self, configs: List, plan: Dict[str, TableShard], rank: int, world: int, device, pooled: bool,
                  names: List[List[str]]):
         self.configs, self.rank, self.world, self.pooled = configs, rank, world, pooled
+        from .embedding_modules import DataType
+
+        if any(getattr(c, "data_type", DataType.FP32) != DataType.FP32 for c in configs):
+            raise NotImplementedError("FP16 tables are supported on unsharded collections only")
         self.dim = configs[0].embedding_dim
         rows_local = [local_rows(c, plan[c.name], rank) for c in configs]
         cls = EmbeddingBagCollection if pooled else EmbeddingCollection

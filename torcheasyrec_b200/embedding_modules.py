@@ -149,7 +149,14 @@ class _ArenaCollection(nn.Module):
         for f, t in enumerate(feat_table):
             self._table_off[t] = self.layout.w_off[f]
             self._table_key[t] = self.layout.key_base[f]
-        self.weights = nn.Parameter(torch.empty(self.layout.arena_elems, dtype=torch.float32, device=self._device),
+        # EmbeddingBagConfig.data_type (feature.proto `data_type`, features/feature.py:626,652): FP16 tables keep their
+        # rows as halfs in the arena — half the gather bytes; pooling, outputs, gradients and optimizer state stay fp32,
+        # the update rounds the new row to nearest.  One dtype per collection.
+        kinds = {getattr(c, "data_type", DataType.FP32) for c in self._configs}
+        if len(kinds) > 1:
+            raise NotImplementedError("a collection mixes FP32 and FP16 tables: group them by data_type")
+        self.table_dtype = torch.float16 if kinds == {DataType.FP16} else torch.float32
+        self.weights = nn.Parameter(torch.empty(self.layout.arena_elems, dtype=self.table_dtype, device=self._device),
                                     requires_grad=False)
         self._opt: Optional[SparseOptimizerSpec] = None
         self.register_buffer("opt_state", None, persistent=False)
@@ -170,7 +177,13 @@ class _ArenaCollection(nn.Module):
                 w = self.table_weight(t)
                 if w.numel() == 0:
                     continue
-                (c.init_fn or (lambda x, c=c: _default_init(c, x)))(w)
+                init = c.init_fn or (lambda x, c=c: _default_init(c, x))
+                if w.dtype == torch.float32:
+                    init(w)
+                else:       # initialise in fp32 (same random stream as an FP32 table), then round once
+                    tmp = torch.empty(w.shape, dtype=torch.float32, device=w.device)
+                    init(tmp)
+                    w.copy_(tmp)
 
     def table_weight(self, t: int) -> torch.Tensor:
         o = self._table_off[t]

@@ -139,6 +139,17 @@ def _tile_path(lay: "FeatureLayout") -> bool:
     return os.environ.get("TZK_BWD_TILE", "0") == "1" and bool(lay.vec_ok) and lay.max_dim <= 128
 
 
+def _table_dtype(weights: torch.Tensor, name: str = "weights") -> bool:
+    """Validates a table arena (fp32, or fp16 for DataType.FP16 tables); returns True for halfs."""
+    if not weights.is_cuda:
+        raise TzkError(f"{name}: expected a CUDA tensor, got {weights.device} (no CPU fallback in torcheasyrec_b200)")
+    if weights.dtype not in (torch.float32, torch.float16):
+        raise TzkError(f"{name}: expected float32 or float16 tables, got {weights.dtype}")
+    if not weights.is_contiguous():
+        raise TzkError(f"{name}: expected a contiguous tensor")
+    return weights.dtype == torch.float16
+
+
 def _opt_args(optimizer: int, state, lr: float, eps: float, ex: dict):
     """tzk_opt_args (include/tzk.h) for the _ex entry points; keeps the tensors it points to alive via the caller."""
     from ._lib import TzkOptArgs
@@ -151,7 +162,7 @@ def _opt_args(optimizer: int, state, lr: float, eps: float, ex: dict):
             _need(t, torch.float32, nm)
     return TzkOptArgs(optimizer, lr, eps, float(ex.get("beta1", 0.9)), float(ex.get("beta2", 0.999)),
                       float(ex.get("weight_decay", 0.0)), float(ex.get("max_gradient", 0.0)),
-                      _ptr(state), _ptr(st2), _ptr(step))
+                      _ptr(state), _ptr(st2), _ptr(step), int(bool(ex.get("weights_f16", False))), 0)
 
 
 class CudaKernels:
@@ -189,7 +200,7 @@ class CudaKernels:
     # ------------------------------------------------------------------ K4
     def pooled_gather_fwd(self, weights: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor,
                           offsets: torch.Tensor, B: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _need(weights, torch.float32, "weights")
+        f16 = _table_dtype(weights)
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         F = lay.num_features
@@ -198,7 +209,8 @@ class CudaKernels:
         if out is None:
             out = torch.empty((B, lay.total_dim), dtype=torch.float32, device=weights.device)
         out, ld = _rows2d(out, "out")
-        check(self._lib.tzk_pooled_gather_fwd(
+        fn = self._lib.tzk_pooled_gather_fwd_f16 if f16 else self._lib.tzk_pooled_gather_fwd
+        check(fn(
             _ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim), _ptr(lay.d_col),
             _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, lay.max_dim, lay.vec_ok, _ptr(out), ld,
             _stream()), "tzk_pooled_gather_fwd")
@@ -207,7 +219,7 @@ class CudaKernels:
 
     def seq_gather_fwd(self, weights: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor,
                        offsets: torch.Tensor, B: int) -> torch.Tensor:
-        _need(weights, torch.float32, "weights")
+        f16 = _table_dtype(weights)
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         F = lay.num_features
@@ -216,9 +228,9 @@ class CudaKernels:
             raise TzkError("seq_gather_fwd: all features of an un-pooled collection must share one dim")
         nnz = ids.numel()
         out = torch.empty((nnz, D), dtype=torch.float32, device=weights.device)
-        check(self._lib.tzk_seq_gather_fwd(_ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(ids),
-                                           _ptr(offsets), F, B, D, nnz, _ptr(out), _stream()),
-              "tzk_seq_gather_fwd")
+        fn = self._lib.tzk_seq_gather_fwd_f16 if f16 else self._lib.tzk_seq_gather_fwd
+        check(fn(_ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(ids), _ptr(offsets), F, B, D, nnz, _ptr(out),
+                 _stream()), "tzk_seq_gather_fwd")
         self.launches += 1
         return out
 
@@ -227,7 +239,8 @@ class CudaKernels:
                   state: Optional[torch.Tensor], lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
                   B: int, lr: float, eps: float, grad_scale: float = 1.0, **ex) -> None:
         """`ex` (optional): state2, step, beta1, beta2, weight_decay, max_gradient -> tzk_fused_bwd_ex."""
-        _need(weights, torch.float32, "weights")
+        if _table_dtype(weights):
+            ex = dict(ex, weights_f16=True)
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         grad_out, ld = _rows2d(grad_out, "grad_out")
@@ -274,7 +287,8 @@ class CudaKernels:
     def fused_bwd_apply(self, optimizer: int, pooled: bool, grad_out: torch.Tensor, weights: torch.Tensor,
                         state: Optional[torch.Tensor], lay: FeatureLayout, offsets: torch.Tensor, nnz: int, B: int,
                         lr: float, eps: float, grad_scale: float, ws: torch.Tensor, **ex) -> None:
-        _need(weights, torch.float32, "weights")
+        if _table_dtype(weights):
+            ex = dict(ex, weights_f16=True)
         _need(offsets, torch.int64, "offsets")
         grad_out, ld = _rows2d(grad_out, "grad_out")
         if state is not None:
