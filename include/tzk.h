@@ -47,6 +47,9 @@ extern "C" {
 /* the next two only through tzk_fused_bwd_ex / tzk_fused_bwd_apply_ex (they need tzk_opt_args) */
 #define TZK_OPT_ADAM 3            /* m=b1 m+(1-b1)g ; v=b2 v+(1-b2)g*g ; w -= lr*(m^/(sqrt(v^)+eps) + wd*w)  (ADAM) */
 #define TZK_OPT_PARTIAL_ROWWISE_ADAM 4 /* m element-wise, v one value per row from mean_d(g*g)  (PARTIAL_ROWWISE_ADAM) */
+/* peer-memory step only (_ex entry points): no update — weights[row] = summed gradient of the row, ((int32*)state)[key]
+ * = 1; `weights` is then a dense per-row partial-sum buffer, not a table (see tzk_peer_small_update) */
+#define TZK_OPT_ACCUM_OUT 100
 
 /* Optimizer description for the _ex entry points (what tzrec/optim/optimizer_builder.py:30-97 passes to
  * apply_optimizer_in_backward; field names follow tzrec/protos/optimizer.proto:76-139).  Host struct, device
@@ -357,6 +360,16 @@ int tzk_peer_push_grad(const uint64_t* recv_ptrs, const float* grad, int64_t ld_
                        const int32_t* feat_pool, const int64_t* offsets, const int32_t* wire_idx, const int32_t* counts,
                        int32_t me, int32_t W, int64_t cap, int32_t B, int32_t D, int32_t pooled, tzk_stream_t stream);
 int tzk_peer_allreduce_mean(const uint64_t* src_ptrs, int32_t W, int64_t n, float* out, tzk_stream_t stream);
+/* Small tables (the mirrored ones): every rank reduces its own batch's gradients per row into a dense buffer
+ * psum [R_small, dim] + flags [R_small] (tzk_fused_bwd_apply_ex with TZK_OPT_ACCUM_OUT over a layout whose w_off / key_base
+ * address that buffer); the owner of a row then adds the W partial sums in rank order (sequential NVLink reads) and
+ * applies one update: tzk_peer_small_update.  `tabs`: device array of n_tabs records
+ * { int64 kb_small, start, w_off, psum_off, key_base; int32 first, n_local, dim, pad } — per small table: its first key
+ * in the small key space, this rank's first global row, the shard's arena offset, the table's offset in psum, the
+ * shard's local key base, the prefix sum of local rows, the local row count, the dim.  total_rows = sum of n_local. */
+int tzk_peer_small_update(const tzk_opt_args* opt, const uint64_t* psum_ptrs, const uint64_t* flag_ptrs, int32_t W,
+                          const void* tabs, int32_t n_tabs, int32_t total_rows, int32_t max_dim, float* weights,
+                          tzk_stream_t stream);
 int tzk_fused_bwd_sort_peer(const uint64_t* key_ptrs, const uint64_t* idx_ptrs, const uint64_t* count_ptrs, int32_t me,
                             int32_t W, int64_t cap, int32_t idx_span, int64_t total_keys, int32_t max_dim,
                             int32_t* overflow, void* workspace, size_t workspace_bytes, tzk_stream_t stream);

@@ -278,6 +278,8 @@ class OracleKernels:
         fill = [0] * W
         for bag in range(F * B):
             f = bag // B
+            if blocks[f] <= 0:         # feature kept off the wire (small table, reduced at the source)
+                continue
             for l in range(off[bag], off[bag + 1]):
                 i = idl[l] if 0 <= idl[l] < rows[f] else 0
                 r, loc = self._owner_of(i, blocks[f], owners[f], W)
@@ -344,7 +346,10 @@ class OracleKernels:
 
     def fused_bwd_apply(self, optimizer, pooled, grad_out, weights, state, lay, offsets, nnz, B, lr, eps, grad_scale, ws,
                         **ex):
-        """Only the slot-mode use of the peer path (after fused_bwd_sort_peer with idx_span = 0) is modelled."""
+        """Two uses of the peer path are modelled: the slot-mode update (after fused_bwd_sort_peer with idx_span = 0)
+        and the small tables' per-row gradient sums (optimizer = TZK_OPT_ACCUM_OUT after fused_bwd_sort)."""
+        if optimizer == 100:
+            return self._accum_out(pooled, grad_out, weights, state, lay, grad_scale, ws)
         assert not pooled and ws.data_ptr() in getattr(self, "_peer_sorted", {})
 
         class _Local:       # every "rank"'s gradient is the local receive buffer
@@ -445,3 +450,69 @@ class OracleKernels:
                 d_s[lo:hi] = p[lo:hi] * (dp - t)
                 d_k[lo:hi] = p[lo:hi, None] * g[b][None, :]
         return torch.from_numpy(d_s), torch.from_numpy(d_k)
+
+    # ------------------------------------------------------------------ small tables of the peer step (model)
+    def fused_bwd_sort(self, pooled, lay, ids, offsets, B, ws):
+        """Id half of the local backward: the model just remembers the ids for the gradient half."""
+        if not hasattr(self, "_local_sorted"):
+            self._local_sorted = {}
+        self._local_sorted[ws.data_ptr()] = (_np(ids).copy(), _np(offsets).copy(), B, bool(pooled))
+
+    def _accum_out(self, pooled, grad_out, psum, flags, lay, grad_scale, ws):
+        ids, off, B, _ = self._local_sorted[ws.data_ptr()]
+        g = _np(grad_out)
+        P, Fl = psum.numpy(), flags.numpy()
+        sums = {}
+        for f in range(lay.num_features):
+            if lay.rows[f] <= 0:
+                continue
+            D = lay.dim[f]
+            for bag in range(f * B, (f + 1) * B):
+                for l in range(off[bag], off[bag + 1]):
+                    i = ids[l] if 0 <= ids[l] < lay.rows[f] else 0
+                    if pooled:
+                        row = g[bag - f * B, lay.col[f]:lay.col[f] + D].astype(np.float32)
+                        sc = np.float32(grad_scale) / np.float32(off[bag + 1] - off[bag]) if lay.pool[f] == 1 \
+                            else np.float32(grad_scale)
+                    else:
+                        row, sc = g[l, :D].astype(np.float32), np.float32(grad_scale)
+                    key = lay.key_base[f] + i
+                    cur = sums.get(key)
+                    sums[key] = (row * sc if cur is None else cur[0] + row * sc, lay.w_off[f] + i * D, D)
+        for key, (acc, o, D) in sums.items():
+            P[o:o + D] = acc
+            Fl[key] = 1
+
+    def peer_small_update(self, optimizer, psum, flags, W, tabs, n_tabs, total_rows, max_dim, weights, state, lr, eps,
+                          **ex):
+        from torcheasyrec_b200.kernels import FeatureLayout
+
+        rec = np.dtype([("kb", "<i8"), ("start", "<i8"), ("w_off", "<i8"), ("psum_off", "<i8"), ("key_base", "<i8"),
+                        ("first", "<i4"), ("n", "<i4"), ("dim", "<i4"), ("pad", "<i4")])
+        T = tabs.numpy()[:n_tabs * rec.itemsize].view(rec)
+        rows_out, ids_out, lens = [], [], []
+        for t in T:
+            cnt = 0
+            for i in range(int(t["n"])):
+                key = int(t["kb"] + t["start"] + i)
+                acc, any_ = np.zeros(int(t["dim"]), np.float32), False
+                for r in range(W):
+                    if int(flags.everyone[r][key]):
+                        any_ = True
+                        o = int(t["psum_off"] + (t["start"] + i) * t["dim"])
+                        acc = acc + psum.everyone[r].numpy()[o:o + int(t["dim"])]
+                if any_:
+                    rows_out.append(acc)
+                    ids_out.append(i)
+                    cnt += 1
+            lens.append(cnt)
+        if not ids_out:
+            return
+        D = int(T[0]["dim"])
+        assert all(int(t["dim"]) == D for t in T), "model: one dim per group"
+        tl = FeatureLayout(w_off=[int(t["w_off"]) for t in T], rows=[int(t["n"]) for t in T], dim=[D] * len(T),
+                           col=[0] * len(T), pool=[0] * len(T), key_base=[int(t["key_base"]) for t in T],
+                           total_keys=1, total_dim=D, arena_elems=weights.numel())
+        bounds = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+        self.fused_bwd(optimizer, False, torch.from_numpy(np.stack(rows_out)), weights, state, tl,
+                       torch.tensor(ids_out, dtype=torch.int64), bounds, 1, lr, eps, 1.0, **ex)

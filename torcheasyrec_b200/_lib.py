@@ -110,6 +110,7 @@ SIGNATURES = {
     "tzk_peer_push_grad": (
         c_int32, [P, P, c_int64, P, P, P, P, P, c_int32, c_int32, c_int64, c_int32, c_int32, c_int32, P]),
     "tzk_peer_allreduce_mean": (c_int32, [P, c_int32, c_int64, P, P]),
+    "tzk_peer_small_update": (c_int32, [P, P, P, c_int32, P, c_int32, c_int32, c_int32, P, P]),
     "tzk_fused_bwd_sort_peer": (
         c_int32, [P, P, P, c_int32, c_int32, c_int64, c_int32, c_int64, c_int32, P, P, c_size_t, P]),
     "tzk_fused_bwd_apply_peer": (

@@ -23,6 +23,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kShortRun = 32;
 
+// TZK_OPT_ACCUM_OUT (include/tzk.h): do not update — store the summed row gradient in `weights` (a dense per-row buffer)
+// and raise `state[key]` (int32 flags): the source-side half of "reduce small tables locally, exchange per-row partial
+// sums" (tzk_peer_small_update is the owner-side half)
 struct BwdFeat {
   int64_t w_off;
   int64_t rows;
@@ -64,7 +67,7 @@ struct PeerGrads { unsigned long long p[16]; };
 
 __device__ __forceinline__ void init_bias_correction(BwdArgs& a) {
   a.bc1 = a.bc2 = 1.f;
-  if (a.optimizer >= TZK_OPT_ADAM) {
+  if (a.optimizer == TZK_OPT_ADAM || a.optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM) {
     const float t = a.step ? __ldg(a.step) : 1.f;
     a.bc1 = 1.f - powf(a.beta1, t);
     a.bc2 = 1.f - powf(a.beta2, t);
@@ -308,7 +311,7 @@ __device__ __forceinline__ float clip_grad(const BwdArgs& a, float g) {
   return a.max_gradient > 0.f ? fminf(fmaxf(g, -a.max_gradient), a.max_gradient) : g;
 }
 __device__ __forceinline__ bool has_elem_state(const BwdArgs& a) {   // first state laid out like the weights
-  return a.optimizer == TZK_OPT_ADAGRAD || a.optimizer >= TZK_OPT_ADAM;
+  return a.optimizer == TZK_OPT_ADAGRAD || a.optimizer == TZK_OPT_ADAM || a.optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM;
 }
 // per-row denominator of the row-wise variants; `ss` = sum over the row of g^2 (already reduced over the lane group),
 // lane 0 of the group owns the state element
@@ -357,6 +360,18 @@ __device__ __forceinline__ float group_sum(float v) {
 template <int G, int VEC, int CH>
 __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, int64_t row, int64_t key,
                                            float (&acc)[CH][VEC], int lane) {
+  if (a.optimizer == TZK_OPT_ACCUM_OUT) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = (ch * G + lane) * VEC;
+      if (c >= d.dim) continue;
+      float* wp = a.weights + d.w_off + row * d.dim + c;
+      if (VEC == 4) *reinterpret_cast<float4*>(wp) = make_float4(acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
+      else wp[0] = acc[ch][0];
+    }
+    if (lane == 0) reinterpret_cast<int32_t*>(a.state)[key] = 1;
+    return;
+  }
   if (a.max_gradient > 0.f) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
@@ -1047,8 +1062,8 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   const int32_t optimizer = opt.optimizer;
   float* state = opt.state;
   const float lr = opt.lr, eps = opt.eps;
-  TZK_REQUIRE(optimizer >= 0 && optimizer <= TZK_OPT_PARTIAL_ROWWISE_ADAM, "fused_bwd: unknown optimizer %d",
-              optimizer);
+  TZK_REQUIRE((optimizer >= 0 && optimizer <= TZK_OPT_PARTIAL_ROWWISE_ADAM) || optimizer == TZK_OPT_ACCUM_OUT,
+              "fused_bwd: unknown optimizer %d", optimizer);
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0, "fused_bwd: negative size");
   if (F == 0 || B == 0 || nnz == 0) return 0;
   TZK_REQUIRE(nnz < ((int64_t)1 << 31) && (int64_t)F * std::max(B, 1) < ((int64_t)1 << 31),
@@ -1060,7 +1075,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
                 "fused_bwd: NULL argument");
     TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
     TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
-    TZK_REQUIRE(optimizer < TZK_OPT_ADAM || (opt.state2 && opt.step),
+    TZK_REQUIRE((optimizer != TZK_OPT_ADAM && optimizer != TZK_OPT_PARTIAL_ROWWISE_ADAM) || (opt.state2 && opt.step),
                 "fused_bwd: Adam variants need state2 and the device step counter");
   }
   TZK_REQUIRE(F <= 2048, "fused_bwd: F=%d > 2048 keys per collection", F);
@@ -1161,7 +1176,8 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   const int vec = (vec_ok && peers_aligned && ((uintptr_t)weights % (a.w_f16 ? 8 : 16) == 0) &&
                    ((uintptr_t)a.grad_out % 16 == 0) &&
                    (ld_grad % 4 == 0) &&
-                   (!(optimizer == TZK_OPT_ADAGRAD || optimizer >= TZK_OPT_ADAM) || (uintptr_t)state % 16 == 0) &&
+                   (!(optimizer == TZK_OPT_ADAGRAD || optimizer == TZK_OPT_ADAM ||
+                      optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM) || (uintptr_t)state % 16 == 0) &&
                    (optimizer != TZK_OPT_ADAM || (uintptr_t)opt.state2 % 16 == 0))
                       ? 4 : 1;
   int need = (max_dim + vec - 1) / vec;  // chunks per row
@@ -1177,7 +1193,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   // way — and the general kernels execute fewer instructions (74 M vs 87 M warp-instructions) without the three
   // barriers per tile, so they stay the default.
   const char* tile_env = getenv("TZK_BWD_TILE");
-  const bool tile_path = tile_env && tile_env[0] == '1' && !a.w_f16;   // (the tile kernels are fp32-table only)
+  const bool tile_path = tile_env && tile_env[0] == '1' && !a.w_f16 && optimizer != TZK_OPT_ACCUM_OUT;   // (fp32 tables, real updates)
   if (vec == 4 && ch == 1 && tile_path) {
     // tile path: every gradient / weight / state row of a tile is requested at once, runs are reduced in shared memory
     float* carry_first = reinterpret_cast<float*>(ws + L.carry);
@@ -1303,6 +1319,103 @@ extern "C" int tzk_fused_bwd_apply_ex(const tzk_opt_args* opt, int32_t pooled, c
   return fused_bwd_impl(2, *opt, pooled, grad_out, ld_grad, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool,
                         feat_key_base, nullptr, offsets, F, B, nnz, total_keys, max_dim, vec_ok, weights, grad_scale,
                         workspace, workspace_bytes, stream);
+}
+
+// ---- owner side of the small-table exchange ----------------------------------------------------------------------------
+// Every rank reduced its own batch's gradients of the small tables into a dense per-row buffer psum_r [R_small, dim]
+// (+ flags_r [R_small]: row touched this step) in symmetric memory.  The owner of a row adds the W partial sums in rank
+// order — long sequential NVLink reads, a few MB in all — and applies ONE optimizer update to its arena row.
+struct SmallTab {
+  int64_t kb_small;    // key of the table's first row in the small key space (= row index into psum / flags)
+  int64_t start;       // global row of this rank's first local row
+  int64_t w_off;       // local arena offset of the shard
+  int64_t psum_off;    // element offset of the table in psum
+  int64_t key_base;    // local linearised key of the shard's first row (row-wise optimizer state)
+  int32_t first;       // prefix sum of local rows over the small tables
+  int32_t n_local;
+  int32_t dim;
+  int32_t pad;
+};
+struct SmallPeers { unsigned long long psum[16], flags[16]; };
+
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+small_table_update_kernel(BwdArgs a, const __grid_constant__ SmallPeers sp, const SmallTab* __restrict__ tabs, int n_tabs,
+                          int total_rows, int W) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallTab* st = reinterpret_cast<SmallTab*>(smem_raw);
+  for (int i = threadIdx.x; i < n_tabs; i += blockDim.x) st[i] = tabs[i];
+  __syncthreads();
+  init_bias_correction(a);
+  constexpr int NG = kThreads / G;
+  const int lane = threadIdx.x % G;
+  for (int j = blockIdx.x * NG + threadIdx.x / G; j < total_rows; j += gridDim.x * NG) {
+    int lo = 0, hi = n_tabs;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (st[mid].first <= j) lo = mid; else hi = mid;
+    }
+    const SmallTab t = st[lo];
+    const int64_t i = j - t.first;                      // local row
+    const int64_t key_s = t.kb_small + t.start + i;     // row in the small key space
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    bool any = false;
+    const int c = lane * 4;
+    for (int r = 0; r < W; ++r) {                       // rank order: the same sum on every run
+      if (reinterpret_cast<const int32_t*>(sp.flags[r])[key_s]) {
+        any = true;
+        if (c < t.dim) {
+          const float4 v = ld_coh_f4(reinterpret_cast<const float*>(sp.psum[r]) + t.psum_off + (t.start + i) * t.dim + c);
+          acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+        }
+      }
+    }
+    if (!any) continue;                                 // (group-uniform: every lane read the same flags)
+    BwdFeat d;
+    d.w_off = t.w_off; d.rows = t.n_local; d.key_base = t.key_base; d.dim = t.dim; d.col = 0; d.pool = 0; d.pad = 0;
+    finish_run<G, 4, 1>(a, d, i, t.key_base + i, acc, lane);
+  }
+}
+
+// psum_ptrs / flag_ptrs: HOST arrays [W] of device addresses (rank r's partial-sum buffer / flags as mapped here).
+// tabs: device array of n_tabs descriptors {kb_small, start, w_off, psum_off, key_base, first, n_local, dim} (int64 x5,
+// int32 x4 — struct SmallTab); total_rows = sum of n_local.  Dims must be multiples of 4 and <= 128.
+extern "C" int tzk_peer_small_update(const tzk_opt_args* opt, const uint64_t* psum_ptrs, const uint64_t* flag_ptrs,
+                                     int32_t W, const void* tabs, int32_t n_tabs, int32_t total_rows, int32_t max_dim,
+                                     float* weights, tzk_stream_t stream) {
+  TZK_REQUIRE(opt && psum_ptrs && flag_ptrs && W >= 1 && W <= 16 && n_tabs >= 0 && total_rows >= 0,
+              "peer_small_update: bad argument");
+  if (n_tabs == 0 || total_rows == 0) return 0;
+  TZK_REQUIRE(tabs && weights && max_dim >= 4 && max_dim <= 128 && max_dim % 4 == 0 && n_tabs <= 1024,
+              "peer_small_update: dims must be multiples of 4 and <= 128");
+  TZK_REQUIRE(opt->optimizer >= 0 && opt->optimizer <= TZK_OPT_PARTIAL_ROWWISE_ADAM && !opt->weights_f16,
+              "peer_small_update: unsupported optimizer");
+  TZK_REQUIRE(opt->optimizer == TZK_OPT_SGD || opt->state, "peer_small_update: optimizer state is NULL");
+  BwdArgs a;
+  a.grad_out = nullptr; a.ld_grad = 0; a.offsets = nullptr; a.weights = weights; a.state = opt->state;
+  a.lr = opt->lr; a.eps = opt->eps; a.grad_scale = 1.f; a.F = 0; a.B = 1; a.optimizer = opt->optimizer; a.pooled = 0;
+  a.n = total_rows; a.sentinel = 0; a.state2 = opt->state2; a.step = opt->step; a.beta1 = opt->beta1; a.beta2 = opt->beta2;
+  a.weight_decay = opt->weight_decay; a.max_gradient = opt->max_gradient; a.bc1 = a.bc2 = 1.f;
+  a.peer_w = 0; a.idx_span = 1; a.w_f16 = 0; a.pad2 = 0;
+  SmallPeers sp;
+  for (int r = 0; r < 16; ++r) { sp.psum[r] = r < W ? psum_ptrs[r] : 0ull; sp.flags[r] = r < W ? flag_ptrs[r] : 0ull; }
+  int G = 1;
+  while (G * 4 < max_dim) G <<= 1;
+  const int NG = kThreads / G;
+  const int grid = (int)std::min<int64_t>(ceil_div64(total_rows, NG), kSmCountB200 * 8);
+  const size_t smem = (size_t)n_tabs * sizeof(SmallTab);
+  cudaStream_t st = as_stream(stream);
+  const SmallTab* tp = static_cast<const SmallTab*>(tabs);
+  switch (G) {
+    case 1: small_table_update_kernel<1><<<grid, kThreads, smem, st>>>(a, sp, tp, n_tabs, total_rows, W); break;
+    case 2: small_table_update_kernel<2><<<grid, kThreads, smem, st>>>(a, sp, tp, n_tabs, total_rows, W); break;
+    case 4: small_table_update_kernel<4><<<grid, kThreads, smem, st>>>(a, sp, tp, n_tabs, total_rows, W); break;
+    case 8: small_table_update_kernel<8><<<grid, kThreads, smem, st>>>(a, sp, tp, n_tabs, total_rows, W); break;
+    case 16: small_table_update_kernel<16><<<grid, kThreads, smem, st>>>(a, sp, tp, n_tabs, total_rows, W); break;
+    default: small_table_update_kernel<32><<<grid, kThreads, smem, st>>>(a, sp, tp, n_tabs, total_rows, W); break;
+  }
+  TZK_CHECK_LAUNCH("small_table_update_kernel");
+  return 0;
 }
 
 static int fill_wire(PeerWire* pw, const uint64_t* key_ptrs, const uint64_t* idx_ptrs, const uint64_t* count_ptrs,

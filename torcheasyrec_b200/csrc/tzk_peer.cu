@@ -295,6 +295,7 @@ peer_bkt_count_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict
     const int64_t bag = bag0 + k;
     if (bag >= n_bags) break;
     const BktFeat d = fd[(uint32_t)bag / (uint32_t)B];
+    if (d.block <= 0) continue;        // feature kept off the wire (small table: its gradient is reduced at the source)
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     for (int64_t l = s; l < e; ++l) {
       int64_t id = __ldg(ids + l), loc;
@@ -363,6 +364,7 @@ peer_bkt_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restri
     const int64_t bag = bag0 + k;
     if (bag >= n_bags) break;
     const BktFeat d = fd[(uint32_t)bag / (uint32_t)B];
+    if (d.block <= 0) continue;
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     for (int64_t l = s; l < e; ++l) {
       int64_t id = __ldg(ids + l), loc;
@@ -403,6 +405,7 @@ peer_bkt_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restri
     if (bag >= n_bags) break;
     const int f = (int)((uint32_t)bag / (uint32_t)B);
     const BktFeat d = fd[f];
+    if (d.block <= 0) continue;
     const int64_t s = __ldg(offsets + bag), e = __ldg(offsets + bag + 1);
     for (int64_t l = s; l < e; ++l) {
       int64_t id = __ldg(ids + l), loc;

@@ -18,6 +18,7 @@ from ._lib import TzkError, check, lib
 
 POOL_SUM, POOL_MEAN = 0, 1
 OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM = 0, 1, 2, 3, 4
+OPT_ACCUM_OUT = 100      # peer-memory step: per-row gradient sums into a dense buffer instead of an update
 
 
 @dataclass
@@ -155,7 +156,7 @@ def _opt_args(optimizer: int, state, lr: float, eps: float, ex: dict):
     from ._lib import TzkOptArgs
 
     st2, step = ex.get("state2"), ex.get("step")
-    if optimizer >= OPT_ADAM and (st2 is None or step is None):
+    if optimizer in (OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM) and (st2 is None or step is None):
         raise TzkError("Adam variants need state2 and the device step counter")
     for t, nm in ((st2, "state2"), (step, "step")):
         if t is not None:
@@ -291,7 +292,10 @@ class CudaKernels:
             ex = dict(ex, weights_f16=True)
         _need(offsets, torch.int64, "offsets")
         grad_out, ld = _rows2d(grad_out, "grad_out")
-        if state is not None:
+        if optimizer == OPT_ACCUM_OUT:
+            _need(state, torch.int32, "state (row flags)")
+            ex = dict(ex, max_gradient=0.0)             # -> the _ex entry point
+        elif state is not None:
             _need(state, torch.float32, "state")
         if ex:
             oa = _opt_args(optimizer, state, lr, eps, ex)
@@ -523,6 +527,16 @@ class CudaKernels:
     def peer_allreduce_mean(self, srcs, W: int, n: int, out: torch.Tensor) -> None:
         _need(out, torch.float32, "out")
         check(self._lib.tzk_peer_allreduce_mean(srcs.ptrs, W, n, _ptr(out), _stream()), "tzk_peer_allreduce_mean")
+        self.launches += 1
+
+    def peer_small_update(self, optimizer: int, psum, flags, W: int, tabs: torch.Tensor, n_tabs: int, total_rows: int,
+                          max_dim: int, weights: torch.Tensor, state: Optional[torch.Tensor], lr: float, eps: float,
+                          **ex) -> None:
+        """Owner side of the small-table exchange (see tzk_peer_small_update): psum / flags are symmetric buffers."""
+        _need(weights, torch.float32, "weights")
+        oa = _opt_args(optimizer, state, lr, eps, ex)
+        check(self._lib.tzk_peer_small_update(ctypes.byref(oa), psum.ptrs, flags.ptrs, W, _ptr(tabs), n_tabs, total_rows,
+                                              max_dim, _ptr(weights), _stream()), "tzk_peer_small_update")
         self.launches += 1
 
     def fused_bwd_sort_peer(self, wire_key, wire_idx, counts, me: int, W: int, cap: int, idx_span: int,

@@ -172,13 +172,16 @@ class PeerState(PeerBase):
         n = g.local.weights.numel()
         self.tables.t[:n].copy_(g.local.weights.data)
         g.local.weights.data = self.tables.t[:n]
+        self.bwd_mode = os.environ.get("TZK_PEER_BWD", "push")
         self._init_mirror(plan, per_rank)
         # id budget per step: one id per bag unless the caller knows better (sequence features: B * sequence_length)
         per_f = list(ids_per_feature) if ids_per_feature is not None else [self.B] * F
         self.max_nnz = int(sum(per_f))
         self.idx_span = F * self.B if self.pooled else max(self.max_nnz, 1)
-        self.cap = (int(alpha * expected_load(g, plan, per_f)) + 8) // 8 * 8
-        self.cap = min(self.cap, (self.max_nnz + 8) // 8 * 8)          # a destination never gets more than everything
+        self._init_small_bwd(plan, per_rank)
+        wire_f = [0 if (self.small is not None and self.small["is_small"][f]) else n for f, n in enumerate(per_f)]
+        self.cap = (int(alpha * expected_load(g, plan, wire_f)) + 8) // 8 * 8
+        self.cap = min(self.cap, (int(sum(wire_f)) + 8) // 8 * 8)     # a destination never gets more than everything
         assert W * self.idx_span < 2 ** 31 and W * self.cap < 2 ** 31
         g.static_nnz, g.static_cap = self.max_nnz, self.cap
         self.wire_key = self._alloc(W * self.cap, torch.int64)
@@ -187,7 +190,6 @@ class PeerState(PeerBase):
         # backward transport: "push" (default) = every source writes its gradient slices into the owners' receive
         # buffers in wire order (coalesced NVLink writes, the update then runs on local memory); "pull" = the sources
         # publish their gradient and the owners' update kernels read the 64-B slices over NVLink in place
-        self.bwd_mode = os.environ.get("TZK_PEER_BWD", "push")
         if self.bwd_mode == "push":
             self.recv = self._alloc(W * self.cap * g.dim, torch.float32)
             self._dummy_off = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -210,6 +212,7 @@ class PeerState(PeerBase):
         thr = int(os.environ.get("TZK_PEER_MIRROR_ROWS", "65536"))
         self.mirror = None
         self.feat_mirror_off = None
+        self._m_off = {}
         if thr <= 0 or self.W == 1:
             return
         m_off, o = {}, 0
@@ -234,10 +237,71 @@ class PeerState(PeerBase):
                     seg_src.append(per_rank[r].w_off[first_feat[t]])
                     seg_dst.append(base + start * c.embedding_dim)
                     seg_n.append(n * c.embedding_dim)
+        self._m_off = m_off
         self.mirror = torch.zeros(max(o, 4), dtype=torch.float32, device=dev)
         self.feat_mirror_off = torch.tensor([m_off.get(t, -1) for t in g.local._feat_table], dtype=torch.int64, device=dev)
         self._seg = (torch.tensor(seg_rank, dtype=torch.int32, device=dev), torch.tensor(seg_src, dtype=torch.int64, device=dev),
                      torch.tensor(seg_dst, dtype=torch.int64, device=dev), torch.tensor(seg_n, dtype=torch.int64, device=dev))
+
+    def _init_small_bwd(self, plan, per_rank) -> None:
+        """Backward of the mirrored (small) tables: every rank reduces its OWN batch's gradients per row into a dense
+        symmetric buffer (the fused backward's sort + run kernels with TZK_OPT_ACCUM_OUT), the owners add the W
+        partial sums in rank order and update (tzk_peer_small_update).  69 % of Criteo's gradient rows never cross
+        NVLink; what crosses is a few MB of sequential reads.  TZK_PEER_SMALL_BWD=0 sends every row over the wire."""
+        import numpy as np
+
+        from .distributed import local_rows
+        from .kernels import FeatureLayout
+
+        g, dev = self.g, self.device
+        self.small = None
+        self.feat_block_wire = g.feat_block
+        lay = g.local.layout
+        if (self.mirror is None or self.bwd_mode != "push" or os.environ.get("TZK_PEER_SMALL_BWD", "1") == "0"
+                or any(d % 4 or d > 128 for d in lay.dim) or not lay.vec_ok):
+            return
+        m_off = self._m_off
+        kb, k = {}, 0
+        for t in sorted(m_off, key=lambda t: m_off[t]):
+            kb[t] = k
+            k += g.configs[t].num_embeddings
+        ft = g.local._feat_table
+        is_small = [t in m_off for t in ft]
+        sl = FeatureLayout(
+            w_off=[m_off.get(t, 0) for t in ft], rows=[g.configs[t].num_embeddings if t in m_off else 0 for t in ft],
+            dim=list(lay.dim), col=list(lay.col), pool=list(lay.pool), key_base=[kb.get(t, -1) for t in ft],
+            total_keys=max(k, 1), total_dim=lay.total_dim, arena_elems=self.mirror.numel()).to(dev)
+        rec = np.dtype([("kb", "<i8"), ("start", "<i8"), ("w_off", "<i8"), ("psum_off", "<i8"), ("key_base", "<i8"),
+                        ("first", "<i4"), ("n", "<i4"), ("dim", "<i4"), ("pad", "<i4")])
+        first_feat = {}
+        for f, t in enumerate(ft):
+            first_feat.setdefault(t, f)
+        rows, first = [], 0
+        for t in sorted(m_off, key=lambda t: m_off[t]):
+            c = g.configs[t]
+            sh = plan[c.name]
+            n = local_rows(c, sh, self.me)
+            if n:
+                start = 0 if sh.kind == "table_wise" else self.me * sh.block
+                f = first_feat[t]
+                rows.append((kb[t], start, lay.w_off[f], m_off[t], lay.key_base[f], first, n, c.embedding_dim, 0))
+                first += n
+        tabs = np.array(rows, dtype=rec) if rows else np.zeros(0, dtype=rec)
+        blk = g.feat_block.clone()
+        blk[torch.tensor(is_small, device=dev)] = 0
+        self.feat_block_wire = blk
+        self.small = dict(
+            is_small=is_small, layout=sl, n_tabs=len(rows), total_rows=first,
+            tabs=torch.from_numpy(tabs.view(np.uint8).copy()).to(dev) if rows else torch.zeros(8, dtype=torch.uint8, device=dev),
+            psum=self._alloc(self.mirror.numel(), torch.float32), flags=self._alloc(max(k, 1), torch.int32), ws=None)
+
+    def _small_ws(self, nnz: int) -> torch.Tensor:
+        k = Fn.backend()
+        need = k.fused_bwd_workspace_bytes(self.small["layout"], max(nnz, self.max_nnz))
+        ws = self.small["ws"]
+        if ws is None or ws.numel() < need:
+            ws = self.small["ws"] = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        return ws
 
     # ---- forward ---------------------------------------------------------------------------------------------------
     def gather(self, ids: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
@@ -267,8 +331,11 @@ class PeerState(PeerBase):
         def run():
             if self._prep_pending:            # a forward pass without a backward: peers may still be pulling
                 self._barrier(self.site_c)
-            k.peer_bucketize(ids, offsets, g.F, self.B, self.W, g.feat_block, g.feat_owner, self.feat_rows,
+            k.peer_bucketize(ids, offsets, g.F, self.B, self.W, self.feat_block_wire, g.feat_owner, self.feat_rows,
                              self.rf_key_base, self.pooled, self.cap, self.wire_key.t, self.wire_idx.t, self.counts.t)
+            if self.small is not None:        # small tables: this rank's own ids, sorted by (table, row)
+                self.small["flags"].t.zero_()
+                k.fused_bwd_sort(self.pooled, self.small["layout"], ids, offsets, self.B, self._small_ws(ids.numel()))
             self._barrier(self.site_a)
             k.fused_bwd_sort_peer(self.wire_key, self.wire_idx, self.counts, self.me, self.W, self.cap,
                                   0 if self.bwd_mode == "push" else self.idx_span, g.local.layout, g.overflow,
@@ -288,6 +355,15 @@ class PeerState(PeerBase):
             raise RuntimeError("peer exchange: backward without the forward pass's id exchange")
         lay = g.local.layout
         push = self.bwd_mode == "push"
+        sm = self.small
+        if sm is not None:                    # per-row sums of this rank's gradients of the small tables (1/W folded in)
+            from .kernels import OPT_ACCUM_OUT
+
+            gr = grad if self.pooled else grad.reshape(-1, g.dim)
+            nnz = int(self._keep[0].numel()) if self._keep is not None else 0
+            if nnz:
+                k.fused_bwd_apply(OPT_ACCUM_OUT, self.pooled, gr, sm["psum"].t, sm["flags"].t, sm["layout"], offsets, nnz,
+                                  self.B, 0.0, 0.0, 1.0 / self.W, self._small_ws(nnz))
         if push:
             if not self.pooled:
                 grad = grad.reshape(-1, g.dim)
@@ -307,6 +383,10 @@ class PeerState(PeerBase):
                 k.fused_bwd_apply(spec.kind, False, self.recv.t.view(self.W * self.cap, g.dim), g.local.weights.data,
                                   g.local.opt_state, lay, self._dummy_off, self.W * self.cap, 1, spec.lr, spec.eps,
                                   1.0 / self.W, self._workspace(), **extras)
+                if sm is not None and sm["total_rows"]:
+                    k.peer_small_update(spec.kind, sm["psum"], sm["flags"], self.W, sm["tabs"], sm["n_tabs"],
+                                        sm["total_rows"], lay.max_dim, g.local.weights.data, g.local.opt_state, spec.lr,
+                                        spec.eps, **extras)
             else:
                 k.fused_bwd_apply_peer(spec.kind, self.pooled, self.grad, ld, g.local.weights.data, g.local.opt_state,
                                        lay, self.B, self.me, self.W, self.cap, self.idx_span, spec.lr, spec.eps,
