@@ -82,7 +82,8 @@ def parse_args():
     ap.add_argument("--sharded-mode", default="auto", choices=["auto", "graph", "eager"],
                     help="N>1: 'graph' = fixed-capacity exchange captured in one CUDA graph, 'eager' = step by step "
                          "(auto: graph unless the model has sequence features)")
-    ap.add_argument("--static-capacity", type=float, default=1.5)
+    ap.add_argument("--static-capacity", type=float, default=1.25,
+                    help="head-room of the fixed-capacity wire buffers over the expected ids per destination")
     ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="sharded runs: the peer-memory kernels of csrc/tzk_peer.cu (default), or NCCL all-to-alls")
     ap.add_argument("--sharding", default="row_wise", choices=["row_wise", "table_wise", "mixed"],
