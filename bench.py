@@ -89,6 +89,8 @@ def parse_args():
     ap.add_argument("--sharding", default="row_wise", choices=["row_wise", "table_wise", "mixed"],
                     help="placement of the tables at N>1 (BASELINE configs: dlrm row_wise, deepfm table_wise, mmoe mixed)")
     ap.add_argument("--rw-min-rows", type=int, default=200000, help="mixed: tables with at least this many rows go row-wise")
+    ap.add_argument("--trace", default="", help="after the timed runs: chrome trace of 3 steps of rank 0 (torch.profiler) "
+                                                "written to this path — diagnosis only, never a reported number")
     ap.add_argument("--no-verify", action="store_true",
                     help="N>1: skip the in-process parity check of the sharded step against its unsharded twin")
     ap.add_argument("--force-sharded", action="store_true",
@@ -426,6 +428,22 @@ def run_ours(args):
         zipf = z0.elapsed_time(z1)
         del zring
     clk = clocks.stop() if clocks else None
+    if args.trace:             # kernel timeline of a few steps (all ranks step, rank 0 records)
+        from torch.profiler import ProfilerActivity, profile
+
+        barrier()
+        if rank == 0:
+            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+                for i in range(3):
+                    step.load(ring[i % len(ring)])
+                    step.replay()
+                torch.cuda.synchronize()
+            prof.export_chrome_trace(args.trace)
+        else:
+            for i in range(3):
+                step.load(ring[i % len(ring)])
+                step.replay()
+        barrier()
     pipe.check_overflow()      # fixed-capacity exchange: no peer needed more than its wire capacity
     if world > 1:
         import torch.distributed as dist
