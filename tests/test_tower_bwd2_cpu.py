@@ -36,7 +36,7 @@ def tower(tmp_path_factory):
     return L
 
 
-@pytest.mark.parametrize("K,N", [(13, 64), (64, 16), (64, 32), (32, 1), (64, 64), (7, 3), (16, 2), (60, 4)])
+@pytest.mark.parametrize("K,N", [(13, 64), (64, 16), (64, 32), (32, 1), (64, 64), (7, 3), (16, 2), (60, 4), (64, 30), (33, 17)])
 @pytest.mark.parametrize("M,relu,pad", [(1, 1, 0), (300, 1, 0), (300, 0, 0), (77, 1, 3)])
 def test_small_linear_bwd2_source_matches_numpy(tower, K, N, M, relu, pad):
     """The four DLRM tower shapes (13->64, 64->16, 64->32, 32->1), the 128-thread limit case 64x64 (NB x KB = 4 x 8) and
@@ -69,11 +69,45 @@ def test_small_linear_bwd2_source_matches_numpy(tower, K, N, M, relu, pad):
     np.testing.assert_array_equal(db, db2)
 
 
-def test_small_linear_bwd2_rejects_what_it_cannot_map(tower):
-    # N = 30 is not a multiple of 4 -> NB = 1 -> 30 x 8 = 240 threads per row group > 128: the caller keeps the library kernel
-    M, K, N = 8, 64, 30
-    z = np.zeros((M, 64), dtype=np.float32)
-    ws = np.zeros(1 << 16, dtype=np.float32)
-    rc = tower.tzk_small_linear_bwd2(_p(z), K, _p(z), _p(z), N, _p(z), N, M, K, N, 0, None, 0, _p(z), _p(z), _p(ws),
-                                     ws.nbytes, None)
-    assert rc == 4
+@pytest.mark.parametrize("K,N,pad", [(64, 32, 0), (13, 64, 1)])
+def test_small_linear_dw_tiles_several_tiles_per_cta(tower, K, N, pad):
+    """M > 592 x 32 rows: every CTA walks two tiles (32 rows + a short one) through both shared-memory stages."""
+    M = 19500
+    rng = np.random.default_rng(K + N)
+    x = rng.standard_normal((M, K + pad)).astype(np.float32)
+    w = rng.standard_normal((N, K)).astype(np.float32)
+    y = rng.standard_normal((M, N + pad)).astype(np.float32)
+    dy = rng.standard_normal((M, N + pad)).astype(np.float32)
+    dw = np.full((N, K), np.nan, dtype=np.float32)
+    db = np.full(N, np.nan, dtype=np.float32)
+    nb = tower.tzk_small_linear_bwd2_workspace_bytes(M, K, N)
+    ws = np.zeros(nb // 4 + 1, dtype=np.float32)
+    rc = tower.tzk_small_linear_bwd2(_p(x), K + pad, _p(w), _p(y), N + pad, _p(dy), N + pad, M, K, N, 1, None, 0, _p(dw),
+                                     _p(db), _p(ws), nb, None)
+    assert rc == 0
+    dz = dy[:, :N].astype(np.float64) * (y[:, :N] > 0)
+    np.testing.assert_allclose(dw, dz.T @ x[:, :K].astype(np.float64), rtol=2e-5, atol=2e-3)
+    np.testing.assert_allclose(db, dz.sum(0), rtol=2e-5, atol=2e-3)
+
+
+def test_small_linear_bwd2_row_group_kernel_still_matches(tower, monkeypatch):
+    """TZK_SMALL_LINEAR_DW=0 keeps the row-group dW kernel selectable for A/B timing; 64 x 30 (which it cannot map) falls
+    through to the tile kernel."""
+    monkeypatch.setenv("TZK_SMALL_LINEAR_DW", "0")
+    rng = np.random.default_rng(5)
+    for K, N in ((64, 32), (64, 30)):
+        M = 200
+        x = rng.standard_normal((M, K)).astype(np.float32)
+        w = rng.standard_normal((N, K)).astype(np.float32)
+        y = rng.standard_normal((M, N)).astype(np.float32)
+        dy = rng.standard_normal((M, N)).astype(np.float32)
+        dw = np.full((N, K), np.nan, dtype=np.float32)
+        db = np.full(N, np.nan, dtype=np.float32)
+        nb = tower.tzk_small_linear_bwd2_workspace_bytes(M, K, N)
+        ws = np.zeros(nb // 4 + 1, dtype=np.float32)
+        rc = tower.tzk_small_linear_bwd2(_p(x), K, _p(w), _p(y), N, _p(dy), N, M, K, N, 1, None, 0, _p(dw), _p(db), _p(ws),
+                                         nb, None)
+        assert rc == 0
+        dz = dy.astype(np.float64) * (y > 0)
+        np.testing.assert_allclose(dw, dz.T @ x.astype(np.float64), rtol=2e-5, atol=2e-4)
+        np.testing.assert_allclose(db, dz.sum(0), rtol=2e-5, atol=2e-4)
