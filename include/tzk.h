@@ -69,7 +69,11 @@ typedef struct tzk_opt_args {
   const float* step;
   int32_t weights_f16; /* 1: `weights` points to an arena of IEEE halfs (EmbeddingBagConfig.data_type = FP16,
                         * tzrec/protos/feature.proto data_type): rows are widened to fp32, updated, rounded to nearest */
-  int32_t reserved;
+  int32_t interleaved; /* 1 (fp32 tables, TZK_OPT_ADAGRAD): `weights` holds [weight row | accumulator row] back to back, row
+                        * stride 2 * D_f elements (feat_w_off in those units): a D = 16 row and its state share one 128-B
+                        * line, so the update reads and writes whole lines (two half-line writes cost a read-modify-write
+                        * each in DRAM: profiles/README.md).  `state` is ignored.  Lookups over such an arena:
+                        * tzk_pooled_gather_fwd_strided / tzk_seq_gather_fwd_strided. */
 } tzk_opt_args;
 
 typedef void* tzk_stream_t; /* cudaStream_t */
@@ -107,6 +111,18 @@ int tzk_pooled_gather_fwd(const float* weights, const int64_t* feat_w_off, const
 int tzk_seq_gather_fwd(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
                        const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t D,
                        int64_t nnz, float* out, tzk_stream_t stream);
+
+/* ---- strided tables: rows of feature f's table are feat_stride[f] >= D_f elements apart (NULL: dense rows) — the
+ * interleaved [weight row | optimizer-state row] arena of tzk_opt_args.interleaved.  vec_ok additionally promises
+ * that every stride is a multiple of 4.  Same reference call sites as K4 / K4-nobag above. */
+int tzk_pooled_gather_fwd_strided(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                  const int32_t* feat_dim, const int32_t* feat_stride, const int32_t* feat_col,
+                                  const int32_t* feat_pool, const int64_t* ids, const int64_t* offsets, int32_t F,
+                                  int32_t B, int32_t max_dim, int32_t vec_ok, float* out, int64_t ld_out,
+                                  tzk_stream_t stream);
+int tzk_seq_gather_fwd_strided(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                               const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t D,
+                               int32_t row_stride, int64_t nnz, float* out, tzk_stream_t stream);
 
 /* ---- FP16 tables (tzrec/protos/feature.proto `data_type = "FP16"` -> EmbeddingBagConfig.data_type, features/feature.py:
  * 626,652): the same lookups over an arena of IEEE halfs; pooling and outputs stay fp32.  The fused backward takes such

@@ -13,7 +13,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = "regex:linearize|RadixSort|run_update|long_chunk|long_combine|small_table|pooled_gather_fwd|zero_counters|tile_update|carry_combine"
+KERNELS = "regex:linearize|RadixSort|fused_apply|find_long_runs|run_update|long_chunk|long_combine|small_table|pooled_gather_fwd|zero_counters|tile_update|carry_combine"
 
 
 def source_sha16():

@@ -20,15 +20,19 @@ def load(path):
 
 def group(name):
     own_sparse = ("scan_tile", "pooled_gather", "seq_gather", "linearize", "run_update", "long_chunk", "long_combine",
-                  "tile_update", "carry_combine", "zero_counters", "bucketize", "bag_grad", "permute_", "col_gather",
-                  "jagged", "fm_", "dot_interact")
+                  "fused_apply", "find_long_runs", "tile_update", "carry_combine", "zero_counters", "bucketize", "bag_grad",
+                  "permute_", "col_gather", "jagged", "fm_", "dot_interact", "peer_", "small_table_update", "din_",
+                  "softmax_wsum")
     own_tower = ("small_linear", "bce_", "bias_act", "act_bwd_colsum", "colsum_final")
+    own_gemm = ("gemm3x_kernel", "wgrad3x_kernel", "wgrad_reduce", "split_w_kernel")
     if "DeviceRadixSort" in name:
         return "radix sort (CUB, inside tzk_fused_bwd)"
     if any(k in name for k in own_sparse):
         return "own: sparse path + interaction"
     if any(k in name for k in own_tower):
         return "own: tower / loss kernels"
+    if any(k in name for k in own_gemm):
+        return "own: tcgen05 3xTF32 GEMMs of the wide tower layer"
     if "gemm" in name.lower() or "inf_patching" in name or "splitK" in name or "cutlass" in name:
         return "library GEMM (cuBLASLt BF16x9 + its inf/nan scans)"
     return "torch element-wise / optimizer"

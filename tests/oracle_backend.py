@@ -23,9 +23,22 @@ def _tables(weights, lay):
         key = (lay.w_off[f], lay.rows[f], lay.dim[f])   # zero-row shards share an offset with their neighbour
         if key not in seen:
             seen[key] = len(tabs)
-            tabs.append(arr[key[0]:key[0] + lay.rows[f] * lay.dim[f]].reshape(lay.rows[f], lay.dim[f]))
+            st = lay.row_stride(f)      # interleaved arenas: [weight row | state row] lines -> a strided view
+            tabs.append(arr[key[0]:key[0] + lay.rows[f] * st].reshape(lay.rows[f], st)[:, :lay.dim[f]])
         feat_table.append(seen[key])
     return tabs, feat_table
+
+
+def _interleaved_states(weights, lay, ft, n_tabs):
+    """The accumulator halves of an interleaved arena, one strided view per table."""
+    arr = weights.detach().numpy()
+    states = [None] * n_tabs
+    for f in range(lay.num_features):
+        t = ft[f]
+        if states[t] is None:
+            st, d = lay.row_stride(f), lay.dim[f]
+            states[t] = arr[lay.w_off[f]:lay.w_off[f] + lay.rows[f] * st].reshape(lay.rows[f], st)[:, d:]
+    return states
 
 
 def _c(a):
@@ -51,7 +64,7 @@ class OracleKernels:
         return torch.from_numpy(O.lengths_to_offsets(_np(lengths)))
 
     def pooled_gather_fwd(self, weights, lay, ids, offsets, B, out=None):
-        if self.use_c:
+        if self.use_c and lay.stride is None:
             res = torch.from_numpy(self.C.pooled_lookup(_c(weights), lay, _c(ids), _c(offsets), B))
         else:
             tabs, ft = _tables(weights, lay)
@@ -67,14 +80,16 @@ class OracleKernels:
 
     def fused_bwd(self, optimizer, pooled, grad_out, weights, state, lay, ids, offsets, B, lr, eps, grad_scale=1.0,
                   **ex):
-        if self.use_c and pooled and not ex:
+        if self.use_c and pooled and not ex and lay.stride is None:
             self.C.fused_update(optimizer, _np(grad_out), weights.detach().numpy(),
                                 None if state is None else state.numpy(), lay, _c(ids), _c(offsets), B, lr, eps,
                                 grad_scale)
             return
         tabs, ft = _tables(weights, lay)
         states = [None] * len(tabs)
-        if state is not None:
+        if lay.interleaved:
+            states = _interleaved_states(weights, lay, ft, len(tabs))
+        elif state is not None:
             sarr = state.numpy()
             for f in range(lay.num_features):
                 t = ft[f]

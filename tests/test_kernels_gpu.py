@@ -735,3 +735,94 @@ def test_fp16_sequence_collection_rows(kernels):
     rows = kernels.seq_gather_fwd(ec.weights.data, ec.layout, cu(ids), cu(off), B)
     assert rows.dtype == torch.float32
     assert torch.equal(rows, ec.table_weight(0)[cu(ids)].float())
+
+
+# ---- interleaved [weight row | Adagrad accumulator row] arenas (tzk_opt_args.interleaved) -----------------------------------
+def _interleaved_arena(lay, tables, states, feat_table):
+    arena = np.zeros(lay.arena_elems, dtype=np.float32)
+    for f, t in enumerate(feat_table):
+        r, d = tables[t].shape
+        v = arena[lay.w_off[f]:lay.w_off[f] + r * 2 * d].reshape(r, 2 * d)
+        v[:, :d], v[:, d:] = tables[t], states[t]
+    return arena
+
+
+def _split_interleaved(arena, lay, tables, feat_table):
+    w, s = {}, {}
+    for f, t in enumerate(feat_table):
+        r, d = tables[t].shape
+        v = arena[lay.w_off[f]:lay.w_off[f] + r * 2 * d].reshape(r, 2 * d)
+        w[t], s[t] = v[:, :d], v[:, d:]
+    return [w[t] for t in range(len(tables))], [s[t] for t in range(len(tables))]
+
+
+@pytest.mark.parametrize("case", ["criteo_like_L1", "deepfm_mixed_dims", "shared_table", "wide_rows", "unaligned_dims",
+                                  "tiny_tables_long_runs", "multi_hot_33", "long_runs_d4"])
+@pytest.mark.parametrize("pool", [O.POOL_SUM, O.POOL_MEAN])
+def test_interleaved_gather_and_adagrad_update(kernels, case, pool):
+    """The strided gather and the fused Adagrad update over [weight | state] lines against the oracle on dense tables:
+    lookups bit-exact at L = 1, two update steps, weights AND accumulators compared, run-to-run identical bits."""
+    rows, dims, feat_table, B, max_len = CASES[case]
+    rng = np.random.default_rng(zlib.crc32(case.encode()) % 1000 + 91)
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    st_np = [np.abs(rng.standard_normal(t.shape)).astype(np.float32) * 0.01 for t in tables]
+    F = len(feat_table)
+    frows = [rows[t] for t in feat_table]
+    ids, lengths, offsets = random_kjt(rng, F, B, frows, max_len or 1, fixed_len=1 if max_len is None else None)
+    lay = build_layout(rows, dims, feat_table, [pool] * F, interleaved=True).to(DEV)
+    assert lay.interleaved and all(lay.stride[f] == 2 * lay.dim[f] for f in range(F))
+    arena0 = _interleaved_arena(lay, tables, st_np, feat_table)
+    arena = cu(arena0)
+    got = kernels.pooled_gather_fwd(arena, lay, cu(ids), cu(offsets), B).cpu().numpy()
+    want_out = O.pooled_lookup(tables, feat_table, [pool] * F, ids, offsets, B)
+    if pool == O.POOL_SUM and max_len is None:
+        np.testing.assert_array_equal(got, want_out)
+    np.testing.assert_allclose(got, want_out, rtol=1e-5, atol=1e-7)
+    grad = rng.standard_normal((B, lay.total_dim)).astype(np.float32)
+    lr, eps, gs = 0.05, 1e-8, 0.5
+    long_runs = case in ("tiny_tables_long_runs", "long_runs_d4")
+    state_rtol = 3e-4 if long_runs else 2e-5
+    w_rtol, w_atol = (5e-5, 5e-6) if long_runs else (1e-5, 1e-6)
+    want = [t.copy() for t in tables]
+    twin = cu(arena0)
+    for _ in range(2):
+        kernels.fused_bwd(O.OPT_ADAGRAD, True, cu(grad), arena, None, lay, cu(ids), cu(offsets), B, lr, eps, gs)
+        kernels.fused_bwd(O.OPT_ADAGRAD, True, cu(grad), twin, None, lay, cu(ids), cu(offsets), B, lr, eps, gs)
+        O.fused_update(O.OPT_ADAGRAD, want, st_np, feat_table, [pool] * F, ids, offsets, B, grad, lr, eps, gs)
+    assert torch.equal(arena, twin)
+    gw, gs_ = _split_interleaved(arena.cpu().numpy(), lay, tables, feat_table)
+    for t in range(len(tables)):
+        np.testing.assert_allclose(gw[t], want[t], rtol=w_rtol, atol=w_atol, err_msg=f"table {t}")
+        np.testing.assert_allclose(gs_[t], st_np[t], rtol=state_rtol, atol=1e-7, err_msg=f"state {t}")
+
+
+def test_interleaved_split_sort_apply_and_sequence_layout(kernels):
+    """The two halves of the fused backward (sort on the ids, apply on the gradient) and the un-pooled lookup / update."""
+    rng = np.random.default_rng(77)
+    rows, dims, feat_table, B = [400, 30, 400], [16, 16, 16], [0, 1, 2], 64
+    tables = [O.default_table_init(r, d, rng) for r, d in zip(rows, dims)]
+    st_np = [np.zeros_like(t) for t in tables]
+    ids, lengths, offsets = random_kjt(rng, 3, B, rows, 12)
+    lay = build_layout(rows, dims, feat_table, [0] * 3, interleaved=True).to(DEV)
+    arena = cu(_interleaved_arena(lay, tables, st_np, feat_table))
+    rows_out = kernels.seq_gather_fwd(arena, lay, cu(ids), cu(offsets), B).cpu().numpy()
+    np.testing.assert_array_equal(rows_out, O.seq_lookup(tables, feat_table, ids, offsets, B))
+    grad = rng.standard_normal((len(ids), 16)).astype(np.float32)
+    ws = torch.empty(kernels.fused_bwd_workspace_bytes(lay, len(ids)), dtype=torch.uint8, device=DEV)
+    kernels.fused_bwd_sort(False, lay, cu(ids), cu(offsets), B, ws)
+    kernels.fused_bwd_apply(O.OPT_ADAGRAD, False, cu(grad), arena, None, lay, cu(offsets), len(ids), B, 0.02, 1e-8, 1.0, ws)
+    want = [t.copy() for t in tables]
+    O.fused_update(O.OPT_ADAGRAD, want, st_np, feat_table, [0] * 3, ids, offsets, B, grad, 0.02, 1e-8, 1.0, pooled=False)
+    gw, gs_ = _split_interleaved(arena.cpu().numpy(), lay, tables, feat_table)
+    for t in range(3):
+        np.testing.assert_allclose(gw[t], want[t], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(gs_[t], st_np[t], rtol=2e-5, atol=1e-7)
+
+
+def test_interleaved_rejects_what_it_does_not_cover(kernels):
+    lay = build_layout([10], [16], [0], [0], interleaved=True).to(DEV)
+    arena = torch.zeros(lay.arena_elems, device=DEV)
+    ids, off = torch.zeros(4, dtype=torch.int64, device=DEV), torch.arange(5, dtype=torch.int64, device=DEV)
+    grad = torch.zeros(4, 16, device=DEV)
+    with pytest.raises(Exception, match="interleaved"):
+        kernels.fused_bwd(O.OPT_ROWWISE_ADAGRAD, True, grad, arena, None, lay, ids, off, 4, 0.1, 1e-8, 1.0)

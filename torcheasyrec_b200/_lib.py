@@ -18,7 +18,7 @@ class TzkOptArgs(ctypes.Structure):
 
     _fields_ = [("optimizer", c_int32), ("lr", c_float), ("eps", c_float), ("beta1", c_float), ("beta2", c_float),
                 ("weight_decay", c_float), ("max_gradient", c_float), ("state", c_void_p), ("state2", c_void_p),
-                ("step", c_void_p), ("weights_f16", c_int32), ("reserved", c_int32)]
+                ("step", c_void_p), ("weights_f16", c_int32), ("interleaved", c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/tzk.h one to one (tests/test_abi.py checks both directions)
@@ -38,6 +38,11 @@ SIGNATURES = {
         [P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P],
     ),
     "tzk_seq_gather_fwd_f16": (c_int32, [P, P, P, P, P, c_int32, c_int32, c_int32, c_int64, P, P]),
+    "tzk_pooled_gather_fwd_strided": (
+        c_int32,
+        [P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P],
+    ),
+    "tzk_seq_gather_fwd_strided": (c_int32, [P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int64, P, P]),
     "tzk_fused_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "tzk_fused_bwd": (
         c_int32,

@@ -54,6 +54,8 @@ def _state_names(kind: int) -> List[str]:
 def _local_state(coll: _ArenaCollection, t: int, which: str) -> Optional[torch.Tensor]:
     """[rows_local, D] / [rows_local] view of table t's optimizer state (`momentum1` / `momentum2`)."""
     spec = coll.optimizer
+    if which == "momentum1" and coll.layout.interleaved and spec is not None and t in coll._table_off:
+        return coll.table_state(t)            # [weight row | accumulator row] arena: a strided view
     buf = coll.opt_state if which == "momentum1" else coll.opt_state2
     if spec is None or buf is None or t not in coll._table_off:
         return None

@@ -33,7 +33,7 @@ struct BwdFeat {
   int32_t dim;
   int32_t col;
   int32_t pool;
-  int32_t pad;
+  int32_t stride;   // elements between consecutive rows of the table: dim, or 2 * dim when a.interleaved
 };
 
 struct BwdArgs {
@@ -59,7 +59,8 @@ struct BwdArgs {
   int32_t peer_w;
   int32_t idx_span;
   int32_t w_f16;      // 1: `weights` is an arena of halfs (FP16 tables): rows are widened, updated in fp32, rounded back
-  int32_t pad2;
+  int32_t interleaved;  // 1: [weight row | state row] back to back (row stride 2 * dim): the first state of table row r is
+                        // at weights + w_off + r * 2 dim + dim — one 128-B line per D = 16 row, written whole
 };
 // peer mode: the sources' published gradient buffers.  A kernel parameter of its own (__grid_constant__): indexing it
 // with a run-time rank must not drag the whole argument block into local memory.
@@ -76,7 +77,8 @@ __device__ __forceinline__ void init_bias_correction(BwdArgs& a) {
 
 __device__ __forceinline__ void stage_feats(BwdFeat* fd, const int64_t* feat_w_off, const int64_t* feat_rows,
                                             const int64_t* feat_key_base, const int32_t* feat_dim,
-                                            const int32_t* feat_col, const int32_t* feat_pool, int F) {
+                                            const int32_t* feat_col, const int32_t* feat_pool, int F,
+                                            int interleaved = 0) {
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     fd[f].w_off = feat_w_off[f];
     fd[f].rows = feat_rows[f];
@@ -84,6 +86,7 @@ __device__ __forceinline__ void stage_feats(BwdFeat* fd, const int64_t* feat_w_o
     fd[f].dim = feat_dim[f];
     fd[f].col = feat_col ? feat_col[f] : 0;
     fd[f].pool = feat_pool ? feat_pool[f] : 0;
+    fd[f].stride = interleaved ? 2 * feat_dim[f] : feat_dim[f];
   }
   __syncthreads();
 }
@@ -365,7 +368,7 @@ __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, i
     for (int ch = 0; ch < CH; ++ch) {
       const int c = (ch * G + lane) * VEC;
       if (c >= d.dim) continue;
-      float* wp = a.weights + d.w_off + row * d.dim + c;
+      float* wp = a.weights + d.w_off + row * d.stride + c;
       if (VEC == 4) *reinterpret_cast<float4*>(wp) = make_float4(acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
       else wp[0] = acc[ch][0];
     }
@@ -397,10 +400,10 @@ __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, i
   for (int ch = 0; ch < CH; ++ch) {
     const int c = (ch * G + lane) * VEC;
     if (c >= d.dim) continue;
-    const int64_t off = d.w_off + row * d.dim + c;
+    const int64_t off = d.w_off + row * d.stride + c;
     float* wp = a.weights + off;
     __half* wph = reinterpret_cast<__half*>(a.weights) + off;       // (FP16 tables: same element offset, half the bytes)
-    float* sp = es ? a.state + off : nullptr;
+    float* sp = es ? (a.interleaved ? wp + d.dim : a.state + off) : nullptr;
     float* sp2 = es2 ? a.state2 + off : nullptr;
     if (VEC == 4) {
       float4 w4;
@@ -701,7 +704,7 @@ fused_apply_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
                    const __grid_constant__ PeerGrads gp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdFeat* fd = reinterpret_cast<BwdFeat*>(smem_raw);
-  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F);
+  stage_feats(fd, feat_w_off, feat_rows, feat_key_base, feat_dim, feat_col, feat_pool, a.F, a.interleaved);
   init_bias_correction(a);
   // the long-run CTAs come FIRST in the grid: they are few, each has a lot to do, and the hardware starts CTAs in
   // index order — their work overlaps the whole short-run sweep instead of trailing it
@@ -1074,7 +1077,9 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
     TZK_REQUIRE((grad_out || grad_ptrs) && feat_w_off && feat_dim && weights && feat_rows && feat_key_base,
                 "fused_bwd: NULL argument");
     TZK_REQUIRE(!pooled || (feat_col && feat_pool), "fused_bwd: pooled mode needs feat_col/feat_pool");
-    TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr, "fused_bwd: optimizer state is NULL");
+    TZK_REQUIRE(optimizer == TZK_OPT_SGD || state != nullptr || opt.interleaved, "fused_bwd: optimizer state is NULL");
+    TZK_REQUIRE(!opt.interleaved || (optimizer == TZK_OPT_ADAGRAD && !opt.weights_f16),
+                "fused_bwd: interleaved [weight | state] rows are implemented for fp32 tables with element-wise Adagrad");
     TZK_REQUIRE((optimizer != TZK_OPT_ADAM && optimizer != TZK_OPT_PARTIAL_ROWWISE_ADAM) || (opt.state2 && opt.step),
                 "fused_bwd: Adam variants need state2 and the device step counter");
   }
@@ -1161,7 +1166,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   a.pooled = pooled; a.n = nnz; a.sentinel = sentinel;
   a.state2 = opt.state2; a.step = opt.step; a.beta1 = opt.beta1; a.beta2 = opt.beta2;
   a.weight_decay = opt.weight_decay; a.max_gradient = opt.max_gradient; a.bc1 = a.bc2 = 1.f;
-  a.peer_w = 0; a.idx_span = 1; a.w_f16 = opt.weights_f16 ? 1 : 0; a.pad2 = 0;
+  a.peer_w = 0; a.idx_span = 1; a.w_f16 = opt.weights_f16 ? 1 : 0; a.interleaved = opt.interleaved ? 1 : 0;
   PeerGrads gp;
   for (int r = 0; r < 16; ++r) gp.p[r] = 0ull;
   if (pw) {
@@ -1177,7 +1182,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
                    ((uintptr_t)a.grad_out % 16 == 0) &&
                    (ld_grad % 4 == 0) &&
                    (!(optimizer == TZK_OPT_ADAGRAD || optimizer == TZK_OPT_ADAM ||
-                      optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM) || (uintptr_t)state % 16 == 0) &&
+                      optimizer == TZK_OPT_PARTIAL_ROWWISE_ADAM) || opt.interleaved || (uintptr_t)state % 16 == 0) &&
                    (optimizer != TZK_OPT_ADAM || (uintptr_t)opt.state2 % 16 == 0))
                       ? 4 : 1;
   int need = (max_dim + vec - 1) / vec;  // chunks per row
@@ -1193,7 +1198,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   // way — and the general kernels execute fewer instructions (74 M vs 87 M warp-instructions) without the three
   // barriers per tile, so they stay the default.
   const char* tile_env = getenv("TZK_BWD_TILE");
-  const bool tile_path = tile_env && tile_env[0] == '1' && !a.w_f16 && optimizer != TZK_OPT_ACCUM_OUT;   // (fp32 tables, real updates)
+  const bool tile_path = tile_env && tile_env[0] == '1' && !a.w_f16 && !a.interleaved && optimizer != TZK_OPT_ACCUM_OUT;   // (fp32 tables, real updates)
   if (vec == 4 && ch == 1 && tile_path) {
     // tile path: every gradient / weight / state row of a tile is requested at once, runs are reduced in shared memory
     float* carry_first = reinterpret_cast<float*>(ws + L.carry);
@@ -1254,7 +1259,7 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
 static tzk_opt_args classic_opt(int32_t optimizer, float* state, float lr, float eps) {
   tzk_opt_args o;
   o.optimizer = optimizer; o.lr = lr; o.eps = eps; o.beta1 = 0.9f; o.beta2 = 0.999f; o.weight_decay = 0.f;
-  o.max_gradient = 0.f; o.state = state; o.state2 = nullptr; o.step = nullptr; o.weights_f16 = 0; o.reserved = 0;
+  o.max_gradient = 0.f; o.state = state; o.state2 = nullptr; o.step = nullptr; o.weights_f16 = 0; o.interleaved = 0;
   return o;
 }
 
@@ -1372,7 +1377,8 @@ small_table_update_kernel(BwdArgs a, const __grid_constant__ SmallPeers sp, cons
     }
     if (!any) continue;                                 // (group-uniform: every lane read the same flags)
     BwdFeat d;
-    d.w_off = t.w_off; d.rows = t.n_local; d.key_base = t.key_base; d.dim = t.dim; d.col = 0; d.pool = 0; d.pad = 0;
+    d.w_off = t.w_off; d.rows = t.n_local; d.key_base = t.key_base; d.dim = t.dim; d.col = 0; d.pool = 0;
+    d.stride = a.interleaved ? 2 * t.dim : t.dim;
     finish_run<G, 4, 1>(a, d, i, t.key_base + i, acc, lane);
   }
 }
@@ -1396,7 +1402,7 @@ extern "C" int tzk_peer_small_update(const tzk_opt_args* opt, const uint64_t* ps
   a.lr = opt->lr; a.eps = opt->eps; a.grad_scale = 1.f; a.F = 0; a.B = 1; a.optimizer = opt->optimizer; a.pooled = 0;
   a.n = total_rows; a.sentinel = 0; a.state2 = opt->state2; a.step = opt->step; a.beta1 = opt->beta1; a.beta2 = opt->beta2;
   a.weight_decay = opt->weight_decay; a.max_gradient = opt->max_gradient; a.bc1 = a.bc2 = 1.f;
-  a.peer_w = 0; a.idx_span = 1; a.w_f16 = 0; a.pad2 = 0;
+  a.peer_w = 0; a.idx_span = 1; a.w_f16 = 0; a.interleaved = opt->interleaved ? 1 : 0;
   SmallPeers sp;
   for (int r = 0; r < 16; ++r) { sp.psum[r] = r < W ? psum_ptrs[r] : 0ull; sp.flags[r] = r < W ? flag_ptrs[r] : 0ull; }
   int G = 1;

@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int32_t* __rest
                                                             const int64_t* __restrict__ tile_off,
                                                             int64_t* __restrict__ offsets) {
   __shared__ int64_t total;
-  __shared__ int32_t vals[kScanTile];
+  // one staging buffer, two uses: the tile's lengths (int32, coalesced in), then its offsets (int64, coalesced out)
+  __shared__ __align__(16) int64_t stage[kScanTile];
+  int32_t* vals = reinterpret_cast<int32_t*>(stage);
   const int64_t base = (int64_t)blockIdx.x * kScanTile;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
@@ -116,13 +118,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int32_t* __rest
     loc[k] = s;
     s += vals[threadIdx.x * kScanItems + k];
   }
-  int64_t ex = block_excl_scan(s, &total) + tile_off[blockIdx.x];
+  int64_t ex = block_excl_scan(s, &total) + tile_off[blockIdx.x];   // (its barriers also fence the reads of `vals`)
+  // a thread's 16 results are 128 B apart from its neighbour's: through shared memory, then full-line stores
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) stage[threadIdx.x * kScanItems + k] = ex + loc[k];
   __syncthreads();
-  // stage results through shared memory (as int64 would not fit twice: write directly, 128-B runs)
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    int64_t i = base + threadIdx.x * kScanItems + k;
-    if (i < n) offsets[i] = ex + loc[k];
+    const int j = k * kScanThreads + threadIdx.x;
+    if (base + j < n) offsets[base + j] = stage[j];
   }
   if (base + kScanTile >= n && threadIdx.x == 0) {
     // last tile: trailing total

@@ -21,7 +21,7 @@ struct FeatDesc {
   int32_t dim;
   int32_t col;
   int32_t pool;
-  int32_t pad;
+  int32_t stride;  // elements between consecutive rows of the table (= dim, or 2 * dim for [weight row | state row] lines)
 };
 
 constexpr int kThreads = 256;
@@ -47,7 +47,7 @@ pooled_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restri
                          const int64_t* __restrict__ feat_rows, const int32_t* __restrict__ feat_dim,
                          const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,
                          const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets, int F, int B,
-                         float* __restrict__ out, int64_t ld_out) {
+                         float* __restrict__ out, int64_t ld_out, const int32_t* __restrict__ feat_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FeatDesc* fd = reinterpret_cast<FeatDesc*>(smem_raw);
   BagStage* st = reinterpret_cast<BagStage*>(smem_raw + align16((size_t)F * sizeof(FeatDesc)));
@@ -58,6 +58,7 @@ pooled_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restri
     fd[f].dim = feat_dim[f];
     fd[f].col = feat_col[f];
     fd[f].pool = feat_pool[f];
+    fd[f].stride = feat_stride ? feat_stride[f] : feat_dim[f];
   }
   __syncthreads();
 
@@ -117,7 +118,7 @@ pooled_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restri
             const FeatDesc& d = fd[f0 + i / kTB];
             int64_t id = st[i].id0;
             if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-            if (lane * 4 < d.dim) acc[u] = ld_table_f4<WT>(weights + d.w_off + id * d.dim + lane * 4);
+            if (lane * 4 < d.dim) acc[u] = ld_table_f4<WT>(weights + d.w_off + id * d.stride + lane * 4);
           }
         }
 #pragma unroll
@@ -136,13 +137,13 @@ pooled_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restri
               } else {
                 int64_t id = st[i].id0;
                 if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-                a = ld_table_f4<WT>(weights + d.w_off + id * d.dim + c);
+                a = ld_table_f4<WT>(weights + d.w_off + id * d.stride + c);
               }
               const int64_t s0 = st[i].start;
               for (int l = 1; l < L; ++l) {
                 int64_t idl = __ldg(ids + s0 + l);
                 if ((uint64_t)idl >= (uint64_t)d.rows) idl = 0;
-                a = f4_add(a, ld_table_f4<WT>(weights + d.w_off + idl * d.dim + c));
+                a = f4_add(a, ld_table_f4<WT>(weights + d.w_off + idl * d.stride + c));
               }
               if (d.pool == TZK_POOL_MEAN) a = f4_scale(a, 1.0f / (float)L);
             }
@@ -164,11 +165,11 @@ pooled_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restri
             if (L > 0) {
               int64_t id = st[i].id0;
               if ((uint64_t)id >= (uint64_t)d.rows) id = 0;
-              acc = ld_table_f1<WT>(weights + d.w_off + id * d.dim + c);
+              acc = ld_table_f1<WT>(weights + d.w_off + id * d.stride + c);
               for (int l = 1; l < L; ++l) {
                 int64_t idl = __ldg(ids + s0 + l);
                 if ((uint64_t)idl >= (uint64_t)d.rows) idl = 0;
-                acc += ld_table_f1<WT>(weights + d.w_off + idl * d.dim + c);
+                acc += ld_table_f1<WT>(weights + d.w_off + idl * d.stride + c);
               }
               if (d.pool == TZK_POOL_MEAN) acc = acc * (1.0f / (float)L);
             }
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kThreads)
 seq_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restrict__ feat_w_off,
                       const int64_t* __restrict__ feat_rows, const int64_t* __restrict__ ids,
                       const int64_t* __restrict__ offsets, int F, int B, int D, int64_t nnz,
-                      float* __restrict__ out) {
+                      float* __restrict__ out, int row_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int64_t* key_start = reinterpret_cast<int64_t*>(smem_raw);  // [F+1]
   int64_t* w_off = key_start + (F + 1);
@@ -209,7 +210,7 @@ seq_gather_fwd_kernel(const WT* __restrict__ weights, const int64_t* __restrict_
     }
     int64_t id = __ldg(ids + l);
     if ((uint64_t)id >= (uint64_t)rows[lo]) id = 0;
-    const WT* src = weights + w_off[lo] + id * D;
+    const WT* src = weights + w_off[lo] + id * row_stride;
     float* dst = out + l * D;
     for (int c = lane * VEC; c < D; c += G * VEC) {
       if (VEC == 4) st_stream_f4(dst + c, ld_table_f4<WT>(src + c));
@@ -241,7 +242,8 @@ template <typename WT>
 static int pooled_gather_fwd_impl(const WT* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
                                   const int32_t* feat_dim, const int32_t* feat_col, const int32_t* feat_pool,
                                   const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t max_dim,
-                                  int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream) {
+                                  int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream,
+                                  const int32_t* feat_stride = nullptr) {
   TZK_REQUIRE(F >= 0 && B >= 0, "pooled_gather_fwd: negative F/B");
   if (F == 0 || B == 0) return 0;
   TZK_REQUIRE(weights && feat_w_off && feat_rows && feat_dim && feat_col && feat_pool && offsets && out,
@@ -259,10 +261,10 @@ static int pooled_gather_fwd_impl(const WT* weights, const int64_t* feat_w_off, 
   TZK_REQUIRE(smem <= 48 * 1024, "pooled_gather_fwd: F=%d keys need %zu B of shared memory (> 48 KB)", F, smem);
   if (vec == 4) {
     TZK_DISPATCH_G(G, 4, WT, pooled_gather_fwd_kernel, weights, feat_w_off, feat_rows, feat_dim, feat_col,
-                   feat_pool, ids, offsets, F, B, out, ld_out)
+                   feat_pool, ids, offsets, F, B, out, ld_out, feat_stride)
   } else {
     TZK_DISPATCH_G(G, 1, WT, pooled_gather_fwd_kernel, weights, feat_w_off, feat_rows, feat_dim, feat_col,
-                   feat_pool, ids, offsets, F, B, out, ld_out)
+                   feat_pool, ids, offsets, F, B, out, ld_out, feat_stride)
   }
   TZK_CHECK_LAUNCH("pooled_gather_fwd");
   return 0;
@@ -290,8 +292,10 @@ extern "C" int tzk_pooled_gather_fwd_f16(const void* weights, const int64_t* fea
 template <typename WT>
 static int seq_gather_fwd_impl(const WT* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
                                const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t D, int64_t nnz,
-                               float* out, tzk_stream_t stream) {
+                               float* out, tzk_stream_t stream, int32_t row_stride = 0) {
   TZK_REQUIRE(F >= 0 && B >= 0 && nnz >= 0 && D >= 1, "seq_gather_fwd: bad sizes");
+  if (row_stride == 0) row_stride = D;
+  TZK_REQUIRE(row_stride >= D && (D % 4 != 0 || row_stride % 4 == 0), "seq_gather_fwd: bad row stride %d for D=%d", row_stride, D);
   if (F == 0 || nnz == 0) return 0;
   TZK_REQUIRE(weights && feat_w_off && feat_rows && ids && offsets && out, "seq_gather_fwd: NULL argument");
   TZK_REQUIRE(F <= 2048, "seq_gather_fwd: F=%d > 2048", F);
@@ -303,9 +307,9 @@ static int seq_gather_fwd_impl(const WT* weights, const int64_t* feat_w_off, con
   int grid = blocks < kSmCountB200 * 16 ? (int)blocks : kSmCountB200 * 16;
   size_t smem = (size_t)(3 * F + 1) * sizeof(int64_t);
   if (vec == 4) {
-    TZK_DISPATCH_G(G, 4, WT, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out)
+    TZK_DISPATCH_G(G, 4, WT, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out, row_stride)
   } else {
-    TZK_DISPATCH_G(G, 1, WT, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out)
+    TZK_DISPATCH_G(G, 1, WT, seq_gather_fwd_kernel, weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out, row_stride)
   }
   TZK_CHECK_LAUNCH("seq_gather_fwd");
   return 0;
@@ -322,4 +326,22 @@ extern "C" int tzk_seq_gather_fwd_f16(const void* weights, const int64_t* feat_w
                                       int32_t D, int64_t nnz, float* out, tzk_stream_t stream) {
   return seq_gather_fwd_impl<__half>(static_cast<const __half*>(weights), feat_w_off, feat_rows, ids, offsets, F, B, D,
                                      nnz, out, stream);
+}
+
+// Strided tables: consecutive rows of feature f's table are feat_stride[f] (>= D_f) elements apart — the interleaved
+// [weight row | optimizer-state row] layout (tzk_opt_args.interleaved) keeps a row and its Adagrad accumulator in one
+// 128-B line for D = 16, so the update writes whole lines.  feat_stride == NULL: dense rows.
+extern "C" int tzk_pooled_gather_fwd_strided(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                             const int32_t* feat_dim, const int32_t* feat_stride,
+                                             const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
+                                             const int64_t* offsets, int32_t F, int32_t B, int32_t max_dim,
+                                             int32_t vec_ok, float* out, int64_t ld_out, tzk_stream_t stream) {
+  return pooled_gather_fwd_impl<float>(weights, feat_w_off, feat_rows, feat_dim, feat_col, feat_pool, ids, offsets, F,
+                                       B, max_dim, vec_ok, out, ld_out, stream, feat_stride);
+}
+
+extern "C" int tzk_seq_gather_fwd_strided(const float* weights, const int64_t* feat_w_off, const int64_t* feat_rows,
+                                          const int64_t* ids, const int64_t* offsets, int32_t F, int32_t B, int32_t D,
+                                          int32_t row_stride, int64_t nnz, float* out, tzk_stream_t stream) {
+  return seq_gather_fwd_impl<float>(weights, feat_w_off, feat_rows, ids, offsets, F, B, D, nnz, out, stream, row_stride);
 }

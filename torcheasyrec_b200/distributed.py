@@ -102,6 +102,7 @@ class _DimGroup:
         cls = EmbeddingBagCollection if pooled else EmbeddingCollection
         # local shard arena + slot bookkeeping; output keys follow the WHOLE collection's naming
         self.local = cls(configs, device=device, local_rows=rows_local, names_by_table=names)
+        self.local.allow_interleave = False      # peers read this arena (dense rows): csrc/tzk_peer.cu
         self.feature_names = self.local.feature_names()
         self.embedding_names = self.local._embedding_names
         F = len(self.feature_names)

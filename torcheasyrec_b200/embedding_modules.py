@@ -164,6 +164,9 @@ class _ArenaCollection(nn.Module):
         self.register_buffer("opt_step", None, persistent=False)
         self._hook = None
         self.grad_scale = 1.0  # sharded wrappers set 1/W here (App. A.6)
+        # [weight row | Adagrad accumulator row] interleaving (set_optimizer): unsharded CUDA collections only; the local
+        # shards of sharded collections keep dense rows (their arenas are read by peers: csrc/tzk_peer.cu)
+        self.allow_interleave = True
         if self._device.type != "meta":
             self.reset_parameters()
             self.layout.to(self._device)
@@ -186,11 +189,15 @@ class _ArenaCollection(nn.Module):
                     w.copy_(tmp)
 
     def table_weight(self, t: int) -> torch.Tensor:
-        o = self._table_off[t]
-        return self.weights.data[o:o + self._table_rows[t] * self._table_dim[t]].view(self._table_rows[t],
-                                                                                       self._table_dim[t])
+        o, r, d = self._table_off[t], self._table_rows[t], self._table_dim[t]
+        if self.layout.interleaved:       # [rows, 2 D] lines: weights in the first half (a strided view)
+            return self.weights.data[o:o + r * 2 * d].view(r, 2 * d)[:, :d]
+        return self.weights.data[o:o + r * d].view(r, d)
 
     def table_state(self, t: int) -> Optional[torch.Tensor]:
+        if self.layout.interleaved:
+            o, r, d = self._table_off[t], self._table_rows[t], self._table_dim[t]
+            return self.weights.data[o:o + r * 2 * d].view(r, 2 * d)[:, d:]
         if self.opt_state is None:
             return None
         if self._opt.kind in (OPT_ADAGRAD, OPT_ADAM, OPT_PARTIAL_ROWWISE_ADAM):
@@ -201,6 +208,27 @@ class _ArenaCollection(nn.Module):
 
     def set_table_weight(self, t: int, w: torch.Tensor) -> None:
         with torch.no_grad():
+            self.table_weight(t).copy_(w)
+
+    def dense_weights(self) -> torch.Tensor:
+        """The tables back to back with dense rows (what `weights` holds unless the rows are interleaved with their
+        optimizer state): layout-independent comparisons in tests, checkpoints of earlier versions."""
+        if not self.layout.interleaved:
+            return self.weights.data
+        return torch.cat([self.table_weight(t).reshape(-1) for t in range(len(self._configs)) if t in self._table_off])
+
+    def _relayout(self, interleaved: bool, fill: float) -> None:
+        """Re-lays the arena with dense rows, or as [weight row | accumulator row] lines (kernels.build_layout)."""
+        old = {t: self.table_weight(t) for t in range(len(self._configs)) if t in self._table_off}   # views of the old arena
+        lay = build_layout(self._table_rows, self._table_dim, self._feat_table, list(self.layout.pool),
+                           interleaved=interleaved)
+        arena = torch.full((lay.arena_elems,), fill, dtype=torch.float32, device=self.weights.device)
+        self.layout = lay.to(self.weights.device)
+        for f, t in enumerate(self._feat_table):
+            self._table_off[t] = lay.w_off[f]
+            self._table_key[t] = lay.key_base[f]
+        self.weights.data = arena
+        for t, w in old.items():
             self.table_weight(t).copy_(w)
 
     # ---- checkpoint keys (SURVEY §8f N2) ------------------------------------------------------------------
@@ -224,7 +252,16 @@ class _ArenaCollection(nn.Module):
         arena_key = prefix + "weights"          # checkpoints written by earlier versions of this package
         if arena_key in state_dict:
             w = state_dict[arena_key]
-            if w.numel() != self.weights.numel():
+            if self.layout.interleaved:
+                with torch.no_grad():
+                    o = 0
+                    for t in range(len(self._configs)):
+                        if t in self._table_off:
+                            n = self._table_rows[t] * self._table_dim[t]
+                            o = (o + 3) // 4 * 4
+                            self.table_weight(t).copy_(w.reshape(-1)[o:o + n].view(self._table_rows[t], -1))
+                            o += n
+            elif w.numel() != self.weights.numel():
                 error_msgs.append(f"size mismatch for {arena_key}: {tuple(w.shape)} vs {tuple(self.weights.shape)}")
             else:
                 with torch.no_grad():
@@ -274,7 +311,16 @@ class _ArenaCollection(nn.Module):
         """apply_optimizer_in_backward equivalent (tzrec/main.py:774-781)."""
         self._opt = spec
         dev = self.weights.device
-        if spec.kind == OPT_ADAGRAD:
+        if self.layout.interleaved:        # a second set_optimizer: back to dense rows first (the old state is dropped)
+            self._relayout(False, 0.0)
+        env = os.environ.get("TZK_INTERLEAVE", "1")      # "0": dense rows; "force": also off CUDA (host-logic tests)
+        if (spec.kind == OPT_ADAGRAD and self.allow_interleave and self.table_dtype == torch.float32
+                and ((dev.type == "cuda" and env != "0") or env == "force")):
+            # a D = 16 row and its accumulator in ONE 128-B line: the fused update reads and writes whole lines (two
+            # half-line writes cost DRAM a read-modify-write each — profiles/README.md, round 2)
+            self._relayout(True, spec.initial_accumulator_value)
+            self.opt_state = None
+        elif spec.kind == OPT_ADAGRAD:
             self.opt_state = torch.full((self.layout.arena_elems,), spec.initial_accumulator_value,
                                         dtype=torch.float32, device=dev)
         elif spec.kind == OPT_ROWWISE_ADAGRAD:

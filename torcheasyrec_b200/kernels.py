@@ -38,6 +38,11 @@ class FeatureLayout:
     total_keys: int
     total_dim: int
     arena_elems: int
+    # elements between consecutive rows of each key's table: None = dense rows (= dim); `interleaved` = every table row is
+    # followed by its element-wise optimizer-state row (stride 2 * dim; tzk_opt_args.interleaved, include/tzk.h)
+    stride: Optional[List[int]] = None
+    interleaved: bool = False
+    d_stride: Optional[torch.Tensor] = None
     # device copies (filled by .to())
     d_w_off: Optional[torch.Tensor] = None
     d_rows: Optional[torch.Tensor] = None
@@ -57,7 +62,10 @@ class FeatureLayout:
     @property
     def vec_ok(self) -> int:
         return int(all(d % 4 == 0 for d in self.dim) and all(c % 4 == 0 for c in self.col)
-                   and all(o % 4 == 0 for o in self.w_off))
+                   and all(o % 4 == 0 for o in self.w_off) and all(s % 4 == 0 for s in (self.stride or [])))
+
+    def row_stride(self, f: int) -> int:
+        return self.stride[f] if self.stride is not None else self.dim[f]
 
     def to(self, device) -> "FeatureLayout":
         self.d_w_off = torch.tensor(self.w_off, dtype=torch.int64, device=device)
@@ -66,19 +74,25 @@ class FeatureLayout:
         self.d_col = torch.tensor(self.col, dtype=torch.int32, device=device)
         self.d_pool = torch.tensor(self.pool, dtype=torch.int32, device=device)
         self.d_key_base = torch.tensor(self.key_base, dtype=torch.int64, device=device)
+        self.d_stride = None if self.stride is None else torch.tensor(self.stride, dtype=torch.int32, device=device)
         return self
 
 
 def build_layout(table_rows: Sequence[int], table_dim: Sequence[int], feat_table: Sequence[int],
-                 feat_pool: Sequence[int], align: int = 4) -> FeatureLayout:
-    """Packs tables back to back into one arena (row starts 16-B aligned) and lays features out in order."""
+                 feat_pool: Sequence[int], align: int = 4, interleaved: bool = False) -> FeatureLayout:
+    """Packs tables back to back into one arena (row starts 16-B aligned) and lays features out in order.
+    `interleaved`: every table row is followed by its optimizer-state row (row stride 2 * dim; table starts 128-B
+    aligned so that a D = 16 row and its state share one line)."""
     t_off, t_key = [], []
     o = k = 0
+    mult = 2 if interleaved else 1
+    if interleaved:
+        align = max(align, 32)
     for r, d in zip(table_rows, table_dim):
         o = (o + align - 1) // align * align
         t_off.append(o)
         t_key.append(k)
-        o += r * d
+        o += r * d * mult
         k += r
     col, c = [], 0
     for t in feat_table:
@@ -88,7 +102,8 @@ def build_layout(table_rows: Sequence[int], table_dim: Sequence[int], feat_table
         w_off=[t_off[t] for t in feat_table], rows=[table_rows[t] for t in feat_table],
         dim=[table_dim[t] for t in feat_table], col=col, pool=list(feat_pool),
         key_base=[t_key[t] for t in feat_table], total_keys=max(k, 1), total_dim=c,
-        arena_elems=max(o, 128))   # never smaller than one (widest) row: padding slots read row 0
+        arena_elems=max(o, 128),   # never smaller than one (widest) row: padding slots read row 0
+        stride=[table_dim[t] * 2 for t in feat_table] if interleaved else None, interleaved=interleaved)
 
 
 def _stream() -> int:
@@ -124,20 +139,15 @@ def _rows2d(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
 
 
 def _small_linear_rows_path(K: int, N: int) -> bool:
-    """Mirrors use_bwd2() of csrc/tzk_tower.cu (launch accounting only)."""
-    if os.environ.get("TZK_SMALL_LINEAR_BWD", "")[:1] == "1" or not (1 <= K <= 64 and 1 <= N <= 64):
-        return False
-    nb = 4 if N % 4 == 0 else 1
-    t = -(-N // nb) * -(-K // 4)
-    if t > 128:
-        t = -(-N // nb) * -(-K // 8)
-    return t <= 128
+    """Mirrors use_bwd2() of csrc/tzk_tower.cu (launch accounting only): dx rows kernel + dW tile kernel + reduction for
+    every K, N <= 64 unless TZK_SMALL_LINEAR_BWD=1 selects the 128-row tile kernel."""
+    return os.environ.get("TZK_SMALL_LINEAR_BWD", "")[:1] != "1" and 1 <= K <= 64 and 1 <= N <= 64
 
 
 def _tile_path(lay: "FeatureLayout") -> bool:
     import os
 
-    return os.environ.get("TZK_BWD_TILE", "0") == "1" and bool(lay.vec_ok) and lay.max_dim <= 128
+    return os.environ.get("TZK_BWD_TILE", "0") == "1" and bool(lay.vec_ok) and lay.max_dim <= 128 and not lay.interleaved
 
 
 def _table_dtype(weights: torch.Tensor, name: str = "weights") -> bool:
@@ -163,7 +173,8 @@ def _opt_args(optimizer: int, state, lr: float, eps: float, ex: dict):
             _need(t, torch.float32, nm)
     return TzkOptArgs(optimizer, lr, eps, float(ex.get("beta1", 0.9)), float(ex.get("beta2", 0.999)),
                       float(ex.get("weight_decay", 0.0)), float(ex.get("max_gradient", 0.0)),
-                      _ptr(state), _ptr(st2), _ptr(step), int(bool(ex.get("weights_f16", False))), 0)
+                      _ptr(state), _ptr(st2), _ptr(step), int(bool(ex.get("weights_f16", False))),
+                      int(bool(ex.get("interleaved", False))))
 
 
 class CudaKernels:
@@ -210,6 +221,15 @@ class CudaKernels:
         if out is None:
             out = torch.empty((B, lay.total_dim), dtype=torch.float32, device=weights.device)
         out, ld = _rows2d(out, "out")
+        if lay.stride is not None:
+            if f16:
+                raise TzkError("strided (interleaved) tables are fp32")
+            check(self._lib.tzk_pooled_gather_fwd_strided(
+                _ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim), _ptr(lay.d_stride),
+                _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, lay.max_dim, lay.vec_ok,
+                _ptr(out), ld, _stream()), "tzk_pooled_gather_fwd_strided")
+            self.launches += 1
+            return out
         fn = self._lib.tzk_pooled_gather_fwd_f16 if f16 else self._lib.tzk_pooled_gather_fwd
         check(fn(
             _ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(lay.d_dim), _ptr(lay.d_col),
@@ -229,6 +249,14 @@ class CudaKernels:
             raise TzkError("seq_gather_fwd: all features of an un-pooled collection must share one dim")
         nnz = ids.numel()
         out = torch.empty((nnz, D), dtype=torch.float32, device=weights.device)
+        if lay.stride is not None:
+            if f16:
+                raise TzkError("strided (interleaved) tables are fp32")
+            check(self._lib.tzk_seq_gather_fwd_strided(_ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(ids),
+                                                       _ptr(offsets), F, B, D, lay.stride[0] if F else D, nnz, _ptr(out),
+                                                       _stream()), "tzk_seq_gather_fwd_strided")
+            self.launches += 1
+            return out
         fn = self._lib.tzk_seq_gather_fwd_f16 if f16 else self._lib.tzk_seq_gather_fwd
         check(fn(_ptr(weights), _ptr(lay.d_w_off), _ptr(lay.d_rows), _ptr(ids), _ptr(offsets), F, B, D, nnz, _ptr(out),
                  _stream()), "tzk_seq_gather_fwd")
@@ -242,6 +270,8 @@ class CudaKernels:
         """`ex` (optional): state2, step, beta1, beta2, weight_decay, max_gradient -> tzk_fused_bwd_ex."""
         if _table_dtype(weights):
             ex = dict(ex, weights_f16=True)
+        if lay.interleaved:
+            ex, state = dict(ex, interleaved=True), None    # the state rows live inside `weights`
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         grad_out, ld = _rows2d(grad_out, "grad_out")
@@ -290,6 +320,8 @@ class CudaKernels:
                         lr: float, eps: float, grad_scale: float, ws: torch.Tensor, **ex) -> None:
         if _table_dtype(weights):
             ex = dict(ex, weights_f16=True)
+        if lay.interleaved:
+            ex, state = dict(ex, interleaved=True), None    # the state rows live inside `weights`
         _need(offsets, torch.int64, "offsets")
         grad_out, ld = _rows2d(grad_out, "grad_out")
         if optimizer == OPT_ACCUM_OUT:
