@@ -26,6 +26,8 @@
 
 struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
@@ -140,6 +142,15 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   return m;
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+namespace tzk_shim {
+// every live lane of the warp contributes one 32-bit value and reads all of them (building block of the emulated mma)
+inline void warp_allgather(unsigned v, unsigned (&out)[32]) {
+  t_wslots->v[t_lane] = v;
+  t_wbar->arrive_and_wait();
+  for (unsigned l = 0; l < 32; ++l) out[l] = l < t_wslots->n ? (unsigned)t_wslots->v[l] : 0u;
+  t_wbar->arrive_and_wait();
+}
+}  // namespace tzk_shim
 template <class T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 template <class T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 template <class T> inline T atomicMax(T* p, T v) {

@@ -826,3 +826,46 @@ def test_interleaved_rejects_what_it_does_not_cover(kernels):
     grad = torch.zeros(4, 16, device=DEV)
     with pytest.raises(Exception, match="interleaved"):
         kernels.fused_bwd(O.OPT_ROWWISE_ADAGRAD, True, grad, arena, None, lay, ids, off, 4, 0.1, 1e-8, 1.0)
+
+
+# ---- DLRM interaction on the tensor cores (csrc/tzk_interact_tc.cuh; TZK_INTERACT_TC=1) ------------------------------------
+@pytest.mark.parametrize("B", [1, 8, 777, 40000])
+def test_interaction_tensor_core_kernels_match_reference_and_fp64(kernels, monkeypatch, B):
+    """mma.sync m16n8k8 with the 3xTF32 split, DLRM-Criteo shape (27 x 16, [351 | 0 | 16 | 416] rows): the reference's own
+    golden vectors (B = the fixture's batch), float64 at other batch sizes, and the FFMA kernels of tzk_dense.cu."""
+    sparse_g, all_feat = GOLD["dlrm_sparse"], GOLD["dlrm_all_feat"]
+    rng = np.random.default_rng(B)
+    if B == 8 and sparse_g.shape[0] >= 8:
+        sparse, dense = sparse_g[:8], all_feat[:8, 351:367]
+        want_fwd = all_feat[:8]
+    else:
+        sparse = rng.standard_normal((B, 416)).astype(np.float32)
+        dense = rng.standard_normal((B, 16)).astype(np.float32)
+        want_fwd = None
+    d_pad = rng.standard_normal((B, 784)).astype(np.float32)
+    monkeypatch.setenv("TZK_INTERACT_TC", "0")
+    ref = kernels.dot_interact_fwd(cu(dense), cu(sparse), 26, 16, True, True, pad_to=4, p_pad=1)
+    rdd, rds = kernels.dot_interact_bwd(cu(dense), cu(sparse), cu(d_pad), 26, 16, True, True, p_pad=1)
+    monkeypatch.setenv("TZK_INTERACT_TC", "1")
+    got = kernels.dot_interact_fwd(cu(dense), cu(sparse), 26, 16, True, True, pad_to=4, p_pad=1)
+    dd, ds = kernels.dot_interact_bwd(cu(dense), cu(sparse), cu(d_pad), 26, 16, True, True, p_pad=1)
+    torch.cuda.synchronize()
+    assert got.shape == (B, 784)
+    assert torch.equal(got[:, 351:], ref[:, 351:])                     # zero + copy part: same bits
+    x = np.concatenate([dense[:, None, :], sparse.reshape(B, 26, 16)], 1).astype(np.float64)
+    z = x @ x.transpose(0, 2, 1)
+    iu = np.triu_indices(27, 1)
+    np.testing.assert_allclose(got[:, :351].cpu().numpy(), z[:, iu[0], iu[1]], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(got[:, :351], ref[:, :351], rtol=1e-5, atol=1e-5)
+    if want_fwd is not None:
+        np.testing.assert_allclose(got[:, :351].cpu().numpy(), want_fwd[:, :351], rtol=1e-5, atol=1e-5)
+    G = np.zeros((B, 27, 27))
+    G[:, iu[0], iu[1]] = d_pad[:, :351]
+    dx = (G + G.transpose(0, 2, 1)) @ x + d_pad[:, 352:].astype(np.float64).reshape(B, 27, 16)
+    np.testing.assert_allclose(dd.cpu().numpy(), dx[:, 0], rtol=1e-5, atol=3e-5)
+    np.testing.assert_allclose(ds.cpu().numpy(), dx[:, 1:].reshape(B, -1), rtol=1e-5, atol=3e-5)
+    torch.testing.assert_close(dd, rdd, rtol=1e-5, atol=3e-5)
+    torch.testing.assert_close(ds, rds, rtol=1e-5, atol=3e-5)
+    # run-to-run identical bits
+    again = kernels.dot_interact_fwd(cu(dense), cu(sparse), 26, 16, True, True, pad_to=4, p_pad=1)
+    assert torch.equal(again, got)

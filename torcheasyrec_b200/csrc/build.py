@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["tzk_core.cu", "tzk_gather.cu", "tzk_bwd.cu", "tzk_dist.cu", "tzk_dense.cu", "tzk_tower.cu", "tzk_din.cu", "tzk_peer.cu"]
-HEADERS = ["tzk_common.cuh", "tzk_tower_bwd2.cuh", os.path.join("..", "..", "include", "tzk.h")]
+HEADERS = ["tzk_common.cuh", "tzk_tower_bwd2.cuh", "tzk_interact_tc.cuh", os.path.join("..", "..", "include", "tzk.h")]
 LIB = os.path.join(HERE, "libtzk.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -50,8 +50,10 @@ def build(verbose: bool = False, force: bool = False) -> str:
     if failed:
         raise RuntimeError("libtzk build failed")
     if force or procs or _mtime(LIB) < max(_mtime(o) for o in objs):
-        cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs]
+        # link next to the target and rename: a reader (a gpurun snapshot, another process) never sees a torn library
+        cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB + ".tmp", *objs]
         subprocess.run(cmd, check=True)
+        os.replace(LIB + ".tmp", LIB)
     build_gemm(force)
     build_gemm3x(force)
     return LIB
@@ -63,7 +65,8 @@ def build_gemm3x(force: bool = False) -> str:
     lib = os.path.join(HERE, "libtzk_gemm3x.so")
     deps = [src] + [os.path.join(HERE, h) for h in ("tzk_umma_desc.h", "tzk_tcgen05_ptx.h")]
     if force or _mtime(lib) < max(_mtime(d) for d in deps):
-        subprocess.run([NVCC, *FLAGS, "-shared", src, "-o", lib], check=True)
+        subprocess.run([NVCC, *FLAGS, "-shared", src, "-o", lib + ".tmp"], check=True)
+        os.replace(lib + ".tmp", lib)
     return lib
 
 

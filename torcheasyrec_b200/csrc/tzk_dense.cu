@@ -7,6 +7,25 @@
 
 using namespace tzk;
 
+// ---- tensor-core variant of the DLRM interaction (mma.sync m16n8k8, 3xTF32) -------------------------------------------
+#define TZK_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define TZK_UNPAREN(...) __VA_ARGS__
+#define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) TZK_UNPAREN kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+namespace tzk_itc {
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+}  // namespace tzk_itc
+#include "tzk_interact_tc.cuh"
+
+
 namespace {
 constexpr int kThreads = 256;
 
@@ -489,6 +508,13 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
   }
 }
 
+// TZK_INTERACT_TC=1: the DLRM-Criteo shape (27 x 16, aligned output row) on the tensor cores (tzk_interact_tc.cuh);
+// read per call (tests flip it)
+inline bool use_interact_tc() {
+  const char* e = getenv("TZK_INTERACT_TC");
+  return e && e[0] == '1';
+}
+
 inline int grid_for(int64_t n, int per_block, int max_blocks) {
   int64_t g = ceil_div64(n, per_block);
   if (g < 1) g = 1;
@@ -583,6 +609,13 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
   TZK_REQUIRE(p_pad >= 0 && p_pad < 4, "dot_interact_fwd: p_pad must be in [0,3]");
+  if (use_interact_tc() && tzk_itc::covers(dense, ld_dense, ld_sparse, Ns, D, copy_dense, copy_sparse, p_pad, out, ld_out)) {
+    tzk_itc::dot_interact27_fwd_tc_kernel<<<tzk_itc::grid_for(B, kSmCountB200 * 8), tzk_itc::kWarps * 32,
+                                            tzk_itc::fwd_smem(), as_stream(stream)>>>(dense, ld_dense, sparse, ld_sparse,
+                                                                                      B, out, ld_out);
+    TZK_CHECK_LAUNCH("dot_interact27_fwd_tc_kernel");
+    return 0;
+  }
   const int aligned = (((P + p_pad) % 4) == 0) && (ld_out % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const int nb = Np / 4, n_blocks = nb * (nb + 1) / 2;
   size_t smem = ((size_t)((n_blocks + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + ((P + 3 + 4) & ~3))) * sizeof(float);
@@ -635,6 +668,13 @@ extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const 
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
   TZK_REQUIRE(p_pad >= 0 && p_pad < 4, "dot_interact_bwd: p_pad must be in [0,3]");
+  if (use_interact_tc() && tzk_itc::covers(dense, ld_dense, ld_sparse, Ns, D, copy_dense, copy_sparse, p_pad, d_out, ld_dout)) {
+    tzk_itc::dot_interact27_bwd_tc_kernel<<<tzk_itc::grid_for(B, kSmCountB200 * 8), tzk_itc::kWarps * 32,
+                                            tzk_itc::bwd_smem(), as_stream(stream)>>>(
+        dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, d_dense, ld_ddense, d_sparse, ld_dsparse);
+    TZK_CHECK_LAUNCH("dot_interact27_bwd_tc_kernel");
+    return 0;
+  }
   const int aligned = (((P + p_pad) % 4) == 0) && (ld_dout % 4 == 0) && ((uintptr_t)d_out % 16 == 0);
   size_t smem = ((size_t)((P + 7) / 8) * 4 + (size_t)kIWarps * (Np * (D + 4) + Np * (Np + 8))) * sizeof(float);
 #define TZK_IBWD(DT_, NT_)                                                                                    \
