@@ -195,7 +195,7 @@ class PeerState(PeerBase):
             self._dummy_off = torch.zeros(2, dtype=torch.int64, device=dev)
         else:
             self.grad = self._alloc(self.B * g.total_dim if self.pooled else self.max_nnz * g.dim, torch.float32)
-        self.site_a, self.site_b, self.site_c = _Site(self), _Site(self), _Site(self)
+        self.site_a, self.site_b, self.site_c, self.site_b2 = _Site(self), _Site(self), _Site(self), _Site(self)
         self._ws = None
         self._prep_pending = False
         self._host_barrier()                 # flags are zero and tables are in place everywhere before the first step
@@ -356,7 +356,13 @@ class PeerState(PeerBase):
         lay = g.local.layout
         push = self.bwd_mode == "push"
         sm = self.small
-        if sm is not None:                    # per-row sums of this rank's gradients of the small tables (1/W folded in)
+        # TZK_PEER_ACCUM_SIDE=1: the per-row sums of the small tables' gradients (a pass over ALL local ids) leave the
+        # main stream: they run on the side stream next to the push, followed by a barrier of their own (site_b2) — the
+        # main stream only pushes the big tables' rows and crosses barrier B.
+        accum_side = (sm is not None and push and os.environ.get("TZK_PEER_ACCUM_SIDE", "0") == "1"
+                      and self._side_stream() is not None)
+
+        def accumulate_small():
             from .kernels import OPT_ACCUM_OUT
 
             gr = grad if self.pooled else grad.reshape(-1, g.dim)
@@ -364,6 +370,15 @@ class PeerState(PeerBase):
             if nnz:
                 k.fused_bwd_apply(OPT_ACCUM_OUT, self.pooled, gr, sm["psum"].t, sm["flags"].t, sm["layout"], offsets, nnz,
                                   self.B, 0.0, 0.0, 1.0 / self.W, self._small_ws(nnz))
+
+        if sm is not None and not accum_side:   # per-row sums of this rank's gradients of the small tables (1/W folded in)
+            accumulate_small()
+        if accum_side:
+            def side_accum():
+                accumulate_small()
+                self._barrier(self.site_b2)   # every rank's partial sums are complete
+            self._on_side(side_accum)         # (forks after everything enqueued so far: the gradient exists)
+            self._pending_accum = (grad, offsets)   # the side stream reads them: away from the allocator until the join
         if push:
             if not self.pooled:
                 grad = grad.reshape(-1, g.dim)
@@ -404,10 +419,15 @@ class PeerState(PeerBase):
         if self._side_stream() is None:
             return
         cur = torch.cuda.current_stream()
-        try:
-            torch.autograd.Variable._execution_engine.queue_callback(lambda: cur.wait_stream(self._side_stream()))
-        except RuntimeError:                  # not inside a backward pass
+
+        def join():
             cur.wait_stream(self._side_stream())
+            self._pending_accum = None
+
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join)
+        except RuntimeError:                  # not inside a backward pass
+            join()
 
 
 class _PeerLookup(torch.autograd.Function):
