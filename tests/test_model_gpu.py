@@ -52,7 +52,8 @@ def test_train_steps_match_oracle(name):
             # the gradient entering the fused update comes out of cuBLAS (GPU) vs MKL (CPU) dense towers, which
             # differ by ~1e-6 rel; the kernels themselves are held to 1e-5 in test_kernels_gpu.py
             # (the GPU arena holds [weight row | accumulator row] lines, the CPU twin dense rows: compare per table)
-            assert cg.layout.interleaved and not cc.layout.interleaved
+            assert cg.layout.interleaved == (os.environ.get("TZK_INTERLEAVE", os.environ.get("TZK_EXPERIMENTAL", "0")) == "1")
+            assert not cc.layout.interleaved
             np.testing.assert_allclose(cg.dense_weights().cpu().numpy(), cc.dense_weights().numpy(), rtol=5e-5, atol=1e-6)
             for t in range(len(cg._configs)):
                 np.testing.assert_allclose(cg.table_state(t).cpu().numpy(), cc.table_state(t).numpy(), rtol=1e-4,

@@ -26,6 +26,12 @@ def _p(a):
     return None if a is None else a.ctypes.data
 
 
+@pytest.fixture(autouse=True)
+def _tile_kernel_by_default(monkeypatch):
+    # (the library keeps the dW tile kernel switched off until it has been through a GPU validation pass)
+    monkeypatch.setenv("TZK_SMALL_LINEAR_DW", "1")
+
+
 # ---- narrow tower layers, backward v2 ---------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def tower(tmp_path_factory):

@@ -1366,13 +1366,23 @@ small_table_update_kernel(BwdArgs a, const __grid_constant__ SmallPeers sp, cons
     float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
     bool any = false;
     const int c = lane * 4;
-    for (int r = 0; r < W; ++r) {                       // rank order: the same sum on every run
-      if (reinterpret_cast<const int32_t*>(sp.flags[r])[key_s]) {
+    // all W flags, then all flagged partial sums, are requested before anything is consumed: two NVLink round trips per
+    // row instead of 2 W dependent ones; the additions stay in rank order (the same sum on every run)
+    int32_t fl[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) fl[r] = r < W ? reinterpret_cast<const int32_t*>(sp.flags[r])[key_s] : 0;
+    float4 pv[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      pv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fl[r] && c < t.dim)
+        pv[r] = ld_coh_f4(reinterpret_cast<const float*>(sp.psum[r]) + t.psum_off + (t.start + i) * t.dim + c);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (fl[r]) {
         any = true;
-        if (c < t.dim) {
-          const float4 v = ld_coh_f4(reinterpret_cast<const float*>(sp.psum[r]) + t.psum_off + (t.start + i) * t.dim + c);
-          acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
-        }
+        acc[0][0] += pv[r].x; acc[0][1] += pv[r].y; acc[0][2] += pv[r].z; acc[0][3] += pv[r].w;
       }
     }
     if (!any) continue;                                 // (group-uniform: every lane read the same flags)

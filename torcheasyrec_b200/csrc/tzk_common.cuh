@@ -1,5 +1,6 @@
 // Shared helpers for the tzk kernels (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,6 +32,15 @@ inline cudaStream_t as_stream(tzk_stream_t s) { return reinterpret_cast<cudaStre
   } while (0)
 
 constexpr int kSmCountB200 = 148;
+
+// Switches of code paths that have not been through a GPU validation pass yet: `name`=0/1 decides; unset,
+// TZK_EXPERIMENTAL=1 turns them all on (scripts/gpu_call_n1.sh); otherwise they stay off.
+inline bool unvalidated_switch(const char* name) {
+  const char* e = getenv(name);
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  const char* x = getenv("TZK_EXPERIMENTAL");
+  return x && x[0] == '1';
+}
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(int64_t* __res
   }
 }
 
+// STAGED: the offsets leave through shared memory as full-line stores (TZK_SCAN_STAGED); otherwise every thread writes
+// its 16 results directly (128-B stride between neighbouring lanes)
+template <bool STAGED>
 __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int32_t* __restrict__ len, int64_t n,
                                                             const int64_t* __restrict__ tile_off,
                                                             int64_t* __restrict__ offsets) {
@@ -119,14 +122,22 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int32_t* __rest
     s += vals[threadIdx.x * kScanItems + k];
   }
   int64_t ex = block_excl_scan(s, &total) + tile_off[blockIdx.x];   // (its barriers also fence the reads of `vals`)
-  // a thread's 16 results are 128 B apart from its neighbour's: through shared memory, then full-line stores
+  if (STAGED) {
+    // a thread's 16 results are 128 B apart from its neighbour's: through shared memory, then full-line stores
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) stage[threadIdx.x * kScanItems + k] = ex + loc[k];
-  __syncthreads();
+    for (int k = 0; k < kScanItems; ++k) stage[threadIdx.x * kScanItems + k] = ex + loc[k];
+    __syncthreads();
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const int j = k * kScanThreads + threadIdx.x;
-    if (base + j < n) offsets[base + j] = stage[j];
+    for (int k = 0; k < kScanItems; ++k) {
+      const int j = k * kScanThreads + threadIdx.x;
+      if (base + j < n) offsets[base + j] = stage[j];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      int64_t i = base + threadIdx.x * kScanItems + k;
+      if (i < n) offsets[i] = ex + loc[k];
+    }
   }
   if (base + kScanTile >= n && threadIdx.x == 0) {
     // last tile: trailing total
@@ -161,7 +172,8 @@ extern "C" int tzk_lengths_to_offsets(const int32_t* lengths, int64_t n, int64_t
   TZK_CHECK_LAUNCH("scan_tile_sums");
   scan_tile_offsets<<<1, kScanThreads, 0, st>>>(tile_sum, tiles);
   TZK_CHECK_LAUNCH("scan_tile_offsets");
-  scan_tiles<<<(unsigned)tiles, kScanThreads, 0, st>>>(lengths, n, tile_sum, offsets);
+  if (unvalidated_switch("TZK_SCAN_STAGED")) scan_tiles<true><<<(unsigned)tiles, kScanThreads, 0, st>>>(lengths, n, tile_sum, offsets);
+  else scan_tiles<false><<<(unsigned)tiles, kScanThreads, 0, st>>>(lengths, n, tile_sum, offsets);
   TZK_CHECK_LAUNCH("scan_tiles");
   return 0;
 }

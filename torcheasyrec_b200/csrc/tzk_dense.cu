@@ -510,10 +510,7 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
 
 // TZK_INTERACT_TC=1: the DLRM-Criteo shape (27 x 16, aligned output row) on the tensor cores (tzk_interact_tc.cuh);
 // read per call (tests flip it)
-inline bool use_interact_tc() {
-  const char* e = getenv("TZK_INTERACT_TC");
-  return e && e[0] == '1';
-}
+inline bool use_interact_tc() { return unvalidated_switch("TZK_INTERACT_TC"); }
 
 inline int grid_for(int64_t n, int per_block, int max_blocks) {
   int64_t g = ceil_div64(n, per_block);

@@ -34,6 +34,7 @@
 #define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) TZK_UNPAREN kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -244,15 +245,79 @@ peer_seq_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_t* 
 // at ~750 GB/s — and its gather reads those features from local memory; only the big tables' rows cross NVLink as
 // random 64-B reads (~430 GB/s, measured).  Segment s: n[s] floats from rank r[s]'s arena at src[s] to mirror + dst[s].
 __global__ void __launch_bounds__(kThreads)
-peer_mirror_refresh_kernel(const __grid_constant__ Peers tables, const int32_t* __restrict__ seg_rank,
-                           const int64_t* __restrict__ seg_src, const int64_t* __restrict__ seg_dst,
-                           const int64_t* __restrict__ seg_n, int n_seg, float* __restrict__ mirror) {
+peer_mirror_refresh_simple_kernel(const __grid_constant__ Peers tables, const int32_t* __restrict__ seg_rank,
+                                  const int64_t* __restrict__ seg_src, const int64_t* __restrict__ seg_dst,
+                                  const int64_t* __restrict__ seg_n, int n_seg, float* __restrict__ mirror) {
   for (int s = blockIdx.y; s < n_seg; s += gridDim.y) {
     const float* src = reinterpret_cast<const float*>(tables.p[__ldg(seg_rank + s)]) + __ldg(seg_src + s);
     float* dst = mirror + __ldg(seg_dst + s);
     const int64_t n4 = __ldg(seg_n + s) >> 2;       // table starts and row sizes are multiples of 4 floats
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
       reinterpret_cast<float4*>(dst)[i] = ld_peer_f4(src + i * 4);
+  }
+}
+
+// The segments cut into chunks of kMirrorChunk floats, chunks dealt round-robin to the CTAs: every thread has
+// kMirrorChunk / (4 * kThreads) independent 16-B NVLink reads in flight (one load in flight per thread — the simple kernel —
+// pays the NVLink round trip once per 16 B and thread: ~100 us for Criteo's 7.7 MB at W = 2).  n_seg <= kMirrorMaxSeg.
+constexpr int kMirrorChunk = 4096;
+constexpr int kMirrorMaxSeg = 4 * kThreads;
+__global__ void __launch_bounds__(kThreads)
+peer_mirror_refresh_kernel(const __grid_constant__ Peers tables, const int32_t* __restrict__ seg_rank,
+                           const int64_t* __restrict__ seg_src, const int64_t* __restrict__ seg_dst,
+                           const int64_t* __restrict__ seg_n, int n_seg, float* __restrict__ mirror) {
+  TZK_DYN_SMEM(int32_t, pre);                     // [kMirrorMaxSeg + 1] chunks before segment s
+  int32_t* part = pre + kMirrorMaxSeg + 1;        // [kThreads]
+  {   // exclusive scan of the segments' chunk counts: 4 segments per thread + a Hillis-Steele scan of the 256 partial sums
+    int32_t c[4], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sidx = threadIdx.x * 4 + q;
+      c[q] = sidx < n_seg ? (int32_t)((__ldg(seg_n + sidx) + kMirrorChunk - 1) / kMirrorChunk) : 0;
+      tot += c[q];
+    }
+    part[threadIdx.x] = tot;
+    __syncthreads();
+    for (int d = 1; d < kThreads; d <<= 1) {
+      const int32_t add = (int)threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+      __syncthreads();
+      part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    int32_t run = part[threadIdx.x] - tot;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sidx = threadIdx.x * 4 + q;
+      if (sidx < n_seg) pre[sidx] = run;
+      run += c[q];
+    }
+    if (threadIdx.x == kThreads - 1) pre[n_seg] = part[kThreads - 1];
+    __syncthreads();
+  }
+  const int total = pre[n_seg];
+  constexpr int Q = kMirrorChunk / (4 * kThreads);
+  for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    int lo = 0, hi = n_seg;                       // largest s with pre[s] <= chunk (empty segments share a prefix: skip them)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (pre[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    const int sg = lo;
+    const float* src = reinterpret_cast<const float*>(tables.p[__ldg(seg_rank + sg)]) + __ldg(seg_src + sg);
+    float* dst = mirror + __ldg(seg_dst + sg);
+    const int64_t n4 = __ldg(seg_n + sg) >> 2;
+    const int64_t base4 = (int64_t)(chunk - pre[sg]) * (kMirrorChunk / 4);
+    float4 v[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int64_t i = base4 + threadIdx.x + q * kThreads;
+      if (i < n4) v[q] = ld_peer_f4(src + i * 4);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int64_t i = base4 + threadIdx.x + q * kThreads;
+      if (i < n4) reinterpret_cast<float4*>(dst)[i] = v[q];
+    }
   }
 }
 
@@ -487,8 +552,13 @@ __global__ void __launch_bounds__(kThreads)
 peer_allreduce_mean_kernel(const __grid_constant__ Peers src, int W, int64_t n, float* __restrict__ out) {
   const float inv = 1.0f / (float)W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float acc = reinterpret_cast<const float*>(src.p[0])[i];
-    for (int r = 1; r < W; ++r) acc += reinterpret_cast<const float*>(src.p[r])[i];
+    float v[kMaxPeers];           // every rank's value requested before the first one is consumed: ONE NVLink round trip
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) v[r] = r < W ? reinterpret_cast<const float*>(src.p[r])[i] : 0.f;
+    float acc = v[0];
+#pragma unroll
+    for (int r = 1; r < kMaxPeers; ++r)
+      if (r < W) acc += v[r];     // rank order: the same bits on every rank
     out[i] = acc * inv;
   }
 }
@@ -585,13 +655,32 @@ extern "C" int tzk_peer_mirror_refresh(const uint64_t* table_ptrs, int32_t W, co
   if (fill(&t, table_ptrs, W) || n_seg < 0) return 1;
   if (n_seg == 0) return 0;
   if (!seg_rank || !seg_src || !seg_dst || !seg_n || !mirror) return 1;
+  // TZK_PEER_MIRROR_CHUNKED: the chunked kernel (unvalidated on hardware: off unless it or TZK_EXPERIMENTAL is 1)
+  const char* mc = getenv("TZK_PEER_MIRROR_CHUNKED");
+  const char* xp = getenv("TZK_EXPERIMENTAL");
 #ifdef TZK_CPU_SHIM
-  dim3 grid(1, n_seg);            // (host emulation: one std::thread per CUDA thread — keep the launch small)
+  const bool chunked = !(mc && mc[0] == '0');      // (host emulation: the chunked kernel unless told otherwise)
+  (void)xp;
 #else
-  dim3 grid(8, n_seg < 4096 ? n_seg : 4096);
+  const bool chunked = (mc && (mc[0] == '0' || mc[0] == '1')) ? mc[0] == '1' : (xp && xp[0] == '1');
 #endif
-  TZK_LAUNCH((peer_mirror_refresh_kernel), grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream), t, seg_rank, seg_src,
-             seg_dst, seg_n, n_seg, mirror);
+  if (n_seg > kMirrorMaxSeg || !chunked) {
+#ifdef TZK_CPU_SHIM
+    dim3 grid(1, n_seg);          // (one std::thread per CUDA thread — keep the launch small)
+#else
+    dim3 grid(8, n_seg < 4096 ? n_seg : 4096);
+#endif
+    TZK_LAUNCH((peer_mirror_refresh_simple_kernel), grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream), t, seg_rank,
+               seg_src, seg_dst, seg_n, n_seg, mirror);
+    return cudaGetLastError() == cudaSuccess ? 0 : 3;
+  }
+#ifdef TZK_CPU_SHIM
+  const int grid = 3;             // (host emulation: one std::thread per CUDA thread — keep the launch small)
+#else
+  const int grid = 148 * 4;
+#endif
+  TZK_LAUNCH((peer_mirror_refresh_kernel), grid, kThreads, (kMirrorMaxSeg + 1 + kThreads) * sizeof(int32_t),
+             reinterpret_cast<cudaStream_t>(stream), t, seg_rank, seg_src, seg_dst, seg_n, n_seg, mirror);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

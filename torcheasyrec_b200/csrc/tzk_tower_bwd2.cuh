@@ -400,14 +400,23 @@ inline int dw_grid(int64_t M) {
 
 inline size_t workspace_bytes(int64_t M, int K, int N) { return (size_t)dw_grid(M) * ((size_t)N * K + N) * sizeof(float); }
 
-// the tile kernel pads K and N to its compiled sizes, so every K, N <= 64 is covered
-inline bool supported(int K, int N) { return K >= 1 && N >= 1 && K <= 64 && N <= 64; }
+// Switches of code paths that have not been through a GPU validation pass yet: `name`=0/1 decides; unset, TZK_EXPERIMENTAL=1
+// turns them all on (scripts/gpu_call_n1.sh); otherwise they stay off.  A validated path gets its default flipped here.
+inline bool unvalidated_switch(const char* name) {
+  const char* e = getenv(name);
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  const char* x = getenv("TZK_EXPERIMENTAL");
+  return x && x[0] == '1';
+}
 
-// TZK_SMALL_LINEAR_DW=0: the row-group dW kernel (straight from global memory, U rows in flight per thread) instead of the
-// tile kernel — kept for A/B timing; read per call
-inline bool use_dw_tiles() {
-  const char* e = getenv("TZK_SMALL_LINEAR_DW");
-  return !(e && e[0] == '0');
+// TZK_SMALL_LINEAR_DW=1: the tile kernel; 0: the row-group dW kernel (straight from global memory, U rows in flight per
+// thread).  Read per call.
+inline bool use_dw_tiles() { return unvalidated_switch("TZK_SMALL_LINEAR_DW"); }
+
+// the tile kernel pads K and N to its compiled sizes, so every K, N <= 64 is covered; the row-group kernel needs its
+// mapping to fit 128 threads (otherwise the caller keeps the tile kernel of tzk_tower.cu)
+inline bool supported(int K, int N) {
+  return K >= 1 && N >= 1 && K <= 64 && N <= 64 && (use_dw_tiles() || pick(K, N).t <= kThreads);
 }
 
 // dz = dy * (relu ? y > 0 : 1); dx = dz @ W (skipped when dx is NULL); dW = dz^T @ x; db = colsum(dz) (db nullable).

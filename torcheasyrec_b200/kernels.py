@@ -138,10 +138,25 @@ def _rows2d(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
     return t, ld
 
 
+def _unvalidated_switch(name: str) -> bool:
+    """Mirrors unvalidated_switch() of csrc/tzk_common.cuh: `name`=0/1 decides, else TZK_EXPERIMENTAL=1 turns it on."""
+    e = os.environ.get(name, "")
+    if e[:1] in ("0", "1"):
+        return e[:1] == "1"
+    return os.environ.get("TZK_EXPERIMENTAL", "")[:1] == "1"
+
+
 def _small_linear_rows_path(K: int, N: int) -> bool:
-    """Mirrors use_bwd2() of csrc/tzk_tower.cu (launch accounting only): dx rows kernel + dW tile kernel + reduction for
-    every K, N <= 64 unless TZK_SMALL_LINEAR_BWD=1 selects the 128-row tile kernel."""
-    return os.environ.get("TZK_SMALL_LINEAR_BWD", "")[:1] != "1" and 1 <= K <= 64 and 1 <= N <= 64
+    """Mirrors use_bwd2() of csrc/tzk_tower.cu (launch accounting only)."""
+    if os.environ.get("TZK_SMALL_LINEAR_BWD", "")[:1] == "1" or not (1 <= K <= 64 and 1 <= N <= 64):
+        return False
+    if _unvalidated_switch("TZK_SMALL_LINEAR_DW"):
+        return True
+    nb = 4 if N % 4 == 0 else 1
+    t = -(-N // nb) * -(-K // 4)
+    if t > 128:
+        t = -(-N // nb) * -(-K // 8)
+    return t <= 128
 
 
 def _tile_path(lay: "FeatureLayout") -> bool:
