@@ -170,6 +170,13 @@ dot_interact27_bwd_tc_kernel(const float* __restrict__ dense, int64_t ld_dense, 
         else if (j < kN) v = *reinterpret_cast<const float2*>(sr + (j - 1) * kD + 2 * g);
         xv[ks][h] = v;
       }
+    // pass-through gradient of the four rows this lane finishes: requested now, consumed after the MMAs
+    float4 pass[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = g + 8 * q;
+      pass[q] = i < kN ? *reinterpret_cast<const float4*>(go + kInter + i * kD + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // pair gradients -> symmetric S (coalesced reads, 11 per lane)
     {
       float gv[11];
@@ -235,7 +242,7 @@ dot_interact27_bwd_tc_kernel(const float* __restrict__ dense, int64_t ld_dense, 
         if (i >= kN) continue;
         float4 v = make_float4(acc[mt][0][2 * hrow], acc[mt][1][2 * hrow], acc[mt][0][2 * hrow + 1],
                                acc[mt][1][2 * hrow + 1]);
-        const float4 p = *reinterpret_cast<const float4*>(go + kInter + i * kD + 4 * t);   // pass-through gradient
+        const float4 p = pass[2 * mt + hrow];
         v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
         if (i == 0) *reinterpret_cast<float4*>(d_dense + b * ld_ddense + 4 * t) = v;
         else *reinterpret_cast<float4*>(d_sparse + b * ld_dsparse + (i - 1) * kD + 4 * t) = v;
