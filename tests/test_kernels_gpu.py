@@ -438,8 +438,7 @@ def test_tower_helpers_bias_act_and_relu_bwd_colsum(kernels, N):
     np.testing.assert_allclose(cs2.cpu().numpy(), dy.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
 
 
-@pytest.fixture(params=["rows", "tile", pytest.param("rows+dw_tiles", marks=pytest.mark.skipif(
-    os.environ.get("TZK_EXPERIMENTAL") != "1", reason="unvalidated path: set TZK_EXPERIMENTAL=1"))])
+@pytest.fixture(params=["rows", "tile", "rows+dw_tiles"])
 def slb_path(request, monkeypatch):
     """Both backward implementations behind tzk_small_linear_bwd: the barrier-free dx / dW kernels (default where the
     shape is covered) and the 128-row shared-memory tile kernel (TZK_SMALL_LINEAR_BWD=1; also the fallback)."""
@@ -764,7 +763,6 @@ def _split_interleaved(arena, lay, tables, feat_table):
     return [w[t] for t in range(len(tables))], [s[t] for t in range(len(tables))]
 
 
-@unvalidated
 @pytest.mark.parametrize("case", ["criteo_like_L1", "deepfm_mixed_dims", "shared_table", "wide_rows", "unaligned_dims",
                                   "tiny_tables_long_runs", "multi_hot_33", "long_runs_d4"])
 @pytest.mark.parametrize("pool", [O.POOL_SUM, O.POOL_MEAN])
@@ -805,7 +803,6 @@ def test_interleaved_gather_and_adagrad_update(kernels, case, pool):
         np.testing.assert_allclose(gs_[t], st_np[t], rtol=state_rtol, atol=1e-7, err_msg=f"state {t}")
 
 
-@unvalidated
 def test_interleaved_split_sort_apply_and_sequence_layout(kernels):
     """The two halves of the fused backward (sort on the ids, apply on the gradient) and the un-pooled lookup / update."""
     rng = np.random.default_rng(77)
@@ -829,7 +826,6 @@ def test_interleaved_split_sort_apply_and_sequence_layout(kernels):
         np.testing.assert_allclose(gs_[t], st_np[t], rtol=2e-5, atol=1e-7)
 
 
-@unvalidated
 def test_interleaved_rejects_what_it_does_not_cover(kernels):
     lay = build_layout([10], [16], [0], [0], interleaved=True).to(DEV)
     arena = torch.zeros(lay.arena_elems, device=DEV)
@@ -840,7 +836,6 @@ def test_interleaved_rejects_what_it_does_not_cover(kernels):
 
 
 # ---- DLRM interaction on the tensor cores (csrc/tzk_interact_tc.cuh; TZK_INTERACT_TC=1) ------------------------------------
-@unvalidated
 @pytest.mark.parametrize("B", [1, 8, 777, 40000])
 def test_interaction_tensor_core_kernels_match_reference_and_fp64(kernels, monkeypatch, B):
     """mma.sync m16n8k8 with the 3xTF32 split, DLRM-Criteo shape (27 x 16, [351 | 0 | 16 | 416] rows): the reference's own
@@ -859,6 +854,7 @@ def test_interaction_tensor_core_kernels_match_reference_and_fp64(kernels, monke
     ref = kernels.dot_interact_fwd(cu(dense), cu(sparse), 26, 16, True, True, pad_to=4, p_pad=1)
     rdd, rds = kernels.dot_interact_bwd(cu(dense), cu(sparse), cu(d_pad), 26, 16, True, True, p_pad=1)
     monkeypatch.setenv("TZK_INTERACT_TC", "1")
+    monkeypatch.setenv("TZK_INTERACT_TC_BWD", "1")
     got = kernels.dot_interact_fwd(cu(dense), cu(sparse), 26, 16, True, True, pad_to=4, p_pad=1)
     dd, ds = kernels.dot_interact_bwd(cu(dense), cu(sparse), cu(d_pad), 26, 16, True, True, p_pad=1)
     torch.cuda.synchronize()

@@ -52,8 +52,7 @@ def test_train_steps_match_oracle(name):
             # the gradient entering the fused update comes out of cuBLAS (GPU) vs MKL (CPU) dense towers, which
             # differ by ~1e-6 rel; the kernels themselves are held to 1e-5 in test_kernels_gpu.py
             # (the GPU arena holds [weight row | accumulator row] lines, the CPU twin dense rows: compare per table)
-            assert cg.layout.interleaved == (os.environ.get("TZK_INTERLEAVE", os.environ.get("TZK_EXPERIMENTAL", "0")) == "1")
-            assert not cc.layout.interleaved
+            assert cg.layout.interleaved == (os.environ.get("TZK_INTERLEAVE", "1") != "0") and not cc.layout.interleaved
             np.testing.assert_allclose(cg.dense_weights().cpu().numpy(), cc.dense_weights().numpy(), rtol=5e-5, atol=1e-6)
             for t in range(len(cg._configs)):
                 np.testing.assert_allclose(cg.table_state(t).cpu().numpy(), cc.table_state(t).numpy(), rtol=1e-4,
@@ -88,7 +87,10 @@ def test_cuda_graph_step_equals_eager_step():
     b = Pipeline("dlrm_criteo", device="cuda:0", max_rows=5000, seed=3)   # eager twin, cloned AFTER the capture
     b.model.load_state_dict(a.model.state_dict())
     for ca, cb in zip(a.model.sparse_collections(), b.model.sparse_collections()):
-        cb.weights.data.copy_(ca.weights.data)      # interleaved arena: weights and Adagrad accumulators in one buffer
+        if ca.layout.interleaved:
+            cb.weights.data.copy_(ca.weights.data)  # weights and Adagrad accumulators live in one buffer
+        else:
+            cb.opt_state.copy_(ca.opt_state)
     # deepcopy: Optimizer.load_state_dict keeps same-device tensors by reference, the twins must not share moments
     b.dense_optimizer.load_state_dict(copy.deepcopy(a.dense_optimizer.state_dict()))
     losses_a, losses_b = [], []

@@ -508,9 +508,16 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
   }
 }
 
-// TZK_INTERACT_TC=1: the DLRM-Criteo shape (27 x 16, aligned output row) on the tensor cores (tzk_interact_tc.cuh);
-// read per call (tests flip it)
-inline bool use_interact_tc() { return unvalidated_switch("TZK_INTERACT_TC"); }
+// The DLRM-Criteo shape (27 x 16, aligned output row) on the tensor cores (tzk_interact_tc.cuh); read per call (tests flip
+// it).  Forward: default on (validated on B200: 82.7 -> 58.7 us at B = 65536), TZK_INTERACT_TC=0 / TZK_INTERACT_TC_FWD=0
+// selects the FFMA kernel.  Backward: measured on par with the FFMA kernel (126 vs 121 us), so it stays a switch
+// (TZK_INTERACT_TC_BWD=1).
+inline bool env_is(const char* name, char v) {
+  const char* e = getenv(name);
+  return e && e[0] == v;
+}
+inline bool use_interact_tc_fwd() { return !env_is("TZK_INTERACT_TC", '0') && !env_is("TZK_INTERACT_TC_FWD", '0'); }
+inline bool use_interact_tc_bwd() { return !env_is("TZK_INTERACT_TC", '0') && env_is("TZK_INTERACT_TC_BWD", '1'); }
 
 inline int grid_for(int64_t n, int per_block, int max_blocks) {
   int64_t g = ceil_div64(n, per_block);
@@ -606,7 +613,7 @@ extern "C" int tzk_dot_interact_fwd(const float* dense, int64_t ld_dense, const 
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
   TZK_REQUIRE(p_pad >= 0 && p_pad < 4, "dot_interact_fwd: p_pad must be in [0,3]");
-  if (use_interact_tc() && tzk_itc::covers(dense, ld_dense, ld_sparse, Ns, D, copy_dense, copy_sparse, p_pad, out, ld_out)) {
+  if (use_interact_tc_fwd() && tzk_itc::covers(dense, ld_dense, ld_sparse, Ns, D, copy_dense, copy_sparse, p_pad, out, ld_out)) {
     tzk_itc::dot_interact27_fwd_tc_kernel<<<tzk_itc::grid_for(B, kSmCountB200 * 8), tzk_itc::kWarps * 32,
                                             tzk_itc::fwd_smem(), as_stream(stream)>>>(dense, ld_dense, sparse, ld_sparse,
                                                                                       B, out, ld_out);
@@ -665,7 +672,7 @@ extern "C" int tzk_dot_interact_bwd(const float* dense, int64_t ld_dense, const 
   const int Np = (N + 3) & ~3;
   const int P = N * (N - 1) / 2;
   TZK_REQUIRE(p_pad >= 0 && p_pad < 4, "dot_interact_bwd: p_pad must be in [0,3]");
-  if (use_interact_tc() && tzk_itc::covers(dense, ld_dense, ld_sparse, Ns, D, copy_dense, copy_sparse, p_pad, d_out, ld_dout)) {
+  if (use_interact_tc_bwd() && tzk_itc::covers(dense, ld_dense, ld_sparse, Ns, D, copy_dense, copy_sparse, p_pad, d_out, ld_dout)) {
     tzk_itc::dot_interact27_bwd_tc_kernel<<<tzk_itc::grid_for(B, kSmCountB200 * 8), tzk_itc::kWarps * 32,
                                             tzk_itc::bwd_smem(), as_stream(stream)>>>(
         dense, ld_dense, sparse, ld_sparse, d_out, ld_dout, B, d_dense, ld_ddense, d_sparse, ld_dsparse);

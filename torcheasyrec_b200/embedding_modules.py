@@ -313,9 +313,8 @@ class _ArenaCollection(nn.Module):
         dev = self.weights.device
         if self.layout.interleaved:        # a second set_optimizer: back to dense rows first (the old state is dropped)
             self._relayout(False, 0.0)
-        # TZK_INTERLEAVE: "1" / "0" decide; "force": also off CUDA (host-logic tests); unset: on only with TZK_EXPERIMENTAL=1
-        # until the layout has been through a GPU validation pass (scripts/gpu_call_n1.sh)
-        env = os.environ.get("TZK_INTERLEAVE", "1" if os.environ.get("TZK_EXPERIMENTAL") == "1" else "0")
+        # TZK_INTERLEAVE: "0": dense rows; "force": also off CUDA (host-logic tests); default on (validated on B200)
+        env = os.environ.get("TZK_INTERLEAVE", "1")
         if (spec.kind == OPT_ADAGRAD and self.allow_interleave and self.table_dtype == torch.float32
                 and ((dev.type == "cuda" and env != "0") or env == "force")):
             # a D = 16 row and its accumulator in ONE 128-B line: the fused update reads and writes whole lines (two

@@ -150,7 +150,7 @@ def _small_linear_rows_path(K: int, N: int) -> bool:
     """Mirrors use_bwd2() of csrc/tzk_tower.cu (launch accounting only)."""
     if os.environ.get("TZK_SMALL_LINEAR_BWD", "")[:1] == "1" or not (1 <= K <= 64 and 1 <= N <= 64):
         return False
-    if _unvalidated_switch("TZK_SMALL_LINEAR_DW"):
+    if os.environ.get("TZK_SMALL_LINEAR_DW", "1")[:1] != "0":
         return True
     nb = 4 if N % 4 == 0 else 1
     t = -(-N // nb) * -(-K // 4)
