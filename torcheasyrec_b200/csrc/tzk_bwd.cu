@@ -360,9 +360,12 @@ __device__ __forceinline__ float group_sum(float v) {
 
 // finish a run: `acc` holds this lane's chunk(s) of the summed gradient.  Only called with all G lanes
 // of the group active (needed for the row-wise shuffle).
+// `pre_w` / `pre_s` (CH == 1, VEC == 4, fp32 tables): the row's weight / first-state chunk of this lane, already
+// requested by the caller (next to the gradient rows instead of after them).
 template <int G, int VEC, int CH>
 __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, int64_t row, int64_t key,
-                                           float (&acc)[CH][VEC], int lane) {
+                                           float (&acc)[CH][VEC], int lane, const float4* pre_w = nullptr,
+                                           const float4* pre_s = nullptr) {
   if (a.optimizer == TZK_OPT_ACCUM_OUT) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
@@ -413,13 +416,13 @@ __device__ __forceinline__ void finish_run(const BwdArgs& a, const BwdFeat& d, i
         const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
         w4 = make_float4(lo.x, lo.y, hi.x, hi.y);
       } else {
-        w4 = *reinterpret_cast<float4*>(wp);
+        w4 = pre_w ? *pre_w : *reinterpret_cast<float4*>(wp);
       }
       float w[4] = {w4.x, w4.y, w4.z, w4.w};
       float s[4] = {0.f, 0.f, 0.f, 0.f};
       float s2[4] = {0.f, 0.f, 0.f, 0.f};
       if (sp) {
-        float4 s4 = *reinterpret_cast<float4*>(sp);
+        float4 s4 = pre_s ? *pre_s : *reinterpret_cast<float4*>(sp);
         s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
       }
       if (sp2) {
@@ -529,64 +532,101 @@ __device__ __forceinline__ void run_update_body(const BwdArgs& a, const PeerGrad
                                                 const KeyT* __restrict__ keys,
                                                 const int32_t* __restrict__ vals, int cta, int n_ctas) {
   constexpr int NG = kThreads / G;
-  constexpr int kPos = 1;   // positions per lane group per iteration (2 and 4 with a batched single-run path were
-                            // measured slower: 349 / 375 / 461 us for 1 / 2 / 4 on DLRM-Criteo)
+  // One sorted position per lane group and iteration (2 and 4 positions with a batched single-run path were measured
+  // slower in round 1: 349 / 375 / 461 us for 1 / 2 / 4 on DLRM-Criteo).  The keys / value of the NEXT position are
+  // requested before the current one is worked on.
   const int lane = threadIdx.x % G;
-  const int64_t stride = (int64_t)n_ctas * NG * kPos;
+  const int64_t stride = (int64_t)n_ctas * NG;
   // all G lanes of a group follow the same control flow (positions, keys, run lengths are group-uniform)
-  for (int64_t p0 = ((int64_t)cta * NG + threadIdx.x / G) * kPos; p0 < a.n; p0 += stride) {
-    KeyT key[kPos + 2];  // key[0] = left neighbour, key[kPos+1] = right neighbour
-    int32_t v[kPos];
-    key[0] = p0 > 0 ? keys[p0 - 1] : (KeyT)~keys[p0];
-#pragma unroll
-    for (int u = 0; u < kPos; ++u) {
-      const int64_t p = p0 + u;
-      key[u + 1] = p < a.n ? keys[p] : (KeyT)~key[u];
-      v[u] = p < a.n ? vals[p] : 0;
+  int64_t p0 = (int64_t)cta * NG + threadIdx.x / G;
+  KeyT kl = 0, kc = 0, kr = 0;     // left neighbour, this position, right neighbour
+  int32_t vc = 0;
+  auto fetch = [&](int64_t p, KeyT& l, KeyT& c, KeyT& r, int32_t& vv) {
+    if (p < a.n) {
+      c = keys[p];
+      l = p > 0 ? keys[p - 1] : (KeyT)~c;
+      r = p + 1 < a.n ? keys[p + 1] : (KeyT)~c;
+      vv = vals[p];
     }
-    {
-      const int64_t pn = p0 + kPos;
-      key[kPos + 1] = pn < a.n ? keys[pn] : (KeyT)~key[kPos];
-    }
-    bool head[kPos], single[kPos];
-#pragma unroll
-    for (int u = 0; u < kPos; ++u) {
-      head[u] = (p0 + u < a.n) && key[u + 1] != key[u] && key[u + 1] != (KeyT)a.sentinel;
-      single[u] = head[u] && ((p0 + u + 1 >= a.n) || key[u + 2] != key[u + 1]);
-    }
+  };
+  fetch(p0, kl, kc, kr, vc);
+  for (; p0 < a.n; p0 += stride) {
+    KeyT nl = 0, nc = 0, nr = 0;
+    int32_t nv = 0;
+    fetch(p0 + stride, nl, nc, nr, nv);
+    const KeyT key_l = kl, key_c = kc, key_r = kr;
+    const int32_t v_c = vc;
+    kl = nl; kc = nc; kr = nr; vc = nv;
+    const bool head = key_c != key_l && key_c != (KeyT)a.sentinel;
+    (void)key_r;
     // ---- every run head: sum the run (<= kShortRun) in sorted order and update, or hand it to the long-run kernels
-#pragma unroll 1
-    for (int u = 0; u < kPos; ++u) {
-      if (!head[u]) continue;
-      const int64_t p = p0 + u;
-      const KeyT k0 = key[u + 1];
+    {
+      if (!head) continue;
+      const int64_t p = p0;
+      const KeyT k0 = key_c;
       int len = 1;
-      while (len <= kShortRun && p + len < a.n && keys[p + len] == k0) ++len;
+      if (key_r == k0) {
+        len = 2;
+        while (len <= kShortRun && p + len < a.n && keys[p + len] == k0) ++len;
+      }
       if (len > kShortRun) continue;   // long runs are on the work list (find_long_runs_kernel, id half) for the chunk CTAs
-      const int32_t v0 = v[u];
+      const int32_t v0 = v_c;
       int f00;
       if (a.pooled) f00 = bag_feat(a, v0); else f00 = feat_of_key<KeyT>(fd, a.F, k0);
       const BwdFeat d = fd[f00];
       const int64_t row = (int64_t)k0 - d.key_base;
+      // the row's weight / state chunks depend on the key only: requested here, next to the gradient rows, so that a
+      // single-position run costs ONE exposed DRAM latency instead of two dependent ones
+      constexpr bool kPre = (VEC == 4 && CH == 1);
+      float4 pre_w = make_float4(0.f, 0.f, 0.f, 0.f), pre_s = pre_w;
+      const bool pre = kPre && !a.w_f16 && a.optimizer != TZK_OPT_ACCUM_OUT;      // (group-uniform)
+      if (pre && lane * 4 < d.dim) {
+        const float* wp = a.weights + d.w_off + row * d.stride + lane * 4;
+        pre_w = ld_rw_f4(wp);
+        if (has_elem_state(a)) pre_s = ld_rw_f4(a.interleaved ? wp + d.dim : a.state + (d.w_off + row * d.stride + lane * 4));
+      }
       float acc[CH][VEC];
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-      for (int j = 0; j < len; ++j) {
-        const Entry en = entry_of(a, gp, fd, j == 0 ? v0 : vals[p + j], f00);
+      // kGU gradient rows of the run in flight; added in sorted order
+      constexpr int kGU = 4;
+      for (int j0 = 0; j0 < len; j0 += kGU) {
+        Entry en[kGU];
+        bool ok[kGU];
+#pragma unroll
+        for (int q = 0; q < kGU; ++q) {
+          const int j = j0 + q;
+          ok[q] = j < len;
+          en[q] = entry_of(a, gp, fd, (j == 0 || !ok[q]) ? v0 : vals[p + j], f00);
+        }
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
           const int c = (ch * G + lane) * VEC;
           if (c < d.dim) {
-            float gg[VEC];
-            load_grad<VEC>(en.g + c, gg, a.peer_w);
+            float gg[kGU][VEC];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) acc[ch][k] += gg[k] * en.scale;
+            for (int q = 0; q < kGU; ++q) {
+              if (ok[q]) {
+                load_grad<VEC>(en[q].g + c, gg[q], a.peer_w);
+              } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) gg[q][k] = 0.f;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < kGU; ++q)
+              if (ok[q]) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[ch][k] += gg[q][k] * en[q].scale;
+              }
           }
         }
       }
-      finish_run<G, VEC, CH>(a, d, row, (int64_t)k0, acc, lane);
+      // (one call site: the row-wise variants shuffle inside, every lane of the group must arrive at the same instruction)
+      finish_run<G, VEC, CH>(a, d, row, (int64_t)k0, acc, lane, pre ? &pre_w : nullptr,
+                             (pre && has_elem_state(a)) ? &pre_s : nullptr);
     }
   }
 }
@@ -696,7 +736,7 @@ __device__ __forceinline__ void long_chunk_body(const BwdArgs& a, const PeerGrad
 
 // ---- 3 + 4 in one launch: CTAs [0, n_short) walk the sorted positions (short runs), the rest serve the long-run list
 template <typename KeyT, int G, int VEC, int CH>
-__global__ void __launch_bounds__(kThreads, CH == 1 ? 5 : 1)     // 5 CTAs / SM like the short-run kernel had on its own
+__global__ void __launch_bounds__(kThreads, CH == 1 ? 4 : 1)     // 4 CTAs / SM: 64 registers (weight / state prefetch + 2 gradient rows in flight)
 fused_apply_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int64_t* __restrict__ feat_rows,
                    const int64_t* __restrict__ feat_key_base, const int32_t* __restrict__ feat_dim,
                    const int32_t* __restrict__ feat_col, const int32_t* __restrict__ feat_pool,

@@ -167,6 +167,11 @@ class _ArenaCollection(nn.Module):
         # [weight row | Adagrad accumulator row] interleaving (set_optimizer): unsharded CUDA collections only; the local
         # shards of sharded collections keep dense rows (their arenas are read by peers: csrc/tzk_peer.cu)
         self.allow_interleave = True
+        # the fused update runs on a side stream and is normally joined when the backward pass ends; a step driver that
+        # promises to call join_pending() itself (engine.Pipeline.step_body: after the dense optimizer step) sets this and
+        # gets the dense-gradient sync and the dense optimizer overlapped with the sparse update as well
+        self.defer_join = False
+        self._pending_join = None
         if self._device.type != "meta":
             self.reset_parameters()
             self.layout.to(self._device)
@@ -380,6 +385,14 @@ class _ArenaCollection(nn.Module):
             self._side = st
         return st
 
+    def join_pending(self) -> None:
+        """Orders the current stream after a fused update that is still running on the side stream (defer_join)."""
+        pj = self._pending_join
+        if pj is not None:
+            torch.cuda.current_stream().wait_stream(pj)
+            self._pending_join = None
+            self._pending_apply = None
+
     def _hook_tensor(self) -> torch.Tensor:
         # autograd needs one differentiable input to schedule the fused backward
         if self._hook is None or self._hook.device != self.weights.device:
@@ -455,7 +468,10 @@ def _fused_backward(ctx, mod, pooled: bool, grad, ids, offsets, who: str) -> Non
                 cur.wait_stream(side)
                 mod._pending_apply = None
 
-            torch.autograd.Variable._execution_engine.queue_callback(_join)
+            if mod.defer_join:
+                mod._pending_join = side      # the step driver joins after the dense optimizer step (join_pending)
+            else:
+                torch.autograd.Variable._execution_engine.queue_callback(_join)
         else:
             cur.wait_stream(side)
             k.fused_bwd_apply(spec.kind, pooled, grad, mod.weights.data, mod.opt_state, mod.layout, offsets,

@@ -8,6 +8,7 @@ replayed; a side stream stages the next host batch (pinned H2D) while the curren
 Variable-shape workloads (sequence features) run the same code eagerly.
 """
 
+import os
 from typing import Any, Dict, List, Optional, Sequence
 
 import torch
@@ -125,12 +126,34 @@ class Pipeline:
         """forward + backward (fused sparse update inside) + dense gradient sync + dense optimizer step."""
         if self.grad_sync is not None:
             self.grad_sync.zero()
-        loss, _ = self.train_wrapper(batch)
-        loss.backward()
-        if self.grad_sync is not None:
-            self.grad_sync.sync()
-        self.dense_optimizer.step()
+        # the fused sparse updates stay on their side streams through the dense-gradient sync and the dense optimizer step
+        # (neither touches a table); they are joined here, at the end of the step, instead of at the end of backward()
+        joiners = self._sparse_joiners() if os.environ.get("TZK_DEFER_JOIN", "1") != "0" else []
+        for j in joiners:
+            j.defer_join = True
+        try:
+            loss, _ = self.train_wrapper(batch)
+            loss.backward()
+            if self.grad_sync is not None:
+                self.grad_sync.sync()
+            self.dense_optimizer.step()
+        finally:
+            for j in joiners:
+                j.defer_join = False
+                j.join_pending()
         return loss.detach()
+
+    def _sparse_joiners(self) -> list:
+        """Everything that runs a fused sparse update on a side stream: unsharded collections, peer-exchange states."""
+        out = getattr(self, "_joiners", None)
+        if out is None:
+            from .embedding_modules import _ArenaCollection
+
+            out = [m for m in self.model.modules() if isinstance(m, _ArenaCollection)]
+            for sm in self.sharded:
+                out += list(getattr(sm, "_peer_states", []) or [])
+            self._joiners = out
+        return out
 
     def eager_step(self, batch: Batch) -> torch.Tensor:
         if self.grad_sync is None:

@@ -356,10 +356,10 @@ class PeerState(PeerBase):
         lay = g.local.layout
         push = self.bwd_mode == "push"
         sm = self.small
-        # TZK_PEER_ACCUM_SIDE=1: the per-row sums of the small tables' gradients (a pass over ALL local ids) leave the
+        # (TZK_PEER_ACCUM_SIDE=0 switches this off) The per-row sums of the small tables' gradients (a pass over ALL local ids) leave the
         # main stream: they run on the side stream next to the push, followed by a barrier of their own (site_b2) — the
         # main stream only pushes the big tables' rows and crosses barrier B.
-        accum_side = (sm is not None and push and os.environ.get("TZK_PEER_ACCUM_SIDE", "0") == "1"
+        accum_side = (sm is not None and push and os.environ.get("TZK_PEER_ACCUM_SIDE", "1") != "0"
                       and self._side_stream() is not None)
 
         def accumulate_small():
@@ -424,10 +424,23 @@ class PeerState(PeerBase):
             cur.wait_stream(self._side_stream())
             self._pending_accum = None
 
+        if getattr(self, "defer_join", False):    # the step driver joins after the dense optimizer step (join_pending)
+            self._pending_join = True
+            return
         try:
             torch.autograd.Variable._execution_engine.queue_callback(join)
         except RuntimeError:                  # not inside a backward pass
             join()
+
+
+def _peer_join_pending(st: "PeerState") -> None:
+    if getattr(st, "_pending_join", False) and st._side_stream() is not None:
+        torch.cuda.current_stream().wait_stream(st._side_stream())
+    st._pending_join = False
+    st._pending_accum = None
+
+
+PeerState.join_pending = _peer_join_pending
 
 
 class _PeerLookup(torch.autograd.Function):
