@@ -349,6 +349,14 @@ int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_o
                                const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
                                const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim, float* out,
                                int64_t ld_out, const float* mirror, const int64_t* feat_mirror_off, tzk_stream_t stream);
+/* the same lookup for the features listed in feat_sel [n_sel] only (device int32 indices into the F descriptors; only their
+ * output columns are written): complementary lists on two streams overlap the mirrored half with the NVLink half */
+int tzk_peer_pooled_gather_fwd_sel(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
+                                   const int64_t* feat_block, const int32_t* feat_owner, const int32_t* feat_dim,
+                                   const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
+                                   const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim, float* out,
+                                   int64_t ld_out, const float* mirror, const int64_t* feat_mirror_off,
+                                   const int32_t* feat_sel, int32_t n_sel, tzk_stream_t stream);
 int tzk_peer_seq_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
                             const int64_t* feat_block, const int32_t* feat_owner, const int64_t* ids,
                             const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t D, int64_t nnz, float* out,

@@ -225,15 +225,22 @@ class OracleKernels:
             m[d:d + n] = tables.everyone[r].numpy()[s:s + n]
 
     def peer_pooled_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W,
-                               out=None, mirror=None, feat_mirror_off=None):
-        if mirror is not None:       # the model keeps reading the owners (the mirror is checked to be an exact copy)
+                               out=None, mirror=None, feat_mirror_off=None, feat_sel=None):
+        sel = None if feat_sel is None else set(feat_sel.tolist())
+        uses_mirror = mirror is not None and (sel is None or any(feat_mirror_off.tolist()[f] >= 0 for f in sel))
+        if uses_mirror:              # the model keeps reading the owners (the mirror is checked to be an exact copy)
             self._check_mirror(tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, W, mirror, feat_mirror_off)
         F = lay.num_features
         blocks, owners = feat_block.tolist(), feat_owner.tolist()
         rows, w_off = feat_rows.tolist(), rf_w_off.tolist()
         idl, off = ids.tolist(), offsets.tolist()
         o = np.zeros((B, lay.total_dim), dtype=np.float32)
+        if sel is not None:          # a launch over a feature list writes those features' columns only
+            assert out is not None
+            o = out.numpy()
         for f in range(F):
+            if sel is not None and f not in sel:
+                continue
             D, col = lay.dim[f], lay.col[f]
             for b in range(B):
                 s, e = off[f * B + b], off[f * B + b + 1]
@@ -246,6 +253,8 @@ class OracleKernels:
                 if lay.pool[f] == 1 and e > s:
                     acc = acc * np.float32(1.0 / (e - s))
                 o[b, col:col + D] = acc
+        if sel is not None:
+            return out
         res = torch.from_numpy(o)
         if out is not None:
             out.copy_(res)

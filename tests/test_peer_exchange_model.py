@@ -58,6 +58,7 @@ def host_compiled_peer_lib(tmp_path_factory):
                     "-fPIC", "-o", out], check=True)
     L = ctypes.CDLL(out)
     L.tzk_peer_pooled_gather_fwd.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P, I64, P, P, P]
+    L.tzk_peer_pooled_gather_fwd_sel.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P, I64, P, P, P, I32, P]
     L.tzk_peer_seq_gather_fwd.argtypes = [P, P, P, P, P, P, P, I32, I32, I32, I32, I64, P, P, P, P]
     L.tzk_peer_mirror_refresh.argtypes = [P, I32, P, P, P, P, I32, P, P]
     L.tzk_peer_bucketize_workspace_bytes.restype = ctypes.c_size_t
@@ -89,9 +90,18 @@ class SourceKernels(OracleKernels):
         assert rc == 0, rc
 
     def peer_pooled_gather_fwd(self, tables, rf_w_off, feat_rows, feat_block, feat_owner, lay, ids, offsets, B, W,
-                               out=None, mirror=None, feat_mirror_off=None):
+                               out=None, mirror=None, feat_mirror_off=None, feat_sel=None):
         dim, col, pool = self._lay(lay)
         out = torch.full((B, lay.total_dim), float("nan")) if out is None else out
+        if feat_sel is not None:
+            rc = self.L.tzk_peer_pooled_gather_fwd_sel(
+                tables.ptrs, rf_w_off.data_ptr(), feat_rows.data_ptr(), feat_block.data_ptr(), feat_owner.data_ptr(),
+                dim.data_ptr(), col.data_ptr(), pool.data_ptr(), ids.data_ptr(), offsets.data_ptr(), lay.num_features, B, W,
+                (lay.max_dim + 3) // 4 * 4, out.data_ptr(), lay.total_dim, None if mirror is None else mirror.data_ptr(),
+                None if feat_mirror_off is None else feat_mirror_off.data_ptr(), feat_sel.data_ptr(), feat_sel.numel(),
+                None)
+            assert rc == 0, rc
+            return out
         rc = self.L.tzk_peer_pooled_gather_fwd(tables.ptrs, rf_w_off.data_ptr(), feat_rows.data_ptr(),
                                                feat_block.data_ptr(), feat_owner.data_ptr(), dim.data_ptr(),
                                                col.data_ptr(), pool.data_ptr(), ids.data_ptr(), offsets.data_ptr(),

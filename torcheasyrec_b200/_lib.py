@@ -104,6 +104,8 @@ SIGNATURES = {
     "tzk_jagged_softmax_wsum_bwd": (c_int32, [P, P, P, P, c_int32, c_int32, c_int32, c_int64, P, P, P]),
     "tzk_peer_pooled_gather_fwd": (
         c_int32, [P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P, P, P]),
+    "tzk_peer_pooled_gather_fwd_sel": (
+        c_int32, [P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int64, P, P, P, c_int32, P]),
     "tzk_peer_seq_gather_fwd": (
         c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int64, P, P, P, P]),
     "tzk_peer_mirror_refresh": (c_int32, [P, c_int32, P, P, P, P, c_int32, P, P]),

@@ -92,13 +92,19 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
                               const int32_t* __restrict__ feat_pool, const int64_t* __restrict__ ids,
                               const int64_t* __restrict__ offsets, int F, int B, int W, float* __restrict__ out,
                               int64_t ld_out, const float* __restrict__ mirror,
-                              const int64_t* __restrict__ feat_mirror_off) {
+                              const int64_t* __restrict__ feat_mirror_off, const int32_t* __restrict__ feat_sel,
+                              int n_sel) {
+  // feat_sel (nullable): this launch serves only the listed features (e.g. the mirrored ones, or the ones whose rows
+  // cross NVLink — two launches on two streams overlap the local and the remote half of the lookup)
   constexpr int NG = kThreads / G, TB = 32, U = 8;
   TZK_DYN_SMEM(unsigned char, smem_raw);
   FeatDesc* fd = reinterpret_cast<FeatDesc*>(smem_raw);
   int64_t* w_off = reinterpret_cast<int64_t*>(fd + F);                      // [W * F] arena offsets per (rank, feature)
   unsigned long long* base = reinterpret_cast<unsigned long long*>(w_off + (size_t)W * F);   // [W]
   int64_t* m_off = reinterpret_cast<int64_t*>(base + W);                    // [F] offset in the local mirror, or -1
+  int32_t* sel = reinterpret_cast<int32_t*>(m_off + F);                     // [F] features of this launch
+  const int nF = feat_sel ? n_sel : F;
+  for (int f = threadIdx.x; f < nF; f += kThreads) sel[f] = feat_sel ? feat_sel[f] : f;
   for (int f = threadIdx.x; f < F; f += kThreads) m_off[f] = (mirror && feat_mirror_off) ? feat_mirror_off[f] : -1;
   for (int f = threadIdx.x; f < F; f += kThreads) {
     fd[f].rows = feat_rows[f];
@@ -122,7 +128,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
 
   const int g = threadIdx.x / G, lane = threadIdx.x % G;
   const int n_tiles = (B + TB - 1) / TB;
-  const int items = F * TB;
+  const int items = nF * TB;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b0 = tile * TB;
     for (int i0 = g; i0 < items; i0 += NG * U) {
@@ -134,7 +140,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
         s[u] = 0;
         len[u] = -1;
         if (i < items && b < B) {
-          const int64_t bag = (int64_t)(i / TB) * B + b;
+          const int64_t bag = (int64_t)sel[i / TB] * B + b;
           s[u] = (int32_t)__ldg(offsets + bag);
           len[u] = (int32_t)__ldg(offsets + bag + 1) - s[u];
         }
@@ -147,7 +153,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
       for (int u = 0; u < U; ++u) {
         acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (len[u] > 0) {
-          const int f = (i0 + u * NG) / TB;
+          const int f = sel[(i0 + u * NG) / TB];
           const FeatDesc& d = fd[f];
           if (lane * 4 < d.dim) acc[u] = ld_peer_f4(row_ptr(f, d, id0[u]) + lane * 4);
         }
@@ -155,7 +161,7 @@ peer_pooled_gather_fwd_kernel(const __grid_constant__ Peers tables, const int64_
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (len[u] < 0) continue;
-        const int i = i0 + u * NG, f = i / TB;
+        const int i = i0 + u * NG, f = sel[i / TB];
         const FeatDesc d = fd[f];
         float* orow = out + (int64_t)(b0 + (i % TB)) * ld_out + d.col;
         for (int c = lane * 4; c < d.dim; c += G * 4) {
@@ -603,26 +609,57 @@ inline int64_t bkt_tiles(int64_t n_bags) { return (n_bags + kBktTile - 1) / kBkt
 
 // table_ptrs: HOST array [W] of device addresses (rank r's arena as mapped in THIS process); rf_w_off: device
 // [W * F] int64 arena element offset of feature f's table on rank r; the other feature arrays as in tzk.h.
-extern "C" int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
-                                          const int64_t* feat_block, const int32_t* feat_owner, const int32_t* feat_dim,
-                                          const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
-                                          const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim,
-                                          float* out, int64_t ld_out, const float* mirror,
-                                          const int64_t* feat_mirror_off, void* stream) {
+static int peer_pooled_gather_fwd_impl(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
+                                       const int64_t* feat_block, const int32_t* feat_owner, const int32_t* feat_dim,
+                                       const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
+                                       const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim,
+                                       float* out, int64_t ld_out, const float* mirror,
+                                       const int64_t* feat_mirror_off, const int32_t* feat_sel, int32_t n_sel,
+                                       void* stream) {
   Peers t;
   if (fill(&t, table_ptrs, W) || F <= 0 || B <= 0 || max_dim <= 0 || (max_dim % 4) || (ld_out % 4)) return 1;
+  if (feat_sel && (n_sel < 0 || n_sel > F)) return 1;
+  if (feat_sel && n_sel == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t smem = (size_t)F * sizeof(FeatDesc) + (size_t)W * F * 8 + (size_t)W * 8 + (size_t)F * 8;
+  const size_t smem = (size_t)F * sizeof(FeatDesc) + (size_t)W * F * 8 + (size_t)W * 8 + (size_t)F * 8 + (size_t)F * 4;
   const int grid = grid_for((B + 31) / 32);
 #define TZK_PEER_LAUNCH(G)                                                                                             \
   TZK_LAUNCH((peer_pooled_gather_fwd_kernel<G>), grid, kThreads, smem, st, t, rf_w_off, feat_rows, feat_block,         \
-             feat_owner, feat_dim, feat_col, feat_pool, ids, offsets, F, B, W, out, ld_out, mirror, feat_mirror_off)
+             feat_owner, feat_dim, feat_col, feat_pool, ids, offsets, F, B, W, out, ld_out, mirror, feat_mirror_off,   \
+             feat_sel, n_sel)
   if (max_dim <= 16) TZK_PEER_LAUNCH(4);
   else if (max_dim <= 32) TZK_PEER_LAUNCH(8);
   else if (max_dim <= 64) TZK_PEER_LAUNCH(16);
   else TZK_PEER_LAUNCH(32);
 #undef TZK_PEER_LAUNCH
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+extern "C" int tzk_peer_pooled_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,
+                                          const int64_t* feat_block, const int32_t* feat_owner, const int32_t* feat_dim,
+                                          const int32_t* feat_col, const int32_t* feat_pool, const int64_t* ids,
+                                          const int64_t* offsets, int32_t F, int32_t B, int32_t W, int32_t max_dim,
+                                          float* out, int64_t ld_out, const float* mirror,
+                                          const int64_t* feat_mirror_off, void* stream) {
+  return peer_pooled_gather_fwd_impl(table_ptrs, rf_w_off, feat_rows, feat_block, feat_owner, feat_dim, feat_col, feat_pool,
+                                     ids, offsets, F, B, W, max_dim, out, ld_out, mirror, feat_mirror_off, nullptr, 0,
+                                     stream);
+}
+
+// The same lookup restricted to the features listed in feat_sel [n_sel] (device int32, indices into the F descriptors):
+// only their output columns are written.  Two launches over complementary lists on two streams overlap the local half
+// of the lookup (mirrored tables) with the half whose rows cross NVLink.
+extern "C" int tzk_peer_pooled_gather_fwd_sel(const uint64_t* table_ptrs, const int64_t* rf_w_off,
+                                              const int64_t* feat_rows, const int64_t* feat_block,
+                                              const int32_t* feat_owner, const int32_t* feat_dim, const int32_t* feat_col,
+                                              const int32_t* feat_pool, const int64_t* ids, const int64_t* offsets,
+                                              int32_t F, int32_t B, int32_t W, int32_t max_dim, float* out, int64_t ld_out,
+                                              const float* mirror, const int64_t* feat_mirror_off,
+                                              const int32_t* feat_sel, int32_t n_sel, void* stream) {
+  if (!feat_sel) return 1;
+  return peer_pooled_gather_fwd_impl(table_ptrs, rf_w_off, feat_rows, feat_block, feat_owner, feat_dim, feat_col, feat_pool,
+                                     ids, offsets, F, B, W, max_dim, out, ld_out, mirror, feat_mirror_off, feat_sel, n_sel,
+                                     stream);
 }
 
 extern "C" int tzk_peer_seq_gather_fwd(const uint64_t* table_ptrs, const int64_t* rf_w_off, const int64_t* feat_rows,

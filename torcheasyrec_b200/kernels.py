@@ -484,7 +484,9 @@ class CudaKernels:
     def peer_pooled_gather_fwd(self, tables, rf_w_off: torch.Tensor, feat_rows: torch.Tensor, feat_block: torch.Tensor,
                                feat_owner: torch.Tensor, lay: FeatureLayout, ids: torch.Tensor, offsets: torch.Tensor,
                                B: int, W: int, out: Optional[torch.Tensor] = None, mirror: Optional[torch.Tensor] = None,
-                               feat_mirror_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+                               feat_mirror_off: Optional[torch.Tensor] = None,
+                               feat_sel: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`feat_sel` (device int32 indices): serve only these features (their output columns); `out` is then required."""
         _need(ids, torch.int64, "ids")
         _need(offsets, torch.int64, "offsets")
         F = lay.num_features
@@ -495,6 +497,15 @@ class CudaKernels:
         if out is None:
             out = torch.empty((B, lay.total_dim), dtype=torch.float32, device=ids.device)
         out, ld = _rows2d(out, "out")
+        if feat_sel is not None:
+            _need(feat_sel, torch.int32, "feat_sel")
+            check(self._lib.tzk_peer_pooled_gather_fwd_sel(
+                tables.ptrs, _ptr(rf_w_off), _ptr(feat_rows), _ptr(feat_block), _ptr(feat_owner), _ptr(lay.d_dim),
+                _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, W, (lay.max_dim + 3) // 4 * 4,
+                _ptr(out), ld, _ptr(mirror), _ptr(feat_mirror_off), _ptr(feat_sel), feat_sel.numel(), _stream()),
+                "tzk_peer_pooled_gather_fwd_sel")
+            self.launches += 1
+            return out
         check(self._lib.tzk_peer_pooled_gather_fwd(
             tables.ptrs, _ptr(rf_w_off), _ptr(feat_rows), _ptr(feat_block), _ptr(feat_owner), _ptr(lay.d_dim),
             _ptr(lay.d_col), _ptr(lay.d_pool), _ptr(ids), _ptr(offsets), F, B, W, (lay.max_dim + 3) // 4 * 4, _ptr(out),

@@ -308,6 +308,32 @@ class PeerState(PeerBase):
         g, k = self.g, Fn.backend()
         if ids.numel() > self.max_nnz:
             raise RuntimeError(f"peer exchange is sized for {self.max_nnz} ids per step, got {ids.numel()}")
+        sel = self._split_lists() if self.pooled else None
+        if sel is not None:
+            # two launches over complementary feature lists: the one whose rows cross NVLink starts first, on its own
+            # stream; the mirror refresh and the mirrored features' lookup run next to it
+            out = torch.empty((self.B, g.local.layout.total_dim), dtype=torch.float32, device=ids.device)
+            gs = self._gather_stream()
+            cur = torch.cuda.current_stream() if gs is not None else None
+
+            def remote():
+                k.peer_pooled_gather_fwd(self.tables, self.rf_w_off, self.feat_rows, g.feat_block, g.feat_owner,
+                                         g.local.layout, ids, offsets, self.B, self.W, out, self.mirror,
+                                         self.feat_mirror_off, feat_sel=sel[1])
+
+            if gs is not None:
+                gs.wait_stream(cur)
+                with torch.cuda.stream(gs):
+                    remote()
+            else:
+                remote()
+            k.peer_mirror_refresh(self.tables, self.W, *self._seg, self.mirror)
+            k.peer_pooled_gather_fwd(self.tables, self.rf_w_off, self.feat_rows, g.feat_block, g.feat_owner,
+                                     g.local.layout, ids, offsets, self.B, self.W, out, self.mirror, self.feat_mirror_off,
+                                     feat_sel=sel[0])
+            if gs is not None:
+                cur.wait_stream(gs)
+            return out
         if self.mirror is not None:
             k.peer_mirror_refresh(self.tables, self.W, *self._seg, self.mirror)
         if self.pooled:
@@ -316,6 +342,33 @@ class PeerState(PeerBase):
                                             self.feat_mirror_off)
         return k.peer_seq_gather_fwd(self.tables, self.rf_w_off, self.feat_rows, g.feat_block, g.feat_owner,
                                      g.local.layout, ids, offsets, self.B, self.W, self.mirror, self.feat_mirror_off)
+
+    def _split_lists(self):
+        """(mirrored features, features whose rows live in the owners' arenas) as device int32 lists, or None when the
+        lookup stays one launch (no mirror, one of the lists empty, or TZK_PEER_SPLIT_GATHER off — the split has not been
+        through a GPU validation pass yet: on with TZK_PEER_SPLIT_GATHER=1 / TZK_EXPERIMENTAL=1)."""
+        sl = getattr(self, "_split_sel", False)
+        if sl is False:
+            from .kernels import _unvalidated_switch
+
+            sl = None
+            if self.mirror is not None and _unvalidated_switch("TZK_PEER_SPLIT_GATHER"):
+                ft = self.g.local._feat_table
+                loc = [f for f, t in enumerate(ft) if t in self._m_off]
+                rem = [f for f, t in enumerate(ft) if t not in self._m_off]
+                if loc and rem:
+                    sl = (torch.tensor(loc, dtype=torch.int32, device=self.device),
+                          torch.tensor(rem, dtype=torch.int32, device=self.device))
+            self._split_sel = sl
+        return sl
+
+    def _gather_stream(self):
+        if self.device.type != "cuda":
+            return None
+        st = getattr(self, "_gstream", None)
+        if st is None:
+            st = self._gstream = torch.cuda.Stream(device=self.device)
+        return st
 
     def _workspace(self) -> torch.Tensor:
         k = Fn.backend()
