@@ -36,6 +36,28 @@ struct BwdFeat {
   int32_t stride;   // elements between consecutive rows of the table: dim, or 2 * dim when a.interleaved
 };
 
+// q = v / d for 0 <= v < 2^31, d >= 1: m = ceil(2^(31 + l) / d), l = ceil(log2 d) fits 32 bits and
+// floor(v * m / 2^(31 + l)) is exact for 31-bit v (Granlund & Montgomery); d == 1 -> mul = 0.
+struct FastDiv {
+  uint32_t mul;
+  int32_t shift;   // l - 1 (applied after the high word of the product)
+};
+inline FastDiv make_fast_div(int64_t d) {
+  FastDiv f;
+  f.mul = 0;
+  f.shift = 0;
+  if (d <= 1) return f;
+  int l = 0;
+  while (((int64_t)1 << l) < d) ++l;
+  const unsigned __int128 num = (unsigned __int128)1 << (31 + l);
+  f.mul = (uint32_t)((num + (unsigned __int128)d - 1) / (unsigned __int128)d);
+  f.shift = l - 1;
+  return f;
+}
+__device__ __forceinline__ int fast_div(int v, const FastDiv& f) {
+  return f.mul ? (int)(__umulhi((unsigned)v, f.mul) >> f.shift) : v;
+}
+
 struct BwdArgs {
   const float* grad_out;
   int64_t ld_grad;
@@ -61,6 +83,11 @@ struct BwdArgs {
   int32_t w_f16;      // 1: `weights` is an arena of halfs (FP16 tables): rows are widened, updated in fp32, rounded back
   int32_t interleaved;  // 1: [weight row | state row] back to back (row stride 2 * dim): the first state of table row r is
                         // at weights + w_off + r * 2 dim + dim — one 128-B line per D = 16 row, written whole
+  // v / B and v / idx_span for 0 <= v < 2^31 as a multiply-high + shift (the division by a run-time divisor was 20 % of
+  // the kernel's instructions): mul == 0 means "divisor is 1"
+  FastDiv div_b, div_span;
+  int32_t ld32;         // = ld_grad (< 2^31, checked on the host): row offsets are ONE 32 x 32 -> 64-bit multiply
+  int32_t pad3;
 };
 // peer mode: the sources' published gradient buffers.  A kernel parameter of its own (__grid_constant__): indexing it
 // with a run-time rank must not drag the whole argument block into local memory.
@@ -235,15 +262,15 @@ __device__ __forceinline__ Entry entry_of(const BwdArgs& a, const PeerGrads& gp,
   Entry en;
   const float* base = a.grad_out;
   if (a.peer_w) {
-    const int r = v / a.idx_span;
+    const int r = fast_div(v, a.div_span);
     v -= r * a.idx_span;
     base = reinterpret_cast<const float*>(gp.p[r]);
   }
   if (a.pooled) {
-    const int f = v / a.B;
+    const int f = fast_div(v, a.div_b);
     const int b = v - f * a.B;
     en.f = f;
-    en.g = base + (int64_t)b * a.ld_grad + fd[f].col;
+    en.g = base + (int64_t)b * a.ld32 + fd[f].col;
     en.scale = a.grad_scale;
     if (fd[f].pool == TZK_POOL_MEAN && !a.peer_w) {
       const int64_t L = __ldg(a.offsets + v + 1) - __ldg(a.offsets + v);
@@ -251,7 +278,7 @@ __device__ __forceinline__ Entry entry_of(const BwdArgs& a, const PeerGrads& gp,
     }
   } else {
     en.f = f_hint;
-    en.g = base + (int64_t)v * a.ld_grad;
+    en.g = base + (int64_t)v * a.ld32;
     en.scale = a.grad_scale;
   }
   return en;
@@ -259,8 +286,8 @@ __device__ __forceinline__ Entry entry_of(const BwdArgs& a, const PeerGrads& gp,
 
 // feature of a sorted entry: from the bag index for pooled layouts, from the key ranges otherwise
 __device__ __forceinline__ int bag_feat(const BwdArgs& a, int32_t v) {
-  if (a.peer_w) v %= a.idx_span;
-  return v / a.B;
+  if (a.peer_w) v -= fast_div(v, a.div_span) * a.idx_span;
+  return fast_div(v, a.div_b);
 }
 
 template <typename KeyT>
@@ -291,7 +318,7 @@ __device__ __forceinline__ void apply_update(const BwdArgs& a, float* w, float* 
     } else if (a.optimizer == TZK_OPT_ADAGRAD) {
       const float sk = s[k] + gk * gk;
       s[k] = sk;
-      w[k] = w[k] - a.lr * gk / (sqrtf(sk) + a.eps);
+      w[k] = w[k] - __fdividef(a.lr * gk, sqrtf(sk) + a.eps);   // (2-ulp quotient: the IEEE division was 10 % of the kernel)
     } else if (a.optimizer == TZK_OPT_ROWWISE_ADAGRAD) {
       w[k] = w[k] - a.lr * gk / rw_denom;
     } else if (a.optimizer == TZK_OPT_ADAM) {
@@ -478,8 +505,12 @@ struct ChunkItem {
 struct WorkLists {
   ChunkItem* items;
   int32_t* run_done;  // [partial slots] per multi-chunk run (indexed by pbase): chunks finished so far
-  int32_t* counters;  // [0] items, [2] partial slots
+  int32_t* counters;  // [0] items, [2] partial slots, [3] short-run heads
   float* partials;    // [slots][ROWF]
+  // compact list of the SHORT runs (<= kShortRun positions): first sorted position and length of each, written by the id
+  // half (find_long_runs_kernel) into the sort's dead input buffers; NULL: the gradient half walks every sorted position
+  int32_t* head_pos;
+  int32_t* head_len;
 };
 
 // ---- 2'. work list of the long runs (id half: runs right after the sort, on the side stream) ---------------------------
@@ -490,10 +521,33 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 find_long_runs_kernel(const KeyT* __restrict__ keys, int64_t n, KeyT sentinel, WorkLists wl) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-    const KeyT k0 = keys[p];
-    if (k0 == sentinel || (p > 0 && keys[p - 1] == k0)) continue;
-    if (p + kShortRun >= n || keys[p + kShortRun] != k0) continue;
+  const unsigned lane = threadIdx.x & 31u;
+  // (every lane of a warp makes the same number of trips: the short-run list is appended with one atomic per warp)
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+    const int64_t p = base + threadIdx.x;
+    bool is_head = false, is_long = false;
+    KeyT k0 = 0;
+    if (p < n) {
+      k0 = keys[p];
+      is_head = k0 != sentinel && !(p > 0 && keys[p - 1] == k0);
+      is_long = is_head && p + kShortRun < n && keys[p + kShortRun] == k0;
+    }
+    if (wl.head_pos) {
+      const bool is_short = is_head && !is_long;
+      int len = 1;
+      if (is_short)
+        while (p + len < n && keys[p + len] == k0) ++len;      // <= kShortRun
+      const unsigned m = __ballot_sync(0xffffffffu, is_short);
+      int wbase = 0;
+      if (lane == 0 && m) wbase = atomicAdd(wl.counters + 3, __popc(m));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (is_short) {
+        const int idx = wbase + __popc(m & ((1u << lane) - 1u));
+        wl.head_pos[idx] = (int32_t)p;
+        wl.head_len[idx] = len;
+      }
+    }
+    if (!is_long) continue;
     int64_t lo = p + kShortRun, step = kShortRun;  // keys[lo] == k0
     int64_t hi = lo + step;
     while (hi < n && keys[hi] == k0) { lo = hi; step <<= 1; hi = lo + step; }
@@ -504,7 +558,7 @@ find_long_runs_kernel(const KeyT* __restrict__ keys, int64_t n, KeyT sentinel, W
     }
     const int64_t end = hi;
     const int n_chunks = (int)((end - p + kChunk - 1) / kChunk);
-    const int base = atomicAdd(wl.counters + 0, n_chunks);
+    const int base_i = atomicAdd(wl.counters + 0, n_chunks);
     int pbase = -1;
     if (n_chunks > 1) {
       pbase = atomicAdd(wl.counters + 2, n_chunks);
@@ -518,7 +572,7 @@ find_long_runs_kernel(const KeyT* __restrict__ keys, int64_t n, KeyT sentinel, W
       it.pbase = pbase;
       it.cc = cc;
       it.pad = 0;
-      wl.items[base + cc] = it;
+      wl.items[base_i + cc] = it;
     }
   }
 }
@@ -527,17 +581,97 @@ find_long_runs_kernel(const KeyT* __restrict__ keys, int64_t n, KeyT sentinel, W
 // Each lane group owns kPos consecutive sorted positions per iteration.  Runs of length 1 (the common case on
 // big tables) take a batched path: the gradient / weight / state rows of all of them are requested before any
 // is consumed, so a group keeps 3*kPos independent 64-B requests in flight instead of one dependent chain.
+// One short run (<= kShortRun sorted positions starting at p, key k0, first value v0): sum its gradient rows in sorted
+// order, ONE optimizer update.  All G lanes of the group call it together.
+template <typename KeyT, int G, int VEC, int CH>
+__device__ __forceinline__ void short_run(const BwdArgs& a, const PeerGrads& gp, const BwdFeat* fd,
+                                          const int32_t* __restrict__ vals, int64_t p, KeyT k0, int32_t v0, int len,
+                                          int lane) {
+        int f00;
+    if (a.pooled) f00 = bag_feat(a, v0); else f00 = feat_of_key<KeyT>(fd, a.F, k0);
+    const BwdFeat d = fd[f00];
+    const int64_t row = (int64_t)k0 - d.key_base;
+    // the row's weight / state chunks depend on the key only: requested here, next to the gradient rows, so that a
+    // single-position run costs ONE exposed DRAM latency instead of two dependent ones
+    constexpr bool kPre = (VEC == 4 && CH == 1);
+    float4 pre_w = make_float4(0.f, 0.f, 0.f, 0.f), pre_s = pre_w;
+    const bool pre = kPre && !a.w_f16 && a.optimizer != TZK_OPT_ACCUM_OUT;      // (group-uniform)
+    if (pre && lane * 4 < d.dim) {
+      const float* wp = a.weights + d.w_off + row * d.stride + lane * 4;
+      pre_w = ld_rw_f4(wp);
+      if (has_elem_state(a)) pre_s = ld_rw_f4(a.interleaved ? wp + d.dim : a.state + (d.w_off + row * d.stride + lane * 4));
+    }
+    float acc[CH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+    // kGU gradient rows of the run in flight; added in sorted order
+    constexpr int kGU = 4;
+    for (int j0 = 0; j0 < len; j0 += kGU) {
+      Entry en[kGU];
+      bool ok[kGU];
+#pragma unroll
+      for (int q = 0; q < kGU; ++q) {
+        const int j = j0 + q;
+        ok[q] = j < len;
+        en[q] = entry_of(a, gp, fd, (j == 0 || !ok[q]) ? v0 : vals[p + j], f00);
+      }
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = (ch * G + lane) * VEC;
+        if (c < d.dim) {
+          float gg[kGU][VEC];
+#pragma unroll
+          for (int q = 0; q < kGU; ++q) {
+            if (ok[q]) {
+              load_grad<VEC>(en[q].g + c, gg[q], a.peer_w);
+            } else {
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) gg[q][k] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < kGU; ++q)
+            if (ok[q]) {
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) acc[ch][k] += gg[q][k] * en[q].scale;
+            }
+        }
+      }
+    }
+    // (one call site: the row-wise variants shuffle inside, every lane of the group must arrive at the same instruction)
+    finish_run<G, VEC, CH>(a, d, row, (int64_t)k0, acc, lane, pre ? &pre_w : nullptr,
+                           (pre && has_elem_state(a)) ? &pre_s : nullptr);
+}
+
 template <typename KeyT, int G, int VEC, int CH>
 __device__ __forceinline__ void run_update_body(const BwdArgs& a, const PeerGrads& gp, const BwdFeat* fd,
                                                 const KeyT* __restrict__ keys,
-                                                const int32_t* __restrict__ vals, int cta, int n_ctas) {
+                                                const int32_t* __restrict__ vals, const WorkLists& wl, int cta,
+                                                int n_ctas) {
   constexpr int NG = kThreads / G;
-  // One sorted position per lane group and iteration (2 and 4 positions with a batched single-run path were measured
-  // slower in round 1: 349 / 375 / 461 us for 1 / 2 / 4 on DLRM-Criteo).  The keys / value of the NEXT position are
-  // requested before the current one is worked on.
   const int lane = threadIdx.x % G;
   const int64_t stride = (int64_t)n_ctas * NG;
   // all G lanes of a group follow the same control flow (positions, keys, run lengths are group-uniform)
+  if (wl.head_pos) {
+    // the id half left a compact list of the short runs: no neighbour compares, no length scan, no iterations spent on
+    // the ~60 % of the sorted positions that do not start a run
+    const int64_t n_heads = wl.counters[3];
+    int64_t h = (int64_t)cta * NG + threadIdx.x / G;
+    int32_t hp = 0, hl = 0;
+    if (h < n_heads) { hp = wl.head_pos[h]; hl = wl.head_len[h]; }
+    for (; h < n_heads; h += stride) {
+      const int64_t p = hp;
+      const int len = hl;
+      if (h + stride < n_heads) { hp = wl.head_pos[h + stride]; hl = wl.head_len[h + stride]; }   // next head, early
+      short_run<KeyT, G, VEC, CH>(a, gp, fd, vals, p, keys[p], vals[p], len, lane);
+    }
+    return;
+  }
+  // One sorted position per lane group and iteration (2 and 4 positions with a batched single-run path were measured
+  // slower in round 1: 349 / 375 / 461 us for 1 / 2 / 4 on DLRM-Criteo).  The keys / value of the NEXT position are
+  // requested before the current one is worked on.
   int64_t p0 = (int64_t)cta * NG + threadIdx.x / G;
   KeyT kl = 0, kc = 0, kr = 0;     // left neighbour, this position, right neighbour
   int32_t vc = 0;
@@ -557,77 +691,16 @@ __device__ __forceinline__ void run_update_body(const BwdArgs& a, const PeerGrad
     const KeyT key_l = kl, key_c = kc, key_r = kr;
     const int32_t v_c = vc;
     kl = nl; kc = nc; kr = nr; vc = nv;
-    const bool head = key_c != key_l && key_c != (KeyT)a.sentinel;
-    (void)key_r;
-    // ---- every run head: sum the run (<= kShortRun) in sorted order and update, or hand it to the long-run kernels
-    {
-      if (!head) continue;
-      const int64_t p = p0;
-      const KeyT k0 = key_c;
-      int len = 1;
-      if (key_r == k0) {
-        len = 2;
-        while (len <= kShortRun && p + len < a.n && keys[p + len] == k0) ++len;
-      }
-      if (len > kShortRun) continue;   // long runs are on the work list (find_long_runs_kernel, id half) for the chunk CTAs
-      const int32_t v0 = v_c;
-      int f00;
-      if (a.pooled) f00 = bag_feat(a, v0); else f00 = feat_of_key<KeyT>(fd, a.F, k0);
-      const BwdFeat d = fd[f00];
-      const int64_t row = (int64_t)k0 - d.key_base;
-      // the row's weight / state chunks depend on the key only: requested here, next to the gradient rows, so that a
-      // single-position run costs ONE exposed DRAM latency instead of two dependent ones
-      constexpr bool kPre = (VEC == 4 && CH == 1);
-      float4 pre_w = make_float4(0.f, 0.f, 0.f, 0.f), pre_s = pre_w;
-      const bool pre = kPre && !a.w_f16 && a.optimizer != TZK_OPT_ACCUM_OUT;      // (group-uniform)
-      if (pre && lane * 4 < d.dim) {
-        const float* wp = a.weights + d.w_off + row * d.stride + lane * 4;
-        pre_w = ld_rw_f4(wp);
-        if (has_elem_state(a)) pre_s = ld_rw_f4(a.interleaved ? wp + d.dim : a.state + (d.w_off + row * d.stride + lane * 4));
-      }
-      float acc[CH][VEC];
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-      // kGU gradient rows of the run in flight; added in sorted order
-      constexpr int kGU = 4;
-      for (int j0 = 0; j0 < len; j0 += kGU) {
-        Entry en[kGU];
-        bool ok[kGU];
-#pragma unroll
-        for (int q = 0; q < kGU; ++q) {
-          const int j = j0 + q;
-          ok[q] = j < len;
-          en[q] = entry_of(a, gp, fd, (j == 0 || !ok[q]) ? v0 : vals[p + j], f00);
-        }
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          const int c = (ch * G + lane) * VEC;
-          if (c < d.dim) {
-            float gg[kGU][VEC];
-#pragma unroll
-            for (int q = 0; q < kGU; ++q) {
-              if (ok[q]) {
-                load_grad<VEC>(en[q].g + c, gg[q], a.peer_w);
-              } else {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) gg[q][k] = 0.f;
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < kGU; ++q)
-              if (ok[q]) {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[ch][k] += gg[q][k] * en[q].scale;
-              }
-          }
-        }
-      }
-      // (one call site: the row-wise variants shuffle inside, every lane of the group must arrive at the same instruction)
-      finish_run<G, VEC, CH>(a, d, row, (int64_t)k0, acc, lane, pre ? &pre_w : nullptr,
-                             (pre && has_elem_state(a)) ? &pre_s : nullptr);
+    // every run head: sum the run (<= kShortRun) in sorted order and update; long runs are on the work list
+    // (find_long_runs_kernel, id half) for the chunk CTAs
+    if (key_c == key_l || key_c == (KeyT)a.sentinel) continue;
+    int len = 1;
+    if (key_r == key_c) {
+      len = 2;
+      while (len <= kShortRun && p0 + len < a.n && keys[p0 + len] == key_c) ++len;
     }
+    if (len > kShortRun) continue;
+    short_run<KeyT, G, VEC, CH>(a, gp, fd, vals, p0, key_c, v_c, len, lane);
   }
 }
 
@@ -749,7 +822,7 @@ fused_apply_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const int6
   // the long-run CTAs come FIRST in the grid: they are few, each has a lot to do, and the hardware starts CTAs in
   // index order — their work overlaps the whole short-run sweep instead of trailing it
   if ((int)blockIdx.x < n_long) long_chunk_body<KeyT, G, VEC, CH>(a, gp, fd, keys, vals, wl, blockIdx.x, n_long);
-  else run_update_body<KeyT, G, VEC, CH>(a, gp, fd, keys, vals, blockIdx.x - n_long, gridDim.x - n_long);
+  else run_update_body<KeyT, G, VEC, CH>(a, gp, fd, keys, vals, wl, blockIdx.x - n_long, gridDim.x - n_long);
 }
 
 // ---- 3'. tile path: rows of <= 128 floats, 16-B aligned (vec4, one chunk per lane) -------------------------
@@ -1010,7 +1083,7 @@ carry_combine_kernel(BwdArgs a, const int64_t* __restrict__ feat_w_off, const in
   }
 }
 
-__global__ void zero_counters(int32_t* c) { c[0] = 0; c[1] = 0; c[2] = 0; }
+__global__ void zero_counters(int32_t* c) { c[0] = 0; c[1] = 0; c[2] = 0; c[3] = 0; }
 
 inline int bits_for(int64_t total_keys) {
   int b = 1;
@@ -1207,11 +1280,15 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   a.state2 = opt.state2; a.step = opt.step; a.beta1 = opt.beta1; a.beta2 = opt.beta2;
   a.weight_decay = opt.weight_decay; a.max_gradient = opt.max_gradient; a.bc1 = a.bc2 = 1.f;
   a.peer_w = 0; a.idx_span = 1; a.w_f16 = opt.weights_f16 ? 1 : 0; a.interleaved = opt.interleaved ? 1 : 0;
+  a.div_b = make_fast_div(B); a.div_span = make_fast_div(1);
+  TZK_REQUIRE(ld_grad >= 0 && ld_grad < ((int64_t)1 << 31), "fused_bwd: ld_grad out of range");
+  a.ld32 = (int32_t)ld_grad; a.pad3 = 0;
   PeerGrads gp;
   for (int r = 0; r < 16; ++r) gp.p[r] = 0ull;
   if (pw) {
     TZK_REQUIRE(grad_ptrs, "fused_bwd: peer mode needs the published gradient pointers");
     a.peer_w = pw->W; a.idx_span = pw->idx_span;
+    a.div_span = make_fast_div(pw->idx_span);
     for (int r = 0; r < pw->W; ++r) gp.p[r] = grad_ptrs[r];
     a.grad_out = reinterpret_cast<const float*>(grad_ptrs[pw->me]);
   }
@@ -1453,6 +1530,7 @@ extern "C" int tzk_peer_small_update(const tzk_opt_args* opt, const uint64_t* ps
   a.n = total_rows; a.sentinel = 0; a.state2 = opt->state2; a.step = opt->step; a.beta1 = opt->beta1; a.beta2 = opt->beta2;
   a.weight_decay = opt->weight_decay; a.max_gradient = opt->max_gradient; a.bc1 = a.bc2 = 1.f;
   a.peer_w = 0; a.idx_span = 1; a.w_f16 = 0; a.interleaved = opt->interleaved ? 1 : 0;
+  a.div_b = make_fast_div(1); a.div_span = make_fast_div(1); a.ld32 = 0; a.pad3 = 0;
   SmallPeers sp;
   for (int r = 0; r < 16; ++r) { sp.psum[r] = r < W ? psum_ptrs[r] : 0ull; sp.flags[r] = r < W ? flag_ptrs[r] : 0ull; }
   int G = 1;

@@ -510,14 +510,14 @@ dot_interact_bwd_kernel(const float* __restrict__ dense, int64_t ld_dense, const
 
 // The DLRM-Criteo shape (27 x 16, aligned output row) on the tensor cores (tzk_interact_tc.cuh); read per call (tests flip
 // it).  Forward: default on (validated on B200: 82.7 -> 58.7 us at B = 65536), TZK_INTERACT_TC=0 / TZK_INTERACT_TC_FWD=0
-// selects the FFMA kernel.  Backward: measured on par with the FFMA kernel (126 vs 121 us), so it stays a switch
-// (TZK_INTERACT_TC_BWD=1).
+// selects the FFMA kernel.  Backward: default on since its pass-through loads are requested up front (step 1.031 -> 1.010 ms);
+// TZK_INTERACT_TC_BWD=0 selects the FFMA kernel.
 inline bool env_is(const char* name, char v) {
   const char* e = getenv(name);
   return e && e[0] == v;
 }
 inline bool use_interact_tc_fwd() { return !env_is("TZK_INTERACT_TC", '0') && !env_is("TZK_INTERACT_TC_FWD", '0'); }
-inline bool use_interact_tc_bwd() { return !env_is("TZK_INTERACT_TC", '0') && env_is("TZK_INTERACT_TC_BWD", '1'); }
+inline bool use_interact_tc_bwd() { return !env_is("TZK_INTERACT_TC", '0') && !env_is("TZK_INTERACT_TC_BWD", '0'); }
 
 inline int grid_for(int64_t n, int per_block, int max_blocks) {
   int64_t g = ceil_div64(n, per_block);
