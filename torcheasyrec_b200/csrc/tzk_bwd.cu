@@ -1212,6 +1212,15 @@ static int fused_bwd_impl(int phases, const tzk_opt_args& opt, int32_t pooled, c
   wl.run_done = reinterpret_cast<int32_t*>(ws + L.runs);
   wl.counters = reinterpret_cast<int32_t*>(ws + L.counters);
   wl.partials = reinterpret_cast<float*>(ws + L.partials);
+  // short-run head list in the sort's dead INPUT buffers (n int32 positions in vals_in, n int32 lengths in keys_in);
+  // TZK_BWD_HEADS: not through a GPU validation pass yet — on with TZK_BWD_HEADS=1 / TZK_EXPERIMENTAL=1.  Both halves
+  // of a step read the switch, so it must not change between a sort and its apply.
+  wl.head_pos = nullptr;
+  wl.head_len = nullptr;
+  if (unvalidated_switch("TZK_BWD_HEADS")) {
+    wl.head_pos = vals_in;
+    wl.head_len = reinterpret_cast<int32_t*>(keys_in);
+  }
   const bool k64 = total_keys >= ((int64_t)1 << 32);
   const int bits = bits_for(total_keys + 1);   // one spare value above the largest key = padding sentinel
   const uint64_t sentinel = ((uint64_t)1 << bits) - 1;
