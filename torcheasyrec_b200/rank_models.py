@@ -310,8 +310,28 @@ class DLRM(RankModel):
         # the lower sequence numbers, so in the backward pass the lookups' node — which launches the fused sparse
         # update on the collection's side stream — is scheduled first and the bottom-MLP backward overlaps it.
         dense_in = self._dense_group_input(batch) if self.dense_mlp else None
-        dense_feat = self.dense_mlp(dense_in) if dense_in is not None else None
+        # TZK_DLRM_BOTTOM_STREAM (not through a GPU validation pass yet: on with =1 / TZK_EXPERIMENTAL=1): the bottom MLP
+        # runs on a stream of its own next to the KJT scan and the lookups — it needs neither — and autograd runs its
+        # backward on that stream too
+        side = None
+        if dense_in is not None and dense_in.is_cuda:
+            from .kernels import _unvalidated_switch
+
+            if _unvalidated_switch("TZK_DLRM_BOTTOM_STREAM"):
+                side = getattr(self, "_bottom_stream", None)
+                if side is None:
+                    side = self._bottom_stream = torch.cuda.Stream(device=dense_in.device)
+        if side is not None:
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                dense_feat = self.dense_mlp(dense_in)
+        else:
+            dense_feat = self.dense_mlp(dense_in) if dense_in is not None else None
         grouped = self.build_input(batch)
+        if side is not None:
+            cur.wait_stream(side)
+            dense_feat.record_stream(cur)
         sparse = grouped[self._sparse_group_name]
         if self.dense_mlp and dense_feat is None:
             dense_feat = self.dense_mlp(grouped[self._dense_group_name])
