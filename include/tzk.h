@@ -300,6 +300,16 @@ int tzk_small_linear_bwd(const float* x, int64_t ld_x, const float* w, const flo
                          int64_t ld_dx, float* dw, float* db, void* workspace, size_t workspace_bytes,
                          tzk_stream_t stream);
 size_t tzk_bce_logits_workspace_bytes(int64_t M);
+
+/* ---- the tower tail in one pass, forward AND backward: last Perceptron of the final MLP (K -> N with ReLU,
+ * tzrec/modules/mlp.py:20-84), output Linear(N, 1) and mean BCE-with-logits on the label (tzrec/models/rank_model.py:
+ * 133-179, 181-262).  h = relu(y1 @ w1^T + b1); logits = h @ w2^T + b2; loss as tzk_bce_logits; and d loss / d ... :
+ * dy1 [M, K] and out = [dW1 (N x K, row-major) | db1 (N) | dw2 (N) | db2 (1) | loss (1)].  K, N <= 64; b1, b2 nullable.
+ * Deterministic (fixed-order folds).  Replaces 18 launches of the unfused chain on DLRM-Criteo (64 -> 32 -> 1). */
+size_t tzk_tower_tail_bce_workspace_bytes(int64_t M, int32_t K, int32_t N);
+int tzk_tower_tail_bce(const float* y1, int64_t ld_y, const float* w1, const float* b1, const float* w2, const float* b2,
+                       const float* labels, int64_t M, int32_t K, int32_t N, float* logits, float* dy1, int64_t ld_dy,
+                       float* out, void* workspace, size_t workspace_bytes, tzk_stream_t stream);
 int tzk_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t M, float* loss, float* dlogits,
                            void* workspace, size_t workspace_bytes, tzk_stream_t stream);
 

@@ -877,3 +877,36 @@ def test_interaction_tensor_core_kernels_match_reference_and_fp64(kernels, monke
     # run-to-run identical bits
     again = kernels.dot_interact_fwd(cu(dense), cu(sparse), 26, 16, True, True, pad_to=4, p_pad=1)
     assert torch.equal(again, got)
+
+
+# ---- fused tower tail: last Perceptron + Linear(N, 1) + mean BCE, forward and backward in one kernel ---------------------
+@unvalidated
+@pytest.mark.parametrize("M,K,N", [(1, 64, 32), (127, 64, 32), (1000, 13, 7), (4099, 64, 64), (65536 + 5, 64, 32), (300, 32, 16)])
+def test_tower_tail_bce_matches_torch_autograd(kernels, M, K, N):
+    """tzk_tower_tail_bce against torch autograd in float64 (tzrec/modules/mlp.py Perceptron -> Linear ->
+    BCEWithLogitsLoss(mean)): loss, logits and every gradient; y1 as a column slice of a wider buffer."""
+    from torcheasyrec_b200.dense_gemm import tower_tail_bce
+
+    g = torch.Generator(device="cpu").manual_seed(M + K + N)
+    wide = torch.relu(torch.randn(M, K + 4, generator=g)).to(DEV)
+    y1 = wide[:, :K].detach().requires_grad_()
+    w1 = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).requires_grad_()
+    b1 = (0.1 * torch.randn(N, generator=g)).to(DEV).requires_grad_()
+    w2 = (torch.randn(1, N, generator=g) / N ** 0.5).to(DEV).requires_grad_()
+    b2 = torch.tensor([0.05]).to(DEV).requires_grad_()
+    lab = (torch.rand(M, generator=g) < 0.3).float().to(DEV)
+    loss, logits = tower_tail_bce(y1, w1, b1, w2, b2, lab)
+    (loss * 1.0).backward()
+    ref_in = [t.detach().double().requires_grad_() for t in (y1, w1, b1, w2, b2)]
+    h = torch.relu(ref_in[0] @ ref_in[1].t() + ref_in[2])
+    z = (h @ ref_in[3].t() + ref_in[4]).squeeze(1)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(z, lab.double())
+    ref.backward()
+    torch.testing.assert_close(loss.double(), ref, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(logits.double(), z.detach(), rtol=1e-5, atol=1e-5)
+    for got, want, name in zip((y1, w1, b1, w2, b2), ref_in, ("dy1", "dW1", "db1", "dw2", "db2")):
+        torch.testing.assert_close(got.grad.double(), want.grad, rtol=2e-4, atol=2e-7, msg=lambda m, n=name: f"{n}: {m}")
+    # run-to-run identical bits
+    y1b = wide[:, :K].detach().requires_grad_()
+    loss2, _ = tower_tail_bce(y1b, w1.detach().requires_grad_(), b1, w2, b2, lab)
+    assert torch.equal(loss2, loss)

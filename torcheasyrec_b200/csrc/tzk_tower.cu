@@ -17,6 +17,7 @@
 #define TZK_UNPAREN(...) __VA_ARGS__
 #define TZK_LAUNCH(kernel, grid, block, smem, stream, ...) TZK_UNPAREN kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #include "tzk_tower_bwd2.cuh"
+#include "tzk_tower_tail.cuh"
 
 using namespace tzk;
 
@@ -468,5 +469,26 @@ extern "C" int tzk_bce_logits_fwd_bwd(const float* logits, const float* labels, 
   TZK_CHECK_LAUNCH("bce_fwd_bwd_kernel");
   bce_final_kernel<<<1, 256, 0, st>>>(partial, (int)nb, inv_m, loss);
   TZK_CHECK_LAUNCH("bce_final_kernel");
+  return 0;
+}
+
+// ---- the tower tail in one pass: last Perceptron (K -> N, ReLU) + Linear(N, 1) + mean BCE, forward and backward ---------
+extern "C" size_t tzk_tower_tail_bce_workspace_bytes(int64_t M, int32_t K, int32_t N) {
+  return tzk_tail::supported(K, N) ? tzk_tail::workspace_bytes(M < 1 ? 1 : M, K, N) : 0;
+}
+
+extern "C" int tzk_tower_tail_bce(const float* y1, int64_t ld_y, const float* w1, const float* b1, const float* w2,
+                                  const float* b2, const float* labels, int64_t M, int32_t K, int32_t N, float* logits,
+                                  float* dy1, int64_t ld_dy, float* out, void* workspace, size_t workspace_bytes,
+                                  tzk_stream_t stream) {
+  TZK_REQUIRE(M >= 1, "tower_tail_bce: empty batch");
+  TZK_REQUIRE(tzk_tail::supported(K, N), "tower_tail_bce: K=%d, N=%d must be in [1, 64]", K, N);
+  TZK_REQUIRE(y1 && w1 && w2 && labels && logits && dy1 && out, "tower_tail_bce: NULL argument");
+  TZK_REQUIRE(ld_y >= K && ld_dy >= K, "tower_tail_bce: leading dimension smaller than the row");
+  TZK_REQUIRE(workspace && workspace_bytes >= tzk_tower_tail_bce_workspace_bytes(M, K, N),
+              "tower_tail_bce: workspace too small");
+  const int rc = tzk_tail::run(y1, ld_y, w1, b1, w2, b2, labels, M, K, N, logits, dy1, ld_dy, out, workspace,
+                               workspace_bytes, as_stream(stream));
+  TZK_REQUIRE(rc == 0, "tower_tail_bce: tzk_tail::run failed with code %d", rc);
   return 0;
 }

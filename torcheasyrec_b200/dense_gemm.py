@@ -300,6 +300,39 @@ class _BceFn(torch.autograd.Function):
         return (dz * g).view(ctx.shape), None
 
 
+class _TowerTailFn(torch.autograd.Function):
+    """(loss, logits) = BCE(Linear(relu(Linear(y1)))) with every gradient computed in the forward kernel."""
+
+    @staticmethod
+    def forward(ctx, y1, w1, b1, w2, b2, labels):
+        from .kernels import default_kernels
+
+        loss, logits, dy1, dw1, db1, dw2, db2 = default_kernels().tower_tail_bce(y1, w1, b1, w2, b2, labels)
+        ctx.save_for_backward(dy1, dw1, db1, dw2, db2)
+        ctx.has = (b1 is not None, b2 is not None)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_logits):
+        dy1, dw1, db1, dw2, db2 = ctx.saved_tensors
+        # (g_loss is 1 in a plain `loss.backward()`; any other scale multiplies through)
+        return (dy1 * g_loss, dw1 * g_loss, (db1 * g_loss) if ctx.has[0] else None, dw2 * g_loss,
+                (db2 * g_loss) if ctx.has[1] else None, None)
+
+
+def tower_tail_usable(y1: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, labels: torch.Tensor) -> bool:
+    """The fused tail covers fp32 CUDA towers ending K -> N (ReLU) -> 1 with K, N <= 64 and a float label per row."""
+    return (y1.is_cuda and y1.dim() == 2 and y1.dtype == torch.float32 and w1.dtype == torch.float32
+            and w1.shape[1] == y1.shape[1] <= 64 and w1.shape[0] <= 64 and tuple(w2.shape) == (1, w1.shape[0])
+            and labels.dtype == torch.float32 and labels.numel() == y1.shape[0] >= 1 and y1.stride(1) == 1)
+
+
+def tower_tail_bce(y1, w1, b1, w2, b2, labels):
+    """-> (mean BCE loss, logits [M]) of Linear(N, 1)(relu(Linear(K, N)(y1))) against `labels`."""
+    return _TowerTailFn.apply(y1, w1, b1, w2, b2, labels)
+
+
 def bce_with_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """F.binary_cross_entropy_with_logits(logits, labels) (mean); fused fwd+bwd kernel on CUDA fp32 inputs."""
     if (logits.is_cuda and logits.dtype == torch.float32 and labels.dtype == torch.float32 and logits.numel() >= 1

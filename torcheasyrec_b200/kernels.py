@@ -799,6 +799,32 @@ class CudaKernels:
         self.launches += 2
         return loss, dz
 
+    def tower_tail_bce(self, y1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+                       b2: Optional[torch.Tensor], labels: torch.Tensor):
+        """Last Perceptron (K -> N, ReLU) + Linear(N, 1) + mean BCE, forward and backward in one pass
+        (csrc/tzk_tower_tail.cuh).  -> (loss [scalar], logits [M], dy1 [M, K], dW1 [N, K], db1 [N], dw2 [1, N], db2 [1])."""
+        y1, ld = _rows2d(y1, "y1")
+        _need(w1, torch.float32, "w1")
+        _need(w2, torch.float32, "w2")
+        _need(labels, torch.float32, "labels")
+        M, K = y1.shape
+        N = w1.shape[0]
+        if w1.shape != (N, K) or w2.numel() != N or labels.numel() != M:
+            raise TzkError("tower_tail_bce: shapes do not chain")
+        dev = y1.device
+        logits = torch.empty(M, dtype=torch.float32, device=dev)
+        dy1 = torch.empty((M, K), dtype=torch.float32, device=dev)
+        out = torch.empty(N * K + 2 * N + 2, dtype=torch.float32, device=dev)
+        nb = self._lib.tzk_tower_tail_bce_workspace_bytes(M, K, N)
+        ws = self._workspace("tail", nb, dev)
+        check(self._lib.tzk_tower_tail_bce(_ptr(y1), ld, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(labels), M, K, N,
+                                           _ptr(logits), _ptr(dy1), K, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+              "tzk_tower_tail_bce")
+        self.launches += 2
+        o = N * K
+        return (out[o + 2 * N + 1], logits, dy1, out[:o].view(N, K), out[o:o + N], out[o + N:o + 2 * N].view(1, N),
+                out[o + 2 * N:o + 2 * N + 1])
+
 
 @dataclass
 class ColPlan:

@@ -256,6 +256,10 @@ class RankModel(nn.Module):
 
     def loss(self, predictions: Dict[str, torch.Tensor], batch: Batch) -> Dict[str, torch.Tensor]:
         """rank_model.py:181-287: BCEWithLogitsLoss(mean) on the first label."""
+        tail = getattr(self, "_tail_loss", None)
+        if tail is not None:                 # computed together with the tower's tail (DLRM._fused_tail)
+            self._tail_loss = None
+            return {"binary_cross_entropy": tail}
         label = batch.labels[self._label_name].to(torch.float32)
         from .dense_gemm import bce_with_logits
 
@@ -342,7 +346,40 @@ class DLRM(RankModel):
         all_feat, in_map = Fn.dlrm_interaction(dense_feat, sparse, self._sparse_num, self._per_sparse_dim,
                                                with_dense=True,
                                                with_sparse=bool(self._model_config.arch_with_sparse), aligned=True)
+        fused = self._fused_tail(batch, all_feat, in_map)
+        if fused is not None:
+            return fused
         return self._output_to_prediction(self.output_mlp(self.final_mlp(all_feat, in_map)))
+
+    def _fused_tail(self, batch: Batch, all_feat: torch.Tensor, in_map):
+        """Training steps on CUDA: the last Perceptron of the final MLP, the output layer and the BCE loss as ONE kernel
+        that also produces their gradients (csrc/tzk_tower_tail.cuh; 18 launches of latency-bound work on DLRM-Criteo).
+        The loss is handed to `loss()` through `_tail_loss`.  TZK_FUSED_TAIL: not through a GPU validation pass yet — on
+        with =1 / TZK_EXPERIMENTAL=1."""
+        from .dense_gemm import tower_tail_bce, tower_tail_usable
+        from .kernels import _unvalidated_switch
+
+        self._tail_loss = None
+        layers = list(self.final_mlp.mlp)
+        if (not self.training or not torch.is_grad_enabled() or not all_feat.is_cuda or self._num_class != 1
+                or not layers or self._label_name not in batch.labels or not _unvalidated_switch("TZK_FUSED_TAIL")):
+            return None
+        last = layers[-1].perceptron
+        if not (len(last) == 2 and isinstance(last[1], nn.ReLU)):     # Linear -> ReLU only (no BN / LN / dropout)
+            return None
+        label = batch.labels[self._label_name].to(torch.float32)
+        w1, b1 = last[0].weight, last[0].bias
+        w2, b2 = self.output_mlp.weight, self.output_mlp.bias
+        x = all_feat
+        for i, layer in enumerate(layers[:-1]):
+            x = layer(x, in_map) if (i == 0 and in_map is not None) else layer(x)
+        if len(layers) == 1 and in_map is not None:
+            return None
+        if not tower_tail_usable(x, w1, w2, label):
+            return None
+        loss, logits = tower_tail_bce(x, w1, b1, w2, b2, label)
+        self._tail_loss = loss
+        return {"logits": logits, "probs": torch.sigmoid(logits)}
 
 
     def _dense_group_input(self, batch: Batch) -> Optional[torch.Tensor]:
