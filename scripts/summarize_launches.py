@@ -23,7 +23,7 @@ def group(name):
                   "fused_apply", "find_long_runs", "tile_update", "carry_combine", "zero_counters", "bucketize", "bag_grad",
                   "permute_", "col_gather", "jagged", "fm_", "dot_interact", "peer_", "small_table_update", "din_",
                   "softmax_wsum")
-    own_tower = ("small_linear", "bce_", "bias_act", "act_bwd_colsum", "colsum_final")
+    own_tower = ("small_linear", "bce_", "bias_act", "act_bwd_colsum", "colsum_final", "tower_tail")
     own_gemm = ("gemm3x_kernel", "wgrad3x_kernel", "wgrad_reduce", "split_w_kernel")
     if "DeviceRadixSort" in name:
         return "radix sort (CUB, inside tzk_fused_bwd)"
