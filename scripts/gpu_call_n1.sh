@@ -1,17 +1,15 @@
 #!/bin/bash
-# One 1-GPU validation + measurement pass (gpurun runs whatever this file says at snapshot time):
-#   gpurun --timeout 1500 -- 'bash scripts/gpu_call_n1.sh'
+# Last short 1-GPU pass of the round (3 GPU-minutes left): default-path tests first, then the headline line, then the fused
+# tail A/B if the box is still there.
 set -u
 cd "$(dirname "$0")/.."
-o=gpurun_out/c7
+o=gpurun_out/c8
 mkdir -p $o
-(time TZK_EXPERIMENTAL=1 python -m pytest tests -x -q -m gpu) > $o/pytest_experimental.txt 2>&1
-tail -4 $o/pytest_experimental.txt
-(time python -m pytest tests -x -q -m gpu) > $o/pytest_default.txt 2>&1
-tail -4 $o/pytest_default.txt
-bash scripts/ab_bench.sh "" TZK_FUSED_TAIL=1 TZK_DLRM_BOTTOM_STREAM=1 "TZK_FUSED_TAIL=1 TZK_DLRM_BOTTOM_STREAM=1" > $o/ab.txt 2>&1
-cat $o/ab.txt
-TZK_FUSED_TAIL=1 TZK_DLRM_BOTTOM_STREAM=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/launches.csv \
-    python bench.py --steps 3 --warmup 3 --ring 2 --no-cpu-baseline --no-zipf --no-extras > $o/ncu_bench.log 2>&1
-python scripts/summarize_launches.py $o/launches.csv > $o/launch_summary.txt 2>&1
-head -60 $o/launch_summary.txt | cut -c1-120
+(time timeout 100 python -m pytest tests -x -q -m gpu) > $o/pytest_default.txt 2>&1
+tail -3 $o/pytest_default.txt
+timeout 60 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-zipf --no-extras > $o/bench_default.json 2> $o/bench_default.err
+tail -c 300 $o/bench_default.json
+TZK_FUSED_TAIL=1 timeout 60 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-zipf --no-extras > $o/bench_tail.json 2> $o/bench_tail.err
+tail -c 300 $o/bench_tail.json
+(TZK_EXPERIMENTAL=1 timeout 60 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -x -q -m gpu -k "tower_tail or train_steps or graph") > $o/pytest_tail.txt 2>&1
+tail -3 $o/pytest_tail.txt
