@@ -880,7 +880,6 @@ def test_interaction_tensor_core_kernels_match_reference_and_fp64(kernels, monke
 
 
 # ---- fused tower tail: last Perceptron + Linear(N, 1) + mean BCE, forward and backward in one kernel ---------------------
-@unvalidated
 @pytest.mark.parametrize("M,K,N", [(1, 64, 32), (127, 64, 32), (1000, 13, 7), (4099, 64, 64), (65536 + 5, 64, 32), (300, 32, 16)])
 def test_tower_tail_bce_matches_torch_autograd(kernels, M, K, N):
     """tzk_tower_tail_bce against torch autograd in float64 (tzrec/modules/mlp.py Perceptron -> Linear ->
