@@ -75,7 +75,7 @@ def test_small_linear_bwd2_source_matches_numpy(tower, K, N, M, relu, pad):
     np.testing.assert_array_equal(db, db2)
 
 
-@pytest.mark.parametrize("K,N,pad", [(64, 32, 0), (13, 64, 1)])
+@pytest.mark.parametrize("K,N,pad", [(13, 64, 1)])
 def test_small_linear_dw_tiles_several_tiles_per_cta(tower, K, N, pad):
     """M > 592 x 32 rows: every CTA walks two tiles (32 rows + a short one) through both shared-memory stages."""
     M = 19500

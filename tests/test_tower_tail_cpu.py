@@ -37,7 +37,7 @@ def reference(y1, w1, b1, w2, b2, lab):
 
 
 @pytest.mark.parametrize("K,N", [(64, 32), (64, 64), (32, 16), (13, 7), (60, 33), (16, 1)])
-@pytest.mark.parametrize("M,pad", [(1, 0), (100, 0), (129, 3), (700, 0)])
+@pytest.mark.parametrize("M,pad", [(1, 0), (129, 3), (300, 0)])
 def test_tower_tail_source_matches_float64(tail, K, N, M, pad):
     rng = np.random.default_rng(K * 100 + N + M)
     y1 = np.maximum(rng.standard_normal((M, K + pad)), 0).astype(np.float32)      # (a ReLU output)
