@@ -42,8 +42,8 @@ def tower(tmp_path_factory):
     return L
 
 
-@pytest.mark.parametrize("K,N", [(13, 64), (64, 16), (64, 32), (32, 1), (64, 64), (7, 3), (16, 2), (60, 4), (64, 30), (33, 17)])
-@pytest.mark.parametrize("M,relu,pad", [(1, 1, 0), (300, 1, 0), (300, 0, 0), (77, 1, 3)])
+@pytest.mark.parametrize("K,N", [(13, 64), (64, 16), (64, 32), (32, 1), (64, 64), (7, 3), (64, 30)])
+@pytest.mark.parametrize("M,relu,pad", [(1, 1, 0), (300, 0, 0), (77, 1, 3)])
 def test_small_linear_bwd2_source_matches_numpy(tower, K, N, M, relu, pad):
     """The four DLRM tower shapes (13->64, 64->16, 64->32, 32->1), the 128-thread limit case 64x64 (NB x KB = 4 x 8) and
     odd shapes on the scalar paths; `pad` widens the leading dimensions so that rows lose their 16-B alignment."""
