@@ -515,7 +515,7 @@ def run_ours(args):
     fwd_gbs = gather_b * B / (fwd_ms * 1e-3) / 1e9
     bwd_gbs = bwd_b * B / (bwd_ms * 1e-3) / 1e9
     bwd_gbs_actual = bwd_b_actual * B / (bwd_ms * 1e-3) / 1e9
-    dominant = ("tzk_fused_bwd (linearize + radix sort + run_update / long-run kernels)" if bwd_ms > fwd_ms
+    dominant = ("tzk_fused_bwd (id half: linearize + radix sort + run lists; gradient half: fused_apply_kernel over the short-run list + long-run chunks)" if bwd_ms > fwd_ms
                 else "pooled_gather_fwd_kernel")
     ach = bwd_gbs if bwd_ms > fwd_ms else fwd_gbs
     # dram__bytes_read.sum + dram__bytes_write.sum per launch, all kernels of the dominant op, from the ncu --set full
